@@ -1,0 +1,133 @@
+/*
+ * ipp_b200.h -- C ABI of the B200 (sm_100a) GP-estimation / information-gain hot path.
+ *
+ * The reference (franfrancisco9/Multi-Robot-Informative-Path-Planning) is pure Python and has no
+ * FFI of its own; its boundary for this path is the duck-typed attribute PointSourceField.gp
+ * (an sklearn GaussianProcessRegressor, src/point_source/point_source.py:71) plus the module-level
+ * gain / selection functions in src/rrt/rrt.py.  Each entry point below names the reference
+ * call it replaces.  INTEGRATION.md shows the ctypes binding a maintainer of the reference adds.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to caller-owned memory unless the name ends in _host;
+ *     the library never allocates, frees or synchronises;
+ *   - all matrices are row-major fp64; `stream` is a cudaStream_t passed as void*;
+ *   - return 0 on success, <0 on bad argument (-1) or CUDA launch error (-2).  Numerical failure
+ *     (Gram matrix not positive definite) is reported LAPACK-style through the `info` slot of the
+ *     result block: info = k > 0 means the leading minor of order k is not positive definite
+ *     (the caller raises numpy.linalg.LinAlgError in fit, returns (-inf, 0) inside the optimiser
+ *     objective -- sklearn/gaussian_process/_gpr.py:590-593, 351-361);
+ *   - no global mutable state: re-entrant, one stream per calling thread.
+ */
+#ifndef IPP_B200_H
+#define IPP_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ABI version, bumped on any signature change. */
+int ipp_abi_version(void);
+
+/* ---- GP fit state ------------------------------------------------------------------------
+ * Buffer sizes for n observations.  out[0..9] = {NP, rows, ld, Kbuf doubles, Wbuf doubles,
+ * Tbuf doubles, vbuf doubles, offset of alpha_ in vbuf, offset of the 8-double result block in
+ * vbuf, vector slot length}.  NP = round_up(n, 64); Kbuf is (NP+64) x NP, Wbuf and Tbuf NP x NP.
+ * vbuf slots of length out[9]: 0 = x/l, 1 = y/l, 2 = (unused), 3 = back-substitution work,
+ * 4 = alpha_.  Result block: {lml, dlml/dlog c, dlml/dlog l, info, z.z, sum log diag L, -, -}. */
+int ipp_gp_layout(int n, long long* out_host);
+
+/* K = c * exp(-|x-y|^2 / (2 l^2)), n x m, leading dimension ldk.  Y == NULL: symmetric Gram of X
+ * with the diagonal set to exactly c + jitter.
+ * Replaces gp.kernel(X) / gp.kernel(X, Y): src/rrt/rrt.py:447,452 ->
+ * sklearn kernels.py:936-971 (Product), 1244-1296 (ConstantKernel), 1530-1587 (RBF). */
+int ipp_gram_rbf(const double* X, int n, const double* Y, int m, double c, double l, double jitter, double* K,
+                 long long ldk, void* stream);
+
+/* One log-marginal-likelihood (+ gradient w.r.t. log c, log l) evaluation.
+ * X: n x 2, y: n (already normalised), hyp: DEVICE {c, l, jitter}.  On return the result block
+ * in vbuf holds lml / gradient / info; Kbuf holds L (lower, row NP = z = L^-1 y), Wbuf = L^-1.
+ * Replaces GaussianProcessRegressor.log_marginal_likelihood(theta, eval_gradient=True):
+ * sklearn _gpr.py:541-656, the objective of the 11 L-BFGS-B runs of fit (_gpr.py:302-333). */
+int ipp_gp_lml_grad(const double* X, const double* y, int n, const double* hyp, double* Kbuf, double* Wbuf,
+                    double* Tbuf, double* vbuf, int with_grad, void* stream);
+
+/* Final factorisation at the chosen theta: L_ in Kbuf, W = L_^-1 in Wbuf, alpha_ = L_^-T L_^-1 y
+ * in vbuf (offset out[7]), scaled coordinates in slots 0/1, lml in the result block.
+ * Replaces sklearn _gpr.py:349-367 (kernel_(X), cholesky, cho_solve). */
+int ipp_gp_fit_final(const double* X, const double* y, int n, const double* hyp, double* Kbuf, double* Wbuf,
+                     double* Tbuf, double* vbuf, void* stream);
+
+/* ---- GP posterior --------------------------------------------------------------------------
+ * mean = y_std * (k*^T alpha) + y_mean ; std = y_std * sqrt(max(0, c - |W k*|^2)) for the flat
+ * grid indices [g_begin, g_end) of the nx x ny lattice x = linspace(x0, x1, nx),
+ * y = linspace(y0, y1, ny), index = iy * nx + ix (point_source.py:65-67,350).  Outputs are indexed
+ * from 0 (slab-local).  zpred (nullable) receives 10**mean (point_source.py:352); neg_count
+ * (nullable, int*) counts variances clamped at 0 (_gpr.py:485-491).
+ * Replaces gp.predict(r, return_std=True) on the workspace grid: point_source.py:350-351 ->
+ * sklearn _gpr.py:446-500, without materialising K_trans (G x n) or V (n x G). */
+int ipp_gp_posterior_grid(const double* Wbuf, const double* vbuf, int n, double c, double l, double y_mean,
+                          double y_std, double x0, double x1, int nx, double y0, double y1, int ny,
+                          long long g_begin, long long g_end, double* mean, double* std, double* zpred,
+                          int* neg_count, int max_ctas, void* stream);
+
+/* Same posterior at m explicit query points Q (m x 2).
+ * Replaces gp.predict(leaf_points, return_std=True): src/rrt/rrt_thread.py:375. */
+int ipp_gp_posterior_points(const double* Wbuf, const double* vbuf, int n, double c, double l, double y_mean,
+                            double y_std, const double* Q, long long m, double* mean, double* std, double* zpred,
+                            int* neg_count, int max_ctas, void* stream);
+
+/* ---- information gain / selectors ---------------------------------------------------------
+ * 0.5 * log det(I_L + beta * K K^T), K = kernel(leaf_xy (L x 2), obs_xy (na x 2)) with the PRIOR
+ * hyper-parameters (c, l).  Factorises the smaller of the L- and na-order forms (Sylvester).
+ * Buffers: Gtmp >= round_up(L,64) * round_up(na,64) doubles; Kbuf/Wbuf/vbuf sized by
+ * ipp_gp_layout(min(L, na)).  Result block slot [5] = the value, [3] = info.
+ * Replaces mutual_information_gain(K_pi, K_pio, beta_t): src/rrt/rrt.py:512-526 (and the two
+ * gp.kernel calls feeding it, rrt.py:447,452). */
+int ipp_mi_logdet(const double* leaf_xy, int L, const double* obs_xy, int na, double c, double l, double beta,
+                  double* Gtmp, double* Kbuf, double* Wbuf, double* vbuf, void* stream);
+
+/* For each of np points: number of observations strictly closer than d (`sure`), and number
+ * within a few ulp of d (`amb`, to be re-decided by the host with numpy's own norm); amb_total
+ * accumulates the sum of amb (caller zeroes it).
+ * Replaces the inner list comprehension of exploitation_penalty: rrt.py:246-252, 471-477. */
+int ipp_count_close(const double* P, int np, const double* obs, int no, double d, int* sure, int* amb, int* amb_total,
+                    void* stream);
+
+/* Phase 1 of branch scoring: per-node static terms of gain variant
+ *   0 point_source_gain_no_penalties (rrt.py:51-70; only source `closest_idx`)
+ *   1 ..._only_distance_penalty (rrt.py:72-96)   2 ..._distance_rotation_penalty (rrt.py:98-128)
+ *   3 point_source_gain_all (rrt.py:130-259; also wpen[N] = workspace/obstacle penalty of the node)
+ * sources: S x 3 rows [x, y, A] (best_estimates); ws4 = workspace_size; obstacles: n_obst x 4
+ * rows [x, y, width, height].  Includes calculate_suppression_factor (rrt.py:32-47). */
+int ipp_node_terms(int variant, const double* node_xy, int N, const double* sources, int S, int closest_idx,
+                   const double* ws4, const double* obstacles, int n_obst, double* src_gain, double* wpen,
+                   void* stream);
+
+/* Phase 2: gain of B branches.  Branch b starts at node eval_node[b] and follows parent pointers
+ * to the root as they were when node eval_time[b] was inserted: parent0[q] is the insertion-time
+ * parent (-1 = root) and (hist_off, hist_time, hist_parent) is a CSR log of later rewire events
+ * (rrt_utils.py:85-88) applied when hist_time < eval_time[b].  hist_off / eval_time may be NULL
+ * (no rewires / final snapshot).  Replaces the `while current_node.parent` walks of rrt.py:65-70,
+ * 91-96, 123-128, 254-259 as called from rig_tree_generation (rrt.py:321). */
+int ipp_branch_gain(int variant, const double* node_xy, int N, const int* parent0, const int* hist_off,
+                    const int* hist_time, const int* hist_parent, const double* src_gain, const double* wpen,
+                    const int* n_close, int agent_has_obs, int have_estimates, const double* obstacles, int n_obst,
+                    const int* eval_node, const int* eval_time, int B, double* gain_out, void* stream);
+
+/* Stage-1 selector scores ((mi - distance) - workspace) - exploitation for L leaves.
+ * Replaces the penalty loop of bias_beta_path_selection: rrt.py:460-482. */
+int ipp_leaf_penalty(const double* leaf_xy, const double* parent_xy, const int* has_parent, int L, const int* n_close,
+                     int agent_has_obs, const double* ws4, double mi, double* scores, void* stream);
+
+/* acq[i] -= 0.1 * (d - dist) / d for every path point closer than d, in path order.
+ * Replaces src/rrt/rrt_thread.py:383-387. */
+int ipp_ucb_visit_penalty(const double* leaf_xy, int L, const double* path_xy, int P, double d, double* acq,
+                          void* stream);
+
+/* np.argmax semantics (first maximum; the first NaN wins).  rrt.py:486, rrt_thread.py:389. */
+int ipp_argmax_first(const double* v, int n, double* best_val, int* best_idx, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IPP_B200_H */

@@ -1,0 +1,60 @@
+// Shared device helpers for the B200 (sm_100a) informative-path-planning kernels.
+// fp64 everywhere: the measurement Gram matrix has cond ~1e11, so
+// the tensor path is the fp64 DMMA (mma.sync m8n8k4.f64), not tcgen05.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#define IPP_OK 0
+#define IPP_ERR_ARG (-1)
+#define IPP_ERR_CUDA (-2)
+
+#define IPP_LAUNCH_CHECK()                                   \
+  do {                                                       \
+    cudaError_t e__ = cudaPeekAtLastError();                 \
+    if (e__ != cudaSuccess) return IPP_ERR_CUDA;             \
+  } while (0)
+
+namespace ipp {
+
+constexpr int BLK = 64;  // padding / panel granularity of every factor-side matrix
+
+__host__ __device__ __forceinline__ int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// D(8x8) += A(8x4,row) * B(4x8,col); lane T holds A[T/4][T%4], B[T%4][T/4], D[T/4][2*(T%4)+{0,1}]
+__device__ __forceinline__ void dmma884(double (&d)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d[0]), "+d"(d[1])
+               : "d"(a), "d"(b));
+}
+
+// 16-byte async global->shared copy; when !ok the destination is zero-filled (src-size 0).
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc, bool ok) {
+  uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  int bytes = ok ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// RBF on pre-scaled coordinates, arithmetic ordered like scipy cdist('sqeuclidean') followed by
+// np.exp(-0.5 * d) * c (sklearn kernels.py:1569-1570, 964): separate mul/add roundings, no FMA.
+__device__ __forceinline__ double sqdist_nofma(double ax, double ay, double bx, double by) {
+  double dx = __dsub_rn(ax, bx), dy = __dsub_rn(ay, by);
+  return __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+}
+__device__ __forceinline__ double rbf_scaled(double ax, double ay, double bx, double by, double c) {
+  return __dmul_rn(exp(__dmul_rn(-0.5, sqdist_nofma(ax, ay, bx, by))), c);
+}
+
+}  // namespace ipp

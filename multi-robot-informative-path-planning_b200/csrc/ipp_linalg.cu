@@ -1,0 +1,677 @@
+// GP fit side of the hot path: RBF Gram build, blocked fp64 Cholesky,
+// explicit triangular inverse W = L^-1, fused log-marginal-likelihood + gradient.
+//
+// Replaces, for the reference's GaussianProcessRegressor.fit / log_marginal_likelihood
+// (sklearn/gaussian_process/_gpr.py:233-368, 541-656, reached from
+// src/point_source/point_source.py:337,349): kernel(X, eval_gradient=True), scipy cholesky,
+// cho_solve(L, y), cho_solve(L, I) and the einsum trace.
+//
+// Data layout (all row-major fp64, device resident, owned by the caller):
+//   NP   = round_up(n, 64)         padded order; rows/cols >= n carry an identity block
+//   Kbuf = (NP + 64) x NP          Gram -> Cholesky factor in place; row NP holds y, and because
+//                                  the factorisation treats it as one more row block it becomes
+//                                  z = L^-1 y for free (augmented-row trick)
+//   Wbuf = NP x NP                 W = L^-1 (lower), upper part zero
+//   Tbuf = NP x NP                 scratch for the recursive-doubling inverse
+//   vbuf = vectors + partials      see ipp_gp_layout()
+//   hyp  = {c, l, jitter}          in DEVICE memory so a captured CUDA graph replays for any theta
+#include "ipp_gemm.cuh"
+#include "../../include/ipp_b200.h"
+
+namespace ipp {
+
+struct GpDims {
+  int n, np, rows;
+  long ld;
+  long npv;       // length of one vector slot
+  long max_tiles; // partial-sum slots
+};
+__host__ __device__ inline GpDims gp_dims(int n) {
+  GpDims d;
+  d.n = n;
+  d.np = round_up(n > 0 ? n : 1, BLK);
+  d.rows = d.np + BLK;
+  d.ld = d.np;
+  d.npv = d.np + BLK;
+  long t = d.np / BLK;
+  d.max_tiles = t * (t + 1) / 2;
+  return d;
+}
+// vbuf slots
+enum { V_XS = 0, V_YS = 1, V_Y = 2, V_W = 3, V_ALPHA = 4, V_NSLOTS = 5 };
+__host__ __device__ inline long v_partials_off(const GpDims& d) { return (long)V_NSLOTS * d.npv; }
+__host__ __device__ inline long v_result_off(const GpDims& d) { return v_partials_off(d) + 2 * d.max_tiles; }
+__host__ __device__ inline long v_total(const GpDims& d) { return v_result_off(d) + 8; }
+
+// ---------------------------------------------------------------------------------------------
+// Gram build into the padded factor buffer.  K_ij = c * exp(-0.5 * |x_i/l - x_j/l|^2), exact c on
+// the diagonal (sklearn kernels.py:1561-1565) plus jitter (_gpr.py:589); identity padding; y row.
+// Writes 8 * (NP+64) * NP bytes, reads 24 n: HBM-write bound.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gram_fit_kernel(const double* __restrict__ X, const double* __restrict__ y,
+                                                       const double* __restrict__ hyp, double* __restrict__ K,
+                                                       double* __restrict__ vbuf, GpDims d) {
+  __shared__ double sx[2][BLK], sy[2][BLK];
+  const int bj = blockIdx.x, bi = blockIdx.y;
+  const int t = threadIdx.x;
+  const double c = hyp[0], l = hyp[1], jit = hyp[2];
+  const int i0 = bi * BLK, j0 = bj * BLK;
+  if (t < 2 * BLK) {
+    int which = t / BLK, e = t % BLK;
+    int idx = (which ? j0 : i0) + e;
+    double vx = 0.0, vy = 0.0;
+    if (idx < d.n) {
+      vx = __ddiv_rn(X[2 * idx], l);
+      vy = __ddiv_rn(X[2 * idx + 1], l);
+    }
+    sx[which][e] = vx;
+    sy[which][e] = vy;
+    if (which == 1 && bi == bj && idx < d.npv) {  // diagonal blocks publish the scaled coordinates
+      vbuf[V_XS * d.npv + idx] = vx;
+      vbuf[V_YS * d.npv + idx] = vy;
+    }
+  }
+  if (bi == 0 && bj == 0 && t == 0) vbuf[v_result_off(d) + 3] = 0.0;  // info
+  __syncthreads();
+  const bool yblock = (i0 >= d.np);
+#pragma unroll 4
+  for (int e = t; e < BLK * BLK; e += 256) {
+    int r = e / BLK, cc = e % BLK;
+    int gi = i0 + r, gj = j0 + cc;
+    double v = 0.0;
+    if (yblock) {
+      if (r == 0 && gj < d.n) v = y[gj];
+    } else if (gj <= gi) {
+      if (gi < d.n) {
+        v = (gi == gj) ? __dadd_rn(c, jit) : rbf_scaled(sx[0][r], sy[0][r], sx[1][cc], sy[1][cc], c);
+      } else {
+        v = (gi == gj) ? 1.0 : 0.0;
+      }
+    }
+    K[(long)gi * d.ld + gj] = v;
+  }
+}
+
+// Public dense Gram (gp.kernel(X) / gp.kernel(X, Y): rrt.py:447,452).  out is n x m, ld >= m.
+__global__ void __launch_bounds__(256) gram_rbf_kernel(const double* __restrict__ X, int n, const double* __restrict__ Y,
+                                                       int m, double c, double l, double jitter, int symmetric,
+                                                       double* __restrict__ out, long ld) {
+  __shared__ double sx[2][BLK], sy[2][BLK];
+  const int i0 = blockIdx.y * BLK, j0 = blockIdx.x * BLK, t = threadIdx.x;
+  if (t < 2 * BLK) {
+    int which = t / BLK, e = t % BLK;
+    const double* P = which ? Y : X;
+    int lim = which ? m : n, idx = (which ? j0 : i0) + e;
+    double vx = 0.0, vy = 0.0;
+    if (idx < lim) {
+      vx = __ddiv_rn(P[2 * idx], l);
+      vy = __ddiv_rn(P[2 * idx + 1], l);
+    }
+    sx[which][e] = vx;
+    sy[which][e] = vy;
+  }
+  __syncthreads();
+  for (int e = t; e < BLK * BLK; e += 256) {
+    int r = e / BLK, cc = e % BLK;
+    int gi = i0 + r, gj = j0 + cc;
+    if (gi < n && gj < m) {
+      double v = (symmetric && gi == gj) ? __dadd_rn(c, jitter) : rbf_scaled(sx[0][r], sy[0][r], sx[1][cc], sy[1][cc], c);
+      out[(long)gi * ld + gj] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cholesky panel step k (columns [64k, 64k+64)): diagonal factor + inverse (1 CTA), then the panel
+// solve (one CTA per 64-row block below), then the tensor-core trailing update.  The inverse of
+// the diagonal block doubles as the level-0 input of the triangular inverse, so it goes to Wbuf.
+// ---------------------------------------------------------------------------------------------
+constexpr int PSTR = BLK + 1;
+constexpr size_t PANEL_SMEM = sizeof(double) * 2 * BLK * PSTR;
+
+__device__ __forceinline__ void potf2_and_invert(double* D, double* Wt, int t, int first_index, double* info,
+                                                 bool report) {
+  // D: 64x64 (stride PSTR) symmetric input, lower part used; on exit lower = L, Wt[c][i] = inv(L)[i][c]
+  for (int j = 0; j < BLK; ++j) {
+    const double piv = D[j * PSTR + j];
+    __syncthreads();
+    const double lj = sqrt(piv);
+    if (report && t == 0 && !(piv > 0.0) && info[0] == 0.0) info[0] = (double)(first_index + j + 1);
+    if (t == j) D[j * PSTR + j] = lj;
+    if (t > j && t < BLK) D[t * PSTR + j] = D[t * PSTR + j] / lj;
+    __syncthreads();
+    // trailing update of the lower triangle: D[r][c] -= D[r][j] * D[c][j], j < c <= r
+    const int m = BLK - 1 - j;  // trailing order
+    for (int e = t; e < m * m; e += 256) {
+      int r = j + 1 + e / m, cc = j + 1 + e % m;
+      if (cc <= r) D[r * PSTR + cc] -= D[r * PSTR + j] * D[cc * PSTR + j];
+    }
+    __syncthreads();
+  }
+  // inverse, 4 lanes per column
+  const int c = t >> 2, q = t & 3;
+  if (q == 0) {
+    for (int i = 0; i < c; ++i) Wt[c * PSTR + i] = 0.0;
+    Wt[c * PSTR + c] = 1.0 / D[c * PSTR + c];
+  }
+  __syncwarp();
+  for (int i = 1; i < BLK; ++i) {
+    double part = 0.0;
+    if (i > c)
+      for (int kk = c + q; kk < i; kk += 4) part += D[i * PSTR + kk] * Wt[c * PSTR + kk];
+    part += __shfl_xor_sync(0xffffffffu, part, 1);
+    part += __shfl_xor_sync(0xffffffffu, part, 2);
+    if (i > c && q == 0) Wt[c * PSTR + i] = -part / D[i * PSTR + i];
+    __syncwarp();
+  }
+  __syncthreads();
+}
+
+// Diagonal step: one CTA factors the 64x64 diagonal block of panel k in shared memory, inverts it,
+// and writes L_kk (clean lower) to A and W_kk to Winv.  A separate launch, so the blocks below
+// never observe a half-written diagonal block.
+__global__ void __launch_bounds__(256) chol_diag_kernel(double* __restrict__ A, long ld, int k, double* __restrict__ Winv,
+                                                        long ldw, double* __restrict__ info) {
+  extern __shared__ double psm[];
+  double* D = psm;
+  double* Wt = psm + BLK * PSTR;
+  const int t = threadIdx.x, j0 = BLK * k;
+  for (int e = t; e < BLK * BLK; e += 256) {
+    int r = e / BLK, cc = e % BLK;
+    D[r * PSTR + cc] = A[(long)(j0 + r) * ld + j0 + cc];
+  }
+  __syncthreads();
+  potf2_and_invert(D, Wt, t, j0, info, true);
+  for (int e = t; e < BLK * BLK; e += 256) {
+    int r = e / BLK, cc = e % BLK;
+    A[(long)(j0 + r) * ld + j0 + cc] = (cc <= r) ? D[r * PSTR + cc] : 0.0;
+    Winv[(long)(j0 + r) * ldw + j0 + cc] = Wt[cc * PSTR + r];
+  }
+}
+
+// Panel solve: A_ik <- A_ik * L_kk^-T = A_ik * W_kk^T for every 64-row block i below the diagonal.
+__global__ void __launch_bounds__(256) chol_trsm_kernel(double* __restrict__ A, long ld, int k,
+                                                        const double* __restrict__ Winv, long ldw) {
+  extern __shared__ double psm[];
+  double* Wt = psm;               // Wt[p][c] = W_kk[c][p]
+  double* Xs = psm + BLK * PSTR;  // this CTA's row block
+  const int t = threadIdx.x, j0 = BLK * k;
+  const int i0 = j0 + BLK * (blockIdx.x + 1);
+  for (int e = t; e < BLK * BLK; e += 256) {
+    int r = e / BLK, cc = e % BLK;
+    Wt[cc * PSTR + r] = Winv[(long)(j0 + r) * ldw + j0 + cc];
+    Xs[r * PSTR + cc] = A[(long)(i0 + r) * ld + j0 + cc];
+  }
+  __syncthreads();
+  // X[r][c] = sum_p Xs[r][p] * W_kk[c][p] = sum_p Xs[r][p] * Wt[p][c]   (zero for p > c)
+  const int cc = t & 63, rg = t >> 6;
+  double acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.0;
+  for (int p = 0; p < BLK; ++p) {
+    const double w = Wt[p * PSTR + cc];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] += Xs[(rg * 16 + i) * PSTR + p] * w;
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) A[(long)(i0 + rg * 16 + i) * ld + j0 + cc] = acc[i];
+}
+
+// Trailing update after panel k: C[i][j] -= sum_p P[i][p] P[j][p] for i >= j >= r0 = 64(k+1).
+template <class C>
+__global__ void __launch_bounds__(C::THREADS) chol_syrk_kernel(double* __restrict__ A, long ld, int rows_total, int np,
+                                                               int k) {
+  extern __shared__ __align__(16) double smem[];
+  const int j0 = BLK * k, r0 = j0 + BLK;
+  // decode lower-triangular tile index
+  const int b = blockIdx.x;
+  int ti = (int)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
+  while ((long)(ti + 1) * (ti + 2) / 2 <= b) ++ti;
+  while ((long)ti * (ti + 1) / 2 > b) --ti;
+  const int tj = b - ti * (ti + 1) / 2;
+  const int row0 = r0 + ti * C::BM, col0 = r0 + tj * C::BN;
+  if (row0 >= rows_total || col0 >= np) return;
+  double acc[C::MI][C::NI][2];
+  zero_acc<C>(acc);
+  auto fillA = [&](double* s, int k0) {
+    load_tile_async<C::BM, Lay::KCONT, C::THREADS>(s, A, ld, row0, k0, rows_total, j0 + BLK);
+  };
+  auto fillB = [&](double* s, int k0) {
+    load_tile_async<C::BN, Lay::KCONT, C::THREADS>(s, A, ld, col0, k0, np, j0 + BLK);
+  };
+  gemm_mainloop<C, Lay::KCONT, Lay::KCONT>(acc, smem, j0, j0 + BLK, fillA, fillB);
+  for_each_acc<C>(acc, [&](int r, int c, double v) {
+    int gr = row0 + r, gc = col0 + c;
+    if (gr < rows_total && gc < np && (gc >> 6) <= (gr >> 6)) A[(long)gr * ld + gc] -= v;
+  });
+}
+
+// ---------------------------------------------------------------------------------------------
+// W = L^-1 by recursive doubling on an aligned grid.  Level with half-size s merges
+// [r0, r1) and [r1, r2):  W21 = -W22 * (L21 * W11).   Two batched GEMM launches per level.
+//   STEP 1: T[r1+i][r0+j]  =  sum_{k >= j} L[r1+i][r0+k] * W[r0+k][r0+j]
+//   STEP 2: W[r1+i][r0+j]  = -sum_{k <= i} W[r1+i][r1+k] * T[r1+k][r0+j]
+// ---------------------------------------------------------------------------------------------
+template <class C, int STEP>
+__global__ void __launch_bounds__(C::THREADS) trtri_level_kernel(const double* __restrict__ L, long ld,
+                                                                 double* __restrict__ W, long ldw, double* __restrict__ T,
+                                                                 long ldt, int np, int s) {
+  extern __shared__ __align__(16) double smem[];
+  const int p = blockIdx.z;
+  const int r0 = 2 * p * s, r1 = r0 + s;
+  if (r1 >= np) return;
+  const int r2 = min(r0 + 2 * s, np);
+  const int row0 = r1 + blockIdx.y * C::BM, col0 = r0 + blockIdx.x * C::BN;
+  if (row0 >= r2) return;
+  double acc[C::MI][C::NI][2];
+  zero_acc<C>(acc);
+  if (STEP == 1) {
+    auto fillA = [&](double* sm, int k0) { load_tile_async<C::BM, Lay::KCONT, C::THREADS>(sm, L, ld, row0, k0, r2, r1); };
+    auto fillB = [&](double* sm, int k0) { load_tile_async<C::BN, Lay::MCONT, C::THREADS>(sm, W, ldw, col0, k0, r1, r1); };
+    gemm_mainloop<C, Lay::KCONT, Lay::MCONT>(acc, smem, col0, r1, fillA, fillB);
+    for_each_acc<C>(acc, [&](int r, int c, double v) {
+      int gr = row0 + r, gc = col0 + c;
+      if (gr < r2 && gc < r1) T[(long)gr * ldt + gc] = v;
+    });
+  } else {
+    auto fillA = [&](double* sm, int k0) { load_tile_async<C::BM, Lay::KCONT, C::THREADS>(sm, W, ldw, row0, k0, r2, r2); };
+    auto fillB = [&](double* sm, int k0) { load_tile_async<C::BN, Lay::MCONT, C::THREADS>(sm, T, ldt, col0, k0, r1, r2); };
+    gemm_mainloop<C, Lay::KCONT, Lay::MCONT>(acc, smem, r1, min(row0 + C::BM, r2), fillA, fillB);
+    for_each_acc<C>(acc, [&](int r, int c, double v) {
+      int gr = row0 + r, gc = col0 + c;
+      if (gr < r2 && gc < r1) W[(long)gr * ldw + gc] = -v;
+    });
+  }
+}
+
+// Zero the strictly-upper blocks of W before the doubling sweep (diagonal 64-blocks come from the
+// diagonal kernel, strictly-lower ones from the sweep); the posterior and trace kernels read them.
+__global__ void __launch_bounds__(256) w_clear_kernel(double* __restrict__ W, long ldw, int np) {
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  if (bi >= bj) return;  // strictly-lower blocks are fully rewritten by the sweep
+  for (int e = threadIdx.x; e < BLK * BLK; e += 256) {
+    int r = e / BLK, c = e % BLK;
+    W[(long)(bi * BLK + r) * ldw + bj * BLK + c] = 0.0;
+  }
+}
+
+// alpha = W^T z  (z = row NP of the factor buffer).  One CTA per 64 columns, 4 k-lanes per column.
+__global__ void __launch_bounds__(256) gemv_wt_kernel(const double* __restrict__ W, long ldw, const double* __restrict__ z,
+                                                      double* __restrict__ alpha, int np) {
+  __shared__ double red[4][BLK];
+  const int ci = threadIdx.x & 63, kq = threadIdx.x >> 6;
+  const int i0 = blockIdx.x * BLK, i = i0 + ci;
+  double s = 0.0;
+  for (int k = i0 + kq; k < np; k += 4) s += W[(long)k * ldw + i] * z[k];
+  red[kq][ci] = s;
+  __syncthreads();
+  if (kq == 0) alpha[i] = (red[0][ci] + red[1][ci]) + (red[2][ci] + red[3][ci]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused K^-1 trace contraction for the LML gradient (_gpr.py:629-651) without ever storing K^-1
+// or dK:  g_k = sum_ij (alpha_i alpha_j - (W^T W)_ij) * dK_ij,k  with dK_0 = K0 (no jitter) and
+// dK_1 = K0 o D2 (D2 on l-scaled coordinates, kernels.py:1577).  Lower-triangular tiles only,
+// off-diagonal tiles weighted 2.  Per-tile partials, reduced in fixed order by lml_finalize.
+// ---------------------------------------------------------------------------------------------
+template <class C>
+__global__ void __launch_bounds__(C::THREADS) lml_grad_kernel(const double* __restrict__ W, long ldw,
+                                                              const double* __restrict__ vbuf,
+                                                              const double* __restrict__ hyp, double* __restrict__ partials,
+                                                              GpDims d) {
+  extern __shared__ __align__(16) double smem[];
+  __shared__ double red[2][C::THREADS / 32];
+  const int b = blockIdx.x;
+  int ti = (int)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
+  while ((long)(ti + 1) * (ti + 2) / 2 <= b) ++ti;
+  while ((long)ti * (ti + 1) / 2 > b) --ti;
+  const int tj = b - ti * (ti + 1) / 2;
+  const int row0 = ti * C::BM, col0 = tj * C::BN;
+  double acc[C::MI][C::NI][2];
+  zero_acc<C>(acc);
+  auto fillA = [&](double* sm, int k0) { load_tile_async<C::BM, Lay::MCONT, C::THREADS>(sm, W, ldw, row0, k0, d.np, d.np); };
+  auto fillB = [&](double* sm, int k0) { load_tile_async<C::BN, Lay::MCONT, C::THREADS>(sm, W, ldw, col0, k0, d.np, d.np); };
+  gemm_mainloop<C, Lay::MCONT, Lay::MCONT>(acc, smem, row0, d.np, fillA, fillB);
+  const double c = hyp[0];
+  const double* xs = vbuf + V_XS * d.npv;
+  const double* ys = vbuf + V_YS * d.npv;
+  const double* al = vbuf + V_ALPHA * d.npv;
+  const double wgt = (ti == tj) ? 1.0 : 2.0;
+  double g0 = 0.0, g1 = 0.0;
+  for_each_acc<C>(acc, [&](int r, int cc, double v) {
+    int gi = row0 + r, gj = col0 + cc;
+    if (gi < d.n && gj < d.n) {
+      double d2 = sqdist_nofma(xs[gi], ys[gi], xs[gj], ys[gj]);
+      double kij = (gi == gj) ? c : __dmul_rn(exp(__dmul_rn(-0.5, d2)), c);
+      double tt = al[gi] * al[gj] - v;
+      g0 += tt * kij;
+      g1 += tt * (kij * d2);
+    }
+  });
+  g0 = warp_sum(g0);
+  g1 = warp_sum(g1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    red[0][warp] = g0;
+    red[1][warp] = g1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s0 = 0.0, s1 = 0.0;
+    for (int w = 0; w < C::THREADS / 32; ++w) {
+      s0 += red[0][w];
+      s1 += red[1][w];
+    }
+    partials[2 * b] = wgt * s0;
+    partials[2 * b + 1] = wgt * s1;
+  }
+}
+
+// result = {lml, dlml/dlog c, dlml/dlog l, info, z.z, sum log diag L}
+__global__ void __launch_bounds__(256) lml_finalize_kernel(const double* __restrict__ K, double* __restrict__ vbuf,
+                                                           int ntiles, int with_grad, GpDims d) {
+  __shared__ double red[4][256];
+  const int t = threadIdx.x;
+  const double* z = K + (long)d.np * d.ld;
+  double zz = 0.0, sl = 0.0, g0 = 0.0, g1 = 0.0;
+  for (int k = t; k < d.n; k += 256) {
+    zz += z[k] * z[k];
+    sl += log(K[(long)k * d.ld + k]);
+  }
+  if (with_grad) {
+    const double* part = vbuf + v_partials_off(d);
+    for (int k = t; k < ntiles; k += 256) {
+      g0 += part[2 * k];
+      g1 += part[2 * k + 1];
+    }
+  }
+  red[0][t] = zz;
+  red[1][t] = sl;
+  red[2][t] = g0;
+  red[3][t] = g1;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (t < o)
+      for (int q = 0; q < 4; ++q) red[q][t] += red[q][t + o];
+    __syncthreads();
+  }
+  if (t == 0) {
+    double* out = vbuf + v_result_off(d);
+    out[0] = -0.5 * red[0][0] - red[1][0] - 0.5 * (double)d.n * 1.8378770664093453;  // log(2 pi)
+    out[1] = 0.5 * red[2][0];
+    out[2] = 0.5 * red[3][0];
+    out[4] = red[0][0];
+    out[5] = red[1][0];
+  }
+}
+
+// Blocked backward substitution alpha = L^-T z for the final fit (_gpr.py:363-367), one launch per
+// 64-block from the bottom up.  CTA c < b updates w_c -= L[b][c]^T alpha_b; CTA b stores alpha_b.
+__global__ void __launch_bounds__(64) backsub_step_kernel(const double* __restrict__ L, long ld,
+                                                          const double* __restrict__ Winv, long ldw,
+                                                          double* __restrict__ w, double* __restrict__ alpha, int b) {
+  __shared__ double wb[BLK], ab[BLK];
+  const int t = threadIdx.x, b0 = b * BLK, c0 = blockIdx.x * BLK;
+  wb[t] = w[b0 + t];
+  __syncthreads();
+  double s = 0.0;
+  for (int k = t; k < BLK; ++k) s += Winv[(long)(b0 + k) * ldw + b0 + t] * wb[k];  // (W_bb^T w_b)[t]
+  ab[t] = s;
+  __syncthreads();
+  if ((int)blockIdx.x == b) {
+    alpha[b0 + t] = s;
+  } else {
+    double u = 0.0;
+#pragma unroll 8
+    for (int k = 0; k < BLK; ++k) u += L[(long)(b0 + k) * ld + c0 + t] * ab[k];
+    w[c0 + t] -= u;
+  }
+}
+
+__global__ void copy_row_kernel(const double* __restrict__ src, double* __restrict__ dst, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host-side launch sequences
+// ---------------------------------------------------------------------------------------------
+template <class K>
+static cudaError_t opt_in_smem(K kernel, size_t bytes) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+static bool use_small_tiles(int np) { return np <= 1536; }
+
+template <class C>
+static int chol_inplace(double* Kb, double* Wb, double* info, const GpDims& d, cudaStream_t st) {
+  constexpr size_t SM = gemm_smem_bytes<C, Lay::KCONT, Lay::KCONT>();
+  if (opt_in_smem(chol_diag_kernel, PANEL_SMEM) != cudaSuccess) return IPP_ERR_CUDA;
+  if (opt_in_smem(chol_trsm_kernel, PANEL_SMEM) != cudaSuccess) return IPP_ERR_CUDA;
+  if (opt_in_smem(chol_syrk_kernel<C>, SM) != cudaSuccess) return IPP_ERR_CUDA;
+  const int nb = d.np / BLK;
+  for (int k = 0; k < nb; ++k) {
+    const int blocks_below = d.rows / BLK - k - 1;
+    chol_diag_kernel<<<1, 256, PANEL_SMEM, st>>>(Kb, d.ld, k, Wb, d.ld, info);
+    chol_trsm_kernel<<<blocks_below, 256, PANEL_SMEM, st>>>(Kb, d.ld, k, Wb, d.ld);
+    const int rem = d.rows - BLK * (k + 1);
+    const int T = (rem + C::BM - 1) / C::BM;
+    if (k + 1 < nb) chol_syrk_kernel<C><<<T * (T + 1) / 2, C::THREADS, SM, st>>>(Kb, d.ld, d.rows, d.np, k);
+  }
+  return IPP_OK;
+}
+
+template <class C>
+static int trtri_inplace(const double* Kb, double* Wb, double* Tb, const GpDims& d, cudaStream_t st) {
+  constexpr size_t SM = gemm_smem_bytes<C, Lay::KCONT, Lay::MCONT>();
+  if (opt_in_smem(trtri_level_kernel<C, 1>, SM) != cudaSuccess) return IPP_ERR_CUDA;
+  if (opt_in_smem(trtri_level_kernel<C, 2>, SM) != cudaSuccess) return IPP_ERR_CUDA;
+  const int nb = d.np / BLK;
+  w_clear_kernel<<<dim3(nb, nb), 256, 0, st>>>(Wb, d.ld, d.np);
+  for (int s = BLK; s < d.np; s *= 2) {
+    const int pairs = (d.np + 2 * s - 1) / (2 * s);
+    dim3 grid((s + C::BN - 1) / C::BN, (s + C::BM - 1) / C::BM, pairs);
+    trtri_level_kernel<C, 1><<<grid, C::THREADS, SM, st>>>(Kb, d.ld, Wb, d.ld, Tb, d.ld, d.np, s);
+    trtri_level_kernel<C, 2><<<grid, C::THREADS, SM, st>>>(Kb, d.ld, Wb, d.ld, Tb, d.ld, d.np, s);
+  }
+  return IPP_OK;
+}
+
+template <class C>
+static int lml_grad_launch(const double* Wb, double* vbuf, const double* hyp, const GpDims& d, int* ntiles,
+                           cudaStream_t st) {
+  constexpr size_t SM = gemm_smem_bytes<C, Lay::MCONT, Lay::MCONT>();
+  if (opt_in_smem(lml_grad_kernel<C>, SM) != cudaSuccess) return IPP_ERR_CUDA;
+  const int T = (d.np + C::BM - 1) / C::BM;
+  *ntiles = T * (T + 1) / 2;
+  lml_grad_kernel<C><<<*ntiles, C::THREADS, SM, st>>>(Wb, d.ld, vbuf, hyp, vbuf + v_partials_off(d), d);
+  return IPP_OK;
+}
+
+static int gp_factor(const double* X, const double* y, int n, const double* hyp, double* Kb, double* Wb, double* Tb,
+                     double* vbuf, bool invert, cudaStream_t st) {
+  if (n <= 0 || !X || !y || !hyp || !Kb || !Wb || !vbuf) return IPP_ERR_ARG;
+  const GpDims d = gp_dims(n);
+  gram_fit_kernel<<<dim3(d.np / BLK, d.rows / BLK), 256, 0, st>>>(X, y, hyp, Kb, vbuf, d);
+  double* info = vbuf + v_result_off(d) + 3;
+  int rc = use_small_tiles(d.np) ? chol_inplace<Cfg64>(Kb, Wb, info, d, st) : chol_inplace<Cfg128>(Kb, Wb, info, d, st);
+  if (rc != IPP_OK) return rc;
+  if (invert) {
+    if (!Tb) return IPP_ERR_ARG;
+    rc = use_small_tiles(d.np) ? trtri_inplace<Cfg64>(Kb, Wb, Tb, d, st) : trtri_inplace<Cfg128>(Kb, Wb, Tb, d, st);
+    if (rc != IPP_OK) return rc;
+  }
+  IPP_LAUNCH_CHECK();
+  return IPP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Mutual-information term of the stage-1 selector (rrt.py:512-526):
+//   0.5 * log det(I_L + beta * K_pio K_pio^T),  K_pio = prior kernel(leaves, agent observations).
+// By Sylvester's identity the determinant equals det(I_na + beta * K_pio^T K_pio), so the smaller of
+// the two orders is factorised.  The reference evaluates it L times with identical arguments and
+// builds the unused L x L matrix K_pi (rrt.py:447,457-459); here it is one SYRK + one Cholesky.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gram_cross_padded_kernel(const double* __restrict__ X, int n,
+                                                                const double* __restrict__ Y, int m, double c, double l,
+                                                                double* __restrict__ out, long ld) {
+  __shared__ double sx[2][BLK], sy[2][BLK];
+  const int i0 = blockIdx.y * BLK, j0 = blockIdx.x * BLK, t = threadIdx.x;
+  if (t < 2 * BLK) {
+    int which = t / BLK, e = t % BLK;
+    const double* P = which ? Y : X;
+    int lim = which ? m : n, idx = (which ? j0 : i0) + e;
+    double vx = 0.0, vy = 0.0;
+    if (idx < lim) {
+      vx = __ddiv_rn(P[2 * idx], l);
+      vy = __ddiv_rn(P[2 * idx + 1], l);
+    }
+    sx[which][e] = vx;
+    sy[which][e] = vy;
+  }
+  __syncthreads();
+  for (int e = t; e < BLK * BLK; e += 256) {
+    int r = e / BLK, cc = e % BLK;
+    int gi = i0 + r, gj = j0 + cc;
+    out[(long)gi * ld + gj] = (gi < n && gj < m) ? rbf_scaled(sx[0][r], sy[0][r], sx[1][cc], sy[1][cc], c) : 0.0;
+  }
+}
+
+template <class C, bool TRANS>
+__global__ void __launch_bounds__(C::THREADS) eye_plus_syrk_kernel(const double* __restrict__ M, long ldm, int rows_m,
+                                                                   int cols_m, double beta, double* __restrict__ G,
+                                                                   GpDims d) {
+  extern __shared__ __align__(16) double smem[];
+  const int b = blockIdx.x;
+  int ti = (int)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
+  while ((long)(ti + 1) * (ti + 2) / 2 <= b) ++ti;
+  while ((long)ti * (ti + 1) / 2 > b) --ti;
+  const int tj = b - ti * (ti + 1) / 2;
+  const int row0 = ti * C::BM, col0 = tj * C::BN;
+  double acc[C::MI][C::NI][2];
+  zero_acc<C>(acc);
+  if (!TRANS) {
+    auto fillA = [&](double* sm, int k0) { load_tile_async<C::BM, Lay::KCONT, C::THREADS>(sm, M, ldm, row0, k0, rows_m, cols_m); };
+    auto fillB = [&](double* sm, int k0) { load_tile_async<C::BN, Lay::KCONT, C::THREADS>(sm, M, ldm, col0, k0, rows_m, cols_m); };
+    gemm_mainloop<C, Lay::KCONT, Lay::KCONT>(acc, smem, 0, cols_m, fillA, fillB);
+  } else {
+    auto fillA = [&](double* sm, int k0) { load_tile_async<C::BM, Lay::MCONT, C::THREADS>(sm, M, ldm, row0, k0, cols_m, rows_m); };
+    auto fillB = [&](double* sm, int k0) { load_tile_async<C::BN, Lay::MCONT, C::THREADS>(sm, M, ldm, col0, k0, cols_m, rows_m); };
+    gemm_mainloop<C, Lay::MCONT, Lay::MCONT>(acc, smem, 0, rows_m, fillA, fillB);
+  }
+  for_each_acc<C>(acc, [&](int r, int c, double v) {
+    int gi = row0 + r, gj = col0 + c;
+    if (gi < d.np && gj < d.np && gj <= gi) G[(long)gi * d.ld + gj] = ((gi == gj) ? 1.0 : 0.0) + beta * v;
+  });
+}
+
+template <class C>
+static int mi_build(const double* Gx, long ldg, int Lp, int nap, bool trans, double beta, double* Kb, const GpDims& d,
+                    cudaStream_t st) {
+  const int T = (d.np + C::BM - 1) / C::BM;
+  if (!trans) {
+    constexpr size_t SM = gemm_smem_bytes<C, Lay::KCONT, Lay::KCONT>();
+    if (opt_in_smem(eye_plus_syrk_kernel<C, false>, SM) != cudaSuccess) return IPP_ERR_CUDA;
+    eye_plus_syrk_kernel<C, false><<<T * (T + 1) / 2, C::THREADS, SM, st>>>(Gx, ldg, Lp, nap, beta, Kb, d);
+  } else {
+    constexpr size_t SM = gemm_smem_bytes<C, Lay::MCONT, Lay::MCONT>();
+    if (opt_in_smem(eye_plus_syrk_kernel<C, true>, SM) != cudaSuccess) return IPP_ERR_CUDA;
+    eye_plus_syrk_kernel<C, true><<<T * (T + 1) / 2, C::THREADS, SM, st>>>(Gx, ldg, Lp, nap, beta, Kb, d);
+  }
+  return IPP_OK;
+}
+
+}  // namespace ipp
+
+using namespace ipp;
+
+extern "C" {
+
+int ipp_gp_layout(int n, long long* out) {
+  if (n <= 0 || !out) return IPP_ERR_ARG;
+  const GpDims d = gp_dims(n);
+  out[0] = d.np;
+  out[1] = d.rows;
+  out[2] = d.ld;
+  out[3] = (long long)d.rows * d.ld;  // Kbuf doubles
+  out[4] = (long long)d.np * d.ld;    // Wbuf doubles
+  out[5] = (long long)d.np * d.ld;    // Tbuf doubles
+  out[6] = v_total(d);                // vbuf doubles
+  out[7] = V_ALPHA * d.npv;           // offset of alpha in vbuf
+  out[8] = v_result_off(d);           // offset of the 8-double result block
+  out[9] = d.npv;                     // vector slot length (slot order: xs, ys, y, w, alpha)
+  return IPP_OK;
+}
+
+int ipp_gram_rbf(const double* X, int n, const double* Y, int m, double c, double l, double jitter, double* K,
+                 long long ldk, void* stream) {
+  if (!X || n <= 0 || !K || !(l > 0.0)) return IPP_ERR_ARG;
+  const int symmetric = (Y == nullptr);
+  if (symmetric) {
+    Y = X;
+    m = n;
+  }
+  if (m <= 0 || ldk < m) return IPP_ERR_ARG;
+  dim3 grid((m + BLK - 1) / BLK, (n + BLK - 1) / BLK);
+  gram_rbf_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, n, Y, m, c, l, jitter, symmetric, K, (long)ldk);
+  IPP_LAUNCH_CHECK();
+  return IPP_OK;
+}
+
+int ipp_gp_lml_grad(const double* X, const double* y, int n, const double* hyp, double* Kbuf, double* Wbuf,
+                    double* Tbuf, double* vbuf, int with_grad, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = gp_factor(X, y, n, hyp, Kbuf, Wbuf, Tbuf, vbuf, with_grad != 0, st);
+  if (rc != IPP_OK) return rc;
+  const GpDims d = gp_dims(n);
+  int ntiles = 0;
+  if (with_grad) {
+    gemv_wt_kernel<<<d.np / BLK, 256, 0, st>>>(Wbuf, d.ld, Kbuf + (long)d.np * d.ld, vbuf + V_ALPHA * d.npv, d.np);
+    rc = use_small_tiles(d.np) ? lml_grad_launch<Cfg64>(Wbuf, vbuf, hyp, d, &ntiles, st)
+                               : lml_grad_launch<Cfg128>(Wbuf, vbuf, hyp, d, &ntiles, st);
+    if (rc != IPP_OK) return rc;
+  }
+  lml_finalize_kernel<<<1, 256, 0, st>>>(Kbuf, vbuf, ntiles, with_grad, d);
+  IPP_LAUNCH_CHECK();
+  return IPP_OK;
+}
+
+int ipp_gp_fit_final(const double* X, const double* y, int n, const double* hyp, double* Kbuf, double* Wbuf,
+                     double* Tbuf, double* vbuf, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = gp_factor(X, y, n, hyp, Kbuf, Wbuf, Tbuf, vbuf, true, st);
+  if (rc != IPP_OK) return rc;
+  const GpDims d = gp_dims(n);
+  double* w = vbuf + V_W * d.npv;
+  double* alpha = vbuf + V_ALPHA * d.npv;
+  copy_row_kernel<<<(d.np + 255) / 256, 256, 0, st>>>(Kbuf + (long)d.np * d.ld, w, d.np);
+  for (int b = d.np / BLK - 1; b >= 0; --b)
+    backsub_step_kernel<<<b + 1, 64, 0, st>>>(Kbuf, d.ld, Wbuf, d.ld, w, alpha, b);
+  lml_finalize_kernel<<<1, 256, 0, st>>>(Kbuf, vbuf, 0, 0, d);
+  IPP_LAUNCH_CHECK();
+  return IPP_OK;
+}
+
+/* result block (vbuf + out[8] of ipp_gp_layout(min(L, na))): [5] = 0.5 * log det(I + beta K K^T), [3] = info */
+int ipp_mi_logdet(const double* leaf_xy, int L, const double* obs_xy, int na, double c, double l, double beta,
+                  double* Gtmp, double* Kbuf, double* Wbuf, double* vbuf, void* stream) {
+  if (L <= 0 || na <= 0 || !leaf_xy || !obs_xy || !Gtmp || !Kbuf || !Wbuf || !vbuf || !(l > 0.0)) return IPP_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Lp = round_up(L, BLK), nap = round_up(na, BLK);
+  const bool trans = na < L;
+  const GpDims d = gp_dims(trans ? na : L);
+  gram_cross_padded_kernel<<<dim3(nap / BLK, Lp / BLK), 256, 0, st>>>(leaf_xy, L, obs_xy, na, c, l, Gtmp, nap);
+  if (cudaMemsetAsync(Kbuf + (long)d.np * d.ld, 0, sizeof(double) * BLK * d.ld, st) != cudaSuccess) return IPP_ERR_CUDA;
+  if (cudaMemsetAsync(vbuf + v_result_off(d), 0, sizeof(double) * 8, st) != cudaSuccess) return IPP_ERR_CUDA;
+  int rc = use_small_tiles(d.np) ? mi_build<Cfg64>(Gtmp, nap, Lp, nap, trans, beta, Kbuf, d, st)
+                                 : mi_build<Cfg128>(Gtmp, nap, Lp, nap, trans, beta, Kbuf, d, st);
+  if (rc != IPP_OK) return rc;
+  double* info = vbuf + v_result_off(d) + 3;
+  rc = use_small_tiles(d.np) ? chol_inplace<Cfg64>(Kbuf, Wbuf, info, d, st) : chol_inplace<Cfg128>(Kbuf, Wbuf, info, d, st);
+  if (rc != IPP_OK) return rc;
+  lml_finalize_kernel<<<1, 256, 0, st>>>(Kbuf, vbuf, 0, 0, d);
+  IPP_LAUNCH_CHECK();
+  return IPP_OK;
+}
+
+}  // extern "C"

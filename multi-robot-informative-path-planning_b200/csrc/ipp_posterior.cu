@@ -1,0 +1,238 @@
+// GP posterior mean / standard deviation over the workspace lattice or explicit query points
+// (SURVEY.md §8a rows G5, G6).  Replaces gp.predict(X, return_std=True)
+// (sklearn/gaussian_process/_gpr.py:446-500 reached from src/point_source/point_source.py:351 and
+// src/rrt/rrt_thread.py:375).
+//
+// Formulation: sigma^2(q) = c - |W k*(q)|^2 with W = L^-1 explicit (the K^-1 quadratic
+// form is numerically unusable at cond 1e11; the per-tile TRSM panel does not fit on chip).  So the
+// kernel is a lower-triangular fp64 GEMM  V = W (NP x NP) * K*^T (NP x 128 queries)  on the DMMA
+// pipe whose B operand is never read from memory -- each k-slab of K* is generated from coordinates
+// straight into shared memory -- and whose C tile is never written: the epilogue squares and
+// column-reduces it in registers.  The mean k*^T alpha rides along in the generation pass.
+//
+// Per 128-query tile: flops = 128 * (NP^2 + ...) fp64, HBM bytes = 16/query out (+16 in for points);
+// W is streamed from L2 (all CTAs walk it in the same order).  Bound: fp64 tensor pipe.
+#include "ipp_gemm.cuh"
+#include "../../include/ipp_b200.h"
+
+namespace ipp {
+
+struct PostArgs {
+  const double* W;
+  long ldw;
+  const double* xs;  // observation coordinates / l, zero padded to NP
+  const double* ys;
+  const double* alpha;
+  int n, np;
+  double c, l, y_mean, y_std;
+  const double* Q;  // explicit points (m x 2) or nullptr
+  double x0, x1, xstep, y0, y1, ystep;
+  int nx, ny;
+  long g_begin, g_end;
+  double* mean;
+  double* std;
+  double* zpred;
+  int* neg_count;
+};
+
+using PC = Cfg128;
+constexpr int QT = PC::BN;  // queries per tile
+
+template <bool GRID>
+__global__ void __launch_bounds__(PC::THREADS, 1) posterior_kernel(PostArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  __shared__ double sq[2][QT];            // scaled query coordinates
+  __shared__ double red[PC::WARPS_M][QT]; // column sums of squares per warp row
+  __shared__ double mred[2][QT];          // mean partials per generation half
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int wm = warp / PC::WARPS_N, wn = warp % PC::WARPS_N;
+  const int g = lane >> 2, tg = lane & 3;
+  const int p = t & (QT - 1), h = t >> 7;  // generation role: query p, k-half h
+  const long total = a.g_end - a.g_begin;
+  const long ntiles = (total + QT - 1) / QT;
+
+  for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    if (t < QT) {
+      long gi = a.g_begin + tile * QT + t;
+      double qx = 0.0, qy = 0.0;
+      if (gi < a.g_end) {
+        if (GRID) {
+          int ix = (int)(gi % a.nx), iy = (int)(gi / a.nx);
+          // np.linspace: i * step + start with separate roundings, endpoint forced
+          qx = (ix == a.nx - 1 && a.nx > 1) ? a.x1 : __dadd_rn(__dmul_rn((double)ix, a.xstep), a.x0);
+          qy = (iy == a.ny - 1 && a.ny > 1) ? a.y1 : __dadd_rn(__dmul_rn((double)iy, a.ystep), a.y0);
+        } else {
+          qx = a.Q[2 * gi];
+          qy = a.Q[2 * gi + 1];
+        }
+      }
+      sq[0][t] = __ddiv_rn(qx, a.l);
+      sq[1][t] = __ddiv_rn(qy, a.l);
+    }
+    __syncthreads();
+    const double qx = sq[0][p], qy = sq[1][p];
+    double csq[PC::NI][2];
+#pragma unroll
+    for (int ni = 0; ni < PC::NI; ++ni) csq[ni][0] = csq[ni][1] = 0.0;
+    double mean_part = 0.0;
+
+    for (int row0 = 0; row0 < a.np; row0 += PC::BM) {
+      double acc[PC::MI][PC::NI][2];
+      zero_acc<PC>(acc);
+      const int kend = min(row0 + PC::BM, a.np);
+      auto fillA = [&](double* s, int k0) {
+        load_tile_async<PC::BM, Lay::KCONT, PC::THREADS>(s, a.W, a.ldw, row0, k0, a.np, a.np);
+      };
+      auto fillB = [&](double* s, int k0) {
+        const bool first_visit = (k0 >= row0);  // slab k0 is generated for every row block >= k0/BM
+        double v[8];
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const int j = k0 + h * 8 + kk;
+          double val = 0.0;
+          if (j < a.n) {
+            val = rbf_scaled(qx, qy, __ldg(a.xs + j), __ldg(a.ys + j), a.c);
+            if (first_visit) mean_part += __ldg(a.alpha + j) * val;
+          }
+          v[kk] = val;
+        }
+        double2* dst = reinterpret_cast<double2*>(s + p * KPAD + h * 8);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) dst[kk] = make_double2(v[2 * kk], v[2 * kk + 1]);
+      };
+      gemm_mainloop<PC, Lay::KCONT, Lay::KCONT>(acc, smem, 0, kend, fillA, fillB);
+#pragma unroll
+      for (int mi = 0; mi < PC::MI; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < PC::NI; ++ni) {
+          csq[ni][0] += acc[mi][ni][0] * acc[mi][ni][0];
+          csq[ni][1] += acc[mi][ni][1] * acc[mi][ni][1];
+        }
+    }
+    // column reduction: over the 8 row-lanes g of the warp, then over the WARPS_M warp rows
+#pragma unroll
+    for (int ni = 0; ni < PC::NI; ++ni)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        double v = csq[ni][e];
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        if (g == 0) red[wm][wn * PC::WTN + ni * 8 + tg * 2 + e] = v;
+      }
+    mred[h][p] = mean_part;
+    __syncthreads();
+    if (t < QT) {
+      long gi = a.g_begin + tile * QT + t;
+      if (gi < a.g_end) {
+        double ss = 0.0;
+#pragma unroll
+        for (int w = 0; w < PC::WARPS_M; ++w) ss += red[w][t];
+        double mu = a.y_std * (mred[0][t] + mred[1][t]) + a.y_mean;
+        double var = a.c - ss;
+        if (var < 0.0) {
+          var = 0.0;
+          if (a.neg_count) atomicAdd(a.neg_count, 1);
+        }
+        long o = gi - a.g_begin;
+        a.mean[o] = mu;
+        a.std[o] = sqrt(var * (a.y_std * a.y_std));
+        if (a.zpred) a.zpred[o] = pow(10.0, mu);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+static int launch_posterior(PostArgs& a, bool grid, int max_ctas, cudaStream_t st) {
+  constexpr size_t SM = gemm_smem_bytes<PC, Lay::KCONT, Lay::KCONT>();
+  const long total = a.g_end - a.g_begin;
+  if (total <= 0) return IPP_OK;
+  const long ntiles = (total + QT - 1) / QT;
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) != cudaSuccess) return IPP_ERR_CUDA;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return IPP_ERR_CUDA;
+  int ctas = (int)(ntiles < (long)sms ? ntiles : (long)sms);  // persistent: one CTA per SM
+  if (max_ctas > 0 && ctas > max_ctas) ctas = max_ctas;
+  if (grid) {
+    if (cudaFuncSetAttribute(posterior_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM) != cudaSuccess)
+      return IPP_ERR_CUDA;
+    posterior_kernel<true><<<ctas, PC::THREADS, SM, st>>>(a);
+  } else {
+    if (cudaFuncSetAttribute(posterior_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM) != cudaSuccess)
+      return IPP_ERR_CUDA;
+    posterior_kernel<false><<<ctas, PC::THREADS, SM, st>>>(a);
+  }
+  IPP_LAUNCH_CHECK();
+  return IPP_OK;
+}
+
+static void fill_state(PostArgs& a, const double* Wbuf, const double* vbuf, int n, double c, double l, double y_mean,
+                       double y_std) {
+  const int np = round_up(n, BLK);
+  const long npv = np + BLK;
+  a.W = Wbuf;
+  a.ldw = np;
+  a.xs = vbuf;
+  a.ys = vbuf + npv;
+  a.alpha = vbuf + 4 * npv;
+  a.n = n;
+  a.np = np;
+  a.c = c;
+  a.l = l;
+  a.y_mean = y_mean;
+  a.y_std = y_std;
+}
+
+}  // namespace ipp
+
+using namespace ipp;
+
+extern "C" {
+
+int ipp_gp_posterior_grid(const double* Wbuf, const double* vbuf, int n, double c, double l, double y_mean,
+                          double y_std, double x0, double x1, int nx, double y0, double y1, int ny,
+                          long long g_begin, long long g_end, double* mean, double* std, double* zpred,
+                          int* neg_count, int max_ctas, void* stream) {
+  if (!Wbuf || !vbuf || n <= 0 || nx <= 0 || ny <= 0 || !mean || !std || !(l > 0.0)) return IPP_ERR_ARG;
+  if (g_begin < 0 || g_end > (long long)nx * ny || g_begin > g_end) return IPP_ERR_ARG;
+  PostArgs a{};
+  fill_state(a, Wbuf, vbuf, n, c, l, y_mean, y_std);
+  a.Q = nullptr;
+  a.x0 = x0;
+  a.x1 = x1;
+  a.y0 = y0;
+  a.y1 = y1;
+  a.nx = nx;
+  a.ny = ny;
+  a.xstep = nx > 1 ? (x1 - x0) / (double)(nx - 1) : 0.0;
+  a.ystep = ny > 1 ? (y1 - y0) / (double)(ny - 1) : 0.0;
+  a.g_begin = g_begin;
+  a.g_end = g_end;
+  a.mean = mean;
+  a.std = std;
+  a.zpred = zpred;
+  a.neg_count = neg_count;
+  return launch_posterior(a, true, max_ctas, (cudaStream_t)stream);
+}
+
+int ipp_gp_posterior_points(const double* Wbuf, const double* vbuf, int n, double c, double l, double y_mean,
+                            double y_std, const double* Q, long long m, double* mean, double* std, double* zpred,
+                            int* neg_count, int max_ctas, void* stream) {
+  if (!Wbuf || !vbuf || n <= 0 || !Q || m < 0 || !mean || !std || !(l > 0.0)) return IPP_ERR_ARG;
+  PostArgs a{};
+  fill_state(a, Wbuf, vbuf, n, c, l, y_mean, y_std);
+  a.Q = Q;
+  a.nx = a.ny = 1;
+  a.g_begin = 0;
+  a.g_end = m;
+  a.mean = mean;
+  a.std = std;
+  a.zpred = zpred;
+  a.neg_count = neg_count;
+  return launch_posterior(a, false, max_ctas, (cudaStream_t)stream);
+}
+
+int ipp_abi_version(void) { return 1; }
+
+}  // extern "C"

@@ -1,0 +1,404 @@
+"""GaussianProcessRegressor-compatible estimator whose arithmetic runs on a B200.
+
+Mirrors the slice of scikit-learn's API that the reference touches through ``PointSourceField.gp``
+(src/point_source/point_source.py:71,337,349,351; src/rrt/rrt.py:447,452; src/rrt/rrt_thread.py:375):
+
+    gp = GaussianProcessRegressor(kernel=C(1.0, (1e-3, 50)) * RBF(1.0, (1e-2, 50)),
+                                  n_restarts_optimizer=10, normalize_y=True)
+    gp.fit(X, y); gp.predict(X, return_std=True); gp.kernel(X[, Y]); gp.kernel_; gp.alpha_; gp.L_
+    gp.log_marginal_likelihood(theta, eval_gradient=True); gp.log_marginal_likelihood_value_
+
+Host code keeps everything that is sequential or consumes the RNG (y normalisation bookkeeping, the
+``n_restarts_optimizer`` uniform draws from the global ``np.random`` stream, scipy's L-BFGS-B
+driver); every dense operation (Gram, Cholesky, triangular inverse, LML + gradient, posterior) is
+a hand-written sm_100a kernel behind the C ABI of include/ipp_b200.h.  torch only owns the device
+buffers and the stream.  No CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import warnings
+
+import numpy as np
+from scipy.optimize import minimize
+
+from . import _lib
+
+__all__ = ["ConstantRBFKernel", "ConstantKernel", "RBF", "GaussianProcessRegressor"]
+
+
+# ------------------------------------------------------------------------------------------
+# kernel objects (host-side description of c * RBF(l); the arithmetic is ipp_gram_rbf)
+# ------------------------------------------------------------------------------------------
+class _Factor:
+    def __init__(self, value, bounds):
+        self.value = float(value)
+        self.bounds = bounds
+
+    def __mul__(self, other):
+        if isinstance(self, ConstantKernel) and isinstance(other, RBF):
+            return ConstantRBFKernel(self.value, other.value, self.bounds, other.bounds)
+        if isinstance(self, RBF) and isinstance(other, ConstantKernel):
+            return ConstantRBFKernel(other.value, self.value, other.bounds, self.bounds)
+        raise TypeError("only ConstantKernel * RBF is on the accelerated path")
+
+
+class ConstantKernel(_Factor):
+    """sklearn.gaussian_process.kernels.ConstantKernel look-alike (factor of the product only)."""
+
+    def __init__(self, constant_value=1.0, constant_value_bounds=(1e-5, 1e5)):
+        super().__init__(constant_value, constant_value_bounds)
+
+
+class RBF(_Factor):
+    """sklearn.gaussian_process.kernels.RBF look-alike (isotropic, factor of the product only)."""
+
+    def __init__(self, length_scale=1.0, length_scale_bounds=(1e-5, 1e5)):
+        super().__init__(length_scale, length_scale_bounds)
+
+
+class ConstantRBFKernel:
+    """``ConstantKernel(c, c_bounds) * RBF(l, l_bounds)`` -- the only kernel the reference builds
+    (point_source.py:82-87).  theta = log([c, l]) (sklearn kernels.py:291-312)."""
+
+    requires_vector_input = True
+    n_dims = 2
+
+    def __init__(self, constant_value=1.0, length_scale=1.0, constant_value_bounds=(1e-3, 50.0),
+                 length_scale_bounds=(1e-2, 50.0)):
+        self.constant_value = float(constant_value)
+        self.length_scale = float(length_scale)
+        self.constant_value_bounds = constant_value_bounds
+        self.length_scale_bounds = length_scale_bounds
+
+    # -- sklearn Kernel protocol -----------------------------------------------------------
+    @property
+    def theta(self):
+        return np.log(np.array([self.constant_value, self.length_scale], dtype=float))
+
+    @theta.setter
+    def theta(self, theta):
+        theta = np.asarray(theta, dtype=float)
+        self.constant_value = float(np.exp(theta[0]))
+        self.length_scale = float(np.exp(theta[1]))
+
+    @property
+    def bounds(self):
+        return np.log(np.array([self.constant_value_bounds, self.length_scale_bounds], dtype=float))
+
+    def clone_with_theta(self, theta):
+        k = ConstantRBFKernel(self.constant_value, self.length_scale, self.constant_value_bounds,
+                              self.length_scale_bounds)
+        k.theta = theta
+        return k
+
+    def clone(self):
+        return ConstantRBFKernel(self.constant_value, self.length_scale, self.constant_value_bounds,
+                                 self.length_scale_bounds)
+
+    def diag(self, X):
+        return np.full(len(np.asarray(X)), self.constant_value, dtype=float)
+
+    def is_stationary(self):
+        return True
+
+    def __call__(self, X, Y=None, eval_gradient=False):
+        """Dense Gram matrix on the device, returned as a host ndarray (rrt.py:447,452 consume it
+        with numpy).  Use :func:`gram_device` to keep it resident."""
+        if eval_gradient:
+            raise NotImplementedError("the fused LML kernel never materialises dK; use "
+                                      "GaussianProcessRegressor.log_marginal_likelihood")
+        return gram_device(X, Y, self.constant_value, self.length_scale).cpu().numpy()
+
+    def __repr__(self):
+        # same text sklearn prints for C(c) * RBF(l)
+        return "{0:.3g}**2 * RBF(length_scale={1:.3g})".format(np.sqrt(self.constant_value), self.length_scale)
+
+
+def _as_points(X):
+    A = np.ascontiguousarray(np.asarray(X, dtype=np.float64))
+    if A.ndim == 1:
+        A = A.reshape(-1, 2)
+    if A.ndim != 2 or A.shape[1] != 2:
+        raise ValueError(f"expected an (n, 2) array of waypoints, got shape {A.shape}")
+    return A
+
+
+def gram_device(X, Y, c, l, jitter=0.0):
+    """K(X, Y) as a device-resident torch tensor (n x m, fp64)."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    Xd = torch.from_numpy(_as_points(X)).cuda()
+    n = Xd.shape[0]
+    if Y is None:
+        Yd, m = None, n
+    else:
+        Yd = torch.from_numpy(_as_points(Y)).cuda()
+        m = Yd.shape[0]
+    out = torch.empty((n, m), dtype=torch.float64, device="cuda")
+    if n and m:
+        _lib.check(lib.ipp_gram_rbf(_lib.ptr(Xd), n, _lib.ptr(Yd), m, float(c), float(l), float(jitter),
+                                    _lib.ptr(out), m, _lib.stream_ptr()), "ipp_gram_rbf")
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# device workspace of one fitted GP
+# ------------------------------------------------------------------------------------------
+class _Workspace:
+    """Caller-owned device buffers of the C ABI (ipp_gp_layout), reused while NP does not change."""
+
+    def __init__(self):
+        self.np_ = -1
+
+    def ensure(self, n):
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        lay = (C.c_longlong * 10)()
+        _lib.check(lib.ipp_gp_layout(int(n), lay), "ipp_gp_layout")
+        self.layout = [int(v) for v in lay]
+        NP = self.layout[0]
+        if NP != self.np_:
+            dev = torch.device("cuda")
+            self.K = torch.empty(self.layout[3], dtype=torch.float64, device=dev)
+            self.W = torch.empty(self.layout[4], dtype=torch.float64, device=dev)
+            self.T = torch.empty(self.layout[5], dtype=torch.float64, device=dev)
+            self.v = torch.zeros(self.layout[6], dtype=torch.float64, device=dev)
+            self.hyp = torch.empty(3, dtype=torch.float64, device=dev)
+            self.hyp_host = torch.empty(3, dtype=torch.float64).pin_memory()
+            self.res_host = torch.empty(8, dtype=torch.float64).pin_memory()
+            self.np_ = NP
+        return self
+
+    @property
+    def result(self):
+        off = self.layout[8]
+        return self.v[off:off + 8]
+
+
+class GaussianProcessRegressor:
+    """Drop-in for sklearn.gaussian_process.GaussianProcessRegressor on the reference's call sites."""
+
+    def __init__(self, kernel=None, *, alpha=1e-10, optimizer="fmin_l_bfgs_b", n_restarts_optimizer=0,
+                 normalize_y=False, copy_X_train=True, n_targets=None, random_state=None):
+        if kernel is None:
+            kernel = ConstantRBFKernel(1.0, 1.0, "fixed", "fixed")
+        if not isinstance(kernel, ConstantRBFKernel):
+            raise TypeError("the B200 path implements ConstantKernel * RBF (point_source.py:86)")
+        if np.iterable(alpha):
+            raise TypeError("per-sample alpha is not used by the reference and is not implemented")
+        self.kernel = kernel
+        self.alpha = float(alpha)
+        self.optimizer = optimizer
+        self.n_restarts_optimizer = int(n_restarts_optimizer)
+        self.normalize_y = normalize_y
+        self.copy_X_train = copy_X_train
+        self.n_targets = n_targets
+        self.random_state = random_state
+        self._ws = _Workspace()
+        self.n_lml_evals_ = 0
+
+    # -- helpers ------------------------------------------------------------------------------
+    def _rng_state(self):
+        rs = self.random_state
+        if rs is None or rs is np.random:
+            return np.random.mtrand._rand  # sklearn.utils.check_random_state(None): the global stream
+        if isinstance(rs, (int, np.integer)):
+            return np.random.RandomState(rs)
+        return rs
+
+    def _upload_training(self, X, yn):
+        torch = _lib.require_cuda()
+        self._Xd = torch.from_numpy(X).cuda()
+        self._yd = torch.from_numpy(np.ascontiguousarray(yn)).cuda()
+
+    def _eval_device(self, c, l, with_grad, final=False):
+        """Launch one LML (+gradient) evaluation or the final factorisation; returns the 8-double
+        result block on the host."""
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        ws = self._ws
+        n = self.X_train_.shape[0]
+        ws.hyp_host[0] = c
+        ws.hyp_host[1] = l
+        ws.hyp_host[2] = self.alpha
+        ws.hyp.copy_(ws.hyp_host, non_blocking=True)
+        st = _lib.stream_ptr()
+        if final:
+            rc = lib.ipp_gp_fit_final(_lib.ptr(self._Xd), _lib.ptr(self._yd), n, _lib.ptr(ws.hyp), _lib.ptr(ws.K),
+                                      _lib.ptr(ws.W), _lib.ptr(ws.T), _lib.ptr(ws.v), st)
+            _lib.check(rc, "ipp_gp_fit_final")
+        else:
+            rc = lib.ipp_gp_lml_grad(_lib.ptr(self._Xd), _lib.ptr(self._yd), n, _lib.ptr(ws.hyp), _lib.ptr(ws.K),
+                                     _lib.ptr(ws.W), _lib.ptr(ws.T), _lib.ptr(ws.v), 1 if with_grad else 0, st)
+            _lib.check(rc, "ipp_gp_lml_grad")
+        ws.res_host.copy_(ws.result, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return ws.res_host.numpy().copy()
+
+    # -- sklearn API ---------------------------------------------------------------------------
+    def log_marginal_likelihood(self, theta=None, eval_gradient=False, clone_kernel=True):
+        """_gpr.py:541-656.  A failed Cholesky gives (-inf, zeros) like the reference (:590-593)."""
+        if theta is None:
+            if eval_gradient:
+                raise ValueError("Gradient can only be evaluated for theta!=None")
+            return self.log_marginal_likelihood_value_
+        theta = np.asarray(theta, dtype=float)
+        if not clone_kernel:
+            self.kernel_.theta = theta
+        c, l = float(np.exp(theta[0])), float(np.exp(theta[1]))
+        res = self._eval_device(c, l, eval_gradient)
+        self.n_lml_evals_ += 1
+        if res[3] != 0.0 or not np.isfinite(res[0]):
+            return (-np.inf, np.zeros_like(theta)) if eval_gradient else -np.inf
+        if eval_gradient:
+            return float(res[0]), np.array([res[1], res[2]])
+        return float(res[0])
+
+    def _constrained_optimization(self, obj_func, initial_theta, bounds):
+        """_gpr.py:658-676: scipy L-BFGS-B with its defaults, or a user callable."""
+        if self.optimizer == "fmin_l_bfgs_b":
+            res = minimize(obj_func, initial_theta, method="L-BFGS-B", jac=True, bounds=bounds)
+            return res.x, res.fun
+        if callable(self.optimizer):
+            return self.optimizer(obj_func, initial_theta, bounds=bounds)
+        raise ValueError(f"Unknown optimizer {self.optimizer}.")
+
+    def fit(self, X, y):
+        """_gpr.py:233-368 (single-output)."""
+        X = _as_points(X)
+        y = np.asarray(y, dtype=np.float64).reshape(-1)
+        if X.shape[0] != y.shape[0]:
+            raise ValueError(f"X and y have inconsistent lengths: {X.shape[0]} != {y.shape[0]}")
+        if X.shape[0] == 0:
+            raise ValueError("Found array with 0 sample(s) while a minimum of 1 is required.")
+        self.kernel_ = self.kernel.clone()
+        self._rng = self._rng_state()
+        if self.normalize_y:
+            self._y_train_mean = np.mean(y, axis=0)
+            std = np.std(y, axis=0)
+            self._y_train_std = 1.0 if std < 10 * np.finfo(float).eps else std  # _handle_zeros_in_scale
+            y = (y - self._y_train_mean) / self._y_train_std
+        else:
+            self._y_train_mean = 0.0
+            self._y_train_std = 1.0
+        self.X_train_ = np.copy(X) if self.copy_X_train else X
+        self.y_train_ = np.copy(y) if self.copy_X_train else y
+        self._ws.ensure(X.shape[0])
+        self._upload_training(self.X_train_, self.y_train_)
+        self._L_host = None
+        self._alpha_host = None
+
+        fixed = isinstance(self.kernel_.constant_value_bounds, str) or isinstance(self.kernel_.length_scale_bounds, str)
+        if self.optimizer is not None and not fixed:
+            def obj_func(theta, eval_gradient=True):
+                if eval_gradient:
+                    lml, grad = self.log_marginal_likelihood(theta, eval_gradient=True, clone_kernel=False)
+                    return -lml, -grad
+                return -self.log_marginal_likelihood(theta, clone_kernel=False)
+
+            bounds = self.kernel_.bounds
+            optima = [self._constrained_optimization(obj_func, self.kernel_.theta, bounds)]
+            if self.n_restarts_optimizer > 0:
+                if not np.isfinite(bounds).all():
+                    raise ValueError("Multiple optimizer restarts (n_restarts_optimizer>0) requires that all "
+                                     "bounds are finite.")
+                for _ in range(self.n_restarts_optimizer):
+                    theta_initial = self._rng.uniform(bounds[:, 0], bounds[:, 1])
+                    optima.append(self._constrained_optimization(obj_func, theta_initial, bounds))
+            lml_values = [o[1] for o in optima]
+            self.kernel_.theta = optima[int(np.argmin(lml_values))][0]
+            self.log_marginal_likelihood_value_ = -np.min(lml_values)
+            self._finalize(set_lml=False)
+        else:
+            self._finalize(set_lml=True)
+        return self
+
+    def _finalize(self, set_lml):
+        res = self._eval_device(self.kernel_.constant_value, self.kernel_.length_scale, False, final=True)
+        if res[3] != 0.0:
+            raise np.linalg.LinAlgError(
+                f"The kernel, {self.kernel_}, is not returning a positive definite matrix. Try gradually "
+                "increasing the 'alpha' parameter of your GaussianProcessRegressor estimator.",
+                f"{int(res[3])}-th leading minor of the array is not positive definite")
+        if set_lml:
+            self.log_marginal_likelihood_value_ = float(res[0])
+        self._fitted_c = self.kernel_.constant_value
+        self._fitted_l = self.kernel_.length_scale
+
+    # -- fitted attributes (lazy device -> host) ------------------------------------------------
+    @property
+    def L_(self):
+        if self._L_host is None:
+            n = self.X_train_.shape[0]
+            NP, ld = self._ws.layout[0], self._ws.layout[2]
+            self._L_host = self._ws.K[: NP * ld].view(NP, ld)[:n, :n].cpu().numpy()
+        return self._L_host
+
+    @property
+    def alpha_(self):
+        if self._alpha_host is None:
+            n = self.X_train_.shape[0]
+            off = self._ws.layout[7]
+            self._alpha_host = self._ws.v[off:off + n].cpu().numpy()
+        return self._alpha_host
+
+    # -- prediction -----------------------------------------------------------------------------
+    def _posterior_args(self):
+        return (_lib.ptr(self._ws.W), _lib.ptr(self._ws.v), int(self.X_train_.shape[0]), float(self._fitted_c),
+                float(self._fitted_l), float(self._y_train_mean), float(self._y_train_std))
+
+    def _warn_negative(self, counter):
+        if int(counter.item()) > 0:
+            warnings.warn("Predicted variances smaller than 0. Setting those variances to 0.")
+
+    def predict(self, X, return_std=False, return_cov=False):
+        """_gpr.py:370-500.  Unfitted: GP prior (mean 0, std sqrt(c))."""
+        if return_cov:
+            raise NotImplementedError("return_cov is not used by the reference and is not implemented")
+        Xq = _as_points(X)
+        if not hasattr(self, "X_train_"):
+            mean = np.zeros(Xq.shape[0])
+            return (mean, np.sqrt(self.kernel.diag(Xq))) if return_std else mean
+        torch = _lib.require_cuda()
+        mean_d, std_d, _ = self.predict_points_device(torch.from_numpy(Xq).cuda())
+        mean = mean_d.cpu().numpy()
+        return (mean, std_d.cpu().numpy()) if return_std else mean
+
+    def predict_points_device(self, Qd, want_zpred=False):
+        """Posterior at explicit device-resident points (m x 2); returns device tensors."""
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        m = int(Qd.shape[0])
+        mean = torch.empty(m, dtype=torch.float64, device="cuda")
+        std = torch.empty(m, dtype=torch.float64, device="cuda")
+        zp = torch.empty(m, dtype=torch.float64, device="cuda") if want_zpred else None
+        neg = torch.zeros(1, dtype=torch.int32, device="cuda")
+        if m:
+            rc = lib.ipp_gp_posterior_points(*self._posterior_args(), _lib.ptr(Qd), m, _lib.ptr(mean), _lib.ptr(std),
+                                             _lib.ptr(zp), _lib.ptr(neg), 0, _lib.stream_ptr())
+            _lib.check(rc, "ipp_gp_posterior_points")
+            self._warn_negative(neg)
+        return mean, std, zp
+
+    def predict_grid_device(self, x0, x1, nx, y0, y1, ny, g_begin=0, g_end=None, want_zpred=True, out=None):
+        """Fused posterior over flat lattice indices [g_begin, g_end) (index = iy * nx + ix).
+        Returns device tensors (mean, std, zpred) of length g_end - g_begin."""
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        g_end = nx * ny if g_end is None else g_end
+        m = int(g_end - g_begin)
+        if out is None:
+            mean = torch.empty(m, dtype=torch.float64, device="cuda")
+            std = torch.empty(m, dtype=torch.float64, device="cuda")
+            zp = torch.empty(m, dtype=torch.float64, device="cuda") if want_zpred else None
+        else:
+            mean, std, zp = out
+        neg = torch.zeros(1, dtype=torch.int32, device="cuda")
+        if m:
+            rc = lib.ipp_gp_posterior_grid(*self._posterior_args(), float(x0), float(x1), int(nx), float(y0), float(y1),
+                                           int(ny), int(g_begin), int(g_end), _lib.ptr(mean), _lib.ptr(std),
+                                           _lib.ptr(zp), _lib.ptr(neg), 0, _lib.stream_ptr())
+            _lib.check(rc, "ipp_gp_posterior_grid")
+            self._neg_counter = neg
+        return mean, std, zp
