@@ -189,32 +189,39 @@ __global__ void __launch_bounds__(256) chol_diag_kernel(double* __restrict__ A, 
   }
 }
 
-// Panel solve: A_ik <- A_ik * L_kk^-T = A_ik * W_kk^T for every 64-row block i below the diagonal.
-__global__ void __launch_bounds__(256) chol_trsm_kernel(double* __restrict__ A, long ld, int k,
-                                                        const double* __restrict__ Winv, long ldw) {
+// Panel solve: A_ik <- A_ik * L_kk^-T for every 64-row block i below the diagonal, by forward
+// substitution (backward stable, unlike multiplying by the explicit inverse: at cond(K) ~ 1e11 the
+// diagonal blocks reach cond ~ 1e5 and the inverse route cost 5 digits of L).  One thread per row,
+// the row lives in registers, L_kk is broadcast from shared memory.
+constexpr size_t TRSM_SMEM = sizeof(double) * 2 * BLK * PSTR;
+__global__ void __launch_bounds__(BLK) chol_trsm_kernel(double* __restrict__ A, long ld, int k) {
   extern __shared__ double psm[];
-  double* Wt = psm;               // Wt[p][c] = W_kk[c][p]
-  double* Xs = psm + BLK * PSTR;  // this CTA's row block
+  double* Ls = psm;
+  double* Xs = psm + BLK * PSTR;
   const int t = threadIdx.x, j0 = BLK * k;
   const int i0 = j0 + BLK * (blockIdx.x + 1);
-  for (int e = t; e < BLK * BLK; e += 256) {
+  for (int e = t; e < BLK * BLK; e += BLK) {
     int r = e / BLK, cc = e % BLK;
-    Wt[cc * PSTR + r] = Winv[(long)(j0 + r) * ldw + j0 + cc];
+    Ls[r * PSTR + cc] = A[(long)(j0 + r) * ld + j0 + cc];
     Xs[r * PSTR + cc] = A[(long)(i0 + r) * ld + j0 + cc];
   }
   __syncthreads();
-  // X[r][c] = sum_p Xs[r][p] * W_kk[c][p] = sum_p Xs[r][p] * Wt[p][c]   (zero for p > c)
-  const int cc = t & 63, rg = t >> 6;
-  double acc[16];
+  double x[BLK];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) acc[i] = 0.0;
-  for (int p = 0; p < BLK; ++p) {
-    const double w = Wt[p * PSTR + cc];
+  for (int c = 0; c < BLK; ++c) x[c] = Xs[t * PSTR + c];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) acc[i] += Xs[(rg * 16 + i) * PSTR + p] * w;
+  for (int c = 0; c < BLK; ++c) {
+    x[c] = x[c] / Ls[c * PSTR + c];
+#pragma unroll
+    for (int q = c + 1; q < BLK; ++q) x[q] -= x[c] * Ls[q * PSTR + c];
   }
 #pragma unroll
-  for (int i = 0; i < 16; ++i) A[(long)(i0 + rg * 16 + i) * ld + j0 + cc] = acc[i];
+  for (int c = 0; c < BLK; ++c) Xs[t * PSTR + c] = x[c];
+  __syncthreads();
+  for (int e = t; e < BLK * BLK; e += BLK) {
+    int r = e / BLK, cc = e % BLK;
+    A[(long)(i0 + r) * ld + j0 + cc] = Xs[r * PSTR + cc];
+  }
 }
 
 // Trailing update after panel k: C[i][j] -= sum_p P[i][p] P[j][p] for i >= j >= r0 = 64(k+1).
@@ -406,20 +413,26 @@ __global__ void __launch_bounds__(256) lml_finalize_kernel(const double* __restr
 }
 
 // Blocked backward substitution alpha = L^-T z for the final fit (_gpr.py:363-367), one launch per
-// 64-block from the bottom up.  CTA c < b updates w_c -= L[b][c]^T alpha_b; CTA b stores alpha_b.
-__global__ void __launch_bounds__(64) backsub_step_kernel(const double* __restrict__ L, long ld,
-                                                          const double* __restrict__ Winv, long ldw,
-                                                          double* __restrict__ w, double* __restrict__ alpha, int b) {
-  __shared__ double wb[BLK], ab[BLK];
+// 64-block from the bottom up.  Every CTA solves the 64x64 diagonal system by substitution (redundantly,
+// it is tiny); CTA c < b then updates w_c -= L[b][c]^T alpha_b and CTA b stores alpha_b.
+__global__ void __launch_bounds__(BLK) backsub_step_kernel(const double* __restrict__ L, long ld, double* __restrict__ w,
+                                                           double* __restrict__ alpha, int b) {
+  __shared__ double Ls[BLK * PSTR];
+  __shared__ double ab[BLK];
   const int t = threadIdx.x, b0 = b * BLK, c0 = blockIdx.x * BLK;
-  wb[t] = w[b0 + t];
+  for (int e = t; e < BLK * BLK; e += BLK) {
+    int r = e / BLK, cc = e % BLK;
+    Ls[r * PSTR + cc] = L[(long)(b0 + r) * ld + b0 + cc];
+  }
+  double wt = w[b0 + t];
   __syncthreads();
-  double s = 0.0;
-  for (int k = t; k < BLK; ++k) s += Winv[(long)(b0 + k) * ldw + b0 + t] * wb[k];  // (W_bb^T w_b)[t]
-  ab[t] = s;
-  __syncthreads();
+  for (int k = BLK - 1; k >= 0; --k) {
+    if (t == k) ab[k] = wt / Ls[k * PSTR + k];
+    __syncthreads();
+    if (t < k) wt -= Ls[k * PSTR + t] * ab[k];
+  }
   if ((int)blockIdx.x == b) {
-    alpha[b0 + t] = s;
+    alpha[b0 + t] = ab[t];
   } else {
     double u = 0.0;
 #pragma unroll 8
@@ -447,13 +460,13 @@ template <class C>
 static int chol_inplace(double* Kb, double* Wb, double* info, const GpDims& d, cudaStream_t st) {
   constexpr size_t SM = gemm_smem_bytes<C, Lay::KCONT, Lay::KCONT>();
   if (opt_in_smem(chol_diag_kernel, PANEL_SMEM) != cudaSuccess) return IPP_ERR_CUDA;
-  if (opt_in_smem(chol_trsm_kernel, PANEL_SMEM) != cudaSuccess) return IPP_ERR_CUDA;
+  if (opt_in_smem(chol_trsm_kernel, TRSM_SMEM) != cudaSuccess) return IPP_ERR_CUDA;
   if (opt_in_smem(chol_syrk_kernel<C>, SM) != cudaSuccess) return IPP_ERR_CUDA;
   const int nb = d.np / BLK;
   for (int k = 0; k < nb; ++k) {
     const int blocks_below = d.rows / BLK - k - 1;
     chol_diag_kernel<<<1, 256, PANEL_SMEM, st>>>(Kb, d.ld, k, Wb, d.ld, info);
-    chol_trsm_kernel<<<blocks_below, 256, PANEL_SMEM, st>>>(Kb, d.ld, k, Wb, d.ld);
+    chol_trsm_kernel<<<blocks_below, BLK, TRSM_SMEM, st>>>(Kb, d.ld, k);
     const int rem = d.rows - BLK * (k + 1);
     const int T = (rem + C::BM - 1) / C::BM;
     if (k + 1 < nb) chol_syrk_kernel<C><<<T * (T + 1) / 2, C::THREADS, SM, st>>>(Kb, d.ld, d.rows, d.np, k);
@@ -646,7 +659,7 @@ int ipp_gp_fit_final(const double* X, const double* y, int n, const double* hyp,
   double* alpha = vbuf + V_ALPHA * d.npv;
   copy_row_kernel<<<(d.np + 255) / 256, 256, 0, st>>>(Kbuf + (long)d.np * d.ld, w, d.np);
   for (int b = d.np / BLK - 1; b >= 0; --b)
-    backsub_step_kernel<<<b + 1, 64, 0, st>>>(Kbuf, d.ld, Wbuf, d.ld, w, alpha, b);
+    backsub_step_kernel<<<b + 1, BLK, 0, st>>>(Kbuf, d.ld, w, alpha, b);
   lml_finalize_kernel<<<1, 256, 0, st>>>(Kbuf, vbuf, 0, 0, d);
   IPP_LAUNCH_CHECK();
   return IPP_OK;

@@ -38,7 +38,7 @@ for n, W in [(40, 10), (64, 10), (131, 40), (500, 20), (1000, 30), (2000, 50)]:
         rel_L = np.abs(L - st["L"]).max() / np.abs(st["L"]).max()
         rel_a = np.abs(a - st["alpha"]).max() / np.abs(st["alpha"]).max()
         q = np.random.RandomState(1).uniform(0, W, (3000, 2))
-        q[:200] = X[:200] + 1e-3
+        kq = min(200, n); q[:kq] = X[:kq] + 1e-3
         mg, sg = gp.predict(q, return_std=True)
         mo, so, _ = O.predict(st, q)
         res[f"c{c0}_l{l0}"] = dict(lml_rel=abs(lml_g - lml_o) / abs(lml_o), lml=lml_o, grad_g=list(grad_g), grad_o=list(grad_o),

@@ -1,0 +1,19 @@
+"""Small fixed workload for ncu: one fit_final + LML evals + one grid posterior.  Args: n W G n_lml"""
+import os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from mripp_b200 import gp as G
+n, W, Gx, n_lml = (int(a) for a in sys.argv[1:5])
+rng = np.random.RandomState(0)
+X = rng.uniform(0, W, (n, 2)); X[-n // 5:] = X[:n // 5]
+y = np.sin(X[:, 0] / 3) + 0.1 * X[:, 1] + 1e-3 * rng.randn(n)
+gp = G.GaussianProcessRegressor(kernel=G.ConstantRBFKernel(1.0, 2.0), optimizer=None, normalize_y=True).fit(X, y)
+th = np.log([1.0, 2.0])
+for _ in range(n_lml):
+    gp.log_marginal_likelihood(th, eval_gradient=True)
+if Gx:
+    gp.predict_grid_device(0, W, Gx, 0, W, Gx)
+torch.cuda.synchronize()
+print("ok")
