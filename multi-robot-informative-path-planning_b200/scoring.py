@@ -1,0 +1,232 @@
+"""Device-side scoring of RRT candidates: the batched replacement of the reference's per-node Python
+gain functions and selector penalty loops (src/rrt/rrt.py:32-259, 438-526; rrt_thread.py:371-401).
+
+`GpuScorer` is the product implementation (C ABI -> sm_100a kernels).  The strategy classes only
+talk to the small interface below, which is also what the CPU tests implement with the oracle to
+check the host logic without a GPU (a test seam, not a fallback: the product constructs GpuScorer
+and GpuScorer raises without CUDA).
+
+    tree_information(variant, tree, ctx)                 -> float64[N]   node.information for every node
+    leaf_scores(leaf_xy, parent_xy, has_parent, ctx, ..) -> (scores float64[L], mi float)
+    ucb_acquisition(gp, leaf_xy, visited_xy, beta, d)    -> float64[L]
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+
+VARIANT_NO_PENALTIES, VARIANT_DISTANCE, VARIANT_DISTANCE_ROTATION, VARIANT_ALL = 0, 1, 2, 3
+
+
+@dataclass
+class ScoreContext:
+    """What the gain functions / selectors read from the strategy object."""
+    best_estimates: np.ndarray  # (S, 3) rows [x, y, A], S may be 0
+    last_point: Optional[np.ndarray]  # agents_full_path[agent][-1] (variant 0 only)
+    agents_obs_wp: Sequence[Sequence[np.ndarray]]  # observations per agent
+    agent_idx: int
+    d_wp: float
+    workspace: Sequence[float]
+    obstacles: List[dict] = field(default_factory=list)
+
+    def estimates(self):
+        return np.ascontiguousarray(np.asarray(self.best_estimates, dtype=np.float64).reshape(-1, 3))
+
+    def all_obs(self):
+        rows = [np.asarray(o, dtype=np.float64).reshape(-1, 2) for o in self.agents_obs_wp if len(o) > 0]
+        return np.ascontiguousarray(np.vstack(rows)) if rows else np.zeros((0, 2))
+
+    def agent_has_obs(self):
+        return len(self.agents_obs_wp[self.agent_idx]) > 0
+
+    def obstacle_rows(self):
+        rows = [[o["x"], o["y"], o["width"], o["height"]] for o in self.obstacles if o.get("type") == "rectangle"]
+        return np.ascontiguousarray(np.asarray(rows, dtype=np.float64).reshape(-1, 4))
+
+    def closest_estimate_index(self):
+        """rrt.py:57: first minimum of the distance from the agent's last path point."""
+        est = self.estimates()
+        if est.shape[0] == 0 or self.last_point is None:
+            return 0
+        lp = self.last_point
+        d = [np.linalg.norm([lp[0] - s[0], lp[1] - s[1]]) for s in est]
+        return int(np.argmin(d))
+
+
+def resolve_close_counts(points, obs, d, sure, amb):
+    """Host re-decision for the points the device flagged as having knife-edge pairs (|dist - d|
+    within a few ulp).  The whole count of such a point is redone: pairs clearly inside / outside are
+    counted vectorised, pairs near the edge with numpy's own scalar norm, so the `< d` outcome is the
+    one the reference computes (rrt.py:250,475)."""
+    counts = sure.astype(np.int64).copy()
+    for i in np.nonzero(amb)[0]:
+        p = points[i]
+        dd = obs - p
+        r = np.sqrt(dd[:, 0] * dd[:, 0] + dd[:, 1] * dd[:, 1])
+        edge = np.abs(r - d) <= 1e-12 * d
+        n = int(np.count_nonzero((r < d) & ~edge))
+        for j in np.nonzero(edge)[0]:
+            if np.linalg.norm(p - obs[j]) < d:
+                n += 1
+        counts[i] = n
+    return counts
+
+
+class GpuScorer:
+    """All scoring through libipp_b200.so on the current CUDA device."""
+
+    def __init__(self):
+        self.torch = _lib.require_cuda()
+        self.lib = _lib.load()
+        self.launches = 0
+
+    # -- helpers ---------------------------------------------------------------------------------
+    def _dev(self, a, dtype=None):
+        t = self.torch.from_numpy(np.ascontiguousarray(a))
+        return t.cuda(non_blocking=True)
+
+    def close_counts(self, points, obs, d):
+        """#observations closer than d to each point (exploitation penalty input)."""
+        torch, lib = self.torch, self.lib
+        P = points.shape[0]
+        if P == 0 or obs.shape[0] == 0:
+            return np.zeros(P, dtype=np.int64), None
+        Pd, Od = self._dev(points), self._dev(obs)
+        sure = torch.empty(P, dtype=torch.int32, device="cuda")
+        amb = torch.empty(P, dtype=torch.int32, device="cuda")
+        tot = torch.zeros(1, dtype=torch.int32, device="cuda")
+        _lib.check(lib.ipp_count_close(_lib.ptr(Pd), P, _lib.ptr(Od), obs.shape[0], float(d), _lib.ptr(sure), _lib.ptr(amb),
+                                       _lib.ptr(tot), _lib.stream_ptr()), "ipp_count_close")
+        self.launches += 1
+        if int(tot.item()) == 0:
+            return None, sure  # device-resident, nothing ambiguous
+        counts = resolve_close_counts(points, obs, d, sure.cpu().numpy(), amb.cpu().numpy())
+        return counts, None
+
+    # -- I1-I5 + T: node.information for the whole tree ----------------------------------------------
+    def tree_information(self, variant, tree, ctx: ScoreContext):
+        torch, lib = self.torch, self.lib
+        N = tree.n
+        if N == 0:
+            return np.zeros(0)
+        est = ctx.estimates()
+        S = est.shape[0]
+        pts = tree.points()
+        node_xy = self._dev(pts)
+        parent0 = self._dev(tree.parent0[:N].astype(np.int32))
+        hoff, htime, hpar = tree.history_csr()
+        hoff_d = self._dev(hoff) if htime.size else None
+        htime_d = self._dev(htime) if htime.size else None
+        hpar_d = self._dev(hpar) if htime.size else None
+        src_d = self._dev(est) if S else None
+        ws_d = self._dev(np.asarray(ctx.workspace, dtype=np.float64))
+        ob = ctx.obstacle_rows()
+        ob_d = self._dev(ob) if ob.shape[0] else None
+        src_gain = torch.empty(N, dtype=torch.float64, device="cuda")
+        wpen = torch.empty(N, dtype=torch.float64, device="cuda") if variant == VARIANT_ALL else None
+        st = _lib.stream_ptr()
+        closest = ctx.closest_estimate_index() if (variant == VARIANT_NO_PENALTIES and S) else 0
+        _lib.check(lib.ipp_node_terms(variant, _lib.ptr(node_xy), N, _lib.ptr(src_d), S, closest, _lib.ptr(ws_d),
+                                      _lib.ptr(ob_d), ob.shape[0], _lib.ptr(src_gain), _lib.ptr(wpen), st), "ipp_node_terms")
+        self.launches += 1
+        has_obs = 1 if ctx.agent_has_obs() else 0
+        nclose_d = None
+        if variant == VARIANT_ALL and has_obs and S:
+            counts, dev_counts = self.close_counts(pts, ctx.all_obs(), ctx.d_wp)
+            nclose_d = dev_counts if dev_counts is not None else self._dev(counts.astype(np.int32))
+        eval_node = torch.arange(N, dtype=torch.int32, device="cuda")
+        out = torch.empty(N, dtype=torch.float64, device="cuda")
+        _lib.check(lib.ipp_branch_gain(variant, _lib.ptr(node_xy), N, _lib.ptr(parent0), _lib.ptr(hoff_d), _lib.ptr(htime_d),
+                                       _lib.ptr(hpar_d), _lib.ptr(src_gain), _lib.ptr(wpen), _lib.ptr(nclose_d), has_obs,
+                                       1 if S else 0, _lib.ptr(ob_d), ob.shape[0], _lib.ptr(eval_node), _lib.ptr(eval_node),
+                                       N, _lib.ptr(out), st), "ipp_branch_gain")
+        self.launches += 1
+        info = out.cpu().numpy()
+        info[0] = 0.0  # the root is never scored (InformativeTreeNode.information = 0, rrt_utils.py:35)
+        return info
+
+    # -- I6 + I7: stage-1 selector ---------------------------------------------------------------------
+    def mutual_information(self, leaf_xy, agent_obs, c, l, beta):
+        """0.5 * log(det(I + beta K K^T)) with numpy.linalg.det's overflow semantics (rrt.py:525-526:
+        det = exp(logdet) overflows to inf above log(DBL_MAX))."""
+        torch, lib = self.torch, self.lib
+        L, na = leaf_xy.shape[0], agent_obs.shape[0]
+        if na == 0:
+            return 0
+        m = min(L, na)
+        lay = (C.c_longlong * 10)()
+        _lib.check(lib.ipp_gp_layout(m, lay), "ipp_gp_layout")
+        lay = [int(v) for v in lay]
+        r64 = lambda v: (v + 63) // 64 * 64
+        G = torch.empty(r64(L) * r64(na), dtype=torch.float64, device="cuda")
+        Kb = torch.empty(lay[3], dtype=torch.float64, device="cuda")
+        Wb = torch.empty(lay[4], dtype=torch.float64, device="cuda")
+        vb = torch.zeros(lay[6], dtype=torch.float64, device="cuda")
+        A, B = self._dev(leaf_xy), self._dev(agent_obs)
+        _lib.check(lib.ipp_mi_logdet(_lib.ptr(A), L, _lib.ptr(B), na, float(c), float(l), float(beta), _lib.ptr(G),
+                                     _lib.ptr(Kb), _lib.ptr(Wb), _lib.ptr(vb), _lib.stream_ptr()), "ipp_mi_logdet")
+        self.launches += 1
+        res = vb[lay[8]:lay[8] + 8].cpu().numpy()
+        if res[3] != 0.0:
+            return float("nan")
+        logdet = 2.0 * float(res[5])
+        with np.errstate(over="ignore"):
+            return 0.5 * np.log(np.exp(np.float64(logdet)))
+
+    def leaf_scores(self, leaf_xy, parent_xy, has_parent, ctx: ScoreContext, beta, kernel_c, kernel_l):
+        torch, lib = self.torch, self.lib
+        L = leaf_xy.shape[0]
+        agent_obs = np.asarray(ctx.agents_obs_wp[ctx.agent_idx], dtype=np.float64).reshape(-1, 2)
+        mi = self.mutual_information(leaf_xy, agent_obs, kernel_c, kernel_l, beta)
+        has_obs = 1 if ctx.agent_has_obs() else 0
+        nclose_d = None
+        if has_obs:
+            counts, dev_counts = self.close_counts(leaf_xy, ctx.all_obs(), ctx.d_wp)
+            nclose_d = dev_counts if dev_counts is not None else self._dev(counts.astype(np.int32))
+        scores = torch.empty(L, dtype=torch.float64, device="cuda")
+        lx, px = self._dev(leaf_xy), self._dev(parent_xy)
+        hp = self._dev(np.asarray(has_parent, dtype=np.int32))
+        ws_d = self._dev(np.asarray(ctx.workspace, dtype=np.float64))
+        _lib.check(lib.ipp_leaf_penalty(_lib.ptr(lx), _lib.ptr(px), _lib.ptr(hp), L, _lib.ptr(nclose_d), has_obs,
+                                        _lib.ptr(ws_d), float(mi), _lib.ptr(scores), _lib.stream_ptr()), "ipp_leaf_penalty")
+        self.launches += 1
+        return scores.cpu().numpy(), mi
+
+    # -- G6 selector half: UCB on the posterior -----------------------------------------------------------
+    def ucb_acquisition(self, gp, leaf_xy, visited_xy, beta, d_wp):
+        """rrt_thread.py:375-387: normalised mu + beta * normalised sigma, minus the visited penalty."""
+        torch, lib = self.torch, self.lib
+        L = leaf_xy.shape[0]
+        if hasattr(gp, "predict_points_device") and hasattr(gp, "X_train_"):
+            mu_d, sd_d, _ = gp.predict_points_device(self._dev(leaf_xy))
+            mu, sd = mu_d.cpu().numpy(), sd_d.cpu().numpy()
+        else:
+            mu, sd = gp.predict(leaf_xy, return_std=True)
+        mu_n = (mu - np.mean(mu)) / np.std(mu) if np.std(mu) != 0 else mu
+        sd_n = (sd - np.mean(sd)) / np.std(sd) if np.std(sd) != 0 else sd
+        acq = mu_n + beta * sd_n
+        visited = np.asarray(visited_xy, dtype=np.float64).reshape(-1, 2)
+        if visited.shape[0]:
+            acq_d = self._dev(acq)
+            lx, vx = self._dev(leaf_xy), self._dev(visited)
+            _lib.check(lib.ipp_ucb_visit_penalty(_lib.ptr(lx), L, _lib.ptr(vx), visited.shape[0], float(d_wp),
+                                                 _lib.ptr(acq_d), _lib.stream_ptr()), "ipp_ucb_visit_penalty")
+            self.launches += 1
+            acq = acq_d.cpu().numpy()
+        return acq, float(np.mean(sd))
+
+    def argmax_first(self, values):
+        """np.argmax semantics on the device (used by the sharded selectors)."""
+        torch, lib = self.torch, self.lib
+        v = self._dev(np.asarray(values, dtype=np.float64))
+        bv = torch.empty(1, dtype=torch.float64, device="cuda")
+        bi = torch.empty(1, dtype=torch.int32, device="cuda")
+        _lib.check(lib.ipp_argmax_first(_lib.ptr(v), v.shape[0], _lib.ptr(bv), _lib.ptr(bi), _lib.stream_ptr()),
+                   "ipp_argmax_first")
+        self.launches += 1
+        return int(bi.item()), float(bv.item())

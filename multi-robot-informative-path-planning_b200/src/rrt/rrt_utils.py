@@ -1,0 +1,302 @@
+"""Tree data model and RRT primitives of the drop-in (API of the reference's src/rrt/rrt_utils.py).
+
+B200-first layout: a tree is a structure of arrays (`TreeArrays`: coordinates, insertion-time parent,
+current parent, a time-stamped rewire log) that uploads to the GPU as-is and is what the branch-gain
+kernels walk (ipp_branch_gain).  Node OBJECTS with the reference's attributes (`point`, `parent`,
+`children`, `information`, `cost`) are materialised from the arrays only for API compatibility
+(`strategy.tree_nodes`, `get_current_node`, plotting hooks).
+
+Decisions are kept bit-identical to the reference:
+  * candidate filtering is vectorised, but every comparison that can flip on a rounding (nearest
+    ties, the `< d` radius test, path-cost comparisons) is re-evaluated on the short candidate list
+    with numpy's own scalar `np.linalg.norm`, exactly the expression of rrt_utils.py:71-101;
+  * `add_node` makes the NEAREST node the parent whatever `choose_parent` picked (rrt_utils.py:26-29,
+    103-105); `rewire` edits the parent pointer only, never `children` (rrt_utils.py:85-88).
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import numpy as np
+
+_norm = np.linalg.norm
+
+
+# ---- reference-shaped node objects ----------------------------------------------------------------
+class TreeNode:
+    """rrt_utils.py:10-29."""
+
+    def __init__(self, point: np.ndarray, parent: Optional["TreeNode"] = None, cost: float = 0):
+        self.point = point
+        self.parent = parent
+        self.children: List["TreeNode"] = []
+        self.cost = cost
+
+    def add_child(self, child: "TreeNode") -> None:
+        self.children.append(child)
+        child.parent = self
+
+
+class InformativeTreeNode(TreeNode):
+    """rrt_utils.py:31-35."""
+
+    def __init__(self, point: np.ndarray, parent: Optional[TreeNode] = None):
+        super().__init__(point, parent)
+        self.information = 0
+
+
+class TreeCollection:
+    """rrt_utils.py:37-54."""
+
+    def __init__(self):
+        self.trees: List[TreeNode] = []
+
+    def add(self, tree: TreeNode) -> None:
+        self.trees.append(tree)
+
+    def __iter__(self):
+        return iter(self.trees)
+
+    def __getitem__(self, idx: int) -> TreeNode:
+        return self.trees[idx]
+
+    def __len__(self) -> int:
+        return len(self.trees)
+
+
+# ---- object-level primitives (same names / semantics as the reference, for external callers) ------
+def node_selection_key_distance(node: TreeNode, target_point: np.ndarray) -> float:
+    return _norm(node.point - target_point)
+
+
+def cost(node: TreeNode) -> float:
+    total = 0
+    while node.parent is not None:
+        total += _norm(node.point - node.parent.point)
+        node = node.parent
+    return total
+
+
+def line_cost(x1: TreeNode, x2: TreeNode) -> float:
+    return _norm(x1.point - x2.point)
+
+
+def obstacle_free(x1: np.ndarray, x2: np.ndarray) -> bool:
+    return True  # rrt_utils.py:81-83: the reference never rejects an edge
+
+
+def choose_parent(X_near: List[TreeNode], x_nearest: TreeNode, x_new: TreeNode) -> TreeNode:
+    best, best_cost = x_nearest, cost(x_nearest) + line_cost(x_nearest, x_new)
+    for cand in X_near:
+        c = cost(cand) + line_cost(cand, x_new)
+        if obstacle_free(cand.point, x_new.point) and c < best_cost:
+            best, best_cost = cand, c
+    x_new.parent = best
+    return x_new
+
+
+def rewire(X_near: List[TreeNode], x_new: TreeNode) -> None:
+    for cand in X_near:
+        if obstacle_free(x_new.point, cand.point) and cost(x_new) + line_cost(x_new, cand) < cost(cand):
+            cand.parent = x_new
+
+
+def near(x_new: TreeNode, tree_nodes: List[TreeNode], d_waypoint_distance: float) -> List[TreeNode]:
+    return [nd for nd in tree_nodes if _norm(x_new.point - nd.point) < d_waypoint_distance]
+
+
+def steer(x_nearest: TreeNode, x_rand: np.ndarray, d_max_step: float) -> np.ndarray:
+    return steer_point(x_nearest.point, x_rand, d_max_step)
+
+
+def nearest(tree_nodes: List[TreeNode], x_rand: np.ndarray) -> TreeNode:
+    return min(tree_nodes, key=lambda nd: _norm(nd.point - x_rand))
+
+
+def add_node(tree_nodes: List[TreeNode], x_new: TreeNode, x_parent: TreeNode) -> None:
+    x_parent.add_child(x_new)
+    tree_nodes.append(x_new)
+
+
+def trace_path_to_root(selected_leaf: TreeNode) -> List[np.ndarray]:
+    out = []
+    node = selected_leaf
+    while node is not None:
+        out.append(node.point)
+        node = node.parent
+    out.reverse()
+    return out
+
+
+def steer_point(origin: np.ndarray, target: np.ndarray, d_max_step: float) -> np.ndarray:
+    """rrt_utils.py:93-98, operation for operation (the coordinates feed every later decision)."""
+    direction = target - origin
+    distance = _norm(direction)
+    direction = direction / distance if distance > 0 else direction
+    distance = min(distance, d_max_step)
+    return origin + direction * distance
+
+
+# ---- structure-of-arrays tree ------------------------------------------------------------------------
+class TreeArrays:
+    """One agent's tree as flat arrays; node id = insertion order (index into tree_nodes[agent])."""
+
+    def __init__(self, root_point: np.ndarray, capacity: int = 256):
+        self._xy = np.empty((capacity, 2), dtype=np.float64)
+        self.parent0 = np.full(capacity, -1, dtype=np.int64)  # parent at insertion (defines `children`)
+        self.parent = np.full(capacity, -1, dtype=np.int64)   # current parent (after rewires)
+        self.edge = np.zeros(capacity, dtype=np.float64)      # |point - current parent|, numpy-exact
+        self.nchild = np.zeros(capacity, dtype=np.int64)
+        self.info = np.zeros(capacity, dtype=np.float64)
+        self._pt: List[np.ndarray] = []                       # the original point objects, in order
+        self.rewires: List[tuple] = []                        # (time, node, new_parent)
+        self.n = 0
+        self._append(root_point, -1)
+
+    # -- storage ----------------------------------------------------------------------------------
+    def _grow(self):
+        cap = self._xy.shape[0] * 2
+        for name in ("_xy", "parent0", "parent", "edge", "nchild", "info"):
+            old = getattr(self, name)
+            new = np.empty((cap,) + old.shape[1:], dtype=old.dtype)
+            new[: old.shape[0]] = old
+            if name in ("parent0", "parent"):
+                new[old.shape[0]:] = -1
+            elif name != "_xy":
+                new[old.shape[0]:] = 0
+            setattr(self, name, new)
+
+    def _append(self, point, parent):
+        if self.n == self._xy.shape[0]:
+            self._grow()
+        i = self.n
+        self._xy[i] = point
+        self._pt.append(point)
+        self.parent0[i] = self.parent[i] = parent
+        self.nchild[i] = 0
+        self.info[i] = 0.0
+        if parent >= 0:
+            self.nchild[parent] += 1
+            self.edge[i] = _norm(point - self._pt[parent])
+        self.n += 1
+        return i
+
+    def points(self) -> np.ndarray:
+        return self._xy[: self.n]
+
+    def point(self, i) -> np.ndarray:
+        return self._pt[i]
+
+    # -- primitives, decision-exact ---------------------------------------------------------------
+    def nearest(self, target: np.ndarray) -> int:
+        """argmin_i |p_i - target| with the reference's first-minimum tie-break (rrt_utils.py:100-101)."""
+        d = self._xy[: self.n] - target
+        r = np.sqrt(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1])
+        m = r.min()
+        cand = np.nonzero(r <= m * (1.0 + 1e-12) + 1e-300)[0]
+        if cand.size == 1:
+            return int(cand[0])
+        best, best_d = -1, None
+        for i in cand:  # ascending index, strict '<' keeps the first minimum
+            di = _norm(self._pt[i] - target)
+            if best_d is None or di < best_d:
+                best, best_d = int(i), di
+        return best
+
+    def near(self, point: np.ndarray, radius: float) -> List[int]:
+        """[i : |point - p_i| < radius], ascending (rrt_utils.py:90-91)."""
+        d = self._xy[: self.n] - point
+        r = np.sqrt(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1])
+        out = []
+        for i in np.nonzero(r < radius * (1.0 + 1e-12))[0]:
+            if r[i] < radius * (1.0 - 1e-12) or _norm(point - self._pt[i]) < radius:
+                out.append(int(i))
+        return out
+
+    def path_cost(self, i: int) -> float:
+        """rrt_utils.py:71-76: leaf-to-root accumulation of the numpy-exact edge lengths."""
+        total = 0
+        while self.parent[i] >= 0:
+            total += self.edge[i]
+            i = self.parent[i]
+        return total
+
+    def add(self, point: np.ndarray, parent: int) -> int:
+        return self._append(point, parent)
+
+    def rewire(self, neighbours: List[int], new: int) -> None:
+        """rrt_utils.py:85-88; logs (time = id of the inserted node, node, new parent) for the
+        versioned branch walk of ipp_branch_gain."""
+        pn = self._pt[new]
+        for q in neighbours:
+            if self.path_cost(new) + _norm(pn - self._pt[q]) < self.path_cost(q):
+                self.parent[q] = new
+                self.edge[q] = _norm(self._pt[q] - pn)
+                self.rewires.append((new, q, new))
+
+    def history_csr(self):
+        """(hist_off[n+1], hist_time[E], hist_parent[E]) int32, events of a node in time order."""
+        E = len(self.rewires)
+        off = np.zeros(self.n + 1, dtype=np.int32)
+        if E == 0:
+            return off, np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.int32)
+        ev = np.asarray(self.rewires, dtype=np.int64)
+        order = np.lexsort((ev[:, 0], ev[:, 1]))  # by node, then time (stable)
+        ev = ev[order]
+        counts = np.bincount(ev[:, 1], minlength=self.n)
+        off[1:] = np.cumsum(counts)
+        return off, ev[:, 0].astype(np.int32), ev[:, 2].astype(np.int32)
+
+    def chain_at(self, i: int) -> List[np.ndarray]:
+        """Points from node i up to the root following the parents as they were when node i was
+        inserted (rewire events with time >= i are ignored) -- the walk ipp_branch_gain does."""
+        hist = {}
+        for t, q, p in self.rewires:
+            if t < i:
+                hist[q] = p  # events are appended in time order: the last one before i wins
+        out, q = [self._pt[i]], i
+        while True:
+            p = hist.get(q, int(self.parent0[q]))
+            if p < 0:
+                break
+            out.append(self._pt[p])
+            q = p
+        return out
+
+    # -- traversal --------------------------------------------------------------------------------
+    def leaves_in_order(self) -> np.ndarray:
+        """Nodes without children, in insertion order (rrt.py:374,443)."""
+        return np.nonzero(self.nchild[: self.n] == 0)[0]
+
+    def leaves_dfs(self) -> List[int]:
+        """Leaves reached from the root through the insertion-time `children` lists, depth first
+        (rrt.py:389-395)."""
+        kids: List[List[int]] = [[] for _ in range(self.n)]
+        for i in range(1, self.n):
+            kids[self.parent0[i]].append(i)
+        out, stack = [], [0]
+        while stack:
+            i = stack.pop()
+            if not kids[i]:
+                out.append(i)
+            stack.extend(reversed(kids[i]))
+        return out
+
+    def path_to_root(self, i: int) -> List[np.ndarray]:
+        """rrt_utils.py:107-114 over the CURRENT parent pointers; returns the original point objects."""
+        out = []
+        while i >= 0:
+            out.append(self._pt[i])
+            i = self.parent[i]
+        out.reverse()
+        return out
+
+    def materialise(self) -> List[InformativeTreeNode]:
+        """Reference-shaped node objects (children from insertion-time parents, parent = current)."""
+        nodes = [InformativeTreeNode(self._pt[i]) for i in range(self.n)]
+        for i in range(1, self.n):
+            nodes[self.parent0[i]].children.append(nodes[i])
+        for i in range(self.n):
+            nodes[i].parent = nodes[self.parent[i]] if self.parent[i] >= 0 else None
+            nodes[i].information = self.info[i] if i else 0
+        return nodes

@@ -14,7 +14,7 @@ Shims applied from the outside (never by editing the reference; SURVEY.md Append
   * np.random.seed(s) after constructing PointSourceField (its ctor re-seeds with None);
   * best_estimates = np.array([]) for the GP-named classes that forget to set it.
 
-Usage:  python oracle/make_golden.py [--only gp|gain|select|runs]
+Usage:  python oracle/make_golden.py [--only gp|gain|select|runs|field]
 """
 from __future__ import annotations
 
@@ -241,8 +241,8 @@ def gold_runs(R, PS, B):
         t = time.time()
         Z, std = strat.run()
         out.update({f"{tag}_obs_wp": np.asarray(strat.obs_wp, float), f"{tag}_meas": np.asarray(strat.measurements, float),
-                    f"{tag}_Z": Z, f"{tag}_std": std, f"{tag}_theta": sc.gp.kernel_.theta.copy(),
-                    f"{tag}_best_estimates": np.asarray(strat.best_estimates, float).reshape(-1, 3),
+                    f"{tag}_Z": Z[::4, ::4].copy(), f"{tag}_std": std.reshape(Z.shape)[::4, ::4].copy(),
+                    f"{tag}_theta": sc.gp.kernel_.theta.copy(), f"{tag}_best_estimates": np.asarray(strat.best_estimates, float).reshape(-1, 3),
                     f"{tag}_rng_after": np.random.uniform(size=3), f"{tag}_sources": np.array(sc.sources)})
         for i, p in enumerate(strat.agents_full_path):
             out[f"{tag}_path{i}"] = np.array(p, float).reshape(-1, 2)
@@ -253,11 +253,43 @@ def gold_runs(R, PS, B):
         np.random.seed(99)
         strat = cls(sc, d_waypoint_distance=2.5, **kw)
         Z, std = strat.run()
-        out.update({f"{tag}_obs_wp": np.asarray(strat.obs_wp, float), f"{tag}_Z": Z, f"{tag}_std": std,
-                    f"{tag}_full_path": np.asarray(strat.full_path, float), f"{tag}_theta": sc.gp.kernel_.theta.copy(),
+        out.update({f"{tag}_obs_wp": np.asarray(strat.obs_wp, float), f"{tag}_Z": Z[::4, ::4].copy(),
+                    f"{tag}_std": std.reshape(Z.shape)[::4, ::4].copy(), f"{tag}_full_path": np.asarray(strat.full_path, float), f"{tag}_theta": sc.gp.kernel_.theta.copy(),
                     f"{tag}_rng_after": np.random.uniform(size=3)})
         print(f"run {tag}: {len(strat.obs_wp)} obs")
     np.savez_compressed(os.path.join(GOLD, "runs_golden.npz"), **out)
+
+
+# ------------------------------------------------------------------------------------------------
+def gold_field(PS):
+    """Ground truth / simulated measurements (with and without a rectangular obstacle) and the
+    Bayesian source estimator, all from the reference's own host code."""
+    import src.estimation.estimation as E
+
+    out = {"versions": versions()}
+    W = 12
+    obst = [{"type": "rectangle", "x": 4, "y": 5, "width": 3, "height": 2}]
+    for tag, obstacles in [("free", []), ("obst", obst)]:
+        sc = PS.PointSourceField(num_sources=2, workspace_size=(0, W, 0, W), obstacles=obstacles, seed=8)
+        rng = np.random.RandomState(2)
+        wp = rng.uniform(0, W, (25, 2))
+        np.random.seed(4)
+        meas = sc.simulate_measurements(wp)
+        out.update({f"{tag}_sources": np.array(sc.sources), f"{tag}_gtruth": sc.g_truth, f"{tag}_wp": wp,
+                    f"{tag}_intensity": sc.intensity(wp), f"{tag}_meas": meas, f"{tag}_single": sc.intensity(wp[3])})
+    sc = PS.PointSourceField(num_sources=2, workspace_size=(0, 20, 0, 20), seed=21)
+    rng = np.random.RandomState(6)
+    wp = rng.uniform(0, 20, (30, 2))
+    np.random.seed(12)
+    meas = sc.simulate_measurements(wp)
+    np.random.seed(13)
+    est, M, bic = E.estimate_sources_bayesian(list(wp), list(meas), 1, 2, 80, 5, sc)
+    thetas = np.random.RandomState(1).uniform([0, 0, 1e5] * 2, [20, 20, 1e6] * 2, (7, 6))
+    ll = np.array([E.poisson_log_likelihood(t, wp, meas, 1, 2) for t in thetas])
+    out.update(est_wp=wp, est_meas=meas, est_theta=est, est_M=M, est_bic=bic, est_rng_after=np.random.uniform(size=3),
+               ll_thetas=thetas, ll_values=ll)
+    np.savez_compressed(os.path.join(GOLD, "field_golden.npz"), **out)
+    print(f"field: estimate M={M} bic={bic:.3f}")
 
 
 def main():
@@ -274,6 +306,8 @@ def main():
         gold_select(R, PS)
     if a.only in (None, "runs"):
         gold_runs(R, PS, B)
+    if a.only in (None, "field"):
+        gold_field(PS)
 
 
 if __name__ == "__main__":

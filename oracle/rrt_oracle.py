@@ -287,7 +287,9 @@ def bias_beta_scores(nodes, kernel_fn, agents_obs_wp, agent_idx, n_agents, beta,
     obs = np.array(agents_obs_wp[agent_idx])
     K_pio = kernel_fn(pts, obs) if obs.size > 0 else np.zeros((len(pts), 0))
     mi = mutual_information(K_pio, len(pts), beta)
-    scores = np.array([mi for _ in leaves], dtype=float)
+    # NB: no dtype -- when the agent has no observations mi is the int 0 and the reference's score
+    # array is int64, so every `-=` below truncates toward zero (and -inf casts to INT64_MIN).
+    scores = np.array([mi for _ in leaves])
     for i, nd in enumerate(leaves):
         scores[i] -= np.exp(0.5 * norm(nd.point - nd.parent.point) ** 2) if nd.parent else 0
         p = nd.point

@@ -1,0 +1,172 @@
+"""CPU tests of the product's HOST logic against reference-generated goldens: array-backed tree
+growth (bit-exact coordinates / parents), versioned-parent scoring order, selectors, RNG order and
+the whole strategy.run() waypoint sequences.  Device backends are replaced by the oracle doubles."""
+import numpy as np
+import pytest
+
+from mripp_b200.scoring import ScoreContext
+from mripp_b200.src.boustrophedon.boustrophedon import Boustrophedon, MR_Boustrophedon
+from mripp_b200.src.estimation import estimation as E
+from mripp_b200.src.point_source.point_source import PointSourceField
+from mripp_b200.src.rrt import rrt as R
+from mripp_b200.src.rrt.rrt_utils import TreeArrays
+from tests._doubles import OracleGP, OracleScorer
+
+GAINS = [R.point_source_gain_no_penalties, R.point_source_gain_only_distance_penalty,
+         R.point_source_gain_distance_rotation_penalty, R.point_source_gain_all]
+
+
+class FastGP(OracleGP):
+    full = False
+
+
+def _strategy(cls, W, seed, gp=FastGP, **kw):
+    sc = PointSourceField(num_sources=2, workspace_size=(0, W, 0, W), seed=seed, gp_factory=gp)
+    return sc, (lambda **extra: cls(sc, scorer=OracleScorer(), **kw, **extra))
+
+
+@pytest.mark.parametrize("S", [0, 1, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+def test_rig_tree_bit_exact_and_information(gold, S, variant):
+    g = gold("gain_golden.npz")
+    tag = f"S{S}_v{variant}"
+    sc, make = _strategy(R.MR_IPP, 40, 5, budget=120, d_waypoint_distance=2.5, num_agents=2, budget_iter=4)
+    np.random.seed(int(g[f"{tag}_seed"]))
+    st = make()
+    st.best_estimates = g[f"{tag}_est"] if S else np.array([])
+    st.agents_obs_wp = [list(g[f"{tag}_obs0"]), list(g[f"{tag}_obs1"])]
+    start = g[f"{tag}_start"]
+    st.agents_full_path = [[start.copy()], [np.array([30.0, 5.0])]]
+    st.initialize_trees(start, 0)
+    R.rig_tree_generation(st, 120, 0, gain_function=GAINS[variant])
+    tree = st.trees_soa[0]
+    assert np.array_equal(tree.points(), g[f"{tag}_pts"])
+    assert np.array_equal(tree.parent[: tree.n], g[f"{tag}_parent_final"])
+    assert np.array_equal(tree.nchild[: tree.n], g[f"{tag}_nchild"])
+    assert np.array_equal(tree.info[: tree.n], g[f"{tag}_info"])
+    nodes = st.tree_nodes[0]  # reference-shaped objects
+    assert len(nodes) == tree.n and nodes[0].parent is None
+    assert [len(nd.children) for nd in nodes] == list(g[f"{tag}_nchild"])
+
+
+def test_history_csr_orders_events_per_node():
+    t = TreeArrays(np.array([0.0, 0.0]))
+    for k in range(1, 6):
+        t.add(np.array([float(k), 0.0]), k - 1)
+    t.rewires = [(3, 1, 3), (5, 1, 5), (4, 2, 4)]
+    off, tm, par = t.history_csr()
+    assert list(off) == [0, 0, 2, 3, 3, 3, 3]
+    assert list(tm) == [3, 5, 4] and list(par) == [3, 5, 4]
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_selectors_bit_exact(gold, tag):
+    g = gold("select_golden.npz")
+    sc, make = _strategy(R.MR_IPP, 40, 5, budget=150, d_waypoint_distance=2.5, num_agents=2, budget_iter=4,
+                         beta_t=float(g[f"{tag}_beta"]))
+    np.random.seed(int(g[f"{tag}_seed"]))
+    st = make()
+    start = g[f"{tag}_start"]
+    st.agents_obs_wp = [list(g[f"{tag}_obs0"]), list(g[f"{tag}_obs1"])]
+    st.agents_full_path = [[start.copy()], [np.array([30.0, 5.0])]]
+    st.best_estimates = g[f"{tag}_est"]
+    st.initialize_trees(start, 0)
+    R.rig_tree_generation(st, 150, 0, gain_function=R.point_source_gain_all)
+    assert np.array_equal(st.trees_soa[0].points(), g[f"{tag}_pts"])
+    assert np.array_equal(st.trees_soa[0].info[: st.trees_soa[0].n], g[f"{tag}_info"])
+    p1 = R.bias_beta_path_selection(st, 0, start, 30.0)
+    assert np.array_equal(np.array(p1), g[f"{tag}_path_bias"])
+    p2 = R.informative_source_metric_path_selection(st, 0, start, 30.0)
+    assert np.array_equal(np.array(p2), g[f"{tag}_path_info"])
+    Kpio = g[f"{tag}_Kpio"]
+    if Kpio.size:
+        assert R.mutual_information_gain(np.zeros((Kpio.shape[0],) * 2), Kpio, float(g[f"{tag}_beta"])) == pytest.approx(
+            float(g[f"{tag}_mi"]), rel=1e-13)
+
+
+RUNS = [("mripp_1a", R.MR_IPP, dict(num_agents=1, stage_lambda=0.5)),
+        ("mripp_2a", R.MR_IPP, dict(num_agents=2, stage_lambda=0.5)),
+        ("rig_nopen", R.RRTRIG_PointSourceInformative_SourceMetric_PathPlanning, dict(num_agents=1, stage_lambda=0.6)),
+        ("rig_dist", R.RRTRIG_PointSourceInformative_Distance_SourceMetric_PathPlanning, dict(num_agents=1, stage_lambda=0.6)),
+        ("rig_rot", R.RRTRIG_PointSourceInformative_DistanceRotation_SourceMetric_PathPlanning, dict(num_agents=1, stage_lambda=0.6)),
+        ("biasbeta", R.RRT_BiasBetaInformative_GP_PathPlanning, dict(num_agents=1, stage_lambda=0.5)),
+        ("rrt_random", R.RRT_Random_GP_PathPlanning, dict(num_agents=1, stage_lambda=0.0)),
+        ("rrtstar_random", R.RRTStar_Random_GP_PathPlanning, dict(num_agents=1, stage_lambda=0.0))]
+COMMON = dict(budget=40, d_waypoint_distance=2.5, budget_iter=2, n_samples=60, s_stages=4, max_sources=2, lambda_b=1, beta_t=5.0)
+
+
+@pytest.mark.parametrize("tag,cls,extra", RUNS, ids=[r[0] for r in RUNS])
+def test_run_waypoint_sequences_identical(gold, tag, cls, extra):
+    """T3: chosen waypoints, simulated measurements, source estimates and the RNG position after the
+    run are bit-identical to the reference for a fixed seed."""
+    g = gold("runs_golden.npz")
+    sc, make = _strategy(cls, 20, 21, **COMMON, **extra)
+    assert np.array_equal(np.array(sc.sources), g[f"{tag}_sources"])
+    np.random.seed(1234)
+    st = make()
+    Z, std = st.run()
+    assert np.array_equal(np.asarray(st.obs_wp, float), g[f"{tag}_obs_wp"])
+    assert np.array_equal(np.asarray(st.measurements, float), g[f"{tag}_meas"])
+    for i, p in enumerate(st.agents_full_path):
+        assert np.array_equal(np.array(p, float).reshape(-1, 2), g[f"{tag}_path{i}"])
+    assert np.array_equal(np.asarray(st.best_estimates, float).reshape(-1, 3), g[f"{tag}_best_estimates"])
+    assert np.array_equal(np.random.uniform(size=3), g[f"{tag}_rng_after"])
+    assert Z.shape == (200, 200) and std.shape == (40000,)
+
+
+def test_run_field_reoptimised_tier(gold):
+    """T2: with the full optimiser the field agrees with the reference within the loose tier."""
+    g = gold("runs_golden.npz")
+    tag = "rig_nopen"
+    sc, make = _strategy(R.RRTRIG_PointSourceInformative_SourceMetric_PathPlanning, 20, 21, gp=OracleGP, **COMMON,
+                         num_agents=1, stage_lambda=0.6)
+    np.random.seed(1234)
+    Z, std = make().run()
+    assert np.abs(np.log10(Z[::4, ::4]) - np.log10(g[f"{tag}_Z"])).max() <= 2e-2
+    assert np.abs(std.reshape(Z.shape)[::4, ::4] - g[f"{tag}_std"]).max() <= 2e-2
+
+
+@pytest.mark.parametrize("tag,cls,kw", [("boust", Boustrophedon, dict(budget=60)),
+                                        ("mr_boust", MR_Boustrophedon, dict(budget=40, num_agents=2))])
+def test_boustrophedon_paths(gold, tag, cls, kw):
+    g = gold("runs_golden.npz")
+    sc = PointSourceField(num_sources=2, workspace_size=(0, 20, 0, 20), seed=21, gp_factory=FastGP)
+    np.random.seed(99)
+    st = cls(sc, d_waypoint_distance=2.5, **kw)
+    st.run()
+    assert np.array_equal(np.asarray(st.obs_wp, float), g[f"{tag}_obs_wp"])
+    assert np.array_equal(np.asarray(st.full_path, float), g[f"{tag}_full_path"])
+    assert np.array_equal(np.random.uniform(size=3), g[f"{tag}_rng_after"])
+
+
+@pytest.mark.parametrize("tag", ["free", "obst"])
+def test_field_physics_bit_exact(gold, tag):
+    g = gold("field_golden.npz")
+    obst = [{"type": "rectangle", "x": 4, "y": 5, "width": 3, "height": 2}] if tag == "obst" else []
+    sc = PointSourceField(num_sources=2, workspace_size=(0, 12, 0, 12), obstacles=obst, seed=8, gp_factory=FastGP)
+    assert np.array_equal(np.array(sc.sources), g[f"{tag}_sources"])
+    assert np.array_equal(sc.g_truth, g[f"{tag}_gtruth"])
+    assert np.array_equal(sc.intensity(g[f"{tag}_wp"]), g[f"{tag}_intensity"])
+    assert np.array_equal(sc.intensity(g[f"{tag}_wp"][3]), g[f"{tag}_single"])
+    np.random.seed(4)
+    assert np.array_equal(sc.simulate_measurements(g[f"{tag}_wp"]), g[f"{tag}_meas"])
+
+
+def test_source_estimator_bit_exact(gold):
+    g = gold("field_golden.npz")
+    sc = PointSourceField(num_sources=2, workspace_size=(0, 20, 0, 20), seed=21, gp_factory=FastGP)
+    ll = E.batched_poisson_log_likelihood(g["ll_thetas"], g["est_wp"], g["est_meas"], 1, 2)
+    assert np.array_equal(ll, g["ll_values"])
+    np.random.seed(13)
+    est, M, bic = E.estimate_sources_bayesian(list(g["est_wp"]), list(g["est_meas"]), 1, 2, 80, 5, sc)
+    assert M == int(g["est_M"]) and bic == float(g["est_bic"])
+    assert np.array_equal(est, g["est_theta"])
+    assert np.array_equal(np.random.uniform(size=3), g["est_rng_after"])
+
+
+def test_score_context_helpers():
+    ctx = ScoreContext(np.array([[1.0, 1.0, 5.0], [4.0, 4.0, 6.0]]), np.array([3.9, 3.9]), [[np.zeros(2)], []], 1, 2.5,
+                       (0, 10, 0, 10), [{"type": "rectangle", "x": 1, "y": 2, "width": 3, "height": 4}])
+    assert ctx.closest_estimate_index() == 1
+    assert ctx.all_obs().shape == (1, 2) and not ctx.agent_has_obs()
+    assert ctx.obstacle_rows().tolist() == [[1.0, 2.0, 3.0, 4.0]]
