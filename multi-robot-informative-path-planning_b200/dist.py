@@ -1,0 +1,128 @@
+"""Multi-GPU sharding of the hot path: one process per GPU over torch.distributed (NCCL on the
+box, gloo in the CPU tests).  The path is embarrassingly parallel:
+
+  * grid posterior   -> contiguous row slabs of the lattice; every rank holds the (replicated)
+                        fitted state, computes its slab, and one all_gather assembles the field;
+  * branch / leaf scoring -> contiguous candidate batches; the only exchange is an all_gather of one
+                        (best value, global index) pair per rank, reduced with np.argmax semantics
+                        (first maximum, first NaN wins) so the choice is rank-count independent;
+  * independent rounds -> round r runs on rank r mod P, no data-path collective.
+
+No collective moves bulk data on the critical path: the gathers are G*16/P bytes and 16 bytes.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+
+def slab_bounds(total: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous partition of range(total) into `world` near-equal slabs."""
+    base, rem = divmod(int(total), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def row_slab(nx: int, ny: int, world: int, rank: int) -> Tuple[int, int]:
+    """Flat lattice index range [g0, g1) of this rank's slab of whole rows (index = iy * nx + ix)."""
+    r0, r1 = slab_bounds(ny, world, rank)
+    return r0 * nx, r1 * nx
+
+
+def rounds_for_rank(n_rounds: int, world: int, rank: int) -> List[int]:
+    return [r for r in range(n_rounds) if r % world == rank]
+
+
+def _dist():
+    import torch.distributed as dist
+
+    return dist
+
+
+def gather_slabs(local: "torch.Tensor", sizes: Sequence[int], group=None) -> "torch.Tensor":
+    """all_gather of unequal 1-D slabs (padded to the largest) -> concatenated full vector."""
+    import torch
+
+    dist = _dist()
+    world = dist.get_world_size(group)
+    m = max(sizes)
+    buf = torch.zeros(m, dtype=local.dtype, device=local.device)
+    buf[: local.numel()] = local
+    parts = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(parts, buf, group=group)
+    return torch.cat([p[:s] for p, s in zip(parts, sizes)])
+
+
+def sharded_grid_posterior(gp, ws, nx: int, ny: int, group=None, compute_slab: Optional[Callable] = None):
+    """(zpred, std) over the whole lattice, each rank computing one row slab.
+
+    `compute_slab(g0, g1) -> (zpred, std)` torch tensors; defaults to the fused device posterior of
+    the fitted `gp` (mripp_b200.gp.GaussianProcessRegressor.predict_grid_device)."""
+    dist = _dist()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    bounds = [row_slab(nx, ny, world, r) for r in range(world)]
+    g0, g1 = bounds[rank]
+    if compute_slab is None:
+        def compute_slab(a, b):
+            _, std_d, z_d = gp.predict_grid_device(ws[0], ws[1], nx, ws[2], ws[3], ny, g_begin=a, g_end=b, want_zpred=True)
+            return z_d, std_d
+    z_loc, s_loc = compute_slab(g0, g1)
+    sizes = [b - a for a, b in bounds]
+    z = gather_slabs(z_loc, sizes, group)
+    s = gather_slabs(s_loc, sizes, group)
+    return z.cpu().numpy(), s.cpu().numpy()
+
+
+def combine_argmax(values: np.ndarray, indices: np.ndarray) -> int:
+    """np.argmax over the concatenation, given each shard's (local best value, GLOBAL index):
+    a NaN wins at the smallest index, otherwise the largest value at the smallest index.
+    indices < 0 mark empty shards."""
+    best = -1
+    for v, i in zip(values, indices):
+        if i < 0:
+            continue
+        if best < 0:
+            best, bv = int(i), v
+            continue
+        if np.isnan(bv) or np.isnan(v):
+            take = np.isnan(v) and (not np.isnan(bv) or i < best)
+        else:
+            take = v > bv or (v == bv and i < best)
+        if take:
+            best, bv = int(i), v
+    return best
+
+
+def sharded_argmax(local_scores: "torch.Tensor", offset: int, group=None) -> int:
+    """Global np.argmax of a score vector sharded in contiguous batches (this rank holds
+    [offset, offset + len))."""
+    import torch
+
+    dist = _dist()
+    world = dist.get_world_size(group)
+    if local_scores.numel():
+        v = local_scores.detach().double().cpu().numpy()
+        k = int(np.argmax(v))  # numpy semantics on the shard
+        pair = torch.tensor([float(v[k]), float(offset + k)], dtype=torch.float64, device=local_scores.device)
+    else:
+        pair = torch.tensor([0.0, -1.0], dtype=torch.float64, device=local_scores.device)
+    parts = [torch.empty_like(pair) for _ in range(world)]
+    dist.all_gather(parts, pair, group=group)
+    vals = np.array([float(p[0]) for p in parts])
+    idx = np.array([int(p[1]) for p in parts])
+    return combine_argmax(vals, idx)
+
+
+def broadcast_path(path: Optional[np.ndarray], src: int, group=None, device="cpu") -> np.ndarray:
+    """Broadcast the chosen waypoint list (k x 2 doubles) from rank `src`."""
+    import torch
+
+    dist = _dist()
+    n = torch.tensor([0 if path is None else len(path)], dtype=torch.int64, device=device)
+    dist.broadcast(n, src=src, group=group)
+    buf = torch.zeros((int(n.item()), 2), dtype=torch.float64, device=device)
+    if dist.get_rank(group) == src and path is not None:
+        buf.copy_(torch.as_tensor(np.asarray(path, dtype=np.float64).reshape(-1, 2)))
+    dist.broadcast(buf, src=src, group=group)
+    return buf.cpu().numpy()

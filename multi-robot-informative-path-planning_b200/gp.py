@@ -197,6 +197,8 @@ class GaussianProcessRegressor:
         self.random_state = random_state
         self._ws = _Workspace()
         self.n_lml_evals_ = 0
+        self.lazy = False
+        self._pending = False
 
     # -- helpers ------------------------------------------------------------------------------
     def _rng_state(self):
@@ -243,9 +245,14 @@ class GaussianProcessRegressor:
             if eval_gradient:
                 raise ValueError("Gradient can only be evaluated for theta!=None")
             return self.log_marginal_likelihood_value_
+        self._ensure()
         theta = np.asarray(theta, dtype=float)
         if not clone_kernel:
-            self.kernel_.theta = theta
+            self._kernel_fitted.theta = theta
+        return self._lml(theta, eval_gradient)
+
+    def _lml(self, theta, eval_gradient):
+        theta = np.asarray(theta, dtype=float)
         c, l = float(np.exp(theta[0])), float(np.exp(theta[1]))
         res = self._eval_device(c, l, eval_gradient)
         self.n_lml_evals_ += 1
@@ -265,14 +272,20 @@ class GaussianProcessRegressor:
         raise ValueError(f"Unknown optimizer {self.optimizer}.")
 
     def fit(self, X, y):
-        """_gpr.py:233-368 (single-output)."""
+        """_gpr.py:233-368 (single-output).
+
+        The restart start points are drawn from the RNG here, in the reference's order
+        (_gpr.py:329-333; nothing else in fit consumes random numbers).  With `self.lazy = True`
+        the optimisation itself is deferred until fitted state is first read (`kernel_`, `alpha_`,
+        `L_`, `predict`, ...): a later `fit` supersedes a pending one, which is what makes the
+        per-step refits of rrt.py:339,360,749 -- whose results the reference never reads -- free."""
         X = _as_points(X)
         y = np.asarray(y, dtype=np.float64).reshape(-1)
         if X.shape[0] != y.shape[0]:
             raise ValueError(f"X and y have inconsistent lengths: {X.shape[0]} != {y.shape[0]}")
         if X.shape[0] == 0:
             raise ValueError("Found array with 0 sample(s) while a minimum of 1 is required.")
-        self.kernel_ = self.kernel.clone()
+        self._kernel_fitted = self.kernel.clone()
         self._rng = self._rng_state()
         if self.normalize_y:
             self._y_train_mean = np.mean(y, axis=0)
@@ -284,51 +297,74 @@ class GaussianProcessRegressor:
             self._y_train_std = 1.0
         self.X_train_ = np.copy(X) if self.copy_X_train else X
         self.y_train_ = np.copy(y) if self.copy_X_train else y
-        self._ws.ensure(X.shape[0])
-        self._upload_training(self.X_train_, self.y_train_)
         self._L_host = None
         self._alpha_host = None
-
-        fixed = isinstance(self.kernel_.constant_value_bounds, str) or isinstance(self.kernel_.length_scale_bounds, str)
+        k = self._kernel_fitted
+        fixed = isinstance(k.constant_value_bounds, str) or isinstance(k.length_scale_bounds, str)
+        self._starts = None
         if self.optimizer is not None and not fixed:
+            bounds = k.bounds
+            if self.n_restarts_optimizer > 0 and not np.isfinite(bounds).all():
+                raise ValueError("Multiple optimizer restarts (n_restarts_optimizer>0) requires that all "
+                                 "bounds are finite.")
+            self._starts = [k.theta] + [self._rng.uniform(bounds[:, 0], bounds[:, 1])
+                                        for _ in range(self.n_restarts_optimizer)]
+        self._pending = True
+        if not self.lazy:
+            self._ensure()
+        return self
+
+    def _ensure(self):
+        """Run the deferred optimisation + final factorisation (no-op when up to date)."""
+        if not getattr(self, "_pending", False):
+            return
+        self._pending = False
+        self._ws.ensure(self.X_train_.shape[0])
+        self._upload_training(self.X_train_, self.y_train_)
+        if self._starts is not None:
             def obj_func(theta, eval_gradient=True):
                 if eval_gradient:
-                    lml, grad = self.log_marginal_likelihood(theta, eval_gradient=True, clone_kernel=False)
+                    lml, grad = self._lml(theta, True)
                     return -lml, -grad
-                return -self.log_marginal_likelihood(theta, clone_kernel=False)
+                return -self._lml(theta, False)
 
-            bounds = self.kernel_.bounds
-            optima = [self._constrained_optimization(obj_func, self.kernel_.theta, bounds)]
-            if self.n_restarts_optimizer > 0:
-                if not np.isfinite(bounds).all():
-                    raise ValueError("Multiple optimizer restarts (n_restarts_optimizer>0) requires that all "
-                                     "bounds are finite.")
-                for _ in range(self.n_restarts_optimizer):
-                    theta_initial = self._rng.uniform(bounds[:, 0], bounds[:, 1])
-                    optima.append(self._constrained_optimization(obj_func, theta_initial, bounds))
+            bounds = self._kernel_fitted.bounds
+            optima = [self._constrained_optimization(obj_func, t0, bounds) for t0 in self._starts]
             lml_values = [o[1] for o in optima]
-            self.kernel_.theta = optima[int(np.argmin(lml_values))][0]
-            self.log_marginal_likelihood_value_ = -np.min(lml_values)
+            self._kernel_fitted.theta = optima[int(np.argmin(lml_values))][0]
+            self._lml_value = -np.min(lml_values)
             self._finalize(set_lml=False)
         else:
             self._finalize(set_lml=True)
-        return self
+
+    # fitted attributes resolve a pending lazy fit first
+    @property
+    def kernel_(self):
+        self._ensure()
+        return self._kernel_fitted
+
+    @property
+    def log_marginal_likelihood_value_(self):
+        self._ensure()
+        return self._lml_value
 
     def _finalize(self, set_lml):
-        res = self._eval_device(self.kernel_.constant_value, self.kernel_.length_scale, False, final=True)
+        k = self._kernel_fitted
+        res = self._eval_device(k.constant_value, k.length_scale, False, final=True)
         if res[3] != 0.0:
             raise np.linalg.LinAlgError(
-                f"The kernel, {self.kernel_}, is not returning a positive definite matrix. Try gradually "
+                f"The kernel, {k}, is not returning a positive definite matrix. Try gradually "
                 "increasing the 'alpha' parameter of your GaussianProcessRegressor estimator.",
                 f"{int(res[3])}-th leading minor of the array is not positive definite")
         if set_lml:
-            self.log_marginal_likelihood_value_ = float(res[0])
-        self._fitted_c = self.kernel_.constant_value
-        self._fitted_l = self.kernel_.length_scale
+            self._lml_value = float(res[0])
+        self._fitted_c = k.constant_value
+        self._fitted_l = k.length_scale
 
     # -- fitted attributes (lazy device -> host) ------------------------------------------------
     @property
     def L_(self):
+        self._ensure()
         if self._L_host is None:
             n = self.X_train_.shape[0]
             NP, ld = self._ws.layout[0], self._ws.layout[2]
@@ -337,6 +373,7 @@ class GaussianProcessRegressor:
 
     @property
     def alpha_(self):
+        self._ensure()
         if self._alpha_host is None:
             n = self.X_train_.shape[0]
             off = self._ws.layout[7]
@@ -345,6 +382,7 @@ class GaussianProcessRegressor:
 
     # -- prediction -----------------------------------------------------------------------------
     def _posterior_args(self):
+        self._ensure()
         return (_lib.ptr(self._ws.W), _lib.ptr(self._ws.v), int(self.X_train_.shape[0]), float(self._fitted_c),
                 float(self._fitted_l), float(self._y_train_mean), float(self._y_train_std))
 

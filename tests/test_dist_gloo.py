@@ -1,0 +1,82 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU plumbing: slab partition + all_gather assembly of the
+grid posterior, global argmax with numpy tie/NaN semantics, path broadcast, round sharding."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from mripp_b200 import dist as D
+from oracle import gp_oracle as O
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.RandomState(0)
+        X = rng.uniform(0, 6, (40, 2))
+        y = np.sin(X[:, 0]) + 0.1 * X[:, 1]
+        st = O.fit(X, y, 1.0, 1.5, optimize=False)
+        ws, nx, ny = (0, 6, 0, 5), 60, 50
+        _, _, r, _ = O.workspace_grid(ws)
+
+        def slab(a, b):
+            m, s, _ = O.predict(st, r[a:b])
+            return torch.from_numpy(10 ** m), torch.from_numpy(s)
+
+        z, s = D.sharded_grid_posterior(None, ws, nx, ny, compute_slab=slab)
+        scores = np.array([1.0, 5.0, 5.0, np.nan, 2.0, np.nan, 9.0])
+        lo, hi = D.slab_bounds(len(scores), world, rank)
+        k_nan = D.sharded_argmax(torch.from_numpy(scores[lo:hi]), lo)
+        clean = np.array([1.0, 5.0, 3.0, 5.0, 5.0, 0.0, 4.0])
+        k_tie = D.sharded_argmax(torch.from_numpy(clean[lo:hi]), lo)
+        path = D.broadcast_path(np.array([[1.0, 2.0], [3.0, 4.0]]) if rank == 1 else None, src=1)
+        q.put((rank, z, s, k_nan, k_tie, path, D.rounds_for_rank(7, world, rank)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_sharding_matches_single_process():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rng = np.random.RandomState(0)
+    X = rng.uniform(0, 6, (40, 2))
+    y = np.sin(X[:, 0]) + 0.1 * X[:, 1]
+    st = O.fit(X, y, 1.0, 1.5, optimize=False)
+    _, _, r, _ = O.workspace_grid((0, 6, 0, 5))
+    m, s, _ = O.predict(st, r)
+    for rank, z, sd, k_nan, k_tie, path, rounds in out:
+        assert np.array_equal(z, 10 ** m) and np.array_equal(sd, s)  # slabs are row independent: exact
+        assert k_nan == 3 and k_tie == 1
+        assert np.array_equal(path, [[1.0, 2.0], [3.0, 4.0]])
+        assert rounds == [r_ for r_ in range(7) if r_ % 2 == rank]
+
+
+def test_partition_helpers():
+    for total in (0, 1, 7, 1000):
+        for world in (1, 2, 3, 8):
+            b = [D.slab_bounds(total, world, r) for r in range(world)]
+            assert b[0][0] == 0 and b[-1][1] == total
+            assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+            assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1
+    assert D.row_slab(10, 7, 2, 1) == (40, 70)
+    assert D.combine_argmax(np.array([np.nan, 1.0]), np.array([5, 0])) == 5
+    assert D.combine_argmax(np.array([2.0, 2.0, 3.0]), np.array([4, 1, -1])) == 1
