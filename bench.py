@@ -1,0 +1,441 @@
+"""Benchmark of the B200 GP-posterior / information-gain hot path (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c3|c2] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One step = one posterior pass (mean, std, 10**mean) over the whole workspace lattice of the named
+workload with the fitted GP state resident, plus -- reported separately in the same JSON line -- one
+batch of candidate-branch information-gain evaluations.  Multi-GPU: every rank owns one independent
+simulation round of the same shape (SURVEY.md §8e "independent rounds"; no data-path collective),
+so scaling is weak and `value` = points all ranks processed / max-over-ranks time.
+
+`--impl reference` times the reference's CPU implementation of the same step (scikit-learn's
+GaussianProcessRegressor driven as src/point_source/point_source.py:349-351 drives it, and the
+Python gain functions restated in oracle/rrt_oracle.py) on the host cores, on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "gp_posterior_grid_points_per_sec"
+UNIT = "grid points/s"
+L2_BYTES = 126 * 1024 * 1024
+
+# BASELINE.json configs (10 lattice points per unit length)
+WORKLOADS = {
+    "c2": dict(desc="configs[1]: single robot, 200x200 grid, 500 measurements", n=500, W=20, agents=1, branches=2048),
+    "c3": dict(desc="configs[2]: 3 robots, 500x500 grid, 2000 measurements", n=2000, W=50, agents=3, branches=4096),
+    "c4": dict(desc="configs[3]: 8 robots, 1000x1000 grid, 5000 measurements, 8192 candidate branches", n=5000, W=100,
+               agents=8, branches=8192),
+}
+THETA = (1.0, 2.0)  # fixed (c, l): the posterior cost does not depend on it
+
+
+def synth_observations(n, W, seed):
+    """Noisy log10 readings of a 3-source inverse-square field at n waypoints, 20 % exact duplicates
+    (the reference re-measures the root of every re-rooted tree)."""
+    rng = np.random.RandomState(seed)
+    X = rng.uniform(0, W, (n, 2))
+    k = n // 5
+    X[n - k:] = X[:k]
+    src = np.array([[0.3 * W, 0.6 * W, 5e5], [0.7 * W, 0.2 * W, 8e5], [0.5 * W, 0.5 * W, 2e5]])
+    d2 = ((X[:, None, :] - src[None, :, :2]) ** 2).sum(-1)
+    inten = (src[None, :, 2] / (4 * np.pi * np.maximum(d2, 0.25))).sum(1)
+    meas = np.maximum(inten * (1 + 1e-3 * rng.randn(n)), 1e-6)
+    return X, meas, src
+
+
+def synth_tree(B, W, seed):
+    """A seeded random tree with B + 1 nodes (node id = insertion order, parent among the previous
+    400 nodes, step < d_wp) as flat arrays: every non-root node is one candidate branch."""
+    rng = np.random.RandomState(seed)
+    N = B + 1
+    xy = np.empty((N, 2))
+    parent = np.full(N, -1, dtype=np.int64)
+    xy[0] = (0.5 * W, 0.5 * W)
+    lo = np.maximum(0, np.arange(N) - 400)
+    par = (lo + rng.random_sample(N) * (np.arange(N) - lo)).astype(np.int64)
+    step = rng.uniform(-1.0, 1.0, (N, 2))
+    for k in range(1, N):
+        parent[k] = par[k]
+        xy[k] = xy[par[k]] + step[k]
+    return xy, parent
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def window(self, t0, t1):
+        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+
+def fp64_peak_tflops():
+    """fp64 tensor (DMMA) peak measured on this pool's B200 by csrc/fp64_peak.cu (MEASURED_PEAKS.json
+    carries only HBM and bf16).  Returns (value, source)."""
+    p = os.path.join(ROOT, "profiles", "fp64_peak_r01.json")
+    try:
+        d = json.load(open(p))
+        return float(max(d["dmma884_tflops"], d["dmma16816_tflops"], d["dfma_tflops"])), "measured: profiles/fp64_peak_r01.json"
+    except (OSError, KeyError, ValueError):
+        return 37.0, "fallback: NVIDIA HGX B200 sheet, 296 TF fp64 / 8 GPUs"
+
+
+def hbm_peak_gbs():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured: MEASURED_PEAKS.json"
+    except (OSError, KeyError, ValueError):
+        return 6650.0, "fallback: B200_PROFILING.md"
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU legs (the only places that execute oracle/)
+# ---------------------------------------------------------------------------------------------------
+def cpu_posterior_leg(wl, seed, sample_pts, steps, warmup):
+    """The reference's own predict path on host cores: sklearn GPR at fixed theta (fit once, untimed
+    here but reported), then gp.predict(sample of the lattice, return_std=True) per step, exactly the
+    calls of point_source.py:349-351."""
+    from threadpoolctl import threadpool_info
+
+    from oracle import gp_oracle as O
+
+    X, meas, _ = synth_observations(wl["n"], wl["W"], seed)
+    ylog = np.log10(np.maximum(meas, 1e-6))
+    gp = O.sklearn_fixed_theta_gp(*THETA)
+    t = time.perf_counter()
+    gp.fit(X, ylog)
+    t_fit = time.perf_counter() - t
+    x, y, _, _ = O.workspace_grid((0, wl["W"], 0, wl["W"]))
+    nx = len(x)
+    G = nx * len(y)
+    rng = np.random.RandomState(1)
+    times = []
+    for it in range(warmup + steps):
+        row0 = int(rng.randint(0, len(y)))
+        idx = (row0 * nx + np.arange(sample_pts)) % G  # a contiguous run of lattice points, like a row slab
+        r = np.column_stack((x[idx % nx], y[idx // nx]))
+        t = time.perf_counter()
+        mean, std = gp.predict(r, return_std=True)
+        z = 10 ** mean
+        dt = time.perf_counter() - t
+        if it >= warmup:
+            times.append(dt)
+    threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    return dict(pts_per_s=sample_pts / float(np.mean(times)), ms_per_step=1e3 * float(np.mean(times)), fit_fixed_theta_s=t_fit,
+                cores=int(threads), sample_pts=sample_pts)
+
+
+def cpu_branch_leg(wl, seed, sample_branches):
+    """Reference gain function point_source_gain_all (rrt.py:130-259) restated in oracle/rrt_oracle.py:
+    single-threaded Python like the reference's (GIL)."""
+    from oracle import rrt_oracle as T
+
+    W = wl["W"]
+    xy, parent = synth_tree(wl["branches"], W, seed)
+    X, _, src = synth_observations(wl["n"], W, seed)
+    per = wl["n"] // wl["agents"]
+    obs = [list(X[a * per:(a + 1) * per]) for a in range(wl["agents"])]
+    nodes = []
+    for k in range(len(xy)):
+        nd = T.Node(xy[k])
+        if k:
+            T.attach(nodes, nd, nodes[parent[k]])
+        else:
+            nd.index = 0
+            nodes.append(nd)
+    ctx = T.GainContext(src, xy[0], obs, 0, wl["agents"], 1.0, (0, W, 0, W), [])
+    pick = np.random.RandomState(2).choice(np.arange(1, len(xy)), sample_branches, replace=False)
+    t = time.perf_counter()
+    for i in pick:
+        T.branch_gain(3, ctx, nodes[i])
+    dt = time.perf_counter() - t
+    return dict(evals_per_s=sample_branches / dt, sample_branches=int(sample_branches), seconds=dt)
+
+
+def run_reference(args, wl, rank, world):
+    if rank != 0:
+        return
+    sample = args.cpu_sample or max(2048, min(20000, int(2.0e7 / wl["n"])))
+    post = cpu_posterior_leg(wl, 0, sample, args.steps, args.warmup)
+    br = cpu_branch_leg(wl, 0, 16 if wl["n"] >= 2000 else 64)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": post["pts_per_s"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": post["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload + " -- " + wl["desc"], "n_measurements": wl["n"],
+                   "grid": [wl["W"] * 10, wl["W"] * 10], "theta_c_l": list(THETA)},
+        "cpu_baseline": {"value": post["pts_per_s"], "unit": UNIT, "cores": post["cores"], "kind": "port",
+                         "sample": f"{sample} contiguous lattice points per step through scikit-learn "
+                                   f"GaussianProcessRegressor.predict(return_std=True) at fixed theta (the reference's own "
+                                   f"dependency, called as point_source.py:351); one-off fixed-theta fit took "
+                                   f"{post['fit_fixed_theta_s']:.2f} s, not in the step"},
+        "e2e": {"value": post["pts_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "branch_gain": {"value": br["evals_per_s"], "unit": "branch evals/s", "cores": 1,
+                        "sample": f"{br['sample_branches']} of {wl['branches']} branches, point_source_gain_all "
+                                  f"(pure Python, single thread)"},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------------
+def run_b200(args, wl, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    from mripp_b200 import _lib
+    from mripp_b200 import gp as G
+    from mripp_b200.scoring import GpuScorer, ScoreContext
+    from mripp_b200.src.point_source.point_source import PointSourceField
+    from mripp_b200.src.rrt.rrt_utils import TreeArrays
+
+    _lib.require_cuda()
+    _lib.load()
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n, W = wl["n"], wl["W"]
+    nx = ny = W * 10
+    Gpts = nx * ny
+    seed = rank  # every rank owns one independent simulation round
+    X, meas, src = synth_observations(n, W, seed)
+    ylog = np.log10(np.maximum(meas, 1e-6))
+
+    # the public objects a user of the reference holds: a scenario and its estimator
+    field = PointSourceField(num_sources=3, workspace_size=(0, W, 0, W), seed=seed)
+    field.gp = G.GaussianProcessRegressor(kernel=G.ConstantRBFKernel(*THETA), optimizer=None, normalize_y=True)
+    gp = field.gp
+    gp.fit(X, ylog)
+    gp._ensure()
+    NP = gp._ws.layout[0]
+    out = tuple(torch.empty(Gpts, dtype=torch.float64, device="cuda") for _ in range(3))
+    flush = None
+    state_bytes = 8 * NP * NP
+    if state_bytes + 24 * Gpts < 2 * L2_BYTES:
+        flush = torch.empty(3 * L2_BYTES // 8, dtype=torch.float64, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    launches = {"n": 0}
+
+    def posterior_step():
+        gp.predict_grid_device(0, W, nx, 0, W, ny, want_zpred=True, out=out)
+        launches["n"] += 1
+
+    def timed(fn, steps, warmup, count=True):
+        for _ in range(warmup):
+            fn()
+        if flush is not None:
+            flush.zero_()
+        barrier()
+        before = launches["n"]
+        evs = []
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            evs.append((e0, e1))
+            if flush is not None:
+                flush.zero_()  # evict the operands between timed iterations (outside the event pairs)
+        barrier()
+        t1 = time.perf_counter()
+        ms = [a.elapsed_time(b) for a, b in evs]
+        tot = torch.tensor([sum(ms)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+        return float(tot.item()) / steps, (t0, t1), launches["n"] - before
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    time.sleep(0.3)
+
+    # ---- (1) device-resident posterior: the headline `value` and the roofline ---------------------
+    ms_post, win, n_launch = timed(posterior_step, args.steps, args.warmup)
+    clocks = sampler.window(*win) if sampler else None
+
+    # ---- (2) end to end through the public API with host buffers ------------------------------------
+    wp = [X[i] for i in range(n)]  # the reference passes a Python list of 1-D arrays (rrt.py:749)
+
+    def e2e_step():
+        z, std = field.predict_spatial_field(wp, meas)  # H2D obs -> factor -> posterior -> D2H (pinned)
+        launches["n"] += 1
+        return z, std
+
+    saved = launches["n"]
+    for _ in range(max(1, args.warmup // 2)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, args.steps // 2) if wl["n"] >= 5000 else args.steps
+    for _ in range(e2e_steps):
+        z, std = e2e_step()
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_ms = 1e3 * float(dt.item()) / e2e_steps
+    assert z.shape == (ny, nx) and std.shape == (Gpts,) and np.isfinite(std).all()
+    launches["n"] = saved
+
+    # ---- (3) fit side: LML + gradient evaluations (what gp.fit spends its time on) -----------------
+    th = np.log(THETA)
+    for _ in range(2):
+        gp.log_marginal_likelihood(th, eval_gradient=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    n_lml = 5
+    for _ in range(n_lml):
+        gp.log_marginal_likelihood(th, eval_gradient=True)
+    torch.cuda.synchronize()
+    lml_ms = 1e3 * (time.perf_counter() - t0) / n_lml
+
+    # ---- (4) candidate-branch information gain -------------------------------------------------------
+    B = wl["branches"]
+    xy, parent = synth_tree(B, W, seed)
+    tree = TreeArrays(xy[0], capacity=B + 1)
+    for k in range(1, B + 1):
+        tree.add(xy[k], int(parent[k]))
+    per = n // wl["agents"]
+    obs = [list(X[a * per:(a + 1) * per]) for a in range(wl["agents"])]
+    ctx = ScoreContext(src, xy[0], obs, 0, 1.0, (0, W, 0, W), [])
+    scorer = GpuScorer()
+    for _ in range(3):
+        info = scorer.tree_information(3, tree, ctx)
+    barrier()
+    t0 = time.perf_counter()
+    reps = 10
+    for _ in range(reps):
+        info = scorer.tree_information(3, tree, ctx)  # host arrays in, host array out
+    barrier()
+    br_e2e = B * reps / (time.perf_counter() - t0)
+    br_dev_ms = scorer.time_device_pass(3, tree, ctx, reps=20)
+    if world > 1:
+        t = torch.tensor([br_dev_ms, 1.0 / br_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        br_dev_ms, br_e2e = float(t[0]), 1.0 / float(t[1])
+    if sampler:
+        sampler.stop()
+
+    if rank == 0:
+        peak64, src64 = fp64_peak_tflops()
+        hbm, srchbm = hbm_peak_gbs()
+        flops = float(Gpts) * (float(n) * n + 4.0 * n)  # n^2 (triangular solve) + 4n per point
+        ach = flops / (ms_post * 1e-3) / 1e12
+        cpu_post = cpu_posterior_leg(wl, 0, args.cpu_sample or max(2048, min(20000, int(2.0e7 / n))), 2, 1)
+        cpu_br = cpu_branch_leg(wl, 0, 16 if n >= 2000 else 64)
+        line = {
+            "metric": METRIC, "value": world * Gpts / (ms_post * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_post, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload + " -- " + wl["desc"], "n_measurements": n, "grid": [nx, ny],
+                       "theta_c_l": list(THETA), "parallelism": f"{world} independent rounds, one per GPU",
+                       "l2": ("flushed between timed iterations" if flush is not None else
+                              f"no flush: state {state_bytes >> 20} MiB + outputs {24 * Gpts >> 20} MiB exceed L2 (126 MiB)")},
+            "e2e": {"value": world * Gpts / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": 24 * n, "d2h_bytes_per_step": 16 * Gpts,
+                    "call": "PointSourceField.predict_spatial_field(waypoints, measurements) at fixed theta: upload, "
+                            "Gram + Cholesky + inverse + alpha, lattice posterior, pinned read-back of Z_pred and std"},
+            "gpu_launches": n_launch,
+            "roofline": {"bound": "tensor", "achieved": ach, "peak": peak64, "unit": "TFLOP/s", "frac": ach / peak64,
+                         "traffic": None, "kernel": "posterior_kernel<GRID>", "flops_per_launch": flops,
+                         "peak_source": src64 + " (fp64 DMMA; tcgen05 has no fp64 MMA)"},
+            "roofline_hbm": {"bound": "hbm", "achieved": 24.0 * Gpts / (ms_post * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                             "frac": 24.0 * Gpts / (ms_post * 1e-3) / 1e9 / hbm, "peak_source": srchbm,
+                             "note": "24 B written per point; the kernel is fp64-compute bound by n^2/24 flop/B"},
+            "cpu_baseline": {"value": cpu_post["pts_per_s"], "unit": UNIT, "cores": cpu_post["cores"], "kind": "port",
+                             "sample": f"{cpu_post['sample_pts']} lattice points per step through scikit-learn "
+                                       f"GaussianProcessRegressor.predict(return_std=True), fixed theta, n = {n}"},
+            "fit": {"lml_grad_eval_ms": lml_ms, "lml_grad_evals_per_s": 1e3 / lml_ms,
+                    "tflops": float(NP) ** 3 / (lml_ms * 1e-3) / 1e12},
+            "branch_gain": {"value": world * B / (br_dev_ms * 1e-3), "unit": "branch evals/s", "ms_per_batch": br_dev_ms,
+                            "branches": B, "variant": "point_source_gain_all", "observations": n,
+                            "e2e": {"value": world * br_e2e, "unit": "branch evals/s"},
+                            "cpu_baseline": {"value": cpu_br["evals_per_s"], "cores": 1, "kind": "port",
+                                             "sample": f"{cpu_br['sample_branches']} branches, pure-Python gain function"}},
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=0, help="lattice points per CPU-baseline step")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world == 1 and args.gpus > 1:
+        # not under torchrun: re-launch one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr",
+               "127.0.0.1", "--master-port", "29531", os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl, rank, world)
+    else:
+        run_b200(args, wl, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

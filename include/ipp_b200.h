@@ -63,12 +63,16 @@ int ipp_gp_fit_final(const double* X, const double* y, int n, const double* hyp,
  * y = linspace(y0, y1, ny), index = iy * nx + ix (point_source.py:65-67,350).  Outputs are indexed
  * from 0 (slab-local).  zpred (nullable) receives 10**mean (point_source.py:352); neg_count
  * (nullable, int*) counts variances clamped at 0 (_gpr.py:485-491).
+ * tables (nullable): caller-owned scratch of (nx + ny) * NP doubles (NP = ipp_gp_layout out[0]).  When
+ * given and nx >= 128 the lattice fast path is used: the RBF cross-covariance factorises over the
+ * lattice axes, so two coordinate tables replace the G x n exponentials; without it every element of
+ * k* is evaluated with exp() like the explicit-point entry below.
  * Replaces gp.predict(r, return_std=True) on the workspace grid: point_source.py:350-351 ->
  * sklearn _gpr.py:446-500, without materialising K_trans (G x n) or V (n x G). */
 int ipp_gp_posterior_grid(const double* Wbuf, const double* vbuf, int n, double c, double l, double y_mean,
                           double y_std, double x0, double x1, int nx, double y0, double y1, int ny,
                           long long g_begin, long long g_end, double* mean, double* std, double* zpred,
-                          int* neg_count, int max_ctas, void* stream);
+                          int* neg_count, double* tables, int max_ctas, void* stream);
 
 /* Same posterior at m explicit query points Q (m x 2).
  * Replaces gp.predict(leaf_points, return_std=True): src/rrt/rrt_thread.py:375. */

@@ -96,11 +96,11 @@ __global__ void __launch_bounds__(PC::THREADS, 1) posterior_kernel(PostArgs a) {
           }
           v[kk] = val;
         }
-        double2* dst = reinterpret_cast<double2*>(s + p * KPAD + h * 8);
+        // k-major tile: consecutive threads (queries) hit consecutive 8-byte banks
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) dst[kk] = make_double2(v[2 * kk], v[2 * kk + 1]);
+        for (int kk = 0; kk < 8; ++kk) s[(h * 8 + kk) * (QT + 4) + p] = v[kk];
       };
-      gemm_mainloop<PC, Lay::KCONT, Lay::KCONT>(acc, smem, 0, kend, fillA, fillB);
+      gemm_mainloop<PC, Lay::KCONT, Lay::MCONT>(acc, smem, 0, kend, fillA, fillB);
 #pragma unroll
       for (int mi = 0; mi < PC::MI; ++mi)
 #pragma unroll
@@ -144,8 +144,204 @@ __global__ void __launch_bounds__(PC::THREADS, 1) posterior_kernel(PostArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Lattice fast path.  On the workspace lattice the RBF cross-covariance factorises,
+//   k*(q, j) = [c exp(-(qy - yj)^2 / 2l^2)] * [exp(-(qx - xj)^2 / 2l^2)] = Ey[iy][j] * Ex[ix][j],
+// and a lattice has only nx + ny distinct coordinates: two small tables (nx x NP and ny x NP) replace
+// the G x n exponentials (each of which the generic kernel re-evaluates once per 128-row block of W).
+// The B operand then arrives by cp.async exactly like W: a tile of 128 Ex rows plus the two Ey rows a
+// 128-query tile can touch (nx >= 128), multiplied together when the fragment is read from shared
+// memory.  The main loop is a uniform 4-stage async pipeline flattened over (row block, k slab), so
+// the fp64 pipe sees DMMAs back to back instead of alternating with latency-bound exp() phases.
+// ---------------------------------------------------------------------------------------------
+constexpr int SEP_STAGES = 4;
+constexpr int SEP_A = PC::BM * KPAD;
+constexpr int SEP_B = QT * KPAD;
+constexpr int SEP_E = 2 * BK;
+constexpr int SEP_STAGE = SEP_A + SEP_B + SEP_E;
+constexpr size_t SEP_SMEM = sizeof(double) * SEP_STAGES * SEP_STAGE;
+
+// T[i][k] = scale * exp(-0.5 * (q_i / l - xs_k)^2) for lattice coordinate i in [i_begin, i_begin + gridDim.y),
+// k < n; zero for the padded k.  q_i follows np.linspace.
+__global__ void __launch_bounds__(256) axis_table_kernel(const double* __restrict__ xs, int n, int np, double l, double q0,
+                                                         double q1, double qstep, int nq, double scale, int i_begin,
+                                                         double* __restrict__ T, long ldt) {
+  const int i = i_begin + blockIdx.y;
+  const int k = blockIdx.x * 256 + threadIdx.x;
+  if (k >= np || i >= nq) return;
+  const double q = (i == nq - 1 && nq > 1) ? q1 : __dadd_rn(__dmul_rn((double)i, qstep), q0);
+  double v = 0.0;
+  if (k < n) {
+    const double d = __dsub_rn(__ddiv_rn(q, l), xs[k]);
+    v = __dmul_rn(exp(__dmul_rn(-0.5, __dmul_rn(d, d))), scale);
+  }
+  T[(long)i * ldt + k] = v;
+}
+
+__global__ void __launch_bounds__(PC::THREADS, 1) posterior_lattice_kernel(PostArgs a, const double* __restrict__ Ex,
+                                                                            const double* __restrict__ Ey, long ldt) {
+  extern __shared__ __align__(16) double smem[];
+  __shared__ double red[PC::WARPS_M][QT];
+  __shared__ double mred[2][QT];
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int wm = warp / PC::WARPS_N, wn = warp % PC::WARPS_N;
+  const int g = lane >> 2, tg = lane & 3;
+  const int p = t & (QT - 1), h = t >> 7;
+  const long total = a.g_end - a.g_begin;
+  const long ntiles = (total + QT - 1) / QT;
+  const int nrb = (a.np + PC::BM - 1) / PC::BM;
+  int tot = 0;  // pipeline iterations per tile
+  for (int rb = 0; rb < nrb; ++rb) tot += min((rb + 1) * PC::BM, a.np) / BK;
+
+  for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long gq0 = a.g_begin + tile * QT;
+    const int iy0 = (int)(gq0 / a.nx), ix0 = (int)(gq0 % a.nx);
+    const int iy1 = min(iy0 + 1, a.ny - 1);
+    const int nvalid = (int)min((long)QT, a.g_end - gq0);
+    bool sel[PC::NI];  // does my B column fall on the tile's second lattice row?
+#pragma unroll
+    for (int ni = 0; ni < PC::NI; ++ni) sel[ni] = (ix0 + wn * PC::WTN + ni * 8 + g) >= a.nx;
+    const int prow = (ix0 + p >= a.nx) ? BK : 0;
+
+    int prb = 0, pk = 0;
+    auto produce = [&](int stage) {
+      double* s = smem + stage * SEP_STAGE;
+      load_tile_async<PC::BM, Lay::KCONT, PC::THREADS>(s, a.W, a.ldw, prb * PC::BM, pk, a.np, a.np);
+#pragma unroll
+      for (int it = 0; it < QT * BK / 2 / PC::THREADS; ++it) {
+        const int c = t + it * PC::THREADS;
+        const int r = c / (BK / 2), kc = (c % (BK / 2)) * 2;
+        int ix = ix0 + min(r, nvalid - 1);
+        if (ix >= a.nx) ix -= a.nx;
+        cp_async16(s + SEP_A + r * KPAD + kc, Ex + (long)ix * ldt + pk + kc, true);
+      }
+      if (t < BK) {
+        const int row = t >> 3, kc = (t & 7) * 2;
+        cp_async16(s + SEP_A + SEP_B + row * BK + kc, Ey + (long)(row ? iy1 : iy0) * ldt + pk + kc, true);
+      }
+      pk += BK;
+      if (pk >= min((prb + 1) * PC::BM, a.np)) {
+        pk = 0;
+        ++prb;
+      }
+    };
+
+    double acc[PC::MI][PC::NI][2];
+    zero_acc<PC>(acc);
+    double csq[PC::NI][2];
+#pragma unroll
+    for (int ni = 0; ni < PC::NI; ++ni) csq[ni][0] = csq[ni][1] = 0.0;
+    double mean_part = 0.0;
+    int crb = 0, ck = 0;
+
+#pragma unroll
+    for (int s = 0; s < SEP_STAGES - 1; ++s) {
+      if (s < tot) produce(s);
+      cp_async_commit();
+    }
+    for (int it = 0; it < tot; ++it) {
+      cp_async_wait<SEP_STAGES - 2>();
+      __syncthreads();
+      const int nxt = it + SEP_STAGES - 1;
+      if (nxt < tot) produce(nxt % SEP_STAGES);
+      cp_async_commit();
+      const double* sA = smem + (it % SEP_STAGES) * SEP_STAGE;
+      const double* sB = sA + SEP_A;
+      const double* sE = sB + SEP_B;
+#pragma unroll
+      for (int kk = 0; kk < BK; kk += 4) {
+        const double e0 = sE[kk + tg], e1 = sE[BK + kk + tg];
+        double af[PC::MI], bf[PC::NI];
+#pragma unroll
+        for (int mi = 0; mi < PC::MI; ++mi) af[mi] = sA[(wm * PC::WTM + mi * 8 + g) * KPAD + kk + tg];
+#pragma unroll
+        for (int ni = 0; ni < PC::NI; ++ni)
+          bf[ni] = __dmul_rn(sB[(wn * PC::WTN + ni * 8 + g) * KPAD + kk + tg], sel[ni] ? e1 : e0);
+#pragma unroll
+        for (int mi = 0; mi < PC::MI; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < PC::NI; ++ni) dmma884(acc[mi][ni], af[mi], bf[ni]);
+      }
+      if (crb == nrb - 1) {  // the last row block sees every k slab once: the mean rides along there
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const int k = h * 8 + kk;
+          mean_part += __ldg(a.alpha + ck + k) * __dmul_rn(sB[p * KPAD + k], sE[prow + k]);
+        }
+      }
+      ck += BK;
+      if (ck >= min((crb + 1) * PC::BM, a.np)) {  // row block finished: fold its rows into the column norms
+#pragma unroll
+        for (int mi = 0; mi < PC::MI; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < PC::NI; ++ni) {
+            csq[ni][0] += acc[mi][ni][0] * acc[mi][ni][0];
+            csq[ni][1] += acc[mi][ni][1] * acc[mi][ni][1];
+            acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+          }
+        ck = 0;
+        ++crb;
+      }
+    }
+    cp_async_wait<0>();
+#pragma unroll
+    for (int ni = 0; ni < PC::NI; ++ni)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        double v = csq[ni][e];
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        if (g == 0) red[wm][wn * PC::WTN + ni * 8 + tg * 2 + e] = v;
+      }
+    mred[h][p] = mean_part;
+    __syncthreads();
+    if (t < nvalid) {
+      double ss = 0.0;
+#pragma unroll
+      for (int w = 0; w < PC::WARPS_M; ++w) ss += red[w][t];
+      const double mu = a.y_std * (mred[0][t] + mred[1][t]) + a.y_mean;
+      double var = a.c - ss;
+      if (var < 0.0) {
+        var = 0.0;
+        if (a.neg_count) atomicAdd(a.neg_count, 1);
+      }
+      const long o = gq0 + t - a.g_begin;
+      a.mean[o] = mu;
+      a.std[o] = sqrt(var * (a.y_std * a.y_std));
+      if (a.zpred) a.zpred[o] = pow(10.0, mu);
+    }
+    __syncthreads();
+  }
+}
+
+static int launch_lattice(PostArgs& a, double* tables, int max_ctas, cudaStream_t st) {
+  const long total = a.g_end - a.g_begin;
+  if (total <= 0) return IPP_OK;
+  const long ldt = a.np;
+  double* Ex = tables;
+  double* Ey = tables + (long)a.nx * ldt;
+  const int iy_lo = (int)(a.g_begin / a.nx);
+  const int iy_hi = (int)min((long)a.ny - 1, (a.g_end - 1) / a.nx + 1);  // +1: a tile may read the next row
+  const int kb = (a.np + 255) / 256;
+  axis_table_kernel<<<dim3(kb, a.nx), 256, 0, st>>>(a.xs, a.n, a.np, a.l, a.x0, a.x1, a.xstep, a.nx, 1.0, 0, Ex, ldt);
+  axis_table_kernel<<<dim3(kb, iy_hi - iy_lo + 1), 256, 0, st>>>(a.ys, a.n, a.np, a.l, a.y0, a.y1, a.ystep, a.ny, a.c, iy_lo,
+                                                                  Ey, ldt);
+  const long ntiles = (total + QT - 1) / QT;
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) != cudaSuccess) return IPP_ERR_CUDA;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return IPP_ERR_CUDA;
+  int ctas = (int)(ntiles < (long)sms ? ntiles : (long)sms);
+  if (max_ctas > 0 && ctas > max_ctas) ctas = max_ctas;
+  if (cudaFuncSetAttribute(posterior_lattice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEP_SMEM) != cudaSuccess)
+    return IPP_ERR_CUDA;
+  posterior_lattice_kernel<<<ctas, PC::THREADS, SEP_SMEM, st>>>(a, Ex, Ey, ldt);
+  IPP_LAUNCH_CHECK();
+  return IPP_OK;
+}
+
 static int launch_posterior(PostArgs& a, bool grid, int max_ctas, cudaStream_t st) {
-  constexpr size_t SM = gemm_smem_bytes<PC, Lay::KCONT, Lay::KCONT>();
+  constexpr size_t SM = gemm_smem_bytes<PC, Lay::KCONT, Lay::MCONT>();
   const long total = a.g_end - a.g_begin;
   if (total <= 0) return IPP_OK;
   const long ntiles = (total + QT - 1) / QT;
@@ -193,7 +389,7 @@ extern "C" {
 int ipp_gp_posterior_grid(const double* Wbuf, const double* vbuf, int n, double c, double l, double y_mean,
                           double y_std, double x0, double x1, int nx, double y0, double y1, int ny,
                           long long g_begin, long long g_end, double* mean, double* std, double* zpred,
-                          int* neg_count, int max_ctas, void* stream) {
+                          int* neg_count, double* tables, int max_ctas, void* stream) {
   if (!Wbuf || !vbuf || n <= 0 || nx <= 0 || ny <= 0 || !mean || !std || !(l > 0.0)) return IPP_ERR_ARG;
   if (g_begin < 0 || g_end > (long long)nx * ny || g_begin > g_end) return IPP_ERR_ARG;
   PostArgs a{};
@@ -213,6 +409,7 @@ int ipp_gp_posterior_grid(const double* Wbuf, const double* vbuf, int n, double 
   a.std = std;
   a.zpred = zpred;
   a.neg_count = neg_count;
+  if (tables && nx >= QT) return launch_lattice(a, tables, max_ctas, (cudaStream_t)stream);
   return launch_posterior(a, true, max_ctas, (cudaStream_t)stream);
 }
 
@@ -233,6 +430,6 @@ int ipp_gp_posterior_points(const double* Wbuf, const double* vbuf, int n, doubl
   return launch_posterior(a, false, max_ctas, (cudaStream_t)stream);
 }
 
-int ipp_abi_version(void) { return 1; }
+int ipp_abi_version(void) { return 2; }
 
 }  // extern "C"

@@ -175,6 +175,15 @@ class _Workspace:
         off = self.layout[8]
         return self.v[off:off + 8]
 
+    def pinned(self, name, numel):
+        """Reusable page-locked staging buffer (fp64) of at least `numel` elements."""
+        torch = _lib.require_cuda()
+        buf = getattr(self, "_pin_" + name, None)
+        if buf is None or buf.numel() < numel:
+            buf = torch.empty(max(int(numel), 1), dtype=torch.float64).pin_memory()
+            setattr(self, "_pin_" + name, buf)
+        return buf[:numel]
+
 
 class GaussianProcessRegressor:
     """Drop-in for sklearn.gaussian_process.GaussianProcessRegressor on the reference's call sites."""
@@ -211,8 +220,15 @@ class GaussianProcessRegressor:
 
     def _upload_training(self, X, yn):
         torch = _lib.require_cuda()
-        self._Xd = torch.from_numpy(X).cuda()
-        self._yd = torch.from_numpy(np.ascontiguousarray(yn)).cuda()
+        n = X.shape[0]
+        stage = self._ws.pinned("train", 3 * n)  # one pinned buffer, one H2D copy: [X (n x 2) | y (n)]
+        stage[: 2 * n].view(n, 2).copy_(torch.from_numpy(X))
+        stage[2 * n:].copy_(torch.from_numpy(np.ascontiguousarray(yn)))
+        dev = torch.empty(3 * n, dtype=torch.float64, device="cuda")
+        dev.copy_(stage, non_blocking=True)
+        self._Xd = dev[: 2 * n].view(n, 2)
+        self._yd = dev[2 * n:]
+        self.h2d_bytes_ = 24 * n
 
     def _eval_device(self, c, l, with_grad, final=False):
         """Launch one LML (+gradient) evaluation or the final factorisation; returns the 8-double
@@ -419,7 +435,35 @@ class GaussianProcessRegressor:
             self._warn_negative(neg)
         return mean, std, zp
 
-    def predict_grid_device(self, x0, x1, nx, y0, y1, ny, g_begin=0, g_end=None, want_zpred=True, out=None):
+    def predict_grid_host(self, x0, x1, nx, y0, y1, ny, g_begin=0, g_end=None):
+        """Fused lattice posterior returned as fresh host arrays (zpred, std): device outputs are
+        read back through one pinned staging buffer (2 * m doubles, one D2H copy)."""
+        torch = _lib.require_cuda()
+        g_end = nx * ny if g_end is None else g_end
+        m = int(g_end - g_begin)
+        out = torch.empty(3 * m, dtype=torch.float64, device="cuda")  # [std | zpred | mean]
+        self.predict_grid_device(x0, x1, nx, y0, y1, ny, g_begin, g_end, want_zpred=True,
+                                 out=(out[2 * m:], out[:m], out[m:2 * m]))
+        stage = self._ws.pinned("grid", 2 * m)
+        stage.copy_(out[: 2 * m], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        self._warn_negative(self._neg_counter)
+        host = stage.numpy()
+        self.d2h_bytes_ = 16 * m
+        return host[m:].copy(), host[:m].copy()
+
+    def _lattice_tables(self, nx, ny):
+        """Scratch for the lattice fast path of ipp_gp_posterior_grid: (nx + ny) * NP doubles."""
+        torch = _lib.require_cuda()
+        need = (int(nx) + int(ny)) * self._ws.layout[0]
+        buf = getattr(self._ws, "tables", None)
+        if buf is None or buf.numel() < need:
+            buf = torch.empty(need, dtype=torch.float64, device="cuda")
+            self._ws.tables = buf
+        return buf
+
+    def predict_grid_device(self, x0, x1, nx, y0, y1, ny, g_begin=0, g_end=None, want_zpred=True, out=None,
+                            lattice=True):
         """Fused posterior over flat lattice indices [g_begin, g_end) (index = iy * nx + ix).
         Returns device tensors (mean, std, zpred) of length g_end - g_begin."""
         torch = _lib.require_cuda()
@@ -434,9 +478,11 @@ class GaussianProcessRegressor:
             mean, std, zp = out
         neg = torch.zeros(1, dtype=torch.int32, device="cuda")
         if m:
-            rc = lib.ipp_gp_posterior_grid(*self._posterior_args(), float(x0), float(x1), int(nx), float(y0), float(y1),
+            args = self._posterior_args()
+            tables = self._lattice_tables(nx, ny) if (lattice and nx >= 128) else None
+            rc = lib.ipp_gp_posterior_grid(*args, float(x0), float(x1), int(nx), float(y0), float(y1),
                                            int(ny), int(g_begin), int(g_end), _lib.ptr(mean), _lib.ptr(std),
-                                           _lib.ptr(zp), _lib.ptr(neg), 0, _lib.stream_ptr())
+                                           _lib.ptr(zp), _lib.ptr(neg), _lib.ptr(tables), 0, _lib.stream_ptr())
             _lib.check(rc, "ipp_gp_posterior_grid")
-            self._neg_counter = neg
+        self._neg_counter = neg
         return mean, std, zp

@@ -212,9 +212,7 @@ class PointSourceField:
 
                 z, std = sharded_grid_posterior(gp, w, nx, ny, self.grid_group)
             else:
-                _, std_d, z_d = gp.predict_grid_device(w[0], w[1], nx, w[2], w[3], ny, want_zpred=True)
-                z, std = z_d.cpu().numpy(), std_d.cpu().numpy()
-                gp._warn_negative(gp._neg_counter)
+                z, std = gp.predict_grid_host(w[0], w[1], nx, w[2], w[3], ny)
             return z.reshape(self.X.shape), std
         # generic estimator (the CPU test seam): the reference's own three lines
         r = np.column_stack((self.X.ravel(), self.Y.ravel()))

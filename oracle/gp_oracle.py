@@ -183,3 +183,12 @@ def sklearn_reference_gp(c0=1.0, l0=1.0):
 
     k = C(c0, C_BOUNDS) * RBF(l0, L_BOUNDS)
     return GaussianProcessRegressor(kernel=k, n_restarts_optimizer=N_RESTARTS, normalize_y=True)
+
+
+def sklearn_fixed_theta_gp(c=1.0, l=1.0):
+    """Same estimator with the hyper-parameters held at (c, l) (`optimizer=None`): the posterior-only
+    leg of bench.py, so the CPU and GPU arms evaluate the posterior at the same theta."""
+    from sklearn.gaussian_process import GaussianProcessRegressor
+    from sklearn.gaussian_process.kernels import RBF, ConstantKernel as C
+
+    return GaussianProcessRegressor(kernel=C(c, C_BOUNDS) * RBF(l, L_BOUNDS), optimizer=None, normalize_y=True)
