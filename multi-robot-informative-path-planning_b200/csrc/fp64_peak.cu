@@ -104,6 +104,120 @@ __global__ void k_dmma16816(double* out, double a, double b) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// The posterior kernel's occupancy: ONE 256-thread CTA per SM (2 warps per scheduler), 32 independent
+// accumulator tiles per warp (warp tile 64 x 32), operands re-read every k-step.
+__global__ void __launch_bounds__(256, 1) k_dmma884_tile(double* out, double a, double b) {
+  double d[8][4][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) d[i][j][0] = d[i][j][1] = threadIdx.x;
+  for (int it = 0; it < ITERS; ++it) {
+    double af[8], bf[4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) af[i] = a + it * 1e-9 + i;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bf[j] = b + it * 1e-9 + j;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                     : "+d"(d[i][j][0]), "+d"(d[i][j][1])
+                     : "d"(af[i]), "d"(bf[j]));
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s += d[i][j][0] + d[i][j][1];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// Same tile, operands read from shared memory with the kernel's fragment pattern (12 LDS per 32 DMMA).
+__global__ void __launch_bounds__(256, 1) k_dmma884_tile_lds(double* out, double a, double b) {
+  __shared__ double sA[128 * 20], sB[128 * 20];
+  for (int e = threadIdx.x; e < 128 * 20; e += 256) {
+    sA[e] = a + e * 1e-9;
+    sB[e] = b + e * 1e-9;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wm = warp >> 2, wn = warp & 3, g = lane >> 2, tg = lane & 3;
+  double d[8][4][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) d[i][j][0] = d[i][j][1] = threadIdx.x;
+  for (int it = 0; it < ITERS / 4; ++it) {
+#pragma unroll
+    for (int kk = 0; kk < 16; kk += 4) {
+      double af[8], bf[4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) af[i] = sA[(wm * 64 + i * 8 + g) * 20 + kk + tg];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bf[j] = sB[(wn * 32 + j * 8 + g) * 20 + kk + tg];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                       : "+d"(d[i][j][0]), "+d"(d[i][j][1])
+                       : "d"(af[i]), "d"(bf[j]));
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s += d[i][j][0] + d[i][j][1];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// Same 64 x 32 warp tile from m16n8k16 instructions (16 per k16-step), operands from shared memory.
+__global__ void __launch_bounds__(256, 1) k_dmma16816_tile_lds(double* out, double a, double b) {
+  __shared__ double sA[128 * 20], sB[128 * 20];
+  for (int e = threadIdx.x; e < 128 * 20; e += 256) {
+    sA[e] = a + e * 1e-9;
+    sB[e] = b + e * 1e-9;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wm = warp >> 2, wn = warp & 3, g = lane >> 2, tg = lane & 3;
+  double d[4][4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) d[i][j][e] = threadIdx.x;
+  for (int it = 0; it < ITERS / 4; ++it) {
+    double af[4][8], bf[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) af[i][e] = sA[(wm * 64 + i * 16 + g + 8 * (e & 1)) * 20 + tg + 4 * (e >> 1)];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) bf[j][e] = sB[(wn * 32 + j * 8 + g) * 20 + tg + 4 * e];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        asm volatile(
+            "mma.sync.aligned.m16n8k16.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7,%8,%9,%10,%11}, "
+            "{%12,%13,%14,%15}, {%0,%1,%2,%3};\n"
+            : "+d"(d[i][j][0]), "+d"(d[i][j][1]), "+d"(d[i][j][2]), "+d"(d[i][j][3])
+            : "d"(af[i][0]), "d"(af[i][1]), "d"(af[i][2]), "d"(af[i][3]), "d"(af[i][4]), "d"(af[i][5]), "d"(af[i][6]),
+              "d"(af[i][7]), "d"(bf[j][0]), "d"(bf[j][1]), "d"(bf[j][2]), "d"(bf[j][3]));
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s += d[i][j][0] + d[i][j][1] + d[i][j][2] + d[i][j][3];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 // fp64 exp throughput (the K* generation cost)
 __global__ void k_dexp(double* out, double a) {
   double x[8];
@@ -158,6 +272,15 @@ int main() {
   printf(", \"dmma1688_tflops\": %.2f", 2.0 * 1024 * 8 * ITERS * nwarps / (t * 1e-3) / 1e12);
   t = time_ms([&] { k_dmma16816<<<blocks, threads>>>(out, 1e-9, 0.999); }, 10);
   printf(", \"dmma16816_tflops\": %.2f", 2.0 * 2048 * 8 * ITERS * nwarps / (t * 1e-3) / 1e12);
+  {
+    const double w1 = (double)sms * 8;  // warps with one 256-thread CTA per SM
+    t = time_ms([&] { k_dmma884_tile<<<sms, 256>>>(out, 1e-9, 0.999); }, 10);
+    printf(", \"dmma884_1cta_tile_tflops\": %.2f", 2.0 * 256 * 32 * ITERS * w1 / (t * 1e-3) / 1e12);
+    t = time_ms([&] { k_dmma884_tile_lds<<<sms, 256>>>(out, 1e-9, 0.999); }, 10);
+    printf(", \"dmma884_1cta_tile_lds_tflops\": %.2f", 2.0 * 256 * 32 * ITERS * w1 / (t * 1e-3) / 1e12);
+    t = time_ms([&] { k_dmma16816_tile_lds<<<sms, 256>>>(out, 1e-9, 0.999); }, 10);
+    printf(", \"dmma16816_1cta_tile_lds_tflops\": %.2f", 2.0 * 2048 * 16 * (ITERS / 4) * w1 / (t * 1e-3) / 1e12);
+  }
   t = time_ms([&] { k_dexp<<<blocks, threads>>>(out, 0.5); }, 10);
   printf(", \"dexp_gops\": %.2f", 8.0 * (ITERS / 8) * nthreads / (t * 1e-3) / 1e9);
   printf("}\n");

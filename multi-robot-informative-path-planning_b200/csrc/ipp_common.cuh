@@ -41,6 +41,36 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
 }
 
+// ---- mbarrier helpers (shared::cta).  Used by the lattice posterior pipeline, where each stage has a
+// "full" barrier (completed by every thread's cp.async group through cp.async.mbarrier.arrive.noinc)
+// and an "empty" barrier (one arrival per consumer warp), instead of a CTA-wide __syncthreads per slab.
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+// Arrive on `bar` once all cp.async issued so far by this thread have landed (does not add to the
+// expected count: the barrier is initialised with one expected arrival per producing thread).
+__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "MBAR_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra MBAR_DONE_%=;\n"
+      "bra MBAR_WAIT_%=;\n"
+      "MBAR_DONE_%=:\n"
+      "}\n" ::"r"(a),
+      "r"(parity)
+      : "memory");
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -183,6 +183,7 @@ __global__ void __launch_bounds__(PC::THREADS, 1) posterior_lattice_kernel(PostA
   extern __shared__ __align__(16) double smem[];
   __shared__ double red[PC::WARPS_M][QT];
   __shared__ double mred[2][QT];
+  __shared__ __align__(8) uint64_t bar_full[SEP_STAGES], bar_empty[SEP_STAGES];
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int wm = warp / PC::WARPS_N, wn = warp % PC::WARPS_N;
   const int g = lane >> 2, tg = lane & 3;
@@ -190,8 +191,18 @@ __global__ void __launch_bounds__(PC::THREADS, 1) posterior_lattice_kernel(PostA
   const long total = a.g_end - a.g_begin;
   const long ntiles = (total + QT - 1) / QT;
   const int nrb = (a.np + PC::BM - 1) / PC::BM;
-  int tot = 0;  // pipeline iterations per tile
+  int tot = 0;  // pipeline iterations (k slabs summed over the row blocks) per tile
   for (int rb = 0; rb < nrb; ++rb) tot += min((rb + 1) * PC::BM, a.np) / BK;
+  if (t == 0) {
+    for (int s = 0; s < SEP_STAGES; ++s) {
+      mbar_init(&bar_full[s], PC::THREADS);       // one cp.async-completion arrival per thread
+      mbar_init(&bar_empty[s], PC::THREADS / 32);  // one arrival per consumer warp
+    }
+  }
+  __syncthreads();
+  // Slabs are numbered globally across tiles: slab G lives in stage G % STAGES and is that stage's
+  // (G / STAGES)-th use, which fixes the phase parity of both of its barriers.
+  unsigned gslab = 0;  // next slab this thread consumes
 
   for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long gq0 = a.g_begin + tile * QT;
@@ -204,7 +215,9 @@ __global__ void __launch_bounds__(PC::THREADS, 1) posterior_lattice_kernel(PostA
     const int prow = (ix0 + p >= a.nx) ? BK : 0;
 
     int prb = 0, pk = 0;
-    auto produce = [&](int stage) {
+    auto produce = [&](unsigned G) {
+      const unsigned stage = G % SEP_STAGES, use = G / SEP_STAGES;
+      if (use > 0) mbar_wait(&bar_empty[stage], (use - 1) & 1);  // every warp is done with the previous contents
       double* s = smem + stage * SEP_STAGE;
       load_tile_async<PC::BM, Lay::KCONT, PC::THREADS>(s, a.W, a.ldw, prb * PC::BM, pk, a.np, a.np);
 #pragma unroll
@@ -219,6 +232,7 @@ __global__ void __launch_bounds__(PC::THREADS, 1) posterior_lattice_kernel(PostA
         const int row = t >> 3, kc = (t & 7) * 2;
         cp_async16(s + SEP_A + SEP_B + row * BK + kc, Ey + (long)(row ? iy1 : iy0) * ldt + pk + kc, true);
       }
+      cp_async_mbar_arrive(&bar_full[stage]);
       pk += BK;
       if (pk >= min((prb + 1) * PC::BM, a.np)) {
         pk = 0;
@@ -234,18 +248,12 @@ __global__ void __launch_bounds__(PC::THREADS, 1) posterior_lattice_kernel(PostA
     double mean_part = 0.0;
     int crb = 0, ck = 0;
 
-#pragma unroll
-    for (int s = 0; s < SEP_STAGES - 1; ++s) {
-      if (s < tot) produce(s);
-      cp_async_commit();
-    }
-    for (int it = 0; it < tot; ++it) {
-      cp_async_wait<SEP_STAGES - 2>();
-      __syncthreads();
-      const int nxt = it + SEP_STAGES - 1;
-      if (nxt < tot) produce(nxt % SEP_STAGES);
-      cp_async_commit();
-      const double* sA = smem + (it % SEP_STAGES) * SEP_STAGE;
+    for (int s = 0; s < SEP_STAGES - 1; ++s)
+      if (s < tot) produce(gslab + s);
+    for (int it = 0; it < tot; ++it, ++gslab) {
+      const unsigned stage = gslab % SEP_STAGES;
+      mbar_wait(&bar_full[stage], (gslab / SEP_STAGES) & 1);
+      const double* sA = smem + stage * SEP_STAGE;
       const double* sB = sA + SEP_A;
       const double* sE = sB + SEP_B;
 #pragma unroll
@@ -269,6 +277,8 @@ __global__ void __launch_bounds__(PC::THREADS, 1) posterior_lattice_kernel(PostA
           mean_part += __ldg(a.alpha + ck + k) * __dmul_rn(sB[p * KPAD + k], sE[prow + k]);
         }
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_empty[stage]);  // this warp no longer reads the stage
       ck += BK;
       if (ck >= min((crb + 1) * PC::BM, a.np)) {  // row block finished: fold its rows into the column norms
 #pragma unroll
@@ -282,8 +292,10 @@ __global__ void __launch_bounds__(PC::THREADS, 1) posterior_lattice_kernel(PostA
         ck = 0;
         ++crb;
       }
+      // refill: the slab STAGES-1 ahead goes into the stage consumed one iteration ago, so the wait
+      // inside produce() is for work the other warps finished a whole slab earlier
+      if (it + SEP_STAGES - 1 < tot) produce(gslab + SEP_STAGES - 1);
     }
-    cp_async_wait<0>();
 #pragma unroll
     for (int ni = 0; ni < PC::NI; ++ni)
 #pragma unroll
