@@ -17,6 +17,8 @@
 //   hyp  = {c, l, jitter}          in DEVICE memory so a captured CUDA graph replays for any theta
 #include "ipp_gemm.cuh"
 #include "../../include/ipp_b200.h"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 namespace ipp {
 
@@ -122,116 +124,106 @@ __global__ void __launch_bounds__(256) gram_rbf_kernel(const double* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------
-// Cholesky panel step k (columns [64k, 64k+64)): diagonal factor + inverse (1 CTA), then the panel
-// solve (one CTA per 64-row block below), then the tensor-core trailing update.  The inverse of
-// the diagonal block doubles as the level-0 input of the triangular inverse, so it goes to Wbuf.
+// Blocked right-looking Cholesky as ONE persistent cooperative kernel (one CTA per SM, grid-wide
+// barriers between dependent phases) instead of three launches per 64-column panel:
+//   for panel k:   [grid barrier]  panel solve  A_ik <- A_ik L_kk^-T   (one CTA per 64-row block)
+//                  [grid barrier]  trailing update on the DMMA pipe    (lower tiles over all CTAs);
+//                                  the CTA that owns the tile holding block (k+1, k+1) updates it
+//                                  first and factors it at once, so the next diagonal factor
+//                                  overlaps the rest of the update instead of serialising the grid.
+// At n = 5000 that is 158 grid barriers instead of 237 dependent launches.
 // ---------------------------------------------------------------------------------------------
 constexpr int PSTR = BLK + 1;
 constexpr size_t PANEL_SMEM = sizeof(double) * 2 * BLK * PSTR;
 
-__device__ __forceinline__ void potf2_and_invert(double* D, double* Wt, int t, int first_index, double* info,
-                                                 bool report) {
-  // D: 64x64 (stride PSTR) symmetric input, lower part used; on exit lower = L, Wt[c][i] = inv(L)[i][c]
+// In-place Cholesky of a 64x64 block held in shared memory (stride PSTR, lower part used).
+template <int NT>
+__device__ __forceinline__ void potf2_block(double* D, int t, int first_index, double* info) {
   for (int j = 0; j < BLK; ++j) {
     const double piv = D[j * PSTR + j];
     __syncthreads();
     const double lj = sqrt(piv);
-    if (report && t == 0 && !(piv > 0.0) && info[0] == 0.0) info[0] = (double)(first_index + j + 1);
+    if (t == 0 && !(piv > 0.0) && info[0] == 0.0) info[0] = (double)(first_index + j + 1);
     if (t == j) D[j * PSTR + j] = lj;
     if (t > j && t < BLK) D[t * PSTR + j] = D[t * PSTR + j] / lj;
     __syncthreads();
     // trailing update of the lower triangle: D[r][c] -= D[r][j] * D[c][j], j < c <= r
-    const int m = BLK - 1 - j;  // trailing order
-    for (int e = t; e < m * m; e += 256) {
+    const int m = BLK - 1 - j;
+    for (int e = t; e < m * m; e += NT) {
       int r = j + 1 + e / m, cc = j + 1 + e % m;
       if (cc <= r) D[r * PSTR + cc] -= D[r * PSTR + j] * D[cc * PSTR + j];
     }
     __syncthreads();
   }
-  // inverse, 4 lanes per column
-  const int c = t >> 2, q = t & 3;
-  if (q == 0) {
-    for (int i = 0; i < c; ++i) Wt[c * PSTR + i] = 0.0;
-    Wt[c * PSTR + c] = 1.0 / D[c * PSTR + c];
-  }
-  __syncwarp();
-  for (int i = 1; i < BLK; ++i) {
-    double part = 0.0;
-    if (i > c)
-      for (int kk = c + q; kk < i; kk += 4) part += D[i * PSTR + kk] * Wt[c * PSTR + kk];
-    part += __shfl_xor_sync(0xffffffffu, part, 1);
-    part += __shfl_xor_sync(0xffffffffu, part, 2);
-    if (i > c && q == 0) Wt[c * PSTR + i] = -part / D[i * PSTR + i];
-    __syncwarp();
-  }
-  __syncthreads();
 }
 
-// Diagonal step: one CTA factors the 64x64 diagonal block of panel k in shared memory, inverts it,
-// and writes L_kk (clean lower) to A and W_kk to Winv.  A separate launch, so the blocks below
-// never observe a half-written diagonal block.
-__global__ void __launch_bounds__(256) chol_diag_kernel(double* __restrict__ A, long ld, int k, double* __restrict__ Winv,
-                                                        long ldw, double* __restrict__ info) {
-  extern __shared__ double psm[];
+template <int NT>
+__device__ __forceinline__ void chol_diag_step(double* __restrict__ A, long ld, int k, double* psm, double* info) {
   double* D = psm;
-  double* Wt = psm + BLK * PSTR;
   const int t = threadIdx.x, j0 = BLK * k;
-  for (int e = t; e < BLK * BLK; e += 256) {
+  for (int e = t; e < BLK * BLK; e += NT) {
     int r = e / BLK, cc = e % BLK;
     D[r * PSTR + cc] = A[(long)(j0 + r) * ld + j0 + cc];
   }
   __syncthreads();
-  potf2_and_invert(D, Wt, t, j0, info, true);
-  for (int e = t; e < BLK * BLK; e += 256) {
+  potf2_block<NT>(D, t, j0, info);
+  for (int e = t; e < BLK * BLK; e += NT) {
     int r = e / BLK, cc = e % BLK;
     A[(long)(j0 + r) * ld + j0 + cc] = (cc <= r) ? D[r * PSTR + cc] : 0.0;
-    Winv[(long)(j0 + r) * ldw + j0 + cc] = Wt[cc * PSTR + r];
   }
+  __syncthreads();
 }
 
-// Panel solve: A_ik <- A_ik * L_kk^-T for every 64-row block i below the diagonal, by forward
-// substitution (backward stable, unlike multiplying by the explicit inverse: at cond(K) ~ 1e11 the
-// diagonal blocks reach cond ~ 1e5 and the inverse route cost 5 digits of L).  One thread per row,
-// the row lives in registers, L_kk is broadcast from shared memory.
-constexpr size_t TRSM_SMEM = sizeof(double) * 2 * BLK * PSTR;
-__global__ void __launch_bounds__(BLK) chol_trsm_kernel(double* __restrict__ A, long ld, int k) {
-  extern __shared__ double psm[];
+// Panel solve of one 64-row block: A_ik <- A_ik * L_kk^-T by forward substitution (backward stable,
+// unlike multiplying by the explicit inverse: at cond(K) ~ 1e11 the diagonal blocks reach cond ~ 1e5 and
+// the inverse route cost 5 digits of L).  NT / 64 adjacent lanes share a row (columns interleaved), the
+// row lives in their registers, the solved entry is broadcast by shuffle, L_kk comes from shared memory.
+template <int NT>
+__device__ __forceinline__ void chol_trsm_block(double* __restrict__ A, long ld, int k, int i, double* psm) {
+  constexpr int LPR = NT / BLK;   // lanes per row
+  constexpr int CPL = BLK / LPR;  // columns per lane
   double* Ls = psm;
   double* Xs = psm + BLK * PSTR;
-  const int t = threadIdx.x, j0 = BLK * k;
-  const int i0 = j0 + BLK * (blockIdx.x + 1);
-  for (int e = t; e < BLK * BLK; e += BLK) {
+  const int t = threadIdx.x, j0 = BLK * k, i0 = BLK * i;
+  for (int e = t; e < BLK * BLK; e += NT) {
     int r = e / BLK, cc = e % BLK;
     Ls[r * PSTR + cc] = A[(long)(j0 + r) * ld + j0 + cc];
     Xs[r * PSTR + cc] = A[(long)(i0 + r) * ld + j0 + cc];
   }
   __syncthreads();
-  double x[BLK];
+  {
+    const int r = t / LPR, q0 = t % LPR, lane = t & 31;
+    double x[CPL];
 #pragma unroll
-  for (int c = 0; c < BLK; ++c) x[c] = Xs[t * PSTR + c];
+    for (int m = 0; m < CPL; ++m) x[m] = Xs[r * PSTR + q0 + m * LPR];
 #pragma unroll
-  for (int c = 0; c < BLK; ++c) {
-    x[c] = x[c] / Ls[c * PSTR + c];
+    for (int c = 0; c < BLK; ++c) {
+      const int owner = c % LPR, mc = c / LPR;
+      double xc = x[mc] / Ls[c * PSTR + c];  // meaningful in the owner lane only
+      xc = __shfl_sync(0xffffffffu, xc, (lane & ~(LPR - 1)) + owner);
+      if (q0 == owner) x[mc] = xc;
 #pragma unroll
-    for (int q = c + 1; q < BLK; ++q) x[q] -= x[c] * Ls[q * PSTR + c];
+      for (int m = 0; m < CPL; ++m) {
+        const int q = q0 + m * LPR;
+        if (q > c) x[m] -= xc * Ls[q * PSTR + c];
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < CPL; ++m) Xs[r * PSTR + q0 + m * LPR] = x[m];
   }
-#pragma unroll
-  for (int c = 0; c < BLK; ++c) Xs[t * PSTR + c] = x[c];
   __syncthreads();
-  for (int e = t; e < BLK * BLK; e += BLK) {
+  for (int e = t; e < BLK * BLK; e += NT) {
     int r = e / BLK, cc = e % BLK;
     A[(long)(i0 + r) * ld + j0 + cc] = Xs[r * PSTR + cc];
   }
+  __syncthreads();
 }
 
-// Trailing update after panel k: C[i][j] -= sum_p P[i][p] P[j][p] for i >= j >= r0 = 64(k+1).
+// Trailing update of one lower tile after panel k: C[i][j] -= sum_p P[i][p] P[j][p], i >= j >= 64(k+1).
 template <class C>
-__global__ void __launch_bounds__(C::THREADS) chol_syrk_kernel(double* __restrict__ A, long ld, int rows_total, int np,
-                                                               int k) {
-  extern __shared__ __align__(16) double smem[];
+__device__ __forceinline__ void chol_syrk_tile(double* __restrict__ A, long ld, int rows_total, int np, int k, int b,
+                                               double* smem) {
   const int j0 = BLK * k, r0 = j0 + BLK;
-  // decode lower-triangular tile index
-  const int b = blockIdx.x;
   int ti = (int)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
   while ((long)(ti + 1) * (ti + 2) / 2 <= b) ++ti;
   while ((long)ti * (ti + 1) / 2 > b) --ti;
@@ -251,6 +243,67 @@ __global__ void __launch_bounds__(C::THREADS) chol_syrk_kernel(double* __restric
     int gr = row0 + r, gc = col0 + c;
     if (gr < rows_total && gc < np && (gc >> 6) <= (gr >> 6)) A[(long)gr * ld + gc] -= v;
   });
+}
+
+template <class C>
+__global__ void __launch_bounds__(C::THREADS, 1) chol_coop_kernel(double* __restrict__ A, long ld, int rows_total, int np,
+                                                                  double* __restrict__ info) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ __align__(16) double smem[];
+  const int nb = np / BLK, nrb = rows_total / BLK;
+  if (blockIdx.x == 0) chol_diag_step<C::THREADS>(A, ld, 0, smem, info);
+  for (int k = 0; k < nb; ++k) {
+    grid.sync();  // L_kk is final
+    for (int i = k + 1 + blockIdx.x; i < nrb; i += gridDim.x) chol_trsm_block<C::THREADS>(A, ld, k, i, smem);
+    grid.sync();  // panel k is final
+    if (k + 1 < nb) {
+      const int rem = rows_total - BLK * (k + 1);
+      const int T = (rem + C::BM - 1) / C::BM;
+      const int ntile = T * (T + 1) / 2;
+      for (int b = blockIdx.x; b < ntile; b += gridDim.x) {
+        chol_syrk_tile<C>(A, ld, rows_total, np, k, b, smem);
+        if (b == 0) {  // tile 0 holds block (k+1, k+1): factor it now, behind the other CTAs' tiles
+          __syncthreads();
+          chol_diag_step<C::THREADS>(A, ld, k + 1, smem, info);
+        }
+      }
+    }
+  }
+}
+
+// W_kk = L_kk^-1 for every 64x64 diagonal block at once (level 0 of the triangular inverse).
+__global__ void __launch_bounds__(256) diag_inverse_kernel(const double* __restrict__ L, long ld, double* __restrict__ Winv,
+                                                           long ldw) {
+  extern __shared__ double psm[];
+  double* D = psm;
+  double* Wt = psm + BLK * PSTR;
+  const int t = threadIdx.x, j0 = BLK * blockIdx.x;
+  for (int e = t; e < BLK * BLK; e += 256) {
+    int r = e / BLK, cc = e % BLK;
+    D[r * PSTR + cc] = L[(long)(j0 + r) * ld + j0 + cc];
+  }
+  __syncthreads();
+  // Wt[c][i] = inv(L)[i][c]; 4 lanes per column, columns are independent
+  const int c = t >> 2, q = t & 3;
+  if (q == 0) {
+    for (int i = 0; i < c; ++i) Wt[c * PSTR + i] = 0.0;
+    Wt[c * PSTR + c] = 1.0 / D[c * PSTR + c];
+  }
+  __syncwarp();
+  for (int i = 1; i < BLK; ++i) {
+    double part = 0.0;
+    if (i > c)
+      for (int kk = c + q; kk < i; kk += 4) part += D[i * PSTR + kk] * Wt[c * PSTR + kk];
+    part += __shfl_xor_sync(0xffffffffu, part, 1);
+    part += __shfl_xor_sync(0xffffffffu, part, 2);
+    if (i > c && q == 0) Wt[c * PSTR + i] = -part / D[i * PSTR + i];
+    __syncwarp();
+  }
+  __syncthreads();
+  for (int e = t; e < BLK * BLK; e += 256) {
+    int r = e / BLK, cc = e % BLK;
+    Winv[(long)(j0 + r) * ldw + j0 + cc] = Wt[cc * PSTR + r];
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -458,18 +511,29 @@ static bool use_small_tiles(int np) { return np <= 1536; }
 
 template <class C>
 static int chol_inplace(double* Kb, double* Wb, double* info, const GpDims& d, cudaStream_t st) {
-  constexpr size_t SM = gemm_smem_bytes<C, Lay::KCONT, Lay::KCONT>();
-  if (opt_in_smem(chol_diag_kernel, PANEL_SMEM) != cudaSuccess) return IPP_ERR_CUDA;
-  if (opt_in_smem(chol_trsm_kernel, TRSM_SMEM) != cudaSuccess) return IPP_ERR_CUDA;
-  if (opt_in_smem(chol_syrk_kernel<C>, SM) != cudaSuccess) return IPP_ERR_CUDA;
-  const int nb = d.np / BLK;
-  for (int k = 0; k < nb; ++k) {
-    const int blocks_below = d.rows / BLK - k - 1;
-    chol_diag_kernel<<<1, 256, PANEL_SMEM, st>>>(Kb, d.ld, k, Wb, d.ld, info);
-    chol_trsm_kernel<<<blocks_below, BLK, TRSM_SMEM, st>>>(Kb, d.ld, k);
-    const int rem = d.rows - BLK * (k + 1);
-    const int T = (rem + C::BM - 1) / C::BM;
-    if (k + 1 < nb) chol_syrk_kernel<C><<<T * (T + 1) / 2, C::THREADS, SM, st>>>(Kb, d.ld, d.rows, d.np, k);
+  constexpr size_t SYRK_SM = gemm_smem_bytes<C, Lay::KCONT, Lay::KCONT>();
+  constexpr size_t SM = SYRK_SM > PANEL_SMEM ? SYRK_SM : PANEL_SMEM;
+  if (opt_in_smem(chol_coop_kernel<C>, SM) != cudaSuccess) return IPP_ERR_CUDA;
+  int dev = 0, sms = 0, per_sm = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return IPP_ERR_CUDA;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return IPP_ERR_CUDA;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chol_coop_kernel<C>, C::THREADS, SM) != cudaSuccess || per_sm < 1)
+    return IPP_ERR_CUDA;
+  // no more CTAs than the first (largest) trailing update has tiles: grid barriers cost with the grid size
+  const int T0 = (d.rows - BLK + C::BM - 1) / C::BM;
+  int useful = T0 * (T0 + 1) / 2;
+  if (useful < d.rows / BLK) useful = d.rows / BLK;
+  int ctas = sms * per_sm;
+  if (ctas > useful) ctas = useful;
+  if (ctas < 1) ctas = 1;
+  long ld = d.ld;
+  int rows = d.rows, np = d.np;
+  void* args[] = {(void*)&Kb, (void*)&ld, (void*)&rows, (void*)&np, (void*)&info};
+  if (cudaLaunchCooperativeKernel((void*)chol_coop_kernel<C>, dim3(ctas), dim3(C::THREADS), args, SM, st) != cudaSuccess)
+    return IPP_ERR_CUDA;
+  if (Wb) {
+    if (opt_in_smem(diag_inverse_kernel, PANEL_SMEM) != cudaSuccess) return IPP_ERR_CUDA;
+    diag_inverse_kernel<<<d.np / BLK, 256, PANEL_SMEM, st>>>(Kb, d.ld, Wb, d.ld);
   }
   return IPP_OK;
 }

@@ -183,6 +183,7 @@ __global__ void __launch_bounds__(PC::THREADS, 1) posterior_lattice_kernel(PostA
   extern __shared__ __align__(16) double smem[];
   __shared__ double red[PC::WARPS_M][QT];
   __shared__ double mred[2][QT];
+  __shared__ double csq_s[2 * PC::NI][PC::THREADS];  // per-thread column norms (kept out of the register file)
   __shared__ __align__(8) uint64_t bar_full[SEP_STAGES], bar_empty[SEP_STAGES];
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int wm = warp / PC::WARPS_N, wn = warp % PC::WARPS_N;
@@ -190,9 +191,16 @@ __global__ void __launch_bounds__(PC::THREADS, 1) posterior_lattice_kernel(PostA
   const int p = t & (QT - 1), h = t >> 7;
   const long total = a.g_end - a.g_begin;
   const long ntiles = (total + QT - 1) / QT;
-  const int nrb = (a.np + PC::BM - 1) / PC::BM;
+  // Row blocks of W.  Only rows < n matter (the padding rows of W are identity rows times a zero k*), and
+  // the short block goes FIRST, where its k range is short too: rows [0, first), then full 128-row blocks.
+  // Block j covers rows [row0, rlim) and, W being lower triangular, k in [0, round_up(rlim, 16)).
+  const int first = a.n % PC::BM;
+  const int nrb = a.n / PC::BM + (first ? 1 : 0);
+  auto blk_row0 = [&](int j) { return first ? (j ? first + (j - 1) * PC::BM : 0) : j * PC::BM; };
+  auto blk_rlim = [&](int j) { return (first && j == 0) ? first : blk_row0(j) + PC::BM; };
+  auto blk_kend = [&](int j) { return (blk_rlim(j) + BK - 1) / BK * BK; };
   int tot = 0;  // pipeline iterations (k slabs summed over the row blocks) per tile
-  for (int rb = 0; rb < nrb; ++rb) tot += min((rb + 1) * PC::BM, a.np) / BK;
+  for (int rb = 0; rb < nrb; ++rb) tot += blk_kend(rb) / BK;
   if (t == 0) {
     for (int s = 0; s < SEP_STAGES; ++s) {
       mbar_init(&bar_full[s], PC::THREADS);       // one cp.async-completion arrival per thread
@@ -209,17 +217,17 @@ __global__ void __launch_bounds__(PC::THREADS, 1) posterior_lattice_kernel(PostA
     const int iy0 = (int)(gq0 / a.nx), ix0 = (int)(gq0 % a.nx);
     const int iy1 = min(iy0 + 1, a.ny - 1);
     const int nvalid = (int)min((long)QT, a.g_end - gq0);
-    bool sel[PC::NI];  // does my B column fall on the tile's second lattice row?
+    int eoff[PC::NI];  // offset of my B column's lattice row inside the stage's two Ey rows
 #pragma unroll
-    for (int ni = 0; ni < PC::NI; ++ni) sel[ni] = (ix0 + wn * PC::WTN + ni * 8 + g) >= a.nx;
+    for (int ni = 0; ni < PC::NI; ++ni) eoff[ni] = ((ix0 + wn * PC::WTN + ni * 8 + g) >= a.nx ? BK : 0) + tg;
     const int prow = (ix0 + p >= a.nx) ? BK : 0;
 
-    int prb = 0, pk = 0;
+    int prb = 0, pk = 0, p_row0 = 0, p_rlim = blk_rlim(0), p_kend = blk_kend(0);
     auto produce = [&](unsigned G) {
       const unsigned stage = G % SEP_STAGES, use = G / SEP_STAGES;
       if (use > 0) mbar_wait(&bar_empty[stage], (use - 1) & 1);  // every warp is done with the previous contents
       double* s = smem + stage * SEP_STAGE;
-      load_tile_async<PC::BM, Lay::KCONT, PC::THREADS>(s, a.W, a.ldw, prb * PC::BM, pk, a.np, a.np);
+      load_tile_async<PC::BM, Lay::KCONT, PC::THREADS>(s, a.W, a.ldw, p_row0, pk, p_rlim, a.np);
 #pragma unroll
       for (int it = 0; it < QT * BK / 2 / PC::THREADS; ++it) {
         const int c = t + it * PC::THREADS;
@@ -234,63 +242,77 @@ __global__ void __launch_bounds__(PC::THREADS, 1) posterior_lattice_kernel(PostA
       }
       cp_async_mbar_arrive(&bar_full[stage]);
       pk += BK;
-      if (pk >= min((prb + 1) * PC::BM, a.np)) {
+      if (pk >= p_kend) {
         pk = 0;
         ++prb;
+        p_row0 = blk_row0(prb);
+        p_rlim = blk_rlim(prb);
+        p_kend = blk_kend(prb);
       }
     };
 
     double acc[PC::MI][PC::NI][2];
     zero_acc<PC>(acc);
-    double csq[PC::NI][2];
 #pragma unroll
-    for (int ni = 0; ni < PC::NI; ++ni) csq[ni][0] = csq[ni][1] = 0.0;
+    for (int i = 0; i < 2 * PC::NI; ++i) csq_s[i][t] = 0.0;
     double mean_part = 0.0;
-    int crb = 0, ck = 0;
+    int crb = 0, ck = 0, c_kend = blk_kend(0);
 
     for (int s = 0; s < SEP_STAGES - 1; ++s)
       if (s < tot) produce(gslab + s);
     for (int it = 0; it < tot; ++it, ++gslab) {
       const unsigned stage = gslab % SEP_STAGES;
       mbar_wait(&bar_full[stage], (gslab / SEP_STAGES) & 1);
-      const double* sA = smem + stage * SEP_STAGE;
-      const double* sB = sA + SEP_A;
-      const double* sE = sB + SEP_B;
+      const double* sA = smem + stage * SEP_STAGE + (wm * PC::WTM + g) * KPAD + tg;
+      const double* sB = smem + stage * SEP_STAGE + SEP_A + (wn * PC::WTN + g) * KPAD + tg;
+      const double* sE = smem + stage * SEP_STAGE + SEP_A + SEP_B;
+      // B fragments (Ex * Ey) are prepared one k-step ahead of the DMMAs that use them
+      double bf[PC::NI], bn[PC::NI];
+#pragma unroll
+      for (int ni = 0; ni < PC::NI; ++ni) bf[ni] = __dmul_rn(sB[ni * 8 * KPAD], sE[eoff[ni]]);
 #pragma unroll
       for (int kk = 0; kk < BK; kk += 4) {
-        const double e0 = sE[kk + tg], e1 = sE[BK + kk + tg];
-        double af[PC::MI], bf[PC::NI];
+        double af[PC::MI];
 #pragma unroll
-        for (int mi = 0; mi < PC::MI; ++mi) af[mi] = sA[(wm * PC::WTM + mi * 8 + g) * KPAD + kk + tg];
+        for (int mi = 0; mi < PC::MI; ++mi) af[mi] = sA[mi * 8 * KPAD + kk];
+        if (kk + 4 < BK) {
 #pragma unroll
-        for (int ni = 0; ni < PC::NI; ++ni)
-          bf[ni] = __dmul_rn(sB[(wn * PC::WTN + ni * 8 + g) * KPAD + kk + tg], sel[ni] ? e1 : e0);
+          for (int ni = 0; ni < PC::NI; ++ni) bn[ni] = __dmul_rn(sB[ni * 8 * KPAD + kk + 4], sE[eoff[ni] + kk + 4]);
+        }
 #pragma unroll
         for (int mi = 0; mi < PC::MI; ++mi)
 #pragma unroll
           for (int ni = 0; ni < PC::NI; ++ni) dmma884(acc[mi][ni], af[mi], bf[ni]);
+#pragma unroll
+        for (int ni = 0; ni < PC::NI; ++ni) bf[ni] = bn[ni];
       }
       if (crb == nrb - 1) {  // the last row block sees every k slab once: the mean rides along there
+        const double* sBq = smem + stage * SEP_STAGE + SEP_A + p * KPAD;
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
           const int k = h * 8 + kk;
-          mean_part += __ldg(a.alpha + ck + k) * __dmul_rn(sB[p * KPAD + k], sE[prow + k]);
+          mean_part += __ldg(a.alpha + ck + k) * __dmul_rn(sBq[k], sE[prow + k]);
         }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_empty[stage]);  // this warp no longer reads the stage
       ck += BK;
-      if (ck >= min((crb + 1) * PC::BM, a.np)) {  // row block finished: fold its rows into the column norms
+      if (ck >= c_kend) {  // row block finished: fold its rows into the column norms
 #pragma unroll
-        for (int mi = 0; mi < PC::MI; ++mi)
+        for (int ni = 0; ni < PC::NI; ++ni)
 #pragma unroll
-          for (int ni = 0; ni < PC::NI; ++ni) {
-            csq[ni][0] += acc[mi][ni][0] * acc[mi][ni][0];
-            csq[ni][1] += acc[mi][ni][1] * acc[mi][ni][1];
-            acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+          for (int e = 0; e < 2; ++e) {
+            double v = csq_s[2 * ni + e][t];
+#pragma unroll
+            for (int mi = 0; mi < PC::MI; ++mi) {
+              v += acc[mi][ni][e] * acc[mi][ni][e];
+              acc[mi][ni][e] = 0.0;
+            }
+            csq_s[2 * ni + e][t] = v;
           }
         ck = 0;
         ++crb;
+        c_kend = blk_kend(crb);
       }
       // refill: the slab STAGES-1 ahead goes into the stage consumed one iteration ago, so the wait
       // inside produce() is for work the other warps finished a whole slab earlier
@@ -300,7 +322,7 @@ __global__ void __launch_bounds__(PC::THREADS, 1) posterior_lattice_kernel(PostA
     for (int ni = 0; ni < PC::NI; ++ni)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        double v = csq[ni][e];
+        double v = csq_s[2 * ni + e][t];
         v += __shfl_xor_sync(0xffffffffu, v, 4);
         v += __shfl_xor_sync(0xffffffffu, v, 8);
         v += __shfl_xor_sync(0xffffffffu, v, 16);
