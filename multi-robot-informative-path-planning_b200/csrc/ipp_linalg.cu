@@ -134,24 +134,60 @@ __global__ void __launch_bounds__(256) gram_rbf_kernel(const double* __restrict_
 // At n = 5000 that is 158 grid barriers instead of 237 dependent launches.
 // ---------------------------------------------------------------------------------------------
 constexpr int PSTR = BLK + 1;
-constexpr size_t PANEL_SMEM = sizeof(double) * 2 * BLK * PSTR;
+constexpr size_t PANEL_SMEM = sizeof(double) * (2 * BLK * PSTR + BLK);  // two 64x64 blocks + 64 reciprocals
 
-// In-place Cholesky of a 64x64 block held in shared memory (stride PSTR, lower part used).
+// In-place Cholesky of a 64x64 block held in shared memory (stride PSTR, lower part used), blocked by 8
+// columns: warp 0 factors each 64 x 8 panel in registers (lane r owns rows jb + r and jb + r + 32; pivots and
+// multipliers travel by shuffle, no barrier inside a panel), then the whole CTA applies the rank-8 update.
+// 16 CTA barriers per block instead of 192; every entry sees the same operations in the same order as the
+// textbook right-looking column sweep.
 template <int NT>
 __device__ __forceinline__ void potf2_block(double* D, int t, int first_index, double* info) {
-  for (int j = 0; j < BLK; ++j) {
-    const double piv = D[j * PSTR + j];
+  const int lane = t & 31, warp = t >> 5;
+  for (int jb = 0; jb < BLK; jb += 8) {
+    if (warp == 0) {
+      const int r0 = jb + lane, r1 = jb + lane + 32;
+      const bool has0 = r0 < BLK, has1 = r1 < BLK;
+      double a0[8], a1[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        a0[c] = has0 ? D[r0 * PSTR + jb + c] : 1.0;
+        a1[c] = has1 ? D[r1 * PSTR + jb + c] : 1.0;
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const double piv = __shfl_sync(0xffffffffu, a0[c], c);  // row jb + c lives in lane c
+        // one reciprocal square root per column (no divide on the chain); a non-positive pivot gives NaN
+        const double rs = rsqrt(piv);
+        if (lane == 0 && !(piv > 0.0) && info[0] == 0.0) info[0] = (double)(first_index + jb + c + 1);
+        if (lane == c)
+          a0[c] = piv > 0.0 ? piv * rs : sqrt(piv);
+        else if (lane > c)
+          a0[c] = a0[c] * rs;
+        a1[c] = a1[c] * rs;
+#pragma unroll
+        for (int q = c + 1; q < 8; ++q) {
+          const double lqc = __shfl_sync(0xffffffffu, a0[c], q);  // L[jb + q][jb + c]
+          if (lane > c) a0[q] -= a0[c] * lqc;
+          a1[q] -= a1[c] * lqc;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        if (has0) D[r0 * PSTR + jb + c] = a0[c];
+        if (has1) D[r1 * PSTR + jb + c] = a1[c];
+      }
+    }
     __syncthreads();
-    const double lj = sqrt(piv);
-    if (t == 0 && !(piv > 0.0) && info[0] == 0.0) info[0] = (double)(first_index + j + 1);
-    if (t == j) D[j * PSTR + j] = lj;
-    if (t > j && t < BLK) D[t * PSTR + j] = D[t * PSTR + j] / lj;
-    __syncthreads();
-    // trailing update of the lower triangle: D[r][c] -= D[r][j] * D[c][j], j < c <= r
-    const int m = BLK - 1 - j;
-    for (int e = t; e < m * m; e += NT) {
-      int r = j + 1 + e / m, cc = j + 1 + e % m;
-      if (cc <= r) D[r * PSTR + cc] -= D[r * PSTR + j] * D[cc * PSTR + j];
+    // rank-8 update of the trailing lower triangle; (r, cc) from shifts, not divisions
+    for (int e = t; e < BLK * BLK; e += NT) {
+      const int r = e >> 6, cc = e & 63;
+      if (cc >= jb + 8 && cc <= r) {
+        double v = D[r * PSTR + cc];
+#pragma unroll
+        for (int pp = 0; pp < 8; ++pp) v -= D[r * PSTR + jb + pp] * D[cc * PSTR + jb + pp];
+        D[r * PSTR + cc] = v;
+      }
     }
     __syncthreads();
   }
@@ -174,6 +210,59 @@ __device__ __forceinline__ void chol_diag_step(double* __restrict__ A, long ld, 
   __syncthreads();
 }
 
+// Diagonal block k after panel kp = k - 1: apply that panel's update to the 64x64 block with plain FMAs
+// (it is 1/4 of a 128x128 tensor tile and sits on the critical path), then factor it.
+template <int NT>
+__device__ __forceinline__ void chol_diag_update_step(double* __restrict__ A, long ld, int k, int kp, double* psm,
+                                                      double* info) {
+  double* D = psm;
+  double* P = psm + BLK * PSTR;
+  const int t = threadIdx.x, j0 = BLK * k, p0 = BLK * kp;
+  for (int e = t; e < BLK * BLK; e += NT) {
+    int r = e / BLK, cc = e % BLK;
+    D[r * PSTR + cc] = A[(long)(j0 + r) * ld + j0 + cc];
+    P[r * PSTR + cc] = A[(long)(j0 + r) * ld + p0 + cc];
+  }
+  __syncthreads();
+  {  // D -= P P^T on the DMMA pipe: each warp owns 64 / (NT / 32) rows, all 64 columns
+    constexpr int RPW = BLK / (NT / 32), MT = RPW / 8;
+    const int warp = t >> 5, lane = t & 31, g = lane >> 2, tg = lane & 3;
+    double acc[MT][8][2];
+#pragma unroll
+    for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 8; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+#pragma unroll 4
+    for (int kk = 0; kk < BLK; kk += 4) {
+      double af[MT], bf[8];
+#pragma unroll
+      for (int mi = 0; mi < MT; ++mi) af[mi] = P[(warp * RPW + mi * 8 + g) * PSTR + kk + tg];
+#pragma unroll
+      for (int ni = 0; ni < 8; ++ni) bf[ni] = P[(ni * 8 + g) * PSTR + kk + tg];
+#pragma unroll
+      for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni) dmma884(acc[mi][ni], af[mi], bf[ni]);
+    }
+#pragma unroll
+    for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 8; ++ni)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int r = warp * RPW + mi * 8 + g, cc = ni * 8 + tg * 2 + e;
+          if (cc <= r) D[r * PSTR + cc] -= acc[mi][ni][e];
+        }
+  }
+  __syncthreads();
+  potf2_block<NT>(D, t, j0, info);
+  for (int e = t; e < BLK * BLK; e += NT) {
+    int r = e / BLK, cc = e % BLK;
+    A[(long)(j0 + r) * ld + j0 + cc] = (cc <= r) ? D[r * PSTR + cc] : 0.0;
+  }
+  __syncthreads();
+}
+
 // Panel solve of one 64-row block: A_ik <- A_ik * L_kk^-T by forward substitution (backward stable,
 // unlike multiplying by the explicit inverse: at cond(K) ~ 1e11 the diagonal blocks reach cond ~ 1e5 and
 // the inverse route cost 5 digits of L).  NT / 64 adjacent lanes share a row (columns interleaved), the
@@ -184,12 +273,16 @@ __device__ __forceinline__ void chol_trsm_block(double* __restrict__ A, long ld,
   constexpr int CPL = BLK / LPR;  // columns per lane
   double* Ls = psm;
   double* Xs = psm + BLK * PSTR;
+  double* rinv = psm + 2 * BLK * PSTR;
   const int t = threadIdx.x, j0 = BLK * k, i0 = BLK * i;
   for (int e = t; e < BLK * BLK; e += NT) {
     int r = e / BLK, cc = e % BLK;
     Ls[r * PSTR + cc] = A[(long)(j0 + r) * ld + j0 + cc];
     Xs[r * PSTR + cc] = A[(long)(i0 + r) * ld + j0 + cc];
   }
+  // One reciprocal per column, then multiplies: 64 dependent fp64 divides per row were most of this step,
+  // and rows of exact zeros (identity padding, the y block) sent every one of them down the divide's slow path.
+  if (t < BLK) rinv[t] = 1.0 / A[(long)(j0 + t) * ld + j0 + t];
   __syncthreads();
   {
     const int r = t / LPR, q0 = t % LPR, lane = t & 31;
@@ -199,7 +292,7 @@ __device__ __forceinline__ void chol_trsm_block(double* __restrict__ A, long ld,
 #pragma unroll
     for (int c = 0; c < BLK; ++c) {
       const int owner = c % LPR, mc = c / LPR;
-      double xc = x[mc] / Ls[c * PSTR + c];  // meaningful in the owner lane only
+      double xc = x[mc] * rinv[c];  // meaningful in the owner lane only
       xc = __shfl_sync(0xffffffffu, xc, (lane & ~(LPR - 1)) + owner);
       if (q0 == owner) x[mc] = xc;
 #pragma unroll
@@ -223,6 +316,7 @@ __device__ __forceinline__ void chol_trsm_block(double* __restrict__ A, long ld,
 template <class C>
 __device__ __forceinline__ void chol_syrk_tile(double* __restrict__ A, long ld, int rows_total, int np, int k, int b,
                                                double* smem) {
+  const int skip = k + 1;  // diagonal block (k+1, k+1) is updated and factored by chol_diag_update_step
   const int j0 = BLK * k, r0 = j0 + BLK;
   int ti = (int)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
   while ((long)(ti + 1) * (ti + 2) / 2 <= b) ++ti;
@@ -241,34 +335,55 @@ __device__ __forceinline__ void chol_syrk_tile(double* __restrict__ A, long ld, 
   gemm_mainloop<C, Lay::KCONT, Lay::KCONT>(acc, smem, j0, j0 + BLK, fillA, fillB);
   for_each_acc<C>(acc, [&](int r, int c, double v) {
     int gr = row0 + r, gc = col0 + c;
-    if (gr < rows_total && gc < np && (gc >> 6) <= (gr >> 6)) A[(long)gr * ld + gc] -= v;
+    const int br = gr >> 6, bc = gc >> 6;
+    if (gr < rows_total && gc < np && bc <= br && !(br == skip && bc == skip)) A[(long)gr * ld + gc] -= v;
   });
 }
 
 template <class C>
 __global__ void __launch_bounds__(C::THREADS, 1) chol_coop_kernel(double* __restrict__ A, long ld, int rows_total, int np,
-                                                                  double* __restrict__ info) {
+                                                                  double* __restrict__ info, double* __restrict__ phase_cycles) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(16) double smem[];
   const int nb = np / BLK, nrb = rows_total / BLK;
+  // phase_cycles (nullable): CTA 0's clock64() spent in {barrier 1, panel solve, barrier 2, diagonal block,
+  // trailing tiles} summed over the panels -- the evidence for where a latency-bound factorisation goes
+  const bool timing = phase_cycles != nullptr && blockIdx.x < 2 && threadIdx.x == 0;  // CTA 0 (panel) and CTA 1 (tiles)
+  long long tc[5] = {0, 0, 0, 0, 0}, t0 = 0;
+  auto tick = [&](int slot) {
+    if (timing) {
+      const long long now = clock64();
+      tc[slot] += now - t0;
+      t0 = now;
+    }
+  };
   if (blockIdx.x == 0) chol_diag_step<C::THREADS>(A, ld, 0, smem, info);
+  if (timing) t0 = clock64();
   for (int k = 0; k < nb; ++k) {
     grid.sync();  // L_kk is final
+    tick(0);
     for (int i = k + 1 + blockIdx.x; i < nrb; i += gridDim.x) chol_trsm_block<C::THREADS>(A, ld, k, i, smem);
+    tick(1);
     grid.sync();  // panel k is final
+    tick(2);
     if (k + 1 < nb) {
       const int rem = rows_total - BLK * (k + 1);
       const int T = (rem + C::BM - 1) / C::BM;
       const int ntile = T * (T + 1) / 2;
-      for (int b = blockIdx.x; b < ntile; b += gridDim.x) {
-        chol_syrk_tile<C>(A, ld, rows_total, np, k, b, smem);
-        if (b == 0) {  // tile 0 holds block (k+1, k+1): factor it now, behind the other CTAs' tiles
-          __syncthreads();
-          chol_diag_step<C::THREADS>(A, ld, k + 1, smem, info);
-        }
+      // the next diagonal block first (CTA 0), behind the other CTAs' tiles
+      // CTA 0 owns the critical path (next diagonal block); the other CTAs share the tiles
+      if (blockIdx.x == 0) chol_diag_update_step<C::THREADS>(A, ld, k + 1, k, smem, info);
+      tick(3);
+      if (gridDim.x == 1) {
+        for (int b = 0; b < ntile; ++b) chol_syrk_tile<C>(A, ld, rows_total, np, k, b, smem);
+      } else if (blockIdx.x > 0) {
+        for (int b = blockIdx.x - 1; b < ntile; b += gridDim.x - 1) chol_syrk_tile<C>(A, ld, rows_total, np, k, b, smem);
       }
+      tick(4);
     }
   }
+  if (timing)
+    for (int q = 0; q < 5; ++q) phase_cycles[5 * blockIdx.x + q] = (double)tc[q];
 }
 
 // W_kk = L_kk^-1 for every 64x64 diagonal block at once (level 0 of the triangular inverse).
@@ -355,17 +470,31 @@ __global__ void __launch_bounds__(256) w_clear_kernel(double* __restrict__ W, lo
   }
 }
 
-// alpha = W^T z  (z = row NP of the factor buffer).  One CTA per 64 columns, 4 k-lanes per column.
+// alpha = W^T z  (z = row NP of the factor buffer).  W is 8 NP^2 bytes and read once: HBM bound, so the
+// k range is split GEMV_SPLIT ways across CTAs (one 64-column strip alone gives NP/64 CTAs, too few to
+// pull HBM bandwidth); partial sums land in `part` and are combined in a fixed order (deterministic).
+constexpr int GEMV_SPLIT = 16;
 __global__ void __launch_bounds__(256) gemv_wt_kernel(const double* __restrict__ W, long ldw, const double* __restrict__ z,
-                                                      double* __restrict__ alpha, int np) {
+                                                      double* __restrict__ part, int np) {
   __shared__ double red[4][BLK];
   const int ci = threadIdx.x & 63, kq = threadIdx.x >> 6;
   const int i0 = blockIdx.x * BLK, i = i0 + ci;
+  // rows [i0, np) of this strip are non-zero; chunk them evenly over blockIdx.y
+  const int rows = np - i0, chunk = (rows + GEMV_SPLIT - 1) / GEMV_SPLIT;
+  const int kb = i0 + blockIdx.y * chunk, ke = min(np, kb + chunk);
   double s = 0.0;
-  for (int k = i0 + kq; k < np; k += 4) s += W[(long)k * ldw + i] * z[k];
+  for (int k = kb + kq; k < ke; k += 4) s += W[(long)k * ldw + i] * z[k];
   red[kq][ci] = s;
   __syncthreads();
-  if (kq == 0) alpha[i] = (red[0][ci] + red[1][ci]) + (red[2][ci] + red[3][ci]);
+  if (kq == 0) part[(long)blockIdx.y * np + i] = (red[0][ci] + red[1][ci]) + (red[2][ci] + red[3][ci]);
+}
+__global__ void __launch_bounds__(256) gemv_reduce_kernel(const double* __restrict__ part, double* __restrict__ alpha, int np) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= np) return;
+  double s = 0.0;
+#pragma unroll
+  for (int q = 0; q < GEMV_SPLIT; ++q) s += part[(long)q * np + i];
+  alpha[i] = s;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -524,11 +653,13 @@ static int chol_inplace(double* Kb, double* Wb, double* info, const GpDims& d, c
   int useful = T0 * (T0 + 1) / 2;
   if (useful < d.rows / BLK) useful = d.rows / BLK;
   int ctas = sms * per_sm;
-  if (ctas > useful) ctas = useful;
+  if (ctas > useful + 1) ctas = useful + 1;  // + the panel CTA
   if (ctas < 1) ctas = 1;
   long ld = d.ld;
   int rows = d.rows, np = d.np;
-  void* args[] = {(void*)&Kb, (void*)&ld, (void*)&rows, (void*)&np, (void*)&info};
+  // the tile-partials area of vbuf (free until the gradient kernel runs) receives the phase counters
+  double* phase = (2 * d.max_tiles >= 10) ? info - 3 - 2 * d.max_tiles : nullptr;
+  void* args[] = {(void*)&Kb, (void*)&ld, (void*)&rows, (void*)&np, (void*)&info, (void*)&phase};
   if (cudaLaunchCooperativeKernel((void*)chol_coop_kernel<C>, dim3(ctas), dim3(C::THREADS), args, SM, st) != cudaSuccess)
     return IPP_ERR_CUDA;
   if (Wb) {
@@ -703,7 +834,9 @@ int ipp_gp_lml_grad(const double* X, const double* y, int n, const double* hyp, 
   const GpDims d = gp_dims(n);
   int ntiles = 0;
   if (with_grad) {
-    gemv_wt_kernel<<<d.np / BLK, 256, 0, st>>>(Wbuf, d.ld, Kbuf + (long)d.np * d.ld, vbuf + V_ALPHA * d.npv, d.np);
+    // partials go to Tbuf, which the triangular inverse is done with
+    gemv_wt_kernel<<<dim3(d.np / BLK, GEMV_SPLIT), 256, 0, st>>>(Wbuf, d.ld, Kbuf + (long)d.np * d.ld, Tbuf, d.np);
+    gemv_reduce_kernel<<<(d.np + 255) / 256, 256, 0, st>>>(Tbuf, vbuf + V_ALPHA * d.npv, d.np);
     rc = use_small_tiles(d.np) ? lml_grad_launch<Cfg64>(Wbuf, vbuf, hyp, d, &ntiles, st)
                                : lml_grad_launch<Cfg128>(Wbuf, vbuf, hyp, d, &ntiles, st);
     if (rc != IPP_OK) return rc;
