@@ -129,6 +129,14 @@ def fp64_peak_tflops():
         return 37.0, "fallback: NVIDIA HGX B200 sheet, 296 TF fp64 / 8 GPUs"
 
 
+def ncu_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one posterior launch, from the committed ncu capture."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic_r01.json")))[workload]["dram_bytes_per_launch"]
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def hbm_peak_gbs():
     try:
         return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured: MEASURED_PEAKS.json"
@@ -169,8 +177,11 @@ def cpu_posterior_leg(wl, seed, sample_pts, steps, warmup):
         if it >= warmup:
             times.append(dt)
     threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    t = time.perf_counter()
+    gp.log_marginal_likelihood(np.log(THETA), eval_gradient=True)  # the objective of the reference's 11 L-BFGS-B runs
+    t_lml = time.perf_counter() - t
     return dict(pts_per_s=sample_pts / float(np.mean(times)), ms_per_step=1e3 * float(np.mean(times)), fit_fixed_theta_s=t_fit,
-                cores=int(threads), sample_pts=sample_pts)
+                cores=int(threads), sample_pts=sample_pts, lml_grad_eval_ms=1e3 * t_lml)
 
 
 def cpu_branch_leg(wl, seed, sample_branches):
@@ -343,6 +354,19 @@ def run_b200(args, wl, rank, world, local_rank):
     torch.cuda.synchronize()
     lml_ms = 1e3 * (time.perf_counter() - t0) / n_lml
 
+    # one full re-optimised fit exactly as PointSourceField.update runs it (11 L-BFGS-B restarts, same RNG draws)
+    full_fit = None
+    if not args.skip_full_fit:
+        gpf = G.GaussianProcessRegressor(kernel=G.ConstantRBFKernel(1.0, 1.0), n_restarts_optimizer=10, normalize_y=True)
+        np.random.seed(0)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        gpf.fit(X, ylog)
+        torch.cuda.synchronize()
+        full_fit = {"seconds": time.perf_counter() - t0, "lml_evals": gpf.n_lml_evals_,
+                    "theta_c_l": [gpf.kernel_.constant_value, gpf.kernel_.length_scale]}
+        del gpf
+
     # ---- (4) candidate-branch information gain -------------------------------------------------------
     B = wl["branches"]
     xy, parent = synth_tree(B, W, seed)
@@ -367,6 +391,39 @@ def run_b200(args, wl, rank, world, local_rank):
         t = torch.tensor([br_dev_ms, 1.0 / br_e2e], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         br_dev_ms, br_e2e = float(t[0]), 1.0 / float(t[1])
+    # ---- (5) whole planning step: every agent scores its tree and selects (stage 2 argmax of information, stage 1
+    # mutual-information + penalty selector), host arrays in and out; GP refits deferred (lazy mode)
+    agents = wl["agents"]
+    per_agent = B // agents
+    a_trees = []
+    for a in range(agents):
+        xy_a, par_a = synth_tree(per_agent, W, 1000 * seed + a)
+        tr = TreeArrays(xy_a[0], capacity=per_agent + 1)
+        for k in range(1, per_agent + 1):
+            tr.add(xy_a[k], int(par_a[k]))
+        a_trees.append(tr)
+
+    def planning_step():
+        chosen = []
+        for a, tr in enumerate(a_trees):
+            ctx_a = ScoreContext(src, tr.point(0), obs, a, 1.0, (0, W, 0, W), [])
+            info_a = scorer.tree_information(3, tr, ctx_a)
+            leaves = tr.leaves_in_order()
+            par_l = tr.parent[leaves]
+            leaf_xy = np.ascontiguousarray(tr.points()[leaves])
+            parent_xy = np.ascontiguousarray(tr.points()[np.where(par_l >= 0, par_l, 0)])
+            scores, _ = scorer.leaf_scores(leaf_xy, parent_xy, par_l >= 0, ctx_a, 5.0, 1.0, 1.0)
+            chosen.append((int(leaves[int(np.argmax(info_a[leaves]))]), int(leaves[int(np.argmax(scores))])))
+        return chosen
+
+    for _ in range(2):
+        planning_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        chosen = planning_step()
+    barrier()
+    plan_ms = 1e3 * (time.perf_counter() - t0) / 5
     if sampler:
         sampler.stop()
 
@@ -391,7 +448,8 @@ def run_b200(args, wl, rank, world, local_rank):
                             "Gram + Cholesky + inverse + alpha, lattice posterior, pinned read-back of Z_pred and std"},
             "gpu_launches": n_launch,
             "roofline": {"bound": "tensor", "achieved": ach, "peak": peak64, "unit": "TFLOP/s", "frac": ach / peak64,
-                         "traffic": None, "kernel": "posterior_kernel<GRID>", "flops_per_launch": flops,
+                         "traffic": ncu_traffic(args.workload), "kernel": "posterior_lattice_kernel",
+                         "flops_per_launch": flops,
                          "peak_source": src64 + " (fp64 DMMA; tcgen05 has no fp64 MMA)"},
             "roofline_hbm": {"bound": "hbm", "achieved": 24.0 * Gpts / (ms_post * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                              "frac": 24.0 * Gpts / (ms_post * 1e-3) / 1e9 / hbm, "peak_source": srchbm,
@@ -400,7 +458,11 @@ def run_b200(args, wl, rank, world, local_rank):
                              "sample": f"{cpu_post['sample_pts']} lattice points per step through scikit-learn "
                                        f"GaussianProcessRegressor.predict(return_std=True), fixed theta, n = {n}"},
             "fit": {"lml_grad_eval_ms": lml_ms, "lml_grad_evals_per_s": 1e3 / lml_ms,
-                    "tflops": float(NP) ** 3 / (lml_ms * 1e-3) / 1e12},
+                    "tflops": float(NP) ** 3 / (lml_ms * 1e-3) / 1e12, "full_fit_11_restarts": full_fit,
+                    "cpu_lml_grad_eval_ms": cpu_post["lml_grad_eval_ms"], "cpu_cores": cpu_post["cores"]},
+            "planning_step": {"ms": plan_ms, "agents": agents, "branches_per_agent": per_agent,
+                              "mode": "lazy GP refits (DESIGN.md section 5): per agent tree scoring (point_source_gain_all) + "
+                                      "stage-2 argmax + stage-1 mutual-information/penalty selector, host arrays in and out"},
             "branch_gain": {"value": world * B / (br_dev_ms * 1e-3), "unit": "branch evals/s", "ms_per_batch": br_dev_ms,
                             "branches": B, "variant": "point_source_gain_all", "observations": n,
                             "e2e": {"value": world * br_e2e, "unit": "branch evals/s"},
@@ -421,6 +483,7 @@ def main():
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="lattice points per CPU-baseline step")
+    ap.add_argument("--skip-full-fit", action="store_true", help="skip the one-off 11-restart hyper-parameter fit")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

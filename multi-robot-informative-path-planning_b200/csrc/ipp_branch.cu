@@ -37,6 +37,9 @@ __global__ void __launch_bounds__(256) count_close_kernel(const double* __restri
     py = P[2 * pi + 1];
   }
   int ns = 0, na = 0;
+  // r < d is decided on squared distances (no square root per pair): outside a band of ~18 ulp around d^2 the
+  // comparison of the squares equals the comparison numpy makes on the correctly rounded roots
+  const double d2 = d * d, band = 4e-15 * d2;
   for (int o0 = 0; o0 < no; o0 += 512) {
     __syncthreads();
     for (int e = threadIdx.x; e < 512; e += 256) {
@@ -47,11 +50,11 @@ __global__ void __launch_bounds__(256) count_close_kernel(const double* __restri
     __syncthreads();
     const int lim = min(512, no - o0);
     for (int e = lane; e < lim; e += 32) {
-      double r = norm2(px - so[0][e], py - so[1][e]);
-      // ambiguous band: |r - d| <= 8 ulp(d)
-      if (fabs(r - d) <= 1.8e-15 * d)
+      const double dx = px - so[0][e], dy = py - so[1][e];
+      const double r2 = __fma_rn(dy, dy, __dmul_rn(dx, dx));
+      if (fabs(r2 - d2) <= band)
         ++na;
-      else if (r < d)
+      else if (r2 < d2)
         ++ns;
     }
   }
