@@ -211,9 +211,20 @@ def cpu_branch_leg(wl, seed, sample_branches):
     return dict(evals_per_s=sample_branches / dt, sample_branches=int(sample_branches), seconds=dt)
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU legs are meant to use every host core."""
+    try:
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(limits=os.cpu_count())
+    except Exception:  # pragma: no cover
+        pass
+
+
 def run_reference(args, wl, rank, world):
     if rank != 0:
         return
+    use_all_host_threads()
     sample = args.cpu_sample or max(2048, min(20000, int(2.0e7 / wl["n"])))
     post = cpu_posterior_leg(wl, 0, sample, args.steps, args.warmup)
     br = cpu_branch_leg(wl, 0, 16 if wl["n"] >= 2000 else 64)
@@ -254,6 +265,9 @@ def run_b200(args, wl, rank, world, local_rank):
     _lib.load()
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # NCCL prints its version banner on STDOUT at the VERSION/INFO levels; stdout carries the one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "INFO"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n, W = wl["n"], wl["W"]
     nx = ny = W * 10
@@ -432,6 +446,7 @@ def run_b200(args, wl, rank, world, local_rank):
         hbm, srchbm = hbm_peak_gbs()
         flops = float(Gpts) * (float(n) * n + 4.0 * n)  # n^2 (triangular solve) + 4n per point
         ach = flops / (ms_post * 1e-3) / 1e12
+        use_all_host_threads()
         cpu_post = cpu_posterior_leg(wl, 0, args.cpu_sample or max(2048, min(20000, int(2.0e7 / n))), 2, 1)
         cpu_br = cpu_branch_leg(wl, 0, 16 if n >= 2000 else 64)
         line = {
