@@ -10,7 +10,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libipp_b200.so")
+LIB_PATH = os.environ.get("IPP_B200_LIB", os.path.join(_HERE, "libipp_b200.so"))  # override: kernel experiments only
 
 _lib = None
 _lock = threading.Lock()

@@ -40,12 +40,13 @@ __host__ __device__ constexpr int tile_doubles() {
 // ld must be even and g 16-byte aligned.
 template <int R, Lay L, int THREADS>
 __device__ __forceinline__ void load_tile_async(double* __restrict__ s, const double* __restrict__ g, long ld, int r0,
-                                                int k0, int rlim, int klim) {
+                                                int k0, int rlim, int klim, int tid = -1) {
   constexpr int CHUNKS = R * BK / 2;
-  static_assert(CHUNKS % THREADS == 0, "tile chunks must divide evenly over the CTA");
+  static_assert(CHUNKS % THREADS == 0, "tile chunks must divide evenly over the copying threads");
+  if (tid < 0) tid = threadIdx.x;  // default: the whole CTA copies; a warp-specialised caller passes its own index
 #pragma unroll
   for (int it = 0; it < CHUNKS / THREADS; ++it) {
-    int c = threadIdx.x + it * THREADS;
+    int c = tid + it * THREADS;
     if (L == Lay::KCONT) {
       int r = c / (BK / 2), kc = (c % (BK / 2)) * 2;
       int gr = r0 + r, gk = k0 + kc;

@@ -178,17 +178,16 @@ __global__ void __launch_bounds__(256) axis_table_kernel(const double* __restric
   T[(long)i * ldt + k] = v;
 }
 
-__global__ void __launch_bounds__(PC::THREADS, 1) posterior_lattice_kernel(PostArgs a, const double* __restrict__ Ex,
-                                                                            const double* __restrict__ Ey, long ldt) {
+constexpr int LAT_THREADS = PC::THREADS + 128;  // 8 DMMA (consumer) warps + one copy (producer) warpgroup
+
+__global__ void __launch_bounds__(LAT_THREADS, 1) posterior_lattice_kernel(PostArgs a, const double* __restrict__ Ex,
+                                                                           const double* __restrict__ Ey, long ldt) {
   extern __shared__ __align__(16) double smem[];
   __shared__ double red[PC::WARPS_M][QT];
   __shared__ double mred[2][QT];
   __shared__ double csq_s[2 * PC::NI][PC::THREADS];  // per-thread column norms (kept out of the register file)
   __shared__ __align__(8) uint64_t bar_full[SEP_STAGES], bar_empty[SEP_STAGES];
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const int wm = warp / PC::WARPS_N, wn = warp % PC::WARPS_N;
-  const int g = lane >> 2, tg = lane & 3;
-  const int p = t & (QT - 1), h = t >> 7;
   const long total = a.g_end - a.g_begin;
   const long ntiles = (total + QT - 1) / QT;
   // Row blocks of W.  Only rows < n matter (the padding rows of W are identity rows times a zero k*), and
@@ -203,133 +202,171 @@ __global__ void __launch_bounds__(PC::THREADS, 1) posterior_lattice_kernel(PostA
   for (int rb = 0; rb < nrb; ++rb) tot += blk_kend(rb) / BK;
   if (t == 0) {
     for (int s = 0; s < SEP_STAGES; ++s) {
-      mbar_init(&bar_full[s], PC::THREADS);       // one cp.async-completion arrival per thread
+      mbar_init(&bar_full[s], 128);                // one cp.async-completion arrival per copy thread
       mbar_init(&bar_empty[s], PC::THREADS / 32);  // one arrival per consumer warp
     }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
   // Slabs are numbered globally across tiles: slab G lives in stage G % STAGES and is that stage's
   // (G / STAGES)-th use, which fixes the phase parity of both of its barriers.
-  unsigned gslab = 0;  // next slab this thread consumes
+  unsigned gslab = 0;  // next slab of this thread (producer: to copy, consumer: to multiply)
 
+  if (warp >= PC::THREADS / 32) {
+    // Register file: the copy warpgroup gives its registers back so that the DMMA warps can hold their
+    // 128 accumulator registers plus fragments without spilling (384 threads compile for 168 each).
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
+    const int pt = t - PC::THREADS;  // 0..127 within the copy warpgroup
+    for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const long gq0 = a.g_begin + tile * QT;
+      const int iy0 = (int)(gq0 / a.nx), ix0 = (int)(gq0 % a.nx);
+      const int iy1 = min(iy0 + 1, a.ny - 1);
+      const int nvalid = (int)min((long)QT, a.g_end - gq0);
+      // ---- producer warpgroup: 16-byte cp.async (LDGSTS) into the padded, bank-conflict-free stage layout; each
+      // thread's copies complete on the stage's full barrier (cp.async.mbarrier.arrive.noinc).  Per-row 128-byte
+      // bulk copies (UBLKCP) were tried here and ran 3x slower: ~260 small bulk requests per slab swamp the unit.
+      int prb = 0, pk = 0, p_row0 = 0, p_rlim = blk_rlim(0), p_kend = blk_kend(0);
+      for (int it = 0; it < tot; ++it, ++gslab) {
+        const unsigned stage = gslab % SEP_STAGES, use = gslab / SEP_STAGES;
+        if (use > 0) mbar_wait(&bar_empty[stage], (use - 1) & 1);  // every consumer warp is done with the old contents
+        double* s = smem + stage * SEP_STAGE;
+        load_tile_async<PC::BM, Lay::KCONT, 128>(s, a.W, a.ldw, p_row0, pk, p_rlim, a.np, pt);
+#pragma unroll
+        for (int q = 0; q < QT * BK / 2 / 128; ++q) {
+          const int c = pt + q * 128;
+          const int r = c / (BK / 2), kc = (c % (BK / 2)) * 2;
+          int ix = ix0 + min(r, nvalid - 1);
+          if (ix >= a.nx) ix -= a.nx;
+          cp_async16(s + SEP_A + r * KPAD + kc, Ex + (long)ix * ldt + pk + kc, true);
+        }
+        if (pt < BK) {
+          const int row = pt >> 3, kc = (pt & 7) * 2;
+          cp_async16(s + SEP_A + SEP_B + row * BK + kc, Ey + (long)(row ? iy1 : iy0) * ldt + pk + kc, true);
+        }
+        cp_async_mbar_arrive(&bar_full[stage]);
+        pk += BK;
+        if (pk >= p_kend) {
+          pk = 0;
+          ++prb;
+          p_row0 = blk_row0(prb);
+          p_rlim = blk_rlim(prb);
+          p_kend = blk_kend(prb);
+        }
+      }
+    }
+    cp_async_wait<0>();
+    return;  // the copy warps run ahead across tile boundaries, held back only by the empty barriers
+  }
+
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
   for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long gq0 = a.g_begin + tile * QT;
-    const int iy0 = (int)(gq0 / a.nx), ix0 = (int)(gq0 % a.nx);
-    const int iy1 = min(iy0 + 1, a.ny - 1);
+    const int ix0 = (int)(gq0 % a.nx);
     const int nvalid = (int)min((long)QT, a.g_end - gq0);
-    int eoff[PC::NI];  // offset of my B column's lattice row inside the stage's two Ey rows
+    {
+      // ---- consumer warps: DMMA only ----
+      const int wm = warp / PC::WARPS_N, wn = warp % PC::WARPS_N;
+      const int g = lane >> 2, tg = lane & 3;
+      const int p = t & (QT - 1), h = t >> 7;
+      int eoff[PC::NI];  // offset of my B column's lattice row inside the stage's two Ey rows
 #pragma unroll
-    for (int ni = 0; ni < PC::NI; ++ni) eoff[ni] = ((ix0 + wn * PC::WTN + ni * 8 + g) >= a.nx ? BK : 0) + tg;
-    const int prow = (ix0 + p >= a.nx) ? BK : 0;
+      for (int ni = 0; ni < PC::NI; ++ni) eoff[ni] = ((ix0 + wn * PC::WTN + ni * 8 + g) >= a.nx ? BK : 0) + tg;
+      const int prow = (ix0 + p >= a.nx) ? BK : 0;
+      double acc[PC::MI][PC::NI][2];
+      zero_acc<PC>(acc);
+#pragma unroll
+      for (int i = 0; i < 2 * PC::NI; ++i) csq_s[i][t] = 0.0;
+      double mean_part = 0.0;
+      int crb = 0, ck = 0, c_kend = blk_kend(0);
 
-    int prb = 0, pk = 0, p_row0 = 0, p_rlim = blk_rlim(0), p_kend = blk_kend(0);
-    auto produce = [&](unsigned G) {
-      const unsigned stage = G % SEP_STAGES, use = G / SEP_STAGES;
-      if (use > 0) mbar_wait(&bar_empty[stage], (use - 1) & 1);  // every warp is done with the previous contents
-      double* s = smem + stage * SEP_STAGE;
-      load_tile_async<PC::BM, Lay::KCONT, PC::THREADS>(s, a.W, a.ldw, p_row0, pk, p_rlim, a.np);
-#pragma unroll
-      for (int it = 0; it < QT * BK / 2 / PC::THREADS; ++it) {
-        const int c = t + it * PC::THREADS;
-        const int r = c / (BK / 2), kc = (c % (BK / 2)) * 2;
-        int ix = ix0 + min(r, nvalid - 1);
-        if (ix >= a.nx) ix -= a.nx;
-        cp_async16(s + SEP_A + r * KPAD + kc, Ex + (long)ix * ldt + pk + kc, true);
-      }
-      if (t < BK) {
-        const int row = t >> 3, kc = (t & 7) * 2;
-        cp_async16(s + SEP_A + SEP_B + row * BK + kc, Ey + (long)(row ? iy1 : iy0) * ldt + pk + kc, true);
-      }
-      cp_async_mbar_arrive(&bar_full[stage]);
-      pk += BK;
-      if (pk >= p_kend) {
-        pk = 0;
-        ++prb;
-        p_row0 = blk_row0(prb);
-        p_rlim = blk_rlim(prb);
-        p_kend = blk_kend(prb);
-      }
-    };
-
-    double acc[PC::MI][PC::NI][2];
-    zero_acc<PC>(acc);
-#pragma unroll
-    for (int i = 0; i < 2 * PC::NI; ++i) csq_s[i][t] = 0.0;
-    double mean_part = 0.0;
-    int crb = 0, ck = 0, c_kend = blk_kend(0);
-
-    for (int s = 0; s < SEP_STAGES - 1; ++s)
-      if (s < tot) produce(gslab + s);
-    for (int it = 0; it < tot; ++it, ++gslab) {
-      const unsigned stage = gslab % SEP_STAGES;
-      mbar_wait(&bar_full[stage], (gslab / SEP_STAGES) & 1);
-      const double* sA = smem + stage * SEP_STAGE + (wm * PC::WTM + g) * KPAD + tg;
-      const double* sB = smem + stage * SEP_STAGE + SEP_A + (wn * PC::WTN + g) * KPAD + tg;
-      const double* sE = smem + stage * SEP_STAGE + SEP_A + SEP_B;
-      // B fragments (Ex * Ey) are prepared one k-step ahead of the DMMAs that use them
-      double bf[PC::NI], bn[PC::NI];
-#pragma unroll
-      for (int ni = 0; ni < PC::NI; ++ni) bf[ni] = __dmul_rn(sB[ni * 8 * KPAD], sE[eoff[ni]]);
-#pragma unroll
-      for (int kk = 0; kk < BK; kk += 4) {
-        double af[PC::MI];
-#pragma unroll
-        for (int mi = 0; mi < PC::MI; ++mi) af[mi] = sA[mi * 8 * KPAD + kk];
-        if (kk + 4 < BK) {
-#pragma unroll
-          for (int ni = 0; ni < PC::NI; ++ni) bn[ni] = __dmul_rn(sB[ni * 8 * KPAD + kk + 4], sE[eoff[ni] + kk + 4]);
-        }
-#pragma unroll
-        for (int mi = 0; mi < PC::MI; ++mi)
-#pragma unroll
-          for (int ni = 0; ni < PC::NI; ++ni) dmma884(acc[mi][ni], af[mi], bf[ni]);
-#pragma unroll
-        for (int ni = 0; ni < PC::NI; ++ni) bf[ni] = bn[ni];
-      }
-      if (crb == nrb - 1) {  // the last row block sees every k slab once: the mean rides along there
-        const double* sBq = smem + stage * SEP_STAGE + SEP_A + p * KPAD;
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          const int k = h * 8 + kk;
-          mean_part += __ldg(a.alpha + ck + k) * __dmul_rn(sBq[k], sE[prow + k]);
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_empty[stage]);  // this warp no longer reads the stage
-      ck += BK;
-      if (ck >= c_kend) {  // row block finished: fold its rows into the column norms
+      for (int it = 0; it < tot; ++it, ++gslab) {
+        const unsigned stage = gslab % SEP_STAGES;
+        mbar_wait(&bar_full[stage], (gslab / SEP_STAGES) & 1);
+        const double* sA = smem + stage * SEP_STAGE + (wm * PC::WTM + g) * KPAD + tg;
+        const double* sB = smem + stage * SEP_STAGE + SEP_A + (wn * PC::WTN + g) * KPAD + tg;
+        const double* sE = smem + stage * SEP_STAGE + SEP_A + SEP_B;
+        // B fragments (Ex * Ey) are prepared one k-step ahead of the DMMAs that use them.  The loads and the
+        // multiply are volatile asm, issued between the two halves of the previous k-step's DMMA burst, so that
+        // ptxas cannot sink them to the point of use (it does when they are plain C++).
+        const uint32_t aB = (uint32_t)__cvta_generic_to_shared(sB);
+        const uint32_t aE = (uint32_t)__cvta_generic_to_shared(sE);
+        auto lds64 = [](uint32_t addr) {
+          double v;
+          asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(addr));
+          return v;
+        };
+        auto vmul = [](double x, double y) {
+          double v;
+          asm volatile("mul.rn.f64 %0, %1, %2;\n" : "=d"(v) : "d"(x), "d"(y));
+          return v;
+        };
+        double bf[PC::NI], bn[PC::NI];
 #pragma unroll
         for (int ni = 0; ni < PC::NI; ++ni)
+          bf[ni] = vmul(lds64(aB + 8 * (ni * 8 * KPAD)), lds64(aE + 8 * eoff[ni]));
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            double v = csq_s[2 * ni + e][t];
+        for (int kk = 0; kk < BK; kk += 4) {
+          double af[PC::MI];
 #pragma unroll
-            for (int mi = 0; mi < PC::MI; ++mi) {
-              v += acc[mi][ni][e] * acc[mi][ni][e];
-              acc[mi][ni][e] = 0.0;
-            }
-            csq_s[2 * ni + e][t] = v;
+          for (int mi = 0; mi < PC::MI; ++mi) af[mi] = sA[mi * 8 * KPAD + kk];
+#pragma unroll
+          for (int mi = 0; mi < PC::MI / 2; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < PC::NI; ++ni) dmma884(acc[mi][ni], af[mi], bf[ni]);
+          if (kk + 4 < BK) {
+#pragma unroll
+            for (int ni = 0; ni < PC::NI; ++ni)
+              bn[ni] = vmul(lds64(aB + 8 * (ni * 8 * KPAD + kk + 4)), lds64(aE + 8 * (eoff[ni] + kk + 4)));
           }
-        ck = 0;
-        ++crb;
-        c_kend = blk_kend(crb);
+#pragma unroll
+          for (int mi = PC::MI / 2; mi < PC::MI; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < PC::NI; ++ni) dmma884(acc[mi][ni], af[mi], bf[ni]);
+#pragma unroll
+          for (int ni = 0; ni < PC::NI; ++ni) bf[ni] = bn[ni];
+        }
+        if (crb == nrb - 1) {  // the last row block sees every k slab once: the mean rides along there
+          const double* sBq = smem + stage * SEP_STAGE + SEP_A + p * KPAD;
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            const int k = h * 8 + kk;
+            mean_part += __ldg(a.alpha + ck + k) * __dmul_rn(sBq[k], sE[prow + k]);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_empty[stage]);  // this warp no longer reads the stage
+        ck += BK;
+        if (ck >= c_kend) {  // row block finished: fold its rows into the column norms
+#pragma unroll
+          for (int ni = 0; ni < PC::NI; ++ni)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              double v = csq_s[2 * ni + e][t];
+#pragma unroll
+              for (int mi = 0; mi < PC::MI; ++mi) {
+                v += acc[mi][ni][e] * acc[mi][ni][e];
+                acc[mi][ni][e] = 0.0;
+              }
+              csq_s[2 * ni + e][t] = v;
+            }
+          ck = 0;
+          ++crb;
+          c_kend = blk_kend(crb);
+        }
       }
-      // refill: the slab STAGES-1 ahead goes into the stage consumed one iteration ago, so the wait
-      // inside produce() is for work the other warps finished a whole slab earlier
-      if (it + SEP_STAGES - 1 < tot) produce(gslab + SEP_STAGES - 1);
+#pragma unroll
+      for (int ni = 0; ni < PC::NI; ++ni)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          double v = csq_s[2 * ni + e][t];
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          if (g == 0) red[wm][wn * PC::WTN + ni * 8 + tg * 2 + e] = v;
+        }
+      mred[h][p] = mean_part;
     }
-#pragma unroll
-    for (int ni = 0; ni < PC::NI; ++ni)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        double v = csq_s[2 * ni + e][t];
-        v += __shfl_xor_sync(0xffffffffu, v, 4);
-        v += __shfl_xor_sync(0xffffffffu, v, 8);
-        v += __shfl_xor_sync(0xffffffffu, v, 16);
-        if (g == 0) red[wm][wn * PC::WTN + ni * 8 + tg * 2 + e] = v;
-      }
-    mred[h][p] = mean_part;
-    __syncthreads();
+    asm volatile("bar.sync 1, 256;\n" ::: "memory");  // consumer warps only
     if (t < nvalid) {
       double ss = 0.0;
 #pragma unroll
@@ -345,7 +382,7 @@ __global__ void __launch_bounds__(PC::THREADS, 1) posterior_lattice_kernel(PostA
       a.std[o] = sqrt(var * (a.y_std * a.y_std));
       if (a.zpred) a.zpred[o] = pow(10.0, mu);
     }
-    __syncthreads();
+    asm volatile("bar.sync 1, 256;\n" ::: "memory");
   }
 }
 
@@ -369,7 +406,7 @@ static int launch_lattice(PostArgs& a, double* tables, int max_ctas, cudaStream_
   if (max_ctas > 0 && ctas > max_ctas) ctas = max_ctas;
   if (cudaFuncSetAttribute(posterior_lattice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEP_SMEM) != cudaSuccess)
     return IPP_ERR_CUDA;
-  posterior_lattice_kernel<<<ctas, PC::THREADS, SEP_SMEM, st>>>(a, Ex, Ey, ldt);
+  posterior_lattice_kernel<<<ctas, LAT_THREADS, SEP_SMEM, st>>>(a, Ex, Ey, ldt);
   IPP_LAUNCH_CHECK();
   return IPP_OK;
 }
