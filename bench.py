@@ -401,6 +401,42 @@ def run_b200(args, wl, rank, world, local_rank):
     barrier()
     br_e2e = B * reps / (time.perf_counter() - t0)
     br_dev_ms = scorer.time_device_pass(3, tree, ctx, reps=20)
+
+    # the same scoring pass over a forest of 64 independent trees (configs[4]: 64 rounds per batch): the
+    # throughput regime of the kernels, one launch sequence for 64 x B branches
+    class Forest:
+        def __init__(self, trees):
+            self.n = sum(len(x) for x, _ in trees)
+            self._xy = np.ascontiguousarray(np.vstack([x for x, _ in trees]))
+            off, par = 0, []
+            for x, p_ in trees:
+                par.append(np.where(p_ >= 0, p_ + off, -1))
+                off += len(x)
+            self.parent0 = np.concatenate(par)
+
+        def points(self):
+            return self._xy
+
+        def history_csr(self):
+            return np.zeros(self.n + 1, dtype=np.int32), np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.int32)
+
+    forest = Forest([synth_tree(B, W, 5000 + 64 * seed + r) for r in range(64)])
+    forest_ms = scorer.time_device_pass(3, forest, ctx, reps=5)
+
+    # Gram build (HBM-write bound): the dense n x n prior kernel block the selectors ask for
+    Xd = torch.from_numpy(X).cuda()
+    Kd = torch.empty((n, n), dtype=torch.float64, device="cuda")
+    lib = _lib.load()
+    for _ in range(3):
+        lib.ipp_gram_rbf(_lib.ptr(Xd), n, None, 0, 1.0, 1.0, 0.0, _lib.ptr(Kd), n, _lib.stream_ptr())
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(10):
+        lib.ipp_gram_rbf(_lib.ptr(Xd), n, None, 0, 1.0, 1.0, 0.0, _lib.ptr(Kd), n, _lib.stream_ptr())
+    g1.record()
+    torch.cuda.synchronize()
+    gram_ms = g0.elapsed_time(g1) / 10
+    del Kd
     if world > 1:
         t = torch.tensor([br_dev_ms, 1.0 / br_e2e], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -475,12 +511,16 @@ def run_b200(args, wl, rank, world, local_rank):
             "fit": {"lml_grad_eval_ms": lml_ms, "lml_grad_evals_per_s": 1e3 / lml_ms,
                     "tflops": float(NP) ** 3 / (lml_ms * 1e-3) / 1e12, "full_fit_11_restarts": full_fit,
                     "cpu_lml_grad_eval_ms": cpu_post["lml_grad_eval_ms"], "cpu_cores": cpu_post["cores"]},
+            "gram": {"ms": gram_ms, "n": n, "GBps_written": 8.0 * n * n / (gram_ms * 1e-3) / 1e9,
+                     "frac_of_measured_hbm": 8.0 * n * n / (gram_ms * 1e-3) / 1e9 / hbm, "bound": "hbm (write)"},
             "planning_step": {"ms": plan_ms, "agents": agents, "branches_per_agent": per_agent,
                               "mode": "lazy GP refits (DESIGN.md section 5): per agent tree scoring (point_source_gain_all) + "
                                       "stage-2 argmax + stage-1 mutual-information/penalty selector, host arrays in and out"},
             "branch_gain": {"value": world * B / (br_dev_ms * 1e-3), "unit": "branch evals/s", "ms_per_batch": br_dev_ms,
                             "branches": B, "variant": "point_source_gain_all", "observations": n,
                             "e2e": {"value": world * br_e2e, "unit": "branch evals/s"},
+                            "forest_64_rounds": {"value": world * 64 * B / (forest_ms * 1e-3), "unit": "branch evals/s",
+                                                 "ms_per_batch": forest_ms, "branches": 64 * B},
                             "cpu_baseline": {"value": cpu_br["evals_per_s"], "cores": 1, "kind": "port",
                                              "sample": f"{cpu_br['sample_branches']} branches, pure-Python gain function"}},
             "clocks": clocks,

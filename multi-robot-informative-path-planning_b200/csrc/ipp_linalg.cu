@@ -123,6 +123,48 @@ __global__ void __launch_bounds__(256) gram_rbf_kernel(const double* __restrict_
   }
 }
 
+// Symmetric case of the public Gram: one CTA per LOWER 64x64 tile computes it once (half the exp() calls, which
+// bound this kernel together with the 8 n^2 bytes it must write) and stores both the tile and, through a
+// padded shared-memory transpose, its mirror image -- every global store a full 512-byte row segment,
+// streaming (evict-first) because the matrix is written once and is larger than L2 at n = 5000.
+__global__ void __launch_bounds__(256) gram_sym_kernel(const double* __restrict__ X, int n, double c, double l,
+                                                       double jitter, double* __restrict__ out, long ld) {
+  __shared__ double sx[2][BLK], sy[2][BLK];
+  __shared__ double tile[BLK][BLK + 1];
+  const int b = blockIdx.x, t = threadIdx.x;
+  int ti = (int)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
+  while ((long)(ti + 1) * (ti + 2) / 2 <= b) ++ti;
+  while ((long)ti * (ti + 1) / 2 > b) --ti;
+  const int tj = b - ti * (ti + 1) / 2;
+  const int i0 = ti * BLK, j0 = tj * BLK;
+  if (t < 2 * BLK) {
+    const int which = t / BLK, e = t % BLK, idx = (which ? j0 : i0) + e;
+    double vx = 0.0, vy = 0.0;
+    if (idx < n) {
+      vx = __ddiv_rn(X[2 * idx], l);
+      vy = __ddiv_rn(X[2 * idx + 1], l);
+    }
+    sx[which][e] = vx;
+    sy[which][e] = vy;
+  }
+  __syncthreads();
+  const int cc = t & 63, rq = t >> 6;
+#pragma unroll 4
+  for (int it = 0; it < BLK / 4; ++it) {
+    const int r = rq + 4 * it, gi = i0 + r, gj = j0 + cc;
+    const double v = (gi == gj) ? __dadd_rn(c, jitter) : rbf_scaled(sx[0][r], sy[0][r], sx[1][cc], sy[1][cc], c);
+    tile[r][cc] = v;
+    if (gi < n && gj < n) __stcs(out + (long)gi * ld + gj, v);
+  }
+  if (ti == tj) return;
+  __syncthreads();
+#pragma unroll 4
+  for (int it = 0; it < BLK / 4; ++it) {
+    const int r = rq + 4 * it, gi = j0 + r, gj = i0 + cc;  // mirror tile: row = a column index of the computed tile
+    if (gi < n && gj < n) __stcs(out + (long)gi * ld + gj, tile[cc][r]);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Blocked right-looking Cholesky as ONE persistent cooperative kernel (one CTA per SM, grid-wide
 // barriers between dependent phases) instead of three launches per 64-column panel:
@@ -820,8 +862,13 @@ int ipp_gram_rbf(const double* X, int n, const double* Y, int m, double c, doubl
     m = n;
   }
   if (m <= 0 || ldk < m) return IPP_ERR_ARG;
-  dim3 grid((m + BLK - 1) / BLK, (n + BLK - 1) / BLK);
-  gram_rbf_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, n, Y, m, c, l, jitter, symmetric, K, (long)ldk);
+  if (symmetric) {
+    const long T = (n + BLK - 1) / BLK;
+    gram_sym_kernel<<<(unsigned)(T * (T + 1) / 2), 256, 0, (cudaStream_t)stream>>>(X, n, c, l, jitter, K, (long)ldk);
+  } else {
+    dim3 grid((m + BLK - 1) / BLK, (n + BLK - 1) / BLK);
+    gram_rbf_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, n, Y, m, c, l, jitter, 0, K, (long)ldk);
+  }
   IPP_LAUNCH_CHECK();
   return IPP_OK;
 }

@@ -223,8 +223,11 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) posterior_lattice_kernel(PostA
       const int iy1 = min(iy0 + 1, a.ny - 1);
       const int nvalid = (int)min((long)QT, a.g_end - gq0);
       // ---- producer warpgroup: 16-byte cp.async (LDGSTS) into the padded, bank-conflict-free stage layout; each
-      // thread's copies complete on the stage's full barrier (cp.async.mbarrier.arrive.noinc).  Per-row 128-byte
-      // bulk copies (UBLKCP) were tried here and ran 3x slower: ~260 small bulk requests per slab swamp the unit.
+      // thread's copies complete on the stage's full barrier (cp.async.mbarrier.arrive.noinc).  Two alternatives
+      // were measured and rejected at C4 (769 ms with this version): per-row 128-byte bulk copies (UBLKCP), 3x
+      // slower -- ~260 small bulk requests per slab swamp the unit; and multiplying Ex * Ey in this warpgroup
+      // (LDG, DMUL, STS) so that the DMMA warps load finished k* values, 880-900 ms -- the copy warps then sit on
+      // L2 latency with too few registers to keep a slab of loads in flight.
       int prb = 0, pk = 0, p_row0 = 0, p_rlim = blk_rlim(0), p_kend = blk_kend(0);
       for (int it = 0; it < tot; ++it, ++gslab) {
         const unsigned stage = gslab % SEP_STAGES, use = gslab / SEP_STAGES;
