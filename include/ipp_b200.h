@@ -46,10 +46,12 @@ int ipp_gram_rbf(const double* X, int n, const double* Y, int m, double c, doubl
 /* One log-marginal-likelihood (+ gradient w.r.t. log c, log l) evaluation.
  * X: n x 2, y: n (already normalised), hyp: DEVICE {c, l, jitter}.  On return the result block
  * in vbuf holds lml / gradient / info; Kbuf holds L (lower, row NP = z = L^-1 y), Wbuf = L^-1.
+ * max_ctas > 1 caps the grid of the cooperative Cholesky kernel, so that several evaluations (the
+ * independent optimiser restarts, one stream and one buffer set each) can be resident at once; 0 = whole GPU.
  * Replaces GaussianProcessRegressor.log_marginal_likelihood(theta, eval_gradient=True):
  * sklearn _gpr.py:541-656, the objective of the 11 L-BFGS-B runs of fit (_gpr.py:302-333). */
 int ipp_gp_lml_grad(const double* X, const double* y, int n, const double* hyp, double* Kbuf, double* Wbuf,
-                    double* Tbuf, double* vbuf, int with_grad, void* stream);
+                    double* Tbuf, double* vbuf, int with_grad, int max_ctas, void* stream);
 
 /* Final factorisation at the chosen theta: L_ in Kbuf, W = L_^-1 in Wbuf, alpha_ = L_^-T L_^-1 y
  * in vbuf (offset out[7]), scaled coordinates in slots 0/1, lml in the result block.

@@ -681,7 +681,7 @@ static cudaError_t opt_in_smem(K kernel, size_t bytes) {
 static bool use_small_tiles(int np) { return np <= 1536; }
 
 template <class C>
-static int chol_inplace(double* Kb, double* Wb, double* info, const GpDims& d, cudaStream_t st) {
+static int chol_inplace(double* Kb, double* Wb, double* info, const GpDims& d, cudaStream_t st, int max_ctas = 0) {
   constexpr size_t SYRK_SM = gemm_smem_bytes<C, Lay::KCONT, Lay::KCONT>();
   constexpr size_t SM = SYRK_SM > PANEL_SMEM ? SYRK_SM : PANEL_SMEM;
   if (opt_in_smem(chol_coop_kernel<C>, SM) != cudaSuccess) return IPP_ERR_CUDA;
@@ -696,6 +696,7 @@ static int chol_inplace(double* Kb, double* Wb, double* info, const GpDims& d, c
   if (useful < d.rows / BLK) useful = d.rows / BLK;
   int ctas = sms * per_sm;
   if (ctas > useful + 1) ctas = useful + 1;  // + the panel CTA
+  if (max_ctas > 1 && ctas > max_ctas) ctas = max_ctas;  // leave SMs to concurrent factorisations (restart streams)
   if (ctas < 1) ctas = 1;
   long ld = d.ld;
   int rows = d.rows, np = d.np;
@@ -739,12 +740,13 @@ static int lml_grad_launch(const double* Wb, double* vbuf, const double* hyp, co
 }
 
 static int gp_factor(const double* X, const double* y, int n, const double* hyp, double* Kb, double* Wb, double* Tb,
-                     double* vbuf, bool invert, cudaStream_t st) {
+                     double* vbuf, bool invert, cudaStream_t st, int max_ctas) {
   if (n <= 0 || !X || !y || !hyp || !Kb || !Wb || !vbuf) return IPP_ERR_ARG;
   const GpDims d = gp_dims(n);
   gram_fit_kernel<<<dim3(d.np / BLK, d.rows / BLK), 256, 0, st>>>(X, y, hyp, Kb, vbuf, d);
   double* info = vbuf + v_result_off(d) + 3;
-  int rc = use_small_tiles(d.np) ? chol_inplace<Cfg64>(Kb, Wb, info, d, st) : chol_inplace<Cfg128>(Kb, Wb, info, d, st);
+  int rc = use_small_tiles(d.np) ? chol_inplace<Cfg64>(Kb, Wb, info, d, st, max_ctas)
+                                 : chol_inplace<Cfg128>(Kb, Wb, info, d, st, max_ctas);
   if (rc != IPP_OK) return rc;
   if (invert) {
     if (!Tb) return IPP_ERR_ARG;
@@ -874,9 +876,9 @@ int ipp_gram_rbf(const double* X, int n, const double* Y, int m, double c, doubl
 }
 
 int ipp_gp_lml_grad(const double* X, const double* y, int n, const double* hyp, double* Kbuf, double* Wbuf,
-                    double* Tbuf, double* vbuf, int with_grad, void* stream) {
+                    double* Tbuf, double* vbuf, int with_grad, int max_ctas, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = gp_factor(X, y, n, hyp, Kbuf, Wbuf, Tbuf, vbuf, with_grad != 0, st);
+  int rc = gp_factor(X, y, n, hyp, Kbuf, Wbuf, Tbuf, vbuf, with_grad != 0, st, max_ctas);
   if (rc != IPP_OK) return rc;
   const GpDims d = gp_dims(n);
   int ntiles = 0;
@@ -896,7 +898,7 @@ int ipp_gp_lml_grad(const double* X, const double* y, int n, const double* hyp, 
 int ipp_gp_fit_final(const double* X, const double* y, int n, const double* hyp, double* Kbuf, double* Wbuf,
                      double* Tbuf, double* vbuf, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = gp_factor(X, y, n, hyp, Kbuf, Wbuf, Tbuf, vbuf, true, st);
+  int rc = gp_factor(X, y, n, hyp, Kbuf, Wbuf, Tbuf, vbuf, true, st, 0);
   if (rc != IPP_OK) return rc;
   const GpDims d = gp_dims(n);
   double* w = vbuf + V_W * d.npv;

@@ -17,6 +17,7 @@ buffers and the stream.  No CPU fallback.
 from __future__ import annotations
 
 import ctypes as C
+import threading
 import warnings
 
 import numpy as np
@@ -205,6 +206,11 @@ class GaussianProcessRegressor:
         self.n_targets = n_targets
         self.random_state = random_state
         self._ws = _Workspace()
+        self._count_lock = threading.Lock()
+        self._restart_slots = []
+        # optimiser restarts are independent once their start points are drawn: run them on this many streams
+        # (None = automatic: all of them for small problems, 4 when one buffer set is already > 100 MB; 1 = serial)
+        self.restart_streams = None
         self.n_lml_evals_ = 0
         self.lazy = False
         self._pending = False
@@ -230,12 +236,12 @@ class GaussianProcessRegressor:
         self._yd = dev[2 * n:]
         self.h2d_bytes_ = 24 * n
 
-    def _eval_device(self, c, l, with_grad, final=False):
-        """Launch one LML (+gradient) evaluation or the final factorisation; returns the 8-double
-        result block on the host."""
+    def _eval_device(self, c, l, with_grad, final=False, ws=None, max_ctas=0):
+        """Launch one LML (+gradient) evaluation or the final factorisation on the calling thread's
+        current stream; returns the 8-double result block on the host."""
         torch = _lib.require_cuda()
         lib = _lib.load()
-        ws = self._ws
+        ws = self._ws if ws is None else ws
         n = self.X_train_.shape[0]
         ws.hyp_host[0] = c
         ws.hyp_host[1] = l
@@ -248,7 +254,7 @@ class GaussianProcessRegressor:
             _lib.check(rc, "ipp_gp_fit_final")
         else:
             rc = lib.ipp_gp_lml_grad(_lib.ptr(self._Xd), _lib.ptr(self._yd), n, _lib.ptr(ws.hyp), _lib.ptr(ws.K),
-                                     _lib.ptr(ws.W), _lib.ptr(ws.T), _lib.ptr(ws.v), 1 if with_grad else 0, st)
+                                     _lib.ptr(ws.W), _lib.ptr(ws.T), _lib.ptr(ws.v), 1 if with_grad else 0, int(max_ctas), st)
             _lib.check(rc, "ipp_gp_lml_grad")
         ws.res_host.copy_(ws.result, non_blocking=True)
         torch.cuda.current_stream().synchronize()
@@ -267,11 +273,12 @@ class GaussianProcessRegressor:
             self._kernel_fitted.theta = theta
         return self._lml(theta, eval_gradient)
 
-    def _lml(self, theta, eval_gradient):
+    def _lml(self, theta, eval_gradient, ws=None, max_ctas=0):
         theta = np.asarray(theta, dtype=float)
         c, l = float(np.exp(theta[0])), float(np.exp(theta[1]))
-        res = self._eval_device(c, l, eval_gradient)
-        self.n_lml_evals_ += 1
+        res = self._eval_device(c, l, eval_gradient, ws=ws, max_ctas=max_ctas)
+        with self._count_lock:
+            self.n_lml_evals_ += 1
         if res[3] != 0.0 or not np.isfinite(res[0]):
             return (-np.inf, np.zeros_like(theta)) if eval_gradient else -np.inf
         if eval_gradient:
@@ -345,13 +352,66 @@ class GaussianProcessRegressor:
                 return -self._lml(theta, False)
 
             bounds = self._kernel_fitted.bounds
-            optima = [self._constrained_optimization(obj_func, t0, bounds) for t0 in self._starts]
+            workers = self._restart_workers(len(self._starts))
+            if workers > 1:
+                optima = self._optimise_concurrently(self._starts, bounds, workers)
+            else:
+                optima = [self._constrained_optimization(obj_func, t0, bounds) for t0 in self._starts]
             lml_values = [o[1] for o in optima]
             self._kernel_fitted.theta = optima[int(np.argmin(lml_values))][0]
             self._lml_value = -np.min(lml_values)
             self._finalize(set_lml=False)
         else:
             self._finalize(set_lml=True)
+
+    def _restart_workers(self, n_starts):
+        if n_starts <= 1:
+            return 1
+        if self.restart_streams is not None:
+            return max(1, min(int(self.restart_streams), n_starts))
+        return min(n_starts, 11 if self._ws.layout[0] <= 2048 else 4)
+
+    def _optimise_concurrently(self, starts, bounds, workers):
+        """The restarts of _gpr.py:312-333 side by side: one host thread, one CUDA stream and one device
+        buffer set per worker.  Every optimisation sees exactly the objective values it would see alone
+        (same kernels, same launch geometry), so the optima -- and the first-minimum choice among them,
+        taken in start order -- are those of the serial loop; only the wall time changes."""
+        import queue
+        from concurrent.futures import ThreadPoolExecutor
+
+        torch = _lib.require_cuda()
+        n = self.X_train_.shape[0]
+        device = torch.cuda.current_device()
+        while len(self._restart_slots) < workers:
+            self._restart_slots.append((_Workspace(), torch.cuda.Stream()))
+        slots = queue.SimpleQueue()
+        for ws, stream in self._restart_slots[:workers]:
+            ws.ensure(n)
+            slots.put((ws, stream))
+        uploaded = torch.cuda.Event()
+        uploaded.record()
+        sms = torch.cuda.get_device_properties(device).multi_processor_count
+        cap = max(8, sms // workers)
+
+        def run(t0):
+            torch.cuda.set_device(device)
+            ws, stream = slots.get()
+            try:
+                with torch.cuda.stream(stream):
+                    stream.wait_event(uploaded)
+
+                    def obj_func(theta, eval_gradient=True):
+                        if eval_gradient:
+                            lml, grad = self._lml(theta, True, ws=ws, max_ctas=cap)
+                            return -lml, -grad
+                        return -self._lml(theta, False, ws=ws, max_ctas=cap)
+
+                    return self._constrained_optimization(obj_func, t0, bounds)
+            finally:
+                slots.put((ws, stream))
+
+        with ThreadPoolExecutor(max_workers=workers) as pool:
+            return list(pool.map(run, starts))
 
     # fitted attributes resolve a pending lazy fit first
     @property

@@ -301,6 +301,23 @@ def test_not_positive_definite_is_reported(G):
     assert v == -np.inf and np.array_equal(gr, np.zeros(2))
 
 
+def test_concurrent_restart_streams_equal_serial(G):
+    """The optimiser restarts run on several streams / host threads by default; the optimum, its LML, the number of
+    objective evaluations and the RNG position must be exactly those of the serial loop of _gpr.py:312-337."""
+    X, y = _make(300, 15, seed=2)
+    out = []
+    for streams in (1, 3, None):
+        gp = G.GaussianProcessRegressor(kernel=G.ConstantRBFKernel(1.0, 1.0), n_restarts_optimizer=5, normalize_y=True)
+        gp.restart_streams = streams
+        np.random.seed(5)
+        gp.fit(X, y)
+        out.append((gp.kernel_.theta.copy(), gp.log_marginal_likelihood_value_, gp.n_lml_evals_, np.random.uniform(),
+                    gp.predict(X[:50] + 0.01, return_std=True)))
+    for o in out[1:]:
+        assert np.array_equal(o[0], out[0][0]) and o[1] == out[0][1] and o[2] == out[0][2] and o[3] == out[0][3]
+        assert np.array_equal(o[4][0], out[0][4][0]) and np.array_equal(o[4][1], out[0][4][1])
+
+
 def test_unfitted_prior_and_negative_variance_warning(G):
     gp = G.GaussianProcessRegressor(kernel=G.ConstantRBFKernel(2.0, 1.0))
     m, s = gp.predict(np.zeros((3, 2)), return_std=True)
