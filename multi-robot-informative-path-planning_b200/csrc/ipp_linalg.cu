@@ -221,14 +221,37 @@ __device__ __forceinline__ void potf2_block(double* D, int t, int first_index, d
       }
     }
     __syncthreads();
-    // rank-8 update of the trailing lower triangle; (r, cc) from shifts, not divisions
-    for (int e = t; e < BLK * BLK; e += NT) {
-      const int r = e >> 6, cc = e & 63;
-      if (cc >= jb + 8 && cc <= r) {
-        double v = D[r * PSTR + cc];
+    // rank-8 update of the trailing lower triangle in 4x4 register tiles (16 independent FMA chains per thread,
+    // 5 shared loads per 8 FMAs instead of 17); every entry still sees its 8 subtractions in column order
+    for (int blk = t; blk < (BLK / 4) * (BLK / 4); blk += NT) {
+      const int br = blk >> 4, bc = blk & 15, r0 = 4 * br, c0 = 4 * bc;
+      if (bc <= br && c0 >= jb + 8) {
+        double d[4][4];
 #pragma unroll
-        for (int pp = 0; pp < 8; ++pp) v -= D[r * PSTR + jb + pp] * D[cc * PSTR + jb + pp];
-        D[r * PSTR + cc] = v;
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) d[i][j] = D[(r0 + i) * PSTR + c0 + j];
+#pragma unroll
+        for (int ph = 0; ph < 8; ph += 4) {
+          double pr[4][4], pc[4][4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int pp = 0; pp < 4; ++pp) {
+              pr[i][pp] = D[(r0 + i) * PSTR + jb + ph + pp];
+              pc[i][pp] = D[(c0 + i) * PSTR + jb + ph + pp];
+            }
+#pragma unroll
+          for (int pp = 0; pp < 4; ++pp)
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) d[i][j] -= pr[i][pp] * pc[j][pp];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) D[(r0 + i) * PSTR + c0 + j] = d[i][j];
       }
     }
     __syncthreads();
@@ -357,7 +380,8 @@ __device__ __forceinline__ void chol_trsm_block(double* __restrict__ A, long ld,
 // Trailing update of one lower tile after panel k: C[i][j] -= sum_p P[i][p] P[j][p], i >= j >= 64(k+1).
 template <class C>
 __device__ __forceinline__ void chol_syrk_tile(double* __restrict__ A, long ld, int rows_total, int np, int k, int b,
-                                               double* smem) {
+                                               double* smem, long long* tile_clk = nullptr) {
+  const long long c0 = tile_clk ? clock64() : 0;
   const int skip = k + 1;  // diagonal block (k+1, k+1) is updated and factored by chol_diag_update_step
   const int j0 = BLK * k, r0 = j0 + BLK;
   int ti = (int)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
@@ -366,6 +390,17 @@ __device__ __forceinline__ void chol_syrk_tile(double* __restrict__ A, long ld, 
   const int tj = b - ti * (ti + 1) / 2;
   const int row0 = r0 + ti * C::BM, col0 = r0 + tj * C::BN;
   if (row0 >= rows_total || col0 >= np) return;
+  // The C tile is read-modify-written once per panel and, for n >~ 4000, the trailing matrix no longer fits in
+  // L2: start pulling the tile's 128-byte lines into L2 now, so that the epilogue's loads (measured 10 us per tile
+  // from HBM against 1.8 us from L2) overlap the DMMA main loop instead of following it.
+  {
+    constexpr int LINES_PER_ROW = C::BN * 8 / 128;
+    for (int e = threadIdx.x; e < C::BM * LINES_PER_ROW; e += C::THREADS) {
+      const int gr = row0 + e / LINES_PER_ROW, gc = col0 + (e % LINES_PER_ROW) * 16;
+      if (gr < rows_total && gc < np && (gc >> 6) <= (gr >> 6))
+        asm volatile("prefetch.global.L2 [%0];\n" ::"l"(A + (long)gr * ld + gc));
+    }
+  }
   double acc[C::MI][C::NI][2];
   zero_acc<C>(acc);
   auto fillA = [&](double* s, int k0) {
@@ -375,11 +410,44 @@ __device__ __forceinline__ void chol_syrk_tile(double* __restrict__ A, long ld, 
     load_tile_async<C::BN, Lay::KCONT, C::THREADS>(s, A, ld, col0, k0, np, j0 + BLK);
   };
   gemm_mainloop<C, Lay::KCONT, Lay::KCONT>(acc, smem, j0, j0 + BLK, fillA, fillB);
-  for_each_acc<C>(acc, [&](int r, int c, double v) {
-    int gr = row0 + r, gc = col0 + c;
-    const int br = gr >> 6, bc = gc >> 6;
-    if (gr < rows_total && gc < np && bc <= br && !(br == skip && bc == skip)) A[(long)gr * ld + gc] -= v;
-  });
+  const long long c1 = tile_clk ? clock64() : 0;
+  // C -= acc as 16-byte read-modify-writes, all loads of half a warp tile in flight before the first store
+  // (the compiler's own schedule kept ~8 scalar loads in flight: 8 dependent trips to HBM per tile).
+  {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wm = warp / C::WARPS_N, wn = warp % C::WARPS_N, g = lane >> 2, tg = lane & 3;
+    constexpr int HALF = C::MI >= 8 ? C::MI / 4 : (C::MI / 2 > 0 ? C::MI / 2 : 1);  // rows of 8x8 blocks per batch
+#pragma unroll
+    for (int h0 = 0; h0 < C::MI; h0 += HALF) {
+      double2 cv[HALF][C::NI];
+      bool ok[HALF][C::NI];
+#pragma unroll
+      for (int mi = 0; mi < HALF; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < C::NI; ++ni) {
+          const int gr = row0 + wm * C::WTM + (h0 + mi) * 8 + g, gc = col0 + wn * C::WTN + ni * 8 + tg * 2;
+          const int br = gr >> 6, bc = gc >> 6;
+          ok[mi][ni] = gr < rows_total && gc < np && bc <= br && !(br == skip && bc == skip);
+          if (ok[mi][ni]) cv[mi][ni] = __ldcg(reinterpret_cast<const double2*>(A + (long)gr * ld + gc));
+        }
+#pragma unroll
+      for (int mi = 0; mi < HALF; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < C::NI; ++ni) {
+          const int gr = row0 + wm * C::WTM + (h0 + mi) * 8 + g, gc = col0 + wn * C::WTN + ni * 8 + tg * 2;
+          if (ok[mi][ni])
+            *reinterpret_cast<double2*>(A + (long)gr * ld + gc) =
+                make_double2(cv[mi][ni].x - acc[h0 + mi][ni][0], cv[mi][ni].y - acc[h0 + mi][ni][1]);
+        }
+    }
+  }
+  if (tile_clk) {
+    __syncthreads();
+    const long long c2 = clock64();
+    tile_clk[0] += c1 - c0;  // operand pipeline + DMMA
+    tile_clk[1] += c2 - c1;  // read-modify-write of the C tile
+    tile_clk[2] += 1;
+  }
 }
 
 template <class C>
@@ -391,7 +459,8 @@ __global__ void __launch_bounds__(C::THREADS, 1) chol_coop_kernel(double* __rest
   // phase_cycles (nullable): CTA 0's clock64() spent in {barrier 1, panel solve, barrier 2, diagonal block,
   // trailing tiles} summed over the panels -- the evidence for where a latency-bound factorisation goes
   const bool timing = phase_cycles != nullptr && blockIdx.x < 2 && threadIdx.x == 0;  // CTA 0 (panel) and CTA 1 (tiles)
-  long long tc[5] = {0, 0, 0, 0, 0}, t0 = 0;
+  long long tc[5] = {0, 0, 0, 0, 0}, t0 = 0, tile_clk[3] = {0, 0, 0};
+  long long* tclk = (phase_cycles != nullptr && blockIdx.x == 1) ? tile_clk : nullptr;  // uniform over CTA 1
   auto tick = [&](int slot) {
     if (timing) {
       const long long now = clock64();
@@ -419,13 +488,16 @@ __global__ void __launch_bounds__(C::THREADS, 1) chol_coop_kernel(double* __rest
       if (gridDim.x == 1) {
         for (int b = 0; b < ntile; ++b) chol_syrk_tile<C>(A, ld, rows_total, np, k, b, smem);
       } else if (blockIdx.x > 0) {
-        for (int b = blockIdx.x - 1; b < ntile; b += gridDim.x - 1) chol_syrk_tile<C>(A, ld, rows_total, np, k, b, smem);
+        for (int b = blockIdx.x - 1; b < ntile; b += gridDim.x - 1) chol_syrk_tile<C>(A, ld, rows_total, np, k, b, smem, tclk);
       }
       tick(4);
     }
   }
-  if (timing)
+  if (timing) {
     for (int q = 0; q < 5; ++q) phase_cycles[5 * blockIdx.x + q] = (double)tc[q];
+    if (blockIdx.x == 1)  // (timing is true for thread 0 only)
+      for (int q = 0; q < 3; ++q) phase_cycles[10 + q] = (double)tile_clk[q];
+  }
 }
 
 // W_kk = L_kk^-1 for every 64x64 diagonal block at once (level 0 of the triangular inverse).
@@ -472,13 +544,19 @@ __global__ void __launch_bounds__(256) diag_inverse_kernel(const double* __restr
 template <class C, int STEP>
 __global__ void __launch_bounds__(C::THREADS) trtri_level_kernel(const double* __restrict__ L, long ld,
                                                                  double* __restrict__ W, long ldw, double* __restrict__ T,
-                                                                 long ldt, int np, int s) {
+                                                                 long ldt, int np, int s, int pairs) {
   extern __shared__ __align__(16) double smem[];
-  const int p = blockIdx.z;
+  // 1-D grid, heaviest tiles first (the hardware hands out CTAs in index order): the k range of a tile is
+  // triangular -- STEP 1 sums k in [col0, r1), STEP 2 sums k in [r1, row0 + BM) -- so a plain (x, y) order
+  // leaves the longest tiles for the last wave.
+  const int nx = (s + C::BN - 1) / C::BN, ny = (s + C::BM - 1) / C::BM;
+  const int p = blockIdx.x % pairs, rest = blockIdx.x / pairs;
+  const int bx = (STEP == 1) ? rest / ny : rest % nx;
+  const int by = (STEP == 1) ? rest % ny : ny - 1 - rest / nx;
   const int r0 = 2 * p * s, r1 = r0 + s;
   if (r1 >= np) return;
   const int r2 = min(r0 + 2 * s, np);
-  const int row0 = r1 + blockIdx.y * C::BM, col0 = r0 + blockIdx.x * C::BN;
+  const int row0 = r1 + by * C::BM, col0 = r0 + bx * C::BN;
   if (row0 >= r2) return;
   double acc[C::MI][C::NI][2];
   zero_acc<C>(acc);
@@ -701,7 +779,7 @@ static int chol_inplace(double* Kb, double* Wb, double* info, const GpDims& d, c
   long ld = d.ld;
   int rows = d.rows, np = d.np;
   // the tile-partials area of vbuf (free until the gradient kernel runs) receives the phase counters
-  double* phase = (2 * d.max_tiles >= 10) ? info - 3 - 2 * d.max_tiles : nullptr;
+  double* phase = (2 * d.max_tiles >= 13) ? info - 3 - 2 * d.max_tiles : nullptr;
   void* args[] = {(void*)&Kb, (void*)&ld, (void*)&rows, (void*)&np, (void*)&info, (void*)&phase};
   if (cudaLaunchCooperativeKernel((void*)chol_coop_kernel<C>, dim3(ctas), dim3(C::THREADS), args, SM, st) != cudaSuccess)
     return IPP_ERR_CUDA;
@@ -713,17 +791,27 @@ static int chol_inplace(double* Kb, double* Wb, double* info, const GpDims& d, c
 }
 
 template <class C>
-static int trtri_inplace(const double* Kb, double* Wb, double* Tb, const GpDims& d, cudaStream_t st) {
+static int trtri_level(const double* Kb, double* Wb, double* Tb, const GpDims& d, int s, int pairs, cudaStream_t st) {
   constexpr size_t SM = gemm_smem_bytes<C, Lay::KCONT, Lay::MCONT>();
   if (opt_in_smem(trtri_level_kernel<C, 1>, SM) != cudaSuccess) return IPP_ERR_CUDA;
   if (opt_in_smem(trtri_level_kernel<C, 2>, SM) != cudaSuccess) return IPP_ERR_CUDA;
+  const unsigned grid = (unsigned)(((s + C::BN - 1) / C::BN) * ((s + C::BM - 1) / C::BM) * pairs);
+  trtri_level_kernel<C, 1><<<grid, C::THREADS, SM, st>>>(Kb, d.ld, Wb, d.ld, Tb, d.ld, d.np, s, pairs);
+  trtri_level_kernel<C, 2><<<grid, C::THREADS, SM, st>>>(Kb, d.ld, Wb, d.ld, Tb, d.ld, d.np, s, pairs);
+  return IPP_OK;
+}
+
+template <class C>
+static int trtri_inplace(const double* Kb, double* Wb, double* Tb, const GpDims& d, cudaStream_t st) {
   const int nb = d.np / BLK;
   w_clear_kernel<<<dim3(nb, nb), 256, 0, st>>>(Wb, d.ld, d.np);
   for (int s = BLK; s < d.np; s *= 2) {
     const int pairs = (d.np + 2 * s - 1) / (2 * s);
-    dim3 grid((s + C::BN - 1) / C::BN, (s + C::BM - 1) / C::BM, pairs);
-    trtri_level_kernel<C, 1><<<grid, C::THREADS, SM, st>>>(Kb, d.ld, Wb, d.ld, Tb, d.ld, d.np, s);
-    trtri_level_kernel<C, 2><<<grid, C::THREADS, SM, st>>>(Kb, d.ld, Wb, d.ld, Tb, d.ld, d.np, s);
+    // levels whose 128x128 tiling cannot fill the GPU run on 64x64 tiles (4x the CTAs, each a quarter of the work)
+    const int tiles128 = ((s + 127) / 128) * ((s + 127) / 128) * pairs;
+    const int rc = (C::BM > 64 && tiles128 < 148) ? trtri_level<Cfg64>(Kb, Wb, Tb, d, s, pairs, st)
+                                                  : trtri_level<C>(Kb, Wb, Tb, d, s, pairs, st);
+    if (rc != IPP_OK) return rc;
   }
   return IPP_OK;
 }

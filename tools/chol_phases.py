@@ -25,6 +25,9 @@ for n in [int(a) for a in sys.argv[1:]] or [500, 2000, 5000]:
     ntile = (nb * (nb + 1)) // 2
     off = lay[8] - 2 * ntile
     ph10 = gp._ws.v[off:off + 10].cpu().numpy() / 1.965e3  # us at 1965 MHz
+    tl = gp._ws.v[off + 10:off + 13].cpu().numpy()
+    if tl[2] > 0:
+        print(f"   CTA1 trailing tiles: {int(tl[2])} tiles, mainloop {tl[0] / tl[2] / 1.965e3:.1f} us, C read-modify-write {tl[1] / tl[2] / 1.965e3:.1f} us per tile")
     ph = ph10[:5]
     print("   CTA1 per panel: " + ", ".join(f"{v/nb:.1f}" for v in ph10[5:]))
     torch.cuda.synchronize(); t = time.perf_counter()
