@@ -69,12 +69,18 @@ int ipp_gp_fit_final(const double* X, const double* y, int n, const double* hyp,
  * given and nx >= 128 the lattice fast path is used: the RBF cross-covariance factorises over the
  * lattice axes, so two coordinate tables replace the G x n exponentials; without it every element of
  * k* is evaluated with exp() like the explicit-point entry below.
+ * slab_bbox (nullable) + cutoff: block sparsity of k*.  slab_bbox[s] = {xmin, xmax, ymin, ymax} (unscaled
+ * coordinates) of observations 16 s .. 16 s + 15 in the order the state was fitted in; a slab whose box is farther
+ * than `cutoff` from every query of a 128-query tile is skipped.  The caller chooses cutoff = l * sqrt(2 ln(1/eps))
+ * so that every skipped entry of k* is below eps * c (the Python layer: eps = 1e-30, observations fitted in
+ * Morton order so that slabs are compact).  NULL or cutoff <= 0: dense.
  * Replaces gp.predict(r, return_std=True) on the workspace grid: point_source.py:350-351 ->
  * sklearn _gpr.py:446-500, without materialising K_trans (G x n) or V (n x G). */
 int ipp_gp_posterior_grid(const double* Wbuf, const double* vbuf, int n, double c, double l, double y_mean,
                           double y_std, double x0, double x1, int nx, double y0, double y1, int ny,
                           long long g_begin, long long g_end, double* mean, double* std, double* zpred,
-                          int* neg_count, double* tables, int max_ctas, void* stream);
+                          int* neg_count, double* tables, const double* slab_bbox, double cutoff, int max_ctas,
+                          void* stream);
 
 /* Same posterior at m explicit query points Q (m x 2).
  * Replaces gp.predict(leaf_points, return_std=True): src/rrt/rrt_thread.py:375. */

@@ -33,6 +33,8 @@ struct PostArgs {
   double* std;
   double* zpred;
   int* neg_count;
+  const double* slab_bbox;  // [np / 16][4] = {xmin, xmax, ymin, ymax} of each 16-observation slab, or nullptr
+  double cutoff2;           // skip a slab when its box is farther than sqrt(cutoff2) from the tile's queries; <= 0: never
 };
 
 using PC = Cfg128;
@@ -179,6 +181,44 @@ __global__ void __launch_bounds__(256) axis_table_kernel(const double* __restric
 }
 
 constexpr int LAT_THREADS = PC::THREADS + 128;  // 8 DMMA (consumer) warps + one copy (producer) warpgroup
+constexpr int LAT_MASK_WORDS = 32;              // 1024 slabs = 16384 observations; beyond that nothing is skipped
+
+// Block sparsity of the cross-covariance.  With the observations in spatial (Morton) order a 16-observation
+// slab is a compact cluster; when its bounding box is farther than R = l * sqrt(2 ln(1/eps)) from every query
+// of the tile, all 128 x 16 entries of k* are below eps * c (eps = 1e-30 by default: twelve orders of magnitude
+// under the rounding of the terms that are kept), so the slab is skipped -- no copy, no DMMA, no stage.  Each warp
+// evaluates the same test on the same data (one slab per lane, one ballot per 32 slabs), so the copy warps and
+// the DMMA warps agree on the slab sequence without exchanging anything.
+__device__ __forceinline__ void lattice_slab_mask(const PostArgs& a, unsigned* mask, int lane, long gq0, int nvalid) {
+  const int nslab = a.np / BK;
+  const int words = (nslab + 31) / 32;
+  const bool on = a.slab_bbox != nullptr && a.cutoff2 > 0.0 && words <= LAT_MASK_WORDS;
+  const int iy0 = (int)(gq0 / a.nx), ix0 = (int)(gq0 % a.nx);
+  const int ixl = ix0 + nvalid - 1;
+  double qx0, qx1, qy0, qy1;
+  qy0 = a.y0 + iy0 * a.ystep;
+  if (ixl < a.nx) {  // one lattice row
+    qx0 = a.x0 + ix0 * a.xstep;
+    qx1 = a.x0 + ixl * a.xstep;
+    qy1 = qy0;
+  } else {  // the tile wraps into the next row: take the whole x range
+    qx0 = a.x0;
+    qx1 = a.x1;
+    qy1 = a.y0 + (iy0 + 1) * a.ystep;
+  }
+  for (int w = 0; w < min(words, LAT_MASK_WORDS); ++w) {
+    const int sidx = 32 * w + lane;
+    bool act = sidx < nslab;
+    if (act && on) {
+      const double4 b = *reinterpret_cast<const double4*>(a.slab_bbox + 4 * sidx);
+      const double gx = fmax(0.0, fmax(b.x - qx1, qx0 - b.y)), gy = fmax(0.0, fmax(b.z - qy1, qy0 - b.w));
+      act = gx * gx + gy * gy <= a.cutoff2;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, act);
+    if (lane == 0) mask[w] = m;
+  }
+  __syncwarp();
+}
 
 __global__ void __launch_bounds__(LAT_THREADS, 1) posterior_lattice_kernel(PostArgs a, const double* __restrict__ Ex,
                                                                            const double* __restrict__ Ey, long ldt) {
@@ -187,6 +227,7 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) posterior_lattice_kernel(PostA
   __shared__ double mred[2][QT];
   __shared__ double csq_s[2 * PC::NI][PC::THREADS];  // per-thread column norms (kept out of the register file)
   __shared__ __align__(8) uint64_t bar_full[SEP_STAGES], bar_empty[SEP_STAGES];
+  __shared__ unsigned smask[LAT_THREADS / 32][LAT_MASK_WORDS];  // per warp: which k slabs this tile needs
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const long total = a.g_end - a.g_begin;
   const long ntiles = (total + QT - 1) / QT;
@@ -215,7 +256,7 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) posterior_lattice_kernel(PostA
   if (warp >= PC::THREADS / 32) {
     // Register file: the copy warpgroup gives its registers back so that the DMMA warps can hold their
     // 128 accumulator registers plus fragments without spilling (384 threads compile for 168 each).
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;\n");
     const int pt = t - PC::THREADS;  // 0..127 within the copy warpgroup
     for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const long gq0 = a.g_begin + tile * QT;
@@ -228,8 +269,11 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) posterior_lattice_kernel(PostA
       // slower -- ~260 small bulk requests per slab swamp the unit; and multiplying Ex * Ey in this warpgroup
       // (LDG, DMUL, STS) so that the DMMA warps load finished k* values, 880-900 ms -- the copy warps then sit on
       // L2 latency with too few registers to keep a slab of loads in flight.
+      lattice_slab_mask(a, smask[warp], lane, gq0, nvalid);
       int prb = 0, pk = 0, p_row0 = 0, p_rlim = blk_rlim(0), p_kend = blk_kend(0);
-      for (int it = 0; it < tot; ++it, ++gslab) {
+      for (int it = 0; it < tot; ++it) {
+        const int si = pk / BK;
+        if ((smask[warp][si >> 5] >> (si & 31)) & 1u) {
         const unsigned stage = gslab % SEP_STAGES, use = gslab / SEP_STAGES;
         if (use > 0) mbar_wait(&bar_empty[stage], (use - 1) & 1);  // every consumer warp is done with the old contents
         double* s = smem + stage * SEP_STAGE;
@@ -247,6 +291,8 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) posterior_lattice_kernel(PostA
           cp_async16(s + SEP_A + SEP_B + row * BK + kc, Ey + (long)(row ? iy1 : iy0) * ldt + pk + kc, true);
         }
         cp_async_mbar_arrive(&bar_full[stage]);
+        ++gslab;
+        }
         pk += BK;
         if (pk >= p_kend) {
           pk = 0;
@@ -261,7 +307,7 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) posterior_lattice_kernel(PostA
     return;  // the copy warps run ahead across tile boundaries, held back only by the empty barriers
   }
 
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 224;\n");
   for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long gq0 = a.g_begin + tile * QT;
     const int ix0 = (int)(gq0 % a.nx);
@@ -282,7 +328,10 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) posterior_lattice_kernel(PostA
       double mean_part = 0.0;
       int crb = 0, ck = 0, c_kend = blk_kend(0);
 
-      for (int it = 0; it < tot; ++it, ++gslab) {
+      lattice_slab_mask(a, smask[warp], lane, gq0, nvalid);
+      for (int it = 0; it < tot; ++it) {
+        const int si = ck / BK;
+        if ((smask[warp][si >> 5] >> (si & 31)) & 1u) {
         const unsigned stage = gslab % SEP_STAGES;
         mbar_wait(&bar_full[stage], (gslab / SEP_STAGES) & 1);
         const double* sA = smem + stage * SEP_STAGE + (wm * PC::WTM + g) * KPAD + tg;
@@ -338,6 +387,8 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) posterior_lattice_kernel(PostA
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_empty[stage]);  // this warp no longer reads the stage
+        ++gslab;
+        }
         ck += BK;
         if (ck >= c_kend) {  // row block finished: fold its rows into the column norms
 #pragma unroll
@@ -463,7 +514,8 @@ extern "C" {
 int ipp_gp_posterior_grid(const double* Wbuf, const double* vbuf, int n, double c, double l, double y_mean,
                           double y_std, double x0, double x1, int nx, double y0, double y1, int ny,
                           long long g_begin, long long g_end, double* mean, double* std, double* zpred,
-                          int* neg_count, double* tables, int max_ctas, void* stream) {
+                          int* neg_count, double* tables, const double* slab_bbox, double cutoff, int max_ctas,
+                          void* stream) {
   if (!Wbuf || !vbuf || n <= 0 || nx <= 0 || ny <= 0 || !mean || !std || !(l > 0.0)) return IPP_ERR_ARG;
   if (g_begin < 0 || g_end > (long long)nx * ny || g_begin > g_end) return IPP_ERR_ARG;
   PostArgs a{};
@@ -483,6 +535,8 @@ int ipp_gp_posterior_grid(const double* Wbuf, const double* vbuf, int n, double 
   a.std = std;
   a.zpred = zpred;
   a.neg_count = neg_count;
+  a.slab_bbox = slab_bbox;
+  a.cutoff2 = (slab_bbox && cutoff > 0.0) ? cutoff * cutoff : 0.0;
   if (tables && nx >= QT) return launch_lattice(a, tables, max_ctas, (cudaStream_t)stream);
   return launch_posterior(a, true, max_ctas, (cudaStream_t)stream);
 }
@@ -504,6 +558,6 @@ int ipp_gp_posterior_points(const double* Wbuf, const double* vbuf, int n, doubl
   return launch_posterior(a, false, max_ctas, (cudaStream_t)stream);
 }
 
-int ipp_abi_version(void) { return 3; }
+int ipp_abi_version(void) { return 4; }
 
 }  // extern "C"

@@ -125,6 +125,44 @@ def _as_points(X):
     return A
 
 
+def morton_order(X):
+    """Stable argsort of the points along a Z-order curve over their own bounding box (16 bits per axis): the
+    order in which the final factorisation sees the observations, so that 16 consecutive ones form a compact
+    cluster and whole 16-observation slabs of k* vanish for far-away lattice tiles."""
+    X = np.asarray(X, dtype=np.float64)
+    lo, hi = X.min(axis=0), X.max(axis=0)
+    span = np.where(hi > lo, hi - lo, 1.0)
+    q = np.minimum(((X - lo) / span * 65536.0).astype(np.uint64), np.uint64(65535))
+
+    def spread(v):
+        v = (v | (v << np.uint64(8))) & np.uint64(0x00FF00FF)
+        v = (v | (v << np.uint64(4))) & np.uint64(0x0F0F0F0F)
+        v = (v | (v << np.uint64(2))) & np.uint64(0x33333333)
+        v = (v | (v << np.uint64(1))) & np.uint64(0x55555555)
+        return v
+
+    return np.argsort(spread(q[:, 0]) | (spread(q[:, 1]) << np.uint64(1)), kind="stable")
+
+
+def slab_bounding_boxes(Xs, NP, slab=16):
+    """{xmin, xmax, ymin, ymax} of each `slab` consecutive rows of Xs, padded to NP rows; slabs that hold only
+    padding get an empty box infinitely far away."""
+    n = Xs.shape[0]
+    ns = NP // slab
+    out = np.empty((ns, 4), dtype=np.float64)
+    out[:, 0::2] = 1e300
+    out[:, 1::2] = 1e300
+    full = n // slab
+    if full:
+        blk = Xs[: full * slab].reshape(full, slab, 2)
+        out[:full, 0], out[:full, 1] = blk[:, :, 0].min(1), blk[:, :, 0].max(1)
+        out[:full, 2], out[:full, 3] = blk[:, :, 1].min(1), blk[:, :, 1].max(1)
+    if n > full * slab:
+        rest = Xs[full * slab:]
+        out[full] = (rest[:, 0].min(), rest[:, 0].max(), rest[:, 1].min(), rest[:, 1].max())
+    return out
+
+
 def gram_device(X, Y, c, l, jitter=0.0):
     """K(X, Y) as a device-resident torch tensor (n x m, fp64)."""
     torch = _lib.require_cuda()
@@ -211,6 +249,9 @@ class GaussianProcessRegressor:
         # optimiser restarts are independent once their start points are drawn: run them on this many streams
         # (None = automatic: all of them for small problems, 4 when one buffer set is already > 100 MB; 1 = serial)
         self.restart_streams = None
+        # block sparsity of the lattice posterior: entries of k* below skip_below * c are not computed (0: dense)
+        self.skip_below = 1e-30
+        self._scratch = None
         self.n_lml_evals_ = 0
         self.lazy = False
         self._pending = False
@@ -235,6 +276,8 @@ class GaussianProcessRegressor:
         self._Xd = dev[: 2 * n].view(n, 2)
         self._yd = dev[2 * n:]
         self.h2d_bytes_ = 24 * n
+        self._perm = np.arange(n)
+        self._Xd_fit, self._yd_fit, self._bbox_d = self._Xd, self._yd, None
 
     def _eval_device(self, c, l, with_grad, final=False, ws=None, max_ctas=0):
         """Launch one LML (+gradient) evaluation or the final factorisation on the calling thread's
@@ -249,7 +292,8 @@ class GaussianProcessRegressor:
         ws.hyp.copy_(ws.hyp_host, non_blocking=True)
         st = _lib.stream_ptr()
         if final:
-            rc = lib.ipp_gp_fit_final(_lib.ptr(self._Xd), _lib.ptr(self._yd), n, _lib.ptr(ws.hyp), _lib.ptr(ws.K),
+            Xf, yf = (self._Xd_fit, self._yd_fit) if final == "morton" else (self._Xd, self._yd)
+            rc = lib.ipp_gp_fit_final(_lib.ptr(Xf), _lib.ptr(yf), n, _lib.ptr(ws.hyp), _lib.ptr(ws.K),
                                       _lib.ptr(ws.W), _lib.ptr(ws.T), _lib.ptr(ws.v), st)
             _lib.check(rc, "ipp_gp_fit_final")
         else:
@@ -271,7 +315,12 @@ class GaussianProcessRegressor:
         theta = np.asarray(theta, dtype=float)
         if not clone_kernel:
             self._kernel_fitted.theta = theta
-        return self._lml(theta, eval_gradient)
+        return self._lml(theta, eval_gradient, ws=self._scratch_ws())  # never the buffers the posterior reads
+
+    def _scratch_ws(self):
+        if self._scratch is None:
+            self._scratch = _Workspace()
+        return self._scratch.ensure(self.X_train_.shape[0])
 
     def _lml(self, theta, eval_gradient, ws=None, max_ctas=0):
         theta = np.asarray(theta, dtype=float)
@@ -426,7 +475,8 @@ class GaussianProcessRegressor:
 
     def _finalize(self, set_lml):
         k = self._kernel_fitted
-        res = self._eval_device(k.constant_value, k.length_scale, False, final=True)
+        self._choose_order(k.length_scale)
+        res = self._eval_device(k.constant_value, k.length_scale, False, final="morton")
         if res[3] != 0.0:
             raise np.linalg.LinAlgError(
                 f"The kernel, {k}, is not returning a positive definite matrix. Try gradually "
@@ -437,14 +487,45 @@ class GaussianProcessRegressor:
         self._fitted_c = k.constant_value
         self._fitted_l = k.length_scale
 
+    def _skip_cutoff(self, length_scale, skip=None):
+        """Distance beyond which every entry of k* is below skip_below * c (0.0: dense)."""
+        skip = self.skip_below if skip is None else skip
+        return float(length_scale) * float(np.sqrt(2.0 * np.log(1.0 / skip))) if (skip and 0.0 < skip < 1.0) else 0.0
+
+    def _choose_order(self, length_scale):
+        """Order of the observations in the FINAL factorisation.  When the kernel's reach (the skip cutoff) is
+        well inside the extent of the data, the observations are put in Morton order so that 16-observation slabs
+        of k* are spatial clusters the lattice kernel can skip; alpha_ / L_ undo the permutation.  Otherwise the
+        given order is kept: nothing could be skipped, and a spatially sorted elimination order is the less
+        accurate one for the explicit inverse when the kernel is wide (every row nearly repeats its predecessor)."""
+        torch = _lib.require_cuda()
+        X = self.X_train_
+        n = X.shape[0]
+        cutoff = self._skip_cutoff(length_scale)
+        extent = float(np.max(X.max(axis=0) - X.min(axis=0))) if n > 1 else 0.0
+        if cutoff > 0.0 and cutoff < 0.35 * extent and n >= 256:
+            self._perm = morton_order(X)
+            pd = torch.from_numpy(self._perm).cuda()
+            self._Xd_fit = self._Xd.index_select(0, pd).contiguous()
+            self._yd_fit = self._yd.index_select(0, pd).contiguous()
+            self._bbox_d = torch.from_numpy(slab_bounding_boxes(X[self._perm], self._ws.layout[0])).cuda()
+        else:
+            self._perm = np.arange(n)
+            self._Xd_fit, self._yd_fit, self._bbox_d = self._Xd, self._yd, None
+
     # -- fitted attributes (lazy device -> host) ------------------------------------------------
     @property
     def L_(self):
         self._ensure()
         if self._L_host is None:
+            # sklearn's L_ is the factor in the ORIGINAL order of the observations: factor once more, on demand
             n = self.X_train_.shape[0]
-            NP, ld = self._ws.layout[0], self._ws.layout[2]
-            self._L_host = self._ws.K[: NP * ld].view(NP, ld)[:n, :n].cpu().numpy()
+            ws = self._scratch_ws()
+            res = self._eval_device(self._fitted_c, self._fitted_l, False, final="original", ws=ws)
+            if res[3] != 0.0:
+                raise np.linalg.LinAlgError(f"{int(res[3])}-th leading minor of the array is not positive definite")
+            NP, ld = ws.layout[0], ws.layout[2]
+            self._L_host = ws.K[: NP * ld].view(NP, ld)[:n, :n].cpu().numpy()
         return self._L_host
 
     @property
@@ -453,7 +534,9 @@ class GaussianProcessRegressor:
         if self._alpha_host is None:
             n = self.X_train_.shape[0]
             off = self._ws.layout[7]
-            self._alpha_host = self._ws.v[off:off + n].cpu().numpy()
+            a = np.empty(n)
+            a[self._perm] = self._ws.v[off:off + n].cpu().numpy()  # device state is in Morton order
+            self._alpha_host = a
         return self._alpha_host
 
     # -- prediction -----------------------------------------------------------------------------
@@ -512,6 +595,43 @@ class GaussianProcessRegressor:
         self.d2h_bytes_ = 16 * m
         return host[m:].copy(), host[:m].copy()
 
+    def lattice_work(self, x0, x1, nx, y0, y1, ny, g_begin=0, g_end=None, skip_below=None):
+        """(executed, dense) counts of 128-query x 128-row x 16-observation DMMA slabs of the lattice kernel for
+        this fitted state: the host restatement of the kernel's own slab test (lattice_slab_mask in
+        csrc/ipp_posterior.cu), used by bench.py to turn a launch time into executed flop/s."""
+        self._ensure()
+        n = self.X_train_.shape[0]
+        g_end = nx * ny if g_end is None else g_end
+        first = n % 128
+        rlims = ([first] if first else []) + [first + 128 * j for j in range(1, n // 128 + 1)] if first else \
+            [128 * (j + 1) for j in range(n // 128)]
+        kslabs = np.array([(r + 15) // 16 for r in rlims])
+        nt = (g_end - g_begin + 127) // 128
+        dense = int(kslabs.sum()) * int(nt)
+        cutoff = self._skip_cutoff(self._fitted_l, skip_below) if self._bbox_d is not None else 0.0
+        if cutoff <= 0.0:
+            return dense, dense
+        bb = self._bbox_d.cpu().numpy()
+        xstep = (x1 - x0) / (nx - 1) if nx > 1 else 0.0
+        ystep = (y1 - y0) / (ny - 1) if ny > 1 else 0.0
+        gq0 = g_begin + 128 * np.arange(nt)
+        nvalid = np.minimum(128, g_end - gq0)
+        iy0, ix0 = gq0 // nx, gq0 % nx
+        ixl = ix0 + nvalid - 1
+        same = ixl < nx
+        qx0 = np.where(same, x0 + ix0 * xstep, x0)
+        qx1 = np.where(same, x0 + ixl * xstep, x1)
+        qy0 = y0 + iy0 * ystep
+        qy1 = np.where(same, qy0, y0 + (iy0 + 1) * ystep)
+        executed = 0
+        for lo in range(0, nt, 2048):  # chunked: tiles x slabs
+            sl = slice(lo, lo + 2048)
+            gx = np.maximum(0.0, np.maximum(bb[None, :, 0] - qx1[sl, None], qx0[sl, None] - bb[None, :, 1]))
+            gy = np.maximum(0.0, np.maximum(bb[None, :, 2] - qy1[sl, None], qy0[sl, None] - bb[None, :, 3]))
+            cum = np.cumsum(gx * gx + gy * gy <= cutoff * cutoff, axis=1)
+            executed += int(cum[:, kslabs - 1].sum())
+        return executed, dense
+
     def _lattice_tables(self, nx, ny):
         """Scratch for the lattice fast path of ipp_gp_posterior_grid: (nx + ny) * NP doubles."""
         torch = _lib.require_cuda()
@@ -523,7 +643,7 @@ class GaussianProcessRegressor:
         return buf
 
     def predict_grid_device(self, x0, x1, nx, y0, y1, ny, g_begin=0, g_end=None, want_zpred=True, out=None,
-                            lattice=True):
+                            lattice=True, skip_below=None):
         """Fused posterior over flat lattice indices [g_begin, g_end) (index = iy * nx + ix).
         Returns device tensors (mean, std, zpred) of length g_end - g_begin."""
         torch = _lib.require_cuda()
@@ -540,9 +660,12 @@ class GaussianProcessRegressor:
         if m:
             args = self._posterior_args()
             tables = self._lattice_tables(nx, ny) if (lattice and nx >= 128) else None
+            cutoff = self._skip_cutoff(self._fitted_l, skip_below) if self._bbox_d is not None else 0.0
             rc = lib.ipp_gp_posterior_grid(*args, float(x0), float(x1), int(nx), float(y0), float(y1),
                                            int(ny), int(g_begin), int(g_end), _lib.ptr(mean), _lib.ptr(std),
-                                           _lib.ptr(zp), _lib.ptr(neg), _lib.ptr(tables), 0, _lib.stream_ptr())
+                                           _lib.ptr(zp), _lib.ptr(neg), _lib.ptr(tables),
+                                           _lib.ptr(self._bbox_d) if cutoff > 0.0 else None, float(cutoff), 0,
+                                           _lib.stream_ptr())
             _lib.check(rc, "ipp_gp_posterior_grid")
         self._neg_counter = neg
         return mean, std, zp

@@ -231,15 +231,16 @@ def test_grid_paths_agree_and_slabs_bit_exact(G, torch):
     mp, sp, zp = gp.predict_points_device(torch.from_numpy(r).cuda(), want_zpred=True)
     mg, sg, zg = gp.predict_grid_device(0, W, nx, 0.5, 9.25, ny, lattice=False)
     assert torch.equal(mg, mp) and torch.equal(sg, sp) and torch.equal(zg, zp)
-    m, s, z = gp.predict_grid_device(0, W, nx, 0.5, 9.25, ny)  # lattice fast path (nx >= 128)
+    m, s, z = gp.predict_grid_device(0, W, nx, 0.5, 9.25, ny)  # lattice fast path (nx >= 128), block-sparse k*
     tol = _mean_tol(st, r, mp.cpu().numpy())
     assert (np.abs((m - mp).cpu().numpy()) <= tol).all()
     assert float((s - sp).abs().max()) <= 1e-9
     assert float((s * s - sp * sp).abs().max()) <= _var_tol(st)
     for lattice in (True, False):
-        m, s, z = gp.predict_grid_device(0, W, nx, 0.5, 9.25, ny, lattice=lattice)
+        # (dense k*: with slab skipping the set of < 1e-30 terms a query drops depends on its tile)
+        m, s, z = gp.predict_grid_device(0, W, nx, 0.5, 9.25, ny, lattice=lattice, skip_below=0)
         cuts = [0, 1, 127, 128, 129, 5000, 9999, nx * ny]
-        parts = [gp.predict_grid_device(0, W, nx, 0.5, 9.25, ny, g_begin=a, g_end=b, lattice=lattice)
+        parts = [gp.predict_grid_device(0, W, nx, 0.5, 9.25, ny, g_begin=a, g_end=b, lattice=lattice, skip_below=0)
                  for a, b in zip(cuts[:-1], cuts[1:])]
         assert torch.equal(torch.cat([q[0] for q in parts]), m)
         assert torch.equal(torch.cat([q[1] for q in parts]), s)
@@ -251,6 +252,44 @@ def test_grid_paths_agree_and_slabs_bit_exact(G, torch):
     assert mean0.shape == (0,)
 
 
+@pytest.mark.parametrize("l", [0.4, 0.6])
+def test_block_sparse_posterior_equals_dense(G, torch, l):
+    """Slabs of k* whose entries are all below 1e-30 c are skipped (observations fitted in Morton order).  The
+    result must be the dense one to rounding, including tiles that see no observation at all (prior) and tiles
+    that wrap across two lattice rows."""
+    W, n = 60, 1500
+    X, y = _make(n, W, seed=3)
+    X[:700] = X[:700] * 0.3 + 5.0  # a dense cluster and a sparse remainder: some tiles keep few slabs, some none
+    gp = G.GaussianProcessRegressor(kernel=G.ConstantRBFKernel(1.4, l), optimizer=None, normalize_y=True).fit(X, y)
+    assert gp._bbox_d is not None and not np.array_equal(gp._perm, np.arange(n))  # Morton order is in use
+    nx, ny = 600, 150
+    dense = gp.predict_grid_device(0, W, nx, 0, 15.0, ny, skip_below=0)
+    sparse = gp.predict_grid_device(0, W, nx, 0, 15.0, ny)
+    assert float((dense[0] - sparse[0]).abs().max()) <= 1e-13 * max(1.0, float(dense[0].abs().max()))
+    assert float((dense[1] - sparse[1]).abs().max()) <= 1e-13
+    fin = torch.isfinite(dense[2])
+    assert torch.equal(fin, torch.isfinite(sparse[2]))
+    assert float((dense[2][fin] / sparse[2][fin] - 1).abs().max()) <= 1e-12
+    # the same posterior from the factorisation in the GIVEN order of the observations (no Morton sort): equal to
+    # the rounding noise of a reordered elimination
+    ref = G.GaussianProcessRegressor(kernel=G.ConstantRBFKernel(1.4, l), optimizer=None, normalize_y=True)
+    ref.skip_below = 0
+    ref.fit(X, y)
+    assert ref._bbox_d is None and np.array_equal(ref._perm, np.arange(n))
+    r0 = ref.predict_grid_device(0, W, nx, 0, 15.0, ny)
+    st = O.fit(X, y, 1.4, l, optimize=False)
+    xs, ys = np.linspace(0, W, nx), np.linspace(0, 15.0, ny)
+    pts = np.column_stack((np.tile(xs, 3), np.repeat(ys[[0, 70, 149]], nx)))
+    idx = np.concatenate([np.arange(nx) + nx * r for r in (0, 70, 149)])
+    tol = _mean_tol(st, pts, r0[0].cpu().numpy()[idx])
+    assert (np.abs((sparse[0] - r0[0]).cpu().numpy()[idx]) <= tol).all()
+    assert float((sparse[1] - r0[1]).abs().max()) <= 1e-8
+    assert np.abs(gp.alpha_ - ref.alpha_).max() <= 1e-4 * np.abs(ref.alpha_).max()
+    far = gp.predict_grid_device(1000.0, 1000.0 + W, nx, 0, 15.0, 8)  # nothing within reach: the prior, exactly
+    assert float((far[0] - gp._y_train_mean).abs().max()) == 0.0
+    assert float((far[1] - np.sqrt(1.4) * gp._y_train_std).abs().max()) <= 1e-15
+
+
 def test_factor_properties_full_size(G, torch):
     """C4-sized factor (n = 5000, 20 % duplicate waypoints): W L = I, alpha solves K alpha = y, the
     posterior interpolates the data and the variance stays in [0, c]."""
@@ -260,15 +299,18 @@ def test_factor_properties_full_size(G, torch):
     gp = G.GaussianProcessRegressor(kernel=G.ConstantRBFKernel(c, l), optimizer=None, normalize_y=True).fit(X, y)
     ws = gp._ws
     NP, ld = ws.layout[0], ws.layout[2]
-    L = ws.K[: NP * ld].view(NP, ld)[:n, :n]
+    L = ws.K[: NP * ld].view(NP, ld)[:n, :n]  # device state: observations in Morton order (gp._perm)
     Wm = ws.W[: NP * ld].view(NP, ld)[:n, :n]
+    assert sorted(gp._perm.tolist()) == list(range(n))
     assert float(torch.triu(Wm, 1).abs().max()) == 0.0
     R = Wm @ L - torch.eye(n, dtype=torch.float64, device="cuda")
     assert float(R.abs().max()) <= 1e-7  # cond(L) ~ 3e5
+    Ks = torch.from_numpy(O.kernel(X[gp._perm], None, c, l)).cuda()
+    Ks += 1e-10 * torch.eye(n, dtype=torch.float64, device="cuda")
+    assert float((L @ L.T - Ks).abs().max()) <= 1e-12
     K = torch.from_numpy(O.kernel(X, None, c, l)).cuda()
     K += 1e-10 * torch.eye(n, dtype=torch.float64, device="cuda")
-    assert float((L @ L.T - K).abs().max()) <= 1e-12
-    alpha = torch.from_numpy(gp.alpha_).cuda()
+    alpha = torch.from_numpy(gp.alpha_).cuda()  # original order
     yn = torch.from_numpy(gp.y_train_).cuda()
     resid = K @ alpha - yn
     assert float(resid.abs().max()) <= 1e-5 * float(alpha.abs().max()) * 1e-3
