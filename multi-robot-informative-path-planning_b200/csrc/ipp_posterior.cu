@@ -239,8 +239,6 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) posterior_lattice_kernel(PostA
   auto blk_row0 = [&](int j) { return first ? (j ? first + (j - 1) * PC::BM : 0) : j * PC::BM; };
   auto blk_rlim = [&](int j) { return (first && j == 0) ? first : blk_row0(j) + PC::BM; };
   auto blk_kend = [&](int j) { return (blk_rlim(j) + BK - 1) / BK * BK; };
-  int tot = 0;  // pipeline iterations (k slabs summed over the row blocks) per tile
-  for (int rb = 0; rb < nrb; ++rb) tot += blk_kend(rb) / BK;
   if (t == 0) {
     for (int s = 0; s < SEP_STAGES; ++s) {
       mbar_init(&bar_full[s], 128);                // one cp.async-completion arrival per copy thread
@@ -270,36 +268,33 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) posterior_lattice_kernel(PostA
       // (LDG, DMUL, STS) so that the DMMA warps load finished k* values, 880-900 ms -- the copy warps then sit on
       // L2 latency with too few registers to keep a slab of loads in flight.
       lattice_slab_mask(a, smask[warp], lane, gq0, nvalid);
-      int prb = 0, pk = 0, p_row0 = 0, p_rlim = blk_rlim(0), p_kend = blk_kend(0);
-      for (int it = 0; it < tot; ++it) {
-        const int si = pk / BK;
-        if ((smask[warp][si >> 5] >> (si & 31)) & 1u) {
-        const unsigned stage = gslab % SEP_STAGES, use = gslab / SEP_STAGES;
-        if (use > 0) mbar_wait(&bar_empty[stage], (use - 1) & 1);  // every consumer warp is done with the old contents
-        double* s = smem + stage * SEP_STAGE;
-        load_tile_async<PC::BM, Lay::KCONT, 128>(s, a.W, a.ldw, p_row0, pk, p_rlim, a.np, pt);
+      for (int prb = 0; prb < nrb; ++prb) {
+        const int p_row0 = blk_row0(prb), p_rlim = blk_rlim(prb), nsl = blk_kend(prb) / BK;
+        for (int w = 0; 32 * w < nsl; ++w) {  // the active slabs below the block's last column, by set bit
+          unsigned m = smask[warp][w];
+          if (nsl - 32 * w < 32) m &= (1u << (nsl - 32 * w)) - 1u;
+          while (m) {
+            const int pk = (32 * w + __ffs(m) - 1) * BK;
+            m &= m - 1;
+            const unsigned stage = gslab % SEP_STAGES, use = gslab / SEP_STAGES;
+            if (use > 0) mbar_wait(&bar_empty[stage], (use - 1) & 1);  // every consumer warp is done with the old contents
+            double* s = smem + stage * SEP_STAGE;
+            load_tile_async<PC::BM, Lay::KCONT, 128>(s, a.W, a.ldw, p_row0, pk, p_rlim, a.np, pt);
 #pragma unroll
-        for (int q = 0; q < QT * BK / 2 / 128; ++q) {
-          const int c = pt + q * 128;
-          const int r = c / (BK / 2), kc = (c % (BK / 2)) * 2;
-          int ix = ix0 + min(r, nvalid - 1);
-          if (ix >= a.nx) ix -= a.nx;
-          cp_async16(s + SEP_A + r * KPAD + kc, Ex + (long)ix * ldt + pk + kc, true);
-        }
-        if (pt < BK) {
-          const int row = pt >> 3, kc = (pt & 7) * 2;
-          cp_async16(s + SEP_A + SEP_B + row * BK + kc, Ey + (long)(row ? iy1 : iy0) * ldt + pk + kc, true);
-        }
-        cp_async_mbar_arrive(&bar_full[stage]);
-        ++gslab;
-        }
-        pk += BK;
-        if (pk >= p_kend) {
-          pk = 0;
-          ++prb;
-          p_row0 = blk_row0(prb);
-          p_rlim = blk_rlim(prb);
-          p_kend = blk_kend(prb);
+            for (int q = 0; q < QT * BK / 2 / 128; ++q) {
+              const int c = pt + q * 128;
+              const int r = c / (BK / 2), kc = (c % (BK / 2)) * 2;
+              int ix = ix0 + min(r, nvalid - 1);
+              if (ix >= a.nx) ix -= a.nx;
+              cp_async16(s + SEP_A + r * KPAD + kc, Ex + (long)ix * ldt + pk + kc, true);
+            }
+            if (pt < BK) {
+              const int row = pt >> 3, kc = (pt & 7) * 2;
+              cp_async16(s + SEP_A + SEP_B + row * BK + kc, Ey + (long)(row ? iy1 : iy0) * ldt + pk + kc, true);
+            }
+            cp_async_mbar_arrive(&bar_full[stage]);
+            ++gslab;
+          }
         }
       }
     }
@@ -326,12 +321,15 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) posterior_lattice_kernel(PostA
 #pragma unroll
       for (int i = 0; i < 2 * PC::NI; ++i) csq_s[i][t] = 0.0;
       double mean_part = 0.0;
-      int crb = 0, ck = 0, c_kend = blk_kend(0);
-
       lattice_slab_mask(a, smask[warp], lane, gq0, nvalid);
-      for (int it = 0; it < tot; ++it) {
-        const int si = ck / BK;
-        if ((smask[warp][si >> 5] >> (si & 31)) & 1u) {
+      for (int crb = 0; crb < nrb; ++crb) {
+        const int nsl = blk_kend(crb) / BK;
+        for (int w = 0; 32 * w < nsl; ++w) {  // the active slabs below the block's last column, by set bit
+          unsigned m = smask[warp][w];
+          if (nsl - 32 * w < 32) m &= (1u << (nsl - 32 * w)) - 1u;
+          while (m) {
+            const int ck = (32 * w + __ffs(m) - 1) * BK;
+            m &= m - 1;
         const unsigned stage = gslab % SEP_STAGES;
         mbar_wait(&bar_full[stage], (gslab / SEP_STAGES) & 1);
         const double* sA = smem + stage * SEP_STAGE + (wm * PC::WTM + g) * KPAD + tg;
@@ -388,25 +386,21 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) posterior_lattice_kernel(PostA
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_empty[stage]);  // this warp no longer reads the stage
         ++gslab;
+          }
         }
-        ck += BK;
-        if (ck >= c_kend) {  // row block finished: fold its rows into the column norms
+        // row block finished: fold its rows into the column norms
 #pragma unroll
-          for (int ni = 0; ni < PC::NI; ++ni)
+        for (int ni = 0; ni < PC::NI; ++ni)
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              double v = csq_s[2 * ni + e][t];
+          for (int e = 0; e < 2; ++e) {
+            double v = csq_s[2 * ni + e][t];
 #pragma unroll
-              for (int mi = 0; mi < PC::MI; ++mi) {
-                v += acc[mi][ni][e] * acc[mi][ni][e];
-                acc[mi][ni][e] = 0.0;
-              }
-              csq_s[2 * ni + e][t] = v;
+            for (int mi = 0; mi < PC::MI; ++mi) {
+              v += acc[mi][ni][e] * acc[mi][ni][e];
+              acc[mi][ni][e] = 0.0;
             }
-          ck = 0;
-          ++crb;
-          c_kend = blk_kend(crb);
-        }
+            csq_s[2 * ni + e][t] = v;
+          }
       }
 #pragma unroll
       for (int ni = 0; ni < PC::NI; ++ni)
