@@ -6,6 +6,7 @@ sys.path.insert(0, ROOT)
 import torch
 from mripp_b200 import gp as G
 n, W, Gx, n_lml = (int(a) for a in sys.argv[1:5])
+Gy = int(sys.argv[5]) if len(sys.argv) > 5 else Gx  # optional: fewer lattice rows (a slab) to keep ncu captures short
 rng = np.random.RandomState(0)
 X = rng.uniform(0, W, (n, 2)); X[-n // 5:] = X[:n // 5]
 y = np.sin(X[:, 0] / 3) + 0.1 * X[:, 1] + 1e-3 * rng.randn(n)
@@ -14,6 +15,6 @@ th = np.log([1.0, 2.0])
 for _ in range(n_lml):
     gp.log_marginal_likelihood(th, eval_gradient=True)
 if Gx:
-    gp.predict_grid_device(0, W, Gx, 0, W, Gx)
+    gp.predict_grid_device(0, W, Gx, 0, W * Gy / Gx, Gy)
 torch.cuda.synchronize()
 print("ok")
