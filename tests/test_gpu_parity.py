@@ -290,6 +290,29 @@ def test_block_sparse_posterior_equals_dense(G, torch, l):
     assert float((far[1] - np.sqrt(1.4) * gp._y_train_std).abs().max()) <= 1e-15
 
 
+def test_predict_recognises_the_reference_lattice(G, torch):
+    """gp.predict(r) with r = the raveled meshgrid the reference builds (point_source.py:350) takes the fused
+    lattice kernel; anything else (a permuted or perturbed copy) takes the explicit-point kernel; same numbers."""
+    W = 30
+    X, y = _make(400, W, seed=8)
+    gp = G.GaussianProcessRegressor(kernel=G.ConstantRBFKernel(1.1, 0.9), optimizer=None, normalize_y=True).fit(X, y)
+    xs, ys = np.linspace(0, W, W * 10), np.linspace(0, 12, 120)
+    XX, YY = np.meshgrid(xs, ys)
+    r = np.column_stack((XX.ravel(), YY.ravel()))
+    assert G.as_lattice(r) == (0.0, float(W), W * 10, 0.0, 12.0, 120)
+    r2 = r.copy()
+    r2[1234, 0] += 1e-9
+    assert G.as_lattice(r2) is None and G.as_lattice(r[::-1].copy()) is None and G.as_lattice(r[:100]) is None
+    m1, s1 = gp.predict(r, return_std=True)
+    md, sd, _ = gp.predict_grid_device(0, W, W * 10, 0, 12, 120)
+    assert np.array_equal(m1, md.cpu().numpy()) and np.array_equal(s1, sd.cpu().numpy())
+    m2, s2 = gp.predict(r2, return_std=True)
+    st = O.fit(X, y, 1.1, 0.9, optimize=False)
+    keep = np.arange(len(r)) != 1234
+    assert (np.abs(m1 - m2)[keep][::7] <= _mean_tol(st, r[keep][::7], m2[keep][::7])).all()
+    assert np.abs(s1 - s2)[keep].max() <= 1e-9
+
+
 def test_factor_properties_full_size(G, torch):
     """C4-sized factor (n = 5000, 20 % duplicate waypoints): W L = I, alpha solves K alpha = y, the
     posterior interpolates the data and the variance stays in [0, c]."""
