@@ -176,7 +176,8 @@ __global__ void __launch_bounds__(256) gram_sym_kernel(const double* __restrict_
 // At n = 5000 that is 158 grid barriers instead of 237 dependent launches.
 // ---------------------------------------------------------------------------------------------
 constexpr int PSTR = BLK + 1;
-constexpr size_t PANEL_SMEM = sizeof(double) * (2 * BLK * PSTR + BLK);  // two 64x64 blocks + 64 reciprocals
+constexpr int QSTR = BLK + 4;  // pitch of a block read as DMMA fragments (conflict free for the m8n8k4 pattern)
+constexpr size_t PANEL_SMEM = sizeof(double) * (BLK * PSTR + BLK * QSTR + BLK);  // two 64x64 blocks + 64 reciprocals
 
 // In-place Cholesky of a 64x64 block held in shared memory (stride PSTR, lower part used), blocked by 8
 // columns: warp 0 factors each 64 x 8 panel in registers (lane r owns rows jb + r and jb + r + 32; pivots and
@@ -203,7 +204,7 @@ __device__ __forceinline__ void potf2_block(double* D, int t, int first_index, d
         const double rs = rsqrt(piv);
         if (lane == 0 && !(piv > 0.0) && info[0] == 0.0) info[0] = (double)(first_index + jb + c + 1);
         if (lane == c)
-          a0[c] = piv > 0.0 ? piv * rs : sqrt(piv);
+          a0[c] = piv * rs;  // sqrt(piv); NaN for piv <= 0 (rsqrt gives NaN or inf), as sqrt would
         else if (lane > c)
           a0[c] = a0[c] * rs;
         a1[c] = a1[c] * rs;
@@ -279,16 +280,18 @@ __device__ __forceinline__ void chol_diag_step(double* __restrict__ A, long ld, 
 // (it is 1/4 of a 128x128 tensor tile and sits on the critical path), then factor it.
 template <int NT>
 __device__ __forceinline__ void chol_diag_update_step(double* __restrict__ A, long ld, int k, int kp, double* psm,
-                                                      double* info) {
+                                                      double* info, long long* clk = nullptr) {
+  const long long q0 = clk ? clock64() : 0;
   double* D = psm;
   double* P = psm + BLK * PSTR;
   const int t = threadIdx.x, j0 = BLK * k, p0 = BLK * kp;
   for (int e = t; e < BLK * BLK; e += NT) {
     int r = e / BLK, cc = e % BLK;
     D[r * PSTR + cc] = A[(long)(j0 + r) * ld + j0 + cc];
-    P[r * PSTR + cc] = A[(long)(j0 + r) * ld + p0 + cc];
+    P[r * QSTR + cc] = A[(long)(j0 + r) * ld + p0 + cc];
   }
   __syncthreads();
+  const long long q1 = clk ? clock64() : 0;
   {  // D -= P P^T on the DMMA pipe: each warp owns 64 / (NT / 32) rows, all 64 columns
     constexpr int RPW = BLK / (NT / 32), MT = RPW / 8;
     const int warp = t >> 5, lane = t & 31, g = lane >> 2, tg = lane & 3;
@@ -301,9 +304,9 @@ __device__ __forceinline__ void chol_diag_update_step(double* __restrict__ A, lo
     for (int kk = 0; kk < BLK; kk += 4) {
       double af[MT], bf[8];
 #pragma unroll
-      for (int mi = 0; mi < MT; ++mi) af[mi] = P[(warp * RPW + mi * 8 + g) * PSTR + kk + tg];
+      for (int mi = 0; mi < MT; ++mi) af[mi] = P[(warp * RPW + mi * 8 + g) * QSTR + kk + tg];
 #pragma unroll
-      for (int ni = 0; ni < 8; ++ni) bf[ni] = P[(ni * 8 + g) * PSTR + kk + tg];
+      for (int ni = 0; ni < 8; ++ni) bf[ni] = P[(ni * 8 + g) * QSTR + kk + tg];
 #pragma unroll
       for (int mi = 0; mi < MT; ++mi)
 #pragma unroll
@@ -320,12 +323,21 @@ __device__ __forceinline__ void chol_diag_update_step(double* __restrict__ A, lo
         }
   }
   __syncthreads();
+  const long long q2 = clk ? clock64() : 0;
   potf2_block<NT>(D, t, j0, info);
+  const long long q3 = clk ? clock64() : 0;
   for (int e = t; e < BLK * BLK; e += NT) {
     int r = e / BLK, cc = e % BLK;
     A[(long)(j0 + r) * ld + j0 + cc] = (cc <= r) ? D[r * PSTR + cc] : 0.0;
   }
   __syncthreads();
+  if (clk) {
+    const long long q4 = clock64();
+    clk[0] += q1 - q0;  // block loads
+    clk[1] += q2 - q1;  // DMMA update
+    clk[2] += q3 - q2;  // potf2
+    clk[3] += q4 - q3;  // store
+  }
 }
 
 // Panel solve of one 64-row block: A_ik <- A_ik * L_kk^-T by forward substitution (backward stable,
@@ -338,7 +350,7 @@ __device__ __forceinline__ void chol_trsm_block(double* __restrict__ A, long ld,
   constexpr int CPL = BLK / LPR;  // columns per lane
   double* Ls = psm;
   double* Xs = psm + BLK * PSTR;
-  double* rinv = psm + 2 * BLK * PSTR;
+  double* rinv = psm + BLK * PSTR + BLK * QSTR;
   const int t = threadIdx.x, j0 = BLK * k, i0 = BLK * i;
   for (int e = t; e < BLK * BLK; e += NT) {
     int r = e / BLK, cc = e % BLK;
@@ -461,6 +473,8 @@ __global__ void __launch_bounds__(C::THREADS, 1) chol_coop_kernel(double* __rest
   const bool timing = phase_cycles != nullptr && blockIdx.x < 2 && threadIdx.x == 0;  // CTA 0 (panel) and CTA 1 (tiles)
   long long tc[5] = {0, 0, 0, 0, 0}, t0 = 0, tile_clk[3] = {0, 0, 0};
   long long* tclk = (phase_cycles != nullptr && blockIdx.x == 1) ? tile_clk : nullptr;  // uniform over CTA 1
+  long long diag_clk[4] = {0, 0, 0, 0};
+  long long* dclk = (phase_cycles != nullptr && blockIdx.x == 0) ? diag_clk : nullptr;
   auto tick = [&](int slot) {
     if (timing) {
       const long long now = clock64();
@@ -483,7 +497,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) chol_coop_kernel(double* __rest
       const int ntile = T * (T + 1) / 2;
       // the next diagonal block first (CTA 0), behind the other CTAs' tiles
       // CTA 0 owns the critical path (next diagonal block); the other CTAs share the tiles
-      if (blockIdx.x == 0) chol_diag_update_step<C::THREADS>(A, ld, k + 1, k, smem, info);
+      if (blockIdx.x == 0) chol_diag_update_step<C::THREADS>(A, ld, k + 1, k, smem, info, dclk);
       tick(3);
       if (gridDim.x == 1) {
         for (int b = 0; b < ntile; ++b) chol_syrk_tile<C>(A, ld, rows_total, np, k, b, smem);
@@ -497,6 +511,8 @@ __global__ void __launch_bounds__(C::THREADS, 1) chol_coop_kernel(double* __rest
     for (int q = 0; q < 5; ++q) phase_cycles[5 * blockIdx.x + q] = (double)tc[q];
     if (blockIdx.x == 1)  // (timing is true for thread 0 only)
       for (int q = 0; q < 3; ++q) phase_cycles[10 + q] = (double)tile_clk[q];
+    if (blockIdx.x == 0)
+      for (int q = 0; q < 4; ++q) phase_cycles[13 + q] = (double)diag_clk[q];
   }
 }
 
@@ -779,7 +795,7 @@ static int chol_inplace(double* Kb, double* Wb, double* info, const GpDims& d, c
   long ld = d.ld;
   int rows = d.rows, np = d.np;
   // the tile-partials area of vbuf (free until the gradient kernel runs) receives the phase counters
-  double* phase = (2 * d.max_tiles >= 13) ? info - 3 - 2 * d.max_tiles : nullptr;
+  double* phase = (2 * d.max_tiles >= 17) ? info - 3 - 2 * d.max_tiles : nullptr;
   void* args[] = {(void*)&Kb, (void*)&ld, (void*)&rows, (void*)&np, (void*)&info, (void*)&phase};
   if (cudaLaunchCooperativeKernel((void*)chol_coop_kernel<C>, dim3(ctas), dim3(C::THREADS), args, SM, st) != cudaSuccess)
     return IPP_ERR_CUDA;

@@ -26,6 +26,8 @@ for n in [int(a) for a in sys.argv[1:]] or [500, 2000, 5000]:
     off = lay[8] - 2 * ntile
     ph10 = gp._ws.v[off:off + 10].cpu().numpy() / 1.965e3  # us at 1965 MHz
     tl = gp._ws.v[off + 10:off + 13].cpu().numpy()
+    dg = gp._ws.v[off + 13:off + 17].cpu().numpy() / 1.965e3 / max(nb - 1, 1)
+    print(f"   CTA0 diagonal block per panel: loads {dg[0]:.1f} us, DMMA update {dg[1]:.1f} us, potf2 {dg[2]:.1f} us, store {dg[3]:.1f} us")
     if tl[2] > 0:
         print(f"   CTA1 trailing tiles: {int(tl[2])} tiles, mainloop {tl[0] / tl[2] / 1.965e3:.1f} us, C read-modify-write {tl[1] / tl[2] / 1.965e3:.1f} us per tile")
     ph = ph10[:5]
