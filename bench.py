@@ -337,6 +337,12 @@ def run_b200(args, wl, rank, world, local_rank):
     clocks = sampler.window(*win) if sampler else None
     ms_dense, _, _ = timed(posterior_step_dense, max(2, args.steps // 2), 1)  # same state, every slab of k* computed
     executed, dense_slabs = gp.lattice_work(0, W, nx, 0, W, ny)
+    # the two modes give the same field: checked here, on the benchmarked state, every run
+    sp = gp.predict_grid_device(0, W, nx, 0, W, ny, want_zpred=False)
+    de = gp.predict_grid_device(0, W, nx, 0, W, ny, want_zpred=False, skip_below=0)
+    sparse_diff = {"max_abs_mean": float((sp[0] - de[0]).abs().max()), "max_abs_std": float((sp[1] - de[1]).abs().max())}
+    assert sparse_diff["max_abs_mean"] <= 1e-12 * max(1.0, float(de[0].abs().max())) and sparse_diff["max_abs_std"] <= 1e-12, sparse_diff
+    del sp, de
 
     # ---- (2) end to end through the public API with host buffers ------------------------------------
     wp = [X[i] for i in range(n)]  # the reference passes a Python list of 1-D arrays (rrt.py:749)
@@ -472,10 +478,12 @@ def run_b200(args, wl, rank, world, local_rank):
             tr.add(xy_a[k], int(par_a[k]))
         a_trees.append(tr)
 
+    obs_cache = {}  # what a strategy object keeps between scoring calls (src/rrt/rrt.py::_context)
+
     def planning_step():
         chosen = []
         for a, tr in enumerate(a_trees):
-            ctx_a = ScoreContext(src, tr.point(0), obs, a, 1.0, (0, W, 0, W), [])
+            ctx_a = ScoreContext(src, tr.point(0), obs, a, 1.0, (0, W, 0, W), [], obs_cache=obs_cache)
             info_a = scorer.tree_information(3, tr, ctx_a)
             leaves = tr.leaves_in_order()
             par_l = tr.parent[leaves]
@@ -526,7 +534,7 @@ def run_b200(args, wl, rank, world, local_rank):
             "roofline": {"bound": "tensor", "achieved": ach, "peak": peak64, "unit": "TFLOP/s", "frac": ach / peak64,
                          "traffic": ncu_traffic(args.workload), "kernel": "posterior_lattice_kernel",
                          "flops_per_launch": executed * slab_flops, "dense_model_flops_per_launch": flops,
-                         "executed_slab_fraction": executed / dense_slabs,
+                         "executed_slab_fraction": executed / dense_slabs, "sparse_minus_dense": sparse_diff,
                          "dense": {"ms_per_step": ms_dense, "value": world * Gpts / (ms_dense * 1e-3), "achieved": ach_dense,
                                    "frac": ach_dense / peak64,
                                    "note": "same fitted state with skip_below=0: every slab of k* computed"},

@@ -33,13 +33,28 @@ class ScoreContext:
     d_wp: float
     workspace: Sequence[float]
     obstacles: List[dict] = field(default_factory=list)
+    obs_cache: Optional[dict] = None  # strategy-owned: arrays of the (append-only) observation lists, by length
+    _all: Optional[np.ndarray] = None
 
     def estimates(self):
         return np.ascontiguousarray(np.asarray(self.best_estimates, dtype=np.float64).reshape(-1, 3))
 
     def all_obs(self):
-        rows = [np.asarray(o, dtype=np.float64).reshape(-1, 2) for o in self.agents_obs_wp if len(o) > 0]
-        return np.ascontiguousarray(np.vstack(rows)) if rows else np.zeros((0, 2))
+        """Observations of all agents as one (O, 2) array, agent by agent (built once per context; the strategy
+        passes a cache shared by every context of a planning step: turning 5000 list entries into an array costs
+        more than the kernels that read them)."""
+        if self.obs_cache is not None:
+            return _cached_obs(self.obs_cache, self.agents_obs_wp, None)
+        if self._all is None:
+            rows = [np.asarray(o, dtype=np.float64).reshape(-1, 2) for o in self.agents_obs_wp if len(o) > 0]
+            self._all = np.ascontiguousarray(np.vstack(rows)) if rows else np.zeros((0, 2))
+        return self._all
+
+    def agent_obs(self):
+        """This agent's own observations as an (n_a, 2) array."""
+        if self.obs_cache is not None:
+            return _cached_obs(self.obs_cache, self.agents_obs_wp, self.agent_idx)
+        return np.asarray(self.agents_obs_wp[self.agent_idx], dtype=np.float64).reshape(-1, 2)
 
     def agent_has_obs(self):
         return len(self.agents_obs_wp[self.agent_idx]) > 0
@@ -56,6 +71,24 @@ class ScoreContext:
         lp = self.last_point
         d = [np.linalg.norm([lp[0] - s[0], lp[1] - s[1]]) for s in est]
         return int(np.argmin(d))
+
+
+def _cached_obs(cache, agents_obs_wp, agent):
+    """Array view of the append-only observation lists, rebuilt only when a list has grown.
+    agent = None: all agents stacked in agent order."""
+    lens = tuple((id(o), len(o), id(o[-1]) if len(o) else 0) for o in agents_obs_wp)  # list identity, length, tail
+    key = "all" if agent is None else agent
+    hit = cache.get(key)
+    want = lens if agent is None else lens[agent]
+    if hit is not None and hit[0] == want:
+        return hit[1]
+    if agent is None:
+        rows = [np.asarray(o, dtype=np.float64).reshape(-1, 2) for o in agents_obs_wp if len(o) > 0]
+        arr = np.ascontiguousarray(np.vstack(rows)) if rows else np.zeros((0, 2))
+    else:
+        arr = np.ascontiguousarray(np.asarray(agents_obs_wp[agent], dtype=np.float64).reshape(-1, 2))
+    cache[key] = (want, arr)
+    return arr
 
 
 def resolve_close_counts(points, obs, d, sure, amb):
@@ -231,7 +264,7 @@ class GpuScorer:
     def leaf_scores(self, leaf_xy, parent_xy, has_parent, ctx: ScoreContext, beta, kernel_c, kernel_l):
         torch, lib = self.torch, self.lib
         L = leaf_xy.shape[0]
-        agent_obs = np.asarray(ctx.agents_obs_wp[ctx.agent_idx], dtype=np.float64).reshape(-1, 2)
+        agent_obs = ctx.agent_obs()
         mi = self.mutual_information(leaf_xy, agent_obs, kernel_c, kernel_l, beta)
         has_obs = 1 if ctx.agent_has_obs() else 0
         nclose_d = None

@@ -42,10 +42,11 @@ _norm = np.linalg.norm
 # ---- scoring helpers --------------------------------------------------------------------------------
 def _context(self, agent_idx: int) -> ScoreContext:
     path = self.agents_full_path[agent_idx]
+    cache = self.__dict__.setdefault("_obs_array_cache", {})  # observation lists only ever grow (rrt.py:727-737)
     return ScoreContext(best_estimates=getattr(self, "best_estimates", np.array([])),
                         last_point=path[-1] if len(path) else None, agents_obs_wp=self.agents_obs_wp, agent_idx=agent_idx,
                         d_wp=self.d_waypoint_distance, workspace=self.scenario.workspace_size,
-                        obstacles=list(self.scenario.obstacles))
+                        obstacles=list(self.scenario.obstacles), obs_cache=cache)
 
 
 def _chain_tree(node: TreeNode) -> TreeArrays:
