@@ -265,10 +265,19 @@ def run_b200(args, wl, rank, world, local_rank):
     _lib.load()
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # NCCL prints its version banner on STDOUT at the VERSION/INFO levels; stdout carries the one JSON line
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "INFO"):
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL prints its version banner (the image exports NCCL_DEBUG=VERSION) on STDOUT when the communicator is
+        # created; stdout carries the one JSON line, so file descriptor 1 points at stderr until that has happened
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     n, W = wl["n"], wl["W"]
     nx = ny = W * 10
     Gpts = nx * ny
