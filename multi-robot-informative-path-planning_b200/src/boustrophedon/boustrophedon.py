@@ -98,8 +98,8 @@ class MR_Boustrophedon:
     def finalize_all_agents(self):
         self.obs_wp = np.vstack(self.agents_obs_wp)
         self.full_path = np.vstack(self.agents_full_path).T
-        measurements = self.scenario.simulate_measurements(self.obs_wp)
-        return self.scenario.predict_spatial_field(self.obs_wp, measurements)
+        self.measurements = self.scenario.simulate_measurements(self.obs_wp)
+        return self.scenario.predict_spatial_field(self.obs_wp, self.measurements)
 
 
 # the name the shipped config lists (config/example_setup.json:46)

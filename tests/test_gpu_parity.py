@@ -531,7 +531,11 @@ RUN_COMMON = dict(budget=40, d_waypoint_distance=2.5, budget_iter=2, n_samples=6
     ("mripp_1a", "MR_IPP", dict(num_agents=1, stage_lambda=0.5)),
     ("mripp_2a", "MR_IPP", dict(num_agents=2, stage_lambda=0.5)),
     ("rig_dist", "RRTRIG_PointSourceInformative_Distance_SourceMetric_PathPlanning", dict(num_agents=1, stage_lambda=0.6)),
+    ("rig_nopen", "RRTRIG_PointSourceInformative_SourceMetric_PathPlanning", dict(num_agents=1, stage_lambda=0.6)),
+    ("rig_rot", "RRTRIG_PointSourceInformative_DistanceRotation_SourceMetric_PathPlanning", dict(num_agents=1, stage_lambda=0.6)),
     ("biasbeta", "RRT_BiasBetaInformative_GP_PathPlanning", dict(num_agents=1, stage_lambda=0.5)),
+    ("rrt_random", "RRT_Random_GP_PathPlanning", dict(num_agents=1, stage_lambda=0.0)),
+    ("rrtstar_random", "RRTStar_Random_GP_PathPlanning", dict(num_agents=1, stage_lambda=0.0)),
 ])
 def test_run_waypoints_identical_on_device(gold, tag, cls_name, extra):
     from mripp_b200.src.rrt import rrt as R
@@ -577,6 +581,34 @@ def test_run_waypoints_identical_on_device(gold, tag, cls_name, extra):
         Z1, std1 = sc.predict_spatial_field(st.obs_wp, np.asarray(st.measurements, float))
     assert np.abs(np.log10(Z1[::4, ::4]) - np.log10(g[f"{tag}_Z"])).max() <= 1e-4
     assert np.abs(std1.reshape(Z.shape)[::4, ::4] - g[f"{tag}_std"]).max() <= 1e-6
+
+
+@pytest.mark.parametrize("tag,cls_name,kw", [("boust", "Boustrophedon", dict(budget=60)),
+                                             ("mr_boust", "MR_Boustrophedon", dict(budget=40, num_agents=2))])
+def test_boustrophedon_on_device(gold, tag, cls_name, kw):
+    """The lawn-mower baselines: same waypoints and RNG position as the reference, field within T2 / T1."""
+    from mripp_b200.src.boustrophedon import boustrophedon as B
+    from mripp_b200.src.point_source.point_source import PointSourceField
+
+    g = gold("runs_golden.npz")
+    sc = PointSourceField(num_sources=2, workspace_size=(0, 20, 0, 20), seed=21)
+    np.random.seed(99)
+    st = getattr(B, cls_name)(sc, d_waypoint_distance=2.5, **kw)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        Z, std = st.run()
+    assert np.array_equal(np.asarray(st.obs_wp, float), g[f"{tag}_obs_wp"])
+    assert np.array_equal(np.asarray(st.full_path, float), g[f"{tag}_full_path"])
+    assert np.array_equal(np.random.uniform(size=3), g[f"{tag}_rng_after"])
+    assert np.abs(np.log10(Z[::4, ::4]) - np.log10(g[f"{tag}_Z"])).max() <= 1e-1
+    th = g[f"{tag}_theta"]
+    sc.gp.kernel = type(sc.gp.kernel)(float(np.exp(th[0])), float(np.exp(th[1])))
+    sc.gp.optimizer = None
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        Z1, std1 = sc.predict_spatial_field(st.obs_wp, np.asarray(st.measurements, float))
+    assert np.abs(np.log10(Z1[::4, ::4]) - np.log10(g[f"{tag}_Z"])).max() <= 1e-4
+    assert np.abs(std1.reshape(Z1.shape)[::4, ::4] - g[f"{tag}_std"]).max() <= 1e-6
 
 
 def test_abi_rejects_bad_arguments_on_device(torch):
