@@ -516,38 +516,47 @@ __global__ void __launch_bounds__(C::THREADS, 1) chol_coop_kernel(double* __rest
   }
 }
 
-// W_kk = L_kk^-1 for every 64x64 diagonal block at once (level 0 of the triangular inverse).
+// W_kk = L_kk^-1 for every 64x64 diagonal block at once (level 0 of the triangular inverse): the panel solve
+// applied to the identity, X = I L_kk^-T = W_kk^T -- 64 substitution steps with the rows in registers (4 lanes per
+// row, multipliers by shuffle), the same routine as chol_trsm_block; stored transposed.
 __global__ void __launch_bounds__(256) diag_inverse_kernel(const double* __restrict__ L, long ld, double* __restrict__ Winv,
                                                            long ldw) {
+  constexpr int NT = 256, LPR = NT / BLK, CPL = BLK / LPR;
   extern __shared__ double psm[];
-  double* D = psm;
-  double* Wt = psm + BLK * PSTR;
+  double* Ls = psm;
+  double* Xs = psm + BLK * PSTR;
+  double* rinv = psm + BLK * PSTR + BLK * QSTR;
   const int t = threadIdx.x, j0 = BLK * blockIdx.x;
-  for (int e = t; e < BLK * BLK; e += 256) {
+  for (int e = t; e < BLK * BLK; e += NT) {
     int r = e / BLK, cc = e % BLK;
-    D[r * PSTR + cc] = L[(long)(j0 + r) * ld + j0 + cc];
+    Ls[r * PSTR + cc] = L[(long)(j0 + r) * ld + j0 + cc];
+  }
+  if (t < BLK) rinv[t] = 1.0 / L[(long)(j0 + t) * ld + j0 + t];
+  __syncthreads();
+  {
+    const int r = t / LPR, q0 = t % LPR, lane = t & 31;
+    double x[CPL];
+#pragma unroll
+    for (int m = 0; m < CPL; ++m) x[m] = (q0 + m * LPR == r) ? 1.0 : 0.0;
+#pragma unroll
+    for (int c = 0; c < BLK; ++c) {
+      const int owner = c % LPR, mc = c / LPR;
+      double xc = x[mc] * rinv[c];  // meaningful in the owner lane only
+      xc = __shfl_sync(0xffffffffu, xc, (lane & ~(LPR - 1)) + owner);
+      if (q0 == owner) x[mc] = xc;
+#pragma unroll
+      for (int m = 0; m < CPL; ++m) {
+        const int q = q0 + m * LPR;
+        if (q > c) x[m] -= xc * Ls[q * PSTR + c];
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < CPL; ++m) Xs[r * PSTR + q0 + m * LPR] = x[m];  // X[r][c] = W[c][r]
   }
   __syncthreads();
-  // Wt[c][i] = inv(L)[i][c]; 4 lanes per column, columns are independent
-  const int c = t >> 2, q = t & 3;
-  if (q == 0) {
-    for (int i = 0; i < c; ++i) Wt[c * PSTR + i] = 0.0;
-    Wt[c * PSTR + c] = 1.0 / D[c * PSTR + c];
-  }
-  __syncwarp();
-  for (int i = 1; i < BLK; ++i) {
-    double part = 0.0;
-    if (i > c)
-      for (int kk = c + q; kk < i; kk += 4) part += D[i * PSTR + kk] * Wt[c * PSTR + kk];
-    part += __shfl_xor_sync(0xffffffffu, part, 1);
-    part += __shfl_xor_sync(0xffffffffu, part, 2);
-    if (i > c && q == 0) Wt[c * PSTR + i] = -part / D[i * PSTR + i];
-    __syncwarp();
-  }
-  __syncthreads();
-  for (int e = t; e < BLK * BLK; e += 256) {
+  for (int e = t; e < BLK * BLK; e += NT) {
     int r = e / BLK, cc = e % BLK;
-    Winv[(long)(j0 + r) * ldw + j0 + cc] = Wt[cc * PSTR + r];
+    Winv[(long)(j0 + r) * ldw + j0 + cc] = (cc <= r) ? Xs[cc * PSTR + r] : 0.0;
   }
 }
 
