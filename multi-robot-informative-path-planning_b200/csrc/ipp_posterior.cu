@@ -1,5 +1,7 @@
 // GP posterior mean / standard deviation over the workspace lattice or explicit query points
-// (SURVEY.md §8a rows G5, G6).  Replaces gp.predict(X, return_std=True)
+// (SURVEY.md §8a rows G5, G6).  Two kernels: posterior_kernel (generic: explicit points, k* by exp()) and
+// posterior_lattice_kernel (the workspace lattice: separable coordinate tables, warp-specialised cp.async /
+// mbarrier pipeline, block-sparse k*) -- see the comment blocks above each.  Replaces gp.predict(X, return_std=True)
 // (sklearn/gaussian_process/_gpr.py:446-500 reached from src/point_source/point_source.py:351 and
 // src/rrt/rrt_thread.py:375).
 //
@@ -330,62 +332,62 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) posterior_lattice_kernel(PostA
           while (m) {
             const int ck = (32 * w + __ffs(m) - 1) * BK;
             m &= m - 1;
-        const unsigned stage = gslab % SEP_STAGES;
-        mbar_wait(&bar_full[stage], (gslab / SEP_STAGES) & 1);
-        const double* sA = smem + stage * SEP_STAGE + (wm * PC::WTM + g) * KPAD + tg;
-        const double* sB = smem + stage * SEP_STAGE + SEP_A + (wn * PC::WTN + g) * KPAD + tg;
-        const double* sE = smem + stage * SEP_STAGE + SEP_A + SEP_B;
-        // B fragments (Ex * Ey) are prepared one k-step ahead of the DMMAs that use them.  The loads and the
-        // multiply are volatile asm, issued between the two halves of the previous k-step's DMMA burst, so that
-        // ptxas cannot sink them to the point of use (it does when they are plain C++).
-        const uint32_t aB = (uint32_t)__cvta_generic_to_shared(sB);
-        const uint32_t aE = (uint32_t)__cvta_generic_to_shared(sE);
-        auto lds64 = [](uint32_t addr) {
-          double v;
-          asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(addr));
-          return v;
-        };
-        auto vmul = [](double x, double y) {
-          double v;
-          asm volatile("mul.rn.f64 %0, %1, %2;\n" : "=d"(v) : "d"(x), "d"(y));
-          return v;
-        };
-        double bf[PC::NI], bn[PC::NI];
-#pragma unroll
-        for (int ni = 0; ni < PC::NI; ++ni)
-          bf[ni] = vmul(lds64(aB + 8 * (ni * 8 * KPAD)), lds64(aE + 8 * eoff[ni]));
-#pragma unroll
-        for (int kk = 0; kk < BK; kk += 4) {
-          double af[PC::MI];
-#pragma unroll
-          for (int mi = 0; mi < PC::MI; ++mi) af[mi] = sA[mi * 8 * KPAD + kk];
-#pragma unroll
-          for (int mi = 0; mi < PC::MI / 2; ++mi)
-#pragma unroll
-            for (int ni = 0; ni < PC::NI; ++ni) dmma884(acc[mi][ni], af[mi], bf[ni]);
-          if (kk + 4 < BK) {
+            const unsigned stage = gslab % SEP_STAGES;
+            mbar_wait(&bar_full[stage], (gslab / SEP_STAGES) & 1);
+            const double* sA = smem + stage * SEP_STAGE + (wm * PC::WTM + g) * KPAD + tg;
+            const double* sB = smem + stage * SEP_STAGE + SEP_A + (wn * PC::WTN + g) * KPAD + tg;
+            const double* sE = smem + stage * SEP_STAGE + SEP_A + SEP_B;
+            // B fragments (Ex * Ey) are prepared one k-step ahead of the DMMAs that use them.  The loads and the
+            // multiply are volatile asm, issued between the two halves of the previous k-step's DMMA burst, so that
+            // ptxas cannot sink them to the point of use (it does when they are plain C++).
+            const uint32_t aB = (uint32_t)__cvta_generic_to_shared(sB);
+            const uint32_t aE = (uint32_t)__cvta_generic_to_shared(sE);
+            auto lds64 = [](uint32_t addr) {
+              double v;
+              asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(addr));
+              return v;
+            };
+            auto vmul = [](double x, double y) {
+              double v;
+              asm volatile("mul.rn.f64 %0, %1, %2;\n" : "=d"(v) : "d"(x), "d"(y));
+              return v;
+            };
+            double bf[PC::NI], bn[PC::NI];
 #pragma unroll
             for (int ni = 0; ni < PC::NI; ++ni)
-              bn[ni] = vmul(lds64(aB + 8 * (ni * 8 * KPAD + kk + 4)), lds64(aE + 8 * (eoff[ni] + kk + 4)));
-          }
+              bf[ni] = vmul(lds64(aB + 8 * (ni * 8 * KPAD)), lds64(aE + 8 * eoff[ni]));
 #pragma unroll
-          for (int mi = PC::MI / 2; mi < PC::MI; ++mi)
+            for (int kk = 0; kk < BK; kk += 4) {
+              double af[PC::MI];
 #pragma unroll
-            for (int ni = 0; ni < PC::NI; ++ni) dmma884(acc[mi][ni], af[mi], bf[ni]);
+              for (int mi = 0; mi < PC::MI; ++mi) af[mi] = sA[mi * 8 * KPAD + kk];
 #pragma unroll
-          for (int ni = 0; ni < PC::NI; ++ni) bf[ni] = bn[ni];
-        }
-        if (crb == nrb - 1) {  // the last row block sees every k slab once: the mean rides along there
-          const double* sBq = smem + stage * SEP_STAGE + SEP_A + p * KPAD;
+              for (int mi = 0; mi < PC::MI / 2; ++mi)
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {
-            const int k = h * 8 + kk;
-            mean_part += __ldg(a.alpha + ck + k) * __dmul_rn(sBq[k], sE[prow + k]);
-          }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_empty[stage]);  // this warp no longer reads the stage
-        ++gslab;
+                for (int ni = 0; ni < PC::NI; ++ni) dmma884(acc[mi][ni], af[mi], bf[ni]);
+              if (kk + 4 < BK) {
+#pragma unroll
+                for (int ni = 0; ni < PC::NI; ++ni)
+                  bn[ni] = vmul(lds64(aB + 8 * (ni * 8 * KPAD + kk + 4)), lds64(aE + 8 * (eoff[ni] + kk + 4)));
+              }
+#pragma unroll
+              for (int mi = PC::MI / 2; mi < PC::MI; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < PC::NI; ++ni) dmma884(acc[mi][ni], af[mi], bf[ni]);
+#pragma unroll
+              for (int ni = 0; ni < PC::NI; ++ni) bf[ni] = bn[ni];
+            }
+            if (crb == nrb - 1) {  // the last row block sees every k slab once: the mean rides along there
+              const double* sBq = smem + stage * SEP_STAGE + SEP_A + p * KPAD;
+#pragma unroll
+              for (int kk = 0; kk < 8; ++kk) {
+                const int k = h * 8 + kk;
+                mean_part += __ldg(a.alpha + ck + k) * __dmul_rn(sBq[k], sE[prow + k]);
+              }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_empty[stage]);  // this warp no longer reads the stage
+            ++gslab;
           }
         }
         // row block finished: fold its rows into the column norms
@@ -530,7 +532,8 @@ int ipp_gp_posterior_grid(const double* Wbuf, const double* vbuf, int n, double 
   a.zpred = zpred;
   a.neg_count = neg_count;
   a.slab_bbox = slab_bbox;
-  a.cutoff2 = (slab_bbox && cutoff > 0.0) ? cutoff * cutoff : 0.0;
+  // the box test assumes ascending lattice axes (the reference's linspace(w0, w1, .)); otherwise stay dense
+  a.cutoff2 = (slab_bbox && cutoff > 0.0 && x1 >= x0 && y1 >= y0) ? cutoff * cutoff : 0.0;
   if (tables && nx >= QT) return launch_lattice(a, tables, max_ctas, (cudaStream_t)stream);
   return launch_posterior(a, true, max_ctas, (cudaStream_t)stream);
 }
