@@ -834,7 +834,7 @@ static int trtri_inplace(const double* Kb, double* Wb, double* Tb, const GpDims&
     const int pairs = (d.np + 2 * s - 1) / (2 * s);
     // levels whose 128x128 tiling cannot fill the GPU run on 64x64 tiles (4x the CTAs, each a quarter of the work)
     const int tiles128 = ((s + 127) / 128) * ((s + 127) / 128) * pairs;
-    const int rc = (C::BM > 64 && tiles128 < 148) ? trtri_level<Cfg64>(Kb, Wb, Tb, d, s, pairs, st)
+    const int rc = (C::BM > 64 && tiles128 < 2 * 148) ? trtri_level<Cfg64>(Kb, Wb, Tb, d, s, pairs, st)
                                                   : trtri_level<C>(Kb, Wb, Tb, d, s, pairs, st);
     if (rc != IPP_OK) return rc;
   }
