@@ -269,7 +269,7 @@ class GaussianProcessRegressor:
         self._count_lock = threading.Lock()
         self._restart_slots = []
         # optimiser restarts are independent once their start points are drawn: run them on this many streams
-        # (None = automatic: all of them for small problems, 4 when one buffer set is already > 100 MB; 1 = serial)
+        # (None = automatic: 6 streams, 3 when the Cholesky alone fills the GPU; 1 = serial)
         self.restart_streams = None
         # block sparsity of the lattice posterior: entries of k* below skip_below * c are not computed (0: dense)
         self.skip_below = 1e-30
@@ -440,7 +440,7 @@ class GaussianProcessRegressor:
             return 1
         if self.restart_streams is not None:
             return max(1, min(int(self.restart_streams), n_starts))
-        return min(n_starts, 11 if self._ws.layout[0] <= 2048 else 4)
+        return min(n_starts, 6 if self._ws.layout[0] <= 2048 else 3)  # measured best on a B200 (tools/fit_tune.py)
 
     def _optimise_concurrently(self, starts, bounds, workers):
         """The restarts of _gpr.py:312-333 side by side: one host thread, one CUDA stream and one device
