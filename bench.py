@@ -435,6 +435,7 @@ def run_b200(args, wl, rank, world, local_rank):
     barrier()
     br_e2e = B * reps / (time.perf_counter() - t0)
     br_dev_ms = scorer.time_device_pass(3, tree, ctx, reps=20)
+    br_walk_ms = scorer.last_walk_ms
 
     # the same scoring pass over a forest of 64 independent trees (configs[4]: 64 rounds per batch): the
     # throughput regime of the kernels, one launch sequence for 64 x B branches
@@ -456,6 +457,13 @@ def run_b200(args, wl, rank, world, local_rank):
 
     forest = Forest([synth_tree(B, W, 5000 + 64 * seed + r) for r in range(64)])
     forest_ms = scorer.time_device_pass(3, forest, ctx, reps=5)
+    forest_walk_ms = scorer.last_walk_ms
+    forest_depth = 0.0
+    for x_, p_ in [synth_tree(B, W, 5000 + 64 * seed)]:  # mean branch length of one of the 64 trees
+        dep = np.zeros(len(x_))
+        for k in range(1, len(x_)):
+            dep[k] = dep[p_[k]] + 1
+        forest_depth = float(dep[1:].mean())
 
     # Gram build (HBM-write bound): the dense n x n prior kernel block the selectors ask for
     Xd = torch.from_numpy(X).cuda()
@@ -565,8 +573,17 @@ def run_b200(args, wl, rank, world, local_rank):
             "branch_gain": {"value": world * B / (br_dev_ms * 1e-3), "unit": "branch evals/s", "ms_per_batch": br_dev_ms,
                             "branches": B, "variant": "point_source_gain_all", "observations": n,
                             "e2e": {"value": world * br_e2e, "unit": "branch evals/s"},
+                            "phase2_walk_ms": br_walk_ms,
                             "forest_64_rounds": {"value": world * 64 * B / (forest_ms * 1e-3), "unit": "branch evals/s",
-                                                 "ms_per_batch": forest_ms, "branches": 64 * B},
+                                                 "ms_per_batch": forest_ms, "branches": 64 * B,
+                                                 "phase1_terms_and_counts_ms": forest_ms - forest_walk_ms,
+                                                 "phase2_walk_ms": forest_walk_ms, "mean_branch_length": forest_depth,
+                                                 "walk_gather_GBps": 64 * B * forest_depth * 44.0 / (forest_walk_ms * 1e-3) / 1e9,
+                                                 "walk_frac_of_measured_hbm": 64 * B * forest_depth * 44.0 / (forest_walk_ms * 1e-3) / 1e9 / hbm,
+                                                 "note": "phase 2 is a dependent gather: per step 4 B parent + 16 B node + 16 B parent "
+                                                         "coordinates + 8 B term (12 B/step if only term + index are counted); "
+                                                         "the node tables of a batch are L2 resident, so this is gather "
+                                                         "throughput set against the HBM copy figure, not HBM traffic"},
                             "cpu_baseline": {"value": cpu_br["evals_per_s"], "cores": 1, "kind": "port",
                                              "sample": f"{cpu_br['sample_branches']} branches, pure-Python gain function"}},
             "clocks": clocks,

@@ -101,9 +101,12 @@ int ipp_mi_logdet(const double* leaf_xy, int L, const double* obs_xy, int na, do
 /* For each of np points: number of observations strictly closer than d (`sure`), and number
  * within a few ulp of d (`amb`, to be re-decided by the host with numpy's own norm); amb_total
  * accumulates the sum of amb (caller zeroes it).
+ * tile_bbox (nullable): obs is grouped in tiles of 64 consecutive rows with bounding boxes
+ * tile_bbox[t] = {xmin, xmax, ymin, ymax} (the count is order independent, so the caller may sort the observations
+ * spatially); each point then only visits the tiles within d of it.
  * Replaces the inner list comprehension of exploitation_penalty: rrt.py:246-252, 471-477. */
 int ipp_count_close(const double* P, int np, const double* obs, int no, double d, int* sure, int* amb, int* amb_total,
-                    void* stream);
+                    const double* tile_bbox, void* stream);
 
 /* Phase 1 of branch scoring: per-node static terms of gain variant
  *   0 point_source_gain_no_penalties (rrt.py:51-70; only source `closest_idx`)

@@ -35,6 +35,7 @@ class ScoreContext:
     obstacles: List[dict] = field(default_factory=list)
     obs_cache: Optional[dict] = None  # strategy-owned: arrays of the (append-only) observation lists, by length
     _all: Optional[np.ndarray] = None
+    _tiled: Optional[tuple] = None
 
     def estimates(self):
         return np.ascontiguousarray(np.asarray(self.best_estimates, dtype=np.float64).reshape(-1, 3))
@@ -49,6 +50,19 @@ class ScoreContext:
             rows = [np.asarray(o, dtype=np.float64).reshape(-1, 2) for o in self.agents_obs_wp if len(o) > 0]
             self._all = np.ascontiguousarray(np.vstack(rows)) if rows else np.zeros((0, 2))
         return self._all
+
+    def all_obs_tiled(self):
+        """all_obs() sorted spatially plus its tile boxes (cached with the observation arrays)."""
+        if self.obs_cache is not None:
+            base = self.all_obs()
+            hit = self.obs_cache.get("tiled")
+            if hit is None or hit[0] is not base:
+                hit = (base,) + spatial_tiles(base)
+                self.obs_cache["tiled"] = hit
+            return hit[1], hit[2]
+        if self._tiled is None:
+            self._tiled = spatial_tiles(self.all_obs())
+        return self._tiled
 
     def agent_obs(self):
         """This agent's own observations as an (n_a, 2) array."""
@@ -71,6 +85,21 @@ class ScoreContext:
         lp = self.last_point
         d = [np.linalg.norm([lp[0] - s[0], lp[1] - s[1]]) for s in est]
         return int(np.argmin(d))
+
+
+CC_TILE = 64  # observations per bounding-box tile of ipp_count_close (csrc/ipp_branch.cu)
+
+
+def spatial_tiles(obs):
+    """(observations in Z-order, tile boxes) for the pruned close-count kernel, or (obs, None) when there are too few
+    to be worth sorting.  The count of observations within d of a point does not depend on their order."""
+    from .gp import morton_order, slab_bounding_boxes
+
+    O = obs.shape[0]
+    if O < 4 * CC_TILE:
+        return obs, None
+    srt = np.ascontiguousarray(obs[morton_order(obs)])
+    return srt, slab_bounding_boxes(srt, (O + CC_TILE - 1) // CC_TILE * CC_TILE, slab=CC_TILE)
 
 
 def _cached_obs(cache, agents_obs_wp, agent):
@@ -123,18 +152,20 @@ class GpuScorer:
         t = self.torch.from_numpy(np.ascontiguousarray(a))
         return t.cuda(non_blocking=True)
 
-    def close_counts(self, points, obs, d):
-        """#observations closer than d to each point (exploitation penalty input)."""
+    def close_counts(self, points, obs, d, bbox=None):
+        """#observations closer than d to each point (exploitation penalty input).  bbox: tile boxes of a
+        spatially sorted `obs` (spatial_tiles), which lets every point skip the tiles out of reach."""
         torch, lib = self.torch, self.lib
         P = points.shape[0]
         if P == 0 or obs.shape[0] == 0:
             return np.zeros(P, dtype=np.int64), None
         Pd, Od = self._dev(points), self._dev(obs)
+        Bd = self._dev(bbox) if bbox is not None else None
         sure = torch.empty(P, dtype=torch.int32, device="cuda")
         amb = torch.empty(P, dtype=torch.int32, device="cuda")
         tot = torch.zeros(1, dtype=torch.int32, device="cuda")
         _lib.check(lib.ipp_count_close(_lib.ptr(Pd), P, _lib.ptr(Od), obs.shape[0], float(d), _lib.ptr(sure), _lib.ptr(amb),
-                                       _lib.ptr(tot), _lib.stream_ptr()), "ipp_count_close")
+                                       _lib.ptr(tot), _lib.ptr(Bd), _lib.stream_ptr()), "ipp_count_close")
         self.launches += 1
         if int(tot.item()) == 0:
             return None, sure  # device-resident, nothing ambiguous
@@ -166,8 +197,9 @@ class GpuScorer:
         d["has_obs"] = 1 if ctx.agent_has_obs() else 0
         d["need_close"] = bool(variant == VARIANT_ALL and d["has_obs"] and S)
         if d["need_close"]:
-            d["obs_host"] = ctx.all_obs()
+            d["obs_host"], bbox = ctx.all_obs_tiled()
             d["obs"] = self._dev(d["obs_host"])
+            d["obs_bbox"] = self._dev(bbox) if bbox is not None else None
             d["sure"] = torch.empty(N, dtype=torch.int32, device="cuda")
             d["amb"] = torch.empty(N, dtype=torch.int32, device="cuda")
             d["amb_total"] = torch.zeros(1, dtype=torch.int32, device="cuda")
@@ -186,7 +218,8 @@ class GpuScorer:
         self.launches += 1
         if d["need_close"]:
             _lib.check(lib.ipp_count_close(_lib.ptr(d["node_xy"]), d["N"], _lib.ptr(d["obs"]), d["obs_host"].shape[0],
-                                           d["d_wp"], _lib.ptr(d["sure"]), _lib.ptr(d["amb"]), _lib.ptr(d["amb_total"]), st),
+                                           d["d_wp"], _lib.ptr(d["sure"]), _lib.ptr(d["amb"]), _lib.ptr(d["amb_total"]),
+                                           _lib.ptr(d["obs_bbox"]), st),
                        "ipp_count_close")
             self.launches += 1
             d["nclose"] = d["sure"]
@@ -224,13 +257,17 @@ class GpuScorer:
             self._launch_terms(variant, d)
             self._launch_walk(variant, d)
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         e0.record()
         for _ in range(reps):
             self._launch_terms(variant, d)
             self._launch_walk(variant, d)
         e1.record()
+        for _ in range(reps):
+            self._launch_walk(variant, d)
+        e2.record()
         torch.cuda.synchronize()
+        self.last_walk_ms = e1.elapsed_time(e2) / reps  # phase 2 alone (phase 1 = the difference)
         return e0.elapsed_time(e1) / reps
 
     # -- I6 + I7: stage-1 selector ---------------------------------------------------------------------
@@ -269,7 +306,8 @@ class GpuScorer:
         has_obs = 1 if ctx.agent_has_obs() else 0
         nclose_d = None
         if has_obs:
-            counts, dev_counts = self.close_counts(leaf_xy, ctx.all_obs(), ctx.d_wp)
+            obs_sorted, bbox = ctx.all_obs_tiled()
+            counts, dev_counts = self.close_counts(leaf_xy, obs_sorted, ctx.d_wp, bbox)
             nclose_d = dev_counts if dev_counts is not None else self._dev(counts.astype(np.int32))
         scores = torch.empty(L, dtype=torch.float64, device="cuda")
         lx, px = self._dev(leaf_xy), self._dev(parent_xy)

@@ -482,6 +482,20 @@ def test_count_close_and_argmax_semantics():
     got = counts if counts is not None else dev.cpu().numpy()
     ref = np.array([sum(1 for o in obs if np.linalg.norm(p - o) < 2.5) for p in P[:120]])
     assert np.array_equal(np.asarray(got[:120], dtype=np.int64), ref)
+    # the pruned kernel (observations in Z-order + tile boxes) counts the same, knife-edge pairs included
+    from mripp_b200.scoring import spatial_tiles
+
+    srt, bbox = spatial_tiles(obs)
+    assert bbox is not None and bbox.shape == ((len(obs) + 63) // 64, 4)
+    counts_t, dev_t = sc.close_counts(P, srt, 2.5, bbox)
+    got_t = counts_t if counts_t is not None else dev_t.cpu().numpy()
+    full = counts if counts is not None else dev.cpu().numpy()
+    assert np.array_equal(np.asarray(got_t, dtype=np.int64), np.asarray(full, dtype=np.int64))
+    for dd in (0.05, 40.0):  # nothing in reach / everything in reach
+        a, da = sc.close_counts(P[:200], obs, dd)
+        b, db = sc.close_counts(P[:200], srt, dd, bbox)
+        assert np.array_equal(np.asarray(a if a is not None else da.cpu().numpy(), dtype=np.int64),
+                              np.asarray(b if b is not None else db.cpu().numpy(), dtype=np.int64))
     for v in [np.array([1.0, 3.0, 3.0, 2.0]), np.array([1.0, np.nan, 5.0, np.nan]), np.array([-np.inf, -np.inf]),
               np.array([np.inf, 1.0, np.inf]), rng.randn(100000)]:
         i, _ = sc.argmax_first(v)
