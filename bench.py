@@ -578,12 +578,12 @@ def run_b200(args, wl, rank, world, local_rank):
                                                  "ms_per_batch": forest_ms, "branches": 64 * B,
                                                  "phase1_terms_and_counts_ms": forest_ms - forest_walk_ms,
                                                  "phase2_walk_ms": forest_walk_ms, "mean_branch_length": forest_depth,
-                                                 "walk_gather_GBps": 64 * B * forest_depth * 44.0 / (forest_walk_ms * 1e-3) / 1e9,
-                                                 "walk_frac_of_measured_hbm": 64 * B * forest_depth * 44.0 / (forest_walk_ms * 1e-3) / 1e9 / hbm,
-                                                 "note": "phase 2 is a dependent gather: per step 4 B parent + 16 B node + 16 B parent "
-                                                         "coordinates + 8 B term (12 B/step if only term + index are counted); "
-                                                         "the node tables of a batch are L2 resident, so this is gather "
-                                                         "throughput set against the HBM copy figure, not HBM traffic"},
+                                                 "walk_gather_GBps": 64 * B * forest_depth * 12.0 / (forest_walk_ms * 1e-3) / 1e9,
+                                                 "walk_frac_of_measured_hbm": 64 * B * forest_depth * 12.0 / (forest_walk_ms * 1e-3) / 1e9 / hbm,
+                                                 "note": "phase2_walk_ms = per-node step terms (phase 1b) + the walks; a walk step gathers "
+                                                         "12 B (4 B parent index + 8 B term: SURVEY 8d's algorithmic figure); the node "
+                                                         "tables of a batch are L2 resident, so this is dependent-gather throughput "
+                                                         "set against the HBM copy figure, not HBM traffic"},
                             "cpu_baseline": {"value": cpu_br["evals_per_s"], "cores": 1, "kind": "port",
                                              "sample": f"{cpu_br['sample_branches']} branches, pure-Python gain function"}},
             "clocks": clocks,

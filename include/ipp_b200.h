@@ -122,12 +122,14 @@ int ipp_node_terms(int variant, const double* node_xy, int N, const double* sour
  * to the root as they were when node eval_time[b] was inserted: parent0[q] is the insertion-time
  * parent (-1 = root) and (hist_off, hist_time, hist_parent) is a CSR log of later rewire events
  * (rrt_utils.py:85-88) applied when hist_time < eval_time[b].  hist_off / eval_time may be NULL
- * (no rewires / final snapshot).  Replaces the `while current_node.parent` walks of rrt.py:65-70,
+ * (no rewires / final snapshot).  term0: N doubles of scratch -- the per-step term of every node against its
+ * insertion-time parent is computed once (phase 1b) and the walks gather it; a step is recomputed only where a
+ * rewire changed the parent.  Replaces the `while current_node.parent` walks of rrt.py:65-70,
  * 91-96, 123-128, 254-259 as called from rig_tree_generation (rrt.py:321). */
 int ipp_branch_gain(int variant, const double* node_xy, int N, const int* parent0, const int* hist_off,
                     const int* hist_time, const int* hist_parent, const double* src_gain, const double* wpen,
                     const int* n_close, int agent_has_obs, int have_estimates, const double* obstacles, int n_obst,
-                    const int* eval_node, const int* eval_time, int B, double* gain_out, void* stream);
+                    const int* eval_node, const int* eval_time, int B, double* term0, double* gain_out, void* stream);
 
 /* Stage-1 selector scores ((mi - distance) - workspace) - exploitation for L leaves.
  * Replaces the penalty loop of bias_beta_path_selection: rrt.py:460-482. */

@@ -32,7 +32,7 @@ SIGNATURES = {
     "ipp_mi_logdet": [_D, _I, _D, _I, _F, _F, _F, _D, _D, _D, _D, _D],
     "ipp_count_close": [_D, _I, _D, _I, _F, _D, _D, _D, _D, _D],
     "ipp_node_terms": [_I, _D, _I, _D, _I, _I, _D, _D, _I, _D, _D, _D],
-    "ipp_branch_gain": [_I, _D, _I, _D, _D, _D, _D, _D, _D, _D, _I, _I, _D, _I, _D, _D, _I, _D, _D],
+    "ipp_branch_gain": [_I, _D, _I, _D, _D, _D, _D, _D, _D, _D, _I, _I, _D, _I, _D, _D, _I, _D, _D, _D],
     "ipp_leaf_penalty": [_D, _D, _D, _I, _D, _I, _D, _F, _D, _D],
     "ipp_ucb_visit_penalty": [_D, _I, _D, _I, _F, _D, _D],
     "ipp_argmax_first": [_D, _I, _D, _D, _D],

@@ -208,14 +208,65 @@ __device__ __forceinline__ int parent_at(int q, int T, const int* __restrict__ p
   return p;
 }
 
+// ---- per-step term of a branch walk: node q reached from parent p (rrt.py:65-70, 91-96, 123-128, 254-259) -------
+struct TermArgs {
+  int variant;
+  const double* node_xy;
+  const double* src_gain;
+  const double* wpen;
+  const int* n_close;
+  int agent_has_obs, have_estimates;
+  const double* obst;
+  int n_obst;
+};
+__device__ __forceinline__ double branch_term(const TermArgs& a, int q, int p) {
+  const double qx = a.node_xy[2 * q], qy = a.node_xy[2 * q + 1];
+  const double px = a.node_xy[2 * p], py = a.node_xy[2 * p + 1];
+  if (a.variant == 3) {
+    double w = a.wpen[q];
+    for (int o = 0; o < a.n_obst && w == 0.0; ++o) {  // edge parent -> node against the 4 sides, rrt.py:203-217
+      const double x0 = a.obst[4 * o], y0 = a.obst[4 * o + 1];
+      const double x1 = x0 + a.obst[4 * o + 2], y1 = y0 + a.obst[4 * o + 3];
+      if (seg_hit(px, py, qx, qy, x0, y0, x0, y1) || seg_hit(px, py, qx, qy, x1, y0, x1, y1) ||
+          seg_hit(px, py, qx, qy, x0, y0, x1, y0) || seg_hit(px, py, qx, qy, x0, y1, x1, y1))
+        w = INFINITY;
+    }
+    if (!a.have_estimates) return -w;
+    const double r = norm2(qx - px, qy - py);
+    const double dp = exp(0.5 * (r * r));
+    double ep = 0.0;
+    if (a.agent_has_obs) {
+      const int nc = a.n_close[q];
+      ep = exp(0.05 * (double)((long long)nc * nc));
+    }
+    return ((a.src_gain[q] - dp) - ep) - w;
+  }
+  if (!a.have_estimates) return 0.0;
+  if (a.variant == 0) return a.src_gain[q];
+  const double dx = qx - px, dy = qy - py;
+  double term = a.src_gain[q] * exp(0.5 * norm2(dx, dy));
+  if (a.variant == 2) {
+    const double th = atan2(dy, dx);
+    term = term * exp(0.05 * (th * th) / 0.1);
+  }
+  return term;
+}
+
+// Phase 1b: the term of every node against its INSERTION-TIME parent, once per node.  Almost every step of every
+// walk uses exactly this value (a step differs only where a rewire changed the node's parent before the branch
+// was scored), so phase 2 becomes a gather-sum of 8-byte terms along parent indices instead of two exp() per step.
+__global__ void __launch_bounds__(128) node_term0_kernel(TermArgs a, int N, const int* __restrict__ parent0,
+                                                         double* __restrict__ term0) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= N) return;
+  const int p = parent0[q];
+  term0[q] = p >= 0 ? branch_term(a, q, p) : 0.0;
+}
+
 // ---- phase 2: branch walks -------------------------------------------------------------------
-__global__ void __launch_bounds__(128) branch_gain_kernel(int variant, const double* __restrict__ node_xy, int N,
-                                                          const int* __restrict__ parent0, const int* __restrict__ hoff,
-                                                          const int* __restrict__ htime, const int* __restrict__ hpar,
-                                                          const double* __restrict__ src_gain,
-                                                          const double* __restrict__ wpen, const int* __restrict__ n_close,
-                                                          int agent_has_obs, int have_estimates,
-                                                          const double* __restrict__ obst, int n_obst,
+__global__ void __launch_bounds__(128) branch_gain_kernel(TermArgs a, int N, const int* __restrict__ parent0,
+                                                          const int* __restrict__ hoff, const int* __restrict__ htime,
+                                                          const int* __restrict__ hpar, const double* __restrict__ term0,
                                                           const int* __restrict__ eval_node,
                                                           const int* __restrict__ eval_time, int B,
                                                           double* __restrict__ out) {
@@ -225,48 +276,13 @@ __global__ void __launch_bounds__(128) branch_gain_kernel(int variant, const dou
   const int T = eval_time ? eval_time[b] : 0x7fffffff;
   double sum = 0.0;
   for (int guard = 0; guard < N; ++guard) {
-    const int p = parent_at(q, T, parent0, hoff, htime, hpar);
+    const int p0 = parent0[q];
+    const int p = hoff ? parent_at(q, T, parent0, hoff, htime, hpar) : p0;
     if (p < 0) break;
-    const double qx = node_xy[2 * q], qy = node_xy[2 * q + 1];
-    const double px = node_xy[2 * p], py = node_xy[2 * p + 1];
-    double term;
-    if (variant == 3) {
-      double w = wpen[q];
-      for (int o = 0; o < n_obst && w == 0.0; ++o) {  // edge parent -> node against the 4 sides, rrt.py:203-217
-        const double x0 = obst[4 * o], y0 = obst[4 * o + 1];
-        const double x1 = x0 + obst[4 * o + 2], y1 = y0 + obst[4 * o + 3];
-        if (seg_hit(px, py, qx, qy, x0, y0, x0, y1) || seg_hit(px, py, qx, qy, x1, y0, x1, y1) ||
-            seg_hit(px, py, qx, qy, x0, y0, x1, y0) || seg_hit(px, py, qx, qy, x0, y1, x1, y1))
-          w = INFINITY;
-      }
-      if (have_estimates) {
-        const double r = norm2(qx - px, qy - py);
-        const double dp = exp(0.5 * (r * r));
-        double ep = 0.0;
-        if (agent_has_obs) {
-          const int nc = n_close[q];
-          ep = exp(0.05 * (double)((long long)nc * nc));
-        }
-        term = ((src_gain[q] - dp) - ep) - w;
-      } else {
-        term = -w;
-      }
-    } else if (!have_estimates) {
-      term = 0.0;
-    } else if (variant == 0) {
-      term = src_gain[q];
-    } else {
-      const double dx = qx - px, dy = qy - py;
-      term = src_gain[q] * exp(0.5 * norm2(dx, dy));
-      if (variant == 2) {
-        const double th = atan2(dy, dx);
-        term = term * exp(0.05 * (th * th) / 0.1);
-      }
-    }
-    sum += term;
+    sum += (p == p0) ? term0[q] : branch_term(a, q, p);  // same value, same summation order as the inline form
     q = p;
   }
-  if (variant != 3) sum = fmax(sum, 0.0);  // max(final_gain, 0); rrt.py:70,96,128
+  if (a.variant != 3) sum = fmax(sum, 0.0);  // max(final_gain, 0); rrt.py:70,96,128
   out[b] = sum;
 }
 
@@ -410,14 +426,17 @@ int ipp_node_terms(int variant, const double* node_xy, int N, const double* sour
 int ipp_branch_gain(int variant, const double* node_xy, int N, const int* parent0, const int* hist_off,
                     const int* hist_time, const int* hist_parent, const double* src_gain, const double* wpen,
                     const int* n_close, int agent_has_obs, int have_estimates, const double* obstacles, int n_obst,
-                    const int* eval_node, const int* eval_time, int B, double* gain_out, void* stream) {
-  if (variant < 0 || variant > 3 || N <= 0 || B < 0 || !node_xy || !parent0 || !src_gain || !gain_out) return IPP_ERR_ARG;
+                    const int* eval_node, const int* eval_time, int B, double* term0, double* gain_out, void* stream) {
+  if (variant < 0 || variant > 3 || N <= 0 || B < 0 || !node_xy || !parent0 || !src_gain || !gain_out || !term0)
+    return IPP_ERR_ARG;
   if (B == 0) return IPP_OK;
   if (!eval_node || (variant == 3 && (!wpen || (agent_has_obs && have_estimates && !n_close)))) return IPP_ERR_ARG;
   if (n_obst > 0 && !obstacles) return IPP_ERR_ARG;
-  branch_gain_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
-      variant, node_xy, N, parent0, hist_off, hist_time, hist_parent, src_gain, wpen, n_close, agent_has_obs,
-      have_estimates, obstacles, n_obst, eval_node, eval_time, B, gain_out);
+  TermArgs a{variant, node_xy, src_gain, wpen, n_close, agent_has_obs, have_estimates, obstacles, n_obst};
+  cudaStream_t st = (cudaStream_t)stream;
+  node_term0_kernel<<<(N + 127) / 128, 128, 0, st>>>(a, N, parent0, term0);
+  branch_gain_kernel<<<(B + 127) / 128, 128, 0, st>>>(a, N, parent0, hist_off, hist_time, hist_parent, term0, eval_node,
+                                                      eval_time, B, gain_out);
   IPP_LAUNCH_CHECK();
   return IPP_OK;
 }

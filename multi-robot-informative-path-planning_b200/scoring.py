@@ -206,6 +206,7 @@ class GpuScorer:
         d["nclose"] = None
         d["eval_node"] = torch.arange(N, dtype=torch.int32, device="cuda")
         d["out"] = torch.empty(N, dtype=torch.float64, device="cuda")
+        d["term0"] = torch.empty(N, dtype=torch.float64, device="cuda")
         d["d_wp"] = float(ctx.d_wp)
         return d
 
@@ -231,8 +232,8 @@ class GpuScorer:
                                        _lib.ptr(d["htime"]), _lib.ptr(d["hpar"]), _lib.ptr(d["src_gain"]), _lib.ptr(d["wpen"]),
                                        _lib.ptr(d["nclose"]), d["has_obs"], 1 if d["S"] else 0, _lib.ptr(d["obst"]),
                                        d["n_obst"], _lib.ptr(d["eval_node"]), _lib.ptr(d["eval_node"]), d["N"],
-                                       _lib.ptr(d["out"]), st), "ipp_branch_gain")
-        self.launches += 1
+                                       _lib.ptr(d["term0"]), _lib.ptr(d["out"]), st), "ipp_branch_gain")
+        self.launches += 2
 
     def tree_information(self, variant, tree, ctx: ScoreContext):
         if tree.n == 0:

@@ -634,4 +634,4 @@ def test_abi_rejects_bad_arguments_on_device(torch):
     x = torch.zeros(4, 2, dtype=torch.float64, device="cuda")
     assert lib.ipp_gram_rbf(_lib.ptr(x), 4, None, 0, 1.0, -1.0, 0.0, _lib.ptr(x), 4, None) == -1
     assert lib.ipp_branch_gain(7, None, 0, None, None, None, None, None, None, None, 0, 0, None, 0, None, None, 0, None,
-                               None) == -1
+                               None, None) == -1
