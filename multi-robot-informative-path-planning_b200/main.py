@@ -48,6 +48,9 @@ def initialize_scenarios(config: Dict) -> List[PointSourceField]:
         elif ws is not None:
             params["workspace_size"] = tuple(ws)
         scenario = PointSourceField(**params)
+        # extension of the reference's config: defer the per-step GP refits nobody reads
+        if hasattr(scenario.gp, "lazy"):
+            scenario.gp.lazy = bool(config["args"].get("lazy_gp", False))
         for key, value in sc.get("specific_params", {}).items():
             scenario.update_source(int(key) - 1, *value)
         scenarios.append(scenario)

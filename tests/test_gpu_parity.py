@@ -9,6 +9,7 @@ Tolerances are the tiers of SURVEY.md §8c:
   T3 decisions   : bit-identical trees / argmax / waypoint sequences; gain values rel 1e-12
 """
 import ctypes as C
+import os
 import warnings
 
 import numpy as np
@@ -623,6 +624,25 @@ def test_boustrophedon_on_device(gold, tag, cls_name, kw):
         Z1, std1 = sc.predict_spatial_field(st.obs_wp, np.asarray(st.measurements, float))
     assert np.abs(np.log10(Z1[::4, ::4]) - np.log10(g[f"{tag}_Z"])).max() <= 1e-4
     assert np.abs(std1.reshape(Z1.shape)[::4, ::4] - g[f"{tag}_std"]).max() <= 1e-6
+
+
+def test_main_config_flow_on_device(tmp_path):
+    """The reference's CLI flow (main.py: JSON -> scenarios -> strategies by name -> run -> metrics) end to end on the
+    device, with the strategy names of the reference's shipped config (aliases of MR_Boustrophedon / MR_IPP)."""
+    import json
+
+    from mripp_b200 import main as M
+    from tests.conftest import ROOT
+
+    out = tmp_path / "metrics.json"
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        res = M.main(["-config", os.path.join(ROOT, "config", "example_setup.json"), "--out", str(out)])
+    assert len(res) == 2 and {r["strategy"] for r in res} == {
+        "MultiAgentBoustrophedon", "RRTRIG_PointSourceInformative_All_SourceMetric_PathPlanning"}
+    for r in json.load(open(out)):
+        assert np.isfinite(r["rmse"]) and np.isfinite(r["wrmse"]) and np.isfinite(r["entropy"]) and r["n_obs"] > 10
+        assert r["rmse"] < 2.0  # log10 units: the field is reconstructed, not garbage
 
 
 def test_abi_rejects_bad_arguments_on_device(torch):
