@@ -144,6 +144,36 @@ def morton_order(X):
     return np.argsort(spread(q[:, 0]) | (spread(q[:, 1]) << np.uint64(1)), kind="stable")
 
 
+def clustered_order(X, slab=16, cluster_order="maximin"):
+    """Order of the observations for the final factorisation when the lattice kernel is to skip slabs: the points are
+    cut into spatial clusters of `slab` consecutive points along the Z-order curve (so that a slab of k* is one
+    compact cluster), and the CLUSTERS are then taken coarse to fine -- farthest-point (maximin) order of their
+    centroids -- instead of along the curve.  Eliminating in curve order makes every leading block a dense,
+    badly conditioned neighbourhood, and the explicit inverse W = L^-1 (built from products of such leading
+    blocks) loses 3-4 digits of the variance next to the data when there are more than ~2 observations per
+    l x l cell; coarse-to-fine order keeps the leading blocks as well conditioned as a random order does."""
+    m = morton_order(X)
+    n = len(m)
+    blocks = [m[i:i + slab] for i in range(0, n - n % slab, slab)]
+    tail = m[n - n % slab:]  # the short cluster stays last, so that every slab of 16 rows is exactly one cluster
+    if len(blocks) <= 2 or cluster_order == "curve":
+        return m
+    cent = np.array([X[b].mean(axis=0) for b in blocks])
+    if cluster_order == "shuffled":
+        order = np.random.RandomState(len(blocks)).permutation(len(blocks))
+    else:
+        order = np.empty(len(blocks), dtype=np.int64)
+        order[0] = 0
+        dmin = np.hypot(*(cent - cent[0]).T)
+        dmin[0] = -1.0
+        for k in range(1, len(blocks)):
+            j = int(np.argmax(dmin))
+            order[k] = j
+            dmin = np.minimum(dmin, np.hypot(*(cent - cent[j]).T))
+            dmin[j] = -1.0
+    return np.concatenate([blocks[i] for i in order] + [tail])
+
+
 def slab_bounding_boxes(Xs, NP, slab=16):
     """{xmin, xmax, ymin, ymax} of each `slab` consecutive rows of Xs, padded to NP rows; slabs that hold only
     padding get an empty box infinitely far away."""
@@ -526,7 +556,7 @@ class GaussianProcessRegressor:
         cutoff = self._skip_cutoff(length_scale)
         extent = float(np.max(X.max(axis=0) - X.min(axis=0))) if n > 1 else 0.0
         if cutoff > 0.0 and cutoff < 0.35 * extent and n >= 256:
-            self._perm = morton_order(X)
+            self._perm = clustered_order(X, cluster_order=getattr(self, "cluster_order", "maximin"))
             pd = torch.from_numpy(self._perm).cuda()
             self._Xd_fit = self._Xd.index_select(0, pd).contiguous()
             self._yd_fit = self._yd.index_select(0, pd).contiguous()
