@@ -314,7 +314,7 @@ def test_clustered_elimination_order_keeps_the_variance(G):
     # slabs are exactly the clusters: 16 consecutive rows of the fitted order are spatially compact
     Xs = X[gp._perm]
     w = np.ptp(Xs[: n - n % 16].reshape(-1, 16, 2), axis=1).max(axis=1)
-    assert np.median(w) < 6.0 and sorted(gp._perm.tolist()) == list(range(n))
+    assert np.median(w) < 0.15 * W and sorted(gp._perm.tolist()) == list(range(n))  # (a few clusters straddle a jump of the curve)
 
 
 def test_predict_recognises_the_reference_lattice(G, torch):
