@@ -303,6 +303,7 @@ class GaussianProcessRegressor:
         self.restart_streams = None
         # block sparsity of the lattice posterior: entries of k* below skip_below * c are not computed (0: dense)
         self.skip_below = 1e-30
+        self.cluster_order = "maximin"  # order of the spatial clusters in the sparse state (see clustered_order)
         self._scratch = None
         self.n_lml_evals_ = 0
         self.lazy = False
@@ -556,7 +557,7 @@ class GaussianProcessRegressor:
         cutoff = self._skip_cutoff(length_scale)
         extent = float(np.max(X.max(axis=0) - X.min(axis=0))) if n > 1 else 0.0
         if cutoff > 0.0 and cutoff < 0.35 * extent and n >= 256:
-            self._perm = clustered_order(X, cluster_order=getattr(self, "cluster_order", "maximin"))
+            self._perm = clustered_order(X, cluster_order=self.cluster_order)
             pd = torch.from_numpy(self._perm).cuda()
             self._Xd_fit = self._Xd.index_select(0, pd).contiguous()
             self._yd_fit = self._yd.index_select(0, pd).contiguous()
