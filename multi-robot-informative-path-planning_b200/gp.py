@@ -684,9 +684,11 @@ class GaussianProcessRegressor:
         executed = 0
         for lo in range(0, nt, 2048):  # chunked: tiles x slabs
             sl = slice(lo, lo + 2048)
+            # (padding slabs sit at 1e300: their gap squares to inf, i.e. inactive)
             gx = np.maximum(0.0, np.maximum(bb[None, :, 0] - qx1[sl, None], qx0[sl, None] - bb[None, :, 1]))
             gy = np.maximum(0.0, np.maximum(bb[None, :, 2] - qy1[sl, None], qy0[sl, None] - bb[None, :, 3]))
-            cum = np.cumsum(gx * gx + gy * gy <= cutoff * cutoff, axis=1)
+            with np.errstate(over="ignore"):
+                cum = np.cumsum(gx * gx + gy * gy <= cutoff * cutoff, axis=1)
             executed += int(cum[:, kslabs - 1].sum())
         return executed, dense
 
