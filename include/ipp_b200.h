@@ -144,6 +144,21 @@ int ipp_ucb_visit_penalty(const double* leaf_xy, int L, const double* path_xy, i
 /* np.argmax semantics (first maximum; the first NaN wins).  rrt.py:486, rrt_thread.py:389. */
 int ipp_argmax_first(const double* v, int n, double* best_val, int* best_idx, void* stream);
 
+/* ---- callers either side of the hot path -----------------------------------
+ * Analytic ground-truth field over the workspace lattice (index = iy * nx + ix, np.linspace axes):
+ * inverse-square intensity + detector response with air absorption, and concrete absorption along the chord of
+ * the source -> point ray inside every rectangle obstacle.  sources: S x 3 rows [x, y, A]; obstacles: n_obst x 4
+ * rows [x, y, width, height].  Replaces PointSourceField.ground_truth and compute_path_length_in_obstacle:
+ * src/point_source/point_source.py:163-260 (a Python loop over every lattice point when obstacles are present). */
+int ipp_ground_truth_grid(const double* sources, int S, const double* obstacles, int n_obst, double x0, double x1,
+                          int nx, double y0, double y1, int ny, double r_s, double r_d, double* field, void* stream);
+
+/* out[0..3] = {RMSE, source-weighted RMSE of log10(Z + 1), differential entropy of std in bits, sum of z_true} over
+ * G lattice points, one fused pass over device-resident arrays.  partial: 4 * 592 doubles of scratch.
+ * Replaces main.py:113-114 and calculate_differential_entropy, src/visualization/plot_helper.py:383-398. */
+int ipp_grid_metrics(const double* zpred, const double* std, const double* ztrue, long long G, double* partial,
+                     double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -36,6 +36,8 @@ SIGNATURES = {
     "ipp_leaf_penalty": [_D, _D, _D, _I, _D, _I, _D, _F, _D, _D],
     "ipp_ucb_visit_penalty": [_D, _I, _D, _I, _F, _D, _D],
     "ipp_argmax_first": [_D, _I, _D, _D, _D],
+    "ipp_ground_truth_grid": [_D, _I, _D, _I, _F, _F, _I, _F, _F, _I, _F, _F, _D, _D],
+    "ipp_grid_metrics": [_D, _D, _D, _LL, _D, _D, _D],
 }
 
 

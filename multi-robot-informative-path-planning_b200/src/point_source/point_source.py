@@ -134,6 +134,26 @@ class PointSourceField:
             field += inten + resp
         return field
 
+    def ground_truth_device(self, as_tensor: bool = False):
+        """The same field from the device (ipp_ground_truth_grid): one thread per lattice point instead of the
+        Python loop over every point that the obstacle branch costs on the host (point_source.py:247-258).  Equal to
+        `ground_truth()` to rounding (CUDA vs numpy exp / asin / cos); it feeds metrics only -- the measurements
+        come from `intensity()` on the host, bit-exact."""
+        from mripp_b200 import _lib
+
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        w = self.workspace_size
+        nx, ny = self.x.shape[0], self.y.shape[0]
+        src = torch.from_numpy(np.ascontiguousarray(np.asarray(self.sources, dtype=np.float64).reshape(-1, 3))).cuda()
+        rect = [[o["x"], o["y"], o["width"], o["height"]] for o in self.obstacles if o.get("type") == "rectangle"]
+        ob = torch.from_numpy(np.asarray(rect, dtype=np.float64).reshape(-1, 4)).cuda() if rect else None
+        out = torch.empty(nx * ny, dtype=torch.float64, device="cuda")
+        _lib.check(lib.ipp_ground_truth_grid(_lib.ptr(src), src.shape[0], _lib.ptr(ob), len(rect), float(w[0]), float(w[1]),
+                                             nx, float(w[2]), float(w[3]), ny, float(self.r_s), float(self.r_d),
+                                             _lib.ptr(out), _lib.stream_ptr()), "ipp_ground_truth_grid")
+        return out.view(ny, nx) if as_tensor else out.view(ny, nx).cpu().numpy()
+
     def compute_path_length_in_obstacle(self, R, R_n, obstacle):
         """point_source.py:214-260: chord of the source->point ray inside a rectangle."""
         x_min, x_max = obstacle["x"], obstacle["x"] + obstacle["width"]

@@ -17,12 +17,12 @@ def _declared():
 
 def test_header_library_and_binding_agree():
     names = _declared()
-    assert len(names) >= 14
+    assert len(names) >= 16
     lib = _lib.load()
     for n in names:
         assert hasattr(lib, n), f"{n} declared in ipp_b200.h but not exported"
     assert sorted(_lib.SIGNATURES) == names
-    assert lib.ipp_abi_version() == 6
+    assert lib.ipp_abi_version() == 7
 
 
 def test_layout_is_host_only_and_consistent():

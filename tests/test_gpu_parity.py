@@ -671,6 +671,42 @@ def test_main_config_flow_on_device(tmp_path):
         assert r["rmse"] < 2.0  # log10 units: the field is reconstructed, not garbage
 
 
+@pytest.mark.parametrize("tag", ["free", "obst"])
+def test_ground_truth_and_metrics_on_device(gold, torch, tag):
+    """the analytic field (with a rectangle obstacle) and the fused end-of-run metrics on the
+    device against the reference's golden field and the host expressions."""
+    from mripp_b200.src.point_source.point_source import PointSourceField
+    from mripp_b200.src.visualization.plot_helper import calculate_differential_entropy, field_metrics_device
+
+    g = gold("field_golden.npz")
+    obst = [{"type": "rectangle", "x": 4, "y": 5, "width": 3, "height": 2}] if tag == "obst" else []
+    sc = PointSourceField(num_sources=2, workspace_size=(0, 12, 0, 12), obstacles=obst, seed=8)
+    ref = g[f"{tag}_gtruth"]
+    dev = sc.ground_truth_device()
+    assert dev.shape == ref.shape
+    assert np.abs(dev / ref - 1.0).max() <= 1e-12
+    # metrics: a perturbed copy of the field as "prediction", a positive std with a few exact zeros
+    rng = np.random.RandomState(3)
+    zp = ref * np.exp(0.3 * rng.randn(*ref.shape))
+    sd = np.abs(rng.randn(ref.size)) * 0.2
+    sd[::97] = 0.0
+    err = np.log10(ref + 1) - np.log10(zp + 1)
+    rmse, wrmse = np.sqrt(np.mean(err ** 2)), np.sqrt(np.sum(ref * err ** 2) / np.sum(ref))
+    ent = calculate_differential_entropy(sd.copy())
+    got = field_metrics_device(torch.from_numpy(zp).cuda(), torch.from_numpy(sd).cuda(), torch.from_numpy(ref).cuda())
+    assert got[0] == pytest.approx(rmse, rel=1e-12) and got[1] == pytest.approx(wrmse, rel=1e-12)
+    assert got[2] == pytest.approx(ent, rel=1e-12)
+
+
+def test_ground_truth_device_many_obstacles_matches_host(torch):
+    from mripp_b200.src.point_source.point_source import PointSourceField
+
+    obst = [{"type": "rectangle", "x": 2.0 + 3 * i, "y": 1.5 + 2.5 * (i % 3), "width": 1.2, "height": 0.9} for i in range(5)]
+    sc = PointSourceField(num_sources=4, workspace_size=(0, 18, 0, 9), obstacles=obst, seed=2)
+    host, dev = sc.g_truth, sc.ground_truth_device()
+    assert np.abs(dev / host - 1.0).max() <= 1e-12
+
+
 def test_abi_rejects_bad_arguments_on_device(torch):
     from mripp_b200 import _lib
 
