@@ -369,6 +369,17 @@ def test_factor_properties_full_size(G, torch):
     assert std.min() >= 0.0 and std.max() <= np.sqrt(c) * gp._y_train_std * (1 + 1e-12)
     far = gp.predict(np.array([[1e4, 1e4]]), return_std=True)
     assert far[0][0] == pytest.approx(gp._y_train_mean) and far[1][0] == pytest.approx(np.sqrt(c) * gp._y_train_std)
+    # the whole C4 lattice (10^6 points): block-sparse == dense, variance within the prior, slabs reassemble
+    sp = gp.predict_grid_device(0, W, 1000, 0, W, 1000)
+    de = gp.predict_grid_device(0, W, 1000, 0, W, 1000, skip_below=0)
+    assert float((sp[0] - de[0]).abs().max()) <= 1e-12 * max(1.0, float(de[0].abs().max()))
+    assert float((sp[1] - de[1]).abs().max()) <= 1e-12
+    assert float(sp[1].min()) >= 0.0 and float(sp[1].max()) <= np.sqrt(c) * gp._y_train_std * (1 + 1e-12)
+    assert bool(torch.isfinite(sp[0]).all()) and bool(torch.isfinite(sp[2]).all())
+    executed, dense = gp.lattice_work(0, W, 1000, 0, W, 1000)
+    assert 0.1 * dense < executed < 0.5 * dense  # theta = (1, 2) on 100 x 100: about a quarter of the slabs
+    half = gp.predict_grid_device(0, W, 1000, 0, W, 1000, g_begin=0, g_end=500 * 1000, skip_below=0)
+    assert torch.equal(half[1], de[1][: 500 * 1000])
     # one C4-scale row slab of the lattice against the oracle
     m_d, s_d, _ = gp.predict_grid_device(0, W, 1000, 0, W, 1000, g_begin=500 * 1000, g_end=500 * 1000 + 2048)
     st = O.fit(X, y, c, l, optimize=False)
