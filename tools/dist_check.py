@@ -33,6 +33,37 @@ k2 = D.sharded_argmax(torch.from_numpy(scores[lo:hi]).cuda(), lo)
 ok = ok and k2 == int(np.argmax(scores))
 path = D.broadcast_path(np.array([[1.0, 2.0], [3.5, 4.5], [6.0, 7.0]]) if rank == world - 1 else None, src=world - 1, device="cuda")
 ok = ok and np.array_equal(path, np.array([[1.0, 2.0], [3.5, 4.5], [6.0, 7.0]]))
+# ---- strong scaling of ONE C4 lattice posterior by row slab (device time, max over ranks) ----------------------
+import time
+W4, n4 = 100, 5000
+X4, meas4, _ = synth_observations(n4, W4, 0)
+gp4 = G.GaussianProcessRegressor(kernel=G.ConstantRBFKernel(1.0, 2.0), optimizer=None, normalize_y=True).fit(X4, np.log10(meas4))
+g0, g1 = D.row_slab(1000, 1000, world, rank)
+def slab_step():
+    m_, s_, z_ = gp4.predict_grid_device(0, W4, 1000, 0, W4, 1000, g_begin=g0, g_end=g1)
+    sizes = [b - a for a, b in (D.row_slab(1000, 1000, world, r) for r in range(world))]
+    return D.gather_slabs(z_, sizes), D.gather_slabs(s_, sizes)
+for _ in range(3):
+    slab_step()
+dist.barrier(); torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(5):
+    zf, sf = slab_step()
+e1.record(); dist.barrier(); torch.cuda.synchronize()
+tms = torch.tensor([e0.elapsed_time(e1) / 5], device="cuda"); dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+sc8 = torch.randn(8192, dtype=torch.float64, device="cuda")
+lo8, hi8 = D.slab_bounds(8192, world, rank)
+for _ in range(3):
+    D.sharded_argmax(sc8[lo8:hi8], lo8)
+torch.cuda.synchronize(); t0 = time.perf_counter()
+for _ in range(20):
+    D.sharded_argmax(sc8[lo8:hi8], lo8)
+torch.cuda.synchronize(); t_arg = (time.perf_counter() - t0) / 20
+if rank == 0:
+    print(f"dist_check strong scaling: one C4 lattice (10^6 points, n=5000) by row slab over {world} GPUs incl. all_gather of "
+          f"Z and std: {float(tms):.1f} ms per posterior ({1e6 / float(tms) * 1e3:.3e} points/s); sharded argmax of 8192 "
+          f"scores (all_gather of one pair per rank): {t_arg * 1e6:.0f} us", flush=True)
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
