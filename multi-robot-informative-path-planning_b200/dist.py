@@ -30,6 +30,32 @@ def row_slab(nx: int, ny: int, world: int, rank: int) -> Tuple[int, int]:
     return r0 * nx, r1 * nx
 
 
+def balanced_row_slabs(row_work: Sequence[float], nx: int, world: int) -> List[Tuple[int, int]]:
+    """Flat index ranges of `world` contiguous slabs of whole lattice rows with near-equal WORK: with the
+    block-sparse posterior the rows at the workspace border have fewer observations in reach than the interior, so
+    equal row counts are unequal work.  row_work[iy] >= 0 is any per-row cost estimate (gp.lattice_work)."""
+    w = np.maximum(np.asarray(row_work, dtype=np.float64), 0.0) + 1e-12
+    ny = len(w)
+    cum = np.concatenate([[0.0], np.cumsum(w)])
+    cuts = [0]
+    for r in range(1, world):
+        target = cum[-1] * r / world
+        k = int(np.searchsorted(cum, target))
+        k = min(max(k, cuts[-1] + (1 if ny - cuts[-1] > world - r else 0)), ny - (world - r))
+        cuts.append(max(k, cuts[-1]))
+    cuts.append(ny)
+    return [(cuts[r] * nx, cuts[r + 1] * nx) for r in range(world)]
+
+
+def lattice_slabs(gp, ws, nx: int, ny: int, world: int) -> List[Tuple[int, int]]:
+    """The row-slab split every rank uses for one lattice posterior: equal rows for an estimator without a work model,
+    else balanced on the per-row work estimate of the block-sparse kernel (gp.lattice_row_work).  Every rank holds the same fitted state,
+    so every rank derives the same split without communication."""
+    if world <= 1 or not hasattr(gp, "lattice_row_work"):
+        return [row_slab(nx, ny, world, r) for r in range(world)]
+    return balanced_row_slabs(gp.lattice_row_work(ws[0], ws[1], nx, ws[2], ws[3], ny), nx, world)
+
+
 def rounds_for_rank(n_rounds: int, world: int, rank: int) -> List[int]:
     return [r for r in range(n_rounds) if r % world == rank]
 
@@ -61,7 +87,7 @@ def sharded_grid_posterior(gp, ws, nx: int, ny: int, group=None, compute_slab: O
     the fitted `gp` (mripp_b200.gp.GaussianProcessRegressor.predict_grid_device)."""
     dist = _dist()
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    bounds = [row_slab(nx, ny, world, r) for r in range(world)]
+    bounds = lattice_slabs(gp, ws, nx, ny, world) if compute_slab is None else [row_slab(nx, ny, world, r) for r in range(world)]
     g0, g1 = bounds[rank]
     if compute_slab is None:
         def compute_slab(a, b):

@@ -561,7 +561,8 @@ class GaussianProcessRegressor:
             pd = torch.from_numpy(self._perm).cuda()
             self._Xd_fit = self._Xd.index_select(0, pd).contiguous()
             self._yd_fit = self._yd.index_select(0, pd).contiguous()
-            self._bbox_d = torch.from_numpy(slab_bounding_boxes(X[self._perm], self._ws.layout[0])).cuda()
+            self._bbox_h = slab_bounding_boxes(X[self._perm], self._ws.layout[0])
+            self._bbox_d = torch.from_numpy(self._bbox_h).cuda()
         else:
             self._perm = np.arange(n)
             self._Xd_fit, self._yd_fit, self._bbox_d = self._Xd, self._yd, None
@@ -653,7 +654,7 @@ class GaussianProcessRegressor:
         self.d2h_bytes_ = 16 * m
         return host[m:].copy(), host[:m].copy()
 
-    def lattice_work(self, x0, x1, nx, y0, y1, ny, g_begin=0, g_end=None, skip_below=None):
+    def lattice_work(self, x0, x1, nx, y0, y1, ny, g_begin=0, g_end=None, skip_below=None, per_tile=False):
         """(executed, dense) counts of 128-query x 128-row x 16-observation DMMA slabs of the lattice kernel for
         this fitted state: the host restatement of the kernel's own slab test (lattice_slab_mask in
         csrc/ipp_posterior.cu), used by bench.py to turn a launch time into executed flop/s."""
@@ -668,7 +669,7 @@ class GaussianProcessRegressor:
         dense = int(kslabs.sum()) * int(nt)
         cutoff = self._skip_cutoff(self._fitted_l, skip_below) if self._bbox_d is not None else 0.0
         if cutoff <= 0.0:
-            return dense, dense
+            return np.full(nt, int(kslabs.sum()), dtype=np.int64) if per_tile else (dense, dense)
         bb = self._bbox_d.cpu().numpy()
         xstep = (x1 - x0) / (nx - 1) if nx > 1 else 0.0
         ystep = (y1 - y0) / (ny - 1) if ny > 1 else 0.0
@@ -682,6 +683,7 @@ class GaussianProcessRegressor:
         qy0 = y0 + iy0 * ystep
         qy1 = np.where(same, qy0, y0 + (iy0 + 1) * ystep)
         executed = 0
+        tiles = np.zeros(nt, dtype=np.int64)
         for lo in range(0, nt, 2048):  # chunked: tiles x slabs
             sl = slice(lo, lo + 2048)
             # (padding slabs sit at 1e300: their gap squares to inf, i.e. inactive)
@@ -689,8 +691,32 @@ class GaussianProcessRegressor:
             gy = np.maximum(0.0, np.maximum(bb[None, :, 2] - qy1[sl, None], qy0[sl, None] - bb[None, :, 3]))
             with np.errstate(over="ignore"):
                 cum = np.cumsum(gx * gx + gy * gy <= cutoff * cutoff, axis=1)
-            executed += int(cum[:, kslabs - 1].sum())
-        return executed, dense
+            tiles[sl] = cum[:, kslabs - 1].sum(axis=1)
+            executed += int(tiles[sl].sum())
+        return tiles if per_tile else (executed, dense)
+
+    def lattice_row_work(self, x0, x1, nx, y0, y1, ny, skip_below=None):
+        """Cheap per-row estimate (ny values, arbitrary unit) of the lattice kernel's executed slabs, for splitting one
+        lattice over GPUs by work (dist.lattice_slabs): a slab counts for a row when its box is within the cutoff in y,
+        weighted by the fraction of the row within the cutoff in x and by the row blocks of W that contain it.
+        ny x n_slabs host operations (about 1 ms for C4) against the exact per-tile count of lattice_work."""
+        self._ensure()
+        n = self.X_train_.shape[0]
+        cutoff = self._skip_cutoff(self._fitted_l, skip_below) if self._bbox_d is not None else 0.0
+        if cutoff <= 0.0:
+            return np.ones(int(ny))
+        bb = self._bbox_h                                              # host copy: no device sync before the launch
+        real = bb[:, 0] < 1e299
+        bb = bb[real]
+        first = n % 128
+        slab_lo = 16 * np.arange(len(real))[real]                      # first observation of the slab
+        rlims = np.array(([first] if first else []) + [first + 128 * j for j in range(1, n // 128 + 1)])
+        mult = (rlims[None, :] > slab_lo[:, None]).sum(axis=1).astype(np.float64)   # row blocks of W reading the slab
+        span = max(float(x1 - x0), 1e-300)
+        wx = np.clip(np.minimum(x1, bb[:, 1] + cutoff) - np.maximum(x0, bb[:, 0] - cutoff), 0.0, None) / span
+        ys = np.linspace(y0, y1, int(ny))
+        gy = np.maximum(0.0, np.maximum(bb[None, :, 2] - ys[:, None], ys[:, None] - bb[None, :, 3]))
+        return (gy <= cutoff) @ (wx * mult) + 1e-9
 
     def _lattice_tables(self, nx, ny):
         """Scratch for the lattice fast path of ipp_gp_posterior_grid: (nx + ny) * NP doubles."""

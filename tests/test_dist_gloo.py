@@ -80,3 +80,22 @@ def test_partition_helpers():
     assert D.row_slab(10, 7, 2, 1) == (40, 70)
     assert D.combine_argmax(np.array([np.nan, 1.0]), np.array([5, 0])) == 5
     assert D.combine_argmax(np.array([2.0, 2.0, 3.0]), np.array([4, 1, -1])) == 1
+
+
+def test_balanced_row_slabs_partition_and_balance():
+    """Work-balanced lattice split: contiguous whole rows, covers the lattice once, near-equal work, and never an
+    empty slab while rows remain (dist.balanced_row_slabs)."""
+    from mripp_b200.dist import balanced_row_slabs
+    rng = np.random.RandomState(0)
+    for ny, nx, world in [(1000, 1000, 8), (50, 37, 3), (7, 5, 7), (3, 10, 8), (1, 4, 2)]:
+        w = rng.rand(ny) + np.concatenate([np.linspace(0, 3, ny // 2), np.linspace(3, 0, ny - ny // 2)])
+        b = balanced_row_slabs(w, nx, world)
+        assert len(b) == world and b[0][0] == 0 and b[-1][1] == nx * ny
+        assert all(b[r][1] == b[r + 1][0] for r in range(world - 1))
+        assert all(lo % nx == 0 and hi % nx == 0 and lo <= hi for lo, hi in b)
+        if ny >= world:
+            assert all(hi > lo for lo, hi in b)
+        if ny >= 50 * world:
+            loads = np.array([w[lo // nx:hi // nx].sum() for lo, hi in b])
+            assert loads.max() <= 1.05 * loads.mean()
+    assert balanced_row_slabs(np.zeros(10), 10, 3) == [(0, 40), (40, 70), (70, 100)]  # no information: near-equal rows

@@ -38,11 +38,18 @@ import time
 W4, n4 = 100, 5000
 X4, meas4, _ = synth_observations(n4, W4, 0)
 gp4 = G.GaussianProcessRegressor(kernel=G.ConstantRBFKernel(1.0, 2.0), optimizer=None, normalize_y=True).fit(X4, np.log10(meas4))
-g0, g1 = D.row_slab(1000, 1000, world, rank)
-def slab_step():
-    m_, s_, z_ = gp4.predict_grid_device(0, W4, 1000, 0, W4, 1000, g_begin=g0, g_end=g1)
-    sizes = [b - a for a, b in (D.row_slab(1000, 1000, world, r) for r in range(world))]
+def slab_step(balanced=True):
+    bounds = (D.lattice_slabs(gp4, (0, W4, 0, W4), 1000, 1000, world) if balanced
+              else [D.row_slab(1000, 1000, world, r) for r in range(world)])   # the split is inside the timed step
+    m_, s_, z_ = gp4.predict_grid_device(0, W4, 1000, 0, W4, 1000, g_begin=bounds[rank][0], g_end=bounds[rank][1])
+    sizes = [b - a for a, b in bounds]
     return D.gather_slabs(z_, sizes), D.gather_slabs(s_, sizes)
+zb, sb = slab_step(True); ze, se = slab_step(False)
+mfull, sfull, zfull = gp4.predict_grid_device(0, W4, 1000, 0, W4, 1000)
+ok = ok and bool(torch.allclose(sb, sfull, rtol=1e-9, atol=1e-12)) and bool(torch.allclose(se, sfull, rtol=1e-9, atol=1e-12))
+if rank == 0:
+    print("dist_check balanced slabs:", D.lattice_slabs(gp4, (0, W4, 0, W4), 1000, 1000, world),
+          "max |std - single GPU|", float((sb - sfull).abs().max()), flush=True)
 for _ in range(3):
     slab_step()
 dist.barrier(); torch.cuda.synchronize()
