@@ -518,6 +518,33 @@ def run_b200(args, wl, rank, world, local_rank):
         chosen = planning_step()
     barrier()
     plan_ms = 1e3 * (time.perf_counter() - t0) / 5
+
+    # ---- source estimator: particle log-likelihoods on the device, sampler on the host -------------
+    from mripp_b200.src.estimation import estimation as EST
+    from mripp_b200.src.point_source.point_source import PointSourceField
+    prep = scorer.prepare_counts(list(X), list(meas))
+    NPART, MSRC = 200, 3
+    prng = np.random.RandomState(1)
+    parts = np.column_stack([c for _ in range(MSRC) for c in (prng.uniform(0, W, NPART), prng.uniform(0, W, NPART),
+                                                              prng.uniform(1e5, 1e6, NPART))])
+    parts_d = torch.from_numpy(parts).cuda()
+    ll_out = torch.empty((NPART, 3), dtype=torch.float64, device="cuda")
+
+    def loglik_launch():
+        lib.ipp_poisson_loglik(_lib.ptr(parts_d), NPART, MSRC, _lib.ptr(prep["obs"]), _lib.ptr(prep["counts"]),
+                               _lib.ptr(prep["lgam"]), n, 1.0, _lib.ptr(ll_out), _lib.stream_ptr())
+    ll_us = 1e3 * timed(loglik_launch, 50, 5, count=False)[0]
+    scen = PointSourceField(num_sources=3, workspace_size=(0, W, 0, W), seed=1)
+    est_stats0 = dict(EST.STATS)
+    est_runs = []
+    for rep in range(3):
+        np.random.seed(3)
+        barrier()
+        t0 = time.perf_counter()
+        est_dev = EST.estimate_sources_bayesian(list(X), list(meas), 1, MSRC, NPART, 10, scen, scorer=scorer)
+        est_runs.append(time.perf_counter() - t0)
+    est_rng_dev = np.random.uniform(size=2)
+    est_stats = {k: EST.STATS[k] - est_stats0[k] for k in EST.STATS}
     if sampler:
         sampler.stop()
 
@@ -535,6 +562,14 @@ def run_b200(args, wl, rank, world, local_rank):
         use_all_host_threads()
         cpu_post = cpu_posterior_leg(wl, 0, args.cpu_sample or max(2048, min(20000, int(2.0e7 / n))), 2, 1)
         cpu_br = cpu_branch_leg(wl, 0, 16 if n >= 2000 else 64)
+        # the same sampler on the oracle's per-particle likelihood (the reference's loop, estimation.py:97)
+        from oracle.estimation_oracle import HostLikelihood
+        np.random.seed(3)
+        t0 = time.perf_counter()
+        est_cpu = EST.estimate_sources_bayesian(list(X), list(meas), 1, MSRC, NPART, 10, scen, scorer=HostLikelihood())
+        est_cpu_s = time.perf_counter() - t0
+        est_same = bool(np.array_equal(est_cpu[0], est_dev[0]) and est_cpu[1:] == est_dev[1:]
+                        and np.array_equal(np.random.uniform(size=2), est_rng_dev))
         line = {
             "metric": METRIC, "value": world * Gpts / (ms_post * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_post, "higher_is_better": True, "scaling": "weak",
@@ -586,6 +621,15 @@ def run_b200(args, wl, rank, world, local_rank):
                                                          "set against the HBM copy figure, not HBM traffic"},
                             "cpu_baseline": {"value": cpu_br["evals_per_s"], "cores": 1, "kind": "port",
                                              "sample": f"{cpu_br['sample_branches']} branches, pure-Python gain function"}},
+            "source_estimator": {
+                "loglik_kernel_us": ll_us, "particles": NPART, "observations": n, "sources": MSRC,
+                "terms_per_s": NPART * n * MSRC / (ll_us * 1e-6),
+                "estimate_ms": 1e3 * min(est_runs), "stages": 10 * MSRC, "stats_3_runs": est_stats,
+                "call": "estimate_sources_bayesian(obs_wp, obs_vals, 1, 3, 200, 10, scenario): 30 stages, one "
+                        "ipp_poisson_loglik launch each; RNG-consuming steps on the host",
+                "cpu_baseline": {"estimate_ms": 1e3 * est_cpu_s, "cores": 1, "kind": "port",
+                                 "sample": "the same call on oracle/estimation_oracle.py (per-particle scipy logpmf loop)"},
+                "identical_to_cpu": est_same},
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

@@ -159,6 +159,16 @@ int ipp_ground_truth_grid(const double* sources, int S, const double* obstacles,
 int ipp_grid_metrics(const double* zpred, const double* std, const double* ztrue, long long G, double* partial,
                      double* out, void* stream);
 
+/* Poisson log-likelihood of N particles (rows of 3*M doubles [x, y, A] per source) against n count observations:
+ *   out[3i]   = sum_j [ k_j log(rate_ij) - lgam_j - rate_ij ],  rate_ij = max(lambda_b + sum_m A_im / max(d2_ijm, 1e-6), 1e-10)
+ *   out[3i+1] = sum_j (|k_j log rate_ij| + |lgam_j| + rate_ij),  out[3i+2] = sum_j |term_ij|   (error-bound sums)
+ * counts: the rounded measurements as doubles; lgam: lgamma(counts + 1) from the caller (one per observation,
+ * shared by all particles).  rate is bit-identical to the numpy expression (no contraction, numpy's source-axis
+ * summation order); M <= 32.  Replaces the per-particle loop of calc_weights, src/estimation/estimation.py:97,
+ * over poisson_log_likelihood, src/estimation/estimation.py:15-55. */
+int ipp_poisson_loglik(const double* particles, int N, int M, const double* obs_xy, const double* counts,
+                       const double* lgam, int n, double lambda_b, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

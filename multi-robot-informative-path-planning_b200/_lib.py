@@ -38,6 +38,7 @@ SIGNATURES = {
     "ipp_argmax_first": [_D, _I, _D, _D, _D],
     "ipp_ground_truth_grid": [_D, _I, _D, _I, _F, _F, _I, _F, _F, _I, _F, _F, _D, _D],
     "ipp_grid_metrics": [_D, _D, _D, _LL, _D, _D, _D],
+    "ipp_poisson_loglik": [_D, _I, _I, _D, _D, _D, _I, _F, _D, _D],
 }
 
 

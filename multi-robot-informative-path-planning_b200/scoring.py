@@ -352,3 +352,30 @@ class GpuScorer:
                    "ipp_argmax_first")
         self.launches += 1
         return int(bi.item()), float(bv.item())
+
+    # -- particle log-likelihoods of the importance sampler ---------------------------
+    def prepare_counts(self, obs_wp, obs_vals):
+        """Observation side of the Poisson likelihood (estimation.py:36-37), uploaded once per source estimate and
+        shared by every stage and every source count: coordinates, rounded counts, and scipy's own
+        gammaln(k + 1) -- one value per observation, the same bits the reference computes per (particle, observation)."""
+        from scipy.special import gammaln
+        obs = np.ascontiguousarray(np.array(obs_wp, dtype=np.float64).reshape(-1, 2))
+        counts = np.round(obs_vals).astype(int)
+        return {"n": int(obs.shape[0]), "obs": self._dev(obs), "counts": self._dev(counts.astype(np.float64)),
+                "lgam": self._dev(np.asarray(gammaln(counts + 1), dtype=np.float64))}
+
+    def particle_log_likelihood(self, thetas, prepared, lambda_b, M):
+        """(ll, S1, S2) per particle: the log-likelihood and the two error-bound sums of ipp_poisson_loglik."""
+        torch, lib = self.torch, self.lib
+        P = np.ascontiguousarray(thetas, dtype=np.float64)
+        N = P.shape[0]
+        if P.shape[1] != 3 * M:
+            raise ValueError(f"particles have {P.shape[1]} columns, expected 3 * {M}")
+        Pd = self._dev(P)
+        out = torch.empty((N, 3), dtype=torch.float64, device="cuda")
+        _lib.check(lib.ipp_poisson_loglik(_lib.ptr(Pd), N, int(M), _lib.ptr(prepared["obs"]), _lib.ptr(prepared["counts"]),
+                                          _lib.ptr(prepared["lgam"]), prepared["n"], float(lambda_b), _lib.ptr(out),
+                                          _lib.stream_ptr()), "ipp_poisson_loglik")
+        self.launches += 1
+        h = out.cpu().numpy()
+        return h[:, 0], h[:, 1], h[:, 2]

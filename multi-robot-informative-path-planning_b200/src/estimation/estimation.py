@@ -1,27 +1,53 @@
-"""Multi-source parameter estimation (Morelande / Ristic / Gunatilaka importance sampling with
-progressive correction): host-side mirror of the reference's src/estimation/estimation.py.
+"""Multi-source parameter estimation (Morelande / Ristic / Gunatilaka importance sampling with progressive
+correction): mirror of the reference's src/estimation/estimation.py.
 
-It is NOT on the accelerated path this round: the resampling and
-perturbation steps consume the global RNG in a fixed order that the waypoint sequences depend on,
-so it stays on the host.  The only restructuring is that the Poisson log-likelihood of all
-`n_samples` particles is evaluated in ONE array expression instead of a Python loop over particles
-(estimation.py:97) -- element for element the same numpy / scipy calls, hence the same bits.
+What runs where.  The Poisson log-likelihood of all `n_samples` particles -- an N x n_obs x M array expression per
+stage, 85 % of a whole multi-agent run once the GP and the scoring are on the device -- is one launch of
+ipp_poisson_loglik.  Everything that consumes the global RNG (prior draws, np.random.choice, multivariate_normal.rvs)
+and everything that is returned to the caller (particles, the estimate, its log-likelihood and BIC) stays on the host
+in the reference's own numpy / scipy calls, so those values keep the reference's bits.
+
+Decision parity.  The device log-likelihoods only decide WHICH particles are resampled.  They differ from the
+reference's by rounding (log ulps, summation order), so a resampling draw u could in principle fall on the other side
+of a CDF step.  The kernel returns, next to ll_i, the sums that bound |ll_i - ll_i^reference| (BOUND below); the host
+turns them into a band around every CDF step and, when any of the stage's draws lies inside the band, re-decides that
+stage from the reference's own expression (batched_poisson_log_likelihood, identical numpy / scipy calls) with the
+same draws.  The resampled indices -- and with them every particle, estimate and waypoint downstream -- are
+therefore the reference's, bit for bit; STATS counts how often the band was hit.
 """
 from __future__ import annotations
 
-from typing import List, Tuple
+from typing import List, Optional, Tuple
 
 import numpy as np
 from scipy.stats import multivariate_normal, poisson, uniform
 
+EPS = float(np.finfo(np.float64).eps)
+# |ll_gpu - ll_reference| <= EPS * (C_TERM * S1 + c_sum(n) * S2).  Per observation, both sides hold the same rate,
+# count and lgamma; they differ by the ulp of log() (glibc and CUDA: < 1 ulp each -> 2 EPS |k log rate|), by one
+# rounding of k * log (1 EPS), and by the two subtractions (<= 2 EPS of the partial results): 5 EPS (|k log rate|
+# + lgamma + rate) = 5 EPS S1 in exact arithmetic; C_TERM = 16 leaves room for a log() 6 ulp off on either side.
+# The summations differ in order: numpy's pairwise sum (blocks of 128 on 8 accumulators: <= 24 additions deep for
+# n <= 8192, + 1 per doubling) against the kernel's (ceil(n / 256) sequential + 8 tree levels); each addition
+# contributes EPS / 2 of the running sum, itself <= S2.
+C_TERM = 16.0
+STATS = {"stages": 0, "redecided": 0, "device_evaluations": 0}
+
+
+def c_sum(n: int) -> float:
+    return float(np.ceil(n / 256.0) + 8.0 + 24.0 + max(0.0, np.ceil(np.log2(max(n, 1) / 8192.0))))
+
 
 def poisson_log_likelihood(theta: np.ndarray, obs_wp: np.ndarray, obs_vals: np.ndarray, lambda_b: float, M: int) -> float:
-    """estimation.py:15-55 for one parameter vector."""
+    """estimation.py:15-55 for one parameter vector (host: its value is returned to the caller through the BIC)."""
     return float(batched_poisson_log_likelihood(np.asarray(theta, dtype=float)[None, :], obs_wp, obs_vals, lambda_b, M)[0])
 
 
 def batched_poisson_log_likelihood(thetas: np.ndarray, obs_wp, obs_vals, lambda_b: float, M: int) -> np.ndarray:
-    """Log-likelihood of every row of `thetas` (N x 3M): rate = lambda_b + sum_i A_i / max(d2, 1e-6)."""
+    """Log-likelihood of every row of `thetas` (N x 3M) in ONE array expression instead of the reference's Python
+    loop over particles (estimation.py:97) -- element for element the same numpy / scipy calls, hence the same bits.
+    rate = lambda_b + sum_i A_i / max(d2, 1e-6).  Used for the values that leave this module and to re-decide a stage
+    whose draws fall inside the error band of the device likelihoods."""
     obs_wp = np.array(obs_wp)
     counts = np.round(obs_vals).astype(int)
     src = np.asarray(thetas, dtype=float).reshape(thetas.shape[0], M, 3)
@@ -31,21 +57,74 @@ def batched_poisson_log_likelihood(thetas: np.ndarray, obs_wp, obs_vals, lambda_
     return np.sum(poisson.logpmf(counts[None, :], rate), axis=1)
 
 
+def stage_weights(ll: np.ndarray, gamma: float, n_samples: int) -> np.ndarray:
+    """calc_weights, estimation.py:97-109, from the particles' log-likelihoods."""
+    log_w = gamma * ll
+    w = np.exp(log_w - np.max(log_w))
+    w /= np.sum(w)
+    if np.any(np.isnan(w)):
+        print("Warning: NaN weights encountered. Returning uniform weights.")
+        w = np.full(n_samples, 1 / n_samples)
+    return w
+
+
+def choice_from_draws(w: np.ndarray, u: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """The index computation of RandomState.choice(n, size, p=w) given its uniform draws: cdf = cumsum(p) / cdf[-1],
+    searchsorted(side='right') (numpy/random/mtrand.pyx, legacy choice with replacement)."""
+    cdf = np.cumsum(w)
+    cdf /= cdf[-1]
+    return cdf, cdf.searchsorted(u, side="right").astype(np.int64)
+
+
+def draws_inside_band(cdf: np.ndarray, u: np.ndarray, idx: np.ndarray, band: float) -> bool:
+    """True when some draw lies within `band` of a CDF step it could cross (the steps are cdf[0 .. N-2]; the last
+    entry is exactly 1 on both sides and u < 1)."""
+    n = cdf.shape[0]
+    below = np.where(idx > 0, cdf[np.maximum(idx - 1, 0)], -np.inf)        # the step at or below u
+    above = np.where(idx < n - 1, cdf[np.minimum(idx, n - 1)], np.inf)      # the next step above u
+    return bool(np.any(u - below <= band) or np.any(above - u <= band))
+
+
+def resample_indices(particles, gamma, n_samples, obs_wp, obs_vals, lambda_b, M, scorer, prepared) -> np.ndarray:
+    """np.random.choice(n_samples, size=n_samples, p=weights) of estimation.py:115 with the weights' log-likelihoods
+    from the device; consumes exactly the n_samples uniforms the reference's call consumes."""
+    STATS["stages"] += 1
+    ll, s1, s2 = scorer.particle_log_likelihood(particles, prepared, lambda_b, M)
+    exact = s1 is None                        # a host backend (tests) hands back the reference's own values
+    if not exact:
+        STATS["device_evaluations"] += 1
+    state = np.random.get_state()
+    u = np.random.random_sample(n_samples)
+    ok = exact or bool(np.all(np.isfinite(ll)) and np.all(np.isfinite(s1)) and np.all(np.isfinite(s2)))
+    if ok:
+        w = stage_weights(ll, gamma, n_samples)
+        cdf, idx = choice_from_draws(w, u)
+        if exact:
+            return idx
+        bound = EPS * (C_TERM * s1 + c_sum(len(obs_vals)) * s2)
+        shift = gamma * (bound + bound[int(np.argmax(ll))])
+        if np.all(shift < 1.0):
+            band = 2.0 * float(np.sum(w * np.expm1(shift))) + 8.0 * n_samples * EPS
+            if not draws_inside_band(cdf, u, idx, band):
+                return idx
+    # inside the band (or a non-finite likelihood): the reference's own expression and its own call, same draws
+    STATS["redecided"] += 1
+    np.random.set_state(state)
+    w = stage_weights(batched_poisson_log_likelihood(particles, obs_wp, obs_vals, lambda_b, M), gamma, n_samples)
+    return np.random.choice(n_samples, size=n_samples, p=w)
+
+
 def importance_sampling_with_progressive_correction(obs_wp, obs_vals, lambda_b: float, M: int, n_samples: int, s_stages: int,
-                                                    prior_dist: List, scenario, alpha: float = 0.001
-                                                    ) -> Tuple[np.ndarray, np.ndarray]:
+                                                    prior_dist: List, scenario, alpha: float = 0.001, scorer=None,
+                                                    prepared=None) -> Tuple[np.ndarray, np.ndarray]:
     """estimation.py:57-130; RNG order per stage: np.random.choice, then multivariate_normal.rvs."""
+    scorer = _default_scorer() if scorer is None else scorer
+    prepared = scorer.prepare_counts(obs_wp, obs_vals) if prepared is None else prepared
     gammas = np.linspace(0.1, 1.0, s_stages)
     particles = np.column_stack([d.rvs(n_samples) for d in prior_dist])
     ws, ir = scenario.workspace_size, scenario.intensity_range
     for gamma in gammas:
-        log_w = gamma * batched_poisson_log_likelihood(particles, obs_wp, obs_vals, lambda_b, M)
-        w = np.exp(log_w - np.max(log_w))
-        w /= np.sum(w)
-        if np.any(np.isnan(w)):
-            print("Warning: NaN weights encountered. Returning uniform weights.")
-            w = np.full(n_samples, 1 / n_samples)
-        picked = particles[np.random.choice(n_samples, size=n_samples, p=w)]
+        picked = particles[resample_indices(particles, gamma, n_samples, obs_wp, obs_vals, lambda_b, M, scorer, prepared)]
         mean = np.mean(picked, axis=0)
         cov = np.cov(picked, rowvar=False)
         moved = multivariate_normal.rvs(mean=mean, cov=cov * alpha, size=n_samples)
@@ -61,16 +140,30 @@ def calculate_bic(log_likelihood: float, num_params: int, num_data_points: int) 
     return 2 * log_likelihood + num_params * np.log(num_data_points)
 
 
-def estimate_sources_bayesian(obs_wp, obs_vals, lambda_b: float, max_sources: int, n_samples: int, s_stages: int, scenario
-                              ) -> Tuple[np.ndarray, int, float]:
+_SCORER = None
+
+
+def _default_scorer():
+    """The device scorer (raises without CUDA or without libipp_b200.so: there is no CPU route through here)."""
+    global _SCORER
+    if _SCORER is None:
+        from mripp_b200.scoring import GpuScorer
+        _SCORER = GpuScorer()
+    return _SCORER
+
+
+def estimate_sources_bayesian(obs_wp, obs_vals, lambda_b: float, max_sources: int, n_samples: int, s_stages: int, scenario,
+                              scorer=None) -> Tuple[np.ndarray, int, float]:
     """estimation.py:138-189: model selection over M = 1..max_sources by BIC."""
+    scorer = _default_scorer() if scorer is None else scorer
+    prepared = scorer.prepare_counts(obs_wp, obs_vals)
     ws, ir = scenario.workspace_size, scenario.intensity_range
     best = (None, 0, -np.inf)
     for M in range(1, max_sources + 1):
         # scipy's uniform(loc, scale): the reference passes the upper bounds as `scale` (estimation.py:171-173)
         priors = [uniform(loc=ws[0], scale=ws[1]), uniform(loc=ws[2], scale=ws[3]), uniform(loc=ir[0], scale=ir[1])] * M
         est, _ = importance_sampling_with_progressive_correction(obs_wp, obs_vals, lambda_b, M, n_samples, s_stages, priors,
-                                                                 scenario)
+                                                                 scenario, scorer=scorer, prepared=prepared)
         bic = calculate_bic(poisson_log_likelihood(est, obs_wp, obs_vals, lambda_b, M), 3 * M, len(obs_vals))
         if bic > best[2]:
             best = (est, M, bic)

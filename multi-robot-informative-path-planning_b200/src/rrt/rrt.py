@@ -202,7 +202,7 @@ def gp_information_update(self) -> None:
         self.scenario.update(self.obs_wp, np.log10(np.maximum(self.measurements, 1e-6)))
         if hasattr(self, "best_estimates") and self.best_estimates.size > 0:
             estimates, _, bic = estimate_sources_bayesian(self.obs_wp, self.measurements, self.lambda_b, self.max_sources,
-                                                          self.n_samples, self.s_stages, self.scenario)
+                                                          self.n_samples, self.s_stages, self.scenario, scorer=self.scorer)
             if bic > self.best_bic:
                 self.best_bic = bic
                 self.best_estimates = estimates.reshape((-1, 3))
@@ -216,7 +216,7 @@ def source_metric_information_update(self) -> None:
         self.obs_wp = self.obs_wp[:k]
         self.scenario.update(self.obs_wp, np.log10(np.maximum(self.measurements, 1e-6)))
         estimates, _, bic = estimate_sources_bayesian(self.obs_wp, self.measurements, self.lambda_b, self.max_sources,
-                                                      self.n_samples, self.s_stages, self.scenario)
+                                                      self.n_samples, self.s_stages, self.scenario, scorer=self.scorer)
         self.best_bic = bic
         self.best_estimates = estimates.reshape((-1, 3))
 

@@ -81,6 +81,14 @@ class OracleScorer:
                 nodes[q].parent = nodes[p]
         return info
 
+    def prepare_counts(self, obs_wp, obs_vals):
+        return {"obs_wp": obs_wp, "obs_vals": obs_vals}
+
+    def particle_log_likelihood(self, thetas, prepared, lambda_b, M):
+        """The reference's own values (S1 = S2 = None tells the sampler there is no band to check)."""
+        from mripp_b200.src.estimation.estimation import batched_poisson_log_likelihood
+        return batched_poisson_log_likelihood(thetas, prepared["obs_wp"], prepared["obs_vals"], lambda_b, M), None, None
+
     def leaf_scores(self, leaf_xy, parent_xy, has_parent, ctx, beta, kernel_c, kernel_l):
         nodes = []
         for k in range(len(leaf_xy)):
@@ -96,3 +104,28 @@ class OracleScorer:
         _, acq = T.ucb_select(nodes, lambda P: gp.predict(P, return_std=True), list(visited_xy), beta, d_wp, None)
         _, sd = gp.predict(leaf_xy, return_std=True)
         return acq, float(np.mean(sd))
+
+
+class NoisyLikelihoodScorer(OracleScorer):
+    """Stands in for the device likelihood on a CPU box: the reference's log-likelihoods plus a seeded error of up
+    to `scale` times the bound a real device evaluation reports, with S1 / S2 inflated by the same factor -- i.e. a
+    backend that is as wrong as it is allowed to be.  Lets the error-band logic of the sampler run without a GPU."""
+
+    def __init__(self, scale=1.0, seed=0):
+        super().__init__()
+        self.scale, self.rng = float(scale), np.random.RandomState(seed)
+
+    def particle_log_likelihood(self, thetas, prepared, lambda_b, M):
+        from scipy.special import gammaln
+        from mripp_b200.src.estimation import estimation as E
+        ll, _, _ = super().particle_log_likelihood(thetas, prepared, lambda_b, M)
+        obs = np.array(prepared["obs_wp"], dtype=float).reshape(-1, 2)
+        k = np.round(prepared["obs_vals"]).astype(int)
+        src = np.asarray(thetas, float).reshape(len(thetas), M, 3)
+        d2 = (obs[None, :, None, 0] - src[:, None, :, 0]) ** 2 + (obs[None, :, None, 1] - src[:, None, :, 1]) ** 2
+        rate = np.maximum(lambda_b + np.sum(src[:, None, :, 2] / np.maximum(d2, 1e-6), axis=2), 1e-10)
+        kl, g = k[None, :] * np.log(rate), gammaln(k + 1)[None, :]
+        s1 = (np.abs(kl) + g + rate).sum(axis=1) * self.scale
+        s2 = np.abs(kl - g - rate).sum(axis=1) * self.scale
+        bound = E.EPS * (E.C_TERM * s1 + E.c_sum(len(k)) * s2)
+        return ll + self.rng.uniform(-1.0, 1.0, len(ll)) * bound, s1, s2

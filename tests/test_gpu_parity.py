@@ -608,6 +608,8 @@ def test_run_waypoints_identical_on_device(gold, tag, cls_name, extra):
     for i, p in enumerate(st.agents_full_path):
         assert np.array_equal(np.array(p, float).reshape(-1, 2), g[f"{tag}_path{i}"])
     assert np.array_equal(np.random.uniform(size=3), g[f"{tag}_rng_after"])
+    if f"{tag}_best_estimates" in g.files:  # the source estimates of the device-likelihood sampler: the reference's bits
+        assert np.array_equal(np.asarray(st.best_estimates, float).reshape(-1, 3), g[f"{tag}_best_estimates"])
     assert Z.shape == (200, 200) and std.shape == (40000,)
     # T2 (re-optimised): the LML surface is flat and its gradient is noise limited, so L-BFGS-B may stop
     # at a different but equally good theta (permuting the data moves theta* by 6 %).
@@ -728,3 +730,107 @@ def test_abi_rejects_bad_arguments_on_device(torch):
     assert lib.ipp_gram_rbf(_lib.ptr(x), 4, None, 0, 1.0, -1.0, 0.0, _lib.ptr(x), 4, None) == -1
     assert lib.ipp_branch_gain(7, None, 0, None, None, None, None, None, None, None, 0, 0, None, 0, None, None, 0, None,
                                None, None) == -1
+
+
+# ---- particle log-likelihoods of the importance sampler -----------------------------------
+def _likelihood_case(n, N, M, W, seed):
+    rng = np.random.RandomState(seed)
+    obs = rng.uniform(0, W, (n, 2))
+    truth = np.column_stack([rng.uniform(0, W, M), rng.uniform(0, W, M), rng.uniform(1e5, 1e6, M)])
+    d2 = ((obs[:, None, :] - truth[None, :, :2]) ** 2).sum(-1)
+    meas = 1.0 + (truth[None, :, 2] / np.maximum(d2, 1e-6)).sum(1)
+    meas = meas * (1 + 1e-3 * rng.randn(n))
+    thetas = np.column_stack([c for _ in range(M) for c in (rng.uniform(0, W, N), rng.uniform(0, W, N), rng.uniform(1e5, 1e6, N))])
+    return obs, meas, thetas
+
+
+@pytest.mark.parametrize("n,N,M", [(1, 7, 1), (25, 80, 2), (257, 200, 3), (2000, 200, 3), (5000, 333, 2), (300, 50, 8),
+                                   (300, 50, 9), (64, 20, 17)])
+def test_particle_log_likelihood_within_its_bound(n, N, M):
+    """ipp_poisson_loglik against the reference's expression (estimation.py:15-55 through scipy's logpmf): the
+    difference stays inside a quarter of the bound the sampler derives from the returned sums, including a particle
+    sitting on an observation (the 1e-6 clamp), zero counts and near-truth particles (tiny terms, large pieces)."""
+    from mripp_b200.scoring import GpuScorer
+    from mripp_b200.src.estimation import estimation as E
+
+    obs, meas, thetas = _likelihood_case(n, N, M, 40.0, 100 * n + M)
+    thetas[0, 0:2] = obs[0]                       # d2 = 0 -> clamp
+    meas[n // 2] = 0.2                            # count 0
+    if N > 2:
+        thetas[1] = thetas[2]                     # identical particles -> identical values
+    sc = GpuScorer()
+    prep = sc.prepare_counts(list(obs), list(meas))
+    ll, s1, s2 = sc.particle_log_likelihood(thetas, prep, 1, M)
+    want = E.batched_poisson_log_likelihood(thetas, list(obs), list(meas), 1, M)
+    bound = E.EPS * (E.C_TERM * s1 + E.c_sum(n) * s2)
+    assert np.all(np.isfinite(ll)) and np.all(bound > 0)
+    assert np.all(np.abs(ll - want) <= 0.25 * bound), float(np.max(np.abs(ll - want) / bound))
+    assert np.all(bound <= 1e-12 * s1 + 1e-300)   # the band stays narrow: about 1e4 eps of the pieces' magnitude
+    if N > 2:
+        assert ll[1] == ll[2]
+
+
+def test_particle_rate_is_bit_identical_to_numpy():
+    """With one observation of count 0 the log-likelihood is exactly -rate: the kernel's rate (subtractions, squares,
+    clamp, division, numpy's source-axis summation order for M < 8 and M >= 8) carries numpy's bits."""
+    from mripp_b200.scoring import GpuScorer
+
+    sc = GpuScorer()
+    rng = np.random.RandomState(3)
+    for M in (1, 2, 3, 7, 8, 9, 15, 16, 23, 32):
+        obs = rng.uniform(0, 30, (1, 2))
+        thetas = rng.uniform(0, 30, (400, 3 * M))
+        thetas[:, 2::3] = rng.uniform(1e5, 1e6, (400, M))
+        thetas[5, 0:2] = obs[0]
+        prep = sc.prepare_counts(list(obs), [0.3])
+        ll, _, _ = sc.particle_log_likelihood(thetas, prep, 1, M)
+        src = thetas.reshape(400, M, 3)
+        d2 = (obs[None, :, None, 0] - src[:, None, :, 0]) ** 2 + (obs[None, :, None, 1] - src[:, None, :, 1]) ** 2
+        rate = np.maximum(1 + np.sum(src[:, None, :, 2] / np.maximum(d2, 1e-6), axis=2), 1e-10)[:, 0]
+        assert np.array_equal(ll, -rate), M
+
+
+def test_resampled_indices_are_the_references():
+    """Stage by stage: np.random.choice on the reference's weights vs the device-likelihood sampler from the same RNG
+    state -- same indices, same RNG position -- over spread (few observations) and peaked (many) posteriors."""
+    from mripp_b200.scoring import GpuScorer
+    from mripp_b200.src.estimation import estimation as E
+
+    sc = GpuScorer()
+    before = dict(E.STATS)
+    stages = 0
+    for case, (n, N, M) in enumerate([(3, 200, 1), (5, 200, 2), (10, 300, 3), (40, 200, 3), (400, 200, 2), (2000, 200, 3)]):
+        obs, meas, thetas = _likelihood_case(n, N, M, 40.0, 7 + case)
+        prep = sc.prepare_counts(list(obs), list(meas))
+        rng = np.random.RandomState(case)
+        for rep in range(12):
+            P = thetas if rep == 0 else thetas[rng.randint(N)] * (1 + 1e-3 * rng.randn(N, 3 * M))   # spread / clustered cloud
+            for gamma in (0.1, 0.5, 1.0):
+                np.random.seed(1000 * case + rep)
+                w = E.stage_weights(E.batched_poisson_log_likelihood(P, list(obs), list(meas), 1, M), gamma, N)
+                want = np.random.choice(N, size=N, p=w)
+                after = np.random.uniform(size=2)
+                np.random.seed(1000 * case + rep)
+                got = E.resample_indices(P, gamma, N, list(obs), list(meas), 1, M, sc, prep)
+                assert np.array_equal(want, got) and np.array_equal(after, np.random.uniform(size=2))
+                stages += 1
+    redone = E.STATS["redecided"] - before["redecided"]
+    assert E.STATS["device_evaluations"] - before["device_evaluations"] == stages
+    assert redone <= 0.05 * stages, (redone, stages)   # the band is hit rarely; when it is, the stage is re-decided
+
+
+def test_source_estimator_on_device_matches_reference(gold):
+    """estimate_sources_bayesian with the device likelihood: estimate, model order, BIC and the RNG position after
+    are the reference's own (golden from the unmodified reference, oracle/make_golden.py gold_field)."""
+    from mripp_b200.src.estimation import estimation as E
+    from mripp_b200.src.point_source.point_source import PointSourceField
+
+    g = gold("field_golden.npz")
+    sc = PointSourceField(num_sources=2, workspace_size=(0, 20, 0, 20), seed=21)
+    before = dict(E.STATS)
+    np.random.seed(13)
+    est, M, bic = E.estimate_sources_bayesian(list(g["est_wp"]), list(g["est_meas"]), 1, 2, 80, 5, sc)
+    assert M == int(g["est_M"]) and bic == float(g["est_bic"])
+    assert np.array_equal(est, g["est_theta"])
+    assert np.array_equal(np.random.uniform(size=3), g["est_rng_after"])
+    assert E.STATS["device_evaluations"] - before["device_evaluations"] == 10

@@ -158,10 +158,61 @@ def test_source_estimator_bit_exact(gold):
     ll = E.batched_poisson_log_likelihood(g["ll_thetas"], g["est_wp"], g["est_meas"], 1, 2)
     assert np.array_equal(ll, g["ll_values"])
     np.random.seed(13)
-    est, M, bic = E.estimate_sources_bayesian(list(g["est_wp"]), list(g["est_meas"]), 1, 2, 80, 5, sc)
+    est, M, bic = E.estimate_sources_bayesian(list(g["est_wp"]), list(g["est_meas"]), 1, 2, 80, 5, sc, scorer=OracleScorer())
     assert M == int(g["est_M"]) and bic == float(g["est_bic"])
     assert np.array_equal(est, g["est_theta"])
     assert np.array_equal(np.random.uniform(size=3), g["est_rng_after"])
+
+
+def test_choice_from_draws_is_numpy_choice():
+    """The sampler draws the uniforms itself and replays RandomState.choice's index computation: same indices, same
+    RNG position, for spread, peaked, zero-holding and uniform weights."""
+    rng = np.random.RandomState(5)
+    for case in range(40):
+        n = int(rng.choice([1, 2, 7, 80, 200, 1000]))
+        w = rng.rand(n) ** rng.choice([1, 8, 40])
+        if case % 3 == 0:
+            w[rng.rand(n) < 0.5] = 0.0
+            w[rng.randint(n)] = 1.0
+        if case % 7 == 0:
+            w = np.full(n, 1 / n)
+        w = w / w.sum()
+        np.random.seed(case)
+        want = np.random.choice(n, size=n, p=w)
+        after = np.random.uniform(size=2)
+        np.random.seed(case)
+        _, got = E.choice_from_draws(w, np.random.random_sample(n))
+        assert np.array_equal(want, got) and np.array_equal(after, np.random.uniform(size=2))
+
+
+@pytest.mark.parametrize("scale", [1.0, 1e4, 1e7])
+def test_source_estimator_exact_under_likelihood_error(gold, scale):
+    """A likelihood backend that is off by as much as its reported bound allows (and far more than a device is) must
+    not change one resampled index: estimate, BIC and RNG position stay the reference's; wide bands are re-decided."""
+    from tests._doubles import NoisyLikelihoodScorer
+    g = gold("field_golden.npz")
+    sc = PointSourceField(num_sources=2, workspace_size=(0, 20, 0, 20), seed=21, gp_factory=FastGP)
+    before = dict(E.STATS)
+    np.random.seed(13)
+    est, M, bic = E.estimate_sources_bayesian(list(g["est_wp"]), list(g["est_meas"]), 1, 2, 80, 5, sc,
+                                              scorer=NoisyLikelihoodScorer(scale, seed=3))
+    assert M == int(g["est_M"]) and bic == float(g["est_bic"])
+    assert np.array_equal(est, g["est_theta"])
+    assert np.array_equal(np.random.uniform(size=3), g["est_rng_after"])
+    stages = E.STATS["stages"] - before["stages"]
+    redone = E.STATS["redecided"] - before["redecided"]
+    assert stages == 10 and (redone == 0 if scale == 1.0 else True) and (redone > 0 if scale == 1e7 else True)
+
+
+def test_draws_inside_band():
+    cdf = np.array([0.0, 0.25, 0.25, 0.7, 1.0])
+    u = np.array([0.1, 0.5, 0.9])
+    idx = cdf.searchsorted(u, side="right")
+    assert not E.draws_inside_band(cdf, u, idx, 1e-3)
+    assert E.draws_inside_band(cdf, np.array([0.2501]), cdf.searchsorted([0.2501], side="right"), 1e-3)
+    assert E.draws_inside_band(cdf, np.array([0.6995]), cdf.searchsorted([0.6995], side="right"), 1e-3)
+    assert E.draws_inside_band(cdf, np.array([1e-9]), cdf.searchsorted([1e-9], side="right"), 1e-3)   # the step at 0
+    assert not E.draws_inside_band(cdf, np.array([0.9999999]), cdf.searchsorted([0.9999999], side="right"), 1e-3)  # cdf[-1] is exact
 
 
 def test_score_context_helpers():
