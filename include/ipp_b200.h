@@ -169,6 +169,25 @@ int ipp_grid_metrics(const double* zpred, const double* std, const double* ztrue
 int ipp_poisson_loglik(const double* particles, int N, int M, const double* obs_xy, const double* counts,
                        const double* lgam, int n, double lambda_b, double* out, void* stream);
 
+/* ---- host-side entry points (no device work, no stream): SURVEY.md section 8f row 4 -----------------
+ * np.linalg.norm of m 2-vectors in the rounding form `variant` (0: sqrt(x*x + y*y), 1: sqrt(fma(y, y, x*x)),
+ * 2: sqrt(fma(x, x, y*y))).  Used once, to find the form that equals np.linalg.norm with the BLAS numpy links. */
+int ipp_host_norm2(int variant, const double* xy, int m, double* out);
+
+/* Grow one agent's tree in place on the structure-of-arrays tree (xy[capacity][2], parent0 = parent at insertion,
+ * parent = current parent, edge = |point - current parent|, nchild) from K pre-drawn uniform pairs (np.random.rand(2)
+ * per sample) until the travelled length reaches budget_portion, the pairs run out, or capacity / rewire_cap is
+ * reached.  mode 0: rrt_tree_generation (rrt.py:263-277), 1: rrt_star_tree_generation (:279-304),
+ * 2: rig_tree_generation (:306-327); primitives nearest / steer / near / cost / rewire / add_node of
+ * src/rrt/rrt_utils.py:59-105 with their first-minimum and strict-inequality semantics.  ws4 = {x0, x1, y0, y1};
+ * step = steer's d_max_step, radius = near's distance.  rewires: rows {time = id of the inserted node, node,
+ * new parent} appended from *n_rewires_io; scratch: capacity ints.  Outputs: pairs consumed, node count,
+ * finished (1 when the budget portion is spent).  Host pointers. */
+int ipp_host_tree_grow(int mode, int norm_variant, double* xy, long long* parent0, long long* parent, double* edge,
+                       long long* nchild, int n, int capacity, const double* uniforms, int K, const double* ws4,
+                       double step, double radius, double budget_portion, double* travelled_io, long long* rewires,
+                       int rewire_cap, int* n_rewires_io, int* scratch, int* consumed, int* n_out, int* finished);
+
 #ifdef __cplusplus
 }
 #endif

@@ -133,6 +133,11 @@ def _sample(self) -> np.ndarray:
 def rrt_tree_generation(self, budget_portion: float, agent_idx: int) -> None:
     tree = self.trees_soa[agent_idx]
     travelled = 0
+    samples = tree.grow_native(0, self.scenario.workspace_size, self.d_waypoint_distance, 0.0, budget_portion)
+    if samples is not None:             # grown natively (csrc/ipp_tree_host.cu): same nodes, same RNG position
+        travelled = budget_portion
+        for _ in range(samples - 1):    # the reference's loop registers the root once per non-final iteration
+            self.agents_trees[agent_idx].add(self.agents_roots[agent_idx])
     while travelled < budget_portion:
         target = _sample(self)
         nn = tree.nearest(target)
@@ -149,6 +154,8 @@ def rrt_tree_generation(self, budget_portion: float, agent_idx: int) -> None:
 def rrt_star_tree_generation(self, budget_portion: float, agent_idx: int) -> None:
     tree = self.trees_soa[agent_idx]
     travelled = 0
+    if tree.grow_native(1, self.scenario.workspace_size, 1.0, self.d_waypoint_distance, budget_portion) is not None:
+        travelled = budget_portion
     while travelled < budget_portion:
         target = _sample(self)
         nn = tree.nearest(target)
@@ -171,6 +178,12 @@ def rrt_star_tree_generation(self, budget_portion: float, agent_idx: int) -> Non
 def rig_tree_generation(self, budget_portion: float, agent_idx: int, gain_function: Callable) -> None:
     tree = self.trees_soa[agent_idx]
     travelled = 0
+    samples = tree.grow_native(2, self.scenario.workspace_size, self.d_waypoint_distance, self.d_waypoint_distance,
+                               budget_portion)
+    if samples is not None:
+        travelled = budget_portion
+        for _ in range(samples - 1):
+            self.agents_trees[agent_idx].add(self.agents_roots[agent_idx])
     while travelled < budget_portion:
         target = _sample(self)
         nn = tree.nearest(target)

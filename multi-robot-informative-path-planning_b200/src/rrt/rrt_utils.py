@@ -137,6 +137,34 @@ def steer_point(origin: np.ndarray, target: np.ndarray, d_max_step: float) -> np
     return origin + direction * distance
 
 
+# ---- native tree growth (csrc/ipp_tree_host.cu) --------------------------------------------------------
+NATIVE_GROWTH = True          # False: always the Python loops of rrt.py (same results; the tests compare the two)
+_NATIVE = {"checked": False, "variant": None, "lib": None}
+
+
+def native_norm_variant() -> Optional[int]:
+    """Which rounding form of ipp_host_norm2 equals np.linalg.norm on this machine (numpy's norm of a 1-D vector is
+    sqrt(x.dot(x)); whether that dot fuses its second multiply-add depends on the BLAS numpy links).  Calibrated
+    once against np.linalg.norm itself on 4096 seeded vectors; None when no form reproduces all of them, in which
+    case the growth stays on the Python loops."""
+    if _NATIVE["checked"]:
+        return _NATIVE["variant"]
+    from mripp_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.RandomState(20240711)
+    xy = np.ascontiguousarray(rng.standard_normal((4096, 2)) * 10.0 ** rng.uniform(-3, 3, (4096, 1)))
+    xy[:64] = rng.uniform(0, 100, (64, 2)) - rng.uniform(0, 100, (64, 2))     # the coordinate differences of a run
+    want = np.array([np.linalg.norm(v) for v in xy])
+    out = np.empty(len(xy))
+    match = []
+    for variant in range(3):
+        _lib.check(lib.ipp_host_norm2(variant, xy.ctypes.data, len(xy), out.ctypes.data), "ipp_host_norm2")
+        if np.array_equal(out, want):
+            match.append(variant)
+    _NATIVE.update(checked=True, variant=match[0] if match else None, lib=lib)
+    return _NATIVE["variant"]
+
+
 # ---- structure-of-arrays tree ------------------------------------------------------------------------
 class TreeArrays:
     """One agent's tree as flat arrays; node id = insertion order (index into tree_nodes[agent])."""
@@ -180,6 +208,53 @@ class TreeArrays:
             self.edge[i] = _norm(point - self._pt[parent])
         self.n += 1
         return i
+
+    def grow_native(self, mode: int, workspace, step: float, radius: float, budget_portion: float, block: int = 256
+                    ) -> Optional[int]:
+        """One call of rrt / rrt_star / rig tree generation (mode 0 / 1 / 2; rrt.py:263-327) through
+        ipp_host_tree_grow: samples come from blocks of pre-drawn uniforms -- random_sample(2k) is the stream of k
+        calls of np.random.rand(2) -- and the global RNG is left exactly where the reference's loop leaves it.
+        Returns the number of samples drawn (= loop iterations of the reference), or None (nothing done) when the
+        native norm could not be calibrated or NATIVE_GROWTH is off."""
+        import ctypes as C
+        variant = native_norm_variant() if NATIVE_GROWTH else None
+        if variant is None:
+            return None
+        lib = _NATIVE["lib"]
+        samples = 0
+        ws4 = np.array([workspace[0], workspace[1], workspace[2], workspace[3]], dtype=np.float64)
+        travelled = C.c_double(0.0)
+        consumed, n_out, finished, n_rw = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
+        while True:
+            while self._xy.shape[0] < self.n + block:
+                self._grow()
+            cap_rw = 4 * (self.n + block) + 1024
+            rewires = np.empty((cap_rw, 3), dtype=np.int64)
+            scratch = np.empty(self._xy.shape[0], dtype=np.int32)
+            state = np.random.get_state()
+            u = np.random.random_sample(2 * block)
+            n_rw.value = 0
+            rc = lib.ipp_host_tree_grow(mode, variant, self._xy.ctypes.data, self.parent0.ctypes.data, self.parent.ctypes.data,
+                                        self.edge.ctypes.data, self.nchild.ctypes.data, self.n, self._xy.shape[0],
+                                        u.ctypes.data, block, ws4.ctypes.data, float(step), float(radius),
+                                        float(budget_portion), C.addressof(travelled), rewires.ctypes.data, cap_rw,
+                                        C.addressof(n_rw), scratch.ctypes.data, C.addressof(consumed), C.addressof(n_out),
+                                        C.addressof(finished))
+            if rc != 0:
+                raise RuntimeError(f"ipp_host_tree_grow failed with status {rc}")
+            samples += consumed.value
+            if consumed.value < block:                      # leave the RNG where consumed.value calls of rand(2) leave it
+                np.random.set_state(state)
+                if consumed.value:
+                    np.random.random_sample(2 * consumed.value)
+            for i in range(self.n, n_out.value):
+                self._pt.append(self._xy[i].copy())
+            self.info[self.n: n_out.value] = 0.0
+            self.n = n_out.value
+            if n_rw.value:
+                self.rewires.extend(map(tuple, rewires[: n_rw.value].tolist()))
+            if finished.value:
+                return samples
 
     def points(self) -> np.ndarray:
         return self._xy[: self.n]

@@ -9,6 +9,7 @@ from mripp_b200.src.boustrophedon.boustrophedon import Boustrophedon, MR_Boustro
 from mripp_b200.src.estimation import estimation as E
 from mripp_b200.src.point_source.point_source import PointSourceField
 from mripp_b200.src.rrt import rrt as R
+from mripp_b200.src.rrt import rrt_utils as U
 from mripp_b200.src.rrt.rrt_utils import TreeArrays
 from tests._doubles import OracleGP, OracleScorer
 
@@ -221,3 +222,54 @@ def test_score_context_helpers():
     assert ctx.closest_estimate_index() == 1
     assert ctx.all_obs().shape == (1, 2) and not ctx.agent_has_obs()
     assert ctx.obstacle_rows().tolist() == [[1.0, 2.0, 3.0, 4.0]]
+
+
+# ---- native tree growth (csrc/ipp_tree_host.cu) vs the Python loops -----------------------
+def test_native_norm_is_numpy_norm():
+    """The calibrated rounding form of ipp_host_norm2 reproduces np.linalg.norm on fresh vectors."""
+    from mripp_b200 import _lib
+    variant = U.native_norm_variant()
+    assert variant in (0, 1, 2), "no rounding form of the native norm matches np.linalg.norm on this machine"
+    rng = np.random.RandomState(99)
+    xy = np.ascontiguousarray(rng.uniform(-50, 50, (20000, 2)) * 10.0 ** rng.uniform(-2, 2, (20000, 1)))
+    out = np.empty(len(xy))
+    assert _lib.load().ipp_host_norm2(variant, xy.ctypes.data, len(xy), out.ctypes.data) == 0
+    assert np.array_equal(out, np.array([np.linalg.norm(v) for v in xy]))
+
+
+@pytest.mark.parametrize("gen,budgets,d", [("rig", [120, 37.5, 300], 2.5), ("rig", [2000], 1.0), ("rrt", [120, 60], 2.5),
+                                           ("rrt_star", [80, 80, 40], 2.5), ("rig", [0, 5], 2.5)])
+def test_native_growth_equals_python_loops(monkeypatch, gen, budgets, d):
+    """Same seeded calls through both routes: coordinates, insertion-time and current parents, edge lengths, child
+    counts, the rewire log, node information, the per-iteration root registrations and the RNG position are
+    identical; successive calls keep growing the same tree (several blocks of pre-drawn samples at budget 2000)."""
+    res = []
+    for native in (False, True):
+        monkeypatch.setattr(U, "NATIVE_GROWTH", native)
+        sc, make = _strategy(R.MR_IPP, 40, 5, budget=120, d_waypoint_distance=d, num_agents=2, budget_iter=4)
+        np.random.seed(77)
+        st = make()
+        st.best_estimates = np.array([[10.0, 30.0, 5e5], [28.0, 12.0, 7e5]])
+        start = np.array([3.0, 4.0])
+        st.agents_obs_wp = [[start.copy()], [np.array([30.0, 5.0])]]
+        st.agents_full_path = [[start.copy()], [np.array([30.0, 5.0])]]
+        st.initialize_trees(start, 0)
+        for b in budgets:
+            if gen == "rig":
+                R.rig_tree_generation(st, b, 0, gain_function=R.point_source_gain_all)
+            elif gen == "rrt":
+                R.rrt_tree_generation(st, b, 0)
+            else:
+                R.rrt_star_tree_generation(st, b, 0)
+        t = st.trees_soa[0]
+        res.append((t.points().copy(), t.parent0[: t.n].copy(), t.parent[: t.n].copy(), t.edge[: t.n].copy(),
+                    t.nchild[: t.n].copy(), list(t.rewires), t.info[: t.n].copy(), len(st.agents_trees[0].trees),
+                    np.random.uniform(size=3), [p.copy() for p in t._pt]))
+    a, b = res
+    assert len(a[0]) == len(b[0]) and len(a[0]) > (1 if budgets != [0, 5] else 0)
+    for x, y in zip(a[:5], b[:5]):
+        assert np.array_equal(x, y)
+    assert a[5] == b[5] and np.array_equal(a[6], b[6]) and a[7] == b[7] and np.array_equal(a[8], b[8])
+    assert all(np.array_equal(p, q) for p, q in zip(a[9], b[9]))
+    if gen != "rrt" and budgets[0] >= 80:
+        assert len(a[5]) > 0  # the case exercises rewires
