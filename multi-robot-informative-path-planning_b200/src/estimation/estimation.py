@@ -159,9 +159,12 @@ def estimate_sources_bayesian(obs_wp, obs_vals, lambda_b: float, max_sources: in
     prepared = scorer.prepare_counts(obs_wp, obs_vals)
     ws, ir = scenario.workspace_size, scenario.intensity_range
     best = (None, 0, -np.inf)
+    # scipy's uniform(loc, scale): the reference passes the upper bounds as `scale` (estimation.py:171-173).  The
+    # frozen distributions hold no state of their own (they draw from the global RNG), so the three the reference
+    # rebuilds for every M are built once.
+    prior3 = [uniform(loc=ws[0], scale=ws[1]), uniform(loc=ws[2], scale=ws[3]), uniform(loc=ir[0], scale=ir[1])]
     for M in range(1, max_sources + 1):
-        # scipy's uniform(loc, scale): the reference passes the upper bounds as `scale` (estimation.py:171-173)
-        priors = [uniform(loc=ws[0], scale=ws[1]), uniform(loc=ws[2], scale=ws[3]), uniform(loc=ir[0], scale=ir[1])] * M
+        priors = prior3 * M
         est, _ = importance_sampling_with_progressive_correction(obs_wp, obs_vals, lambda_b, M, n_samples, s_stages, priors,
                                                                  scenario, scorer=scorer, prepared=prepared)
         bic = calculate_bic(poisson_log_likelihood(est, obs_wp, obs_vals, lambda_b, M), 3 * M, len(obs_vals))
