@@ -216,11 +216,16 @@ class TreeArrays:
         calls of np.random.rand(2) -- and the global RNG is left exactly where the reference's loop leaves it.
         Returns the number of samples drawn (= loop iterations of the reference), or None (nothing done) when the
         native norm could not be calibrated or NATIVE_GROWTH is off."""
-        import ctypes as C
         variant = native_norm_variant() if NATIVE_GROWTH else None
         if variant is None:
             return None
+        from mripp_b200.exact import RNG_SECTION
         lib = _NATIVE["lib"]
+        with RNG_SECTION:
+            return self._grow_native_locked(lib, mode, variant, workspace, step, radius, budget_portion, block)
+
+    def _grow_native_locked(self, lib, mode, variant, workspace, step, radius, budget_portion, block) -> int:
+        import ctypes as C
         samples = 0
         ws4 = np.array([workspace[0], workspace[1], workspace[2], workspace[3]], dtype=np.float64)
         travelled = C.c_double(0.0)
