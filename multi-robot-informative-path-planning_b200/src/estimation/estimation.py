@@ -101,6 +101,12 @@ def _resample_indices(particles, gamma, n_samples, obs_wp, obs_vals, lambda_b, M
         STATS["device_evaluations"] += 1
     state = np.random.get_state()
     u = np.random.random_sample(n_samples)
+    if not exact and bool(np.all(particles == particles[0])):
+        # A collapsed cloud (one particle repeated -- the usual state after the first stages once the likelihood is
+        # peaked: all draws pick the same row and the perturbation covariance is zero).  Equal rows get equal
+        # log-likelihoods from the reference's element-wise expression, so its weights are exactly uniform
+        # (or NaN -> replaced by uniform, estimation.py:106-108): no band to check.
+        return choice_from_draws(stage_weights(np.zeros(n_samples), gamma, n_samples), u)[1]
     ok = exact or bool(np.all(np.isfinite(ll)) and np.all(np.isfinite(s1)) and np.all(np.isfinite(s2)))
     if ok:
         w = stage_weights(ll, gamma, n_samples)

@@ -805,6 +805,8 @@ def test_resampled_indices_are_the_references():
         rng = np.random.RandomState(case)
         for rep in range(12):
             P = thetas if rep == 0 else thetas[rng.randint(N)] * (1 + 1e-3 * rng.randn(N, 3 * M))   # spread / clustered cloud
+            if rep == 1:
+                P = np.tile(thetas[rng.randint(N)], (N, 1))                                          # collapsed cloud
             for gamma in (0.1, 0.5, 1.0):
                 np.random.seed(1000 * case + rep)
                 w = E.stage_weights(E.batched_poisson_log_likelihood(P, list(obs), list(meas), 1, M), gamma, N)
