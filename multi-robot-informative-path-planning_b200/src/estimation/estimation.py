@@ -114,9 +114,13 @@ def _resample_indices(particles, gamma, n_samples, obs_wp, obs_vals, lambda_b, M
         if exact:
             return idx
         bound = EPS * (C_TERM * s1 + c_sum(len(obs_vals)) * s2)
-        shift = gamma * (bound + bound[int(np.argmax(ll))])
-        if np.all(shift < 1.0):
-            band = 2.0 * float(np.sum(w * np.expm1(shift))) + 8.0 * n_samples * EPS
+        top = int(np.argmax(ll))
+        shift = gamma * (bound + bound[top])
+        # A particle whose weight stays below e^-700 of the largest even at the far end of its bound cannot move a CDF
+        # step by more than 1e-304: hopeless particles (huge residuals, hence huge S2 and a loose bound) do not count.
+        live = gamma * (ll - ll[top]) + shift >= -700.0
+        if np.all(shift[live] < 1.0):
+            band = 2.0 * float(np.sum(w[live] * np.expm1(shift[live]))) + 8.0 * n_samples * EPS
             if not draws_inside_band(cdf, u, idx, band):
                 return idx
     # inside the band (or a non-finite likelihood): the reference's own expression and its own call, same draws
