@@ -100,6 +100,31 @@ def sharded_grid_posterior(gp, ws, nx: int, ny: int, group=None, compute_slab: O
     return z.cpu().numpy(), s.cpu().numpy()
 
 
+def sharded_restarts(run_one: Callable[[List[int]], List[Tuple[np.ndarray, float]]], n_starts: int, dim: int, group=None,
+                     device="cpu") -> List[Tuple[np.ndarray, float]]:
+    """The optimiser restarts of one fit (sklearn _gpr.py:312-337) spread over the ranks: start i runs on rank
+    i mod P, then one all_gather of (theta*, f*) -- (dim + 1) doubles per start -- gives every rank the full list in
+    start order, so that np.argmin (first minimum wins) picks the same optimum everywhere.  Every rank must hold the
+    same data and the same start points (same RNG state at fit time).  `run_one(indices)` returns the optima of this
+    rank's starts, in the order given."""
+    import torch
+
+    dist = _dist()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    mine = rounds_for_rank(n_starts, world, rank)
+    local = run_one(mine) if mine else []
+    per = (n_starts + world - 1) // world
+    buf = torch.full((per, dim + 1), float("nan"), dtype=torch.float64)
+    for slot, (theta, fval) in enumerate(local):
+        buf[slot, :dim] = torch.as_tensor(np.asarray(theta, dtype=np.float64))
+        buf[slot, dim] = float(fval)
+    buf = buf.to(device)
+    parts = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(parts, buf, group=group)
+    parts = [p.cpu().numpy() for p in parts]
+    return [(parts[i % world][i // world, :dim].copy(), float(parts[i % world][i // world, dim])) for i in range(n_starts)]
+
+
 def combine_argmax(values: np.ndarray, indices: np.ndarray) -> int:
     """np.argmax over the concatenation, given each shard's (local best value, GLOBAL index):
     a NaN wins at the smallest index, otherwise the largest value at the smallest index.

@@ -301,6 +301,9 @@ class GaussianProcessRegressor:
         # optimiser restarts are independent once their start points are drawn: run them on this many streams
         # (None = automatic: 6 streams, 3 when the Cholesky alone fills the GPU; 1 = serial)
         self.restart_streams = None
+        # a torch.distributed group (or True for the default group): spread the restarts of one fit over its ranks
+        # (start i on rank i mod P, dist.sharded_restarts); every rank must call fit with the same data and RNG state
+        self.restart_group = None
         # block sparsity of the lattice posterior: entries of k* below skip_below * c are not computed (0: dense)
         self.skip_below = 1e-30
         self.cluster_order = "maximin"  # order of the spatial clusters in the sparse state (see clustered_order)
@@ -454,11 +457,21 @@ class GaussianProcessRegressor:
                 return -self._lml(theta, False)
 
             bounds = self._kernel_fitted.bounds
-            workers = self._restart_workers(len(self._starts))
-            if workers > 1:
-                optima = self._optimise_concurrently(self._starts, bounds, workers)
+
+            def optimise(starts):
+                workers = self._restart_workers(len(starts))
+                if workers > 1:
+                    return self._optimise_concurrently(starts, bounds, workers)
+                return [self._constrained_optimization(obj_func, t0, bounds) for t0 in starts]
+
+            group = getattr(self, "restart_group", None)
+            if group is not None and len(self._starts) > 1:
+                # start i on rank i mod P, one all_gather of (theta*, f*); every rank then factors at theta*
+                from . import dist as D
+                optima = D.sharded_restarts(lambda idx: optimise([self._starts[i] for i in idx]), len(self._starts),
+                                            len(self._starts[0]), group=None if group is True else group, device="cuda")
             else:
-                optima = [self._constrained_optimization(obj_func, t0, bounds) for t0 in self._starts]
+                optima = optimise(self._starts)
             lml_values = [o[1] for o in optima]
             self._kernel_fitted.theta = optima[int(np.argmin(lml_values))][0]
             self._lml_value = -np.min(lml_values)

@@ -19,6 +19,21 @@ def _free_port():
         return s.getsockname()[1]
 
 
+def _optimum(X, y, i):
+    """Restart i of a fit on the oracle's objective: L-BFGS-B from a seeded start (sklearn _gpr.py:312-333)."""
+    from scipy.optimize import minimize
+    yn, _, _ = O.normalise_y(y)
+    b = O.log_bounds()
+    t0 = np.zeros(2) if i == 0 else np.random.RandomState(100 + i).uniform(b[:, 0], b[:, 1])
+
+    def f(theta):
+        v, g = O.lml(theta, X, yn, True)
+        return -v, -g
+
+    res = minimize(f, t0, method="L-BFGS-B", jac=True, bounds=b)
+    return res.x, res.fun
+
+
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -41,7 +56,8 @@ def _worker(rank, world, port, q):
         clean = np.array([1.0, 5.0, 3.0, 5.0, 5.0, 0.0, 4.0])
         k_tie = D.sharded_argmax(torch.from_numpy(clean[lo:hi]), lo)
         path = D.broadcast_path(np.array([[1.0, 2.0], [3.0, 4.0]]) if rank == 1 else None, src=1)
-        q.put((rank, z, s, k_nan, k_tie, path, D.rounds_for_rank(7, world, rank)))
+        optima = D.sharded_restarts(lambda idx: [_optimum(X, y, i) for i in idx], 5, 2)
+        q.put((rank, z, s, k_nan, k_tie, path, D.rounds_for_rank(7, world, rank), optima))
     finally:
         dist.destroy_process_group()
 
@@ -63,7 +79,12 @@ def test_two_rank_sharding_matches_single_process():
     st = O.fit(X, y, 1.0, 1.5, optimize=False)
     _, _, r, _ = O.workspace_grid((0, 6, 0, 5))
     m, s, _ = O.predict(st, r)
-    for rank, z, sd, k_nan, k_tie, path, rounds in out:
+    serial = [_optimum(X, y, i) for i in range(5)]
+    for rank, z, sd, k_nan, k_tie, path, rounds, optima in out:
+        # restarts spread over the ranks: the gathered list is the serial list, in start order, on every rank
+        assert len(optima) == 5
+        assert all(np.array_equal(a[0], b[0]) and a[1] == b[1] for a, b in zip(optima, serial))
+        assert int(np.argmin([o[1] for o in optima])) == int(np.argmin([o[1] for o in serial]))
         assert np.array_equal(z, 10 ** m) and np.array_equal(sd, s)  # slabs are row independent: exact
         assert k_nan == 3 and k_tie == 1
         assert np.array_equal(path, [[1.0, 2.0], [3.0, 4.0]])

@@ -71,6 +71,27 @@ if rank == 0:
     print(f"dist_check strong scaling: one C4 lattice (10^6 points, n=5000) by row slab over {world} GPUs incl. all_gather of "
           f"Z and std: {float(tms):.1f} ms per posterior ({1e6 / float(tms) * 1e3:.3e} points/s); sharded argmax of 8192 "
           f"scores (all_gather of one pair per rank): {t_arg * 1e6:.0f} us", flush=True)
+# ---- one 11-restart fit with its restarts spread over the ranks ---------------------------------------
+for n_fit, W_fit in ((2000, 50), (5000, 100)):
+    Xf, measf, _ = synth_observations(n_fit, W_fit, 0)
+    res = {}
+    for mode in ("one GPU", "sharded"):
+        gpf = G.GaussianProcessRegressor(kernel=G.ConstantRBFKernel(1.0, 1.0), n_restarts_optimizer=10, normalize_y=True)
+        gpf.restart_group = True if mode == "sharded" else None
+        np.random.seed(5)
+        dist.barrier(); torch.cuda.synchronize(); t0 = time.perf_counter()
+        gpf.fit(Xf, np.log10(measf))
+        torch.cuda.synchronize(); dt = torch.tensor([time.perf_counter() - t0], device="cuda")
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        res[mode] = (float(dt), gpf.kernel_.theta.copy(), gpf.log_marginal_likelihood_value_, gpf.n_lml_evals_, np.random.uniform(size=2))
+    same = (np.array_equal(res["one GPU"][1], res["sharded"][1]) and res["one GPU"][2] == res["sharded"][2]
+            and np.array_equal(res["one GPU"][4], res["sharded"][4]))
+    ok = ok and same
+    ev = torch.tensor([float(res["sharded"][3])], device="cuda"); dist.all_reduce(ev, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(f"dist_check sharded restarts n={n_fit}: 11-restart fit on one GPU {res['one GPU'][0]:.3f} s ({res['one GPU'][3]} evaluations), "
+              f"restarts over {world} GPUs {res['sharded'][0]:.3f} s (at most {int(ev.item())} evaluations on a rank); "
+              f"theta*, LML and RNG position identical: {same}", flush=True)
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
