@@ -99,8 +99,7 @@ def _resample_indices(particles, gamma, n_samples, obs_wp, obs_vals, lambda_b, M
     exact = s1 is None                        # a host backend (tests) hands back the reference's own values
     if not exact:
         STATS["device_evaluations"] += 1
-    state = np.random.get_state()
-    u = np.random.random_sample(n_samples)
+    u = np.random.random_sample(n_samples)        # the draws RandomState.choice makes for this call, nothing else
     if not exact and bool(np.all(particles == particles[0])):
         # A collapsed cloud (one particle repeated -- the usual state after the first stages once the likelihood is
         # peaked: all draws pick the same row and the perturbation covariance is zero).  Equal rows get equal
@@ -123,11 +122,10 @@ def _resample_indices(particles, gamma, n_samples, obs_wp, obs_vals, lambda_b, M
             band = 2.0 * float(np.sum(w[live] * np.expm1(shift[live]))) + 8.0 * n_samples * EPS
             if not draws_inside_band(cdf, u, idx, band):
                 return idx
-    # inside the band (or a non-finite likelihood): the reference's own expression and its own call, same draws
+    # inside the band (or a non-finite likelihood): the reference's own expression for the weights, same draws
     STATS["redecided"] += 1
-    np.random.set_state(state)
     w = stage_weights(batched_poisson_log_likelihood(particles, obs_wp, obs_vals, lambda_b, M), gamma, n_samples)
-    return np.random.choice(n_samples, size=n_samples, p=w)
+    return choice_from_draws(w, u)[1]
 
 
 def importance_sampling_with_progressive_correction(obs_wp, obs_vals, lambda_b: float, M: int, n_samples: int, s_stages: int,

@@ -165,6 +165,56 @@ def native_norm_variant() -> Optional[int]:
     return _NATIVE["variant"]
 
 
+class _RngMark:
+    """Snapshot / restore of the global np.random stream around a block of look-ahead draws.  get_state/set_state
+    cost ~85 us each (they rebuild and validate the 624-word key); the MT19937 bit generator also exposes the address
+    of its raw state (BitGenerator.ctypes.state_address: uint32 key[624], int pos), which copies in under 1 us.  The
+    raw route is used only after it has reproduced a stream once on this numpy (self-test below); uniform draws do
+    not touch the legacy Gaussian cache, which lives outside that struct."""
+    _raw = None   # None: untested, False: use get_state / set_state, else the byte count
+
+    @classmethod
+    def _address(cls):
+        bg = np.random.mtrand._rand._bit_generator
+        return bg.ctypes.state_address if type(bg).__name__ == "MT19937" else None
+
+    @classmethod
+    def _selftest(cls):
+        import ctypes as C
+        try:
+            addr, size = cls._address(), 624 * 4 + 4
+            if addr is None:
+                return False
+            saved = np.random.get_state()
+            np.random.random_sample(700)                      # put pos somewhere inside the key
+            mark = C.string_at(addr, size)
+            a = np.random.random_sample(1500)                 # crosses a regeneration of the key
+            after = np.random.get_state()
+            C.memmove(addr, mark, size)
+            b = np.random.random_sample(1500)
+            now = np.random.get_state()
+            ok = bool(np.array_equal(a, b) and np.array_equal(after[1], now[1]) and after[2:] == now[2:])
+            np.random.set_state(saved)
+            return size if ok else False
+        except Exception:
+            return False
+
+    def __init__(self):
+        import ctypes as C
+        if _RngMark._raw is None:
+            _RngMark._raw = self._selftest()
+        addr = self._address() if _RngMark._raw else None
+        self._addr = addr
+        self._mark = C.string_at(addr, _RngMark._raw) if addr is not None else np.random.get_state()
+
+    def restore(self):
+        import ctypes as C
+        if self._addr is not None:
+            C.memmove(self._addr, self._mark, _RngMark._raw)
+        else:
+            np.random.set_state(self._mark)
+
+
 # ---- structure-of-arrays tree ------------------------------------------------------------------------
 class TreeArrays:
     """One agent's tree as flat arrays; node id = insertion order (index into tree_nodes[agent])."""
@@ -236,7 +286,7 @@ class TreeArrays:
             cap_rw = 4 * (self.n + block) + 1024
             rewires = np.empty((cap_rw, 3), dtype=np.int64)
             scratch = np.empty(self._xy.shape[0], dtype=np.int32)
-            state = np.random.get_state()
+            mark = _RngMark()
             u = np.random.random_sample(2 * block)
             n_rw.value = 0
             rc = lib.ipp_host_tree_grow(mode, variant, self._xy.ctypes.data, self.parent0.ctypes.data, self.parent.ctypes.data,
@@ -249,7 +299,7 @@ class TreeArrays:
                 raise RuntimeError(f"ipp_host_tree_grow failed with status {rc}")
             samples += consumed.value
             if consumed.value < block:                      # leave the RNG where consumed.value calls of rand(2) leave it
-                np.random.set_state(state)
+                mark.restore()
                 if consumed.value:
                     np.random.random_sample(2 * consumed.value)
             for i in range(self.n, n_out.value):
