@@ -1,6 +1,6 @@
 """Benchmark of the B200 GP-posterior / information-gain hot path (BASELINE.json's metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c3|c2] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c5|c3|c2] [--impl b200|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One step = one posterior pass (mean, std, 10**mean) over the whole workspace lattice of the named
@@ -39,6 +39,8 @@ WORKLOADS = {
     "c3": dict(desc="configs[2]: 3 robots, 500x500 grid, 2000 measurements", n=2000, W=50, agents=3, branches=4096),
     "c4": dict(desc="configs[3]: 8 robots, 1000x1000 grid, 5000 measurements, 8192 candidate branches", n=5000, W=100,
                agents=8, branches=8192),
+    "c5": dict(desc="configs[4] (one round of it): 8 robots, 2000x2000 grid, 5000 measurements, 8192 candidate branches",
+               n=5000, W=200, agents=8, branches=8192),
 }
 THETA = (1.0, 2.0)  # fixed (c, l): the posterior cost does not depend on it
 

@@ -836,3 +836,26 @@ def test_source_estimator_on_device_matches_reference(gold):
     assert np.array_equal(est, g["est_theta"])
     assert np.array_equal(np.random.uniform(size=3), g["est_rng_after"])
     assert E.STATS["device_evaluations"] - before["device_evaluations"] == 10
+
+
+def test_work_balanced_lattice_slabs(G):
+    """dist.lattice_slabs: the cheap per-row work model splits one lattice so that the EXACT executed slab counts of
+    the block-sparse kernel (gp.lattice_work, the host restatement of the kernel's own test) are near equal across
+    8 ranks, and closer than equal rows; per-tile counts add up to the total."""
+    from mripp_b200 import dist as D
+
+    X, ylog = _make(3000, 80.0, seed=4)
+    gp = _gp_at(G, X, ylog, np.log([1.0, 2.0]))
+    nx = ny = 800
+    ws = (0, 80, 0, 80)
+    total, dense = gp.lattice_work(ws[0], ws[1], nx, ws[2], ws[3], ny)
+    assert 0 < total < 0.6 * dense                                   # the sparse path is on at this length scale
+    tiles = gp.lattice_work(ws[0], ws[1], nx, ws[2], ws[3], ny, per_tile=True)
+    assert int(tiles.sum()) == total
+    def spread(bounds):
+        w = np.array([gp.lattice_work(ws[0], ws[1], nx, ws[2], ws[3], ny, g_begin=a, g_end=b)[0] for a, b in bounds], float)
+        return w.max() / w.mean()
+    balanced = D.lattice_slabs(gp, ws, nx, ny, 8)
+    equal = [D.row_slab(nx, ny, 8, r) for r in range(8)]
+    assert balanced[0][0] == 0 and balanced[-1][1] == nx * ny and all(b[1] > b[0] for b in balanced)
+    assert spread(balanced) <= 1.06 and spread(balanced) < spread(equal)
