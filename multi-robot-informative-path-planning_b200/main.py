@@ -6,6 +6,9 @@ on top of the B200 path.
 Kept from the reference (main.py:16-150): the config keys, `seed == -1 -> None`, construction of a
 strategy as `cls(scenario, **kwargs)` with kwargs routed by introspection of the constructors'
 argument names, the per-run metrics (log10 RMSE, source-weighted RMSE, differential entropy, time).
+Extension (BASELINE configs[4]): `--shard-rounds` gives every round its own RNG seed
+(`seed + round`, so a round's result does not depend on which process runs it) and, under torchrun, runs round r on
+rank r mod P -- one process per GPU, no data-path collective -- with the per-run metrics gathered on every rank.
 Deliberate differences: the hard-coded sweep over num_agents x stage_lambda (main.py:167-183) runs
 only with --sweep; figures are skipped (matplotlib is not a dependency); a 2-tuple workspace_size
 from the shipped example config is widened to (0, W, 0, H) so the example runs (it raises
@@ -36,7 +39,7 @@ def load_configuration(config_path: str) -> Dict:
         raise SystemExit("Error decoding the configuration file. Please check its format.")
 
 
-def initialize_scenarios(config: Dict) -> List[PointSourceField]:
+def initialize_scenarios(config: Dict, gp_factory=None) -> List[PointSourceField]:
     scenarios = []
     for sc in config["scenarios"]:
         params = dict(sc["params"])
@@ -47,7 +50,7 @@ def initialize_scenarios(config: Dict) -> List[PointSourceField]:
             params["workspace_size"] = (0, ws[0], 0, ws[1])
         elif ws is not None:
             params["workspace_size"] = tuple(ws)
-        scenario = PointSourceField(**params)
+        scenario = PointSourceField(**params) if gp_factory is None else PointSourceField(**params, gp_factory=gp_factory)
         # extension of the reference's config: defer the per-step GP refits nobody reads
         if hasattr(scenario.gp, "lazy"):
             scenario.gp.lazy = bool(config["args"].get("lazy_gp", False))
@@ -68,16 +71,20 @@ def get_constructor_args(cls: Callable, args: Dict) -> Dict:
     return picked
 
 
-def initialize_strategies(config: Dict, args: Dict) -> Dict[str, Callable]:
+def initialize_strategies(config: Dict, args: Dict, scorer_factory=None) -> Dict[str, Callable]:
     makers = {}
     for name in config["strategies"]:
         cls = globals()[name]
         kwargs = get_constructor_args(cls, args)
+        if scorer_factory is not None and get_constructor_args(cls, {"scorer": None}):
+            kwargs = dict(kwargs, scorer=scorer_factory())
         makers[name] = (lambda scenario, cls=cls, kwargs=kwargs: cls(scenario, **kwargs))
     return makers
 
 
-def run_simulations(scenarios, makers, args: Dict, debug: bool = False) -> Dict:
+def run_simulations(scenarios, makers, args: Dict, debug: bool = False, shard=None) -> Dict:
+    """shard = None: the reference's sequential rounds on one RNG stream.  shard = (rank, world): rounds seeded
+    individually, round r run by rank (r - 1) mod world only."""
     run_number = run_number_from_folder() if args.get("run_number", -1) == -1 else args["run_number"]
     names = list(makers)
     rmse_all, wrmse_all, ent_all, time_all, src_all = {}, {}, {}, {}, {}
@@ -90,6 +97,11 @@ def run_simulations(scenarios, makers, args: Dict, debug: bool = False) -> Dict:
         time_all[key] = {n: [] for n in names}
         src_all[key] = {n: {"source": [], "n_sources": []} for n in names}
         for round_number in range(1, args["rounds"] + 1):
+            if shard is not None:
+                if (round_number - 1) % shard[1] != shard[0]:
+                    continue
+                base = args.get("seed", 0)
+                np.random.seed((0 if base in (None, -1) else int(base)) + 7919 * s_idx + round_number)
             for name, make in makers.items():
                 strategy = make(scenario)
                 Z_pred, std = strategy.run()
@@ -110,7 +122,7 @@ def run_simulations(scenarios, makers, args: Dict, debug: bool = False) -> Dict:
                                 "n_obs": int(len(strategy.obs_wp)), "source_errors": calculate_source_errors(scenario.sources, est)})
                 print(f"Round {round_number}/{args['rounds']} scenario {s_idx} {name}: RMSE {rmse:.4f} WRMSE {wrmse:.4f} "
                       f"time {getattr(strategy, 'time_taken', None)}")
-    if args.get("save", False):
+    if args.get("save", False) and (shard is None or shard[1] == 1):  # sharded: the gathered JSON (--out) is the record
         save_run_info(run_number, rmse_all, wrmse_all, ent_all, src_all, time_all, args, scenarios)
     return {"run_number": run_number, "results": results}
 
@@ -121,8 +133,37 @@ def main(argv=None):
     ap.add_argument("-debug", "--debug", action="store_true")
     ap.add_argument("--sweep", action="store_true", help="the reference's num_agents x stage_lambda sweep (main.py:167-183)")
     ap.add_argument("--out", default=None, help="write the per-run metrics as JSON")
+    ap.add_argument("--shard-rounds", action="store_true",
+                    help="seed every round on its own and, under torchrun, run round r on rank r mod P (one process per GPU)")
     a = ap.parse_args(argv)
-    config = load_configuration(a.config)
+    return run(a, load_configuration(a.config))
+
+
+def _init_shard():
+    """(rank, world, group or None) for --shard-rounds: torch.distributed when launched by torchrun, else one process."""
+    import os
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return 0, 1, False
+    import torch
+    import torch.distributed as dist
+    started = False
+    if not dist.is_initialized():
+        cuda = torch.cuda.is_available()
+        if cuda:
+            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl" if cuda else "gloo")
+        started = True
+    return dist.get_rank(), dist.get_world_size(), started
+
+
+def run(a, config: Dict, gp_factory=None, scorer_factory=None):
+    """main() after argument parsing; gp_factory / scorer_factory let the tests drive the flow without a GPU."""
+    shard = None
+    started = False
+    if getattr(a, "shard_rounds", False):
+        rank, world, started = _init_shard()
+        shard = (rank, world)
     grid = [(config["args"].get("num_agents", 1), config["args"].get("stage_lambda", 0.875))]
     if a.sweep:
         grid = [(n, lam) for n in (1, 2, 3) for lam in (1.0, 0.5, 0.25, 0.0)]
@@ -130,13 +171,22 @@ def main(argv=None):
     for num_agents, lam in grid:
         config["args"]["num_agents"] = num_agents
         config["args"]["stage_lambda"] = lam
-        scenarios = initialize_scenarios(config)
-        makers = initialize_strategies(config, config["args"])
-        out = run_simulations(scenarios, makers, config["args"], a.debug)
+        scenarios = initialize_scenarios(config, gp_factory)
+        makers = initialize_strategies(config, config["args"], scorer_factory)
+        out = run_simulations(scenarios, makers, config["args"], a.debug, shard)
         for r in out["results"]:
             r.update(num_agents=num_agents, stage_lambda=lam)
         everything.extend(out["results"])
-    if a.out:
+    if shard is not None and shard[1] > 1:
+        import torch.distributed as dist
+        parts = [None] * shard[1]
+        dist.all_gather_object(parts, everything)          # a few hundred bytes per run: the only exchange
+        order = {name: k for k, name in enumerate(config["strategies"])}
+        everything = sorted((r for p in parts for r in p),
+                            key=lambda r: (r["num_agents"], -r["stage_lambda"], r["scenario"], r["round"], order[r["strategy"]]))
+        if started:
+            dist.destroy_process_group()
+    if a.out and (shard is None or shard[0] == 0):
         with open(a.out, "w") as fh:
             json.dump(everything, fh, indent=1)
     return everything

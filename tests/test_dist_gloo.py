@@ -120,3 +120,54 @@ def test_balanced_row_slabs_partition_and_balance():
             loads = np.array([w[lo // nx:hi // nx].sum() for lo, hi in b])
             assert loads.max() <= 1.05 * loads.mean()
     assert balanced_row_slabs(np.zeros(10), 10, 3) == [(0, 40), (40, 70), (70, 100)]  # no information: near-equal rows
+
+
+# ---- independent rounds sharded over the ranks (BASELINE configs[4]): main.py --shard-rounds ------------------
+_ROUNDS_CONFIG = {
+    "scenarios": [{"class": "PointSourceField",
+                   "params": {"num_sources": 2, "workspace_size": [20, 20], "intensity_range": [100000, 1000000]}}],
+    "strategies": ["RRTRIG_PointSourceInformative_All_SourceMetric_PathPlanning", "MultiAgentBoustrophedon"],
+    "args": {"rounds": 3, "beta_t": 5.0, "save": False, "show": False, "seed": 21, "budget": 30, "d_waypoint_distance": 2.5,
+             "budget_iter": 3, "run_number": 1, "lambda_b": 1, "max_sources": 2, "n_samples": 40, "s_stages": 3, "num_agents": 2,
+             "stage_lambda": 0.5},
+}
+
+
+def _run_rounds(shard_rounds):
+    import argparse
+    import copy
+    from mripp_b200 import main as M
+    from tests._doubles import OracleGP, OracleScorer
+
+    class FastGP(OracleGP):
+        full = False
+
+    a = argparse.Namespace(sweep=False, out=None, debug=False, shard_rounds=shard_rounds)
+    res = M.run(a, copy.deepcopy(_ROUNDS_CONFIG), gp_factory=FastGP, scorer_factory=OracleScorer)
+    return [(r["scenario"], r["round"], r["strategy"], r["rmse"], r["wrmse"], r["entropy"], r["n_obs"]) for r in res]
+
+
+def _rounds_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    q.put((rank, _run_rounds(True)))
+
+
+def test_rounds_sharded_over_two_ranks_equal_one_process(monkeypatch):
+    """Every rank ends up with the full, ordered list of per-run metrics, equal to what one process computes for the
+    same individually seeded rounds."""
+    monkeypatch.setenv("WORLD_SIZE", "1")
+    single = _run_rounds(True)
+    assert [(s, r) for s, r, *_ in single] == [(1, 1), (1, 1), (1, 2), (1, 2), (1, 3), (1, 3)]
+    assert len({t[3] for t in single if t[2].startswith("RRTRIG")}) == 3      # the rounds differ (own seeds)
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_rounds_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, res in out:
+        assert res == single
