@@ -547,6 +547,33 @@ def run_b200(args, wl, rank, world, local_rank):
         est_runs.append(time.perf_counter() - t0)
     est_rng_dev = np.random.uniform(size=2)
     est_stats = {k: EST.STATS[k] - est_stats0[k] for k in EST.STATS}
+
+    # ---- tree growth: host code, native loop vs the Python loop it replaces, same seed ------------------
+    from mripp_b200.src.rrt import rrt_utils as RU
+
+    def grow_tree(native):
+        np.random.seed(1)
+        tr = RU.TreeArrays(np.array([0.05 * W, 0.05 * W]))
+        t0 = time.perf_counter()
+        if native:
+            assert tr.grow_native(2, (0, W, 0, W), 1.0, 1.0, 1000.0) is not None, "native norm not calibrated"
+        else:
+            trav = 0
+            while trav < 1000.0:
+                target = np.random.rand(2) * (W, W) + (0, 0)
+                nn = tr.nearest(target)
+                pt = RU.steer_point(tr.point(nn), target, 1.0)
+                nb = tr.near(pt, 1.0)
+                new = tr.add(pt, nn)
+                trav += np.linalg.norm(tr.point(new) - tr.point(nn))
+                tr.rewire(nb, new)
+        return time.perf_counter() - t0, tr
+
+    grow_tree(True)
+    tg_native, tr_n = min((grow_tree(True) for _ in range(5)), key=lambda r: r[0])
+    tg_python, tr_p = grow_tree(False)
+    tg_same = bool(np.array_equal(tr_n.points(), tr_p.points()) and np.array_equal(tr_n.parent[: tr_n.n], tr_p.parent[: tr_p.n])
+                   and tr_n.rewires == tr_p.rewires)
     if sampler:
         sampler.stop()
 
@@ -632,6 +659,9 @@ def run_b200(args, wl, rank, world, local_rank):
                 "cpu_baseline": {"estimate_ms": 1e3 * est_cpu_s, "cores": 1, "kind": "port",
                                  "sample": "the same call on oracle/estimation_oracle.py (per-particle scipy logpmf loop)"},
                 "identical_to_cpu": est_same},
+            "tree_growth": {"nodes": int(tr_n.n), "native_ms": 1e3 * tg_native, "python_ms": 1e3 * tg_python,
+                            "identical": tg_same, "call": "rig_tree_generation, budget portion 1000, step 1.0 (host code: "
+                                                          "ipp_host_tree_grow vs the numpy-vectorised Python loop)"},
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
