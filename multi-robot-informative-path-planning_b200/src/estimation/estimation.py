@@ -31,7 +31,7 @@ EPS = float(np.finfo(np.float64).eps)
 # n <= 8192, + 1 per doubling) against the kernel's (ceil(n / 256) sequential + 8 tree levels); each addition
 # contributes EPS / 2 of the running sum, itself <= S2.
 C_TERM = 16.0
-STATS = {"stages": 0, "redecided": 0, "device_evaluations": 0}
+STATS = {"stages": 0, "redecided": 0, "device_evaluations": 0, "why_nonfinite": 0, "why_loose_bound": 0, "why_in_band": 0}
 
 
 def c_sum(n: int) -> float:
@@ -122,6 +122,11 @@ def _resample_indices(particles, gamma, n_samples, obs_wp, obs_vals, lambda_b, M
             band = 2.0 * float(np.sum(w[live] * np.expm1(shift[live]))) + 8.0 * n_samples * EPS
             if not draws_inside_band(cdf, u, idx, band):
                 return idx
+            STATS["why_in_band"] += 1
+        else:
+            STATS["why_loose_bound"] += 1
+    else:
+        STATS["why_nonfinite"] += 1
     # inside the band (or a non-finite likelihood): the reference's own expression for the weights, same draws
     STATS["redecided"] += 1
     w = stage_weights(batched_poisson_log_likelihood(particles, obs_wp, obs_vals, lambda_b, M), gamma, n_samples)
