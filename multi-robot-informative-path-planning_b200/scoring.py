@@ -146,6 +146,9 @@ class GpuScorer:
         self.torch = _lib.require_cuda()
         self.lib = _lib.load()
         self.launches = 0
+        # a torch.distributed group (True = default group): shard the branch walks of one tree over its ranks in
+        # contiguous batches of nodes, node table / sources / observations replicated; see tree_information
+        self.branch_group = None
 
     # -- helpers ---------------------------------------------------------------------------------
     def _dev(self, a, dtype=None):
@@ -173,7 +176,7 @@ class GpuScorer:
         return counts, None
 
     # -- I1-I5 + T: node.information for the whole tree ----------------------------------------------
-    def _upload_tree(self, variant, tree, ctx: ScoreContext):
+    def _upload_tree(self, variant, tree, ctx: ScoreContext, eval_range=None):
         """Host tree arrays / context -> device tensors (one dict per scoring pass)."""
         torch = self.torch
         N = tree.n
@@ -204,8 +207,10 @@ class GpuScorer:
             d["amb"] = torch.empty(N, dtype=torch.int32, device="cuda")
             d["amb_total"] = torch.zeros(1, dtype=torch.int32, device="cuda")
         d["nclose"] = None
-        d["eval_node"] = torch.arange(N, dtype=torch.int32, device="cuda")
-        d["out"] = torch.empty(N, dtype=torch.float64, device="cuda")
+        lo, hi = eval_range if eval_range is not None else (0, N)
+        d["B"] = hi - lo
+        d["eval_node"] = torch.arange(lo, hi, dtype=torch.int32, device="cuda")
+        d["out"] = torch.empty(max(hi - lo, 1), dtype=torch.float64, device="cuda")
         d["term0"] = torch.empty(N, dtype=torch.float64, device="cuda")
         d["d_wp"] = float(ctx.d_wp)
         return d
@@ -231,21 +236,37 @@ class GpuScorer:
         _lib.check(lib.ipp_branch_gain(variant, _lib.ptr(d["node_xy"]), d["N"], _lib.ptr(d["parent0"]), _lib.ptr(d["hoff"]),
                                        _lib.ptr(d["htime"]), _lib.ptr(d["hpar"]), _lib.ptr(d["src_gain"]), _lib.ptr(d["wpen"]),
                                        _lib.ptr(d["nclose"]), d["has_obs"], 1 if d["S"] else 0, _lib.ptr(d["obst"]),
-                                       d["n_obst"], _lib.ptr(d["eval_node"]), _lib.ptr(d["eval_node"]), d["N"],
+                                       d["n_obst"], _lib.ptr(d["eval_node"]), _lib.ptr(d["eval_node"]), d["B"],
                                        _lib.ptr(d["term0"]), _lib.ptr(d["out"]), st), "ipp_branch_gain")
         self.launches += 2
 
     def tree_information(self, variant, tree, ctx: ScoreContext):
+        """node.information of every node (the gain of the branch that ends in it).  With `branch_group` set, every
+        rank evaluates the per-node terms of the whole (replicated) tree and walks only its contiguous batch of
+        nodes; one all_gather assembles the vector, identical on every rank and to the single-GPU result (each walk
+        reads the same tables in the same order)."""
         if tree.n == 0:
             return np.zeros(0)
-        d = self._upload_tree(variant, tree, ctx)
+        group, eval_range, sizes = self.branch_group, None, None
+        if group is not None:
+            from . import dist as D
+            import torch.distributed as tdist
+            group = None if group is True else group
+            world, rank = tdist.get_world_size(group), tdist.get_rank(group)
+            bounds = [D.slab_bounds(tree.n, world, r) for r in range(world)]
+            eval_range, sizes = bounds[rank], [b - a for a, b in bounds]
+        d = self._upload_tree(variant, tree, ctx, eval_range)
         self._launch_terms(variant, d)
         if d["need_close"] and int(d["amb_total"].item()) > 0:
             # knife-edge distance pairs: the host re-decides them with numpy's own norm
             counts = resolve_close_counts(d["pts"], d["obs_host"], d["d_wp"], d["sure"].cpu().numpy(), d["amb"].cpu().numpy())
             d["nclose"] = self._dev(counts.astype(np.int32))
         self._launch_walk(variant, d)
-        info = d["out"].cpu().numpy()
+        if sizes is not None:
+            from . import dist as D
+            info = D.gather_slabs(d["out"][: d["B"]], sizes, group).cpu().numpy()
+        else:
+            info = d["out"].cpu().numpy()
         info[0] = 0.0  # the root is never scored (InformativeTreeNode.information = 0, rrt_utils.py:35)
         return info
 

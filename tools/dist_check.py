@@ -71,6 +71,33 @@ if rank == 0:
     print(f"dist_check strong scaling: one C4 lattice (10^6 points, n=5000) by row slab over {world} GPUs incl. all_gather of "
           f"Z and std: {float(tms):.1f} ms per posterior ({1e6 / float(tms) * 1e3:.3e} points/s); sharded argmax of 8192 "
           f"scores (all_gather of one pair per rank): {t_arg * 1e6:.0f} us", flush=True)
+# ---- 8192 candidate branches of one tree sharded over the ranks (BASELINE configs[3]) ------------------
+from bench import synth_tree
+from mripp_b200.scoring import GpuScorer, ScoreContext
+from mripp_b200.src.rrt.rrt_utils import TreeArrays
+txy, tpar = synth_tree(8192, 100, 1)
+tr = TreeArrays(txy[0], capacity=8193)
+for k_ in range(1, 8193):
+    tr.add(txy[k_], int(tpar[k_]))
+Xb, measb, srcb = synth_observations(5000, 100, 0)
+obs_b = [list(Xb[a * 625:(a + 1) * 625]) for a in range(8)]
+ctx_b = ScoreContext(srcb, tr.point(0), obs_b, 0, 1.0, (0, 100, 0, 100), [])
+sc1, scP = GpuScorer(), GpuScorer()
+scP.branch_group = True
+info1 = sc1.tree_information(3, tr, ctx_b)
+infoP = scP.tree_information(3, tr, ctx_b)
+same_b = np.array_equal(info1, infoP, equal_nan=True)
+ok = ok and same_b
+def t_info(sc_):
+    for _ in range(3): sc_.tree_information(3, tr, ctx_b)
+    dist.barrier(); torch.cuda.synchronize(); t0_ = time.perf_counter()
+    for _ in range(10): sc_.tree_information(3, tr, ctx_b)
+    torch.cuda.synchronize(); return (time.perf_counter() - t0_) / 10 * 1e3
+t1_, tP_ = t_info(sc1), t_info(scP)
+if rank == 0:
+    print(f"dist_check sharded branches: information of 8192 branches (point_source_gain_all, 5000 observations) over {world} GPUs "
+          f"== one GPU: {same_b}; host call one GPU {t1_:.2f} ms, sharded {tP_:.2f} ms (the walks are 0.04 ms of it: sharding a "
+          f"batch this small only adds the all_gather)", flush=True)
 # ---- one 11-restart fit with its restarts spread over the ranks ---------------------------------------
 for n_fit, W_fit in ((2000, 50), (5000, 100)):
     Xf, measf, _ = synth_observations(n_fit, W_fit, 0)
