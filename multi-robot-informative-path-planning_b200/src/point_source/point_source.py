@@ -40,7 +40,7 @@ class PointSourceField:
 
     def __init__(self, num_sources: int = 1, workspace_size: Tuple[int, int, int, int] = (0, 40, 0, 40), obstacles: List = [],
                  intensity_range: Tuple[int, int] = (100000, 1000000), kernel_params: Optional[Dict[str, float]] = None,
-                 seed: Optional[int] = None, gp_factory=None):
+                 seed: Optional[int] = None, gp_factory=None, ground_truth_mode: str = "auto"):
         if seed is not None:
             np.random.seed(seed)
         self.validate_inputs(num_sources, workspace_size, intensity_range)
@@ -55,6 +55,10 @@ class PointSourceField:
         self.x = np.linspace(w[0], w[1], (w[1] - w[0]) * 10)
         self.y = np.linspace(w[2], w[3], (w[3] - w[2]) * 10)
         self.X, self.Y = np.meshgrid(self.x, self.y)
+        # "host": the reference's numpy / Python-loop field; "device": ipp_ground_truth_grid; "auto": the device only
+        # where the host costs minutes -- rectangle obstacles on a lattice of more than 10^5 points (the Python loop
+        # over every lattice point, point_source.py:247-258: 100 us per point and obstacle).  Metrics only.
+        self.ground_truth_mode = ground_truth_mode
         self.g_truth = self.ground_truth()
         kernel = self.construct_kernel(kernel_params)
         make = gp_factory if gp_factory is not None else GaussianProcessRegressor
@@ -116,7 +120,17 @@ class PointSourceField:
         return np.sum(per_source, axis=-1)
 
     def ground_truth(self):
-        """point_source.py:163-212."""
+        """point_source.py:163-212 (see ground_truth_mode for where it is evaluated)."""
+        mode = getattr(self, "ground_truth_mode", "host")
+        if mode not in ("auto", "host", "device"):
+            raise ValueError(f"ground_truth_mode must be 'auto', 'host' or 'device', not {mode!r}")
+        rect_only = bool(self.obstacles) and all(o.get("type") == "rectangle" for o in self.obstacles)
+        if mode == "device" or (mode == "auto" and rect_only and self.X.size > 100_000):
+            return self.ground_truth_device()
+        return self.ground_truth_host()
+
+    def ground_truth_host(self):
+        """point_source.py:163-212, the reference's own numpy expressions."""
         R = self.X + 1j * self.Y
         field = np.zeros(R.shape)
         for source in self.sources:

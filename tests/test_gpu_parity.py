@@ -718,6 +718,19 @@ def test_ground_truth_device_many_obstacles_matches_host(torch):
     sc = PointSourceField(num_sources=4, workspace_size=(0, 18, 0, 9), obstacles=obst, seed=2)
     host, dev = sc.g_truth, sc.ground_truth_device()
     assert np.abs(dev / host - 1.0).max() <= 1e-12
+    # ground_truth_mode: small lattices stay on the reference's host expressions, large obstacle lattices (where the
+    # host's per-point Python loop takes minutes) go to the device, "host" / "device" force either
+    assert np.array_equal(host, sc.ground_truth_host())                       # auto, 16 200 points -> host
+    big = PointSourceField(num_sources=2, workspace_size=(0, 40, 0, 30), obstacles=obst[:2], seed=2)   # 120 000 points
+    assert big.ground_truth_mode == "auto" and np.array_equal(big.g_truth, big.ground_truth_device())
+    sub = (slice(0, 300, 37), slice(0, 400, 41))
+    X0, Y0 = big.X, big.Y
+    big.X, big.Y = X0[sub], Y0[sub]                                           # the host expressions on a sub-lattice
+    small_host = big.ground_truth_host()
+    big.X, big.Y = X0, Y0
+    assert np.abs(big.g_truth[sub] / small_host - 1.0).max() <= 1e-12
+    forced = PointSourceField(num_sources=2, workspace_size=(0, 6, 0, 6), seed=2, ground_truth_mode="device")
+    assert np.abs(forced.g_truth / forced.ground_truth_host() - 1.0).max() <= 1e-12
 
 
 def test_abi_rejects_bad_arguments_on_device(torch):
