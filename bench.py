@@ -480,6 +480,17 @@ def run_b200(args, wl, rank, world, local_rank):
     g1.record()
     torch.cuda.synchronize()
     gram_ms = g0.elapsed_time(g1) / 10
+    # context for the write-bound fraction: the same bytes written by cudaMemset (the copy figure in MEASURED_PEAKS.json
+    # counts a read and a write; a pure store stream has its own ceiling)
+    for _ in range(3):
+        Kd.zero_()
+    torch.cuda.synchronize()
+    g0.record()
+    for _ in range(10):
+        Kd.zero_()
+    g1.record()
+    torch.cuda.synchronize()
+    memset_ms = g0.elapsed_time(g1) / 10
     del Kd
     if world > 1:
         t = torch.tensor([br_dev_ms, 1.0 / br_e2e], dtype=torch.float64, device="cuda")
@@ -630,7 +641,9 @@ def run_b200(args, wl, rank, world, local_rank):
                     "tflops": float(NP) ** 3 / (lml_ms * 1e-3) / 1e12, "full_fit_11_restarts": full_fit,
                     "cpu_lml_grad_eval_ms": cpu_post["lml_grad_eval_ms"], "cpu_cores": cpu_post["cores"]},
             "gram": {"ms": gram_ms, "n": n, "GBps_written": 8.0 * n * n / (gram_ms * 1e-3) / 1e9,
-                     "frac_of_measured_hbm": 8.0 * n * n / (gram_ms * 1e-3) / 1e9 / hbm, "bound": "hbm (write)"},
+                     "frac_of_measured_hbm": 8.0 * n * n / (gram_ms * 1e-3) / 1e9 / hbm, "bound": "hbm (write)",
+                     "memset_same_bytes_GBps": 8.0 * n * n / (memset_ms * 1e-3) / 1e9,
+                     "frac_of_memset": memset_ms / gram_ms},
             "planning_step": {"ms": plan_ms, "agents": agents, "branches_per_agent": per_agent,
                               "mode": "lazy GP refits (DESIGN.md section 5): per agent tree scoring (point_source_gain_all) + "
                                       "stage-2 argmax + stage-1 mutual-information/penalty selector, host arrays in and out"},
