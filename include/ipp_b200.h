@@ -177,8 +177,8 @@ int ipp_host_norm2(int variant, const double* xy, int m, double* out);
 /* Grow one agent's tree in place on the structure-of-arrays tree (xy[capacity][2], parent0 = parent at insertion,
  * parent = current parent, edge = |point - current parent|, nchild) from K pre-drawn uniform pairs (np.random.rand(2)
  * per sample) until the travelled length reaches budget_portion, the pairs run out, or capacity / rewire_cap is
- * reached.  mode 0: rrt_tree_generation (rrt.py:263-277), 1: rrt_star_tree_generation (:279-304),
- * 2: rig_tree_generation (:306-327); primitives nearest / steer / near / cost / rewire / add_node of
+ * reached.  mode 0: rrt_tree_generation (rrt.py:263-277), 1: rrt_star_tree_generation (:280-305),
+ * 2: rig_tree_generation (:307-328); primitives nearest / steer / near / cost / rewire / add_node of
  * src/rrt/rrt_utils.py:59-105 with their first-minimum and strict-inequality semantics.  ws4 = {x0, x1, y0, y1};
  * step = steer's d_max_step, radius = near's distance.  rewires: rows {time = id of the inserted node, node,
  * new parent} appended from *n_rewires_io; scratch: capacity ints.  Outputs: pairs consumed, node count,

@@ -86,7 +86,7 @@ def draws_inside_band(cdf: np.ndarray, u: np.ndarray, idx: np.ndarray, band: flo
 
 
 def resample_indices(particles, gamma, n_samples, obs_wp, obs_vals, lambda_b, M, scorer, prepared) -> np.ndarray:
-    """np.random.choice(n_samples, size=n_samples, p=weights) of estimation.py:115 with the weights' log-likelihoods
+    """np.random.choice(n_samples, size=n_samples, p=weights) of estimation.py:117 with the weights' log-likelihoods
     from the device; consumes exactly the n_samples uniforms the reference's call consumes."""
     from mripp_b200.exact import RNG_SECTION
     with RNG_SECTION:
