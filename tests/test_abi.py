@@ -4,6 +4,8 @@ import ctypes
 import os
 import re
 
+import pytest
+
 from tests.conftest import ROOT
 
 from mripp_b200 import _lib
@@ -41,3 +43,25 @@ def test_bad_arguments_are_rejected_without_a_device():
     assert lib.ipp_gram_rbf(None, 0, None, 0, 1.0, 1.0, 0.0, None, 0, None) == -1
     assert lib.ipp_gp_posterior_points(None, None, 0, 1.0, 1.0, 0.0, 1.0, None, 0, None, None, None, None, 0, None) == -1
     assert lib.ipp_argmax_first(None, 0, None, None, None) == -1
+
+
+def test_plain_c_consumer_builds_and_runs(tmp_path):
+    """include/ipp_b200.h compiles as C, libipp_b200.so links from gcc, and the entry points that need no device
+    (version, layout, host-side tree growth) behave (tests/c_abi/consumer.c)."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    from mripp_b200 import _lib
+
+    _lib.load()
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    exe = str(tmp_path / "consumer")
+    src = os.path.join(ROOT, "tests", "c_abi", "consumer.c")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), src, "-o", exe, "-L", libdir,
+                    "-lipp_b200", "-lm", f"-Wl,-rpath,{libdir}"], check=True)
+    run = subprocess.run([exe], capture_output=True, text=True)
+    assert run.returncode == 0, (run.returncode, run.stdout, run.stderr)
+    assert "c_abi ok" in run.stdout
