@@ -157,7 +157,11 @@ def native_norm_variant() -> Optional[int]:
     want = np.array([np.linalg.norm(v) for v in xy])
     out = np.empty(len(xy))
     match = []
-    for variant in range(3):
+    try:  # variants 1 and 2 execute hardware FMA instructions: only try them where the CPU has them
+        has_fma = " fma " in (" " + open("/proc/cpuinfo").read().split("flags", 1)[1].split("\n", 1)[0] + " ")
+    except (OSError, IndexError):
+        has_fma = False
+    for variant in (range(3) if has_fma else range(1)):
         _lib.check(lib.ipp_host_norm2(variant, xy.ctypes.data, len(xy), out.ctypes.data), "ipp_host_norm2")
         if np.array_equal(out, want):
             match.append(variant)
