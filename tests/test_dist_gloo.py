@@ -50,6 +50,21 @@ def _worker(rank, world, port, q):
             return torch.from_numpy(10 ** m), torch.from_numpy(s)
 
         z, s = D.sharded_grid_posterior(None, ws, nx, ny, compute_slab=slab)
+
+        class WorkModelGP:
+            """The two methods sharded_grid_posterior uses of a fitted estimator, on the oracle: a per-row work
+            estimate (uneven on purpose) and the posterior of a flat index range."""
+            def lattice_row_work(self, x0, x1, nx_, y0, y1, ny_):
+                return 1.0 + 4.0 * np.exp(-0.5 * ((np.arange(ny_) - 0.3 * ny_) / (0.1 * ny_)) ** 2)
+
+            def predict_grid_device(self, x0, x1, nx_, y0, y1, ny_, g_begin=0, g_end=None, want_zpred=True):
+                zz, ss = slab(g_begin, g_end)
+                return None, ss, zz
+
+        zb, sb = D.sharded_grid_posterior(WorkModelGP(), ws, nx, ny)
+        assert np.array_equal(zb, z) and np.array_equal(sb, s)          # the split does not change the field
+        bal = D.lattice_slabs(WorkModelGP(), ws, nx, ny, world)
+        assert bal[0][1] != D.row_slab(nx, ny, world, 0)[1]              # ... and it is not the equal-rows split
         scores = np.array([1.0, 5.0, 5.0, np.nan, 2.0, np.nan, 9.0])
         lo, hi = D.slab_bounds(len(scores), world, rank)
         k_nan = D.sharded_argmax(torch.from_numpy(scores[lo:hi]), lo)
