@@ -561,28 +561,35 @@ __global__ void __launch_bounds__(256) diag_inverse_kernel(const double* __restr
 }
 
 // ---------------------------------------------------------------------------------------------
-// W = L^-1 by recursive doubling on an aligned grid.  Level with half-size s merges
-// [r0, r1) and [r1, r2):  W21 = -W22 * (L21 * W11).   Two batched GEMM launches per level.
+// W = L^-1 by recursive doubling over a BALANCED binary partition of the nb = NP/64 block rows: with `parts`
+// (a power of two) parts at the finer level, part i is blocks [floor(i nb / parts), floor((i+1) nb / parts)), and
+// the level merges parts 2p and 2p+1 -- rows [r0, r1) and [r1, r2):  W21 = -W22 * (L21 * W11).  The partitions of
+// successive levels refine each other (floor(2i nb / 2P) = floor(i nb / P)), the finest has at most one block per
+// part (diag_inverse_kernel), empty halves are no-ops.  A grid aligned to powers of two instead makes the top level
+// lopsided whenever NP is not a power of two (n = 5000: 4096 + 960 rows, its longest tile 128 x 128 x 4096 = 0.53 ms
+// of one SM's peak); balanced halves (2496 + 2560) cut the longest k range to 2496 and even out the tile counts.
+// Two batched GEMM launches per level:
 //   STEP 1: T[r1+i][r0+j]  =  sum_{k >= j} L[r1+i][r0+k] * W[r0+k][r0+j]
 //   STEP 2: W[r1+i][r0+j]  = -sum_{k <= i} W[r1+i][r1+k] * T[r1+k][r0+j]
 // ---------------------------------------------------------------------------------------------
 template <class C, int STEP>
 __global__ void __launch_bounds__(C::THREADS) trtri_level_kernel(const double* __restrict__ L, long ld,
                                                                  double* __restrict__ W, long ldw, double* __restrict__ T,
-                                                                 long ldt, int np, int s, int pairs) {
+                                                                 long ldt, int nb, int parts, int s) {
   extern __shared__ __align__(16) double smem[];
   // 1-D grid, heaviest tiles first (the hardware hands out CTAs in index order): the k range of a tile is
   // triangular -- STEP 1 sums k in [col0, r1), STEP 2 sums k in [r1, row0 + BM) -- so a plain (x, y) order
   // leaves the longest tiles for the last wave.
-  const int nx = (s + C::BN - 1) / C::BN, ny = (s + C::BM - 1) / C::BM;
+  // s = 64 * ceil(nb / parts): the largest half at this level
+  const int nx = (s + C::BN - 1) / C::BN, ny = (s + C::BM - 1) / C::BM, pairs = parts / 2;
   const int p = blockIdx.x % pairs, rest = blockIdx.x / pairs;
   const int bx = (STEP == 1) ? rest / ny : rest % nx;
   const int by = (STEP == 1) ? rest % ny : ny - 1 - rest / nx;
-  const int r0 = 2 * p * s, r1 = r0 + s;
-  if (r1 >= np) return;
-  const int r2 = min(r0 + 2 * s, np);
+  const int r0 = BLK * (int)((long)(2 * p) * nb / parts), r1 = BLK * (int)((long)(2 * p + 1) * nb / parts),
+            r2 = BLK * (int)((long)(2 * p + 2) * nb / parts);
+  if (r1 == r0 || r2 == r1) return;  // an empty half: the other one is already inverted
   const int row0 = r1 + by * C::BM, col0 = r0 + bx * C::BN;
-  if (row0 >= r2) return;
+  if (row0 >= r2 || col0 >= r1) return;
   double acc[C::MI][C::NI][2];
   zero_acc<C>(acc);
   if (STEP == 1) {
@@ -816,13 +823,13 @@ static int chol_inplace(double* Kb, double* Wb, double* info, const GpDims& d, c
 }
 
 template <class C>
-static int trtri_level(const double* Kb, double* Wb, double* Tb, const GpDims& d, int s, int pairs, cudaStream_t st) {
+static int trtri_level(const double* Kb, double* Wb, double* Tb, const GpDims& d, int parts, int s, cudaStream_t st) {
   constexpr size_t SM = gemm_smem_bytes<C, Lay::KCONT, Lay::MCONT>();
   if (opt_in_smem(trtri_level_kernel<C, 1>, SM) != cudaSuccess) return IPP_ERR_CUDA;
   if (opt_in_smem(trtri_level_kernel<C, 2>, SM) != cudaSuccess) return IPP_ERR_CUDA;
-  const unsigned grid = (unsigned)(((s + C::BN - 1) / C::BN) * ((s + C::BM - 1) / C::BM) * pairs);
-  trtri_level_kernel<C, 1><<<grid, C::THREADS, SM, st>>>(Kb, d.ld, Wb, d.ld, Tb, d.ld, d.np, s, pairs);
-  trtri_level_kernel<C, 2><<<grid, C::THREADS, SM, st>>>(Kb, d.ld, Wb, d.ld, Tb, d.ld, d.np, s, pairs);
+  const unsigned grid = (unsigned)(((s + C::BN - 1) / C::BN) * ((s + C::BM - 1) / C::BM) * (parts / 2));
+  trtri_level_kernel<C, 1><<<grid, C::THREADS, SM, st>>>(Kb, d.ld, Wb, d.ld, Tb, d.ld, d.np / BLK, parts, s);
+  trtri_level_kernel<C, 2><<<grid, C::THREADS, SM, st>>>(Kb, d.ld, Wb, d.ld, Tb, d.ld, d.np / BLK, parts, s);
   return IPP_OK;
 }
 
@@ -830,12 +837,15 @@ template <class C>
 static int trtri_inplace(const double* Kb, double* Wb, double* Tb, const GpDims& d, cudaStream_t st) {
   const int nb = d.np / BLK;
   w_clear_kernel<<<dim3(nb, nb), 256, 0, st>>>(Wb, d.ld, d.np);
-  for (int s = BLK; s < d.np; s *= 2) {
-    const int pairs = (d.np + 2 * s - 1) / (2 * s);
+  int parts = 1;
+  while (parts < nb) parts *= 2;
+  for (; parts >= 2; parts /= 2) {  // finest level first
+    const int s = BLK * ((nb + parts - 1) / parts);  // the largest half at this level
+    const int pairs = nb < parts ? (nb + 1) / 2 : parts / 2;  // pairs with something to merge (finest level: ~nb / 2)
     // levels whose 128x128 tiling cannot fill the GPU run on 64x64 tiles (4x the CTAs, each a quarter of the work)
     const int tiles128 = ((s + 127) / 128) * ((s + 127) / 128) * pairs;
-    const int rc = (C::BM > 64 && tiles128 < 2 * 148) ? trtri_level<Cfg64>(Kb, Wb, Tb, d, s, pairs, st)
-                                                  : trtri_level<C>(Kb, Wb, Tb, d, s, pairs, st);
+    const int rc = (C::BM > 64 && tiles128 < 2 * 148) ? trtri_level<Cfg64>(Kb, Wb, Tb, d, parts, s, st)
+                                                  : trtri_level<C>(Kb, Wb, Tb, d, parts, s, st);
     if (rc != IPP_OK) return rc;
   }
   return IPP_OK;
