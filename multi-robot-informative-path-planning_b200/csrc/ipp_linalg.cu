@@ -344,17 +344,25 @@ __device__ __forceinline__ void chol_diag_update_step(double* __restrict__ A, lo
 // unlike multiplying by the explicit inverse: at cond(K) ~ 1e11 the diagonal blocks reach cond ~ 1e5 and
 // the inverse route cost 5 digits of L).  NT / 64 adjacent lanes share a row (columns interleaved), the
 // row lives in their registers, the solved entry is broadcast by shuffle, L_kk comes from shared memory.
-template <int NT>
-__device__ __forceinline__ void chol_trsm_block(double* __restrict__ A, long ld, int k, int i, double* psm) {
-  constexpr int LPR = NT / BLK;   // lanes per row
+// ROWS (64, 32 or 16) rows of block i per call, part `h` of the block: when a panel has fewer row blocks than half
+// (a quarter of) the CTAs, the blocks are split so that every SM takes part -- the 64 substitution steps stay, but
+// each step moves 1/2 (1/4) of the shared-memory traffic that bounds it.  Every row sees the same operations in the
+// same order whatever the split, so the factor does not depend on it.
+template <int NT, int ROWS>
+__device__ __forceinline__ void chol_trsm_block(double* __restrict__ A, long ld, int k, int i, int h, double* psm) {
+  constexpr int LPR = NT / ROWS;  // lanes per row
   constexpr int CPL = BLK / LPR;  // columns per lane
+  static_assert(LPR >= 1 && LPR <= 32 && CPL * LPR == BLK, "row split must keep a row inside one warp");
   double* Ls = psm;
   double* Xs = psm + BLK * PSTR;
   double* rinv = psm + BLK * PSTR + BLK * QSTR;
-  const int t = threadIdx.x, j0 = BLK * k, i0 = BLK * i;
+  const int t = threadIdx.x, j0 = BLK * k, i0 = BLK * i + ROWS * h;
   for (int e = t; e < BLK * BLK; e += NT) {
     int r = e / BLK, cc = e % BLK;
     Ls[r * PSTR + cc] = A[(long)(j0 + r) * ld + j0 + cc];
+  }
+  for (int e = t; e < ROWS * BLK; e += NT) {
+    int r = e / BLK, cc = e % BLK;
     Xs[r * PSTR + cc] = A[(long)(i0 + r) * ld + j0 + cc];
   }
   // One reciprocal per column, then multiplies: 64 dependent fp64 divides per row were most of this step,
@@ -382,7 +390,7 @@ __device__ __forceinline__ void chol_trsm_block(double* __restrict__ A, long ld,
     for (int m = 0; m < CPL; ++m) Xs[r * PSTR + q0 + m * LPR] = x[m];
   }
   __syncthreads();
-  for (int e = t; e < BLK * BLK; e += NT) {
+  for (int e = t; e < ROWS * BLK; e += NT) {
     int r = e / BLK, cc = e % BLK;
     A[(long)(i0 + r) * ld + j0 + cc] = Xs[r * PSTR + cc];
   }
@@ -487,7 +495,16 @@ __global__ void __launch_bounds__(C::THREADS, 1) chol_coop_kernel(double* __rest
   for (int k = 0; k < nb; ++k) {
     grid.sync();  // L_kk is final
     tick(0);
-    for (int i = k + 1 + blockIdx.x; i < nrb; i += gridDim.x) chol_trsm_block<C::THREADS>(A, ld, k, i, smem);
+    {
+      const int rem = nrb - (k + 1), G = (int)gridDim.x;
+      if (4 * rem <= G && C::THREADS >= 64) {
+        for (int w = blockIdx.x; w < 4 * rem; w += G) chol_trsm_block<C::THREADS, 16>(A, ld, k, k + 1 + w / 4, w % 4, smem);
+      } else if (2 * rem <= G) {
+        for (int w = blockIdx.x; w < 2 * rem; w += G) chol_trsm_block<C::THREADS, 32>(A, ld, k, k + 1 + w / 2, w % 2, smem);
+      } else {
+        for (int i = k + 1 + blockIdx.x; i < nrb; i += G) chol_trsm_block<C::THREADS, 64>(A, ld, k, i, 0, smem);
+      }
+    }
     tick(1);
     grid.sync();  // panel k is final
     tick(2);
