@@ -111,9 +111,9 @@ class NoisyLikelihoodScorer(OracleScorer):
     to `scale` times the bound a real device evaluation reports, with S1 / S2 inflated by the same factor -- i.e. a
     backend that is as wrong as it is allowed to be.  Lets the error-band logic of the sampler run without a GPU."""
 
-    def __init__(self, scale=1.0, seed=0):
+    def __init__(self, scale=1.0, seed=0, extreme=False):
         super().__init__()
-        self.scale, self.rng = float(scale), np.random.RandomState(seed)
+        self.scale, self.rng, self.extreme = float(scale), np.random.RandomState(seed), bool(extreme)
 
     def particle_log_likelihood(self, thetas, prepared, lambda_b, M):
         from scipy.special import gammaln
@@ -128,4 +128,5 @@ class NoisyLikelihoodScorer(OracleScorer):
         s1 = (np.abs(kl) + g + rate).sum(axis=1) * self.scale
         s2 = np.abs(kl - g - rate).sum(axis=1) * self.scale
         bound = E.EPS * (E.C_TERM * s1 + E.c_sum(len(k)) * s2)
-        return ll + self.rng.uniform(-1.0, 1.0, len(ll)) * bound, s1, s2
+        err = np.sign(self.rng.uniform(-1.0, 1.0, len(ll))) if self.extreme else self.rng.uniform(-1.0, 1.0, len(ll))
+        return ll + err * bound, s1, s2
