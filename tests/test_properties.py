@@ -76,3 +76,50 @@ def test_resampling_survives_a_maximally_wrong_backend(seed, n_obs, M, gamma, sc
         np.random.seed(seed % 1000)
         got = E.resample_indices(P, gamma, N, list(obs), list(meas), 1, M, backend, backend.prepare_counts(list(obs), list(meas)))
         assert np.array_equal(want, got) and np.array_equal(after, np.random.uniform(size=2))
+
+
+def _python_growth(tree, mode, ws, step, radius, budget):
+    """The loops of mripp_b200/src/rrt/rrt.py (rrt / rrt_star / rig) on TreeArrays' decision-exact primitives."""
+    from mripp_b200.src.rrt import rrt_utils as U
+    norm = np.linalg.norm
+    travelled = 0
+    while travelled < budget:
+        target = np.random.rand(2) * (ws[1] - ws[0], ws[3] - ws[2]) + (ws[0], ws[2])
+        nn = tree.nearest(target)
+        point = U.steer_point(tree.point(nn), target, step)
+        nb = tree.near(point, radius) if mode else []
+        best = nn
+        if mode == 1:
+            best_cost = tree.path_cost(nn) + norm(tree.point(nn) - point)
+            for q in nb:
+                c = tree.path_cost(q) + norm(tree.point(q) - point)
+                if c < best_cost:
+                    best, best_cost = q, c
+        new = tree.add(point, best)
+        travelled += norm(tree.point(new) - tree.point(best))
+        if mode:
+            tree.rewire(nb, new)
+
+
+@settings(max_examples=20, deadline=None)
+@given(seed=st.integers(0, 2**31 - 1), mode=st.sampled_from([0, 1, 2]), step=st.sampled_from([0.5, 1.0, 2.5]),
+       radius=st.sampled_from([1.0, 2.5, 4.0]), budget=st.sampled_from([0.0, 3.0, 25.0, 60.0]),
+       ws=st.sampled_from([(0, 40, 0, 40), (0, 10, 0, 25), (-5, 5, 2, 4), (0.5, 12.25, 0, 7)]), calls=st.integers(1, 3))
+def test_native_tree_growth_equals_python_primitives(seed, mode, step, radius, budget, ws, calls):
+    from mripp_b200.src.rrt import rrt_utils as U
+    if U.native_norm_variant() is None:
+        return
+    out = []
+    for native in (True, False):
+        np.random.seed(seed % 100000)
+        root = np.array([ws[0] + 0.3 * (ws[1] - ws[0]), ws[2] + 0.6 * (ws[3] - ws[2])])
+        t = U.TreeArrays(root, capacity=4)
+        for _ in range(calls):
+            if native:
+                assert t.grow_native(mode, ws, step, radius, budget, block=16) is not None     # small blocks: many refills
+            else:
+                _python_growth(t, mode, ws, step, radius, budget)
+        out.append((t.points().copy(), t.parent0[: t.n].copy(), t.parent[: t.n].copy(), t.edge[: t.n].copy(), t.nchild[: t.n].copy(),
+                    list(t.rewires), np.random.uniform(size=2)))
+    a, b = out
+    assert all(np.array_equal(x, y) for x, y in zip(a[:5], b[:5])) and a[5] == b[5] and np.array_equal(a[6], b[6])
