@@ -133,6 +133,48 @@ def _resample_indices(particles, gamma, n_samples, obs_wp, obs_vals, lambda_b, M
     return choice_from_draws(w, u)[1]
 
 
+_MVN_DIRECT = None   # None: untested; True / False after the self-check
+
+
+def _mvn_direct_ok() -> bool:
+    """scipy.stats.multivariate_normal.rvs(mean, cov, size) validates its arguments (an eigendecomposition of cov among
+    other things: half of the call at these sizes) and then draws with the global RandomState's own
+    multivariate_normal(mean, cov, size).  Checked once on this scipy / numpy: same values, same RNG position, for a
+    regular, a rank-deficient and an all-zero covariance.  The global stream is restored afterwards."""
+    global _MVN_DIRECT
+    if _MVN_DIRECT is None:
+        saved = np.random.get_state()
+        try:
+            rng = np.random.RandomState(7)
+            ok = True
+            for dim, kind in ((3, "full"), (6, "deficient"), (9, "zero"), (3, "zero")):
+                A = rng.randn(dim, dim if kind == "full" else 2)
+                cov = np.zeros((dim, dim)) if kind == "zero" else np.cov(A @ rng.randn(A.shape[1], 50))
+                mean = rng.uniform(0, 100, dim)
+                np.random.seed(11)
+                a = multivariate_normal.rvs(mean=mean, cov=cov * 0.001, size=40)
+                ra = np.random.uniform(size=2)
+                np.random.seed(11)
+                b = np.random.multivariate_normal(mean, cov * 0.001, 40)
+                rb = np.random.uniform(size=2)
+                ok = ok and a.shape == b.shape and np.array_equal(a, b) and np.array_equal(ra, rb)
+            _MVN_DIRECT = bool(ok)
+        except Exception:
+            _MVN_DIRECT = False
+        finally:
+            np.random.set_state(saved)
+    return _MVN_DIRECT
+
+
+def perturb(mean: np.ndarray, cov: np.ndarray, n_samples: int) -> np.ndarray:
+    """multivariate_normal.rvs(mean=mean, cov=cov, size=n_samples) of estimation.py:122: through scipy, or -- where the
+    self-check has shown it to be the same draw -- straight from numpy's generator.  Anything scipy's validation would
+    reject (non-finite entries, a single sample whose output scipy squeezes) still goes through scipy."""
+    if n_samples > 1 and _mvn_direct_ok() and np.all(np.isfinite(cov)) and np.all(np.isfinite(mean)):
+        return np.random.multivariate_normal(mean, cov, n_samples)
+    return multivariate_normal.rvs(mean=mean, cov=cov, size=n_samples)
+
+
 def importance_sampling_with_progressive_correction(obs_wp, obs_vals, lambda_b: float, M: int, n_samples: int, s_stages: int,
                                                     prior_dist: List, scenario, alpha: float = 0.001, scorer=None,
                                                     prepared=None) -> Tuple[np.ndarray, np.ndarray]:
@@ -146,7 +188,7 @@ def importance_sampling_with_progressive_correction(obs_wp, obs_vals, lambda_b: 
         picked = particles[resample_indices(particles, gamma, n_samples, obs_wp, obs_vals, lambda_b, M, scorer, prepared)]
         mean = np.mean(picked, axis=0)
         cov = np.cov(picked, rowvar=False)
-        moved = multivariate_normal.rvs(mean=mean, cov=cov * alpha, size=n_samples)
+        moved = perturb(mean, cov * alpha, n_samples)
         moved[:, 0] = np.clip(moved[:, 0], ws[0], ws[1])
         moved[:, 1] = np.clip(moved[:, 1], ws[2], ws[3])
         moved[:, 2] = np.clip(moved[:, 2], ir[0], ir[1])
