@@ -150,7 +150,12 @@ def native_norm_variant() -> Optional[int]:
     if _NATIVE["checked"]:
         return _NATIVE["variant"]
     from mripp_b200 import _lib
-    lib = _lib.load()
+    try:
+        lib = _lib.load()
+    except _lib.IppError:
+        # no built library: the Python loops give the same trees (the device paths still refuse to run without it)
+        _NATIVE.update(checked=True, variant=None)
+        return None
     rng = np.random.RandomState(20240711)
     xy = np.ascontiguousarray(rng.standard_normal((4096, 2)) * 10.0 ** rng.uniform(-3, 3, (4096, 1)))
     xy[:64] = rng.uniform(0, 100, (64, 2)) - rng.uniform(0, 100, (64, 2))     # the coordinate differences of a run
