@@ -26,11 +26,12 @@ from scipy.spatial.distance import cdist
 import threading
 
 _norm = np.linalg.norm
-# Two places draw a block of uniforms from the global np.random stream ahead of the decision that consumes them and
-# may put the stream back (TreeArrays.grow_native, estimation.resample_indices).  They hold this lock for that span.
-# The mirror runs its agents one after the other (a legal interleaving of the reference's threads), so nothing else
-# draws from the global stream meanwhile; callers that drive several strategies from their own threads must not share
-# the global RNG across them (the reference has the same nondeterminism there).
+# Two places draw uniforms from the global np.random stream ahead of the decision that consumes them:
+# TreeArrays.grow_native pre-draws a block of samples and puts the stream back to where the reference's loop would
+# have left it; estimation.resample_indices draws the uniforms of RandomState.choice itself.  They hold this lock for
+# that span.  The mirror runs its agents one after the other (a legal interleaving of the reference's threads), so
+# nothing else draws from the global stream meanwhile; callers that drive several strategies from their own threads
+# must not share the global RNG across them (the reference has the same nondeterminism there).
 RNG_SECTION = threading.RLock()
 REL_TIE = 1e-9
 INT64_MIN = np.iinfo(np.int64).min
