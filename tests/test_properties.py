@@ -7,7 +7,7 @@ from mripp_b200 import dist as D
 from mripp_b200.src.estimation import estimation as E
 from tests._doubles import NoisyLikelihoodScorer, OracleScorer
 
-SET = settings(max_examples=60, deadline=None)
+SET = settings(max_examples=60, deadline=None, derandomize=True)
 
 
 @SET
@@ -55,7 +55,7 @@ def test_balanced_row_slabs_is_a_partition(seed, ny, nx, world):
         assert all(hi > lo for lo, hi in b)
 
 
-@settings(max_examples=25, deadline=None)
+@settings(max_examples=25, deadline=None, derandomize=True)
 @given(seed=st.integers(0, 2**31 - 1), n_obs=st.integers(1, 60), M=st.integers(1, 3), gamma=st.sampled_from([0.1, 0.55, 1.0]),
        scale=st.sampled_from([1.0, 1e3, 1e6]), extreme=st.booleans())
 def test_resampling_survives_a_maximally_wrong_backend(seed, n_obs, M, gamma, scale, extreme):
@@ -101,7 +101,7 @@ def _python_growth(tree, mode, ws, step, radius, budget):
             tree.rewire(nb, new)
 
 
-@settings(max_examples=20, deadline=None)
+@settings(max_examples=20, deadline=None, derandomize=True)
 @given(seed=st.integers(0, 2**31 - 1), mode=st.sampled_from([0, 1, 2]), step=st.sampled_from([0.5, 1.0, 2.5]),
        radius=st.sampled_from([1.0, 2.5, 4.0]), budget=st.sampled_from([0.0, 3.0, 25.0, 60.0]),
        ws=st.sampled_from([(0, 40, 0, 40), (0, 10, 0, 25), (-5, 5, 2, 4), (0.5, 12.25, 0, 7)]), calls=st.integers(1, 3))
