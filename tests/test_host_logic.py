@@ -273,3 +273,24 @@ def test_native_growth_equals_python_loops(monkeypatch, gen, budgets, d):
     assert all(np.array_equal(p, q) for p, q in zip(a[9], b[9]))
     if gen != "rrt" and budgets[0] >= 80:
         assert len(a[5]) > 0  # the case exercises rewires
+
+
+def test_main_configuration_helpers(tmp_path):
+    """main.py:16-60 of the reference: configuration loading errors and constructor-argument routing by introspection."""
+    from mripp_b200 import main as M
+
+    with pytest.raises(SystemExit, match="not found"):
+        M.load_configuration(str(tmp_path / "missing.json"))
+    bad = tmp_path / "bad.json"
+    bad.write_text("{not json")
+    with pytest.raises(SystemExit, match="decoding"):
+        M.load_configuration(str(bad))
+    args = {"budget": 50, "num_agents": 2, "beta_t": 3.0, "line_spacing": 4, "unknown_key": 1, "stage_lambda": 0.25}
+    picked = M.get_constructor_args(R.MR_IPP, args)
+    assert picked["budget"] == 50 and picked["num_agents"] == 2 and picked["stage_lambda"] == 0.25 and "unknown_key" not in picked
+    picked_b = M.get_constructor_args(MR_Boustrophedon, args)
+    assert picked_b == {"budget": 50, "num_agents": 2, "line_spacing": 4}
+    cfg = {"scenarios": [{"class": "PointSourceField", "params": {"num_sources": 2, "workspace_size": [12, 8]},
+                          "specific_params": {"1": [3, 4, 500000]}}], "strategies": [], "args": {"seed": 5, "lazy_gp": True}}
+    (sc,) = M.initialize_scenarios(cfg, gp_factory=FastGP)
+    assert sc.workspace_size == (0, 12, 0, 8) and list(sc.sources[0]) == [3, 4, 500000]      # 2-tuple widened; source 1 pinned
