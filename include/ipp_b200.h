@@ -163,7 +163,7 @@ int ipp_grid_metrics(const double* zpred, const double* std, const double* ztrue
  *   out[3i]   = sum_j [ k_j log(rate_ij) - lgam_j - rate_ij ],  rate_ij = max(lambda_b + sum_m A_im / max(d2_ijm, 1e-6), 1e-10)
  *   out[3i+1] = sum_j (|k_j log rate_ij| + |lgam_j| + rate_ij),  out[3i+2] = sum_j |term_ij|   (error-bound sums)
  * counts: the rounded measurements as doubles; lgam: lgamma(counts + 1) from the caller (one per observation,
- * shared by all particles).  rate is bit-identical to the numpy expression (no contraction, numpy's source-axis
+ * shared by all particles); obs_xy must be 16-byte aligned (read as pairs).  rate is bit-identical to the numpy expression (no contraction, numpy's source-axis
  * summation order); M <= 32.  Replaces the per-particle loop of calc_weights, src/estimation/estimation.py:97,
  * over poisson_log_likelihood, src/estimation/estimation.py:15-55. */
 int ipp_poisson_loglik(const double* particles, int N, int M, const double* obs_xy, const double* counts,
