@@ -59,6 +59,34 @@ int ipp_gp_lml_grad(const double* X, const double* y, int n, const double* hyp, 
 int ipp_gp_fit_final(const double* X, const double* y, int n, const double* hyp, double* Kbuf, double* Wbuf,
                      double* Tbuf, double* vbuf, void* stream);
 
+/* ---- batched fit: the optimiser restarts of one fit evaluated together ---------------------------------
+ * The dataflow Cholesky (csrc/ipp_cholq.cuh) executes a TASK PLAN: the list of block tasks (factor / panel solve /
+ * rank-128 tile update) with the flags each one waits for.  ipp_host_chol_plan writes the plan for n observations
+ * into out_host (host ints; *need = its length; out_host == NULL only sizes it); `ctas` = CTAs the kernel will
+ * have resident (it only sets how finely late panel solves are split).  The caller uploads it once per size.
+ * Host function: no device work, no stream. */
+int ipp_host_chol_plan(int n, int ctas, int* out_host, long long capacity, long long* need_host);
+
+/* ints of device scratch (`sched`: dependency flags + queue heads) the dataflow Cholesky needs for R problems. */
+int ipp_chol_sched_ints(int n, int R, long long* out_host);
+
+/* ipp_gp_lml_grad for R independent hyper-parameter vectors at once over the SAME (X, y): problem r uses slot
+ * s = slots[r] (slots == NULL: s = r) of slot-strided buffers -- Kbuf + s * out[3], Wbuf + s * out[4],
+ * Tbuf + s * out[5], vbuf + s * out[6] (ipp_gp_layout) and hyp + 4 s = {c, l, jitter, -}.  One launch sequence; the
+ * factorisations share one persistent kernel and fill each other's dependency stalls.  Per-problem arithmetic does
+ * not depend on R or on the slot.  plan: DEVICE copy of ipp_host_chol_plan; sched: ipp_chol_sched_ints(n, R) ints.
+ * flags: bit 0 = do not hand the critical chain over by hints (measurement aid); bits 8.. = cap on the CTAs of the
+ * factorisation kernel (0: whole GPU).  info = -7777 in the result block: the kernel's watchdog fired.
+ * Replaces the objective evaluations of the n_restarts_optimizer + 1 L-BFGS-B runs of fit (sklearn _gpr.py:302-333),
+ * which are independent once their start points are drawn. */
+int ipp_gp_lml_grad_batch(const double* X, const double* y, int n, const double* hyp, double* Kbuf, double* Wbuf,
+                          double* Tbuf, double* vbuf, const int* slots, int R, int with_grad, const int* plan, int* sched,
+                          int flags, void* stream);
+
+/* ipp_gp_fit_final with the dataflow Cholesky (plan / sched as above; plan == NULL: the cooperative kernel). */
+int ipp_gp_fit_final_plan(const double* X, const double* y, int n, const double* hyp, double* Kbuf, double* Wbuf,
+                          double* Tbuf, double* vbuf, const int* plan, int* sched, int flags, void* stream);
+
 /* ---- GP posterior --------------------------------------------------------------------------
  * mean = y_std * (k*^T alpha) + y_mean ; std = y_std * sqrt(max(0, c - |W k*|^2)) for the flat
  * grid indices [g_begin, g_end) of the nx x ny lattice x = linspace(x0, x1, nx),

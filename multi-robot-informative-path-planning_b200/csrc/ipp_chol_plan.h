@@ -1,0 +1,169 @@
+// Task plan of the dataflow Cholesky (host side, no CUDA): which task touches which blocks, in which queue, and
+// what it waits for.  The device executor (chol_queue_kernel, ipp_cholq.cuh) is generic: it only reads this table.
+//
+// Blocks are 64 x 64 (BLK); block row nb (the "y" row block, rows NP .. NP+63 of the factor buffer) is one more row
+// block, so nrb = nb + 1.  Work is expressed on TILES of TB x TB blocks at absolute positions (TB = 2: 128 x 128 for
+// NP > 1536, TB = 1 otherwise).  Columns are taken in SUPER-PANELS of two block columns (2s, 2s + 1):
+//   F(k)          factor diagonal block k.  It first applies, itself, the panels the bulk has not applied to that block:
+//                 the whole previous super-panel (k even: blocks k-2, k-1) or the panel k-1 (k odd), so that the
+//                 critical chain F(k) -> S(k+1, k) -> F(k+1) never waits for a bulk tile.
+//   S(i, k, h)    panel solve of row block i (part h of `split`) against L_kk.
+//   UC(tile, 2s)  rank-64 update of block column 2s+1 by panel 2s (inside super-panel s).
+//   U2(tile, s)   rank-128 update of a tile right of super-panel s by panels 2s, 2s+1 (one read-modify-write of the
+//                 tile per TWO panels: half the traffic and twice the k depth of a per-panel update).
+// Flags (per problem; all monotone counters): F[k] in {0,1}; S[i] = number of finished solve parts of row block i
+// (cumulative over the panels); A[tile] = number of panels applied to the tile.
+// Queues: F, S and C (UC + the U2 tiles of the column right behind the super-panel, i.e. everything the chain waits
+// for) are claimed in order and ONLY WHEN READY (a CTA never blocks on them); the bulk queue U (the rest of U2) is
+// claimed in order unconditionally and its owner waits for the dependencies -- polling the chain queues meanwhile.
+// Every dependency of a task precedes it in this order of queues, so any set of resident CTAs makes progress.
+#pragma once
+#include <vector>
+
+namespace ipp {
+
+constexpr int PLAN_MAGIC = 0x43485132;
+constexpr int PLAN_HDR = 16;
+constexpr int PLAN_TS = 24;     // ints per task
+constexpr int PLAN_MAXDEP = 6;
+enum { PT_F = 0, PT_S = 1, PT_U = 2 };
+// header slots
+enum { PH_MAGIC = 0, PH_NB, PH_NRB, PH_TB, PH_NFLAGS, PH_NF, PH_NS, PH_NC, PH_NU, PH_OFFF, PH_OFFS, PH_OFFC, PH_OFFU, PH_TS,
+       PH_TOTAL, PH_NTILE };
+// task slots
+enum { TK_TYPE = 0, TK_A, TK_B, TK_C, TK_D, TK_E, TK_F, TK_G, TK_NDEP, TK_DEP0, TK_OUT = TK_DEP0 + 2 * PLAN_MAXDEP, TK_OUTVAL,
+       TK_RSV };
+static_assert(TK_RSV < PLAN_TS, "task record too small");
+
+struct PlanTask {
+  int v[PLAN_TS];
+  PlanTask() {
+    for (int i = 0; i < PLAN_TS; ++i) v[i] = 0;
+    for (int d = 0; d < PLAN_MAXDEP; ++d) v[TK_DEP0 + 2 * d] = -1;
+  }
+  void dep(int idx, int val) {
+    if (val <= 0) return;
+    for (int d = 0; d < v[TK_NDEP]; ++d)
+      if (v[TK_DEP0 + 2 * d] == idx) {
+        if (v[TK_DEP0 + 2 * d + 1] < val) v[TK_DEP0 + 2 * d + 1] = val;
+        return;
+      }
+    const int d = v[TK_NDEP]++;
+    v[TK_DEP0 + 2 * d] = idx;
+    v[TK_DEP0 + 2 * d + 1] = val;
+  }
+};
+
+inline int plan_split(int rem, int ctas) { return (4 * rem <= ctas) ? 4 : (2 * rem <= ctas) ? 2 : 1; }
+
+// Builds the plan for NP = 64 * nb.  Returns the number of ints.
+inline long chol_plan_build(int nb, int tb, int ctas, std::vector<int>& out) {
+  const int nrb = nb + 1;
+  const int tmax = (nrb - 1) / tb;                    // last tile row
+  const int ntile = (tmax + 1) * (tmax + 2) / 2;
+  const int fF = 0, fS = nb, fA = nb + nrb, nflags = nb + nrb + ntile;
+  auto tile_flag = [&](int ti, int tj) { return fA + ti * (ti + 1) / 2 + tj; };
+  std::vector<int> csplit(nb + 1, 0);                 // csplit[k] = solve parts of the panels < k
+  for (int k = 0; k < nb; ++k) csplit[k + 1] = csplit[k] + plan_split(nrb - (k + 1), ctas);
+  std::vector<PlanTask> qF, qS, qC, qU;
+  std::vector<int> s_first(nb, -1);                   // queue index of S(k+1, k, part 0)
+  {
+    int pos = 0;
+    for (int k = 0; k < nb; ++k) {
+      s_first[k] = pos;
+      pos += (nrb - (k + 1)) * plan_split(nrb - (k + 1), ctas);
+    }
+  }
+
+  for (int k = 0; k < nb; ++k) {                      // ---- F
+    PlanTask t;
+    t.v[TK_TYPE] = PT_F;
+    t.v[TK_A] = k;
+    t.v[TK_B] = (k & 1) ? 1 : (k >= 2 ? 2 : 0);       // own update: panels [k - width, k)
+    t.dep(fS + k, csplit[k]);                         // L(k, p) final for every p < k
+    t.dep(tile_flag(k / tb, k / tb), (k & 1) ? k - 1 : k - 2);
+    t.v[TK_G] = s_first[k];                           // hint: the solve on the critical chain comes next
+    t.v[TK_OUT] = fF + k;
+    t.v[TK_OUTVAL] = 1;
+    qF.push_back(t);
+  }
+  for (int k = 0; k < nb; ++k) {                      // ---- S
+    const int split = plan_split(nrb - (k + 1), ctas);
+    for (int i = k + 1; i < nrb; ++i)
+      for (int h = 0; h < split; ++h) {
+        PlanTask t;
+        t.v[TK_TYPE] = PT_S;
+        t.v[TK_A] = i;
+        t.v[TK_B] = k;
+        t.v[TK_C] = h;
+        t.v[TK_D] = 64 / split;
+        t.v[TK_G] = (i == k + 1 && k + 1 < nb) ? k + 1 : -1;   // hint: F(k+1) comes next
+        t.dep(fF + k, 1);
+        t.dep(tile_flag(i / tb, k / tb), k);          // every panel < k applied to block (i, k)
+        t.v[TK_OUT] = fS + i;
+        t.v[TK_OUTVAL] = -1;                          // atomic increment
+        qS.push_back(t);
+      }
+  }
+  auto u_task = [&](int ti, int tj, int kb, int ke, int cmin, int skip, int applied_before) {
+    PlanTask t;
+    t.v[TK_TYPE] = PT_U;
+    t.v[TK_A] = ti;
+    t.v[TK_B] = tj;
+    t.v[TK_C] = kb;
+    t.v[TK_D] = ke;
+    t.v[TK_E] = cmin;
+    t.v[TK_F] = skip;
+    t.dep(tile_flag(ti, tj), applied_before);
+    for (int i = ti * tb; i < (ti + 1) * tb && i < nrb; ++i) t.dep(fS + i, csplit[ke]);   // A operand rows
+    for (int j = tj * tb; j < (tj + 1) * tb && j < nb; ++j)
+      if (j >= cmin) t.dep(fS + j, csplit[ke]);                                           // B operand rows
+    t.v[TK_OUT] = tile_flag(ti, tj);
+    t.v[TK_OUTVAL] = ke;
+    return t;
+  };
+  for (int s = 0; 2 * s < nb; ++s) {
+    const int p0 = 2 * s, p1 = 2 * s + 1;
+    if (p1 < nb) {
+      // UC: column p1 receives panel p0; the diagonal block (p1, p1) is F(p1)'s own
+      const int tj = p1 / tb;
+      for (int ti = tj; ti <= tmax; ++ti) {
+        bool any = false;
+        for (int i = ti * tb; i < (ti + 1) * tb && i < nrb; ++i) any |= (i > p1);
+        if (!any) continue;
+        qC.push_back(u_task(ti, tj, p0, p1, p1, p1, p0));
+      }
+    }
+    const int ke = (p1 < nb) ? p1 + 1 : p1;
+    // U2: tiles whose columns start at or beyond block 2s + 2; block (2s+2, 2s+2) is F(2s+2)'s own
+    const int tj0 = (2 * s + 2 + tb - 1) / tb;
+    for (int tj = tj0; tj <= (nb - 1) / tb; ++tj)
+      for (int ti = tj; ti <= tmax; ++ti) {
+        const int skip = 2 * s + 2;
+        if (tb == 1 && ti == tj && ti == skip) continue;   // the tile IS the skipped block
+        PlanTask t = u_task(ti, tj, p0, ke, tj * tb, skip, p0);
+        (tj < tj0 + 2 / tb ? qC : qU).push_back(t);   // the next super-panel's own columns are on the chain
+      }
+  }
+  out.assign(PLAN_HDR, 0);
+  out[PH_MAGIC] = PLAN_MAGIC;
+  out[PH_NB] = nb;
+  out[PH_NRB] = nrb;
+  out[PH_TB] = tb;
+  out[PH_NFLAGS] = nflags;
+  out[PH_NF] = (int)qF.size();
+  out[PH_NS] = (int)qS.size();
+  out[PH_NC] = (int)qC.size();
+  out[PH_NU] = (int)qU.size();
+  out[PH_TS] = PLAN_TS;
+  out[PH_NTILE] = ntile;
+  const std::vector<PlanTask>* qs[4] = {&qF, &qS, &qC, &qU};
+  for (int q = 0; q < 4; ++q) {
+    out[PH_OFFF + q] = (int)out.size();
+    for (const PlanTask& t : *qs[q]) out.insert(out.end(), t.v, t.v + PLAN_TS);
+  }
+  out[PH_TOTAL] = (int)out.size();
+  return (long)out.size();
+}
+
+}  // namespace ipp

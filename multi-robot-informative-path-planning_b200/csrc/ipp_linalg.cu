@@ -16,6 +16,7 @@
 //   vbuf = vectors + partials      see ipp_gp_layout()
 //   hyp  = {c, l, jitter}          in DEVICE memory so a captured CUDA graph replays for any theta
 #include "ipp_gemm.cuh"
+#include "ipp_chol_plan.h"
 #include "../../include/ipp_b200.h"
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
@@ -45,6 +46,15 @@ __host__ __device__ inline long v_partials_off(const GpDims& d) { return (long)V
 __host__ __device__ inline long v_result_off(const GpDims& d) { return v_partials_off(d) + 2 * d.max_tiles; }
 __host__ __device__ inline long v_total(const GpDims& d) { return v_result_off(d) + 8; }
 
+// A batch of R independent problems of the same size in slot-strided buffers (the optimiser restarts of one fit run
+// in lockstep: one launch sequence evaluates the objective of every restart that is still iterating).  Problem r uses
+// slot slots[r] (r itself when slots is null); hyp is [slot][4].
+struct Bat {
+  const int* slots;
+  long sK, sW, sT, sV;  // slot strides in doubles
+  __device__ __forceinline__ long slot(int r) const { return slots ? (long)slots[r] : (long)r; }
+};
+
 // ---------------------------------------------------------------------------------------------
 // Gram build into the padded factor buffer.  K_ij = c * exp(-0.5 * |x_i/l - x_j/l|^2), exact c on
 // the diagonal (sklearn kernels.py:1561-1565) plus jitter (_gpr.py:589); identity padding; y row.
@@ -52,10 +62,16 @@ __host__ __device__ inline long v_total(const GpDims& d) { return v_result_off(d
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) gram_fit_kernel(const double* __restrict__ X, const double* __restrict__ y,
                                                        const double* __restrict__ hyp, double* __restrict__ K,
-                                                       double* __restrict__ vbuf, GpDims d) {
+                                                       double* __restrict__ vbuf, GpDims d, Bat bat) {
   __shared__ double sx[2][BLK], sy[2][BLK];
   const int bj = blockIdx.x, bi = blockIdx.y;
   const int t = threadIdx.x;
+  {
+    const long slot = bat.slot(blockIdx.z);
+    hyp += 4 * slot;
+    K += slot * bat.sK;
+    vbuf += slot * bat.sV;
+  }
   const double c = hyp[0], l = hyp[1], jit = hyp[2];
   const int i0 = bi * BLK, j0 = bj * BLK;
   if (t < 2 * BLK) {
@@ -357,17 +373,18 @@ __device__ __forceinline__ void chol_trsm_block(double* __restrict__ A, long ld,
   double* Xs = psm + BLK * PSTR;
   double* rinv = psm + BLK * PSTR + BLK * QSTR;
   const int t = threadIdx.x, j0 = BLK * k, i0 = BLK * i + ROWS * h;
+  // (L2 loads: in the dataflow kernel these blocks were written by other CTAs of the same launch)
   for (int e = t; e < BLK * BLK; e += NT) {
     int r = e / BLK, cc = e % BLK;
-    Ls[r * PSTR + cc] = A[(long)(j0 + r) * ld + j0 + cc];
+    Ls[r * PSTR + cc] = __ldcg(A + (long)(j0 + r) * ld + j0 + cc);
   }
   for (int e = t; e < ROWS * BLK; e += NT) {
     int r = e / BLK, cc = e % BLK;
-    Xs[r * PSTR + cc] = A[(long)(i0 + r) * ld + j0 + cc];
+    Xs[r * PSTR + cc] = __ldcg(A + (long)(i0 + r) * ld + j0 + cc);
   }
   // One reciprocal per column, then multiplies: 64 dependent fp64 divides per row were most of this step,
   // and rows of exact zeros (identity padding, the y block) sent every one of them down the divide's slow path.
-  if (t < BLK) rinv[t] = 1.0 / A[(long)(j0 + t) * ld + j0 + t];
+  if (t < BLK) rinv[t] = 1.0 / __ldcg(A + (long)(j0 + t) * ld + j0 + t);
   __syncthreads();
   {
     const int r = t / LPR, q0 = t % LPR, lane = t & 31;
@@ -537,9 +554,11 @@ __global__ void __launch_bounds__(C::THREADS, 1) chol_coop_kernel(double* __rest
 // applied to the identity, X = I L_kk^-T = W_kk^T -- 64 substitution steps with the rows in registers (4 lanes per
 // row, multipliers by shuffle), the same routine as chol_trsm_block; stored transposed.
 __global__ void __launch_bounds__(256) diag_inverse_kernel(const double* __restrict__ L, long ld, double* __restrict__ Winv,
-                                                           long ldw) {
+                                                           long ldw, Bat bat) {
   constexpr int NT = 256, LPR = NT / BLK, CPL = BLK / LPR;
   extern __shared__ double psm[];
+  L += bat.slot(blockIdx.y) * bat.sK;
+  Winv += bat.slot(blockIdx.y) * bat.sW;
   double* Ls = psm;
   double* Xs = psm + BLK * PSTR;
   double* rinv = psm + BLK * PSTR + BLK * QSTR;
@@ -592,8 +611,11 @@ __global__ void __launch_bounds__(256) diag_inverse_kernel(const double* __restr
 template <class C, int STEP>
 __global__ void __launch_bounds__(C::THREADS) trtri_level_kernel(const double* __restrict__ L, long ld,
                                                                  double* __restrict__ W, long ldw, double* __restrict__ T,
-                                                                 long ldt, int nb, int parts, int s) {
+                                                                 long ldt, int nb, int parts, int s, Bat bat) {
   extern __shared__ __align__(16) double smem[];
+  L += bat.slot(blockIdx.y) * bat.sK;
+  W += bat.slot(blockIdx.y) * bat.sW;
+  T += bat.slot(blockIdx.y) * bat.sT;
   // 1-D grid, heaviest tiles first (the hardware hands out CTAs in index order): the k range of a tile is
   // triangular -- STEP 1 sums k in [col0, r1), STEP 2 sums k in [r1, row0 + BM) -- so a plain (x, y) order
   // leaves the longest tiles for the last wave.
@@ -630,9 +652,10 @@ __global__ void __launch_bounds__(C::THREADS) trtri_level_kernel(const double* _
 
 // Zero the strictly-upper blocks of W before the doubling sweep (diagonal 64-blocks come from the
 // diagonal kernel, strictly-lower ones from the sweep); the posterior and trace kernels read them.
-__global__ void __launch_bounds__(256) w_clear_kernel(double* __restrict__ W, long ldw, int np) {
+__global__ void __launch_bounds__(256) w_clear_kernel(double* __restrict__ W, long ldw, int np, Bat bat) {
   const int bi = blockIdx.y, bj = blockIdx.x;
   if (bi >= bj) return;  // strictly-lower blocks are fully rewritten by the sweep
+  W += bat.slot(blockIdx.z) * bat.sW;
   for (int e = threadIdx.x; e < BLK * BLK; e += 256) {
     int r = e / BLK, c = e % BLK;
     W[(long)(bi * BLK + r) * ldw + bj * BLK + c] = 0.0;
@@ -644,8 +667,11 @@ __global__ void __launch_bounds__(256) w_clear_kernel(double* __restrict__ W, lo
 // pull HBM bandwidth); partial sums land in `part` and are combined in a fixed order (deterministic).
 constexpr int GEMV_SPLIT = 16;
 __global__ void __launch_bounds__(256) gemv_wt_kernel(const double* __restrict__ W, long ldw, const double* __restrict__ z,
-                                                      double* __restrict__ part, int np) {
+                                                      double* __restrict__ part, int np, Bat bat) {
   __shared__ double red[4][BLK];
+  W += bat.slot(blockIdx.z) * bat.sW;
+  z += bat.slot(blockIdx.z) * bat.sK;
+  part += bat.slot(blockIdx.z) * bat.sT;
   const int ci = threadIdx.x & 63, kq = threadIdx.x >> 6;
   const int i0 = blockIdx.x * BLK, i = i0 + ci;
   // rows [i0, np) of this strip are non-zero; chunk them evenly over blockIdx.y
@@ -657,7 +683,10 @@ __global__ void __launch_bounds__(256) gemv_wt_kernel(const double* __restrict__
   __syncthreads();
   if (kq == 0) part[(long)blockIdx.y * np + i] = (red[0][ci] + red[1][ci]) + (red[2][ci] + red[3][ci]);
 }
-__global__ void __launch_bounds__(256) gemv_reduce_kernel(const double* __restrict__ part, double* __restrict__ alpha, int np) {
+__global__ void __launch_bounds__(256) gemv_reduce_kernel(const double* __restrict__ part, double* __restrict__ alpha, int np,
+                                                          Bat bat) {
+  part += bat.slot(blockIdx.y) * bat.sT;
+  alpha += bat.slot(blockIdx.y) * bat.sV;
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= np) return;
   double s = 0.0;
@@ -676,9 +705,16 @@ template <class C>
 __global__ void __launch_bounds__(C::THREADS) lml_grad_kernel(const double* __restrict__ W, long ldw,
                                                               const double* __restrict__ vbuf,
                                                               const double* __restrict__ hyp, double* __restrict__ partials,
-                                                              GpDims d) {
+                                                              GpDims d, Bat bat) {
   extern __shared__ __align__(16) double smem[];
   __shared__ double red[2][C::THREADS / 32];
+  {
+    const long slot = bat.slot(blockIdx.y);
+    W += slot * bat.sW;
+    vbuf += slot * bat.sV;
+    partials += slot * bat.sV;
+    hyp += 4 * slot;
+  }
   const int b = blockIdx.x;
   int ti = (int)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
   while ((long)(ti + 1) * (ti + 2) / 2 <= b) ++ti;
@@ -727,9 +763,11 @@ __global__ void __launch_bounds__(C::THREADS) lml_grad_kernel(const double* __re
 
 // result = {lml, dlml/dlog c, dlml/dlog l, info, z.z, sum log diag L}
 __global__ void __launch_bounds__(256) lml_finalize_kernel(const double* __restrict__ K, double* __restrict__ vbuf,
-                                                           int ntiles, int with_grad, GpDims d) {
+                                                           int ntiles, int with_grad, GpDims d, Bat bat) {
   __shared__ double red[4][256];
   const int t = threadIdx.x;
+  K += bat.slot(blockIdx.x) * bat.sK;
+  vbuf += bat.slot(blockIdx.x) * bat.sV;
   const double* z = K + (long)d.np * d.ld;
   double zz = 0.0, sl = 0.0, g0 = 0.0, g1 = 0.0;
   for (int k = t; k < d.n; k += 256) {
@@ -797,6 +835,8 @@ __global__ void copy_row_kernel(const double* __restrict__ src, double* __restri
   if (i < n) dst[i] = src[i];
 }
 
+#include "ipp_cholq.cuh"
+
 // ---------------------------------------------------------------------------------------------
 // Host-side launch sequences
 // ---------------------------------------------------------------------------------------------
@@ -807,92 +847,183 @@ static cudaError_t opt_in_smem(K kernel, size_t bytes) {
 
 static bool use_small_tiles(int np) { return np <= 1536; }
 
-template <class C>
-static int chol_inplace(double* Kb, double* Wb, double* info, const GpDims& d, cudaStream_t st, int max_ctas = 0) {
-  constexpr size_t SYRK_SM = gemm_smem_bytes<C, Lay::KCONT, Lay::KCONT>();
-  constexpr size_t SM = SYRK_SM > PANEL_SMEM ? SYRK_SM : PANEL_SMEM;
-  if (opt_in_smem(chol_coop_kernel<C>, SM) != cudaSuccess) return IPP_ERR_CUDA;
-  int dev = 0, sms = 0, per_sm = 0;
+static const Bat kOne = {nullptr, 0, 0, 0, 0};  // a single problem in slot 0
+
+// How the factorisation is run: the cooperative kernel (grid barriers; one problem) or the dataflow kernel driven by
+// a task plan (any number of problems, ipp_cholq.cuh).
+struct CholRun {
+  const int* plan;  // device copy of ipp_host_chol_plan's table; null = cooperative kernel
+  int* sched;       // ipp_chol_sched_ints(n, R) ints of scratch
+  int use_hints;
+  int max_ctas;
+};
+
+static int device_sms(int* sms) {
+  int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return IPP_ERR_CUDA;
-  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return IPP_ERR_CUDA;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chol_coop_kernel<C>, C::THREADS, SM) != cudaSuccess || per_sm < 1)
+  if (cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return IPP_ERR_CUDA;
+  return IPP_OK;
+}
+
+static long chol_sched_ints(int n, int R) {
+  const GpDims d = gp_dims(n);
+  const int tb = use_small_tiles(d.np) ? 1 : 2;
+  const int nb = d.np / BLK, nrb = nb + 1, tmax = (nrb - 1) / tb;
+  const long nflags = nb + nrb + (long)(tmax + 1) * (tmax + 2) / 2;
+  return (long)R * nflags + 4L * R + 8;
+}
+
+template <class C>
+static int chol_queue_launch(double* Kb, double* vbuf, const GpDims& d, const Bat& bat, int R, const CholRun& run,
+                             cudaStream_t st) {
+  constexpr size_t SYRK_SM = gemm_smem_bytes<C, Lay::KCONT, Lay::KCONT>();
+  constexpr size_t SM = SYRK_SM > FACT_SMEM ? SYRK_SM : FACT_SMEM;
+  if (opt_in_smem(chol_queue_kernel<C>, SM) != cudaSuccess) return IPP_ERR_CUDA;
+  int sms = 0, per_sm = 0;
+  if (device_sms(&sms) != IPP_OK) return IPP_ERR_CUDA;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chol_queue_kernel<C>, C::THREADS, SM) != cudaSuccess || per_sm < 1)
     return IPP_ERR_CUDA;
-  // no more CTAs than the first (largest) trailing update has tiles: grid barriers cost with the grid size
-  const int T0 = (d.rows - BLK + C::BM - 1) / C::BM;
-  int useful = T0 * (T0 + 1) / 2;
-  if (useful < d.rows / BLK) useful = d.rows / BLK;
-  int ctas = sms * per_sm;
-  if (ctas > useful + 1) ctas = useful + 1;  // + the panel CTA
-  if (max_ctas > 1 && ctas > max_ctas) ctas = max_ctas;  // leave SMs to concurrent factorisations (restart streams)
+  // no more CTAs than the widest front has work for: every extra CTA only polls
+  const int T0 = (d.rows + C::BM - 1) / C::BM;
+  long useful = (long)R * ((long)T0 * (T0 + 1) / 2 + d.rows / BLK);
+  long ctas = (long)sms * per_sm;
+  if (ctas > useful) ctas = useful;
+  if (run.max_ctas > 0 && ctas > run.max_ctas) ctas = run.max_ctas;
   if (ctas < 1) ctas = 1;
-  long ld = d.ld;
-  int rows = d.rows, np = d.np;
-  // the tile-partials area of vbuf (free until the gradient kernel runs) receives the phase counters
-  double* phase = (2 * d.max_tiles >= 17) ? info - 3 - 2 * d.max_tiles : nullptr;
-  void* args[] = {(void*)&Kb, (void*)&ld, (void*)&rows, (void*)&np, (void*)&info, (void*)&phase};
-  if (cudaLaunchCooperativeKernel((void*)chol_coop_kernel<C>, dim3(ctas), dim3(C::THREADS), args, SM, st) != cudaSuccess)
-    return IPP_ERR_CUDA;
+  if (cudaMemsetAsync(run.sched, 0, sizeof(int) * chol_sched_ints(d.n, R), st) != cudaSuccess) return IPP_ERR_CUDA;
+  CholQ a;
+  a.K = Kb;
+  a.pstride = bat.sK;
+  a.ld = d.ld;
+  a.rows_total = d.rows;
+  a.np = d.np;
+  a.vbuf = vbuf;
+  a.vstride = bat.sV;
+  a.info_off = v_result_off(d) + 3;
+  a.slots = bat.slots;
+  a.R = R;
+  a.plan = run.plan;
+  a.sched = run.sched;
+  a.timeout = 4000000000LL;  // ~2 s of polling without work: a scheduling bug, not a slow task
+  a.use_hints = run.use_hints;
+  chol_queue_kernel<C><<<(unsigned)ctas, C::THREADS, SM, st>>>(a);
+  return IPP_OK;
+}
+
+template <class C>
+static int chol_inplace(double* Kb, double* Wb, double* vbuf, const GpDims& d, const Bat& bat, int R, const CholRun& run,
+                        cudaStream_t st) {
+  if (run.plan) {
+    if (!run.sched) return IPP_ERR_ARG;
+    const int rc = chol_queue_launch<C>(Kb, vbuf, d, bat, R, run, st);
+    if (rc != IPP_OK) return rc;
+  } else {
+    if (R != 1 || bat.slots) return IPP_ERR_ARG;  // the cooperative kernel factors one problem
+    constexpr size_t SYRK_SM = gemm_smem_bytes<C, Lay::KCONT, Lay::KCONT>();
+    constexpr size_t SM = SYRK_SM > PANEL_SMEM ? SYRK_SM : PANEL_SMEM;
+    if (opt_in_smem(chol_coop_kernel<C>, SM) != cudaSuccess) return IPP_ERR_CUDA;
+    int sms = 0, per_sm = 0;
+    if (device_sms(&sms) != IPP_OK) return IPP_ERR_CUDA;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chol_coop_kernel<C>, C::THREADS, SM) != cudaSuccess || per_sm < 1)
+      return IPP_ERR_CUDA;
+    // no more CTAs than the first (largest) trailing update has tiles: grid barriers cost with the grid size
+    const int T0 = (d.rows - BLK + C::BM - 1) / C::BM;
+    int useful = T0 * (T0 + 1) / 2;
+    if (useful < d.rows / BLK) useful = d.rows / BLK;
+    int ctas = sms * per_sm;
+    if (ctas > useful + 1) ctas = useful + 1;  // + the panel CTA
+    if (run.max_ctas > 1 && ctas > run.max_ctas) ctas = run.max_ctas;  // leave SMs to concurrent factorisations
+    if (ctas < 1) ctas = 1;
+    long ld = d.ld;
+    int rows = d.rows, np = d.np;
+    double* info = vbuf + v_result_off(d) + 3;
+    double* phase = nullptr;  // CTA 0 / 1 cycle counters: a debugging aid, off in the product
+    void* args[] = {(void*)&Kb, (void*)&ld, (void*)&rows, (void*)&np, (void*)&info, (void*)&phase};
+    if (cudaLaunchCooperativeKernel((void*)chol_coop_kernel<C>, dim3(ctas), dim3(C::THREADS), args, SM, st) != cudaSuccess)
+      return IPP_ERR_CUDA;
+  }
   if (Wb) {
     if (opt_in_smem(diag_inverse_kernel, PANEL_SMEM) != cudaSuccess) return IPP_ERR_CUDA;
-    diag_inverse_kernel<<<d.np / BLK, 256, PANEL_SMEM, st>>>(Kb, d.ld, Wb, d.ld);
+    diag_inverse_kernel<<<dim3(d.np / BLK, R), 256, PANEL_SMEM, st>>>(Kb, d.ld, Wb, d.ld, bat);
   }
   return IPP_OK;
 }
 
 template <class C>
-static int trtri_level(const double* Kb, double* Wb, double* Tb, const GpDims& d, int parts, int s, cudaStream_t st) {
+static int trtri_level(const double* Kb, double* Wb, double* Tb, const GpDims& d, int parts, int s, const Bat& bat, int R,
+                       cudaStream_t st) {
   constexpr size_t SM = gemm_smem_bytes<C, Lay::KCONT, Lay::MCONT>();
   if (opt_in_smem(trtri_level_kernel<C, 1>, SM) != cudaSuccess) return IPP_ERR_CUDA;
   if (opt_in_smem(trtri_level_kernel<C, 2>, SM) != cudaSuccess) return IPP_ERR_CUDA;
   const unsigned grid = (unsigned)(((s + C::BN - 1) / C::BN) * ((s + C::BM - 1) / C::BM) * (parts / 2));
-  trtri_level_kernel<C, 1><<<grid, C::THREADS, SM, st>>>(Kb, d.ld, Wb, d.ld, Tb, d.ld, d.np / BLK, parts, s);
-  trtri_level_kernel<C, 2><<<grid, C::THREADS, SM, st>>>(Kb, d.ld, Wb, d.ld, Tb, d.ld, d.np / BLK, parts, s);
+  trtri_level_kernel<C, 1><<<dim3(grid, R), C::THREADS, SM, st>>>(Kb, d.ld, Wb, d.ld, Tb, d.ld, d.np / BLK, parts, s, bat);
+  trtri_level_kernel<C, 2><<<dim3(grid, R), C::THREADS, SM, st>>>(Kb, d.ld, Wb, d.ld, Tb, d.ld, d.np / BLK, parts, s, bat);
   return IPP_OK;
 }
 
 template <class C>
-static int trtri_inplace(const double* Kb, double* Wb, double* Tb, const GpDims& d, cudaStream_t st) {
+static int trtri_inplace(const double* Kb, double* Wb, double* Tb, const GpDims& d, const Bat& bat, int R, cudaStream_t st) {
   const int nb = d.np / BLK;
-  w_clear_kernel<<<dim3(nb, nb), 256, 0, st>>>(Wb, d.ld, d.np);
+  w_clear_kernel<<<dim3(nb, nb, R), 256, 0, st>>>(Wb, d.ld, d.np, bat);
   int parts = 1;
   while (parts < nb) parts *= 2;
   for (; parts >= 2; parts /= 2) {  // finest level first
     const int s = BLK * ((nb + parts - 1) / parts);  // the largest half at this level
     const int pairs = nb < parts ? (nb + 1) / 2 : parts / 2;  // pairs with something to merge (finest level: ~nb / 2)
     // levels whose 128x128 tiling cannot fill the GPU run on 64x64 tiles (4x the CTAs, each a quarter of the work)
-    const int tiles128 = ((s + 127) / 128) * ((s + 127) / 128) * pairs;
-    const int rc = (C::BM > 64 && tiles128 < 2 * 148) ? trtri_level<Cfg64>(Kb, Wb, Tb, d, parts, s, st)
-                                                  : trtri_level<C>(Kb, Wb, Tb, d, parts, s, st);
+    const int tiles128 = ((s + 127) / 128) * ((s + 127) / 128) * pairs * R;
+    const int rc = (C::BM > 64 && tiles128 < 2 * 148) ? trtri_level<Cfg64>(Kb, Wb, Tb, d, parts, s, bat, R, st)
+                                                  : trtri_level<C>(Kb, Wb, Tb, d, parts, s, bat, R, st);
     if (rc != IPP_OK) return rc;
   }
   return IPP_OK;
 }
 
 template <class C>
-static int lml_grad_launch(const double* Wb, double* vbuf, const double* hyp, const GpDims& d, int* ntiles,
-                           cudaStream_t st) {
+static int lml_grad_launch(const double* Wb, double* vbuf, const double* hyp, const GpDims& d, int* ntiles, const Bat& bat,
+                           int R, cudaStream_t st) {
   constexpr size_t SM = gemm_smem_bytes<C, Lay::MCONT, Lay::MCONT>();
   if (opt_in_smem(lml_grad_kernel<C>, SM) != cudaSuccess) return IPP_ERR_CUDA;
   const int T = (d.np + C::BM - 1) / C::BM;
   *ntiles = T * (T + 1) / 2;
-  lml_grad_kernel<C><<<*ntiles, C::THREADS, SM, st>>>(Wb, d.ld, vbuf, hyp, vbuf + v_partials_off(d), d);
+  lml_grad_kernel<C><<<dim3(*ntiles, R), C::THREADS, SM, st>>>(Wb, d.ld, vbuf, hyp, vbuf + v_partials_off(d), d, bat);
   return IPP_OK;
 }
 
 static int gp_factor(const double* X, const double* y, int n, const double* hyp, double* Kb, double* Wb, double* Tb,
-                     double* vbuf, bool invert, cudaStream_t st, int max_ctas) {
-  if (n <= 0 || !X || !y || !hyp || !Kb || !Wb || !vbuf) return IPP_ERR_ARG;
+                     double* vbuf, bool invert, const Bat& bat, int R, const CholRun& run, cudaStream_t st) {
+  if (n <= 0 || R <= 0 || !X || !y || !hyp || !Kb || !Wb || !vbuf) return IPP_ERR_ARG;
   const GpDims d = gp_dims(n);
-  gram_fit_kernel<<<dim3(d.np / BLK, d.rows / BLK), 256, 0, st>>>(X, y, hyp, Kb, vbuf, d);
-  double* info = vbuf + v_result_off(d) + 3;
-  int rc = use_small_tiles(d.np) ? chol_inplace<Cfg64>(Kb, Wb, info, d, st, max_ctas)
-                                 : chol_inplace<Cfg128>(Kb, Wb, info, d, st, max_ctas);
+  gram_fit_kernel<<<dim3(d.np / BLK, d.rows / BLK, R), 256, 0, st>>>(X, y, hyp, Kb, vbuf, d, bat);
+  int rc = use_small_tiles(d.np) ? chol_inplace<Cfg64>(Kb, Wb, vbuf, d, bat, R, run, st)
+                                 : chol_inplace<Cfg128>(Kb, Wb, vbuf, d, bat, R, run, st);
   if (rc != IPP_OK) return rc;
   if (invert) {
     if (!Tb) return IPP_ERR_ARG;
-    rc = use_small_tiles(d.np) ? trtri_inplace<Cfg64>(Kb, Wb, Tb, d, st) : trtri_inplace<Cfg128>(Kb, Wb, Tb, d, st);
+    rc = use_small_tiles(d.np) ? trtri_inplace<Cfg64>(Kb, Wb, Tb, d, bat, R, st) : trtri_inplace<Cfg128>(Kb, Wb, Tb, d, bat, R, st);
     if (rc != IPP_OK) return rc;
   }
+  IPP_LAUNCH_CHECK();
+  return IPP_OK;
+}
+
+// One LML (+ gradient) evaluation of each of the R problems of a batch.
+static int gp_lml_grad_run(const double* X, const double* y, int n, const double* hyp, double* Kbuf, double* Wbuf,
+                           double* Tbuf, double* vbuf, int with_grad, const Bat& bat, int R, const CholRun& run,
+                           cudaStream_t st) {
+  int rc = gp_factor(X, y, n, hyp, Kbuf, Wbuf, Tbuf, vbuf, with_grad != 0, bat, R, run, st);
+  if (rc != IPP_OK) return rc;
+  const GpDims d = gp_dims(n);
+  int ntiles = 0;
+  if (with_grad) {
+    // partials go to Tbuf, which the triangular inverse is done with
+    gemv_wt_kernel<<<dim3(d.np / BLK, GEMV_SPLIT, R), 256, 0, st>>>(Wbuf, d.ld, Kbuf + (long)d.np * d.ld, Tbuf, d.np, bat);
+    gemv_reduce_kernel<<<dim3((d.np + 255) / 256, R), 256, 0, st>>>(Tbuf, vbuf + V_ALPHA * d.npv, d.np, bat);
+    rc = use_small_tiles(d.np) ? lml_grad_launch<Cfg64>(Wbuf, vbuf, hyp, d, &ntiles, bat, R, st)
+                               : lml_grad_launch<Cfg128>(Wbuf, vbuf, hyp, d, &ntiles, bat, R, st);
+    if (rc != IPP_OK) return rc;
+  }
+  lml_finalize_kernel<<<R, 256, 0, st>>>(Kbuf, vbuf, ntiles, with_grad, d, bat);
   IPP_LAUNCH_CHECK();
   return IPP_OK;
 }
@@ -1017,28 +1148,42 @@ int ipp_gram_rbf(const double* X, int n, const double* Y, int m, double c, doubl
 
 int ipp_gp_lml_grad(const double* X, const double* y, int n, const double* hyp, double* Kbuf, double* Wbuf,
                     double* Tbuf, double* vbuf, int with_grad, int max_ctas, void* stream) {
-  cudaStream_t st = (cudaStream_t)stream;
-  int rc = gp_factor(X, y, n, hyp, Kbuf, Wbuf, Tbuf, vbuf, with_grad != 0, st, max_ctas);
-  if (rc != IPP_OK) return rc;
+  const CholRun run = {nullptr, nullptr, 0, max_ctas};
+  return gp_lml_grad_run(X, y, n, hyp, Kbuf, Wbuf, Tbuf, vbuf, with_grad, kOne, 1, run, (cudaStream_t)stream);
+}
+
+int ipp_host_chol_plan(int n, int ctas, int* out_host, long long capacity, long long* need) {
+  if (n <= 0 || !need) return IPP_ERR_ARG;
   const GpDims d = gp_dims(n);
-  int ntiles = 0;
-  if (with_grad) {
-    // partials go to Tbuf, which the triangular inverse is done with
-    gemv_wt_kernel<<<dim3(d.np / BLK, GEMV_SPLIT), 256, 0, st>>>(Wbuf, d.ld, Kbuf + (long)d.np * d.ld, Tbuf, d.np);
-    gemv_reduce_kernel<<<(d.np + 255) / 256, 256, 0, st>>>(Tbuf, vbuf + V_ALPHA * d.npv, d.np);
-    rc = use_small_tiles(d.np) ? lml_grad_launch<Cfg64>(Wbuf, vbuf, hyp, d, &ntiles, st)
-                               : lml_grad_launch<Cfg128>(Wbuf, vbuf, hyp, d, &ntiles, st);
-    if (rc != IPP_OK) return rc;
+  std::vector<int> plan;
+  chol_plan_build(d.np / BLK, use_small_tiles(d.np) ? 1 : 2, ctas > 0 ? ctas : 148, plan);
+  *need = (long long)plan.size();
+  if (out_host) {
+    if (capacity < (long long)plan.size()) return IPP_ERR_ARG;
+    for (size_t i = 0; i < plan.size(); ++i) out_host[i] = plan[i];
   }
-  lml_finalize_kernel<<<1, 256, 0, st>>>(Kbuf, vbuf, ntiles, with_grad, d);
-  IPP_LAUNCH_CHECK();
   return IPP_OK;
 }
 
-int ipp_gp_fit_final(const double* X, const double* y, int n, const double* hyp, double* Kbuf, double* Wbuf,
-                     double* Tbuf, double* vbuf, void* stream) {
-  cudaStream_t st = (cudaStream_t)stream;
-  int rc = gp_factor(X, y, n, hyp, Kbuf, Wbuf, Tbuf, vbuf, true, st, 0);
+int ipp_chol_sched_ints(int n, int R, long long* out) {
+  if (n <= 0 || R <= 0 || !out) return IPP_ERR_ARG;
+  *out = chol_sched_ints(n, R);
+  return IPP_OK;
+}
+
+int ipp_gp_lml_grad_batch(const double* X, const double* y, int n, const double* hyp, double* Kbuf, double* Wbuf,
+                          double* Tbuf, double* vbuf, const int* slots, int R, int with_grad, const int* plan, int* sched,
+                          int flags, void* stream) {
+  if (R <= 0 || !plan || !sched) return IPP_ERR_ARG;
+  const GpDims d = gp_dims(n > 0 ? n : 1);
+  const Bat bat = {slots, (long)d.rows * d.ld, (long)d.np * d.ld, (long)d.np * d.ld, v_total(d)};
+  const CholRun run = {plan, sched, (flags & 1) ? 0 : 1, flags >> 8};
+  return gp_lml_grad_run(X, y, n, hyp, Kbuf, Wbuf, Tbuf, vbuf, with_grad, bat, R, run, (cudaStream_t)stream);
+}
+
+static int gp_fit_final_run(const double* X, const double* y, int n, const double* hyp, double* Kbuf, double* Wbuf,
+                            double* Tbuf, double* vbuf, const CholRun& run, cudaStream_t st) {
+  int rc = gp_factor(X, y, n, hyp, Kbuf, Wbuf, Tbuf, vbuf, true, kOne, 1, run, st);
   if (rc != IPP_OK) return rc;
   const GpDims d = gp_dims(n);
   double* w = vbuf + V_W * d.npv;
@@ -1046,9 +1191,21 @@ int ipp_gp_fit_final(const double* X, const double* y, int n, const double* hyp,
   copy_row_kernel<<<(d.np + 255) / 256, 256, 0, st>>>(Kbuf + (long)d.np * d.ld, w, d.np);
   for (int b = d.np / BLK - 1; b >= 0; --b)
     backsub_step_kernel<<<b + 1, BLK, 0, st>>>(Kbuf, d.ld, w, alpha, b);
-  lml_finalize_kernel<<<1, 256, 0, st>>>(Kbuf, vbuf, 0, 0, d);
+  lml_finalize_kernel<<<1, 256, 0, st>>>(Kbuf, vbuf, 0, 0, d, kOne);
   IPP_LAUNCH_CHECK();
   return IPP_OK;
+}
+
+int ipp_gp_fit_final(const double* X, const double* y, int n, const double* hyp, double* Kbuf, double* Wbuf,
+                     double* Tbuf, double* vbuf, void* stream) {
+  const CholRun run = {nullptr, nullptr, 0, 0};
+  return gp_fit_final_run(X, y, n, hyp, Kbuf, Wbuf, Tbuf, vbuf, run, (cudaStream_t)stream);
+}
+
+int ipp_gp_fit_final_plan(const double* X, const double* y, int n, const double* hyp, double* Kbuf, double* Wbuf,
+                          double* Tbuf, double* vbuf, const int* plan, int* sched, int flags, void* stream) {
+  const CholRun run = {plan, plan ? sched : nullptr, (flags & 1) ? 0 : 1, 0};
+  return gp_fit_final_run(X, y, n, hyp, Kbuf, Wbuf, Tbuf, vbuf, run, (cudaStream_t)stream);
 }
 
 /* result block (vbuf + out[8] of ipp_gp_layout(min(L, na))): [5] = 0.5 * log det(I + beta K K^T), [3] = info */
@@ -1065,10 +1222,11 @@ int ipp_mi_logdet(const double* leaf_xy, int L, const double* obs_xy, int na, do
   int rc = use_small_tiles(d.np) ? mi_build<Cfg64>(Gtmp, nap, Lp, nap, trans, beta, Kbuf, d, st)
                                  : mi_build<Cfg128>(Gtmp, nap, Lp, nap, trans, beta, Kbuf, d, st);
   if (rc != IPP_OK) return rc;
-  double* info = vbuf + v_result_off(d) + 3;
-  rc = use_small_tiles(d.np) ? chol_inplace<Cfg64>(Kbuf, Wbuf, info, d, st) : chol_inplace<Cfg128>(Kbuf, Wbuf, info, d, st);
+  const CholRun run = {nullptr, nullptr, 0, 0};
+  rc = use_small_tiles(d.np) ? chol_inplace<Cfg64>(Kbuf, Wbuf, vbuf, d, kOne, 1, run, st)
+                             : chol_inplace<Cfg128>(Kbuf, Wbuf, vbuf, d, kOne, 1, run, st);
   if (rc != IPP_OK) return rc;
-  lml_finalize_kernel<<<1, 256, 0, st>>>(Kbuf, vbuf, 0, 0, d);
+  lml_finalize_kernel<<<1, 256, 0, st>>>(Kbuf, vbuf, 0, 0, d, kOne);
   IPP_LAUNCH_CHECK();
   return IPP_OK;
 }

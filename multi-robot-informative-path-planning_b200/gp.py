@@ -17,6 +17,7 @@ buffers and the stream.  No CPU fallback.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import threading
 import warnings
 
@@ -26,6 +27,12 @@ from scipy.optimize import minimize
 from . import _lib
 
 __all__ = ["ConstantRBFKernel", "ConstantKernel", "RBF", "GaussianProcessRegressor"]
+
+
+def _check_watchdog(info):
+    if info == -7777.0:
+        raise _lib.IppError("dataflow Cholesky: a CTA found no runnable task for ~2 s (scheduling fault); "
+                            "set IPP_CHOL=coop to use the cooperative kernel")
 
 
 # ------------------------------------------------------------------------------------------
@@ -236,29 +243,72 @@ def gram_device(X, Y, c, l, jitter=0.0):
 # ------------------------------------------------------------------------------------------
 # device workspace of one fitted GP
 # ------------------------------------------------------------------------------------------
+def chol_mode():
+    """'queue' (default): the dataflow Cholesky driven by a task plan (csrc/ipp_cholq.cuh); 'coop': the cooperative
+    kernel with grid barriers (one problem per launch; kept for A/B measurements).  IPP_CHOL overrides."""
+    return os.environ.get("IPP_CHOL", "queue")
+
+
+_PLANS = {}
+_PLAN_LOCK = threading.Lock()
+
+
+def chol_plan(n):
+    """Device copy of the task plan for n observations (depends on NP and the SM count only; cached)."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    dev = torch.cuda.current_device()
+    NP = (int(n) + 63) // 64 * 64
+    with _PLAN_LOCK:
+        plan = _PLANS.get((dev, NP))
+        if plan is None:
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            ctas = sms * (2 if NP <= 1536 else 1)  # resident CTAs of the kernel (64x64-tile variant: two per SM)
+            need = C.c_longlong(0)
+            _lib.check(lib.ipp_host_chol_plan(int(n), ctas, None, 0, C.byref(need)), "ipp_host_chol_plan")
+            host = torch.empty(need.value, dtype=torch.int32).pin_memory()
+            _lib.check(lib.ipp_host_chol_plan(int(n), ctas, C.cast(host.data_ptr(), C.POINTER(C.c_int)), need.value,
+                                              C.byref(need)), "ipp_host_chol_plan")
+            plan = host.cuda()
+            _PLANS[(dev, NP)] = plan
+    return plan
+
+
 class _Workspace:
-    """Caller-owned device buffers of the C ABI (ipp_gp_layout), reused while NP does not change."""
+    """Caller-owned device buffers of the C ABI (ipp_gp_layout), reused while NP does not change.  `slots` > 1:
+    one buffer set per optimiser restart, slot-strided (ipp_gp_lml_grad_batch)."""
 
     def __init__(self):
         self.np_ = -1
+        self.slots = 0
 
-    def ensure(self, n):
+    def ensure(self, n, slots=1):
         torch = _lib.require_cuda()
         lib = _lib.load()
         lay = (C.c_longlong * 10)()
         _lib.check(lib.ipp_gp_layout(int(n), lay), "ipp_gp_layout")
         self.layout = [int(v) for v in lay]
         NP = self.layout[0]
-        if NP != self.np_:
+        if NP != self.np_ or slots > self.slots:
             dev = torch.device("cuda")
-            self.K = torch.empty(self.layout[3], dtype=torch.float64, device=dev)
-            self.W = torch.empty(self.layout[4], dtype=torch.float64, device=dev)
-            self.T = torch.empty(self.layout[5], dtype=torch.float64, device=dev)
-            self.v = torch.zeros(self.layout[6], dtype=torch.float64, device=dev)
-            self.hyp = torch.empty(3, dtype=torch.float64, device=dev)
-            self.hyp_host = torch.empty(3, dtype=torch.float64).pin_memory()
-            self.res_host = torch.empty(8, dtype=torch.float64).pin_memory()
+            S = int(slots)
+            self.K = self.W = self.T = self.v = None  # release before allocating the new set
+            self.K = torch.empty(S * self.layout[3], dtype=torch.float64, device=dev)
+            self.W = torch.empty(S * self.layout[4], dtype=torch.float64, device=dev)
+            self.T = torch.empty(S * self.layout[5], dtype=torch.float64, device=dev)
+            self.v = torch.zeros(S * self.layout[6], dtype=torch.float64, device=dev)
+            self.hyp = torch.zeros(4 * S, dtype=torch.float64, device=dev)
+            self.hyp_host = torch.zeros(4 * S, dtype=torch.float64).pin_memory()
+            self.res_host = torch.empty(8 * S, dtype=torch.float64).pin_memory()
+            self.res_dev = torch.empty(8 * S, dtype=torch.float64, device=dev)
+            self.slot_ids = torch.zeros(S, dtype=torch.int32, device=dev)
+            self.slot_ids_host = torch.zeros(S, dtype=torch.int32).pin_memory()
+            need = C.c_longlong(0)
+            _lib.check(lib.ipp_chol_sched_ints(int(n), S, C.byref(need)), "ipp_chol_sched_ints")
+            self.sched = torch.zeros(need.value, dtype=torch.int32, device=dev)
             self.np_ = NP
+            self.slots = S
+        self.plan = chol_plan(n) if chol_mode() == "queue" else None
         return self
 
     @property
@@ -308,6 +358,7 @@ class GaussianProcessRegressor:
         self.skip_below = 1e-30
         self.cluster_order = "maximin"  # order of the spatial clusters in the sparse state (see clustered_order)
         self._scratch = None
+        self._batch_ws = None
         self.n_lml_evals_ = 0
         self.lazy = False
         self._pending = False
@@ -347,18 +398,56 @@ class GaussianProcessRegressor:
         ws.hyp_host[2] = self.alpha
         ws.hyp.copy_(ws.hyp_host, non_blocking=True)
         st = _lib.stream_ptr()
+        flags = 1 if os.environ.get("IPP_CHOL_HINTS", "1") == "0" else 0
         if final:
             Xf, yf = (self._Xd_fit, self._yd_fit) if final == "morton" else (self._Xd, self._yd)
-            rc = lib.ipp_gp_fit_final(_lib.ptr(Xf), _lib.ptr(yf), n, _lib.ptr(ws.hyp), _lib.ptr(ws.K),
-                                      _lib.ptr(ws.W), _lib.ptr(ws.T), _lib.ptr(ws.v), st)
-            _lib.check(rc, "ipp_gp_fit_final")
+            rc = lib.ipp_gp_fit_final_plan(_lib.ptr(Xf), _lib.ptr(yf), n, _lib.ptr(ws.hyp), _lib.ptr(ws.K),
+                                           _lib.ptr(ws.W), _lib.ptr(ws.T), _lib.ptr(ws.v), _lib.ptr(ws.plan),
+                                           _lib.ptr(ws.sched), flags, st)
+            _lib.check(rc, "ipp_gp_fit_final_plan")
+        elif ws.plan is not None:
+            rc = lib.ipp_gp_lml_grad_batch(_lib.ptr(self._Xd), _lib.ptr(self._yd), n, _lib.ptr(ws.hyp), _lib.ptr(ws.K),
+                                           _lib.ptr(ws.W), _lib.ptr(ws.T), _lib.ptr(ws.v), None, 1, 1 if with_grad else 0,
+                                           _lib.ptr(ws.plan), _lib.ptr(ws.sched), flags | (int(max_ctas) << 8), st)
+            _lib.check(rc, "ipp_gp_lml_grad_batch")
         else:
             rc = lib.ipp_gp_lml_grad(_lib.ptr(self._Xd), _lib.ptr(self._yd), n, _lib.ptr(ws.hyp), _lib.ptr(ws.K),
                                      _lib.ptr(ws.W), _lib.ptr(ws.T), _lib.ptr(ws.v), 1 if with_grad else 0, int(max_ctas), st)
             _lib.check(rc, "ipp_gp_lml_grad")
-        ws.res_host.copy_(ws.result, non_blocking=True)
+        ws.res_host[:8].copy_(ws.result, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        return ws.res_host.numpy().copy()
+        res = ws.res_host[:8].numpy().copy()
+        _check_watchdog(res[3])
+        return res
+
+    def _eval_batch(self, ws, batch, thetas, with_grad):
+        """One LML (+ gradient) evaluation of every restart in `batch` (slot ids) as ONE launch sequence
+        (ipp_gp_lml_grad_batch); returns the 8-double result block of each."""
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        n = self.X_train_.shape[0]
+        R = len(batch)
+        hh = ws.hyp_host.numpy()
+        for slot, th in zip(batch, thetas):
+            hh[4 * slot:4 * slot + 3] = (float(np.exp(th[0])), float(np.exp(th[1])), self.alpha)
+        ws.slot_ids_host.numpy()[:R] = batch
+        ws.hyp.copy_(ws.hyp_host, non_blocking=True)
+        ws.slot_ids.copy_(ws.slot_ids_host, non_blocking=True)
+        flags = 1 if os.environ.get("IPP_CHOL_HINTS", "1") == "0" else 0
+        rc = lib.ipp_gp_lml_grad_batch(_lib.ptr(self._Xd), _lib.ptr(self._yd), n, _lib.ptr(ws.hyp), _lib.ptr(ws.K),
+                                       _lib.ptr(ws.W), _lib.ptr(ws.T), _lib.ptr(ws.v), _lib.ptr(ws.slot_ids), R,
+                                       1 if with_grad else 0, _lib.ptr(ws.plan), _lib.ptr(ws.sched), flags, _lib.stream_ptr())
+        _lib.check(rc, "ipp_gp_lml_grad_batch")
+        off, vt, S = ws.layout[8], ws.layout[6], ws.slots
+        torch.index_select(ws.v.view(S, vt)[:, off:off + 8], 0, ws.slot_ids[:R].long(), out=ws.res_dev.view(S, 8)[:R])
+        ws.res_host[:8 * R].copy_(ws.res_dev[:8 * R], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        res = ws.res_host[:8 * R].numpy().reshape(R, 8).copy()
+        for row in res:
+            _check_watchdog(row[3])
+        with self._count_lock:
+            self.n_lml_evals_ += R
+        return res
 
     # -- sklearn API ---------------------------------------------------------------------------
     def log_marginal_likelihood(self, theta=None, eval_gradient=False, clone_kernel=True):
@@ -459,6 +548,8 @@ class GaussianProcessRegressor:
             bounds = self._kernel_fitted.bounds
 
             def optimise(starts):
+                if len(starts) > 1 and self.restart_streams is None and chol_mode() == "queue":
+                    return self._optimise_lockstep(starts, bounds)
                 workers = self._restart_workers(len(starts))
                 if workers > 1:
                     return self._optimise_concurrently(starts, bounds, workers)
@@ -485,6 +576,74 @@ class GaussianProcessRegressor:
         if self.restart_streams is not None:
             return max(1, min(int(self.restart_streams), n_starts))
         return min(n_starts, 6 if self._ws.layout[0] <= 2048 else 3)  # measured best on a B200 (tools/fit_tune.py)
+
+    def _optimise_lockstep(self, starts, bounds):
+        """The restarts of _gpr.py:312-333 in lockstep: every L-BFGS-B run lives in its own host thread, and whenever
+        each run that is still iterating has asked for its next objective value, ONE batched launch sequence
+        (ipp_gp_lml_grad_batch) evaluates them all -- the dataflow Cholesky interleaves the factorisations, so the
+        dependency chain of one fills the idle SMs of the others.  Each run sees exactly the values it would see
+        alone (per-problem arithmetic does not depend on the batch), so optima, evaluation counts and the
+        first-minimum choice are those of the serial loop."""
+        torch = _lib.require_cuda()
+        n = self.X_train_.shape[0]
+        R = len(starts)
+        if self._batch_ws is None:
+            self._batch_ws = _Workspace()
+        ws = self._batch_ws.ensure(n, slots=R)
+        device = torch.cuda.current_device()
+        stream = torch.cuda.current_stream()
+        cond = threading.Condition()
+        requests, results, live, outs, errors = {}, {}, set(range(R)), [None] * R, []
+
+        def run(i):
+            def obj_func(theta, eval_gradient=True):
+                with cond:
+                    requests[i] = (np.array(theta, dtype=float), bool(eval_gradient))
+                    cond.notify_all()
+                    while i not in results:
+                        cond.wait()
+                    res = results.pop(i)
+                if isinstance(res, BaseException):
+                    raise res
+                bad = res[3] != 0.0 or not np.isfinite(res[0])
+                if eval_gradient:
+                    return (np.inf, np.zeros_like(theta)) if bad else (-float(res[0]), -np.array([res[1], res[2]]))
+                return np.inf if bad else -float(res[0])
+
+            try:
+                outs[i] = self._constrained_optimization(obj_func, starts[i], bounds)
+            except BaseException as e:  # noqa: BLE001 -- re-raised by the coordinating thread
+                errors.append(e)
+            finally:
+                with cond:
+                    live.discard(i)
+                    cond.notify_all()
+
+        threads = [threading.Thread(target=run, args=(i,), daemon=True) for i in range(R)]
+        for th in threads:
+            th.start()
+        while True:
+            with cond:
+                while live and len(requests) < len(live):
+                    cond.wait()
+                if not live:
+                    break
+                batch = sorted(requests)
+                reqs = [requests.pop(i) for i in batch]
+            try:
+                with torch.cuda.device(device), torch.cuda.stream(stream):
+                    res = self._eval_batch(ws, batch, [r[0] for r in reqs], any(r[1] for r in reqs))
+                out = {i: res[j] for j, i in enumerate(batch)}
+            except BaseException as e:  # noqa: BLE001 -- hand the failure to every waiting run
+                out = {i: e for i in batch}
+            with cond:
+                results.update(out)
+                cond.notify_all()
+        for th in threads:
+            th.join()
+        if errors:
+            raise errors[0]
+        return outs
 
     def _optimise_concurrently(self, starts, bounds, workers):
         """The restarts of _gpr.py:312-333 side by side: one host thread, one CUDA stream and one device

@@ -1,0 +1,229 @@
+"""Host-side check of the dataflow Cholesky's task plan (csrc/ipp_chol_plan.h, executed on the device by
+chol_queue_kernel): a discrete-event simulation of the kernel's own claiming rules -- chain queues claimed in order
+and only when ready, the bulk queue claimed in order unconditionally, successor hints -- over random CTA counts,
+task durations and polling orders.  It checks what the device cannot tell us cheaply:
+
+* no deadlock for any number of resident CTAs (1 included);
+* every block receives every panel to its left exactly once, in ascending order, before it is factored / solved;
+* every operand block a task reads is final when the task starts, and no two running tasks touch the same block.
+"""
+import ctypes as C
+import random
+
+import numpy as np
+import pytest
+
+from mripp_b200 import _lib
+
+HDR, TS, MAXDEP = 16, 24, 6
+(PH_MAGIC, PH_NB, PH_NRB, PH_TB, PH_NFLAGS, PH_NF, PH_NS, PH_NC, PH_NU, PH_OFFF, PH_OFFS, PH_OFFC, PH_OFFU, PH_TS, PH_TOTAL,
+ PH_NTILE) = range(16)
+TK_TYPE, TK_A, TK_B, TK_C, TK_D, TK_E, TK_F, TK_G, TK_NDEP, TK_DEP0 = range(10)
+TK_OUT, TK_OUTVAL = TK_DEP0 + 2 * MAXDEP, TK_DEP0 + 2 * MAXDEP + 1
+
+
+def build_plan(n, ctas):
+    lib = _lib.load()
+    need = C.c_longlong(0)
+    assert lib.ipp_host_chol_plan(n, ctas, None, 0, C.byref(need)) == 0
+    buf = (C.c_int * need.value)()
+    assert lib.ipp_host_chol_plan(n, ctas, buf, need.value, C.byref(need)) == 0
+    return np.frombuffer(buf, dtype=np.int32).copy()
+
+
+class Sim:
+    def __init__(self, plan, R, n_ctas, seed, hints=True):
+        self.p, self.R, self.rng, self.hints = plan, R, random.Random(seed), hints
+        self.nb, self.nrb, self.tb = int(plan[PH_NB]), int(plan[PH_NRB]), int(plan[PH_TB])
+        self.cnt = [int(plan[PH_NF + q]) for q in range(4)]
+        self.off = [int(plan[PH_OFFF + q]) for q in range(4)]
+        self.flags = np.zeros((R, int(plan[PH_NFLAGS])), dtype=np.int64)
+        self.heads = np.zeros((R, 3), dtype=np.int64)
+        self.bulk_head = 0
+        # per problem and block: panels applied so far, final?, solve parts done; blocks being written right now
+        self.applied = [dict() for _ in range(R)]
+        self.final = [set() for _ in range(R)]
+        self.parts = [dict() for _ in range(R)]
+        self.writing = [dict() for _ in range(R)]
+        self.ctas = [dict(pend=None, hint=None, busy_until=0, task=None) for _ in range(n_ctas)]
+        self.executed = 0
+
+    def task(self, q, i):
+        o = self.off[q] + i * TS
+        return self.p[o:o + TS]
+
+    def ready(self, T, r):
+        for d in range(MAXDEP):
+            idx = int(T[TK_DEP0 + 2 * d])
+            if idx >= 0 and self.flags[r, idx] < int(T[TK_DEP0 + 2 * d + 1]):
+                return False
+        return True
+
+    # ---- what a task reads and writes, at block level -------------------------------------------------
+    def blocks_of(self, T):
+        ty = int(T[TK_TYPE])
+        if ty == 0:
+            k, w = int(T[TK_A]), int(T[TK_B])
+            return dict(kind="F", writes=[(k, k)], reads=[(k, p) for p in range(k - w, k)], before=k - w, panels=range(k - w, k))
+        if ty == 1:
+            i, k = int(T[TK_A]), int(T[TK_B])
+            return dict(kind="S", writes=[(i, k)], reads=[(k, k)], before=k, panels=range(0), part=(int(T[TK_C]), 64 // int(T[TK_D])))
+        ti, tj, kb, ke, cmin, skip = (int(T[x]) for x in (TK_A, TK_B, TK_C, TK_D, TK_E, TK_F))
+        writes, reads = [], set()
+        for i in range(ti * self.tb, min((ti + 1) * self.tb, self.nrb)):
+            for j in range(tj * self.tb, min((tj + 1) * self.tb, self.nb)):
+                if j < cmin or j > i or (i == j == skip):
+                    continue
+                assert j >= ke, "a panel may only update columns to its right"
+                writes.append((i, j))
+                for p in range(kb, ke):
+                    reads.add((i, p))
+                    reads.add((j, p))
+        assert writes, "empty update task"
+        return dict(kind="U", writes=writes, reads=sorted(reads), before=kb, panels=range(kb, ke))
+
+    def start(self, cta, q, i, r, now):
+        T = self.task(q, i)
+        assert self.ready(T, r)
+        b = self.blocks_of(T)
+        for blk in b["reads"]:
+            assert blk in self.final[r], (b["kind"], "reads a block that is not final", blk)
+            assert blk not in self.writing[r]
+        for blk in b["writes"]:
+            if b["kind"] == "S":
+                h, split = b["part"]
+                assert (blk, h) not in self.writing[r] and blk not in self.final[r]
+                self.writing[r][(blk, h)] = 1
+            else:
+                assert blk not in self.writing[r], (b["kind"], "two tasks write", blk)
+                assert not any(k[0] == blk for k in self.writing[r] if isinstance(k[0], tuple))
+                self.writing[r][blk] = 1
+            assert blk not in self.final[r]
+            assert self.applied[r].get(blk, 0) == b["before"], (b["kind"], blk, self.applied[r].get(blk, 0), b["before"])
+        cta["task"] = (T, r, b)
+        cta["busy_until"] = now + self.rng.choice((1, 1, 2, 3, 5, 9))
+
+    def finish(self, cta):
+        T, r, b = cta["task"]
+        for blk in b["writes"]:
+            if b["kind"] == "S":
+                h, split = b["part"]
+                del self.writing[r][(blk, h)]
+                self.parts[r][blk] = self.parts[r].get(blk, 0) + 1
+                if self.parts[r][blk] == split:
+                    self.final[r].add(blk)
+            else:
+                del self.writing[r][blk]
+                self.applied[r][blk] = self.applied[r].get(blk, 0) + len(b["panels"])
+                if b["kind"] == "F":
+                    assert self.applied[r][blk] == blk[1]
+                    self.final[r].add(blk)
+        oi, ov = int(T[TK_OUT]), int(T[TK_OUTVAL])
+        if ov < 0:
+            self.flags[r, oi] += 1
+        else:
+            assert self.flags[r, oi] < ov
+            self.flags[r, oi] = ov
+        ty = int(T[TK_TYPE])
+        cta["hint"] = None
+        if self.hints:
+            if ty == 0 and int(T[TK_G]) >= 0:
+                cta["hint"] = (1, int(T[TK_G]), r)
+            elif ty == 1 and int(T[TK_A]) == int(T[TK_B]) + 1 and int(T[TK_G]) >= 0:
+                cta["hint"] = (0, int(T[TK_G]), r)
+        cta["task"] = None
+        self.executed += 1
+
+    def acquire(self, cta, now):
+        """One polling round of one CTA: returns 'exit', 'idle' or 'started'."""
+        if cta["hint"] is not None:
+            q, i, r = cta["hint"]
+            cta["hint"] = None
+            if self.heads[r, q] == i and self.ready(self.task(q, i), r):
+                self.heads[r, q] += 1
+                self.start(cta, q, i, r, now)
+                return "started"
+        exhausted = True
+        for c in range(3 * self.R):
+            q, r = divmod(c, self.R)
+            h = int(self.heads[r, q])
+            if h < self.cnt[q]:
+                exhausted = False
+                if self.ready(self.task(q, h), r):
+                    self.heads[r, q] += 1
+                    self.start(cta, q, h, r, now)
+                    return "started"
+        if cta["pend"] is None:
+            total = self.cnt[3] * self.R
+            if self.bulk_head < total:
+                cta["pend"] = self.bulk_head
+                self.bulk_head += 1
+            else:
+                cta["pend"] = -2
+        if cta["pend"] >= 0:
+            exhausted = False
+            ti, r = divmod(cta["pend"], self.R)
+            if self.ready(self.task(3, ti), r):
+                cta["pend"] = None
+                self.start(cta, 3, ti, r, now)
+                return "started"
+        return "exit" if exhausted else "idle"
+
+    def run(self):
+        now, live = 0, list(range(len(self.ctas)))
+        while live:
+            progressed = False
+            self.rng.shuffle(live)
+            for c in list(live):
+                cta = self.ctas[c]
+                if cta["task"] is not None:
+                    if cta["busy_until"] <= now:
+                        self.finish(cta)
+                        progressed = True
+                    else:
+                        continue
+                res = self.acquire(cta, now)
+                if res == "exit":
+                    live.remove(c)
+                    progressed = True
+                elif res == "started":
+                    progressed = True
+            running = any(self.ctas[c]["task"] is not None for c in live)
+            assert progressed or running, "deadlock: every resident CTA polls and nothing runs"
+            now += 1
+        total = sum(self.cnt) + (self.R - 1) * sum(self.cnt)
+        assert self.executed == total, (self.executed, total)
+        for r in range(self.R):
+            for i in range(self.nrb):
+                for j in range(min(i + 1, self.nb)):
+                    assert (i, j) in self.final[r], ("block never finalised", i, j)
+                    assert self.applied[r].get((i, j), 0) == j, ("panels applied", i, j, self.applied[r].get((i, j), 0))
+
+
+@pytest.mark.parametrize("n,ctas,R,n_sim", [
+    (64, 148, 1, 1), (100, 148, 2, 3), (300, 148, 1, 7), (500, 8, 3, 5), (700, 148, 1, 1), (1000, 296, 2, 40),
+    (1600, 148, 1, 1), (1700, 148, 1, 16), (2000, 148, 2, 33), (2100, 148, 3, 148),
+])
+def test_plan_is_deadlock_free_and_complete(n, ctas, R, n_sim):
+    plan = build_plan(n, ctas)
+    assert plan[PH_MAGIC] == 0x43485132 and plan[PH_TS] == TS and plan[PH_TOTAL] == len(plan)
+    for seed in range(2):
+        Sim(plan, R, n_sim, seed, hints=bool(seed % 2 == 0)).run()
+
+
+def test_plan_shape_at_c4():
+    """The C4 size (n = 5000): tile mode, queue sizes, scratch size reported by the library."""
+    lib = _lib.load()
+    plan = build_plan(5000, 148)
+    nb = 5056 // 64
+    assert plan[PH_NB] == nb and plan[PH_NRB] == nb + 1 and plan[PH_TB] == 2 and plan[PH_NF] == nb
+    out = C.c_longlong(0)
+    assert lib.ipp_chol_sched_ints(5000, 11, C.byref(out)) == 0
+    assert out.value == 11 * int(plan[PH_NFLAGS]) + 4 * 11 + 8
+    # every dependency index is a valid flag
+    for q in range(4):
+        for i in range(int(plan[PH_NF + q])):
+            T = plan[int(plan[PH_OFFF + q]) + i * TS:][:TS]
+            assert 0 <= T[TK_OUT] < plan[PH_NFLAGS]
+            for d in range(int(T[TK_NDEP])):
+                assert 0 <= T[TK_DEP0 + 2 * d] < plan[PH_NFLAGS] and T[TK_DEP0 + 2 * d + 1] > 0
