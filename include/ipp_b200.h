@@ -75,8 +75,8 @@ int ipp_chol_sched_ints(int n, int R, long long* out_host);
  * Tbuf + s * out[5], vbuf + s * out[6] (ipp_gp_layout) and hyp + 4 s = {c, l, jitter, -}.  One launch sequence; the
  * factorisations share one persistent kernel and fill each other's dependency stalls.  Per-problem arithmetic does
  * not depend on R or on the slot.  plan: DEVICE copy of ipp_host_chol_plan; sched: ipp_chol_sched_ints(n, R) ints.
- * flags: bit 0 = do not hand the critical chain over by hints (measurement aid); bits 8.. = cap on the CTAs of the
- * factorisation kernel (0: whole GPU).  info = -7777 in the result block: the kernel's watchdog fired.
+ * flags: bit 0 = do not hand the critical chain over by hints (measurement aid); bit 1 = leave per-CTA task / cycle
+ * counters at the end of sched; bits 8.. = cap on the CTAs of the factorisation kernel (0: whole GPU).  info = -7777 in the result block: the kernel's watchdog fired.
  * Replaces the objective evaluations of the n_restarts_optimizer + 1 L-BFGS-B runs of fit (sklearn _gpr.py:302-333),
  * which are independent once their start points are drawn. */
 int ipp_gp_lml_grad_batch(const double* X, const double* y, int n, const double* hyp, double* Kbuf, double* Wbuf,

@@ -19,10 +19,13 @@ struct CholQ {
   const int* slots;   // nullable: slot(r) = r
   int R;
   const int* plan;
-  int* sched;         // [R][nflags] flags | [R][4] queue heads (F, S, C, -) | bulk head | abort | stats...
+  int* sched;         // [R][nflags] flags | [R][QSTATE] queue heads and ready frontiers | bulk head | abort
   long long timeout;  // cycles a CTA may poll without finding work before it raises `abort`
   int use_hints;
+  int stats;          // != 0: every CTA leaves {tasks F/S/U, cycles F/S/U, cycles acquiring, cycles total} after the abort word
 };
+constexpr int QSTATS = 16;       // ints per CTA
+constexpr int QSTATS_CTAS = 512;
 
 __device__ __forceinline__ int ld_relaxed(const int* p) {
   int v;
@@ -161,7 +164,20 @@ __device__ __forceinline__ void cholq_update_tile(double* __restrict__ A, long l
 }
 
 enum { QS_NONE = -1, QS_EXHAUSTED = -2 };
+constexpr int QSTATE = 8;  // ints of queue state per problem: {head F, ready F, head S, ready S, head C, ready C, -, -}
 
+// Claiming.  Each chain queue (F, S, C of every problem) has a HEAD (next task to hand out) and a READY FRONTIER
+// (every task below it has its dependencies met).  Pollers advance the frontier -- a window of tasks beyond it is
+// tested by the lanes of the polling warp in parallel, the leading run of ready ones is added with one atomicMax --
+// and claim with atomicAdd on the head whenever head < frontier: any number of CTAs claim different ready tasks in
+// the same round trip (a compare-and-swap on the head hands out one task per round trip to all contenders together:
+// measured 4x slower than the cooperative kernel).  A racing claim can land just beyond the frontier; its owner HOLDS
+// that task (tests it every poll, runs it as soon as it is ready) and keeps serving the queues meanwhile -- with
+// compare-and-swap claims, which cannot overshoot, so a CTA never holds more than one chain task.  (Waiting for a
+// held task without serving deadlocks: every CTA can end up holding a task behind an F task nobody is free to run
+// -- found by the host simulation of these rules, tests/test_chol_plan.py.)
+// The bulk queue has no frontier: claimed unconditionally, in order; the owner waits for the task's flags and serves
+// the chain queues meanwhile.
 template <class C>
 __global__ void __launch_bounds__(C::THREADS, 1) chol_queue_kernel(CholQ a) {
   extern __shared__ __align__(16) double smem[];
@@ -169,28 +185,37 @@ __global__ void __launch_bounds__(C::THREADS, 1) chol_queue_kernel(CholQ a) {
   const int* __restrict__ plan = a.plan;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int nflags = __ldg(plan + PH_NFLAGS);
-  const int R = a.R;
-  int* heads = a.sched + (long)R * nflags;
-  int* bulk_head = heads + 4 * R;
+  const int R = a.R, nq = 3 * R;
+  int* qstate = a.sched + (long)R * nflags;
+  int* bulk_head = qstate + QSTATE * R;
   int* abortf = bulk_head + 1;
-  int pend = QS_NONE;                  // this CTA's claimed, not yet started bulk task (warp 0, uniform)
+  int pend = QS_NONE;                       // this CTA's claimed, not yet started bulk task (warp 0, uniform)
   int hint_q = -1, hint_i = 0, hint_r = 0;  // successor of the task just finished (tried first)
+  int held_q = -1, held_i = 0, held_r = 0;  // chain task claimed past its queue's frontier, not started yet
   long long idle_since = 0;
   bool idle = false;
+  long long st_cyc[4] = {0, 0, 0, 0}, st_t0 = clock64(), st_mark = st_t0;  // thread 0: F, S, U, acquiring
+  int st_n[3] = {0, 0, 0};
+  // frontier scan: `per` lanes per queue, each testing two tasks -> a window of 2 * per tasks per queue and poll
+  const int per = nq <= 32 ? 32 / nq : 1;
 
   for (;;) {
     if (warp == 0) {
       int got_q = -1, got_i = 0, got_r = 0;
+      unsigned backoff = 0;
       for (;;) {
-        // ---- 0. the successor of the task this CTA just finished
+        // ---- 0. the successor of the task this CTA just finished: one targeted test, claimed by compare-and-swap
         if (hint_q >= 0) {
           int ok = 0;
           if (lane == 0) {
-            int* hp = heads + 4 * hint_r + hint_q;
+            int* hp = qstate + QSTATE * hint_r + 2 * hint_q;
             const int* T = plan + __ldg(plan + PH_OFFF + hint_q) + hint_i * PLAN_TS;
             const int h = ld_relaxed(hp);
             const bool rdy = task_ready(T, a.sched + (long)hint_r * nflags);
-            if (h == hint_i && rdy) ok = (atomicCAS(hp, hint_i, hint_i + 1) == hint_i);
+            if (h == hint_i && rdy) {
+              ok = (atomicCAS(hp, hint_i, hint_i + 1) == hint_i);
+              if (ok) atomicMax(hp + 1, hint_i + 1);
+            }
           }
           ok = __shfl_sync(0xffffffffu, ok, 0);
           const int hq = hint_q;
@@ -202,24 +227,96 @@ __global__ void __launch_bounds__(C::THREADS, 1) chol_queue_kernel(CholQ a) {
             break;
           }
         }
-        // ---- 1. lanes 0..30: heads of the chain queues (candidate c = queue * R + problem, lowest c wins);
-        //         lane 31: the bulk queue (claim the next task if this CTA holds none, then test it)
-        int best = 0x7fffffff, best_h = 0;
-        bool exhausted = true;
-        if (lane < 31) {
-          for (int c = lane; c < 3 * R; c += 31) {
-            const int q = c / R, r = c % R;
-            const int h = ld_relaxed(heads + 4 * r + q);
-            if (h < __ldg(plan + PH_NF + q)) {
-              exhausted = false;
-              const int* T = plan + __ldg(plan + PH_OFFF + q) + h * PLAN_TS;
-              if (c < best && task_ready(T, a.sched + (long)r * nflags)) {
-                best = c;
-                best_h = h;
-              }
+        // ---- 1a. a held task that has become ready goes first
+        if (held_q >= 0) {
+          int ok = 0;
+          if (lane == 0)
+            ok = task_ready(plan + __ldg(plan + PH_OFFF + held_q) + held_i * PLAN_TS, a.sched + (long)held_r * nflags) ? 1 : 0;
+          ok = __shfl_sync(0xffffffffu, ok, 0);
+          if (ok) {
+            got_q = held_q;
+            got_i = held_i;
+            got_r = held_r;
+            held_q = -1;
+            break;
+          }
+        }
+        // ---- 1b. claim from the highest-priority queue whose head is behind its frontier (queue c = q * R + r)
+        int best = 0x7fffffff, best_rdy = 0, best_h = 0;
+        bool exhausted = held_q < 0;
+        for (int c = lane; c < nq; c += 32) {
+          const int q = c / R, r = c % R;
+          const int* st = qstate + QSTATE * r + 2 * q;
+          const int h = ld_relaxed(st), f = ld_relaxed(st + 1);
+          if (h < __ldg(plan + PH_NF + q)) exhausted = false;
+          if (h < f && c < best) {
+            best = c;
+            best_rdy = f;
+            best_h = h;
+          }
+        }
+        int win = best;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) win = min(win, __shfl_xor_sync(0xffffffffu, win, o));
+        if (win != 0x7fffffff) {
+          const int q = win / R, r = win % R;
+          int h = 0, ok = 0;
+          if (lane == (win & 31)) {
+            int* hp = qstate + QSTATE * r + 2 * q;
+            if (held_q < 0) {
+              h = atomicAdd(hp, 1);
+              ok = h < __ldg(plan + PH_NF + q) ? (h < best_rdy ? 1 : 2) : 0;  // 2: beyond the frontier seen -> test it
+              if (ok == 2 && task_ready(plan + __ldg(plan + PH_OFFF + q) + h * PLAN_TS, a.sched + (long)r * nflags)) ok = 1;
+            } else {  // already holding a task: claim exactly the head seen (below the frontier, hence ready)
+              h = best_h;
+              ok = (atomicCAS(hp, best_h, best_h + 1) == best_h) ? 1 : 0;
             }
           }
-        } else {
+          ok = __shfl_sync(0xffffffffu, ok, win & 31);
+          h = __shfl_sync(0xffffffffu, h, win & 31);
+          if (ok == 1) {
+            got_q = q;
+            got_i = h;
+            got_r = r;
+            break;
+          }
+          if (ok == 2) {
+            held_q = q;
+            held_i = h;
+            held_r = r;
+          }
+          continue;  // lost a race, claimed past the end, or now holding: look again
+        }
+        // ---- 2. nothing claimable: advance the frontiers (every lane tests two tasks beyond the frontier of its
+        //         queue) and test this CTA's bulk task
+        bool advanced = false;
+        for (int c0 = 0; c0 < nq; c0 += 32 / per) {
+          const int c = c0 + lane / per, o = lane % per;
+          bool r0 = false, r1 = false;
+          int f = 0, cnt = 0;
+          int* st = nullptr;
+          if (c < nq && lane < per * (32 / per)) {
+            const int q = c / R, r = c % R;
+            st = qstate + QSTATE * r + 2 * q;
+            f = ld_relaxed(st + 1);
+            cnt = __ldg(plan + PH_NF + q);
+            const int* Tq = plan + __ldg(plan + PH_OFFF + q);
+            const int* fl = a.sched + (long)r * nflags;
+            if (f + o < cnt) r0 = task_ready(Tq + (f + o) * PLAN_TS, fl);
+            if (f + per + o < cnt) r1 = task_ready(Tq + (f + per + o) * PLAN_TS, fl);
+          }
+          const unsigned m0 = __ballot_sync(0xffffffffu, r0), m1 = __ballot_sync(0xffffffffu, r1);
+          if (st != nullptr && o == 0) {
+            const unsigned gmask = per >= 32 ? 0xffffffffu : ((1u << per) - 1u);
+            const unsigned g0 = (m0 >> (lane)) & gmask, g1 = (m1 >> (lane)) & gmask;
+            int m = __ffs(~g0 & gmask) ? __ffs(~g0 & gmask) - 1 : per;  // leading run of ready tasks
+            if (m == per) m += __ffs(~g1 & gmask) ? __ffs(~g1 & gmask) - 1 : per;
+            if (m > 0) advanced = atomicMax(st + 1, f + m) >= 0;  // (the returned value makes the warp wait for the update)
+          }
+        }
+        if (__any_sync(0xffffffffu, advanced)) continue;  // something became claimable: claim it
+        int take = 0;
+        if (lane == 31) {
           if (pend == QS_NONE) {
             const int total = __ldg(plan + PH_NU) * R;
             const int pos = (ld_relaxed(bulk_head) < total) ? atomicAdd(bulk_head, 1) : total;
@@ -227,51 +324,24 @@ __global__ void __launch_bounds__(C::THREADS, 1) chol_queue_kernel(CholQ a) {
           }
           if (pend >= 0) {
             exhausted = false;
-            const int ti = pend / R, r = pend % R;
-            const int* T = plan + __ldg(plan + PH_OFFU) + ti * PLAN_TS;
-            if (task_ready(T, a.sched + (long)r * nflags)) {
-              best = 3 * R;
-              best_h = pend;
-            }
+            const int* T = plan + __ldg(plan + PH_OFFU) + (pend / R) * PLAN_TS;
+            take = task_ready(T, a.sched + (long)(pend % R) * nflags) ? 1 : 0;
           }
         }
         pend = __shfl_sync(0xffffffffu, pend, 31);
-        int win = best;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) win = min(win, __shfl_xor_sync(0xffffffffu, win, o));
-        const bool all_done = __all_sync(0xffffffffu, exhausted);
-        if (win != 0x7fffffff) {
-          const unsigned owner_mask = __ballot_sync(0xffffffffu, best == win);
-          const int owner = __ffs(owner_mask) - 1;
-          int ok = 0;
-          if (win == 3 * R) {
-            ok = 1;
-          } else if (lane == owner) {
-            const int q = win / R, r = win % R;
-            ok = (atomicCAS(heads + 4 * r + q, best_h, best_h + 1) == best_h);
-          }
-          ok = __shfl_sync(0xffffffffu, ok, owner);
-          const int h = __shfl_sync(0xffffffffu, best_h, owner);
-          if (ok) {
-            if (win == 3 * R) {
-              got_q = 3;
-              got_i = h / R;
-              got_r = h % R;
-              pend = QS_NONE;
-            } else {
-              got_q = win / R;
-              got_i = h;
-              got_r = win % R;
-            }
-            break;
-          }
-          continue;  // lost the race: look again at once
+        take = __shfl_sync(0xffffffffu, take, 31);
+        if (take) {
+          got_q = 3;
+          got_i = pend / R;
+          got_r = pend % R;
+          pend = QS_NONE;
+          break;
         }
-        if (all_done) {
+        if (__all_sync(0xffffffffu, exhausted)) {
           got_q = -1;
           break;
         }
-        // ---- nothing ready: watchdog, then poll again
+        // ---- nothing to do right now: watchdog, back off, poll again
         int stop = 0;
         if (lane == 0) {
           const long long now = clock64();
@@ -287,7 +357,8 @@ __global__ void __launch_bounds__(C::THREADS, 1) chol_queue_kernel(CholQ a) {
           got_q = -2;
           break;
         }
-        __nanosleep(32);
+        backoff = backoff < 512 ? backoff + 64 : 512;
+        __nanosleep(backoff);
       }
       idle = false;
       if (lane == 0) {
@@ -299,6 +370,11 @@ __global__ void __launch_bounds__(C::THREADS, 1) chol_queue_kernel(CholQ a) {
     }
     __syncthreads();
     const int q = s_task[0], ti = s_task[1], r = s_task[2];
+    if (a.stats && t == 0) {
+      const long long now = clock64();
+      st_cyc[3] += now - st_mark;
+      st_mark = now;
+    }
     if (q < 0) {
       if (q == -2 && t == 0)  // watchdog: report through every problem's info slot (the host raises)
         for (int rr = 0; rr < R; ++rr) a.vbuf[(a.slots ? (long)a.slots[rr] : (long)rr) * a.vstride + a.info_off] = -7777.0;
@@ -322,6 +398,12 @@ __global__ void __launch_bounds__(C::THREADS, 1) chol_queue_kernel(CholQ a) {
       cholq_update_tile<C>(A, a.ld, a.rows_total, a.np, pa * C::BM, pb * C::BN, pc * BLK, pd * BLK, __ldg(T + TK_E) * BLK,
                            __ldg(T + TK_F), smem);
     }
+    if (a.stats && t == 0) {
+      const long long now = clock64();
+      st_cyc[type] += now - st_mark;
+      st_n[type] += 1;
+      st_mark = now;
+    }
     // every executor ends with a CTA barrier after its last global store: publish
     if (t == 0) {
       const int oi = __ldg(T + TK_OUT), ov = __ldg(T + TK_OUTVAL);
@@ -344,5 +426,11 @@ __global__ void __launch_bounds__(C::THREADS, 1) chol_queue_kernel(CholQ a) {
       }
     }
     __syncthreads();  // s_task is rewritten by warp 0 in the next round
+  }
+  if (a.stats && t == 0 && blockIdx.x < QSTATS_CTAS) {
+    int* o = abortf + 7 + QSTATS * blockIdx.x;
+    for (int i = 0; i < 3; ++i) o[i] = st_n[i];
+    for (int i = 0; i < 4; ++i) o[3 + i] = (int)(st_cyc[i] >> 6);  // units of 64 cycles
+    o[7] = (int)((clock64() - st_t0) >> 6);
   }
 }

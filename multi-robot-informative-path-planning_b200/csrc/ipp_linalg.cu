@@ -856,6 +856,7 @@ struct CholRun {
   int* sched;       // ipp_chol_sched_ints(n, R) ints of scratch
   int use_hints;
   int max_ctas;
+  int stats;
 };
 
 static int device_sms(int* sms) {
@@ -870,7 +871,7 @@ static long chol_sched_ints(int n, int R) {
   const int tb = use_small_tiles(d.np) ? 1 : 2;
   const int nb = d.np / BLK, nrb = nb + 1, tmax = (nrb - 1) / tb;
   const long nflags = nb + nrb + (long)(tmax + 1) * (tmax + 2) / 2;
-  return (long)R * nflags + 4L * R + 8;
+  return (long)R * nflags + 8L * R + 8 + (long)QSTATS * QSTATS_CTAS;  // flags | queue state | bulk head, abort | per-CTA stats
 }
 
 template <class C>
@@ -906,6 +907,7 @@ static int chol_queue_launch(double* Kb, double* vbuf, const GpDims& d, const Ba
   a.sched = run.sched;
   a.timeout = 4000000000LL;  // ~2 s of polling without work: a scheduling bug, not a slow task
   a.use_hints = run.use_hints;
+  a.stats = run.stats;
   chol_queue_kernel<C><<<(unsigned)ctas, C::THREADS, SM, st>>>(a);
   return IPP_OK;
 }
@@ -1148,7 +1150,7 @@ int ipp_gram_rbf(const double* X, int n, const double* Y, int m, double c, doubl
 
 int ipp_gp_lml_grad(const double* X, const double* y, int n, const double* hyp, double* Kbuf, double* Wbuf,
                     double* Tbuf, double* vbuf, int with_grad, int max_ctas, void* stream) {
-  const CholRun run = {nullptr, nullptr, 0, max_ctas};
+  const CholRun run = {nullptr, nullptr, 0, max_ctas, 0};
   return gp_lml_grad_run(X, y, n, hyp, Kbuf, Wbuf, Tbuf, vbuf, with_grad, kOne, 1, run, (cudaStream_t)stream);
 }
 
@@ -1177,7 +1179,7 @@ int ipp_gp_lml_grad_batch(const double* X, const double* y, int n, const double*
   if (R <= 0 || !plan || !sched) return IPP_ERR_ARG;
   const GpDims d = gp_dims(n > 0 ? n : 1);
   const Bat bat = {slots, (long)d.rows * d.ld, (long)d.np * d.ld, (long)d.np * d.ld, v_total(d)};
-  const CholRun run = {plan, sched, (flags & 1) ? 0 : 1, flags >> 8};
+  const CholRun run = {plan, sched, (flags & 1) ? 0 : 1, flags >> 8, (flags >> 1) & 1};
   return gp_lml_grad_run(X, y, n, hyp, Kbuf, Wbuf, Tbuf, vbuf, with_grad, bat, R, run, (cudaStream_t)stream);
 }
 
@@ -1198,13 +1200,13 @@ static int gp_fit_final_run(const double* X, const double* y, int n, const doubl
 
 int ipp_gp_fit_final(const double* X, const double* y, int n, const double* hyp, double* Kbuf, double* Wbuf,
                      double* Tbuf, double* vbuf, void* stream) {
-  const CholRun run = {nullptr, nullptr, 0, 0};
+  const CholRun run = {nullptr, nullptr, 0, 0, 0};
   return gp_fit_final_run(X, y, n, hyp, Kbuf, Wbuf, Tbuf, vbuf, run, (cudaStream_t)stream);
 }
 
 int ipp_gp_fit_final_plan(const double* X, const double* y, int n, const double* hyp, double* Kbuf, double* Wbuf,
                           double* Tbuf, double* vbuf, const int* plan, int* sched, int flags, void* stream) {
-  const CholRun run = {plan, plan ? sched : nullptr, (flags & 1) ? 0 : 1, 0};
+  const CholRun run = {plan, plan ? sched : nullptr, (flags & 1) ? 0 : 1, 0, 0};
   return gp_fit_final_run(X, y, n, hyp, Kbuf, Wbuf, Tbuf, vbuf, run, (cudaStream_t)stream);
 }
 
@@ -1222,7 +1224,7 @@ int ipp_mi_logdet(const double* leaf_xy, int L, const double* obs_xy, int na, do
   int rc = use_small_tiles(d.np) ? mi_build<Cfg64>(Gtmp, nap, Lp, nap, trans, beta, Kbuf, d, st)
                                  : mi_build<Cfg128>(Gtmp, nap, Lp, nap, trans, beta, Kbuf, d, st);
   if (rc != IPP_OK) return rc;
-  const CholRun run = {nullptr, nullptr, 0, 0};
+  const CholRun run = {nullptr, nullptr, 0, 0, 0};
   rc = use_small_tiles(d.np) ? chol_inplace<Cfg64>(Kbuf, Wbuf, vbuf, d, kOne, 1, run, st)
                              : chol_inplace<Cfg128>(Kbuf, Wbuf, vbuf, d, kOne, 1, run, st);
   if (rc != IPP_OK) return rc;

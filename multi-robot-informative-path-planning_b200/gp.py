@@ -29,6 +29,25 @@ from . import _lib
 __all__ = ["ConstantRBFKernel", "ConstantKernel", "RBF", "GaussianProcessRegressor"]
 
 
+def _chol_flags():
+    """Measurement switches of the dataflow Cholesky: IPP_CHOL_HINTS=0 (no chain hand-over), IPP_CHOL_STATS=1 (per-CTA
+    task / cycle counters left in the scheduling scratch)."""
+    return (1 if os.environ.get("IPP_CHOL_HINTS", "1") == "0" else 0) | (2 if os.environ.get("IPP_CHOL_STATS", "0") == "1" else 0)
+
+
+def chol_stats(ws, R):
+    """Aggregate of the per-CTA counters of the last dataflow factorisation run on workspace `ws` (IPP_CHOL_STATS=1)."""
+    plan = ws.plan.cpu().numpy()
+    base = R * int(plan[4]) + 8 * R + 8
+    st = ws.sched[base:base + 16 * 512].cpu().numpy().reshape(512, 16)
+    st = st[st[:, 7] > 0]
+    cyc = st[:, 3:8].astype(np.float64) * 64.0
+    return {"ctas": int(len(st)), "tasks_F_S_U": st[:, 0:3].sum(0).tolist(),
+            "busy_frac_F_S_U": (cyc[:, 0:3].sum(0) / cyc[:, 4].sum()).tolist(), "acquire_frac": float(cyc[:, 3].sum() / cyc[:, 4].sum()),
+            "mean_task_us_F_S_U_at_1965MHz": (cyc[:, 0:3].sum(0) / np.maximum(st[:, 0:3].sum(0), 1) / 1965.0).tolist(),
+            "kernel_us": float(cyc[:, 4].max() / 1965.0)}
+
+
 def _check_watchdog(info):
     if info == -7777.0:
         raise _lib.IppError("dataflow Cholesky: a CTA found no runnable task for ~2 s (scheduling fault); "
@@ -398,7 +417,7 @@ class GaussianProcessRegressor:
         ws.hyp_host[2] = self.alpha
         ws.hyp.copy_(ws.hyp_host, non_blocking=True)
         st = _lib.stream_ptr()
-        flags = 1 if os.environ.get("IPP_CHOL_HINTS", "1") == "0" else 0
+        flags = _chol_flags()
         if final:
             Xf, yf = (self._Xd_fit, self._yd_fit) if final == "morton" else (self._Xd, self._yd)
             rc = lib.ipp_gp_fit_final_plan(_lib.ptr(Xf), _lib.ptr(yf), n, _lib.ptr(ws.hyp), _lib.ptr(ws.K),
@@ -433,7 +452,7 @@ class GaussianProcessRegressor:
         ws.slot_ids_host.numpy()[:R] = batch
         ws.hyp.copy_(ws.hyp_host, non_blocking=True)
         ws.slot_ids.copy_(ws.slot_ids_host, non_blocking=True)
-        flags = 1 if os.environ.get("IPP_CHOL_HINTS", "1") == "0" else 0
+        flags = _chol_flags()
         rc = lib.ipp_gp_lml_grad_batch(_lib.ptr(self._Xd), _lib.ptr(self._yd), n, _lib.ptr(ws.hyp), _lib.ptr(ws.K),
                                        _lib.ptr(ws.W), _lib.ptr(ws.T), _lib.ptr(ws.v), _lib.ptr(ws.slot_ids), R,
                                        1 if with_grad else 0, _lib.ptr(ws.plan), _lib.ptr(ws.sched), flags, _lib.stream_ptr())

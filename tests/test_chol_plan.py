@@ -1,7 +1,8 @@
 """Host-side check of the dataflow Cholesky's task plan (csrc/ipp_chol_plan.h, executed on the device by
-chol_queue_kernel): a discrete-event simulation of the kernel's own claiming rules -- chain queues claimed in order
-and only when ready, the bulk queue claimed in order unconditionally, successor hints -- over random CTA counts,
-task durations and polling orders.  It checks what the device cannot tell us cheaply:
+chol_queue_kernel): a discrete-event simulation of the kernel's own claiming rules -- chain queues with a ready
+frontier, claimed by atomicAdd on a stale view (so that racing claims overshoot the frontier and are HELD), the bulk
+queue claimed in order unconditionally, successor hints -- over random CTA counts, task durations and polling
+orders.  It checks what the device cannot tell us cheaply:
 
 * no deadlock for any number of resident CTAs (1 included);
 * every block receives every panel to its left exactly once, in ascending order, before it is factored / solved;
@@ -39,13 +40,15 @@ class Sim:
         self.off = [int(plan[PH_OFFF + q]) for q in range(4)]
         self.flags = np.zeros((R, int(plan[PH_NFLAGS])), dtype=np.int64)
         self.heads = np.zeros((R, 3), dtype=np.int64)
+        self.front = np.zeros((R, 3), dtype=np.int64)  # ready frontiers
+        self.window = self.rng.choice((1, 2, 20))
         self.bulk_head = 0
         # per problem and block: panels applied so far, final?, solve parts done; blocks being written right now
         self.applied = [dict() for _ in range(R)]
         self.final = [set() for _ in range(R)]
         self.parts = [dict() for _ in range(R)]
         self.writing = [dict() for _ in range(R)]
-        self.ctas = [dict(pend=None, hint=None, busy_until=0, task=None) for _ in range(n_ctas)]
+        self.ctas = [dict(pend=None, hint=None, busy_until=0, task=None, blocked=None) for _ in range(n_ctas)]
         self.executed = 0
 
     def task(self, q, i):
@@ -134,25 +137,60 @@ class Sim:
         cta["task"] = None
         self.executed += 1
 
-    def acquire(self, cta, now):
-        """One polling round of one CTA: returns 'exit', 'idle' or 'started'."""
+    def acquire(self, cta, now, snap):
+        """One polling round of one CTA against the queue state `snap` = (heads, frontiers) as it was at the start of
+        the tick (every CTA of a tick decides on the same stale view, like concurrent pollers on the device): hint,
+        then atomicAdd claim where head < frontier, else frontier scan, else the bulk task.  Returns 'exit', 'idle',
+        'started' or 'blocked' (claimed past the frontier: waits for that one task)."""
+        heads0, front0 = snap
         if cta["hint"] is not None:
             q, i, r = cta["hint"]
             cta["hint"] = None
             if self.heads[r, q] == i and self.ready(self.task(q, i), r):
                 self.heads[r, q] += 1
+                self.front[r, q] = max(self.front[r, q], i + 1)
                 self.start(cta, q, i, r, now)
                 return "started"
-        exhausted = True
+        if cta["blocked"] is not None:  # a task claimed past the frontier: held, tested first, the CTA keeps serving
+            q, h, r = cta["blocked"]
+            if self.ready(self.task(q, h), r):
+                cta["blocked"] = None
+                self.start(cta, q, h, r, now)
+                return "started"
+        exhausted = cta["blocked"] is None
         for c in range(3 * self.R):
             q, r = divmod(c, self.R)
-            h = int(self.heads[r, q])
-            if h < self.cnt[q]:
+            if heads0[r, q] < self.cnt[q]:
                 exhausted = False
-                if self.ready(self.task(q, h), r):
+            if heads0[r, q] < front0[r, q]:
+                if cta["blocked"] is None:
+                    h = int(self.heads[r, q])  # atomicAdd on the live head
+                    self.heads[r, q] += 1
+                    if h >= self.cnt[q]:
+                        return "idle"
+                    if h < front0[r, q] or self.ready(self.task(q, h), r):
+                        self.start(cta, q, h, r, now)
+                        return "started"
+                    cta["blocked"] = (q, h, r)
+                    return "blocked"
+                h = int(heads0[r, q])  # holding: compare-and-swap on exactly the head seen
+                if self.heads[r, q] == h:
                     self.heads[r, q] += 1
                     self.start(cta, q, h, r, now)
                     return "started"
+                return "idle"
+        advanced = False
+        for c in range(3 * self.R):
+            q, r = divmod(c, self.R)
+            f = int(front0[r, q])
+            m = 0
+            while m < self.window and f + m < self.cnt[q] and self.ready(self.task(q, f + m), r):
+                m += 1
+            if m:
+                self.front[r, q] = max(self.front[r, q], f + m)
+                advanced = True
+        if advanced:
+            return "idle"
         if cta["pend"] is None:
             total = self.cnt[3] * self.R
             if self.bulk_head < total:
@@ -171,9 +209,11 @@ class Sim:
 
     def run(self):
         now, live = 0, list(range(len(self.ctas)))
+        stall = 0
         while live:
             progressed = False
             self.rng.shuffle(live)
+            snap = (self.heads.copy(), self.front.copy())
             for c in list(live):
                 cta = self.ctas[c]
                 if cta["task"] is not None:
@@ -182,14 +222,16 @@ class Sim:
                         progressed = True
                     else:
                         continue
-                res = self.acquire(cta, now)
+                before = (self.heads.sum(), self.front.sum(), self.bulk_head)
+                res = self.acquire(cta, now, snap)
                 if res == "exit":
                     live.remove(c)
                     progressed = True
-                elif res == "started":
+                elif res in ("started", "blocked") or before != (self.heads.sum(), self.front.sum(), self.bulk_head):
                     progressed = True
             running = any(self.ctas[c]["task"] is not None for c in live)
-            assert progressed or running, "deadlock: every resident CTA polls and nothing runs"
+            stall = 0 if (progressed or running) else stall + 1
+            assert stall < 3, "deadlock: every resident CTA polls or waits and nothing runs"
             now += 1
         total = sum(self.cnt) + (self.R - 1) * sum(self.cnt)
         assert self.executed == total, (self.executed, total)
@@ -219,7 +261,7 @@ def test_plan_shape_at_c4():
     assert plan[PH_NB] == nb and plan[PH_NRB] == nb + 1 and plan[PH_TB] == 2 and plan[PH_NF] == nb
     out = C.c_longlong(0)
     assert lib.ipp_chol_sched_ints(5000, 11, C.byref(out)) == 0
-    assert out.value == 11 * int(plan[PH_NFLAGS]) + 4 * 11 + 8
+    assert out.value == 11 * int(plan[PH_NFLAGS]) + 8 * 11 + 8 + 16 * 512
     # every dependency index is a valid flag
     for q in range(4):
         for i in range(int(plan[PH_NF + q])):

@@ -130,6 +130,21 @@ def timing(ns):
         os.environ["IPP_CHOL_HINTS"] = "1"
         os.environ["IPP_CHOL"] = "queue"
         try:
+            os.environ["IPP_CHOL_STATS"] = "1"
+            gp = fixed_gp(X, y, "queue")
+            gp.log_marginal_likelihood(th, eval_gradient=False)
+            print("  stats R=1:", G.chol_stats(gp._scratch_ws(), 1), flush=True)
+            for R in (4,):
+                ws = G._Workspace().ensure(n, slots=R)
+                rng = np.random.RandomState(1)
+                thetas = [np.array([rng.uniform(-1, 1), rng.uniform(0, 1.5)]) for _ in range(R)]
+                gp._eval_batch(ws, list(range(R)), thetas, False)
+                print(f"  stats R={R}:", G.chol_stats(ws, R), flush=True)
+                del ws
+        except Exception:
+            traceback.print_exc()
+        os.environ["IPP_CHOL_STATS"] = "0"
+        try:
             gp = fixed_gp(X, y, "queue")
             for R in (2, 4, 11):
                 ws = G._Workspace().ensure(n, slots=R)
@@ -153,7 +168,7 @@ def timing(ns):
             traceback.print_exc()
         section(f"full 11-restart fit, n = {n}")
         for label, mode, streams in (("lockstep batch (queue)", "queue", None), ("queue, serial", "queue", 1),
-                                     ("coop, streams (round 1)", "coop", None), ("coop, serial", "coop", 1)):
+                                     ("coop, streams (round 1)", "coop", None)):
             try:
                 os.environ["IPP_CHOL"] = mode
                 gp = G.GaussianProcessRegressor(kernel=G.ConstantRBFKernel(1.0, 1.0), n_restarts_optimizer=10, normalize_y=True)
