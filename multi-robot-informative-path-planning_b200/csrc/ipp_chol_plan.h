@@ -7,17 +7,19 @@
 //   F(k)          factor diagonal block k.  It first applies, itself, the panels the bulk has not applied to that block:
 //                 the whole previous super-panel (k even: blocks k-2, k-1) or the panel k-1 (k odd), so that the
 //                 critical chain F(k) -> S(k+1, k) -> F(k+1) never waits for a bulk tile.
-//   S(i, k, h)    panel solve of row block i (part h of `split`) against L_kk.
+//   S(i0, k, nblk) panel solve of row blocks i0 .. i0 + nblk - 1 against L_kk: the block right under the diagonal
+//                 (i0 = k + 1, the one the chain waits for) alone, the others one task per tile row.
 //   UC(tile, 2s)  rank-64 update of block column 2s+1 by panel 2s (inside super-panel s).
 //   U2(tile, s)   rank-128 update of a tile right of super-panel s by panels 2s, 2s+1 (one read-modify-write of the
 //                 tile per TWO panels: half the traffic and twice the k depth of a per-panel update).
-// Flags (per problem; all monotone counters): F[k] in {0,1}; S[i] = number of finished solve parts of row block i
-// (cumulative over the panels); A[tile] = number of panels applied to the tile.
+// Flags (per problem; all monotone counters): F[k] in {0,1}; S[i] = number of panels row block i is solved for;
+// A[tile] = number of panels applied to the tile.
 // Queues: F, S and C (UC + the U2 tiles of the column right behind the super-panel, i.e. everything the chain waits
 // for) are claimed in order and ONLY WHEN READY (a CTA never blocks on them); the bulk queue U (the rest of U2) is
 // claimed in order unconditionally and its owner waits for the dependencies -- polling the chain queues meanwhile.
 // Every dependency of a task precedes it in this order of queues, so any set of resident CTAs makes progress.
 #pragma once
+#include <utility>
 #include <vector>
 
 namespace ipp {
@@ -32,14 +34,15 @@ enum { PH_MAGIC = 0, PH_NB, PH_NRB, PH_TB, PH_NFLAGS, PH_NF, PH_NS, PH_NC, PH_NU
        PH_TOTAL, PH_NTILE };
 // task slots
 enum { TK_TYPE = 0, TK_A, TK_B, TK_C, TK_D, TK_E, TK_F, TK_G, TK_NDEP, TK_DEP0, TK_OUT = TK_DEP0 + 2 * PLAN_MAXDEP, TK_OUTVAL,
-       TK_RSV };
-static_assert(TK_RSV < PLAN_TS, "task record too small");
+       TK_OUT2 };  // TK_OUT2: second flag receiving TK_OUTVAL (-1: none)
+static_assert(TK_OUT2 < PLAN_TS, "task record too small");
 
 struct PlanTask {
   int v[PLAN_TS];
   PlanTask() {
     for (int i = 0; i < PLAN_TS; ++i) v[i] = 0;
     for (int d = 0; d < PLAN_MAXDEP; ++d) v[TK_DEP0 + 2 * d] = -1;
+    v[TK_OUT2] = -1;
   }
   void dep(int idx, int val) {
     if (val <= 0) return;
@@ -54,24 +57,34 @@ struct PlanTask {
   }
 };
 
-inline int plan_split(int rem, int ctas) { return (4 * rem <= ctas) ? 4 : (2 * rem <= ctas) ? 2 : 1; }
-
 // Builds the plan for NP = 64 * nb.  Returns the number of ints.
-inline long chol_plan_build(int nb, int tb, int ctas, std::vector<int>& out) {
+inline long chol_plan_build(int nb, int tb, int /*ctas: no task is split by CTA count any more*/, std::vector<int>& out) {
   const int nrb = nb + 1;
   const int tmax = (nrb - 1) / tb;                    // last tile row
   const int ntile = (tmax + 1) * (tmax + 2) / 2;
   const int fF = 0, fS = nb, fA = nb + nrb, nflags = nb + nrb + ntile;
   auto tile_flag = [&](int ti, int tj) { return fA + ti * (ti + 1) / 2 + tj; };
-  std::vector<int> csplit(nb + 1, 0);                 // csplit[k] = solve parts of the panels < k
-  for (int k = 0; k < nb; ++k) csplit[k + 1] = csplit[k] + plan_split(nrb - (k + 1), ctas);
   std::vector<PlanTask> qF, qS, qC, qU;
-  std::vector<int> s_first(nb, -1);                   // queue index of S(k+1, k, part 0)
+  // S tasks of panel k: {k+1} alone, then the rest of its tile row (if any), then whole tile rows
+  auto s_groups = [&](int k, std::vector<std::pair<int, int>>& out) {
+    out.clear();
+    int i = k + 1;
+    if (i < nrb) out.push_back({i, 1}), ++i;
+    while (i < nrb) {
+      int e = (i / tb + 1) * tb;
+      if (e > nrb) e = nrb;
+      out.push_back({i, e - i});
+      i = e;
+    }
+  };
+  std::vector<std::pair<int, int>> grp;
+  std::vector<int> s_first(nb, -1);                   // queue index of S(k+1, k)
   {
     int pos = 0;
     for (int k = 0; k < nb; ++k) {
       s_first[k] = pos;
-      pos += (nrb - (k + 1)) * plan_split(nrb - (k + 1), ctas);
+      s_groups(k, grp);
+      pos += (int)grp.size();
     }
   }
 
@@ -80,7 +93,7 @@ inline long chol_plan_build(int nb, int tb, int ctas, std::vector<int>& out) {
     t.v[TK_TYPE] = PT_F;
     t.v[TK_A] = k;
     t.v[TK_B] = (k & 1) ? 1 : (k >= 2 ? 2 : 0);       // own update: panels [k - width, k)
-    t.dep(fS + k, csplit[k]);                         // L(k, p) final for every p < k
+    t.dep(fS + k, k);                                 // L(k, p) final for every p < k
     t.dep(tile_flag(k / tb, k / tb), (k & 1) ? k - 1 : k - 2);
     t.v[TK_G] = s_first[k];                           // hint: the solve on the critical chain comes next
     t.v[TK_OUT] = fF + k;
@@ -88,22 +101,21 @@ inline long chol_plan_build(int nb, int tb, int ctas, std::vector<int>& out) {
     qF.push_back(t);
   }
   for (int k = 0; k < nb; ++k) {                      // ---- S
-    const int split = plan_split(nrb - (k + 1), ctas);
-    for (int i = k + 1; i < nrb; ++i)
-      for (int h = 0; h < split; ++h) {
-        PlanTask t;
-        t.v[TK_TYPE] = PT_S;
-        t.v[TK_A] = i;
-        t.v[TK_B] = k;
-        t.v[TK_C] = h;
-        t.v[TK_D] = 64 / split;
-        t.v[TK_G] = (i == k + 1 && k + 1 < nb) ? k + 1 : -1;   // hint: F(k+1) comes next
-        t.dep(fF + k, 1);
-        t.dep(tile_flag(i / tb, k / tb), k);          // every panel < k applied to block (i, k)
-        t.v[TK_OUT] = fS + i;
-        t.v[TK_OUTVAL] = -1;                          // atomic increment
-        qS.push_back(t);
-      }
+    s_groups(k, grp);
+    for (auto [i0, nblk] : grp) {
+      PlanTask t;
+      t.v[TK_TYPE] = PT_S;
+      t.v[TK_A] = i0;
+      t.v[TK_B] = k;
+      t.v[TK_C] = nblk;
+      t.v[TK_G] = (i0 == k + 1 && k + 1 < nb) ? k + 1 : -1;   // hint: F(k+1) comes next
+      t.dep(fF + k, 1);
+      t.dep(tile_flag(i0 / tb, k / tb), k);           // every panel < k applied to the blocks (i, k)
+      t.v[TK_OUT] = fS + i0;
+      t.v[TK_OUTVAL] = k + 1;
+      t.v[TK_OUT2] = nblk > 1 ? fS + i0 + 1 : -1;
+      qS.push_back(t);
+    }
   }
   auto u_task = [&](int ti, int tj, int kb, int ke, int cmin, int skip, int applied_before) {
     PlanTask t;
@@ -115,9 +127,9 @@ inline long chol_plan_build(int nb, int tb, int ctas, std::vector<int>& out) {
     t.v[TK_E] = cmin;
     t.v[TK_F] = skip;
     t.dep(tile_flag(ti, tj), applied_before);
-    for (int i = ti * tb; i < (ti + 1) * tb && i < nrb; ++i) t.dep(fS + i, csplit[ke]);   // A operand rows
+    for (int i = ti * tb; i < (ti + 1) * tb && i < nrb; ++i) t.dep(fS + i, ke);   // A operand rows
     for (int j = tj * tb; j < (tj + 1) * tb && j < nb; ++j)
-      if (j >= cmin) t.dep(fS + j, csplit[ke]);                                           // B operand rows
+      if (j >= cmin) t.dep(fS + j, ke);                                           // B operand rows
     t.v[TK_OUT] = tile_flag(ti, tj);
     t.v[TK_OUTVAL] = ke;
     return t;

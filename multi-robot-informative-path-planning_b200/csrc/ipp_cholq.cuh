@@ -167,17 +167,58 @@ enum { QS_NONE = -1, QS_EXHAUSTED = -2 };
 constexpr int QSTATE = 8;  // ints of queue state per problem: {head F, ready F, head S, ready S, head C, ready C, -, -}
 
 // Claiming.  Each chain queue (F, S, C of every problem) has a HEAD (next task to hand out) and a READY FRONTIER
-// (every task below it has its dependencies met).  Pollers advance the frontier -- a window of tasks beyond it is
-// tested by the lanes of the polling warp in parallel, the leading run of ready ones is added with one atomicMax --
-// and claim with atomicAdd on the head whenever head < frontier: any number of CTAs claim different ready tasks in
-// the same round trip (a compare-and-swap on the head hands out one task per round trip to all contenders together:
-// measured 4x slower than the cooperative kernel).  A racing claim can land just beyond the frontier; its owner HOLDS
-// that task (tests it every poll, runs it as soon as it is ready) and keeps serving the queues meanwhile -- with
-// compare-and-swap claims, which cannot overshoot, so a CTA never holds more than one chain task.  (Waiting for a
-// held task without serving deadlocks: every CTA can end up holding a task behind an F task nobody is free to run
-// -- found by the host simulation of these rules, tests/test_chol_plan.py.)
-// The bulk queue has no frontier: claimed unconditionally, in order; the owner waits for the task's flags and serves
-// the chain queues meanwhile.
+// (every task below it has its dependencies met).  The frontier is advanced by whoever has reason to believe it can
+// move -- a CTA that has just finished a chain task (its flag is what the next tasks wait for) and every idle CTA:
+// the lanes of the polling warp test a window of tasks beyond the frontier in parallel and add the leading run of
+// ready ones with one atomicMax.  Tasks are claimed with atomicAdd on the head whenever head < frontier, so any number
+// of CTAs claim different ready tasks in the same round trip (compare-and-swap on the head hands out ONE task per
+// round trip to all contenders together: measured 4x slower than the cooperative kernel).  A racing claim can land
+// just beyond the frontier; its owner HOLDS that task (tests it every poll, runs it as soon as it is ready) and keeps
+// serving the queues meanwhile -- with compare-and-swap claims, which cannot overshoot, so a CTA never holds more than
+// one chain task.  (Waiting for a held task without serving deadlocks: every CTA can end up holding a task behind an
+// F task nobody is free to run -- found by the host simulation of these rules, tests/test_chol_plan.py.)
+// The bulk queue has no frontier: claimed unconditionally, in order, one task AHEAD (the claim and the task's
+// dependency list are fetched while the previous task computes), so that the common case -- a bulk tile whose
+// operands are long final -- costs one round trip to L2 between two tiles.
+struct QueueView {
+  const int* plan;
+  int* sched;
+  int* qstate;
+  int nflags, R;
+};
+
+// Advance the ready frontiers of problem `rsel` (< 0: of every problem).  Returns true (warp-uniform) if any moved.
+__device__ __forceinline__ bool scan_frontiers(const QueueView& v, int rsel, int lane) {
+  const int nq = rsel >= 0 ? 3 : 3 * v.R;
+  const int per = nq <= 32 ? 32 / nq : 1;  // lanes per queue; each lane tests two tasks: window 2 * per
+  bool advanced = false;
+  for (int c0 = 0; c0 < nq; c0 += 32 / per) {
+    const int c = c0 + lane / per, o = lane % per;
+    bool r0 = false, r1 = false;
+    int f = 0;
+    int* st = nullptr;
+    if (c < nq && lane < per * (32 / per)) {
+      const int q = rsel >= 0 ? c : c / v.R, r = rsel >= 0 ? rsel : c % v.R;
+      st = v.qstate + QSTATE * r + 2 * q;
+      f = ld_relaxed(st + 1);
+      const int cnt = __ldg(v.plan + PH_NF + q);
+      const int* Tq = v.plan + __ldg(v.plan + PH_OFFF + q);
+      const int* fl = v.sched + (long)r * v.nflags;
+      if (f + o < cnt) r0 = task_ready(Tq + (f + o) * PLAN_TS, fl);
+      if (f + per + o < cnt) r1 = task_ready(Tq + (f + per + o) * PLAN_TS, fl);
+    }
+    const unsigned m0 = __ballot_sync(0xffffffffu, r0), m1 = __ballot_sync(0xffffffffu, r1);
+    if (st != nullptr && o == 0) {
+      const unsigned gmask = per >= 32 ? 0xffffffffu : ((1u << per) - 1u);
+      const unsigned z0 = ~(m0 >> lane) & gmask, z1 = ~(m1 >> lane) & gmask;
+      int m = z0 ? __ffs(z0) - 1 : per;  // leading run of ready tasks
+      if (m == per) m += z1 ? __ffs(z1) - 1 : per;
+      if (m > 0) advanced = atomicMax(st + 1, f + m) >= 0;  // (the returned value makes the warp wait for the update)
+    }
+  }
+  return __any_sync(0xffffffffu, advanced);
+}
+
 template <class C>
 __global__ void __launch_bounds__(C::THREADS, 1) chol_queue_kernel(CholQ a) {
   extern __shared__ __align__(16) double smem[];
@@ -189,37 +230,104 @@ __global__ void __launch_bounds__(C::THREADS, 1) chol_queue_kernel(CholQ a) {
   int* qstate = a.sched + (long)R * nflags;
   int* bulk_head = qstate + QSTATE * R;
   int* abortf = bulk_head + 1;
-  int pend = QS_NONE;                       // this CTA's claimed, not yet started bulk task (warp 0, uniform)
+  const QueueView qv = {plan, a.sched, qstate, nflags, R};
+  const int bulk_total = __ldg(plan + PH_NU) * R;
+  // ---- warp 0 scheduling state (uniform over the warp unless noted)
+  int pend = QS_NONE;                       // this CTA's claimed, not yet started bulk task
+  int pd_idx = -1, pd_val = 0;              // lane d < PLAN_MAXDEP: dependency d of `pend`
+  bool pd_loaded = false;
   int hint_q = -1, hint_i = 0, hint_r = 0;  // successor of the task just finished (tried first)
   int held_q = -1, held_i = 0, held_r = 0;  // chain task claimed past its queue's frontier, not started yet
+  int scan_r = -1;                          // problem whose frontiers to advance before claiming (-1: none, -2: all)
   long long idle_since = 0;
   bool idle = false;
   long long st_cyc[4] = {0, 0, 0, 0}, st_t0 = clock64(), st_mark = st_t0;  // thread 0: F, S, U, acquiring
   int st_n[3] = {0, 0, 0};
-  // frontier scan: `per` lanes per queue, each testing two tasks -> a window of 2 * per tasks per queue and poll
-  const int per = nq <= 32 ? 32 / nq : 1;
+
+  auto claim_bulk = [&]() {  // lane 31 claims the next bulk task; everybody learns its index
+    int p = 0;
+    if (lane == 31) {
+      const int pos = (ld_relaxed(bulk_head) < bulk_total) ? atomicAdd(bulk_head, 1) : bulk_total;
+      p = pos < bulk_total ? pos : QS_EXHAUSTED;
+    }
+    pend = __shfl_sync(0xffffffffu, p, 31);
+    pd_loaded = false;
+  };
+  auto load_pend_deps = [&]() {
+    if (pend >= 0 && !pd_loaded) {
+      const int* T = plan + __ldg(plan + PH_OFFU) + (pend / R) * PLAN_TS;
+      if (lane < PLAN_MAXDEP) {
+        pd_idx = __ldg(T + TK_DEP0 + 2 * lane);
+        pd_val = __ldg(T + TK_DEP0 + 2 * lane + 1);
+      }
+      pd_loaded = true;
+    }
+  };
 
   for (;;) {
     if (warp == 0) {
       int got_q = -1, got_i = 0, got_r = 0;
       unsigned backoff = 0;
       for (;;) {
-        // ---- 0. the successor of the task this CTA just finished: one targeted test, claimed by compare-and-swap
+        if (pend == QS_NONE) claim_bulk();
+        load_pend_deps();
+        if (scan_r != -1) {
+          scan_frontiers(qv, scan_r == -2 ? -1 : scan_r, lane);
+          scan_r = -1;
+        }
+        // ---- one pass of independent loads: lanes 0..5 the flags of the bulk task, lane 6 the hinted successor,
+        //      lane 7 the held task, lanes 8.. the queue states
+        bool dep_ok = true;
+        if (lane < PLAN_MAXDEP && pend >= 0 && pd_idx >= 0)
+          dep_ok = ld_relaxed(a.sched + (long)(pend % R) * nflags + pd_idx) >= pd_val;
+        int special = 0;  // lane 6: hint can be claimed; lane 7: held task is ready
+        if (lane == 6 && hint_q >= 0) {
+          const int* T = plan + __ldg(plan + PH_OFFF + hint_q) + hint_i * PLAN_TS;
+          const int h = ld_relaxed(qstate + QSTATE * hint_r + 2 * hint_q);
+          special = (task_ready(T, a.sched + (long)hint_r * nflags) && h == hint_i) ? 1 : 0;
+        }
+        if (lane == 7 && held_q >= 0)
+          special = task_ready(plan + __ldg(plan + PH_OFFF + held_q) + held_i * PLAN_TS, a.sched + (long)held_r * nflags) ? 1 : 0;
+        int best = 0x7fffffff, best_rdy = 0, best_h = 0;
+        bool exhausted = held_q < 0 && pend == QS_EXHAUSTED;
+        if (lane >= 8)
+          for (int c = lane - 8; c < nq; c += 24) {
+            const int q = c / R, r = c % R;
+            const int* st = qstate + QSTATE * r + 2 * q;
+            const int h = ld_relaxed(st), f = ld_relaxed(st + 1);
+            if (h < __ldg(plan + PH_NF + q)) exhausted = false;
+            if (h < f && c < best) {
+              best = c;
+              best_rdy = f;
+              best_h = h;
+            }
+          }
+        const bool pend_ready = pend >= 0 && (__ballot_sync(0xffffffffu, dep_ok) & 0x3fu) == 0x3fu;
+        const int hint_ok = __shfl_sync(0xffffffffu, special, 6), held_ok = __shfl_sync(0xffffffffu, special, 7);
+        int win = best;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) win = min(win, __shfl_xor_sync(0xffffffffu, win, o));
+        const bool all_exhausted = __all_sync(0xffffffffu, exhausted);
+        // ---- decide: held > hint > chain queues > bulk
+        if (held_q >= 0 && held_ok) {
+          got_q = held_q;
+          got_i = held_i;
+          got_r = held_r;
+          held_q = -1;
+          break;
+        }
         if (hint_q >= 0) {
+          const int hq = hint_q;
+          hint_q = -1;
           int ok = 0;
-          if (lane == 0) {
-            int* hp = qstate + QSTATE * hint_r + 2 * hint_q;
-            const int* T = plan + __ldg(plan + PH_OFFF + hint_q) + hint_i * PLAN_TS;
-            const int h = ld_relaxed(hp);
-            const bool rdy = task_ready(T, a.sched + (long)hint_r * nflags);
-            if (h == hint_i && rdy) {
+          if (hint_ok) {
+            if (lane == 0) {
+              int* hp = qstate + QSTATE * hint_r + 2 * hq;
               ok = (atomicCAS(hp, hint_i, hint_i + 1) == hint_i);
               if (ok) atomicMax(hp + 1, hint_i + 1);
             }
+            ok = __shfl_sync(0xffffffffu, ok, 0);
           }
-          ok = __shfl_sync(0xffffffffu, ok, 0);
-          const int hq = hint_q;
-          hint_q = -1;
           if (ok) {
             got_q = hq;
             got_i = hint_i;
@@ -227,41 +335,11 @@ __global__ void __launch_bounds__(C::THREADS, 1) chol_queue_kernel(CholQ a) {
             break;
           }
         }
-        // ---- 1a. a held task that has become ready goes first
-        if (held_q >= 0) {
-          int ok = 0;
-          if (lane == 0)
-            ok = task_ready(plan + __ldg(plan + PH_OFFF + held_q) + held_i * PLAN_TS, a.sched + (long)held_r * nflags) ? 1 : 0;
-          ok = __shfl_sync(0xffffffffu, ok, 0);
-          if (ok) {
-            got_q = held_q;
-            got_i = held_i;
-            got_r = held_r;
-            held_q = -1;
-            break;
-          }
-        }
-        // ---- 1b. claim from the highest-priority queue whose head is behind its frontier (queue c = q * R + r)
-        int best = 0x7fffffff, best_rdy = 0, best_h = 0;
-        bool exhausted = held_q < 0;
-        for (int c = lane; c < nq; c += 32) {
-          const int q = c / R, r = c % R;
-          const int* st = qstate + QSTATE * r + 2 * q;
-          const int h = ld_relaxed(st), f = ld_relaxed(st + 1);
-          if (h < __ldg(plan + PH_NF + q)) exhausted = false;
-          if (h < f && c < best) {
-            best = c;
-            best_rdy = f;
-            best_h = h;
-          }
-        }
-        int win = best;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) win = min(win, __shfl_xor_sync(0xffffffffu, win, o));
         if (win != 0x7fffffff) {
           const int q = win / R, r = win % R;
+          const int owner = 8 + win % 24;
           int h = 0, ok = 0;
-          if (lane == (win & 31)) {
+          if (lane == owner) {
             int* hp = qstate + QSTATE * r + 2 * q;
             if (held_q < 0) {
               h = atomicAdd(hp, 1);
@@ -272,8 +350,8 @@ __global__ void __launch_bounds__(C::THREADS, 1) chol_queue_kernel(CholQ a) {
               ok = (atomicCAS(hp, best_h, best_h + 1) == best_h) ? 1 : 0;
             }
           }
-          ok = __shfl_sync(0xffffffffu, ok, win & 31);
-          h = __shfl_sync(0xffffffffu, h, win & 31);
+          ok = __shfl_sync(0xffffffffu, ok, owner);
+          h = __shfl_sync(0xffffffffu, h, owner);
           if (ok == 1) {
             got_q = q;
             got_i = h;
@@ -287,61 +365,19 @@ __global__ void __launch_bounds__(C::THREADS, 1) chol_queue_kernel(CholQ a) {
           }
           continue;  // lost a race, claimed past the end, or now holding: look again
         }
-        // ---- 2. nothing claimable: advance the frontiers (every lane tests two tasks beyond the frontier of its
-        //         queue) and test this CTA's bulk task
-        bool advanced = false;
-        for (int c0 = 0; c0 < nq; c0 += 32 / per) {
-          const int c = c0 + lane / per, o = lane % per;
-          bool r0 = false, r1 = false;
-          int f = 0, cnt = 0;
-          int* st = nullptr;
-          if (c < nq && lane < per * (32 / per)) {
-            const int q = c / R, r = c % R;
-            st = qstate + QSTATE * r + 2 * q;
-            f = ld_relaxed(st + 1);
-            cnt = __ldg(plan + PH_NF + q);
-            const int* Tq = plan + __ldg(plan + PH_OFFF + q);
-            const int* fl = a.sched + (long)r * nflags;
-            if (f + o < cnt) r0 = task_ready(Tq + (f + o) * PLAN_TS, fl);
-            if (f + per + o < cnt) r1 = task_ready(Tq + (f + per + o) * PLAN_TS, fl);
-          }
-          const unsigned m0 = __ballot_sync(0xffffffffu, r0), m1 = __ballot_sync(0xffffffffu, r1);
-          if (st != nullptr && o == 0) {
-            const unsigned gmask = per >= 32 ? 0xffffffffu : ((1u << per) - 1u);
-            const unsigned g0 = (m0 >> (lane)) & gmask, g1 = (m1 >> (lane)) & gmask;
-            int m = __ffs(~g0 & gmask) ? __ffs(~g0 & gmask) - 1 : per;  // leading run of ready tasks
-            if (m == per) m += __ffs(~g1 & gmask) ? __ffs(~g1 & gmask) - 1 : per;
-            if (m > 0) advanced = atomicMax(st + 1, f + m) >= 0;  // (the returned value makes the warp wait for the update)
-          }
-        }
-        if (__any_sync(0xffffffffu, advanced)) continue;  // something became claimable: claim it
-        int take = 0;
-        if (lane == 31) {
-          if (pend == QS_NONE) {
-            const int total = __ldg(plan + PH_NU) * R;
-            const int pos = (ld_relaxed(bulk_head) < total) ? atomicAdd(bulk_head, 1) : total;
-            pend = pos < total ? pos : QS_EXHAUSTED;
-          }
-          if (pend >= 0) {
-            exhausted = false;
-            const int* T = plan + __ldg(plan + PH_OFFU) + (pend / R) * PLAN_TS;
-            take = task_ready(T, a.sched + (long)(pend % R) * nflags) ? 1 : 0;
-          }
-        }
-        pend = __shfl_sync(0xffffffffu, pend, 31);
-        take = __shfl_sync(0xffffffffu, take, 31);
-        if (take) {
+        if (pend_ready) {
           got_q = 3;
           got_i = pend / R;
           got_r = pend % R;
-          pend = QS_NONE;
+          claim_bulk();  // one ahead: the index and its dependency list arrive while this task computes
           break;
         }
-        if (__all_sync(0xffffffffu, exhausted)) {
+        if (all_exhausted) {
           got_q = -1;
           break;
         }
-        // ---- nothing to do right now: watchdog, back off, poll again
+        // ---- nothing to do right now: advance the frontiers; if that changed nothing, watchdog and back off
+        if (scan_frontiers(qv, -1, lane)) continue;
         int stop = 0;
         if (lane == 0) {
           const long long now = clock64();
@@ -388,12 +424,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) chol_queue_kernel(CholQ a) {
     if (type == PT_F) {
       cholq_factor<C::THREADS>(A, a.ld, pa, pb, smem, a.vbuf + (long)slot * a.vstride + a.info_off);
     } else if (type == PT_S) {
-      if (pd == 64)
-        chol_trsm_block<C::THREADS, 64>(A, a.ld, pb, pa, pc, smem);
-      else if (pd == 32)
-        chol_trsm_block<C::THREADS, 32>(A, a.ld, pb, pa, pc, smem);
-      else
-        chol_trsm_block<C::THREADS, 16>(A, a.ld, pb, pa, pc, smem);
+      for (int b = 0; b < pc; ++b) chol_trsm_block<C::THREADS, 64>(A, a.ld, pb, pa + b, 0, smem);
     } else {
       cholq_update_tile<C>(A, a.ld, a.rows_total, a.np, pa * C::BM, pb * C::BN, pc * BLK, pd * BLK, __ldg(T + TK_E) * BLK,
                            __ldg(T + TK_F), smem);
@@ -406,24 +437,28 @@ __global__ void __launch_bounds__(C::THREADS, 1) chol_queue_kernel(CholQ a) {
     }
     // every executor ends with a CTA barrier after its last global store: publish
     if (t == 0) {
-      const int oi = __ldg(T + TK_OUT), ov = __ldg(T + TK_OUTVAL);
-      if (ov < 0)
-        red_add_release(flags + oi, 1);
-      else
-        st_release(flags + oi, ov);
+      const int oi = __ldg(T + TK_OUT), ov = __ldg(T + TK_OUTVAL), o2 = __ldg(T + TK_OUT2);
+      st_release(flags + oi, ov);
+      if (o2 >= 0) st_release(flags + o2, ov);
     }
-    // successor on the critical chain: F(k) -> S(k+1, k) (first solve task of panel k), S(k+1, k) -> F(k+1)
-    if (a.use_hints && warp == 0) {
-      if (type == PT_F) {
-        hint_q = 1;
-        hint_i = __ldg(T + TK_G);  // index of S(k+1, k, 0) in the S queue (-1: none)
-        hint_r = r;
-        if (hint_i < 0) hint_q = -1;
-      } else if (type == PT_S && pa == pb + 1 && __ldg(T + TK_G) >= 0) {
-        hint_q = 0;
-        hint_i = __ldg(T + TK_G);  // F(k+1), set on the last part of S(k+1, k)
-        hint_r = r;
+    if (warp == 0) {
+      // a finished chain task is what the next chain tasks wait for: advance this problem's frontiers before claiming
+      // (and a bulk tile close behind the front: the chain tasks of the next super-panels wait for its flag)
+      scan_r = (q != 3 || pb * (C::BM / BLK) - pc <= 6) ? r : -1;
+      // successor on the critical chain: F(k) -> S(k+1, k), S(k+1, k) -> F(k+1)
+      if (a.use_hints) {
+        const int g = __ldg(T + TK_G);
+        if (type == PT_F && g >= 0) {
+          hint_q = 1;
+          hint_i = g;
+          hint_r = r;
+        } else if (type == PT_S && g >= 0) {
+          hint_q = 0;
+          hint_i = g;
+          hint_r = r;
+        }
       }
+      load_pend_deps();  // the claim made one task ago has arrived: fetch its dependency list now
     }
     __syncthreads();  // s_task is rewritten by warp 0 in the next round
   }

@@ -238,17 +238,12 @@ class PointSourceField:
             gp.fit(waypoints, y_log)
             return None, None
         gp.fit(waypoints, y_log)
-        if hasattr(gp, "predict_grid_device"):
-            w = self.workspace_size
-            nx, ny = self.x.shape[0], self.y.shape[0]
-            if self.grid_group is not None:
-                from mripp_b200.dist import sharded_grid_posterior
+        w = self.workspace_size
+        nx, ny = self.x.shape[0], self.y.shape[0]
+        if self.grid_group is not None:
+            from mripp_b200.dist import sharded_grid_posterior
 
-                z, std = sharded_grid_posterior(gp, w, nx, ny, self.grid_group)
-            else:
-                z, std = gp.predict_grid_host(w[0], w[1], nx, w[2], w[3], ny)
-            return z.reshape(self.X.shape), std
-        # generic estimator (the CPU test seam): the reference's own three lines
-        r = np.column_stack((self.X.ravel(), self.Y.ravel()))
-        z_log, std = gp.predict(r, return_std=True)
-        return 10 ** z_log.reshape(self.X.shape), std
+            z, std = sharded_grid_posterior(gp, w, nx, ny, self.grid_group)
+        else:
+            z, std = gp.predict_grid_host(w[0], w[1], nx, w[2], w[3], ny)  # one path: the fused lattice posterior
+        return z.reshape(self.X.shape), std

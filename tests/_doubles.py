@@ -44,6 +44,13 @@ class OracleGP:
         self.X_train_ = X
         return self
 
+    def predict_grid_host(self, x0, x1, nx, y0, y1, ny):
+        """The estimator interface PointSourceField.predict_spatial_field calls, in the reference's own three lines
+        (point_source.py:350-352) on the numpy oracle -- the product itself has no CPU branch."""
+        Xg, Yg = np.meshgrid(np.linspace(x0, x1, nx), np.linspace(y0, y1, ny))
+        z_log, std = self.predict(np.column_stack((Xg.ravel(), Yg.ravel())), return_std=True)
+        return 10 ** z_log, std
+
     def predict(self, X, return_std=False):
         X = np.asarray(X, float).reshape(-1, 2)
         if self.state is None:

@@ -20,7 +20,7 @@ HDR, TS, MAXDEP = 16, 24, 6
 (PH_MAGIC, PH_NB, PH_NRB, PH_TB, PH_NFLAGS, PH_NF, PH_NS, PH_NC, PH_NU, PH_OFFF, PH_OFFS, PH_OFFC, PH_OFFU, PH_TS, PH_TOTAL,
  PH_NTILE) = range(16)
 TK_TYPE, TK_A, TK_B, TK_C, TK_D, TK_E, TK_F, TK_G, TK_NDEP, TK_DEP0 = range(10)
-TK_OUT, TK_OUTVAL = TK_DEP0 + 2 * MAXDEP, TK_DEP0 + 2 * MAXDEP + 1
+TK_OUT, TK_OUTVAL, TK_OUT2 = TK_DEP0 + 2 * MAXDEP, TK_DEP0 + 2 * MAXDEP + 1, TK_DEP0 + 2 * MAXDEP + 2
 
 
 def build_plan(n, ctas):
@@ -48,7 +48,7 @@ class Sim:
         self.final = [set() for _ in range(R)]
         self.parts = [dict() for _ in range(R)]
         self.writing = [dict() for _ in range(R)]
-        self.ctas = [dict(pend=None, hint=None, busy_until=0, task=None, blocked=None) for _ in range(n_ctas)]
+        self.ctas = [dict(pend=None, hint=None, busy_until=0, task=None, blocked=None, scan=None) for _ in range(n_ctas)]
         self.executed = 0
 
     def task(self, q, i):
@@ -69,8 +69,9 @@ class Sim:
             k, w = int(T[TK_A]), int(T[TK_B])
             return dict(kind="F", writes=[(k, k)], reads=[(k, p) for p in range(k - w, k)], before=k - w, panels=range(k - w, k))
         if ty == 1:
-            i, k = int(T[TK_A]), int(T[TK_B])
-            return dict(kind="S", writes=[(i, k)], reads=[(k, k)], before=k, panels=range(0), part=(int(T[TK_C]), 64 // int(T[TK_D])))
+            i, k, nblk = int(T[TK_A]), int(T[TK_B]), int(T[TK_C])
+            assert nblk >= 1 and i + nblk <= self.nrb
+            return dict(kind="S", writes=[(i + b, k) for b in range(nblk)], reads=[(k, k)], before=k, panels=range(0))
         ti, tj, kb, ke, cmin, skip = (int(T[x]) for x in (TK_A, TK_B, TK_C, TK_D, TK_E, TK_F))
         writes, reads = [], set()
         for i in range(ti * self.tb, min((ti + 1) * self.tb, self.nrb)):
@@ -93,14 +94,8 @@ class Sim:
             assert blk in self.final[r], (b["kind"], "reads a block that is not final", blk)
             assert blk not in self.writing[r]
         for blk in b["writes"]:
-            if b["kind"] == "S":
-                h, split = b["part"]
-                assert (blk, h) not in self.writing[r] and blk not in self.final[r]
-                self.writing[r][(blk, h)] = 1
-            else:
-                assert blk not in self.writing[r], (b["kind"], "two tasks write", blk)
-                assert not any(k[0] == blk for k in self.writing[r] if isinstance(k[0], tuple))
-                self.writing[r][blk] = 1
+            assert blk not in self.writing[r], (b["kind"], "two tasks write", blk)
+            self.writing[r][blk] = 1
             assert blk not in self.final[r]
             assert self.applied[r].get(blk, 0) == b["before"], (b["kind"], blk, self.applied[r].get(blk, 0), b["before"])
         cta["task"] = (T, r, b)
@@ -109,31 +104,21 @@ class Sim:
     def finish(self, cta):
         T, r, b = cta["task"]
         for blk in b["writes"]:
-            if b["kind"] == "S":
-                h, split = b["part"]
-                del self.writing[r][(blk, h)]
-                self.parts[r][blk] = self.parts[r].get(blk, 0) + 1
-                if self.parts[r][blk] == split:
-                    self.final[r].add(blk)
-            else:
-                del self.writing[r][blk]
-                self.applied[r][blk] = self.applied[r].get(blk, 0) + len(b["panels"])
-                if b["kind"] == "F":
-                    assert self.applied[r][blk] == blk[1]
-                    self.final[r].add(blk)
-        oi, ov = int(T[TK_OUT]), int(T[TK_OUTVAL])
-        if ov < 0:
-            self.flags[r, oi] += 1
-        else:
-            assert self.flags[r, oi] < ov
-            self.flags[r, oi] = ov
+            del self.writing[r][blk]
+            self.applied[r][blk] = self.applied[r].get(blk, 0) + len(b["panels"])
+            if b["kind"] in ("F", "S"):
+                assert self.applied[r][blk] == blk[1]
+                self.final[r].add(blk)
+        ov = int(T[TK_OUTVAL])
+        for oi in (int(T[TK_OUT]), int(T[TK_OUT2])):
+            if oi >= 0:
+                assert self.flags[r, oi] < ov
+                self.flags[r, oi] = ov
         ty = int(T[TK_TYPE])
         cta["hint"] = None
-        if self.hints:
-            if ty == 0 and int(T[TK_G]) >= 0:
-                cta["hint"] = (1, int(T[TK_G]), r)
-            elif ty == 1 and int(T[TK_A]) == int(T[TK_B]) + 1 and int(T[TK_G]) >= 0:
-                cta["hint"] = (0, int(T[TK_G]), r)
+        if self.hints and ty in (0, 1) and int(T[TK_G]) >= 0:
+            cta["hint"] = (1 - ty, int(T[TK_G]), r)
+        cta["scan"] = r if ty != 2 or self.rng.random() < 0.3 else None  # chain finishers advance their problem's frontiers
         cta["task"] = None
         self.executed += 1
 
@@ -143,6 +128,15 @@ class Sim:
         then atomicAdd claim where head < frontier, else frontier scan, else the bulk task.  Returns 'exit', 'idle',
         'started' or 'blocked' (claimed past the frontier: waits for that one task)."""
         heads0, front0 = snap
+        if cta["scan"] is not None:
+            r = cta["scan"]
+            cta["scan"] = None
+            for q in range(3):
+                f, m = int(self.front[r, q]), 0
+                while m < self.window and f + m < self.cnt[q] and self.ready(self.task(q, f + m), r):
+                    m += 1
+                self.front[r, q] = f + m
+            front0 = self.front.copy()
         if cta["hint"] is not None:
             q, i, r = cta["hint"]
             cta["hint"] = None
@@ -179,18 +173,6 @@ class Sim:
                     self.start(cta, q, h, r, now)
                     return "started"
                 return "idle"
-        advanced = False
-        for c in range(3 * self.R):
-            q, r = divmod(c, self.R)
-            f = int(front0[r, q])
-            m = 0
-            while m < self.window and f + m < self.cnt[q] and self.ready(self.task(q, f + m), r):
-                m += 1
-            if m:
-                self.front[r, q] = max(self.front[r, q], f + m)
-                advanced = True
-        if advanced:
-            return "idle"
         if cta["pend"] is None:
             total = self.cnt[3] * self.R
             if self.bulk_head < total:
@@ -205,6 +187,18 @@ class Sim:
                 cta["pend"] = None
                 self.start(cta, 3, ti, r, now)
                 return "started"
+        advanced = False
+        for c in range(3 * self.R):
+            q, r = divmod(c, self.R)
+            f = int(front0[r, q])
+            m = 0
+            while m < self.window and f + m < self.cnt[q] and self.ready(self.task(q, f + m), r):
+                m += 1
+            if m:
+                self.front[r, q] = max(self.front[r, q], f + m)
+                advanced = True
+        if advanced:
+            return "idle"
         return "exit" if exhausted else "idle"
 
     def run(self):

@@ -1,0 +1,129 @@
+"""Round-2 CPU tests: the oracle and the product's host logic against the round-2 reference goldens
+(tests/golden/*_r2.npz, written by oracle/make_golden_r2.py from the unmodified reference):
+the UCB selector of rrt_thread.py:371-401, GP cases at n = 500 / 2000 (configs[1] / configs[2]), and whole MR_IPP
+runs with 3 and 8 agents and with a rectangle obstacle."""
+import types
+
+import numpy as np
+import pytest
+
+from mripp_b200.src.point_source.point_source import PointSourceField
+from mripp_b200.src.rrt import rrt as R
+from mripp_b200.src.rrt.rrt_utils import TreeArrays
+from oracle import gp_oracle as O
+from oracle import rrt_oracle as T
+from tests._doubles import OracleGP, OracleScorer
+
+
+class FastGP(OracleGP):
+    full = False
+
+
+def _nodes_from(pts, parent):
+    nodes = []
+    for k in range(len(pts)):
+        nd = T.Node(pts[k])
+        nd.index = k
+        nodes.append(nd)
+    for k in range(len(pts)):
+        if parent[k] >= 0:
+            nodes[k].parent = nodes[parent[k]]
+            nodes[parent[k]].children.append(nodes[k])
+    return nodes
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_oracle_ucb_selector_matches_reference(gold, tag):
+    """rrt_thread.py:371-401 restated in oracle/rrt_oracle.py::ucb_select: acquisition values and chosen path."""
+    g = gold("ucb_golden_r2.npz")
+    th = g[f"{tag}_theta"]
+    st = O.fit(g[f"{tag}_X"], np.log10(np.maximum(g[f"{tag}_meas"], 1e-6)), float(np.exp(th[0])), float(np.exp(th[1])),
+               optimize=False)
+    nodes = _nodes_from(g[f"{tag}_pts"], g[f"{tag}_parent_final"])
+    leaves = [nd for nd in nodes if not nd.children]
+    assert np.array_equal(np.array([nd.point for nd in leaves]), g[f"{tag}_leaf_pts"])
+    mu, sd, _ = O.predict(st, g[f"{tag}_leaf_pts"])
+    assert np.abs(mu - g[f"{tag}_mu"]).max() <= 1e-7 and np.abs(sd - g[f"{tag}_sd"]).max() <= 1e-7
+    path, acq = T.ucb_select(nodes, lambda P: O.predict(st, P)[:2], list(g[f"{tag}_visited"]), float(g[f"{tag}_beta"]), 2.5,
+                             float(g[f"{tag}_budget"]))
+    # the normalisation divides by std(mu) and std(sigma) over the leaves: 1e-7 absolute in mu / sigma -> 1e-6 here
+    assert np.abs(acq - g[f"{tag}_acq"]).max() <= 1e-6 * max(1.0, float(g[f"{tag}_beta"]))
+    assert int(np.argmax(acq)) == int(np.argmax(g[f"{tag}_acq"]))
+    assert np.array_equal(np.array(path), g[f"{tag}_path"])
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_product_ucb_selector_host_logic(gold, tag):
+    """The product's ucb_path_selection (src/rrt/rrt.py) over the structure-of-arrays tree: leaf order, argmax and the
+    budget walk are the reference's; the posterior comes from the oracle double here (device: tests/test_r2_gpu.py)."""
+    g = gold("ucb_golden_r2.npz")
+    th = g[f"{tag}_theta"]
+    gp = OracleGP(kernel=types.SimpleNamespace(constant_value=float(np.exp(th[0])), length_scale=float(np.exp(th[1]))))
+    gp.full = False
+    gp.fit(g[f"{tag}_X"], np.log10(np.maximum(g[f"{tag}_meas"], 1e-6)))
+    tree = TreeArrays.from_snapshot(g[f"{tag}_pts"], g[f"{tag}_parent_final"])
+    me = types.SimpleNamespace(trees_soa=[tree], scenario=types.SimpleNamespace(gp=gp), scorer=OracleScorer(),
+                               agents_full_path=[list(g[f"{tag}_visited"])], beta_t=float(g[f"{tag}_beta"]),
+                               d_waypoint_distance=2.5, uncertainty_reduction=[])
+    path = R.ucb_path_selection(me, 0, g[f"{tag}_start"], float(g[f"{tag}_budget"]))
+    assert np.array_equal(np.array(path), g[f"{tag}_path"])
+    assert me.uncertainty_reduction[0] == pytest.approx(float(g[f"{tag}_mean_std"]), abs=1e-7)
+
+
+@pytest.mark.parametrize("tag", ["n500", "n2000"])
+def test_oracle_gp_large_cases_match_reference(gold, tag):
+    """configs[1] / configs[2] sizes: LML + gradient at fixed thetas and the fixed-theta posterior (explicit points and
+    the strided C2 / C3 lattice) of the oracle against the reference's own sklearn run."""
+    g = gold("gp_golden_r2.npz")
+    X, ylog = g[f"{tag}_X"], np.log10(np.maximum(g[f"{tag}_meas"], 1e-6))
+    yn, ym, ys = O.normalise_y(ylog)
+    assert ym == float(g[f"{tag}_ymean"]) and ys == float(g[f"{tag}_ystd"])
+    for th, v_ref, g_ref in zip(g[f"{tag}_thetas"], g[f"{tag}_lml"], g[f"{tag}_grad"]):
+        v, gr = O.lml(th, X, yn)
+        st = O.fit(X, ylog, float(np.exp(th[0])), float(np.exp(th[1])), optimize=False)
+        aa = float(st["alpha"] @ st["alpha"])
+        assert abs(v - v_ref) <= 1e-10 * abs(v_ref) + 16 * np.finfo(float).eps * float(np.exp(th[0])) * aa
+        assert np.abs(gr - g_ref).max() <= 1e-6 * max(1.0, float(np.abs(g_ref).max()), 1e-9 * aa)
+    th = g[f"{tag}_theta_fit"]
+    st = O.fit(X, ylog, float(np.exp(th[0])), float(np.exp(th[1])), optimize=False)
+    mean, std, _ = O.predict(st, g[f"{tag}_Q"])
+    assert np.abs(mean - g[f"{tag}_qmean"]).max() <= 1e-7 and np.abs(std - g[f"{tag}_qstd"]).max() <= 1e-7
+    W = int(g[f"{tag}_W"])
+    _, _, r, _ = O.workspace_grid((0, W, 0, W))
+    gm, gs, _ = O.predict(st, r[g[f"{tag}_gidx"]])
+    assert np.abs(gm - g[f"{tag}_gmean"]).max() <= 1e-7 and np.abs(gs - g[f"{tag}_gstd"]).max() <= 1e-7
+
+
+MULTI = [("mripp_3a", []), ("mripp_8a", []),
+         ("mripp_2a_obst", [{"type": "rectangle", "x": 14, "y": 12, "width": 6, "height": 5}])]
+MULTI_COMMON = dict(d_waypoint_distance=2.5, budget_iter=2, n_samples=60, s_stages=4, max_sources=2, lambda_b=1, beta_t=5.0,
+                    stage_lambda=0.5)
+
+
+def run_multi(g, tag, obstacles, make_scenario, make_strategy):
+    """Shared by the CPU (doubles) and the device test: one MR_IPP run at the golden's seed and agent count, compared
+    bit for bit with the reference's waypoints, measurements, per-agent paths, source estimates and RNG position."""
+    seed, agents, budget = int(g[f"{tag}_seed"]), int(g[f"{tag}_num_agents"]), int(g[f"{tag}_budget"])
+    sc = make_scenario(num_sources=2, workspace_size=(0, 40, 0, 40), obstacles=obstacles, seed=seed)
+    assert np.array_equal(np.array(sc.sources), g[f"{tag}_sources"])
+    np.random.seed(2000 + seed)
+    st = make_strategy(sc, num_agents=agents, budget=budget, **MULTI_COMMON)
+    # agents start spread along the bottom edge (rrt.py:555-558)
+    assert len(st.agent_positions) == agents
+    Z, std = st.run()
+    assert np.array_equal(np.asarray(st.obs_wp, float), g[f"{tag}_obs_wp"])
+    assert np.array_equal(np.asarray(st.measurements, float), g[f"{tag}_meas"])
+    for i, p in enumerate(st.agents_full_path):
+        assert np.array_equal(np.array(p, float).reshape(-1, 2), g[f"{tag}_path{i}"]), f"agent {i}"
+    assert np.array_equal(np.asarray(st.best_estimates, float).reshape(-1, 3), g[f"{tag}_best_estimates"])
+    assert np.array_equal(np.random.uniform(size=3), g[f"{tag}_rng_after"])
+    return sc, st, Z, std
+
+
+@pytest.mark.parametrize("tag,obstacles", MULTI, ids=[m[0] for m in MULTI])
+def test_multi_agent_runs_identical_host_logic(gold, tag, obstacles):
+    """configs[2] / configs[3] agent counts (3 and 8) and an obstacle run: the N > 1 start rule (rrt.py:555-558), the
+    per-iteration agent loop (:696-711) and exploitation_penalty over all agents (:246-252) against the reference."""
+    g = gold("runs_golden_r2.npz")
+    run_multi(g, tag, obstacles, lambda **kw: PointSourceField(gp_factory=FastGP, **kw),
+              lambda sc, **kw: R.MR_IPP(sc, scorer=OracleScorer(), **kw))
