@@ -8,13 +8,13 @@
 //                 the whole previous super-panel (k even: blocks k-2, k-1) or the panel k-1 (k odd), so that the
 //                 critical chain F(k) -> S(k+1, k) -> F(k+1) never waits for a bulk tile.
 //   S(i0, k, nblk) panel solve of row blocks i0 .. i0 + nblk - 1 against L_kk: the block right under the diagonal
-//                 (i0 = k + 1, the one the chain waits for) alone, the others one task per tile row.
-//   UC(tile, 2s)  rank-64 update of block column 2s+1 by panel 2s (inside super-panel s).
+//                 (i0 = k + 1, the one the chain waits for) alone, the others one task per tile row.  For k odd it
+//                 first applies panel k-1 (the first half of its own super-panel) to its blocks itself.
 //   U2(tile, s)   rank-128 update of a tile right of super-panel s by panels 2s, 2s+1 (one read-modify-write of the
 //                 tile per TWO panels: half the traffic and twice the k depth of a per-panel update).
 // Flags (per problem; all monotone counters): F[k] in {0,1}; S[i] = number of panels row block i is solved for;
 // A[tile] = number of panels applied to the tile.
-// Queues: F, S and C (UC + the U2 tiles of the column right behind the super-panel, i.e. everything the chain waits
+// Queues: F, S and C (the U2 tiles of the columns right behind the super-panel, i.e. everything the chain waits
 // for) are claimed in order and ONLY WHEN READY (a CTA never blocks on them); the bulk queue U (the rest of U2) is
 // claimed in order unconditionally and its owner waits for the dependencies -- polling the chain queues meanwhile.
 // Every dependency of a task precedes it in this order of queues, so any set of resident CTAs makes progress.
@@ -108,9 +108,14 @@ inline long chol_plan_build(int nb, int tb, int /*ctas: no task is split by CTA 
       t.v[TK_A] = i0;
       t.v[TK_B] = k;
       t.v[TK_C] = nblk;
+      t.v[TK_D] = k & 1;                              // own update: panel k - 1 (k odd)
       t.v[TK_G] = (i0 == k + 1 && k + 1 < nb) ? k + 1 : -1;   // hint: F(k+1) comes next
       t.dep(fF + k, 1);
-      t.dep(tile_flag(i0 / tb, k / tb), k);           // every panel < k applied to the blocks (i, k)
+      t.dep(tile_flag(i0 / tb, k / tb), k & ~1);      // every earlier super-panel applied to the blocks (i, k)
+      if (k & 1) {                                    // operands of the own update: L(i, k-1), L(k, k-1)
+        t.dep(fS + k, k);
+        for (int b = 0; b < nblk; ++b) t.dep(fS + i0 + b, k);
+      }
       t.v[TK_OUT] = fS + i0;
       t.v[TK_OUTVAL] = k + 1;
       t.v[TK_OUT2] = nblk > 1 ? fS + i0 + 1 : -1;
@@ -136,16 +141,6 @@ inline long chol_plan_build(int nb, int tb, int /*ctas: no task is split by CTA 
   };
   for (int s = 0; 2 * s < nb; ++s) {
     const int p0 = 2 * s, p1 = 2 * s + 1;
-    if (p1 < nb) {
-      // UC: column p1 receives panel p0; the diagonal block (p1, p1) is F(p1)'s own
-      const int tj = p1 / tb;
-      for (int ti = tj; ti <= tmax; ++ti) {
-        bool any = false;
-        for (int i = ti * tb; i < (ti + 1) * tb && i < nrb; ++i) any |= (i > p1);
-        if (!any) continue;
-        qC.push_back(u_task(ti, tj, p0, p1, p1, p1, p0));
-      }
-    }
     const int ke = (p1 < nb) ? p1 + 1 : p1;
     // U2: tiles whose columns start at or beyond block 2s + 2; block (2s+2, 2s+2) is F(2s+2)'s own
     const int tj0 = (2 * s + 2 + tb - 1) / tb;

@@ -32,6 +32,11 @@ __device__ __forceinline__ int ld_relaxed(const int* p) {
   asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void st_release(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
 }
@@ -112,6 +117,105 @@ __device__ __forceinline__ void cholq_factor(double* __restrict__ A, long ld, in
     const int r = e / (BLK / 2), cc = (e % (BLK / 2)) * 2;
     *reinterpret_cast<double2*>(A + (long)(j0 + r) * ld + j0 + cc) =
         make_double2(cc <= r ? D[r * PSTR + cc] : 0.0, cc + 1 <= r ? D[r * PSTR + cc + 1] : 0.0);
+  }
+  __syncthreads();
+}
+
+// S task: rows [64 i0, 64 (i0 + nblk)) of block column k:  X <- (X - Pa Pb^T) L_kk^-T, where Pa = A(rows, panel k-1),
+// Pb = A(k, panel k-1) is the one panel the bulk leaves to this task (width 1: k odd, the first half of its
+// super-panel; width 0: nothing).  Blocked forward substitution: 8-column groups; inside a group every row is solved
+// by one thread with the 8 x 8 triangle of L_kk read as shared-memory broadcasts (reciprocal pivots: one divide per
+// column, as in chol_trsm_block), the groups to its right are then updated on the DMMA pipe.  16 CTA barriers per
+// task; 64 dependent steps per row in all, but each is an FMA out of registers instead of a shared-memory sweep
+// (chol_trsm_block: 6 us per 64 rows; this: ~2 us per 128 rows).
+template <int SOLVE_ROWS>
+constexpr size_t solve_smem() {
+  return sizeof(double) * ((SOLVE_ROWS + SOLVE_ROWS + BLK) * QSTR + BLK);
+}
+template <int NT, int SOLVE_ROWS>
+__device__ __forceinline__ void cholq_solve(double* __restrict__ A, long ld, int k, int i0, int nblk, int width, double* psm) {
+  const int rows = BLK * nblk, t = threadIdx.x, warp = t >> 5, lane = t & 31, g = lane >> 2, tg = lane & 3;
+  double* Xs = psm;                          // rows x 64, pitch QSTR
+  double* Pa = psm + SOLVE_ROWS * QSTR;      // rows x 64 (own update), then unused
+  double* Ls = psm + 2 * SOLVE_ROWS * QSTR;  // Pb during the own update, then L_kk
+  double* rinv = Ls + BLK * QSTR;
+  const int j0 = BLK * k, r0 = BLK * i0, p0 = BLK * (k - 1);
+  auto load_block = [&](double* dst, int grow0, int gcol0, int nrows) {
+    for (int e = t; e < nrows * (BLK / 2); e += NT) {
+      const int r = e / (BLK / 2), cc = (e % (BLK / 2)) * 2;
+      *reinterpret_cast<double2*>(dst + r * QSTR + cc) =
+          __ldcg(reinterpret_cast<const double2*>(A + (long)(grow0 + r) * ld + gcol0 + cc));
+    }
+  };
+  load_block(Xs, r0, j0, rows);
+  if (width > 0) {
+    load_block(Pa, r0, p0, rows);
+    load_block(Ls, j0, p0, BLK);
+  }
+  __syncthreads();
+  constexpr int NW = NT / 32;
+  if (width > 0) {  // Xs -= Pa Pb^T: warp w owns rows [w * rows / NW, ...) in 8-row groups, all 64 columns
+    const int rpw = rows / NW;
+    for (int m0 = 0; m0 < rpw; m0 += 8) {
+      const int rr = warp * rpw + m0 + g;
+      double acc[8][2];
+#pragma unroll
+      for (int ni = 0; ni < 8; ++ni) acc[ni][0] = acc[ni][1] = 0.0;
+#pragma unroll 4
+      for (int kk = 0; kk < BLK; kk += 4) {
+        const double af = Pa[rr * QSTR + kk + tg];
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni) dmma884(acc[ni], af, Ls[(ni * 8 + g) * QSTR + kk + tg]);
+      }
+#pragma unroll
+      for (int ni = 0; ni < 8; ++ni) {
+        double2* x = reinterpret_cast<double2*>(Xs + rr * QSTR + ni * 8 + tg * 2);
+        const double2 v = *x;
+        *x = make_double2(v.x - acc[ni][0], v.y - acc[ni][1]);
+      }
+    }
+    __syncthreads();
+  }
+  load_block(Ls, j0, j0, BLK);
+  if (t < BLK) rinv[t] = 1.0 / __ldcg(A + (long)(j0 + t) * ld + j0 + t);
+  __syncthreads();
+  for (int c = 0; c < 8; ++c) {
+    if (t < rows) {  // one thread per row: the 8 x 8 triangle of group c
+      double x[8];
+      double* xr = Xs + t * QSTR + 8 * c;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = xr[j];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+#pragma unroll
+        for (int p = 0; p < j; ++p) x[j] -= x[p] * Ls[(8 * c + j) * QSTR + 8 * c + p];
+        x[j] *= rinv[8 * c + j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) xr[j] = x[j];
+    }
+    __syncthreads();
+    if (c < 7) {  // columns right of the group: Xs[:, n] -= X[:, group c] L[n, group c]^T
+      const int rpw = rows / NW, ntile = 7 - c;
+      for (int m0 = 0; m0 < rpw; m0 += 8) {
+        const int rr = warp * rpw + m0 + g;
+        const double a0 = -Xs[rr * QSTR + 8 * c + tg], a1 = -Xs[rr * QSTR + 8 * c + 4 + tg];
+        for (int ni = 0; ni < ntile; ++ni) {
+          const int cn = 8 * (c + 1 + ni);
+          double2* x = reinterpret_cast<double2*>(Xs + rr * QSTR + cn + tg * 2);
+          const double2 v = *x;
+          double acc[2] = {v.x, v.y};
+          dmma884(acc, a0, Ls[(cn + g) * QSTR + 8 * c + tg]);
+          dmma884(acc, a1, Ls[(cn + g) * QSTR + 8 * c + 4 + tg]);
+          *x = make_double2(acc[0], acc[1]);
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int e = t; e < rows * (BLK / 2); e += NT) {
+    const int r = e / (BLK / 2), cc = (e % (BLK / 2)) * 2;
+    *reinterpret_cast<double2*>(A + (long)(r0 + r) * ld + j0 + cc) = *reinterpret_cast<const double2*>(Xs + r * QSTR + cc);
   }
   __syncthreads();
 }
@@ -234,6 +338,8 @@ __global__ void __launch_bounds__(C::THREADS, 1) chol_queue_kernel(CholQ a) {
   const int bulk_total = __ldg(plan + PH_NU) * R;
   // ---- warp 0 scheduling state (uniform over the warp unless noted)
   int pend = QS_NONE;                       // this CTA's claimed, not yet started bulk task
+  int pend_next = QS_NONE;                  // lane 31: the claim made one task ahead (its atomicAdd may still be in flight)
+  bool pend_ahead = false;
   int pd_idx = -1, pd_val = 0;              // lane d < PLAN_MAXDEP: dependency d of `pend`
   bool pd_loaded = false;
   int hint_q = -1, hint_i = 0, hint_r = 0;  // successor of the task just finished (tried first)
@@ -242,7 +348,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) chol_queue_kernel(CholQ a) {
   long long idle_since = 0;
   bool idle = false;
   long long st_cyc[4] = {0, 0, 0, 0}, st_t0 = clock64(), st_mark = st_t0;  // thread 0: F, S, U, acquiring
-  int st_n[3] = {0, 0, 0};
+  int st_n[3] = {0, 0, 0}, st_polls = 0;
 
   auto claim_bulk = [&]() {  // lane 31 claims the next bulk task; everybody learns its index
     int p = 0;
@@ -271,6 +377,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) chol_queue_kernel(CholQ a) {
       for (;;) {
         if (pend == QS_NONE) claim_bulk();
         load_pend_deps();
+        ++st_polls;
         if (scan_r != -1) {
           scan_frontiers(qv, scan_r == -2 ? -1 : scan_r, lane);
           scan_r = -1;
@@ -279,7 +386,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) chol_queue_kernel(CholQ a) {
         //      lane 7 the held task, lanes 8.. the queue states
         bool dep_ok = true;
         if (lane < PLAN_MAXDEP && pend >= 0 && pd_idx >= 0)
-          dep_ok = ld_relaxed(a.sched + (long)(pend % R) * nflags + pd_idx) >= pd_val;
+          dep_ok = ld_acquire(a.sched + (long)(pend % R) * nflags + pd_idx) >= pd_val;
         int special = 0;  // lane 6: hint can be claimed; lane 7: held task is ready
         if (lane == 6 && hint_q >= 0) {
           const int* T = plan + __ldg(plan + PH_OFFF + hint_q) + hint_i * PLAN_TS;
@@ -369,7 +476,10 @@ __global__ void __launch_bounds__(C::THREADS, 1) chol_queue_kernel(CholQ a) {
           got_q = 3;
           got_i = pend / R;
           got_r = pend % R;
-          claim_bulk();  // one ahead: the index and its dependency list arrive while this task computes
+          // claim one ahead WITHOUT waiting for the answer: the index is read after the task has run
+          if (lane == 31) pend_next = atomicAdd(bulk_head, 1);
+          pend_ahead = true;
+          pend = QS_NONE;
           break;
         }
         if (all_exhausted) {
@@ -402,7 +512,9 @@ __global__ void __launch_bounds__(C::THREADS, 1) chol_queue_kernel(CholQ a) {
         s_task[1] = got_i;
         s_task[2] = got_r;
       }
-      __threadfence();  // acquire side of the flags just read (relaxed): order them before this CTA's data loads
+      // acquire side: the bulk task's flags were read with ld.acquire; a chain task was found ready through relaxed
+      // loads (possibly another CTA's, via the frontier), so fence before this CTA touches the data they guard
+      if (got_q != 3) __threadfence();
     }
     __syncthreads();
     const int q = s_task[0], ti = s_task[1], r = s_task[2];
@@ -424,7 +536,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) chol_queue_kernel(CholQ a) {
     if (type == PT_F) {
       cholq_factor<C::THREADS>(A, a.ld, pa, pb, smem, a.vbuf + (long)slot * a.vstride + a.info_off);
     } else if (type == PT_S) {
-      for (int b = 0; b < pc; ++b) chol_trsm_block<C::THREADS, 64>(A, a.ld, pb, pa + b, 0, smem);
+      cholq_solve<C::THREADS, C::BM>(A, a.ld, pb, pa, pc, pd, smem);
     } else {
       cholq_update_tile<C>(A, a.ld, a.rows_total, a.np, pa * C::BM, pb * C::BN, pc * BLK, pd * BLK, __ldg(T + TK_E) * BLK,
                            __ldg(T + TK_F), smem);
@@ -458,7 +570,14 @@ __global__ void __launch_bounds__(C::THREADS, 1) chol_queue_kernel(CholQ a) {
           hint_r = r;
         }
       }
-      load_pend_deps();  // the claim made one task ago has arrived: fetch its dependency list now
+      if (pend_ahead) {  // the claim made before this task ran has long arrived: fetch its dependency list now
+        int p = 0;
+        if (lane == 31) p = pend_next < bulk_total ? pend_next : QS_EXHAUSTED;
+        pend = __shfl_sync(0xffffffffu, p, 31);
+        pd_loaded = false;
+        pend_ahead = false;
+      }
+      load_pend_deps();
     }
     __syncthreads();  // s_task is rewritten by warp 0 in the next round
   }
@@ -467,5 +586,6 @@ __global__ void __launch_bounds__(C::THREADS, 1) chol_queue_kernel(CholQ a) {
     for (int i = 0; i < 3; ++i) o[i] = st_n[i];
     for (int i = 0; i < 4; ++i) o[3 + i] = (int)(st_cyc[i] >> 6);  // units of 64 cycles
     o[7] = (int)((clock64() - st_t0) >> 6);
+    o[8] = st_polls;
   }
 }

@@ -878,7 +878,8 @@ template <class C>
 static int chol_queue_launch(double* Kb, double* vbuf, const GpDims& d, const Bat& bat, int R, const CholRun& run,
                              cudaStream_t st) {
   constexpr size_t SYRK_SM = gemm_smem_bytes<C, Lay::KCONT, Lay::KCONT>();
-  constexpr size_t SM = SYRK_SM > FACT_SMEM ? SYRK_SM : FACT_SMEM;
+  constexpr size_t SM1 = SYRK_SM > FACT_SMEM ? SYRK_SM : FACT_SMEM;
+  constexpr size_t SM = SM1 > solve_smem<C::BM>() ? SM1 : solve_smem<C::BM>();
   if (opt_in_smem(chol_queue_kernel<C>, SM) != cudaSuccess) return IPP_ERR_CUDA;
   int sms = 0, per_sm = 0;
   if (device_sms(&sms) != IPP_OK) return IPP_ERR_CUDA;

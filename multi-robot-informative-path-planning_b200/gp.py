@@ -45,7 +45,7 @@ def chol_stats(ws, R):
     return {"ctas": int(len(st)), "tasks_F_S_U": st[:, 0:3].sum(0).tolist(),
             "busy_frac_F_S_U": (cyc[:, 0:3].sum(0) / cyc[:, 4].sum()).tolist(), "acquire_frac": float(cyc[:, 3].sum() / cyc[:, 4].sum()),
             "mean_task_us_F_S_U_at_1965MHz": (cyc[:, 0:3].sum(0) / np.maximum(st[:, 0:3].sum(0), 1) / 1965.0).tolist(),
-            "kernel_us": float(cyc[:, 4].max() / 1965.0)}
+            "kernel_us": float(cyc[:, 4].max() / 1965.0), "polls_per_task": float(st[:, 8].sum() / max(st[:, 0:3].sum(), 1))}
 
 
 def _check_watchdog(info):

@@ -69,9 +69,10 @@ class Sim:
             k, w = int(T[TK_A]), int(T[TK_B])
             return dict(kind="F", writes=[(k, k)], reads=[(k, p) for p in range(k - w, k)], before=k - w, panels=range(k - w, k))
         if ty == 1:
-            i, k, nblk = int(T[TK_A]), int(T[TK_B]), int(T[TK_C])
-            assert nblk >= 1 and i + nblk <= self.nrb
-            return dict(kind="S", writes=[(i + b, k) for b in range(nblk)], reads=[(k, k)], before=k, panels=range(0))
+            i, k, nblk, w = int(T[TK_A]), int(T[TK_B]), int(T[TK_C]), int(T[TK_D])
+            assert nblk >= 1 and i + nblk <= self.nrb and w == (k & 1)
+            reads = [(k, k)] + [(k, p) for p in range(k - w, k)] + [(i + b, p) for b in range(nblk) for p in range(k - w, k)]
+            return dict(kind="S", writes=[(i + b, k) for b in range(nblk)], reads=reads, before=k - w, panels=range(k - w, k))
         ti, tj, kb, ke, cmin, skip = (int(T[x]) for x in (TK_A, TK_B, TK_C, TK_D, TK_E, TK_F))
         writes, reads = [], set()
         for i in range(ti * self.tb, min((ti + 1) * self.tb, self.nrb)):

@@ -19,7 +19,9 @@ class FastGP(OracleGP):
     full = False
 
 
-def _nodes_from(pts, parent):
+def _nodes_from(pts, parent, nchild):
+    """Reference-shaped nodes from a golden snapshot: final parents; `children` only has to be as long as the
+    reference's list was (rewire never removes a child from its old parent, so leaves are `nchild == 0`)."""
     nodes = []
     for k in range(len(pts)):
         nd = T.Node(pts[k])
@@ -28,8 +30,31 @@ def _nodes_from(pts, parent):
     for k in range(len(pts)):
         if parent[k] >= 0:
             nodes[k].parent = nodes[parent[k]]
-            nodes[parent[k]].children.append(nodes[k])
+        nodes[k].children = [None] * int(nchild[k])
     return nodes
+
+
+def _ucb_strategy(g, tag, gp_factory, scorer):
+    """The strategy object of oracle/make_golden_r2.py::gold_ucb, regrown with the product's tree code (bit-identical
+    to the reference's tree: checked) with the visited points of the golden case."""
+    seed = int(g[f"{tag}_seed"]) - 70
+    W = int(g[f"{tag}_W"])
+    sc = PointSourceField(num_sources=2, workspace_size=(0, W, 0, W), seed=seed, gp_factory=gp_factory)
+    X, n_obs = g[f"{tag}_X"], len(g[f"{tag}_X"])
+    np.random.seed(int(g[f"{tag}_seed"]))
+    st = R.MR_IPP(sc, budget=150, d_waypoint_distance=2.5, num_agents=2, budget_iter=4, beta_t=float(g[f"{tag}_beta"]),
+                  scorer=scorer)
+    start = g[f"{tag}_start"]
+    st.agents_obs_wp = [list(X[: n_obs // 2]), list(X[n_obs // 2:])]
+    st.best_estimates = g[f"{tag}_est"]
+    st.agents_full_path = [[start.copy()], [np.array([25.0, 5.0])]]
+    st.initialize_trees(start, 0)
+    R.rig_tree_generation(st, 150, 0, gain_function=R.point_source_gain_all)
+    tree = st.trees_soa[0]
+    assert np.array_equal(tree.points(), g[f"{tag}_pts"]) and np.array_equal(tree.nchild[: tree.n], g[f"{tag}_nchild"])
+    assert np.array_equal(tree.parent[: tree.n], g[f"{tag}_parent_final"])
+    st.agents_full_path = [list(g[f"{tag}_visited"]), []]
+    return sc, st
 
 
 @pytest.mark.parametrize("tag", ["a", "b", "c"])
@@ -39,7 +64,7 @@ def test_oracle_ucb_selector_matches_reference(gold, tag):
     th = g[f"{tag}_theta"]
     st = O.fit(g[f"{tag}_X"], np.log10(np.maximum(g[f"{tag}_meas"], 1e-6)), float(np.exp(th[0])), float(np.exp(th[1])),
                optimize=False)
-    nodes = _nodes_from(g[f"{tag}_pts"], g[f"{tag}_parent_final"])
+    nodes = _nodes_from(g[f"{tag}_pts"], g[f"{tag}_parent_final"], g[f"{tag}_nchild"])
     leaves = [nd for nd in nodes if not nd.children]
     assert np.array_equal(np.array([nd.point for nd in leaves]), g[f"{tag}_leaf_pts"])
     mu, sd, _ = O.predict(st, g[f"{tag}_leaf_pts"])
@@ -58,16 +83,13 @@ def test_product_ucb_selector_host_logic(gold, tag):
     budget walk are the reference's; the posterior comes from the oracle double here (device: tests/test_r2_gpu.py)."""
     g = gold("ucb_golden_r2.npz")
     th = g[f"{tag}_theta"]
-    gp = OracleGP(kernel=types.SimpleNamespace(constant_value=float(np.exp(th[0])), length_scale=float(np.exp(th[1]))))
-    gp.full = False
-    gp.fit(g[f"{tag}_X"], np.log10(np.maximum(g[f"{tag}_meas"], 1e-6)))
-    tree = TreeArrays.from_snapshot(g[f"{tag}_pts"], g[f"{tag}_parent_final"])
-    me = types.SimpleNamespace(trees_soa=[tree], scenario=types.SimpleNamespace(gp=gp), scorer=OracleScorer(),
-                               agents_full_path=[list(g[f"{tag}_visited"])], beta_t=float(g[f"{tag}_beta"]),
-                               d_waypoint_distance=2.5, uncertainty_reduction=[])
-    path = R.ucb_path_selection(me, 0, g[f"{tag}_start"], float(g[f"{tag}_budget"]))
+    sc, st = _ucb_strategy(g, tag, FastGP, OracleScorer())
+    sc.gp.kernel = types.SimpleNamespace(constant_value=float(np.exp(th[0])), length_scale=float(np.exp(th[1])))
+    sc.gp.n_restarts_optimizer = 0
+    sc.gp.fit(g[f"{tag}_X"], np.log10(np.maximum(g[f"{tag}_meas"], 1e-6)))
+    path = R.ucb_path_selection(st, 0, g[f"{tag}_start"], float(g[f"{tag}_budget"]))
     assert np.array_equal(np.array(path), g[f"{tag}_path"])
-    assert me.uncertainty_reduction[0] == pytest.approx(float(g[f"{tag}_mean_std"]), abs=1e-7)
+    assert st.uncertainty_reduction[-1] == pytest.approx(float(g[f"{tag}_mean_std"]), abs=1e-7)
 
 
 @pytest.mark.parametrize("tag", ["n500", "n2000"])
@@ -125,5 +147,5 @@ def test_multi_agent_runs_identical_host_logic(gold, tag, obstacles):
     """configs[2] / configs[3] agent counts (3 and 8) and an obstacle run: the N > 1 start rule (rrt.py:555-558), the
     per-iteration agent loop (:696-711) and exploitation_penalty over all agents (:246-252) against the reference."""
     g = gold("runs_golden_r2.npz")
-    run_multi(g, tag, obstacles, lambda **kw: PointSourceField(gp_factory=FastGP, **kw),
+    run_multi(g, tag, obstacles, lambda **kw: PointSourceField(gp_factory=FastGP, ground_truth_mode="host", **kw),
               lambda sc, **kw: R.MR_IPP(sc, scorer=OracleScorer(), **kw))

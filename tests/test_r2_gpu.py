@@ -1,0 +1,239 @@
+"""Round-2 device parity tests (-m gpu) against the round-2 reference goldens (tests/golden/*_r2.npz): the UCB
+selector on the device posterior, GP cases at n = 500 / 2000 with the C2 / C3 lattices, whole MR_IPP runs with 3 and 8
+agents and with an obstacle, the concurrency contract (several host threads on one estimator / scorer), and the
+INTEGRATION.md patch (the unmodified reference call sequence with mripp_b200.gp swapped in)."""
+import threading
+import types
+import warnings
+
+import numpy as np
+import pytest
+
+from oracle import gp_oracle as O
+from tests.test_gpu_parity import GRAD_RTOL, _lml_tol, _mean_tol, _var_tol
+from tests.test_r2_cpu import MULTI, _ucb_strategy, run_multi
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def G():
+    from mripp_b200 import gp
+
+    return gp
+
+
+def _fixed_gp(G, X, ylog, th, **kw):
+    gp = G.GaussianProcessRegressor(kernel=G.ConstantRBFKernel(float(np.exp(th[0])), float(np.exp(th[1]))), optimizer=None,
+                                    normalize_y=True, **kw)
+    return gp.fit(X, ylog)
+
+
+# ---------------------------------------------------------------------------------------------------
+# G6: the posterior-driven (UCB) selector, rrt_thread.py:371-401
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_ucb_selector_on_device_vs_reference(G, gold, tag):
+    from mripp_b200.scoring import GpuScorer
+    from mripp_b200.src.rrt import rrt as R
+
+    g = gold("ucb_golden_r2.npz")
+    th = g[f"{tag}_theta"]
+    ylog = np.log10(np.maximum(g[f"{tag}_meas"], 1e-6))
+    sc, st = _ucb_strategy(g, tag, None, GpuScorer())
+    sc.gp = _fixed_gp(G, g[f"{tag}_X"], ylog, th)  # the reference's fitted theta: T1
+    leaf_xy = g[f"{tag}_leaf_pts"]
+    mu, sd = sc.gp.predict(leaf_xy, return_std=True)  # explicit points: ipp_gp_posterior_points
+    assert np.abs(mu - g[f"{tag}_mu"]).max() <= 1e-6 and np.abs(sd - g[f"{tag}_sd"]).max() <= 1e-7
+    acq, mean_std = st.scorer.ucb_acquisition(sc.gp, leaf_xy, list(g[f"{tag}_visited"]), float(g[f"{tag}_beta"]), 2.5)
+    # acq = normalised mu + beta * normalised sigma - visit penalty: the normalisation divides by the spread of mu and
+    # sigma over the leaves (O(0.1)), so 1e-6 / 1e-7 in mu / sigma is up to ~1e-5 * (1 + beta) here; the penalty
+    # itself (ipp_ucb_visit_penalty) is exact to rounding
+    assert np.abs(acq - g[f"{tag}_acq"]).max() <= 2e-5 * (1.0 + float(g[f"{tag}_beta"]))
+    assert int(np.argmax(acq)) == int(np.argmax(g[f"{tag}_acq"]))
+    assert mean_std == pytest.approx(float(g[f"{tag}_mean_std"]), abs=1e-7)
+    path = R.ucb_path_selection(st, 0, g[f"{tag}_start"], float(g[f"{tag}_budget"]))
+    assert np.array_equal(np.array(path), g[f"{tag}_path"])  # chosen path: bit-identical
+    # the penalty kernel alone against its numpy expression (1e-12)
+    rng = np.random.RandomState(3)
+    base = rng.randn(len(leaf_xy))
+    vis = np.asarray(g[f"{tag}_visited"], float)
+    ref = base.copy()
+    for i, p in enumerate(leaf_xy):
+        for v in vis:
+            d = np.linalg.norm(p - v)
+            if d < 2.5:
+                ref[i] -= 0.1 * (2.5 - d) / 2.5
+    import torch
+    from mripp_b200 import _lib
+    lib = _lib.load()
+    acq_d, lx, vx = torch.from_numpy(base.copy()).cuda(), torch.from_numpy(np.ascontiguousarray(leaf_xy)).cuda(), torch.from_numpy(vis).cuda()
+    assert lib.ipp_ucb_visit_penalty(_lib.ptr(lx), len(leaf_xy), _lib.ptr(vx), len(vis), 2.5, _lib.ptr(acq_d), _lib.stream_ptr()) == 0
+    assert np.abs(acq_d.cpu().numpy() - ref).max() <= 1e-12
+
+
+# ---------------------------------------------------------------------------------------------------
+# G2 / G4 / G5 at the sizes of configs[1] (n = 500, 200 x 200) and configs[2] (n = 2000, 500 x 500)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["n500", "n2000"])
+def test_gp_large_cases_vs_reference(G, gold, tag):
+    g = gold("gp_golden_r2.npz")
+    X, ylog = g[f"{tag}_X"], np.log10(np.maximum(g[f"{tag}_meas"], 1e-6))
+    W = int(g[f"{tag}_W"])
+    for th, v_ref, g_ref in zip(g[f"{tag}_thetas"], g[f"{tag}_lml"], g[f"{tag}_grad"]):
+        gp = _fixed_gp(G, X, ylog, th)
+        v, gr = gp.log_marginal_likelihood(th, eval_gradient=True)
+        st = O.fit(X, ylog, float(np.exp(th[0])), float(np.exp(th[1])), optimize=False)
+        aa = float(st["alpha"] @ st["alpha"])
+        assert abs(v - v_ref) <= _lml_tol(v_ref, th, aa)
+        assert np.abs(gr - g_ref).max() <= GRAD_RTOL * max(1.0, float(np.abs(g_ref).max()), 1e-9 * aa)
+    # fixed theta = the reference's optimum: factor, explicit points, and the C2 / C3 lattice (block-sparse and dense)
+    th = g[f"{tag}_theta_fit"]
+    gp = _fixed_gp(G, X, ylog, th)
+    st = O.fit(X, ylog, float(np.exp(th[0])), float(np.exp(th[1])), optimize=False)
+    n = len(X)
+    assert np.abs(np.diag(gp.L_) ** 2 - g[f"{tag}_Ldiag"] ** 2).max() <= 64 * n * np.finfo(float).eps * st["c"]
+    qm, qs = gp.predict(g[f"{tag}_Q"], return_std=True)
+    assert (np.abs(qm - g[f"{tag}_qmean"]) <= _mean_tol(st, g[f"{tag}_Q"], g[f"{tag}_qmean"])).all()
+    assert np.abs(qs - g[f"{tag}_qstd"]).max() <= 1e-7
+    assert np.abs(qs ** 2 - g[f"{tag}_qstd"] ** 2).max() <= _var_tol(st)
+    nx, ny, idx = int(g[f"{tag}_nx"]), int(g[f"{tag}_ny"]), g[f"{tag}_gidx"]
+    assert nx == W * 10 and ny == W * 10
+    _, _, r, _ = O.workspace_grid((0, W, 0, W))
+    for skip in (None, 0):
+        m_d, s_d, z_d = gp.predict_grid_device(0, W, nx, 0, W, ny, skip_below=skip)
+        gm, gs = m_d.cpu().numpy()[idx], s_d.cpu().numpy()[idx]
+        assert (np.abs(gm - g[f"{tag}_gmean"]) <= _mean_tol(st, r[idx], g[f"{tag}_gmean"])).all()
+        assert np.abs(gs - g[f"{tag}_gstd"]).max() <= 1e-7
+        assert np.allclose(z_d.cpu().numpy()[idx], 10.0 ** g[f"{tag}_gmean"], rtol=1e-5)
+
+
+@pytest.mark.parametrize("tag", ["n500", "n2000"])
+def test_reoptimised_fit_large_vs_reference(G, gold, tag):
+    """T2 at n = 500 / 2000: the 11-restart fit (lockstep batch) consumes the reference's RNG draws, and lands on an
+    optimum whose LML -- evaluated by the ORACLE at both thetas -- is within the reference's own evaluation noise."""
+    g = gold("gp_golden_r2.npz")
+    X, ylog = g[f"{tag}_X"], np.log10(np.maximum(g[f"{tag}_meas"], 1e-6))
+    gp = G.GaussianProcessRegressor(kernel=G.ConstantRBFKernel(1.0, 1.0, (1e-3, 50), (1e-2, 50)), n_restarts_optimizer=10,
+                                    normalize_y=True)
+    np.random.seed(321)
+    gp.fit(X, ylog)
+    assert np.array_equal(np.random.uniform(size=3), g[f"{tag}_rng_after"])
+    yn, _, _ = O.normalise_y(ylog)
+    th_ref = g[f"{tag}_theta_fit"]
+    v_ref, v_dev = O.lml(th_ref, X, yn, False), O.lml(gp.kernel_.theta, X, yn, False)
+    prng = np.random.RandomState(0)
+    noise = np.ptp([O.lml(th_ref + 1e-9 * prng.randn(2), X, yn, False) for _ in range(8)])
+    assert v_dev >= v_ref - (1e-3 + 2.0 * noise + 1e-9 * abs(v_ref)), (v_dev, v_ref, noise, gp.kernel_.theta, th_ref)
+    assert np.abs(gp.kernel_.theta - th_ref).max() <= 5e-2  # same basin
+
+
+# ---------------------------------------------------------------------------------------------------
+# T3 at the agent counts of configs[2] / configs[3] and with an obstacle
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag,obstacles", MULTI, ids=[m[0] for m in MULTI])
+def test_multi_agent_runs_identical_on_device(gold, tag, obstacles):
+    from mripp_b200.src.point_source.point_source import PointSourceField
+    from mripp_b200.src.rrt import rrt as R
+
+    g = gold("runs_golden_r2.npz")
+
+    def scenario(**kw):
+        sc = PointSourceField(**kw)
+        sc.gp.lazy = True  # per-step refits the reference never reads only consume their RNG draws
+        return sc
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sc, st, Z, std = run_multi(g, tag, obstacles, scenario, lambda s, **kw: R.MR_IPP(s, **kw))
+        assert Z.shape == (400, 400) and std.shape == (160000,)
+        # T1 on the same run: at the REFERENCE's theta the device field is the reference's field
+        th = g[f"{tag}_theta"]
+        sc.gp.kernel = type(sc.gp.kernel)(float(np.exp(th[0])), float(np.exp(th[1])))
+        sc.gp.optimizer, sc.gp.lazy = None, False
+        Z1, std1 = sc.predict_spatial_field(st.obs_wp, np.asarray(st.measurements, float))
+    assert np.abs(np.log10(Z1[::8, ::8]) - np.log10(g[f"{tag}_Z"])).max() <= 1e-4
+    assert np.abs(std1.reshape(Z1.shape)[::8, ::8] - g[f"{tag}_std"]).max() <= 1e-6
+
+
+# ---------------------------------------------------------------------------------------------------
+# Concurrency contract (include/ipp_b200.h: re-entrant, one stream per calling thread).  The reference calls
+# gp.kernel(...) and the selectors from num_agents threads outside its lock (rrt.py:659-664, 703-711).
+# ---------------------------------------------------------------------------------------------------
+def test_eight_threads_share_estimator_and_scorer(G, gold):
+    import torch
+
+    from mripp_b200.scoring import GpuScorer, ScoreContext
+    from mripp_b200.src.rrt.rrt_utils import TreeArrays
+
+    g = gold("gp_golden_r2.npz")
+    X, ylog = g["n500_X"], np.log10(np.maximum(g["n500_meas"], 1e-6))
+    gp = _fixed_gp(G, X, ylog, g["n500_theta_fit"])
+    scorer = GpuScorer()
+    rng = np.random.RandomState(4)
+    W = 20
+    trees, ctxs, leafs = [], [], []
+    est = np.array([[5.0, 6.0, 5e5], [14.0, 3.0, 7e5]])
+    obs = [list(X[a::8]) for a in range(8)]
+    for a in range(8):
+        tr = TreeArrays(np.array([10.0, 10.0]))
+        for k in range(1, 200):
+            par = int(rng.randint(max(0, k - 30), k))
+            tr.add(tr.point(par) + rng.uniform(-1.0, 1.0, 2), par)
+        trees.append(tr)
+        ctxs.append(ScoreContext(est, tr.point(0), obs, a, 1.0, (0, W, 0, W), []))
+        leafs.append(np.ascontiguousarray(tr.points()[tr.leaves_in_order()]))
+
+    def work(a):
+        info = scorer.tree_information(3, trees[a], ctxs[a])
+        K = gp.kernel_(leafs[a], np.asarray(obs[a]))
+        mu, sd = gp.predict(leafs[a], return_std=True)
+        acq, _ = scorer.ucb_acquisition(gp, leafs[a], list(X[a:a + 20]), 2.0, 2.5)
+        return info, K, mu, sd, acq
+
+    serial = [work(a) for a in range(8)]
+    out, errs = [None] * 8, []
+
+    def run(a):
+        try:
+            with torch.cuda.stream(torch.cuda.Stream()):  # one stream per calling thread
+                for _ in range(5):
+                    out[a] = work(a)
+        except BaseException as e:  # noqa: BLE001
+            errs.append(e)
+
+    ths = [threading.Thread(target=run, args=(a,)) for a in range(8)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert not errs, errs
+    for a in range(8):
+        for x, y in zip(out[a], serial[a]):
+            assert np.array_equal(np.asarray(x), np.asarray(y), equal_nan=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# the reference's own call sequence (point_source.py:346-353, verbatim in a 6-line
+# caller vendored here because /root/reference does not exist on the GPU box) with mripp_b200.gp swapped in.
+# ---------------------------------------------------------------------------------------------------
+def test_integration_patch_reference_call_sequence(G, gold):
+    g = gold("gp_golden.npz")
+    W = int(g["psf_W"])
+    x = np.linspace(0, W, W * 10)
+    Xg, Yg = np.meshgrid(x, x)
+    # what the reference's ctor builds (point_source.py:71,82-87) with the two imports replaced
+    gp = G.GaussianProcessRegressor(kernel=G.ConstantKernel(1.0, (1e-3, 50)) * G.RBF(1.0, (1e-2, 50)), n_restarts_optimizer=10,
+                                    normalize_y=True)
+    np.random.seed(77)
+    # predict_spatial_field, verbatim
+    gp.fit(g["psf_X"], np.log10(np.maximum(g["psf_meas"], 1e-6)))
+    r = np.column_stack((Xg.ravel(), Yg.ravel()))
+    Z_pred, std = gp.predict(r, return_std=True)  # recognised as the workspace lattice -> fused lattice kernel
+    Z_pred = 10 ** Z_pred.reshape(Xg.shape)
+    assert np.array_equal(np.random.uniform(size=3), g["psf_rng_after"])
+    assert np.abs(np.log10(Z_pred) - np.log10(g["psf_Z"])).max() <= 1e-2
+    assert np.abs(std - g["psf_std"]).max() <= 1e-2
+    # gp.kernel(X[, Y]) as rrt.py:447,452 call it
+    L = g["psf_X"][:7]
+    assert np.abs(gp.kernel(L) - O.kernel(L, None, 1.0, 1.0)).max() <= 4e-16
