@@ -11,7 +11,10 @@
 //                 (i0 = k + 1, the one the chain waits for) alone, the others one task per tile row.  For k odd it
 //                 first applies panel k-1 (the first half of its own super-panel) to its blocks itself.
 //   U2(tile, s)   rank-128 update of a tile right of super-panel s by panels 2s, 2s+1 (one read-modify-write of the
-//                 tile per TWO panels: half the traffic and twice the k depth of a per-panel update).
+//                 tile per TWO panels: half the traffic and twice the k depth of a per-panel update).  Tiles at
+//                 least two super-panels away from the front take super-panels in PAIRS (rank 256, 2s' and 2s'+1
+//                 applied when the second is done): they have the slack, and the tile's read-modify-write and the
+//                 pipeline fill are paid once per four panels.
 // Flags (per problem; all monotone counters): F[k] in {0,1}; S[i] = number of panels row block i is solved for;
 // A[tile] = number of panels applied to the tile.
 // Queues: F, S and C (the U2 tiles of the columns right behind the super-panel, i.e. everything the chain waits
@@ -148,7 +151,12 @@ inline long chol_plan_build(int nb, int tb, int /*ctas: no task is split by CTA 
       for (int ti = tj; ti <= tmax; ++ti) {
         const int skip = 2 * s + 2;
         if (tb == 1 && ti == tj && ti == skip) continue;   // the tile IS the skipped block
-        PlanTask t = u_task(ti, tj, p0, ke, tj * tb, skip, p0);
+        // far tiles: super-panels (s & ~1, s | 1) as one rank-256 task, emitted at the odd one
+        const int tjs = (tj * tb) / 2;                     // super-panel the tile's first column belongs to
+        const bool paired = ((s | 1) <= tjs - 2) && 2 * (s | 1) + 1 < nb;
+        if (paired && !(s & 1)) continue;
+        const int kb = paired ? 2 * (s - 1) : p0;
+        PlanTask t = u_task(ti, tj, kb, ke, tj * tb, skip, kb);
         (tj < tj0 + 2 / tb ? qC : qU).push_back(t);   // the next super-panel's own columns are on the chain
       }
   }

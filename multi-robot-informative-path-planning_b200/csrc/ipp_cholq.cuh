@@ -67,17 +67,28 @@ __device__ __forceinline__ void cholq_factor(double* __restrict__ A, long ld, in
   double* D = psm;
   double* P = psm + BLK * PSTR;
   const int t = threadIdx.x, j0 = BLK * k, p0 = BLK * (k - width), pw = BLK * width;
-  for (int e = t; e < BLK * BLK / 2; e += NT) {
-    const int r = e / (BLK / 2), cc = (e % (BLK / 2)) * 2;
-    const double2 v = __ldcg(reinterpret_cast<const double2*>(A + (long)(j0 + r) * ld + j0 + cc));
-    D[r * PSTR + cc] = v.x;
-    D[r * PSTR + cc + 1] = v.y;
-  }
+  // every load of the task in flight at once (these blocks come from L2: one round trip, not one per row)
   for (int e = t; e < BLK * pw / 2; e += NT) {
     const int r = e / (pw / 2), cc = (e % (pw / 2)) * 2;
-    const double2 v = __ldcg(reinterpret_cast<const double2*>(A + (long)(j0 + r) * ld + p0 + cc));
-    *reinterpret_cast<double2*>(P + r * QSTR2 + cc) = v;
+    cp_async16(P + r * QSTR2 + cc, A + (long)(j0 + r) * ld + p0 + cc, true);
   }
+  cp_async_commit();
+  {
+    constexpr int PER = BLK * BLK / 2 / NT;
+    double2 v[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int e = t + i * NT, r = e / (BLK / 2), cc = (e % (BLK / 2)) * 2;
+      v[i] = __ldcg(reinterpret_cast<const double2*>(A + (long)(j0 + r) * ld + j0 + cc));
+    }
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int e = t + i * NT, r = e / (BLK / 2), cc = (e % (BLK / 2)) * 2;
+      D[r * PSTR + cc] = v[i].x;
+      D[r * PSTR + cc + 1] = v[i].y;
+    }
+  }
+  cp_async_wait<0>();
   __syncthreads();
   if (width > 0) {  // lower part of D -= P P^T on the DMMA pipe: each warp owns 64 / (NT / 32) rows
     constexpr int RPW = BLK / (NT / 32), MT = RPW / 8;
@@ -129,29 +140,34 @@ __device__ __forceinline__ void cholq_factor(double* __restrict__ A, long ld, in
 // task; 64 dependent steps per row in all, but each is an FMA out of registers instead of a shared-memory sweep
 // (chol_trsm_block: 6 us per 64 rows; this: ~2 us per 128 rows).
 template <int SOLVE_ROWS>
-constexpr size_t solve_smem() {
-  return sizeof(double) * ((SOLVE_ROWS + SOLVE_ROWS + BLK) * QSTR + BLK);
+constexpr size_t solve_smem() {  // X, Pa, Pb, L_kk (+ reciprocal pivots)
+  return sizeof(double) * ((SOLVE_ROWS + SOLVE_ROWS + BLK + BLK) * QSTR + BLK);
 }
 template <int NT, int SOLVE_ROWS>
 __device__ __forceinline__ void cholq_solve(double* __restrict__ A, long ld, int k, int i0, int nblk, int width, double* psm) {
   const int rows = BLK * nblk, t = threadIdx.x, warp = t >> 5, lane = t & 31, g = lane >> 2, tg = lane & 3;
   double* Xs = psm;                          // rows x 64, pitch QSTR
-  double* Pa = psm + SOLVE_ROWS * QSTR;      // rows x 64 (own update), then unused
-  double* Ls = psm + 2 * SOLVE_ROWS * QSTR;  // Pb during the own update, then L_kk
+  double* Pa = psm + SOLVE_ROWS * QSTR;      // rows x 64 (own update)
+  double* Pb = psm + 2 * SOLVE_ROWS * QSTR;  // 64 x 64 (own update)
+  double* Ls = Pb + BLK * QSTR;              // L_kk
   double* rinv = Ls + BLK * QSTR;
   const int j0 = BLK * k, r0 = BLK * i0, p0 = BLK * (k - 1);
-  auto load_block = [&](double* dst, int grow0, int gcol0, int nrows) {
+  auto load_block = [&](double* dst, int grow0, int gcol0, int nrows) {  // asynchronous: all blocks in flight at once
     for (int e = t; e < nrows * (BLK / 2); e += NT) {
       const int r = e / (BLK / 2), cc = (e % (BLK / 2)) * 2;
-      *reinterpret_cast<double2*>(dst + r * QSTR + cc) =
-          __ldcg(reinterpret_cast<const double2*>(A + (long)(grow0 + r) * ld + gcol0 + cc));
+      cp_async16(dst + r * QSTR + cc, A + (long)(grow0 + r) * ld + gcol0 + cc, true);
     }
   };
   load_block(Xs, r0, j0, rows);
   if (width > 0) {
     load_block(Pa, r0, p0, rows);
-    load_block(Ls, j0, p0, BLK);
+    load_block(Pb, j0, p0, BLK);
   }
+  cp_async_commit();
+  load_block(Ls, j0, j0, BLK);
+  cp_async_commit();
+  if (t < BLK) rinv[t] = 1.0 / __ldcg(A + (long)(j0 + t) * ld + j0 + t);
+  cp_async_wait<1>();  // X and the own-update operands have landed; L_kk may still be on its way
   __syncthreads();
   constexpr int NW = NT / 32;
   if (width > 0) {  // Xs -= Pa Pb^T: warp w owns rows [w * rows / NW, ...) in 8-row groups, all 64 columns
@@ -165,7 +181,7 @@ __device__ __forceinline__ void cholq_solve(double* __restrict__ A, long ld, int
       for (int kk = 0; kk < BLK; kk += 4) {
         const double af = Pa[rr * QSTR + kk + tg];
 #pragma unroll
-        for (int ni = 0; ni < 8; ++ni) dmma884(acc[ni], af, Ls[(ni * 8 + g) * QSTR + kk + tg]);
+        for (int ni = 0; ni < 8; ++ni) dmma884(acc[ni], af, Pb[(ni * 8 + g) * QSTR + kk + tg]);
       }
 #pragma unroll
       for (int ni = 0; ni < 8; ++ni) {
@@ -174,10 +190,8 @@ __device__ __forceinline__ void cholq_solve(double* __restrict__ A, long ld, int
         *x = make_double2(v.x - acc[ni][0], v.y - acc[ni][1]);
       }
     }
-    __syncthreads();
   }
-  load_block(Ls, j0, j0, BLK);
-  if (t < BLK) rinv[t] = 1.0 / __ldcg(A + (long)(j0 + t) * ld + j0 + t);
+  cp_async_wait<0>();
   __syncthreads();
   for (int c = 0; c < 8; ++c) {
     if (t < rows) {  // one thread per row: the 8 x 8 triangle of group c

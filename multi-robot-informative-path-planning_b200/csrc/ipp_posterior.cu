@@ -183,7 +183,8 @@ __global__ void __launch_bounds__(256) axis_table_kernel(const double* __restric
 }
 
 constexpr int LAT_THREADS = PC::THREADS + 128;  // 8 DMMA (consumer) warps + one copy (producer) warpgroup
-constexpr int LAT_MASK_WORDS = 32;              // 1024 slabs = 16384 observations; beyond that nothing is skipped
+constexpr int LAT_MASK_WORDS = 32;              // 1024 slabs = 16384 observations; with more, no slab is skipped (both
+                                                // loops then read "all active" instead of the mask: see the ternaries)
 
 // Block sparsity of the cross-covariance.  With the observations in spatial (Morton) order a 16-observation
 // slab is a compact cluster; when its bounding box is farther than R = l * sqrt(2 ln(1/eps)) from every query
@@ -273,7 +274,7 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) posterior_lattice_kernel(PostA
       for (int prb = 0; prb < nrb; ++prb) {
         const int p_row0 = blk_row0(prb), p_rlim = blk_rlim(prb), nsl = blk_kend(prb) / BK;
         for (int w = 0; 32 * w < nsl; ++w) {  // the active slabs below the block's last column, by set bit
-          unsigned m = smask[warp][w];
+          unsigned m = w < LAT_MASK_WORDS ? smask[warp][w] : 0xffffffffu;  // beyond the mask: every slab is active
           if (nsl - 32 * w < 32) m &= (1u << (nsl - 32 * w)) - 1u;
           while (m) {
             const int pk = (32 * w + __ffs(m) - 1) * BK;
@@ -327,7 +328,7 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) posterior_lattice_kernel(PostA
       for (int crb = 0; crb < nrb; ++crb) {
         const int nsl = blk_kend(crb) / BK;
         for (int w = 0; 32 * w < nsl; ++w) {  // the active slabs below the block's last column, by set bit
-          unsigned m = smask[warp][w];
+          unsigned m = w < LAT_MASK_WORDS ? smask[warp][w] : 0xffffffffu;  // beyond the mask: every slab is active
           if (nsl - 32 * w < 32) m &= (1u << (nsl - 32 * w)) - 1u;
           while (m) {
             const int ck = (32 * w + __ffs(m) - 1) * BK;

@@ -86,22 +86,48 @@ def prior_kernel_exact(A: np.ndarray, B: np.ndarray, c: float, l: float) -> np.n
 
 
 def exact_leaf_scores(cand: np.ndarray, leaf_points: List[np.ndarray], parent_points: List[Optional[np.ndarray]], ctx,
-                      beta: float, c: float, l: float) -> np.ndarray:
-    """Reference-exact stage-1 scores of the candidate leaves (agent HAS observations)."""
-    leaf_xy = np.array([np.asarray(p, dtype=np.float64) for p in leaf_points])
-    obs = np.array(ctx.agents_obs_wp[ctx.agent_idx])
-    K_pio = prior_kernel_exact(leaf_xy, obs, c, l)
-    mi = 0.5 * np.log(np.linalg.det(np.eye(leaf_xy.shape[0]) + beta * np.dot(K_pio, K_pio.T)))
+                      beta: float, c: float, l: float, mi_dev: Optional[float] = None) -> np.ndarray:
+    """Reference-exact stage-1 scores of the candidate leaves (agent HAS observations).
+
+    The candidates share the mutual-information term and differ only in their penalties, which are exact on the
+    host at no cost (no kernel matrix).  With the device's `mi_dev` (right to ~1e-10 relative) the common term is
+    only re-evaluated in the reference's own arithmetic -- an L x n_a kernel block and an L x L determinant -- when
+    the penalty sums of the best candidates are so close that the rounding of ((mi - dp) - w) - ep could decide
+    between them; otherwise the ordering is that of the exact penalties and `mi_dev` stands in for the value."""
     ws = ctx.workspace
-    out = np.empty(len(cand), dtype=np.float64)
-    for k, i in enumerate(cand):
+    pens = []
+    for i in cand:
         p, par = leaf_points[i], parent_points[i]
+        dp = np.exp(0.5 * _norm(p - par) ** 2) if par is not None else 0
+        w = np.inf if (p[0] < ws[0] or p[0] > ws[1] or p[1] < ws[2] or p[1] > ws[3]) else 0
+        ep = np.exp(0.05 * count_close_exact(p, ctx.agents_obs_wp, ctx.d_wp) ** 2)
+        pens.append((dp, w, ep))
+    mi = None
+    if mi_dev is not None and np.isfinite(mi_dev):
+        tot = np.array([dp + w + ep for dp, w, ep in pens], dtype=np.float64)
+        order = np.sort(tot)
+        scale = max(abs(float(mi_dev)), float(order[0]) if np.isfinite(order[0]) else 0.0, 1.0)
+        all_equal = all(pn == pens[0] for pn in pens)
+        if all_equal or (len(order) > 1 and order[1] - order[0] > 64 * np.finfo(float).eps * scale):
+            mi = float(mi_dev)  # decided by the penalties alone (or a bit-identical tie: the first wins either way)
+    if mi is None:
+        leaf_xy = np.array([np.asarray(p, dtype=np.float64) for p in leaf_points])
+        obs = np.array(ctx.agents_obs_wp[ctx.agent_idx])
+        K_pio = prior_kernel_exact(leaf_xy, obs, c, l)
+        mi = 0.5 * np.log(np.linalg.det(np.eye(leaf_xy.shape[0]) + beta * np.dot(K_pio, K_pio.T)))
+        STATS["exact_mi"] += 1
+    STATS["near_ties"] += 1
+    out = np.empty(len(cand), dtype=np.float64)
+    for k, (dp, w, ep) in enumerate(pens):
         v = np.float64(mi)
-        v = v - (np.exp(0.5 * _norm(p - par) ** 2) if par is not None else 0)
-        v = v - (np.inf if (p[0] < ws[0] or p[0] > ws[1] or p[1] < ws[2] or p[1] > ws[3]) else 0)
-        v = v - np.exp(0.05 * count_close_exact(p, ctx.agents_obs_wp, ctx.d_wp) ** 2)
+        v = v - dp
+        v = v - w
+        v = v - ep
         out[k] = v
     return out
+
+
+STATS = {"near_ties": 0, "exact_mi": 0}  # selector near-ties re-decided on the host / of those, with the exact MI term
 
 
 def _suppression(point, source, sources) -> float:

@@ -526,7 +526,8 @@ class GaussianProcessRegressor:
         if self.normalize_y:
             self._y_train_mean = np.mean(y, axis=0)
             std = np.std(y, axis=0)
-            self._y_train_std = 1.0 if std < 10 * np.finfo(float).eps else std  # _handle_zeros_in_scale
+            # sklearn's _handle_zeros_in_scale, scalar branch (y is 1-D here): only an exactly zero spread becomes 1
+            self._y_train_std = 1.0 if std == 0.0 else std
             y = (y - self._y_train_mean) / self._y_train_std
         else:
             self._y_train_mean = 0.0

@@ -116,12 +116,20 @@ def _score_tree(self, agent_idx: int, gain_function: Optional[Callable]) -> None
     tree.variant = variant
     if gain_function is None:
         return
+    # The reference computes node.information once, when the node is inserted, and never refreshes it: a tree that
+    # survives into another tree_generation call (the selector returned an empty path, so initialize_trees was
+    # skipped) keeps the values its old nodes got under the estimates / observations of that time.  Only the nodes
+    # added since the last scoring pass are written.
+    lo = max(1, int(getattr(tree, "scored_upto", 1)))
+    if lo >= tree.n:
+        return
     if variant is not None:
-        tree.info[: tree.n] = self.scorer.tree_information(variant, tree, _context(self, agent_idx))
+        tree.info[lo: tree.n] = self.scorer.tree_information(variant, tree, _context(self, agent_idx))[lo:]
     else:  # user-supplied callable: evaluated per node on reference-shaped objects (final parents)
         nodes = tree.materialise()
-        for i in range(1, tree.n):
+        for i in range(lo, tree.n):
             tree.info[i] = gain_function(self, nodes[i], agent_idx)
+    tree.scored_upto = tree.n
 
 
 def _sample(self) -> np.ndarray:
@@ -315,8 +323,8 @@ def bias_beta_path_selection(self, agent_idx: int, current_position: Optional[np
     parent_xy = np.ascontiguousarray(tree.points()[np.where(has_parent, par, 0)])
     kern = self.scenario.gp.kernel
     ctx = _context(self, agent_idx)
-    scores, _ = self.scorer.leaf_scores(leaf_xy, parent_xy, has_parent, ctx, self.beta_t, kern.constant_value,
-                                        kern.length_scale)
+    scores, mi = self.scorer.leaf_scores(leaf_xy, parent_xy, has_parent, ctx, self.beta_t, kern.constant_value,
+                                         kern.length_scale)
     if not ctx.agent_has_obs():
         # mutual_information_gain returned the int 0: the reference's scores are int64 (mripp_b200.exact)
         best = int(np.argmax(integer_scores(scores)))
@@ -326,7 +334,7 @@ def bias_beta_path_selection(self, agent_idx: int, current_position: Optional[np
         if cand is not None:
             pts = [tree.point(int(i)) for i in leaves]
             pars = [tree.point(int(q)) if q >= 0 else None for q in par]
-            exact = exact_leaf_scores(cand, pts, pars, ctx, self.beta_t, kern.constant_value, kern.length_scale)
+            exact = exact_leaf_scores(cand, pts, pars, ctx, self.beta_t, kern.constant_value, kern.length_scale, mi_dev=mi)
             best = int(cand[int(np.argmax(exact))])
     selected = int(leaves[best])
     possible_path = tree.path_to_root(selected)

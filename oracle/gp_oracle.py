@@ -64,11 +64,12 @@ def kernel_with_gradient(X, c, length_scale):
 
 
 def normalise_y(y):
-    """_gpr.py:275-280 with _handle_zeros_in_scale (std < 10 eps -> 1)."""
+    """_gpr.py:275-280 with _handle_zeros_in_scale: y is 1-D, so np.std is a scalar and sklearn's scalar branch
+    applies (sklearn/preprocessing/_data.py: `if scale == 0.0: scale = 1.0`), not the 10 eps test of the array branch."""
     y = np.asarray(y, dtype=float)
     mean = np.mean(y, axis=0)
     std = np.std(y, axis=0)
-    if std < 10 * np.finfo(float).eps:
+    if std == 0.0:
         std = 1.0
     return (y - mean) / std, float(mean), float(std)
 

@@ -626,8 +626,15 @@ def test_run_waypoints_identical_on_device(gold, tag, cls_name, extra):
     prng = np.random.RandomState(0)
     noise = np.ptp([O.lml(g[f"{tag}_theta"] + 1e-9 * prng.randn(2), Xo, yn, False) for _ in range(24)])
     assert v_gpu >= v_ref - (1e-3 + 2.0 * noise), (v_gpu, v_ref, noise, sc.gp.kernel_.theta, g[f"{tag}_theta"])
-    assert np.abs(np.log10(Z[::4, ::4]) - np.log10(g[f"{tag}_Z"])).max() <= 1e-1
-    assert np.abs(std.reshape(Z.shape)[::4, ::4] - g[f"{tag}_std"]).max() <= 1e-1
+    # T2 field tier: 1e-2 wherever the two optimisers stop in the same place.  Measured on the B200
+    # (tools/t2_report.py, gpurun_out/t2_report.log): 1.9e-4 .. 8.9e-3 for six of the nine cases.  The exceptions are the
+    # 28-observation rig_* runs (the same observations in all three: theta* = (3.61, 3.62) here vs (4.16, 3.71) in the
+    # reference, log10 Z off by 5.9e-2) and rrtstar_random (1.3e-2): their LML is flat in log c to within its own
+    # evaluation noise (`noise` above: O(1) against an LML difference of 1.55 / 0.29), so L-BFGS-B stops where the
+    # rounding of its last line search puts it.  The T1 check below pins the field at the reference's theta.
+    t2 = {"rig_dist": 1e-1, "rig_nopen": 1e-1, "rig_rot": 1e-1, "rrtstar_random": 3e-2}.get(tag, 1e-2)
+    assert np.abs(np.log10(Z[::4, ::4]) - np.log10(g[f"{tag}_Z"])).max() <= t2
+    assert np.abs(std.reshape(Z.shape)[::4, ::4] - g[f"{tag}_std"]).max() <= t2
     # T1 on the same run: at the REFERENCE's theta the device field matches the reference's field
     th = g[f"{tag}_theta"]
     sc.gp.kernel = type(sc.gp.kernel)(float(np.exp(th[0])), float(np.exp(th[1])))
@@ -656,7 +663,7 @@ def test_boustrophedon_on_device(gold, tag, cls_name, kw):
     assert np.array_equal(np.asarray(st.obs_wp, float), g[f"{tag}_obs_wp"])
     assert np.array_equal(np.asarray(st.full_path, float), g[f"{tag}_full_path"])
     assert np.array_equal(np.random.uniform(size=3), g[f"{tag}_rng_after"])
-    assert np.abs(np.log10(Z[::4, ::4]) - np.log10(g[f"{tag}_Z"])).max() <= 1e-1
+    assert np.abs(np.log10(Z[::4, ::4]) - np.log10(g[f"{tag}_Z"])).max() <= 1e-2  # T2 (measured: 1e-14, same optimum)
     th = g[f"{tag}_theta"]
     sc.gp.kernel = type(sc.gp.kernel)(float(np.exp(th[0])), float(np.exp(th[1])))
     sc.gp.optimizer = None
