@@ -19,7 +19,7 @@ struct CholQ {
   const int* slots;   // nullable: slot(r) = r
   int R;
   const int* plan;
-  int* sched;         // [R][nflags] flags | [R][QSTATE] queue heads and ready frontiers | bulk head | abort
+  int* sched;         // [R][nflags] flags | [R][QSTATE] queue heads and ready frontiers | -, abort | per-CTA stats
   long long timeout;  // cycles a CTA may poll without finding work before it raises `abort`
   int use_hints;
   int stats;          // != 0: every CTA leaves {tasks F/S/U, cycles F/S/U, cycles acquiring, cycles total} after the abort word
@@ -214,15 +214,27 @@ __device__ __forceinline__ void cholq_solve(double* __restrict__ A, long ld, int
       for (int m0 = 0; m0 < rpw; m0 += 8) {
         const int rr = warp * rpw + m0 + g;
         const double a0 = -Xs[rr * QSTR + 8 * c + tg], a1 = -Xs[rr * QSTR + 8 * c + 4 + tg];
-        for (int ni = 0; ni < ntile; ++ni) {
-          const int cn = 8 * (c + 1 + ni);
-          double2* x = reinterpret_cast<double2*>(Xs + rr * QSTR + cn + tg * 2);
-          const double2 v = *x;
-          double acc[2] = {v.x, v.y};
-          dmma884(acc, a0, Ls[(cn + g) * QSTR + 8 * c + tg]);
-          dmma884(acc, a1, Ls[(cn + g) * QSTR + 8 * c + 4 + tg]);
-          *x = make_double2(acc[0], acc[1]);
-        }
+        double acc[7][2], b0[7], b1[7];  // all the column groups of this row group in flight together
+#pragma unroll
+        for (int ni = 0; ni < 7; ++ni)
+          if (ni < ntile) {
+            const int cn = 8 * (c + 1 + ni);
+            const double2 v = *reinterpret_cast<const double2*>(Xs + rr * QSTR + cn + tg * 2);
+            acc[ni][0] = v.x;
+            acc[ni][1] = v.y;
+            b0[ni] = Ls[(cn + g) * QSTR + 8 * c + tg];
+            b1[ni] = Ls[(cn + g) * QSTR + 8 * c + 4 + tg];
+          }
+#pragma unroll
+        for (int ni = 0; ni < 7; ++ni)
+          if (ni < ntile) {
+            dmma884(acc[ni], a0, b0[ni]);
+            dmma884(acc[ni], a1, b1[ni]);
+          }
+#pragma unroll
+        for (int ni = 0; ni < 7; ++ni)
+          if (ni < ntile)
+            *reinterpret_cast<double2*>(Xs + rr * QSTR + 8 * (c + 1 + ni) + tg * 2) = make_double2(acc[ni][0], acc[ni][1]);
       }
       __syncthreads();
     }
@@ -281,23 +293,24 @@ __device__ __forceinline__ void cholq_update_tile(double* __restrict__ A, long l
   __syncthreads();
 }
 
-enum { QS_NONE = -1, QS_EXHAUSTED = -2 };
-constexpr int QSTATE = 8;  // ints of queue state per problem: {head F, ready F, head S, ready S, head C, ready C, -, -}
+constexpr int NQ = 4;      // queues per problem: F, S, C (chain), U (bulk)
+constexpr int QSTATE = 8;  // ints of queue state per problem: {head, ready frontier} x NQ
 
-// Claiming.  Each chain queue (F, S, C of every problem) has a HEAD (next task to hand out) and a READY FRONTIER
-// (every task below it has its dependencies met).  The frontier is advanced by whoever has reason to believe it can
-// move -- a CTA that has just finished a chain task (its flag is what the next tasks wait for) and every idle CTA:
-// the lanes of the polling warp test a window of tasks beyond the frontier in parallel and add the leading run of
-// ready ones with one atomicMax.  Tasks are claimed with atomicAdd on the head whenever head < frontier, so any number
-// of CTAs claim different ready tasks in the same round trip (compare-and-swap on the head hands out ONE task per
-// round trip to all contenders together: measured 4x slower than the cooperative kernel).  A racing claim can land
-// just beyond the frontier; its owner HOLDS that task (tests it every poll, runs it as soon as it is ready) and keeps
-// serving the queues meanwhile -- with compare-and-swap claims, which cannot overshoot, so a CTA never holds more than
-// one chain task.  (Waiting for a held task without serving deadlocks: every CTA can end up holding a task behind an
-// F task nobody is free to run -- found by the host simulation of these rules, tests/test_chol_plan.py.)
-// The bulk queue has no frontier: claimed unconditionally, in order, one task AHEAD (the claim and the task's
-// dependency list are fetched while the previous task computes), so that the common case -- a bulk tile whose
-// operands are long final -- costs one round trip to L2 between two tiles.
+// Claiming.  Each queue (F, S, C, U of every problem) has a HEAD (next task to hand out) and a READY FRONTIER (every
+// task below it has its dependencies met).  The frontier is advanced by whoever has reason to believe it can move --
+// a CTA that has just finished a chain task (its flag is what the next tasks wait for) and every CTA that finds
+// nothing to claim: the lanes of the polling warp test a window of tasks beyond the frontier in parallel and add the
+// leading run of ready ones with one atomicMax.  Tasks are claimed with atomicAdd on the head whenever
+// head < frontier, so any number of CTAs claim different ready tasks in the same round trip (compare-and-swap on the
+// head hands out ONE task per round trip to all contenders together: measured 4x slower than the cooperative
+// kernel).  A racing claim can land just beyond the frontier; its owner HOLDS that task (tests it every poll, runs
+// it as soon as it is ready) and keeps serving the queues meanwhile -- with compare-and-swap claims, which cannot
+// overshoot, so a CTA never holds more than one task.  (Waiting for a held task without serving deadlocks: every CTA
+// can end up holding a task behind an F task nobody is free to run -- found by the host simulation of these rules,
+// tests/test_chol_plan.py.)  No task is ever claimed before it is ready or about to be, so a CTA never sits on work
+// of one problem while another problem has tiles to update (an in-order, claim-then-wait bulk queue did: 27 % of
+// the CTA time at four problems went into waiting for the slowest chain).
+// Priority: F, S, C, U; among the problems each CTA starts from its own (blockIdx mod R), which spreads the CTAs.
 struct QueueView {
   const int* plan;
   int* sched;
@@ -305,34 +318,32 @@ struct QueueView {
   int nflags, R;
 };
 
-// Advance the ready frontiers of problem `rsel` (< 0: of every problem).  Returns true (warp-uniform) if any moved.
-__device__ __forceinline__ bool scan_frontiers(const QueueView& v, int rsel, int lane) {
-  const int nq = rsel >= 0 ? 3 : 3 * v.R;
-  const int per = nq <= 32 ? 32 / nq : 1;  // lanes per queue; each lane tests two tasks: window 2 * per
+// Advance the ready frontiers of the NQ queues of problem r (8 lanes per queue, two tasks per lane: a window of 16;
+// the bulk queue, where hundreds of tiles become ready at once, is re-scanned while its whole window was ready).
+// Returns true (warp-uniform) if any frontier moved.
+__device__ __forceinline__ bool scan_frontiers(const QueueView& v, int r, int lane) {
+  constexpr int PER = 32 / NQ;
+  const int q = lane / PER, o = lane % PER;
+  int* st = v.qstate + QSTATE * r + 2 * q;
+  const int cnt = __ldg(v.plan + PH_NF + q);
+  const int* Tq = v.plan + __ldg(v.plan + PH_OFFF + q);
+  const int* fl = v.sched + (long)r * v.nflags;
   bool advanced = false;
-  for (int c0 = 0; c0 < nq; c0 += 32 / per) {
-    const int c = c0 + lane / per, o = lane % per;
-    bool r0 = false, r1 = false;
-    int f = 0;
-    int* st = nullptr;
-    if (c < nq && lane < per * (32 / per)) {
-      const int q = rsel >= 0 ? c : c / v.R, r = rsel >= 0 ? rsel : c % v.R;
-      st = v.qstate + QSTATE * r + 2 * q;
-      f = ld_relaxed(st + 1);
-      const int cnt = __ldg(v.plan + PH_NF + q);
-      const int* Tq = v.plan + __ldg(v.plan + PH_OFFF + q);
-      const int* fl = v.sched + (long)r * v.nflags;
-      if (f + o < cnt) r0 = task_ready(Tq + (f + o) * PLAN_TS, fl);
-      if (f + per + o < cnt) r1 = task_ready(Tq + (f + per + o) * PLAN_TS, fl);
-    }
+  for (int rep = 0; rep < 8; ++rep) {
+    const int f = ld_relaxed(st + 1);
+    const bool r0 = (f + o < cnt) && task_ready(Tq + (f + o) * PLAN_TS, fl);
+    const bool r1 = (f + PER + o < cnt) && task_ready(Tq + (f + PER + o) * PLAN_TS, fl);
     const unsigned m0 = __ballot_sync(0xffffffffu, r0), m1 = __ballot_sync(0xffffffffu, r1);
-    if (st != nullptr && o == 0) {
-      const unsigned gmask = per >= 32 ? 0xffffffffu : ((1u << per) - 1u);
+    int m = 0;
+    if (o == 0) {
+      const unsigned gmask = (1u << PER) - 1u;
       const unsigned z0 = ~(m0 >> lane) & gmask, z1 = ~(m1 >> lane) & gmask;
-      int m = z0 ? __ffs(z0) - 1 : per;  // leading run of ready tasks
-      if (m == per) m += z1 ? __ffs(z1) - 1 : per;
+      m = z0 ? __ffs(z0) - 1 : PER;  // leading run of ready tasks
+      if (m == PER) m += z1 ? __ffs(z1) - 1 : PER;
       if (m > 0) advanced = atomicMax(st + 1, f + m) >= 0;  // (the returned value makes the warp wait for the update)
     }
+    const int m_bulk = __shfl_sync(0xffffffffu, m, (NQ - 1) * PER);
+    if (m_bulk < 2 * PER) break;  // the bulk window was not all ready: nothing more to release right now
   }
   return __any_sync(0xffffffffu, advanced);
 }
@@ -344,63 +355,32 @@ __global__ void __launch_bounds__(C::THREADS, 1) chol_queue_kernel(CholQ a) {
   const int* __restrict__ plan = a.plan;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int nflags = __ldg(plan + PH_NFLAGS);
-  const int R = a.R, nq = 3 * R;
+  const int R = a.R, nq = NQ * R;
   int* qstate = a.sched + (long)R * nflags;
-  int* bulk_head = qstate + QSTATE * R;
-  int* abortf = bulk_head + 1;
+  int* abortf = qstate + QSTATE * R + 1;
   const QueueView qv = {plan, a.sched, qstate, nflags, R};
-  const int bulk_total = __ldg(plan + PH_NU) * R;
-  // ---- warp 0 scheduling state (uniform over the warp unless noted)
-  int pend = QS_NONE;                       // this CTA's claimed, not yet started bulk task
-  int pend_next = QS_NONE;                  // lane 31: the claim made one task ahead (its atomicAdd may still be in flight)
-  bool pend_ahead = false;
-  int pd_idx = -1, pd_val = 0;              // lane d < PLAN_MAXDEP: dependency d of `pend`
-  bool pd_loaded = false;
+  const int rot = blockIdx.x % R;           // this CTA's first problem
+  // ---- warp 0 scheduling state (uniform over the warp)
   int hint_q = -1, hint_i = 0, hint_r = 0;  // successor of the task just finished (tried first)
-  int held_q = -1, held_i = 0, held_r = 0;  // chain task claimed past its queue's frontier, not started yet
-  int scan_r = -1;                          // problem whose frontiers to advance before claiming (-1: none, -2: all)
+  int held_q = -1, held_i = 0, held_r = 0;  // task claimed past its queue's frontier, not started yet
+  int scan_r = -1;                          // problem whose frontiers to advance before claiming (-1: none)
+  int idle_r = rot;                         // problem an idle poll scans next
   long long idle_since = 0;
   bool idle = false;
   long long st_cyc[4] = {0, 0, 0, 0}, st_t0 = clock64(), st_mark = st_t0;  // thread 0: F, S, U, acquiring
   int st_n[3] = {0, 0, 0}, st_polls = 0;
-
-  auto claim_bulk = [&]() {  // lane 31 claims the next bulk task; everybody learns its index
-    int p = 0;
-    if (lane == 31) {
-      const int pos = (ld_relaxed(bulk_head) < bulk_total) ? atomicAdd(bulk_head, 1) : bulk_total;
-      p = pos < bulk_total ? pos : QS_EXHAUSTED;
-    }
-    pend = __shfl_sync(0xffffffffu, p, 31);
-    pd_loaded = false;
-  };
-  auto load_pend_deps = [&]() {
-    if (pend >= 0 && !pd_loaded) {
-      const int* T = plan + __ldg(plan + PH_OFFU) + (pend / R) * PLAN_TS;
-      if (lane < PLAN_MAXDEP) {
-        pd_idx = __ldg(T + TK_DEP0 + 2 * lane);
-        pd_val = __ldg(T + TK_DEP0 + 2 * lane + 1);
-      }
-      pd_loaded = true;
-    }
-  };
 
   for (;;) {
     if (warp == 0) {
       int got_q = -1, got_i = 0, got_r = 0;
       unsigned backoff = 0;
       for (;;) {
-        if (pend == QS_NONE) claim_bulk();
-        load_pend_deps();
         ++st_polls;
-        if (scan_r != -1) {
-          scan_frontiers(qv, scan_r == -2 ? -1 : scan_r, lane);
+        if (scan_r >= 0) {
+          scan_frontiers(qv, scan_r, lane);
           scan_r = -1;
         }
-        // ---- one pass of independent loads: lanes 0..5 the flags of the bulk task, lane 6 the hinted successor,
-        //      lane 7 the held task, lanes 8.. the queue states
-        bool dep_ok = true;
-        if (lane < PLAN_MAXDEP && pend >= 0 && pd_idx >= 0)
-          dep_ok = ld_acquire(a.sched + (long)(pend % R) * nflags + pd_idx) >= pd_val;
+        // ---- one pass of independent loads: lane 6 the hinted successor, lane 7 the held task, lanes 8.. the queues
         int special = 0;  // lane 6: hint can be claimed; lane 7: held task is ready
         if (lane == 6 && hint_q >= 0) {
           const int* T = plan + __ldg(plan + PH_OFFF + hint_q) + hint_i * PLAN_TS;
@@ -409,11 +389,12 @@ __global__ void __launch_bounds__(C::THREADS, 1) chol_queue_kernel(CholQ a) {
         }
         if (lane == 7 && held_q >= 0)
           special = task_ready(plan + __ldg(plan + PH_OFFF + held_q) + held_i * PLAN_TS, a.sched + (long)held_r * nflags) ? 1 : 0;
+        // candidate key = queue * R + (problem - rot mod R): lowest key wins
         int best = 0x7fffffff, best_rdy = 0, best_h = 0;
-        bool exhausted = held_q < 0 && pend == QS_EXHAUSTED;
+        bool exhausted = held_q < 0;
         if (lane >= 8)
           for (int c = lane - 8; c < nq; c += 24) {
-            const int q = c / R, r = c % R;
+            const int q = c / R, r = (c % R + rot) % R;
             const int* st = qstate + QSTATE * r + 2 * q;
             const int h = ld_relaxed(st), f = ld_relaxed(st + 1);
             if (h < __ldg(plan + PH_NF + q)) exhausted = false;
@@ -423,13 +404,12 @@ __global__ void __launch_bounds__(C::THREADS, 1) chol_queue_kernel(CholQ a) {
               best_h = h;
             }
           }
-        const bool pend_ready = pend >= 0 && (__ballot_sync(0xffffffffu, dep_ok) & 0x3fu) == 0x3fu;
         const int hint_ok = __shfl_sync(0xffffffffu, special, 6), held_ok = __shfl_sync(0xffffffffu, special, 7);
         int win = best;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) win = min(win, __shfl_xor_sync(0xffffffffu, win, o));
         const bool all_exhausted = __all_sync(0xffffffffu, exhausted);
-        // ---- decide: held > hint > chain queues > bulk
+        // ---- decide: held > hint > queues in priority order
         if (held_q >= 0 && held_ok) {
           got_q = held_q;
           got_i = held_i;
@@ -457,7 +437,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) chol_queue_kernel(CholQ a) {
           }
         }
         if (win != 0x7fffffff) {
-          const int q = win / R, r = win % R;
+          const int q = win / R, r = (win % R + rot) % R;
           const int owner = 8 + win % 24;
           int h = 0, ok = 0;
           if (lane == owner) {
@@ -486,22 +466,18 @@ __global__ void __launch_bounds__(C::THREADS, 1) chol_queue_kernel(CholQ a) {
           }
           continue;  // lost a race, claimed past the end, or now holding: look again
         }
-        if (pend_ready) {
-          got_q = 3;
-          got_i = pend / R;
-          got_r = pend % R;
-          // claim one ahead WITHOUT waiting for the answer: the index is read after the task has run
-          if (lane == 31) pend_next = atomicAdd(bulk_head, 1);
-          pend_ahead = true;
-          pend = QS_NONE;
-          break;
-        }
         if (all_exhausted) {
           got_q = -1;
           break;
         }
-        // ---- nothing to do right now: advance the frontiers; if that changed nothing, watchdog and back off
-        if (scan_frontiers(qv, -1, lane)) continue;
+        // ---- nothing to claim: advance the frontiers of one problem after the other; if a full round over the
+        //      problems moved nothing, watchdog and back off
+        bool moved = false;
+        for (int k = 0; k < R && !moved; ++k) {
+          moved = scan_frontiers(qv, idle_r, lane);
+          idle_r = (idle_r + 1) % R;
+        }
+        if (moved) continue;
         int stop = 0;
         if (lane == 0) {
           const long long now = clock64();
@@ -526,9 +502,9 @@ __global__ void __launch_bounds__(C::THREADS, 1) chol_queue_kernel(CholQ a) {
         s_task[1] = got_i;
         s_task[2] = got_r;
       }
-      // acquire side: the bulk task's flags were read with ld.acquire; a chain task was found ready through relaxed
-      // loads (possibly another CTA's, via the frontier), so fence before this CTA touches the data they guard
-      if (got_q != 3) __threadfence();
+      // acquire side: the flags were read with relaxed loads (possibly by another CTA, via the frontier): fence before
+      // this CTA touches the data they guard
+      __threadfence();
     }
     __syncthreads();
     const int q = s_task[0], ti = s_task[1], r = s_task[2];
@@ -568,9 +544,9 @@ __global__ void __launch_bounds__(C::THREADS, 1) chol_queue_kernel(CholQ a) {
       if (o2 >= 0) st_release(flags + o2, ov);
     }
     if (warp == 0) {
-      // a finished chain task is what the next chain tasks wait for: advance this problem's frontiers before claiming
+      // a finished chain task is what the next tasks wait for: advance this problem's frontiers before claiming
       // (and a bulk tile close behind the front: the chain tasks of the next super-panels wait for its flag)
-      scan_r = (q != 3 || pb * (C::BM / BLK) - pc <= 6) ? r : -1;
+      scan_r = (q != 3 || pb * (C::BM / BLK) - pd <= 6) ? r : -1;
       // successor on the critical chain: F(k) -> S(k+1, k), S(k+1, k) -> F(k+1)
       if (a.use_hints) {
         const int g = __ldg(T + TK_G);
@@ -584,14 +560,6 @@ __global__ void __launch_bounds__(C::THREADS, 1) chol_queue_kernel(CholQ a) {
           hint_r = r;
         }
       }
-      if (pend_ahead) {  // the claim made before this task ran has long arrived: fetch its dependency list now
-        int p = 0;
-        if (lane == 31) p = pend_next < bulk_total ? pend_next : QS_EXHAUSTED;
-        pend = __shfl_sync(0xffffffffu, p, 31);
-        pd_loaded = false;
-        pend_ahead = false;
-      }
-      load_pend_deps();
     }
     __syncthreads();  // s_task is rewritten by warp 0 in the next round
   }

@@ -80,24 +80,62 @@ def gather_slabs(local: "torch.Tensor", sizes: Sequence[int], group=None) -> "to
     return torch.cat([p[:s] for p, s in zip(parts, sizes)])
 
 
+def gather_field(send: "torch.Tensor", sizes: Sequence[int], group=None, pinned=None):
+    """One collective for both output fields of a slab-sharded lattice posterior.  `send` is this rank's (2, m) buffer
+    -- row 0 zpred, row 1 std, m = the largest slab, the tail beyond this rank's slab unused -- gathered into a
+    pre-sized (world, 2, m) device buffer with all_gather_into_tensor (no list of padded tensors, no torch.cat), read
+    back through ONE pinned staging buffer, and cut to the slab sizes on the host.  Returns (zpred, std) as numpy."""
+    import torch
+
+    dist = _dist()
+    world = dist.get_world_size(group)
+    m = send.shape[1]
+    recv = torch.empty((world, 2, m), dtype=send.dtype, device=send.device)
+    try:
+        dist.all_gather_into_tensor(recv.view(-1), send.reshape(-1), group=group)
+    except (RuntimeError, NotImplementedError):  # a backend without the flat form (older gloo)
+        parts = [torch.empty_like(send) for _ in range(world)]
+        dist.all_gather(parts, send.contiguous(), group=group)
+        recv = torch.stack(parts)
+    if recv.is_cuda:
+        host = pinned(recv.numel()) if pinned is not None else torch.empty(recv.numel(), dtype=recv.dtype).pin_memory()
+        host.copy_(recv.view(-1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        h = host.numpy().reshape(world, 2, m)
+    else:
+        h = recv.numpy()
+    z = np.concatenate([h[r, 0, :sz] for r, sz in enumerate(sizes)])
+    s = np.concatenate([h[r, 1, :sz] for r, sz in enumerate(sizes)])
+    return z, s
+
+
 def sharded_grid_posterior(gp, ws, nx: int, ny: int, group=None, compute_slab: Optional[Callable] = None):
     """(zpred, std) over the whole lattice, each rank computing one row slab.
 
     `compute_slab(g0, g1) -> (zpred, std)` torch tensors; defaults to the fused device posterior of
-    the fitted `gp` (mripp_b200.gp.GaussianProcessRegressor.predict_grid_device)."""
+    the fitted `gp` (mripp_b200.gp.GaussianProcessRegressor.predict_grid_device), which writes straight into the
+    send buffer of the gather."""
+    import torch
+
     dist = _dist()
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     bounds = lattice_slabs(gp, ws, nx, ny, world) if compute_slab is None else [row_slab(nx, ny, world, r) for r in range(world)]
     g0, g1 = bounds[rank]
-    if compute_slab is None:
-        def compute_slab(a, b):
-            _, std_d, z_d = gp.predict_grid_device(ws[0], ws[1], nx, ws[2], ws[3], ny, g_begin=a, g_end=b, want_zpred=True)
-            return z_d, std_d
-    z_loc, s_loc = compute_slab(g0, g1)
     sizes = [b - a for a, b in bounds]
-    z = gather_slabs(z_loc, sizes, group)
-    s = gather_slabs(s_loc, sizes, group)
-    return z.cpu().numpy(), s.cpu().numpy()
+    m, n_loc = max(sizes), g1 - g0
+    if compute_slab is None:
+        send = torch.empty((2, m), dtype=torch.float64, device="cuda")
+        mean = torch.empty(max(n_loc, 1), dtype=torch.float64, device="cuda")
+        gp.predict_grid_device(ws[0], ws[1], nx, ws[2], ws[3], ny, g_begin=g0, g_end=g1, want_zpred=True,
+                               out=(mean[:n_loc], send[1, :n_loc], send[0, :n_loc]))
+        pinned = (lambda numel: gp._ws.pinned("gather", numel)) if hasattr(gp, "_ws") else None
+    else:
+        z_loc, s_loc = compute_slab(g0, g1)
+        send = torch.zeros((2, m), dtype=z_loc.dtype, device=z_loc.device)
+        send[0, :n_loc] = z_loc
+        send[1, :n_loc] = s_loc
+        pinned = None
+    return gather_field(send, sizes, group, pinned)
 
 
 def sharded_restarts(run_one: Callable[[List[int]], List[Tuple[np.ndarray, float]]], n_starts: int, dim: int, group=None,

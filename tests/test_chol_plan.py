@@ -39,16 +39,16 @@ class Sim:
         self.cnt = [int(plan[PH_NF + q]) for q in range(4)]
         self.off = [int(plan[PH_OFFF + q]) for q in range(4)]
         self.flags = np.zeros((R, int(plan[PH_NFLAGS])), dtype=np.int64)
-        self.heads = np.zeros((R, 3), dtype=np.int64)
-        self.front = np.zeros((R, 3), dtype=np.int64)  # ready frontiers
+        self.heads = np.zeros((R, 4), dtype=np.int64)
+        self.front = np.zeros((R, 4), dtype=np.int64)  # ready frontiers
         self.window = self.rng.choice((1, 2, 20))
-        self.bulk_head = 0
         # per problem and block: panels applied so far, final?, solve parts done; blocks being written right now
         self.applied = [dict() for _ in range(R)]
         self.final = [set() for _ in range(R)]
         self.parts = [dict() for _ in range(R)]
         self.writing = [dict() for _ in range(R)]
-        self.ctas = [dict(pend=None, hint=None, busy_until=0, task=None, blocked=None, scan=None) for _ in range(n_ctas)]
+        self.ctas = [dict(hint=None, busy_until=0, task=None, blocked=None, scan=None, rot=c % R, idle_r=c % R)
+                     for c in range(n_ctas)]
         self.executed = 0
 
     def task(self, q, i):
@@ -123,21 +123,35 @@ class Sim:
         cta["task"] = None
         self.executed += 1
 
+    def scan(self, r, front0=None):
+        moved = False
+        for q in range(4):
+            f = int(self.front[r, q] if front0 is None else front0[r, q])
+            m = 0
+            while m < self.window and f + m < self.cnt[q] and self.ready(self.task(q, f + m), r):
+                m += 1
+            if m and f + m > self.front[r, q]:
+                self.front[r, q] = f + m
+                moved = True
+        return moved
+
     def acquire(self, cta, now, snap):
         """One polling round of one CTA against the queue state `snap` = (heads, frontiers) as it was at the start of
-        the tick (every CTA of a tick decides on the same stale view, like concurrent pollers on the device): hint,
-        then atomicAdd claim where head < frontier, else frontier scan, else the bulk task.  Returns 'exit', 'idle',
-        'started' or 'blocked' (claimed past the frontier: waits for that one task)."""
+        the tick (every CTA of a tick decides on the same stale view, like concurrent pollers on the device): frontier
+        scan if the last task asked for one, held task, hint, then an atomicAdd claim from the first queue (priority
+        F, S, C, U; problems rotated by CTA) whose head is behind its frontier -- landing beyond the frontier the
+        task is HELD -- else a scan of one problem after the other.  Returns 'exit', 'idle' or 'started'."""
         heads0, front0 = snap
         if cta["scan"] is not None:
-            r = cta["scan"]
+            self.scan(cta["scan"])
             cta["scan"] = None
-            for q in range(3):
-                f, m = int(self.front[r, q]), 0
-                while m < self.window and f + m < self.cnt[q] and self.ready(self.task(q, f + m), r):
-                    m += 1
-                self.front[r, q] = f + m
             front0 = self.front.copy()
+        if cta["blocked"] is not None:  # a task claimed past the frontier: held, tested first, the CTA keeps serving
+            q, h, r = cta["blocked"]
+            if self.ready(self.task(q, h), r):
+                cta["blocked"] = None
+                self.start(cta, q, h, r, now)
+                return "started"
         if cta["hint"] is not None:
             q, i, r = cta["hint"]
             cta["hint"] = None
@@ -146,17 +160,16 @@ class Sim:
                 self.front[r, q] = max(self.front[r, q], i + 1)
                 self.start(cta, q, i, r, now)
                 return "started"
-        if cta["blocked"] is not None:  # a task claimed past the frontier: held, tested first, the CTA keeps serving
-            q, h, r = cta["blocked"]
-            if self.ready(self.task(q, h), r):
-                cta["blocked"] = None
-                self.start(cta, q, h, r, now)
-                return "started"
         exhausted = cta["blocked"] is None
-        for c in range(3 * self.R):
-            q, r = divmod(c, self.R)
+        rot = cta["rot"]
+        for c in range(4 * self.R):
+            q, j = divmod(c, self.R)
+            r = (j + rot) % self.R
             if heads0[r, q] < self.cnt[q]:
                 exhausted = False
+        for c in range(4 * self.R):
+            q, j = divmod(c, self.R)
+            r = (j + rot) % self.R
             if heads0[r, q] < front0[r, q]:
                 if cta["blocked"] is None:
                     h = int(self.heads[r, q])  # atomicAdd on the live head
@@ -167,40 +180,21 @@ class Sim:
                         self.start(cta, q, h, r, now)
                         return "started"
                     cta["blocked"] = (q, h, r)
-                    return "blocked"
+                    return "idle"
                 h = int(heads0[r, q])  # holding: compare-and-swap on exactly the head seen
                 if self.heads[r, q] == h:
                     self.heads[r, q] += 1
                     self.start(cta, q, h, r, now)
                     return "started"
                 return "idle"
-        if cta["pend"] is None:
-            total = self.cnt[3] * self.R
-            if self.bulk_head < total:
-                cta["pend"] = self.bulk_head
-                self.bulk_head += 1
-            else:
-                cta["pend"] = -2
-        if cta["pend"] >= 0:
-            exhausted = False
-            ti, r = divmod(cta["pend"], self.R)
-            if self.ready(self.task(3, ti), r):
-                cta["pend"] = None
-                self.start(cta, 3, ti, r, now)
-                return "started"
-        advanced = False
-        for c in range(3 * self.R):
-            q, r = divmod(c, self.R)
-            f = int(front0[r, q])
-            m = 0
-            while m < self.window and f + m < self.cnt[q] and self.ready(self.task(q, f + m), r):
-                m += 1
-            if m:
-                self.front[r, q] = max(self.front[r, q], f + m)
-                advanced = True
-        if advanced:
-            return "idle"
-        return "exit" if exhausted else "idle"
+        if exhausted:
+            return "exit"
+        for _ in range(self.R):
+            moved = self.scan(cta["idle_r"], front0)
+            cta["idle_r"] = (cta["idle_r"] + 1) % self.R
+            if moved:
+                break
+        return "idle"
 
     def run(self):
         now, live = 0, list(range(len(self.ctas)))
@@ -217,18 +211,18 @@ class Sim:
                         progressed = True
                     else:
                         continue
-                before = (self.heads.sum(), self.front.sum(), self.bulk_head)
+                before = (self.heads.sum(), self.front.sum())
                 res = self.acquire(cta, now, snap)
                 if res == "exit":
                     live.remove(c)
                     progressed = True
-                elif res in ("started", "blocked") or before != (self.heads.sum(), self.front.sum(), self.bulk_head):
+                elif res == "started" or before != (self.heads.sum(), self.front.sum()):
                     progressed = True
             running = any(self.ctas[c]["task"] is not None for c in live)
             stall = 0 if (progressed or running) else stall + 1
             assert stall < 3, "deadlock: every resident CTA polls or waits and nothing runs"
             now += 1
-        total = sum(self.cnt) + (self.R - 1) * sum(self.cnt)
+        total = self.R * sum(self.cnt)
         assert self.executed == total, (self.executed, total)
         for r in range(self.R):
             for i in range(self.nrb):
