@@ -13,7 +13,8 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libipp_b200.so")
 PEAK = os.path.join(HERE, "fp64_peak")
 SOURCES = ["ipp_linalg.cu", "ipp_posterior.cu", "ipp_branch.cu", "ipp_field.cu", "ipp_estimation.cu", "ipp_tree_host.cu"]
-HEADERS = ["ipp_common.cuh", "ipp_gemm.cuh", os.path.join("..", "..", "include", "ipp_b200.h")]
+# every header under csrc/ (a change in any of them rebuilds) + the public C header
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join("..", "..", "include", "ipp_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off",
          "--expt-relaxed-constexpr", "--extended-lambda"]
