@@ -667,6 +667,64 @@ def run_b200(args, wl, rank, world, local_rank):
     tg_python, tr_p = grow_tree(False)
     tg_same = bool(np.array_equal(tr_n.points(), tr_p.points()) and np.array_equal(tr_n.parent[: tr_n.n], tr_p.parent[: tr_p.n])
                    and tr_n.rewires == tr_p.rewires)
+    # ---- strong scaling: ONE stock call of the workload split over the ranks -------------------------------
+    # the 11 restarts go to the ranks (gp.restart_group: start i on rank i mod P, one all_gather of the optima), the
+    # lattice goes by work-balanced row slabs (field.grid_group, one all_gather_into_tensor of both fields), the branch
+    # walks of one tree by contiguous node batches (scorer.branch_group).  Same data and RNG state on every rank.
+    strong = None
+    if world > 1:
+        Xs, meas_s, _ = synth_observations(n, W, 0)
+        wps = [Xs[i] for i in range(n)]
+
+        def strong_field(sharded):
+            f = PointSourceField(num_sources=3, workspace_size=(0, W, 0, W), seed=0)
+            if sharded:
+                f.gp.restart_group = True
+                f.grid_group = True
+            return f
+
+        def strong_call(f, k):
+            np.random.seed(k)
+            barrier()
+            t0 = time.perf_counter()
+            zz, ss = f.predict_spatial_field(wps, meas_s)
+            barrier()
+            dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            return float(dt.item()), zz, ss
+
+        one = strong_field(False)      # every rank runs the single-GPU call on the same data: the 1-GPU time of this box
+        strong_call(one, 0)
+        t_one, z1, s1 = strong_call(one, 1)
+        del one
+        torch.cuda.empty_cache()
+        shard = strong_field(True)
+        strong_call(shard, 0)
+        t_n, zn, sn = strong_call(shard, 1)
+        same = bool(np.array_equal(z1, zn) and np.array_equal(s1, sn))
+        xy0, par0 = synth_tree(B, W, 0)  # the same tree and observations on every rank
+        tree0 = TreeArrays(xy0[0], capacity=B + 1)
+        for k in range(1, B + 1):
+            tree0.add(xy0[k], int(par0[k]))
+        obs0 = [list(Xs[a * per:(a + 1) * per]) for a in range(wl["agents"])]
+        ctx0 = ScoreContext(src, xy0[0], obs0, 0, 1.0, (0, W, 0, W), [])
+        info = scorer.tree_information(3, tree0, ctx0)
+        scorer_s = GpuScorer()
+        scorer_s.branch_group = True
+        for _ in range(2):
+            scorer_s.tree_information(3, tree0, ctx0)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            info_s = scorer_s.tree_information(3, tree0, ctx0)
+        barrier()
+        br_strong_ms = 1e3 * (time.perf_counter() - t0) / 5
+        strong = {"call": "one stock PointSourceField.predict_spatial_field of the workload, restarts / lattice slabs over the ranks",
+                  "n_gpus": world, "seconds": t_n, "seconds_1gpu_same_box": t_one, "speedup": t_one / t_n,
+                  "efficiency": t_one / (world * t_n), "value": Gpts / t_n, "unit": UNIT,
+                  "identical_to_1gpu": same,
+                  "branch_batch": {"ms": br_strong_ms, "branches": B, "identical_to_1gpu": bool(np.array_equal(info_s, info, equal_nan=True))}}
+        del shard
     if sampler:
         sampler.stop()
 
@@ -784,6 +842,7 @@ def run_b200(args, wl, rank, world, local_rank):
             "tree_growth": {"nodes": int(tr_n.n), "native_ms": 1e3 * tg_native, "python_ms": 1e3 * tg_python,
                             "identical": tg_same, "call": "rig_tree_generation, budget portion 1000, step 1.0 (host code: "
                                                           "ipp_host_tree_grow vs the numpy-vectorised Python loop)"},
+            "strong": strong,
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

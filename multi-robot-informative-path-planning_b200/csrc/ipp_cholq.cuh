@@ -23,6 +23,7 @@ struct CholQ {
   long long timeout;  // cycles a CTA may poll without finding work before it raises `abort`
   int use_hints;
   int stats;          // != 0: every CTA leaves {tasks F/S/U, cycles F/S/U, cycles acquiring, cycles total} after the abort word
+  int use_mb;         // tile updates on the mbarrier pipeline (gemm_mainloop_mb) instead of a CTA barrier per k-slab
 };
 constexpr int QSTATS = 16;       // ints per CTA
 constexpr int QSTATS_CTAS = 512;
@@ -250,7 +251,7 @@ __device__ __forceinline__ void cholq_solve(double* __restrict__ A, long ld, int
 // diagonal block `skip` (block index; that one is its F task's own).
 template <class C>
 __device__ __forceinline__ void cholq_update_tile(double* __restrict__ A, long ld, int rows_total, int np, int row0, int col0,
-                                                  int kb, int ke, int cmin, int skip, double* smem) {
+                                                  int kb, int ke, int cmin, int skip, double* smem, uint64_t* bars) {
   {  // start pulling the C tile into L2 (see chol_syrk_tile)
     constexpr int LINES_PER_ROW = C::BN * 8 / 128;
     for (int e = threadIdx.x; e < C::BM * LINES_PER_ROW; e += C::THREADS) {
@@ -263,7 +264,10 @@ __device__ __forceinline__ void cholq_update_tile(double* __restrict__ A, long l
   zero_acc<C>(acc);
   auto fillA = [&](double* s, int k0) { load_tile_async<C::BM, Lay::KCONT, C::THREADS>(s, A, ld, row0, k0, rows_total, ke); };
   auto fillB = [&](double* s, int k0) { load_tile_async<C::BN, Lay::KCONT, C::THREADS>(s, A, ld, col0, k0, np, ke); };
-  gemm_mainloop<C, Lay::KCONT, Lay::KCONT>(acc, smem, kb, ke, fillA, fillB);
+  if (bars)
+    gemm_mainloop_mb<C, Lay::KCONT, Lay::KCONT>(acc, smem, bars, kb, ke, fillA, fillB);
+  else
+    gemm_mainloop<C, Lay::KCONT, Lay::KCONT>(acc, smem, kb, ke, fillA, fillB);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wm = warp / C::WARPS_N, wn = warp % C::WARPS_N, g = lane >> 2, tg = lane & 3;
   constexpr int HALF = C::MI >= 8 ? C::MI / 4 : (C::MI / 2 > 0 ? C::MI / 2 : 1);
@@ -352,6 +356,7 @@ template <class C>
 __global__ void __launch_bounds__(C::THREADS, 1) chol_queue_kernel(CholQ a) {
   extern __shared__ __align__(16) double smem[];
   __shared__ int s_task[4];  // {queue (0 F, 1 S, 2 C, 3 U; < 0: stop), task index, problem, -}
+  __shared__ __align__(8) uint64_t bars[2 * MB_STAGES];
   const int* __restrict__ plan = a.plan;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int nflags = __ldg(plan + PH_NFLAGS);
@@ -529,7 +534,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) chol_queue_kernel(CholQ a) {
       cholq_solve<C::THREADS, C::BM>(A, a.ld, pb, pa, pc, pd, smem);
     } else {
       cholq_update_tile<C>(A, a.ld, a.rows_total, a.np, pa * C::BM, pb * C::BN, pc * BLK, pd * BLK, __ldg(T + TK_E) * BLK,
-                           __ldg(T + TK_F), smem);
+                           __ldg(T + TK_F), smem, a.use_mb ? bars : nullptr);
     }
     if (a.stats && t == 0) {
       const long long now = clock64();

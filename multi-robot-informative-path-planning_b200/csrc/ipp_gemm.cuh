@@ -140,6 +140,80 @@ __device__ __forceinline__ void gemm_mainloop(double (&acc)[C::MI][C::NI][2], do
   __syncthreads();
 }
 
+// The same main loop without a CTA-wide barrier per k-slab: every stage has a "full" mbarrier (one arrival per thread,
+// fired by the hardware when that thread's cp.async copies of the stage have landed:
+// cp.async.mbarrier.arrive.noinc) and an "empty" mbarrier (one arrival per warp when it has read the stage).  A
+// warp waits only for the data it is about to multiply and for the slot it is about to refill -- which the slowest
+// warp finished PREF slabs ago -- so the eight warps drift by up to two slabs and cover each other's shared-memory
+// latencies, instead of meeting at a barrier sixteen times per rank-256 tile.  (The posterior kernel's pipeline, with
+// every warp both copying and multiplying.)  `bars` = 2 * MB_STAGES mbarriers in shared memory, (re)initialised
+// here; needs MB_STAGES * stage_doubles of shared memory.  A wait that exceeds ~2^28 polls traps: a pipeline bug
+// must end the kernel, not hang the device.
+constexpr int MB_STAGES = 4;
+constexpr int MB_PREF = 2;
+template <class C, Lay LA, Lay LB>
+__host__ __device__ constexpr size_t gemm_mb_smem_bytes() {
+  return sizeof(double) * MB_STAGES * stage_doubles<C, LA, LB>();
+}
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, unsigned parity) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+  for (unsigned spin = 0;; ++spin) {
+    uint32_t done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (spin > (1u << 28)) __trap();
+  }
+}
+template <class C, Lay LA, Lay LB, class FillA, class FillB>
+__device__ __forceinline__ void gemm_mainloop_mb(double (&acc)[C::MI][C::NI][2], double* smem, uint64_t* bars, int kbeg,
+                                                 int kend, FillA fillA, FillB fillB) {
+  constexpr int SD = stage_doubles<C, LA, LB>();
+  constexpr int AOFF = tile_doubles<C::BM, LA>();
+  uint64_t* full = bars;
+  uint64_t* empty = bars + MB_STAGES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wm = warp / C::WARPS_N, wn = warp % C::WARPS_N;
+  const int nk = (kend - kbeg + BK - 1) / BK;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < MB_STAGES; ++s) {
+      mbar_init(&full[s], C::THREADS);
+      mbar_init(&empty[s], C::THREADS / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+  auto produce = [&](int slab) {
+    double* st = smem + (slab % MB_STAGES) * SD;
+    fillA(st, kbeg + slab * BK);
+    fillB(st + AOFF, kbeg + slab * BK);
+    cp_async_mbar_arrive(&full[slab % MB_STAGES]);
+  };
+#pragma unroll
+  for (int s = 0; s < MB_PREF; ++s)
+    if (s < nk) produce(s);
+  for (int it = 0; it < nk; ++it) {
+    const int nx = it + MB_PREF;
+    if (nx < nk) {
+      if (nx >= MB_STAGES) mbar_wait_bounded(&empty[nx % MB_STAGES], ((nx / MB_STAGES) - 1) & 1);  // every warp has read the old contents
+      produce(nx);
+    }
+    mbar_wait_bounded(&full[it % MB_STAGES], (it / MB_STAGES) & 1);
+    const double* cur = smem + (it % MB_STAGES) * SD;
+    mma_slab<C, LA, LB>(acc, cur, cur + AOFF, wm, wn, lane);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[it % MB_STAGES]);
+  }
+  __syncthreads();  // the caller may reuse the stages
+}
+
 // Visit every accumulator element with its tile-local (row, col).
 template <class C, class F>
 __device__ __forceinline__ void for_each_acc(double (&acc)[C::MI][C::NI][2], F f) {

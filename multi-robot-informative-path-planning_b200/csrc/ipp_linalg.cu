@@ -19,6 +19,7 @@
 #include "ipp_chol_plan.h"
 #include "../../include/ipp_b200.h"
 #include <cooperative_groups.h>
+#include <cstdlib>
 namespace cg = cooperative_groups;
 
 namespace ipp {
@@ -608,11 +609,12 @@ __global__ void __launch_bounds__(256) diag_inverse_kernel(const double* __restr
 //   STEP 1: T[r1+i][r0+j]  =  sum_{k >= j} L[r1+i][r0+k] * W[r0+k][r0+j]
 //   STEP 2: W[r1+i][r0+j]  = -sum_{k <= i} W[r1+i][r1+k] * T[r1+k][r0+j]
 // ---------------------------------------------------------------------------------------------
-template <class C, int STEP>
+template <class C, int STEP, bool MB>
 __global__ void __launch_bounds__(C::THREADS) trtri_level_kernel(const double* __restrict__ L, long ld,
                                                                  double* __restrict__ W, long ldw, double* __restrict__ T,
                                                                  long ldt, int nb, int parts, int s, Bat bat) {
   extern __shared__ __align__(16) double smem[];
+  __shared__ __align__(8) uint64_t bars[2 * MB_STAGES];
   L += bat.slot(blockIdx.y) * bat.sK;
   W += bat.slot(blockIdx.y) * bat.sW;
   T += bat.slot(blockIdx.y) * bat.sT;
@@ -634,7 +636,10 @@ __global__ void __launch_bounds__(C::THREADS) trtri_level_kernel(const double* _
   if (STEP == 1) {
     auto fillA = [&](double* sm, int k0) { load_tile_async<C::BM, Lay::KCONT, C::THREADS>(sm, L, ld, row0, k0, r2, r1); };
     auto fillB = [&](double* sm, int k0) { load_tile_async<C::BN, Lay::MCONT, C::THREADS>(sm, W, ldw, col0, k0, r1, r1); };
-    gemm_mainloop<C, Lay::KCONT, Lay::MCONT>(acc, smem, col0, r1, fillA, fillB);
+    if (MB)
+      gemm_mainloop_mb<C, Lay::KCONT, Lay::MCONT>(acc, smem, bars, col0, r1, fillA, fillB);
+    else
+      gemm_mainloop<C, Lay::KCONT, Lay::MCONT>(acc, smem, col0, r1, fillA, fillB);
     for_each_acc<C>(acc, [&](int r, int c, double v) {
       int gr = row0 + r, gc = col0 + c;
       if (gr < r2 && gc < r1) T[(long)gr * ldt + gc] = v;
@@ -642,7 +647,10 @@ __global__ void __launch_bounds__(C::THREADS) trtri_level_kernel(const double* _
   } else {
     auto fillA = [&](double* sm, int k0) { load_tile_async<C::BM, Lay::KCONT, C::THREADS>(sm, W, ldw, row0, k0, r2, r2); };
     auto fillB = [&](double* sm, int k0) { load_tile_async<C::BN, Lay::MCONT, C::THREADS>(sm, T, ldt, col0, k0, r1, r2); };
-    gemm_mainloop<C, Lay::KCONT, Lay::MCONT>(acc, smem, r1, min(row0 + C::BM, r2), fillA, fillB);
+    if (MB)
+      gemm_mainloop_mb<C, Lay::KCONT, Lay::MCONT>(acc, smem, bars, r1, min(row0 + C::BM, r2), fillA, fillB);
+    else
+      gemm_mainloop<C, Lay::KCONT, Lay::MCONT>(acc, smem, r1, min(row0 + C::BM, r2), fillA, fillB);
     for_each_acc<C>(acc, [&](int r, int c, double v) {
       int gr = row0 + r, gc = col0 + c;
       if (gr < r2 && gc < r1) W[(long)gr * ldw + gc] = -v;
@@ -701,13 +709,14 @@ __global__ void __launch_bounds__(256) gemv_reduce_kernel(const double* __restri
 // dK_1 = K0 o D2 (D2 on l-scaled coordinates, kernels.py:1577).  Lower-triangular tiles only,
 // off-diagonal tiles weighted 2.  Per-tile partials, reduced in fixed order by lml_finalize.
 // ---------------------------------------------------------------------------------------------
-template <class C>
+template <class C, bool MB>
 __global__ void __launch_bounds__(C::THREADS) lml_grad_kernel(const double* __restrict__ W, long ldw,
                                                               const double* __restrict__ vbuf,
                                                               const double* __restrict__ hyp, double* __restrict__ partials,
                                                               GpDims d, Bat bat) {
   extern __shared__ __align__(16) double smem[];
   __shared__ double red[2][C::THREADS / 32];
+  __shared__ __align__(8) uint64_t bars[2 * MB_STAGES];
   {
     const long slot = bat.slot(blockIdx.y);
     W += slot * bat.sW;
@@ -725,7 +734,10 @@ __global__ void __launch_bounds__(C::THREADS) lml_grad_kernel(const double* __re
   zero_acc<C>(acc);
   auto fillA = [&](double* sm, int k0) { load_tile_async<C::BM, Lay::MCONT, C::THREADS>(sm, W, ldw, row0, k0, d.np, d.np); };
   auto fillB = [&](double* sm, int k0) { load_tile_async<C::BN, Lay::MCONT, C::THREADS>(sm, W, ldw, col0, k0, d.np, d.np); };
-  gemm_mainloop<C, Lay::MCONT, Lay::MCONT>(acc, smem, row0, d.np, fillA, fillB);
+  if (MB)
+    gemm_mainloop_mb<C, Lay::MCONT, Lay::MCONT>(acc, smem, bars, row0, d.np, fillA, fillB);
+  else
+    gemm_mainloop<C, Lay::MCONT, Lay::MCONT>(acc, smem, row0, d.np, fillA, fillB);
   const double c = hyp[0];
   const double* xs = vbuf + V_XS * d.npv;
   const double* ys = vbuf + V_YS * d.npv;
@@ -849,6 +861,16 @@ static bool use_small_tiles(int np) { return np <= 1536; }
 
 static const Bat kOne = {nullptr, 0, 0, 0, 0};  // a single problem in slot 0
 
+// IPP_GEMM_MB=0 selects the main loop with a CTA barrier per k-slab (A/B measurements); default: the mbarrier pipeline.
+static bool use_mb_pipeline() {
+  static const bool on = [] {
+    const char* e = getenv("IPP_GEMM_MB");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
+
 // How the factorisation is run: the cooperative kernel (grid barriers; one problem) or the dataflow kernel driven by
 // a task plan (any number of problems, ipp_cholq.cuh).
 struct CholRun {
@@ -909,6 +931,7 @@ static int chol_queue_launch(double* Kb, double* vbuf, const GpDims& d, const Ba
   a.timeout = 4000000000LL;  // ~2 s of polling without work: a scheduling bug, not a slow task
   a.use_hints = run.use_hints;
   a.stats = run.stats;
+  a.use_mb = use_mb_pipeline() ? 1 : 0;
   chol_queue_kernel<C><<<(unsigned)ctas, C::THREADS, SM, st>>>(a);
   return IPP_OK;
 }
@@ -952,16 +975,22 @@ static int chol_inplace(double* Kb, double* Wb, double* vbuf, const GpDims& d, c
   return IPP_OK;
 }
 
+template <class C, bool MB>
+static int trtri_level_t(const double* Kb, double* Wb, double* Tb, const GpDims& d, int parts, int s, const Bat& bat, int R,
+                         cudaStream_t st) {
+  constexpr size_t SM = MB ? gemm_mb_smem_bytes<C, Lay::KCONT, Lay::MCONT>() : gemm_smem_bytes<C, Lay::KCONT, Lay::MCONT>();
+  if (opt_in_smem(trtri_level_kernel<C, 1, MB>, SM) != cudaSuccess) return IPP_ERR_CUDA;
+  if (opt_in_smem(trtri_level_kernel<C, 2, MB>, SM) != cudaSuccess) return IPP_ERR_CUDA;
+  const unsigned grid = (unsigned)(((s + C::BN - 1) / C::BN) * ((s + C::BM - 1) / C::BM) * (parts / 2));
+  trtri_level_kernel<C, 1, MB><<<dim3(grid, R), C::THREADS, SM, st>>>(Kb, d.ld, Wb, d.ld, Tb, d.ld, d.np / BLK, parts, s, bat);
+  trtri_level_kernel<C, 2, MB><<<dim3(grid, R), C::THREADS, SM, st>>>(Kb, d.ld, Wb, d.ld, Tb, d.ld, d.np / BLK, parts, s, bat);
+  return IPP_OK;
+}
 template <class C>
 static int trtri_level(const double* Kb, double* Wb, double* Tb, const GpDims& d, int parts, int s, const Bat& bat, int R,
                        cudaStream_t st) {
-  constexpr size_t SM = gemm_smem_bytes<C, Lay::KCONT, Lay::MCONT>();
-  if (opt_in_smem(trtri_level_kernel<C, 1>, SM) != cudaSuccess) return IPP_ERR_CUDA;
-  if (opt_in_smem(trtri_level_kernel<C, 2>, SM) != cudaSuccess) return IPP_ERR_CUDA;
-  const unsigned grid = (unsigned)(((s + C::BN - 1) / C::BN) * ((s + C::BM - 1) / C::BM) * (parts / 2));
-  trtri_level_kernel<C, 1><<<dim3(grid, R), C::THREADS, SM, st>>>(Kb, d.ld, Wb, d.ld, Tb, d.ld, d.np / BLK, parts, s, bat);
-  trtri_level_kernel<C, 2><<<dim3(grid, R), C::THREADS, SM, st>>>(Kb, d.ld, Wb, d.ld, Tb, d.ld, d.np / BLK, parts, s, bat);
-  return IPP_OK;
+  return use_mb_pipeline() ? trtri_level_t<C, true>(Kb, Wb, Tb, d, parts, s, bat, R, st)
+                           : trtri_level_t<C, false>(Kb, Wb, Tb, d, parts, s, bat, R, st);
 }
 
 template <class C>
@@ -982,15 +1011,21 @@ static int trtri_inplace(const double* Kb, double* Wb, double* Tb, const GpDims&
   return IPP_OK;
 }
 
+template <class C, bool MB>
+static int lml_grad_launch_t(const double* Wb, double* vbuf, const double* hyp, const GpDims& d, int* ntiles, const Bat& bat,
+                             int R, cudaStream_t st) {
+  constexpr size_t SM = MB ? gemm_mb_smem_bytes<C, Lay::MCONT, Lay::MCONT>() : gemm_smem_bytes<C, Lay::MCONT, Lay::MCONT>();
+  if (opt_in_smem(lml_grad_kernel<C, MB>, SM) != cudaSuccess) return IPP_ERR_CUDA;
+  const int T = (d.np + C::BM - 1) / C::BM;
+  *ntiles = T * (T + 1) / 2;
+  lml_grad_kernel<C, MB><<<dim3(*ntiles, R), C::THREADS, SM, st>>>(Wb, d.ld, vbuf, hyp, vbuf + v_partials_off(d), d, bat);
+  return IPP_OK;
+}
 template <class C>
 static int lml_grad_launch(const double* Wb, double* vbuf, const double* hyp, const GpDims& d, int* ntiles, const Bat& bat,
                            int R, cudaStream_t st) {
-  constexpr size_t SM = gemm_smem_bytes<C, Lay::MCONT, Lay::MCONT>();
-  if (opt_in_smem(lml_grad_kernel<C>, SM) != cudaSuccess) return IPP_ERR_CUDA;
-  const int T = (d.np + C::BM - 1) / C::BM;
-  *ntiles = T * (T + 1) / 2;
-  lml_grad_kernel<C><<<dim3(*ntiles, R), C::THREADS, SM, st>>>(Wb, d.ld, vbuf, hyp, vbuf + v_partials_off(d), d, bat);
-  return IPP_OK;
+  return use_mb_pipeline() ? lml_grad_launch_t<C, true>(Wb, vbuf, hyp, d, ntiles, bat, R, st)
+                           : lml_grad_launch_t<C, false>(Wb, vbuf, hyp, d, ntiles, bat, R, st);
 }
 
 static int gp_factor(const double* X, const double* y, int n, const double* hyp, double* Kb, double* Wb, double* Tb,
