@@ -375,6 +375,9 @@ class GaussianProcessRegressor:
         self.restart_group = None
         # block sparsity of the lattice posterior: entries of k* below skip_below * c are not computed (0: dense)
         self.skip_below = 1e-30
+        # ... when the kernel's reach (the skip cutoff) is below this fraction of the data extent: beyond it every
+        # tile reaches (nearly) every slab and the clustered order buys nothing
+        self.skip_reach_max = 0.8
         self.cluster_order = "maximin"  # order of the spatial clusters in the sparse state (see clustered_order)
         self._scratch = None
         self._batch_ws = None
@@ -748,7 +751,7 @@ class GaussianProcessRegressor:
         n = X.shape[0]
         cutoff = self._skip_cutoff(length_scale)
         extent = float(np.max(X.max(axis=0) - X.min(axis=0))) if n > 1 else 0.0
-        if cutoff > 0.0 and cutoff < 0.35 * extent and n >= 256:
+        if cutoff > 0.0 and cutoff < self.skip_reach_max * extent and n >= 256:
             self._perm = clustered_order(X, cluster_order=self.cluster_order)
             pd = torch.from_numpy(self._perm).cuda()
             self._Xd_fit = self._Xd.index_select(0, pd).contiguous()

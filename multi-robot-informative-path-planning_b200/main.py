@@ -26,7 +26,8 @@ from mripp_b200.src.boustrophedon.boustrophedon import Boustrophedon, MR_Boustro
 from mripp_b200.src.point_source.point_source import PointSourceField
 from mripp_b200.src.rrt.rrt import *  # noqa: F401,F403  (strategy classes are looked up by name)
 from mripp_b200.src.utils.path_planning_utils import calculate_source_errors, run_number_from_folder, save_run_info
-from mripp_b200.src.visualization.plot_helper import calculate_differential_entropy
+from mripp_b200.src.point_source.point_source import DeviceField
+from mripp_b200.src.visualization.plot_helper import calculate_differential_entropy, field_metrics_device
 
 
 def load_configuration(config_path: str) -> Dict:
@@ -54,6 +55,9 @@ def initialize_scenarios(config: Dict, gp_factory=None) -> List[PointSourceField
         # extension of the reference's config: defer the per-step GP refits nobody reads
         if hasattr(scenario.gp, "lazy"):
             scenario.gp.lazy = bool(config["args"].get("lazy_gp", False))
+        # nothing is saved or shown: the posterior is only reduced to metrics, which happens on the device
+        if gp_factory is None and not config["args"].get("save", False) and not config["args"].get("show", False):
+            scenario.device_outputs = True
         for key, value in sc.get("specific_params", {}).items():
             scenario.update_source(int(key) - 1, *value)
         scenarios.append(scenario)
@@ -105,11 +109,16 @@ def run_simulations(scenarios, makers, args: Dict, debug: bool = False, shard=No
             for name, make in makers.items():
                 strategy = make(scenario)
                 Z_pred, std = strategy.run()
-                Z_true = scenario.ground_truth()
-                err = np.log10(Z_true + 1) - np.log10(Z_pred + 1)
-                rmse = np.sqrt(np.mean(err ** 2))
-                wrmse = np.sqrt(np.sum(Z_true * err ** 2) / np.sum(Z_true))
-                entropy = calculate_differential_entropy(std)
+                if isinstance(Z_pred, DeviceField) and isinstance(std, DeviceField):
+                    # main.py:113-116 in one fused pass over the device-resident posterior (ipp_grid_metrics): the
+                    # 16 B per lattice point are never read back
+                    rmse, wrmse, entropy = field_metrics_device(Z_pred.tensor, std.tensor, scenario.ground_truth_device(as_tensor=True))
+                else:
+                    Z_true = scenario.ground_truth()
+                    err = np.log10(Z_true + 1) - np.log10(Z_pred + 1)
+                    rmse = np.sqrt(np.mean(err ** 2))
+                    wrmse = np.sqrt(np.sum(Z_true * err ** 2) / np.sum(Z_true))
+                    entropy = calculate_differential_entropy(std)
                 est = np.array(getattr(strategy, "best_estimates", [])).reshape(-1, 3)
                 rmse_all[key][name].append(rmse)
                 wrmse_all[key][name].append(wrmse)

@@ -35,6 +35,43 @@ def _segments_intersect(x1, y1, x2, y2, x3, y3, x4, y4) -> bool:
     return 0 <= t <= 1 and 0 <= u <= 1
 
 
+class DeviceField:
+    """A posterior field that lives on the device and behaves like the ndarray the reference returns: any numpy
+    consumer (np.asarray, ufuncs, indexing, reshape) gets the host copy, made once on first use; a consumer that knows
+    about it (main.py's metrics) reads `.tensor` and never triggers the copy."""
+
+    def __init__(self, tensor):
+        self.tensor = tensor
+        self._host = None
+
+    def host(self):
+        if self._host is None:
+            self._host = self.tensor.cpu().numpy()
+        return self._host
+
+    def __array__(self, dtype=None, copy=None):
+        h = self.host()
+        return h if dtype is None else h.astype(dtype)
+
+    @property
+    def shape(self):
+        return tuple(self.tensor.shape)
+
+    def __len__(self):
+        return int(self.tensor.shape[0])
+
+    def __getitem__(self, key):
+        return self.host()[key]
+
+    def reshape(self, *shape):
+        return self.host().reshape(*shape)
+
+    def __getattr__(self, name):  # everything else (ravel, max, ...) is the host array's
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return getattr(self.host(), name)
+
+
 class PointSourceField:
     """Same constructor, attributes and methods as the reference class (point_source.py:17-353)."""
 
@@ -64,6 +101,10 @@ class PointSourceField:
         make = gp_factory if gp_factory is not None else GaussianProcessRegressor
         self.gp = make(kernel=kernel, n_restarts_optimizer=10, normalize_y=True)
         self.grid_group = None  # torch.distributed group: shard the lattice by row slab (mripp_b200.dist)
+        # True: predict_spatial_field returns DeviceField views (numpy-compatible, read back only when a host consumer
+        # touches them), so that a metrics-only caller (main.py with save = false) never copies the 16 B per lattice
+        # point to the host: the metrics are reduced on the device (ipp_grid_metrics)
+        self.device_outputs = False
 
     # -- construction helpers ---------------------------------------------------------------------
     def validate_inputs(self, num_sources, workspace_size, intensity_range) -> None:
@@ -244,6 +285,9 @@ class PointSourceField:
             from mripp_b200.dist import sharded_grid_posterior
 
             z, std = sharded_grid_posterior(gp, w, nx, ny, self.grid_group)
+        elif self.device_outputs and hasattr(gp, "predict_grid_device"):
+            _, std_d, z_d = gp.predict_grid_device(w[0], w[1], nx, w[2], w[3], ny, want_zpred=True)
+            return DeviceField(z_d.view(ny, nx)), DeviceField(std_d)
         else:
             z, std = gp.predict_grid_host(w[0], w[1], nx, w[2], w[3], ny)  # one path: the fused lattice posterior
         return z.reshape(self.X.shape), std

@@ -293,13 +293,15 @@ def test_block_sparse_posterior_equals_dense(G, torch, l):
     assert float((far[1] - np.sqrt(1.4) * gp._y_train_std).abs().max()) <= 1e-15
 
 
-def test_clustered_elimination_order_keeps_the_variance(G):
-    """The densest regime in which the block-sparse path switches on (4 observations per l x l cell): with the
-    clusters taken coarse to fine the variance is as accurate as in the given order (eliminating along the Z-order
-    curve loses 3-4 digits of sigma next to the data here: 1.8e-5)."""
+@pytest.mark.parametrize("l", [2.0, 4.0])
+def test_clustered_elimination_order_keeps_the_variance(G, l):
+    """The densest regimes in which the block-sparse path switches on (4 and 16 observations per l x l cell; at
+    l = 4 the kernel's reach is 0.67 of the workspace, the regime opened by raising the switch from 0.35 to 0.8 of
+    the extent): with the clusters taken coarse to fine the variance is as accurate as in the given order
+    (eliminating along the Z-order curve loses 3-4 digits of sigma next to the data here: 1.8e-5 at l = 2)."""
     from bench import synth_observations
 
-    n, W, l = 5000, 70, 2.0
+    n, W = 5000, 70
     X, meas, _ = synth_observations(n, W, 1)
     y = np.log10(meas)
     q = np.random.RandomState(2).uniform(0, W, (600, 2))
@@ -309,9 +311,16 @@ def test_clustered_elimination_order_keeps_the_variance(G):
     gp = G.GaussianProcessRegressor(kernel=G.ConstantRBFKernel(1.0, l), optimizer=None, normalize_y=True).fit(X, y)
     assert gp._bbox_d is not None  # sparse path on
     m, s = gp.predict(q, return_std=True)
-    # measured: 3.8e-10 c y_std^2 in the clustered order, 3.3e-10 in the given order (n = 5000 terms per column norm)
-    assert np.abs(s ** 2 - so ** 2).max() <= 2e-9 * st["c"] * st["y_std"] ** 2
-    assert np.abs(s - so).max() <= 1e-6
+    given = G.GaussianProcessRegressor(kernel=G.ConstantRBFKernel(1.0, l), optimizer=None, normalize_y=True)
+    given.skip_below = 0  # dense, observations in the given order
+    mg, sg = given.fit(X, y).predict(q, return_std=True)
+    e_clu, e_giv = np.abs(s ** 2 - so ** 2).max(), np.abs(sg ** 2 - so ** 2).max()
+    print(f"l={l}: |d sigma^2| clustered {e_clu:.2e} given {e_giv:.2e} (c y_std^2 = {st['c'] * st['y_std'] ** 2:.3g}); "
+          f"|d sigma| clustered {np.abs(s - so).max():.2e} given {np.abs(sg - so).max():.2e}")
+    # measured at l = 2: 3.8e-10 c y_std^2 in the clustered order, 3.3e-10 in the given order (n = 5000 terms per
+    # column norm); the clustered order may cost at most a small factor over the given one
+    assert e_clu <= max(2e-9 * st["c"] * st["y_std"] ** 2, 4.0 * e_giv)
+    assert np.abs(s - so).max() <= max(1e-6, 4.0 * np.abs(sg - so).max())
     assert (np.abs(m - mo) <= _mean_tol(st, q, mo)).all()
     # slabs are exactly the clusters: 16 consecutive rows of the fitted order are spatially compact
     Xs = X[gp._perm]
@@ -685,7 +694,7 @@ def test_main_config_flow_on_device(tmp_path):
     out = tmp_path / "metrics.json"
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        res = M.main(["-config", os.path.join(ROOT, "config", "example_setup.json"), "--out", str(out)])
+        res = M.main(["-config", os.path.join(ROOT, "config", "small_example_setup.json"), "--out", str(out)])
     assert len(res) == 2 and {r["strategy"] for r in res} == {
         "MultiAgentBoustrophedon", "RRTRIG_PointSourceInformative_All_SourceMetric_PathPlanning"}
     for r in json.load(open(out)):
