@@ -146,6 +146,11 @@ class GpuScorer:
         self.torch = _lib.require_cuda()
         self.lib = _lib.load()
         self.launches = 0
+        # device copies that survive between scoring calls: the tree arrays (a tree is append-only between two
+        # initialize_trees: key = identity, node count, rewire count) and the observation arrays (key = identity of
+        # the host array the context caches).  Re-uploading them on every call was 80 % of a scoring call.
+        self._resident = {}
+        self._resident_lock = __import__("threading").Lock()
         # a torch.distributed group (True = default group): shard the branch walks of one tree over its ranks in
         # contiguous batches of nodes, node table / sources / observations replicated; see tree_information
         self.branch_group = None
@@ -154,6 +159,18 @@ class GpuScorer:
     def _dev(self, a, dtype=None):
         t = self.torch.from_numpy(np.ascontiguousarray(a))
         return t.cuda(non_blocking=True)
+
+    def _resident_get(self, key, build):
+        """Device tensors for `key`, built once (at most 64 entries are kept: the agents' trees and observation sets)."""
+        with self._resident_lock:
+            hit = self._resident.get(key)
+        if hit is None:
+            hit = build()
+            with self._resident_lock:
+                if len(self._resident) >= 64:
+                    self._resident.pop(next(iter(self._resident)))
+                self._resident[key] = hit
+        return hit
 
     def close_counts(self, points, obs, d, bbox=None):
         """#observations closer than d to each point (exploitation penalty input).  bbox: tile boxes of a
@@ -183,12 +200,15 @@ class GpuScorer:
         est = ctx.estimates()
         S = est.shape[0]
         d = {"N": N, "S": S, "pts": tree.points()}
-        d["node_xy"] = self._dev(d["pts"])
-        d["parent0"] = self._dev(tree.parent0[:N].astype(np.int32))
-        hoff, htime, hpar = tree.history_csr()
-        d["hoff"] = self._dev(hoff) if htime.size else None
-        d["htime"] = self._dev(htime) if htime.size else None
-        d["hpar"] = self._dev(hpar) if htime.size else None
+
+        def tree_arrays():
+            hoff, htime, hpar = tree.history_csr()
+            return (self._dev(d["pts"]), self._dev(tree.parent0[:N].astype(np.int32)), self._dev(hoff) if htime.size else None,
+                    self._dev(htime) if htime.size else None, self._dev(hpar) if htime.size else None, tree)
+
+        # (the entry keeps a reference to the tree, so its id cannot be reused while the entry lives)
+        d["node_xy"], d["parent0"], d["hoff"], d["htime"], d["hpar"], _ = self._resident_get(
+            ("tree", id(tree), N, len(getattr(tree, "rewires", ()))), tree_arrays)
         d["src"] = self._dev(est) if S else None
         d["ws"] = self._dev(np.asarray(ctx.workspace, dtype=np.float64))
         ob = ctx.obstacle_rows()
@@ -201,8 +221,9 @@ class GpuScorer:
         d["need_close"] = bool(variant == VARIANT_ALL and d["has_obs"] and S)
         if d["need_close"]:
             d["obs_host"], bbox = ctx.all_obs_tiled()
-            d["obs"] = self._dev(d["obs_host"])
-            d["obs_bbox"] = self._dev(bbox) if bbox is not None else None
+            oh = d["obs_host"]
+            d["obs"], d["obs_bbox"], _ = self._resident_get(
+                ("obs", id(oh), oh.shape[0]), lambda: (self._dev(oh), self._dev(bbox) if bbox is not None else None, oh))
             d["sure"] = torch.empty(N, dtype=torch.int32, device="cuda")
             d["amb"] = torch.empty(N, dtype=torch.int32, device="cuda")
             d["amb_total"] = torch.zeros(1, dtype=torch.int32, device="cuda")

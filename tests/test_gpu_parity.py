@@ -319,8 +319,12 @@ def test_clustered_elimination_order_keeps_the_variance(G, l):
           f"|d sigma| clustered {np.abs(s - so).max():.2e} given {np.abs(sg - so).max():.2e}")
     # measured at l = 2: 3.8e-10 c y_std^2 in the clustered order, 3.3e-10 in the given order (n = 5000 terms per
     # column norm); the clustered order may cost at most a small factor over the given one
-    assert e_clu <= max(2e-9 * st["c"] * st["y_std"] ** 2, 4.0 * e_giv)
-    assert np.abs(s - so).max() <= max(1e-6, 4.0 * np.abs(sg - so).max())
+    # (measured on the B200: l = 2: 2.5e-10 clustered / 2.0e-10 given; l = 4: 6.8e-11 / 9.3e-12)
+    vtol = max(2e-9 * st["c"] * st["y_std"] ** 2, 4.0 * e_giv)
+    assert e_clu <= vtol
+    # sigma itself: next to the data sigma^2 is a ~1e-10 residue, so an error e in sigma^2 is up to sqrt(e) in
+    # sigma (l = 4: 6.4e-6 from 6.8e-11); 1e-6 where the problem is not that singular
+    assert np.abs(s - so).max() <= max(1e-6, np.sqrt(vtol))
     assert (np.abs(m - mo) <= _mean_tol(st, q, mo)).all()
     # slabs are exactly the clusters: 16 consecutive rows of the fitted order are spatially compact
     Xs = X[gp._perm]
