@@ -27,6 +27,14 @@ struct CholQ {
 };
 constexpr int QSTATS = 16;       // ints per CTA
 constexpr int QSTATS_CTAS = 512;
+constexpr int QTRACE_EVENTS = 448;  // stats == 2: per CTA, {queue | problem << 8, task index, start ns, end ns} per task
+constexpr int QTRACE_CTAS = 160;
+
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+  return t;
+}
 
 __device__ __forceinline__ int ld_relaxed(const int* p) {
   int v;
@@ -373,7 +381,9 @@ __global__ void __launch_bounds__(C::THREADS, 1) chol_queue_kernel(CholQ a) {
   long long idle_since = 0;
   bool idle = false;
   long long st_cyc[4] = {0, 0, 0, 0}, st_t0 = clock64(), st_mark = st_t0;  // thread 0: F, S, U, acquiring
-  int st_n[3] = {0, 0, 0}, st_polls = 0;
+  int st_n[3] = {0, 0, 0}, st_polls = 0, tr_n = 0;
+  unsigned long long tr_start = 0;
+  int* trace = abortf + 7 + QSTATS * QSTATS_CTAS;  // after the per-CTA counters
 
   for (;;) {
     if (warp == 0) {
@@ -523,6 +533,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) chol_queue_kernel(CholQ a) {
         for (int rr = 0; rr < R; ++rr) a.vbuf[(a.slots ? (long)a.slots[rr] : (long)rr) * a.vstride + a.info_off] = -7777.0;
       break;
     }
+    if (a.stats == 2 && t == 0) tr_start = global_ns();
     const int* T = plan + __ldg(plan + PH_OFFF + q) + ti * PLAN_TS;
     const int slot = a.slots ? __ldg(a.slots + r) : r;
     double* A = a.K + (long)slot * a.pstride;
@@ -541,6 +552,13 @@ __global__ void __launch_bounds__(C::THREADS, 1) chol_queue_kernel(CholQ a) {
       st_cyc[type] += now - st_mark;
       st_n[type] += 1;
       st_mark = now;
+      if (a.stats == 2 && blockIdx.x < QTRACE_CTAS && tr_n < QTRACE_EVENTS) {
+        int* e = trace + 4 * (QTRACE_EVENTS * blockIdx.x + tr_n++);
+        e[0] = q | (r << 8);
+        e[1] = ti;
+        e[2] = (int)(tr_start & 0x7fffffffu);
+        e[3] = (int)(global_ns() & 0x7fffffffu);
+      }
     }
     // every executor ends with a CTA barrier after its last global store: publish
     if (t == 0) {

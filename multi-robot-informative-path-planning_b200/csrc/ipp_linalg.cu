@@ -893,7 +893,8 @@ static long chol_sched_ints(int n, int R) {
   const int tb = use_small_tiles(d.np) ? 1 : 2;
   const int nb = d.np / BLK, nrb = nb + 1, tmax = (nrb - 1) / tb;
   const long nflags = nb + nrb + (long)(tmax + 1) * (tmax + 2) / 2;
-  return (long)R * nflags + 8L * R + 8 + (long)QSTATS * QSTATS_CTAS;  // flags | queue state | bulk head, abort | per-CTA stats
+  // flags | queue state | -, abort | per-CTA counters | per-CTA task trace (measurement aids, flags bits 1 / 2)
+  return (long)R * nflags + 8L * R + 8 + (long)QSTATS * QSTATS_CTAS + 4L * QTRACE_EVENTS * QTRACE_CTAS;
 }
 
 template <class C>
@@ -1215,7 +1216,7 @@ int ipp_gp_lml_grad_batch(const double* X, const double* y, int n, const double*
   if (R <= 0 || !plan || !sched) return IPP_ERR_ARG;
   const GpDims d = gp_dims(n > 0 ? n : 1);
   const Bat bat = {slots, (long)d.rows * d.ld, (long)d.np * d.ld, (long)d.np * d.ld, v_total(d)};
-  const CholRun run = {plan, sched, (flags & 1) ? 0 : 1, flags >> 8, (flags >> 1) & 1};
+  const CholRun run = {plan, sched, (flags & 1) ? 0 : 1, flags >> 8, (flags & 4) ? 2 : ((flags >> 1) & 1)};
   return gp_lml_grad_run(X, y, n, hyp, Kbuf, Wbuf, Tbuf, vbuf, with_grad, bat, R, run, (cudaStream_t)stream);
 }
 

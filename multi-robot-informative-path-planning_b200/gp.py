@@ -32,7 +32,27 @@ __all__ = ["ConstantRBFKernel", "ConstantKernel", "RBF", "GaussianProcessRegress
 def _chol_flags():
     """Measurement switches of the dataflow Cholesky: IPP_CHOL_HINTS=0 (no chain hand-over), IPP_CHOL_STATS=1 (per-CTA
     task / cycle counters left in the scheduling scratch)."""
-    return (1 if os.environ.get("IPP_CHOL_HINTS", "1") == "0" else 0) | (2 if os.environ.get("IPP_CHOL_STATS", "0") == "1" else 0)
+    st = os.environ.get("IPP_CHOL_STATS", "0")
+    return (1 if os.environ.get("IPP_CHOL_HINTS", "1") == "0" else 0) | (2 if st == "1" else 0) | (4 if st == "2" else 0)
+
+
+def chol_trace(ws, R):
+    """Per-task events of the last dataflow factorisation on `ws` (IPP_CHOL_STATS=2): rows (cta, queue, problem, task
+    index, start_ns, end_ns), times relative to the first event."""
+    plan = ws.plan.cpu().numpy()
+    base = R * int(plan[4]) + 8 * R + 8 + 16 * 512
+    ev = ws.sched[base:base + 4 * 448 * 160].cpu().numpy().reshape(160, 448, 4)
+    rows = []
+    for cta in range(160):
+        for e in ev[cta]:
+            if e[3] == 0 and e[2] == 0:
+                break
+            rows.append((cta, int(e[0]) & 0xff, int(e[0]) >> 8, int(e[1]), int(e[2]), int(e[3])))
+    a = np.array(rows, dtype=np.int64).reshape(-1, 6)
+    if len(a):
+        t0 = a[:, 4].min()
+        a[:, 4:] -= t0
+    return a
 
 
 def chol_stats(ws, R):

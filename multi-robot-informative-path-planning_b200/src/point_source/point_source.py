@@ -100,7 +100,7 @@ class PointSourceField:
         kernel = self.construct_kernel(kernel_params)
         make = gp_factory if gp_factory is not None else GaussianProcessRegressor
         self.gp = make(kernel=kernel, n_restarts_optimizer=10, normalize_y=True)
-        self.grid_group = None  # torch.distributed group: shard the lattice by row slab (mripp_b200.dist)
+        self.grid_group = None  # torch.distributed group (True: the default group): shard the lattice by row slab (mripp_b200.dist)
         # True: predict_spatial_field returns DeviceField views (numpy-compatible, read back only when a host consumer
         # touches them), so that a metrics-only caller (main.py with save = false) never copies the 16 B per lattice
         # point to the host: the metrics are reduced on the device (ipp_grid_metrics)
@@ -284,7 +284,7 @@ class PointSourceField:
         if self.grid_group is not None:
             from mripp_b200.dist import sharded_grid_posterior
 
-            z, std = sharded_grid_posterior(gp, w, nx, ny, self.grid_group)
+            z, std = sharded_grid_posterior(gp, w, nx, ny, None if self.grid_group is True else self.grid_group)
         elif self.device_outputs and hasattr(gp, "predict_grid_device"):
             _, std_d, z_d = gp.predict_grid_device(w[0], w[1], nx, w[2], w[3], ny, want_zpred=True)
             return DeviceField(z_d.view(ny, nx)), DeviceField(std_d)

@@ -250,7 +250,7 @@ def test_plan_shape_at_c4():
     assert plan[PH_NB] == nb and plan[PH_NRB] == nb + 1 and plan[PH_TB] == 2 and plan[PH_NF] == nb
     out = C.c_longlong(0)
     assert lib.ipp_chol_sched_ints(5000, 11, C.byref(out)) == 0
-    assert out.value == 11 * int(plan[PH_NFLAGS]) + 8 * 11 + 8 + 16 * 512
+    assert out.value == 11 * int(plan[PH_NFLAGS]) + 8 * 11 + 8 + 16 * 512 + 4 * 448 * 160
     # every dependency index is a valid flag
     for q in range(4):
         for i in range(int(plan[PH_NF + q])):
