@@ -391,10 +391,6 @@ __global__ void __launch_bounds__(C::THREADS, 1) chol_queue_kernel(CholQ a) {
       unsigned backoff = 0;
       for (;;) {
         ++st_polls;
-        if (scan_r >= 0) {
-          scan_frontiers(qv, scan_r, lane);
-          scan_r = -1;
-        }
         // ---- one pass of independent loads: lane 6 the hinted successor, lane 7 the held task, lanes 8.. the queues
         int special = 0;  // lane 6: hint can be claimed; lane 7: held task is ready
         if (lane == 6 && hint_q >= 0) {
@@ -450,6 +446,14 @@ __global__ void __launch_bounds__(C::THREADS, 1) chol_queue_kernel(CholQ a) {
             got_r = hint_r;
             break;
           }
+        }
+        // A chain task has just finished: what it enables is not below any frontier yet.  If a chain-class task is
+        // claimable anyway, take it (the frontiers are ahead of the heads: nothing is waiting to be discovered that
+        // would not be found by the next CTA that runs dry); otherwise advance this problem's frontiers first.
+        if (scan_r >= 0 && !(win != 0x7fffffff && win / R < NQ - 1)) {
+          const int sr = scan_r;
+          scan_r = -1;
+          if (scan_frontiers(qv, sr, lane)) continue;
         }
         if (win != 0x7fffffff) {
           const int q = win / R, r = (win % R + rot) % R;

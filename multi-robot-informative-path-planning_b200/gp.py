@@ -320,6 +320,7 @@ class _Workspace:
     def __init__(self):
         self.np_ = -1
         self.slots = 0
+        self.K = self.W = self.T = self.v = self.sched = None
 
     def ensure(self, n, slots=1):
         torch = _lib.require_cuda()
@@ -328,25 +329,32 @@ class _Workspace:
         _lib.check(lib.ipp_gp_layout(int(n), lay), "ipp_gp_layout")
         self.layout = [int(v) for v in lay]
         NP = self.layout[0]
-        if NP != self.np_ or slots > self.slots:
+        need = C.c_longlong(0)
+        _lib.check(lib.ipp_chol_sched_ints(int(n), max(int(slots), self.slots, 1), C.byref(need)), "ipp_chol_sched_ints")
+        fits = (self.slots >= slots and self.K is not None and self.K.numel() >= self.slots * self.layout[3]
+                and self.v.numel() >= self.slots * self.layout[6] and self.sched.numel() >= need.value)
+        if not fits:
             dev = torch.device("cuda")
-            S = int(slots)
+            S = max(int(slots), self.slots)
+            # sized for the next multiple of 512 observations: a run whose observation count grows step by step (the
+            # per-step refits of rrt.py:339,360,749) re-allocates every 512 observations, not every 64
+            cap = (C.c_longlong * 10)()
+            _lib.check(lib.ipp_gp_layout((int(n) + 511) // 512 * 512, cap), "ipp_gp_layout")
             self.K = self.W = self.T = self.v = None  # release before allocating the new set
-            self.K = torch.empty(S * self.layout[3], dtype=torch.float64, device=dev)
-            self.W = torch.empty(S * self.layout[4], dtype=torch.float64, device=dev)
-            self.T = torch.empty(S * self.layout[5], dtype=torch.float64, device=dev)
-            self.v = torch.zeros(S * self.layout[6], dtype=torch.float64, device=dev)
+            self.K = torch.empty(S * int(cap[3]), dtype=torch.float64, device=dev)
+            self.W = torch.empty(S * int(cap[4]), dtype=torch.float64, device=dev)
+            self.T = torch.empty(S * int(cap[5]), dtype=torch.float64, device=dev)
+            self.v = torch.zeros(S * int(cap[6]), dtype=torch.float64, device=dev)
             self.hyp = torch.zeros(4 * S, dtype=torch.float64, device=dev)
             self.hyp_host = torch.zeros(4 * S, dtype=torch.float64).pin_memory()
             self.res_host = torch.empty(8 * S, dtype=torch.float64).pin_memory()
             self.res_dev = torch.empty(8 * S, dtype=torch.float64, device=dev)
             self.slot_ids = torch.zeros(S, dtype=torch.int32, device=dev)
             self.slot_ids_host = torch.zeros(S, dtype=torch.int32).pin_memory()
-            need = C.c_longlong(0)
-            _lib.check(lib.ipp_chol_sched_ints(int(n), S, C.byref(need)), "ipp_chol_sched_ints")
+            _lib.check(lib.ipp_chol_sched_ints((int(n) + 511) // 512 * 512, S, C.byref(need)), "ipp_chol_sched_ints")
             self.sched = torch.zeros(need.value, dtype=torch.int32, device=dev)
-            self.np_ = NP
             self.slots = S
+        self.np_ = NP
         self.plan = chol_plan(n) if chol_mode() == "queue" else None
         return self
 
@@ -481,7 +489,7 @@ class GaussianProcessRegressor:
                                        1 if with_grad else 0, _lib.ptr(ws.plan), _lib.ptr(ws.sched), flags, _lib.stream_ptr())
         _lib.check(rc, "ipp_gp_lml_grad_batch")
         off, vt, S = ws.layout[8], ws.layout[6], ws.slots
-        torch.index_select(ws.v.view(S, vt)[:, off:off + 8], 0, ws.slot_ids[:R].long(), out=ws.res_dev.view(S, 8)[:R])
+        torch.index_select(ws.v[: S * vt].view(S, vt)[:, off:off + 8], 0, ws.slot_ids[:R].long(), out=ws.res_dev.view(S, 8)[:R])
         ws.res_host[:8 * R].copy_(ws.res_dev[:8 * R], non_blocking=True)
         torch.cuda.current_stream().synchronize()
         res = ws.res_host[:8 * R].numpy().reshape(R, 8).copy()
@@ -632,6 +640,15 @@ class GaussianProcessRegressor:
         R = len(starts)
         if self._batch_ws is None:
             self._batch_ws = _Workspace()
+        # one buffer set (K, W, T: 24 NP^2 bytes) per restart in flight: all of them when they fit in half of the free
+        # device memory (n = 5000: 11 x 0.6 GB), else the restarts go in groups
+        NP = (n + 63) // 64 * 64
+        per_slot = 3 * 8 * NP * (NP + 64)
+        have = self._batch_ws.slots if self._batch_ws.np_ == NP else 0  # (already allocated: not counted against the free memory)
+        room = int(0.5 * torch.cuda.mem_get_info()[0] // per_slot) + have
+        if room < R:
+            group = max(1, room)
+            return [o for lo in range(0, R, group) for o in self._optimise_lockstep(starts[lo:lo + group], bounds)]
         ws = self._batch_ws.ensure(n, slots=R)
         device = torch.cuda.current_device()
         stream = torch.cuda.current_stream()
