@@ -62,10 +62,11 @@ int ipp_gp_fit_final(const double* X, const double* y, int n, const double* hyp,
 /* ---- batched fit: the optimiser restarts of one fit evaluated together ---------------------------------
  * The dataflow Cholesky (csrc/ipp_cholq.cuh) executes a TASK PLAN: the list of block tasks (factor / panel solve /
  * rank-128 tile update) with the flags each one waits for.  ipp_host_chol_plan writes the plan for n observations
- * into out_host (host ints; *need = its length; out_host == NULL only sizes it); `ctas` = CTAs the kernel will
- * have resident (it only sets how finely late panel solves are split).  The caller uploads it once per size.
+ * into out_host (host ints; *need = its length; out_host == NULL only sizes it); `near_slack` >= 0: tile updates
+ * within near_slack + 1 super-panels of the factorisation front get the priority of the dependency chain (0: only
+ * the tiles the chain waits for at once).  The caller uploads the plan once per size.
  * Host function: no device work, no stream. */
-int ipp_host_chol_plan(int n, int ctas, int* out_host, long long capacity, long long* need_host);
+int ipp_host_chol_plan(int n, int near_slack, int* out_host, long long capacity, long long* need_host);
 
 /* ints of device scratch (`sched`: dependency flags + queue heads) the dataflow Cholesky needs for R problems. */
 int ipp_chol_sched_ints(int n, int R, long long* out_host);
@@ -75,8 +76,9 @@ int ipp_chol_sched_ints(int n, int R, long long* out_host);
  * Tbuf + s * out[5], vbuf + s * out[6] (ipp_gp_layout) and hyp + 4 s = {c, l, jitter, -}.  One launch sequence; the
  * factorisations share one persistent kernel and fill each other's dependency stalls.  Per-problem arithmetic does
  * not depend on R or on the slot.  plan: DEVICE copy of ipp_host_chol_plan; sched: ipp_chol_sched_ints(n, R) ints.
- * flags: bit 0 = do not hand the critical chain over by hints (measurement aid); bit 1 = leave per-CTA task / cycle
- * counters at the end of sched; bits 8.. = cap on the CTAs of the factorisation kernel (0: whole GPU).  info = -7777 in the result block: the kernel's watchdog fired.
+ * flags: bit 0 = do not hand the critical chain over by hints (measurement aid); bit 1 / bit 2 = leave per-CTA task /
+ * cycle counters / a per-task trace at the end of sched; bit 3 = advance the ready frontiers after every chain task;
+ * bits 8.. = cap on the CTAs of the factorisation kernel (0: whole GPU).  info = -7777 in the result block: the kernel's watchdog fired.
  * Replaces the objective evaluations of the n_restarts_optimizer + 1 L-BFGS-B runs of fit (sklearn _gpr.py:302-333),
  * which are independent once their start points are drawn. */
 int ipp_gp_lml_grad_batch(const double* X, const double* y, int n, const double* hyp, double* Kbuf, double* Wbuf,

@@ -61,7 +61,7 @@ struct PlanTask {
 };
 
 // Builds the plan for NP = 64 * nb.  Returns the number of ints.
-inline long chol_plan_build(int nb, int tb, int /*ctas: no task is split by CTA count any more*/, std::vector<int>& out) {
+inline long chol_plan_build(int nb, int tb, int near_slack, std::vector<int>& out) {
   const int nrb = nb + 1;
   const int tmax = (nrb - 1) / tb;                    // last tile row
   const int ntile = (tmax + 1) * (tmax + 2) / 2;
@@ -157,12 +157,11 @@ inline long chol_plan_build(int nb, int tb, int /*ctas: no task is split by CTA 
         if (paired && !(s & 1)) continue;
         const int kb = paired ? 2 * (s - 1) : p0;
         PlanTask t = u_task(ti, tj, kb, ke, tj * tb, skip, kb);
-        // Chain priority (queue C) for every tile the front reaches within three super-panels: the next super-panel's
-        // own columns (slack 0: the chain waits for them at once) and the two after it.  Left in the bulk queue, a
-        // tile of slack 1 sits behind the hundreds of far tiles released one pair earlier, and the chain -- hence
-        // the release of the next bulk tiles -- stalls until those are claimed (measured: the busy fraction of the
-        // SMs dropped from 0.92 to 0.6 for a third of the time with four problems in flight).
-        (tjs - (s + 1) <= 2 ? qC : qU).push_back(t);
+        // Chain priority (queue C) for every tile the front reaches within near_slack + 1 super-panels: the next
+        // super-panel's own columns (slack 0: the chain waits for them at once) and near_slack more.  Left in the
+        // bulk queue, a tile of slack 1 sits behind the hundreds of far tiles released one pair earlier, and the
+        // chain -- hence the release of the next bulk tiles -- stalls until those are claimed.
+        (tjs - (s + 1) <= near_slack ? qC : qU).push_back(t);
       }
   }
   out.assign(PLAN_HDR, 0);

@@ -24,6 +24,7 @@ struct CholQ {
   int use_hints;
   int stats;          // != 0: every CTA leaves {tasks F/S/U, cycles F/S/U, cycles acquiring, cycles total} after the abort word
   int use_mb;         // tile updates on the mbarrier pipeline (gemm_mainloop_mb) instead of a CTA barrier per k-slab
+  int eager_scan;     // advance the frontiers after every chain task, even if a chain task is claimable (A/B aid)
 };
 constexpr int QSTATS = 16;       // ints per CTA
 constexpr int QSTATS_CTAS = 512;
@@ -450,7 +451,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) chol_queue_kernel(CholQ a) {
         // A chain task has just finished: what it enables is not below any frontier yet.  If a chain-class task is
         // claimable anyway, take it (the frontiers are ahead of the heads: nothing is waiting to be discovered that
         // would not be found by the next CTA that runs dry); otherwise advance this problem's frontiers first.
-        if (scan_r >= 0 && !(win != 0x7fffffff && win / R < NQ - 1)) {
+        if (scan_r >= 0 && (a.eager_scan || !(win != 0x7fffffff && win / R < NQ - 1))) {
           const int sr = scan_r;
           scan_r = -1;
           if (scan_frontiers(qv, sr, lane)) continue;

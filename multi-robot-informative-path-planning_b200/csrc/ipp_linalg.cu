@@ -879,6 +879,7 @@ struct CholRun {
   int use_hints;
   int max_ctas;
   int stats;
+  int eager_scan;
 };
 
 static int device_sms(int* sms) {
@@ -933,6 +934,7 @@ static int chol_queue_launch(double* Kb, double* vbuf, const GpDims& d, const Ba
   a.use_hints = run.use_hints;
   a.stats = run.stats;
   a.use_mb = use_mb_pipeline() ? 1 : 0;
+  a.eager_scan = run.eager_scan;
   chol_queue_kernel<C><<<(unsigned)ctas, C::THREADS, SM, st>>>(a);
   return IPP_OK;
 }
@@ -1187,15 +1189,15 @@ int ipp_gram_rbf(const double* X, int n, const double* Y, int m, double c, doubl
 
 int ipp_gp_lml_grad(const double* X, const double* y, int n, const double* hyp, double* Kbuf, double* Wbuf,
                     double* Tbuf, double* vbuf, int with_grad, int max_ctas, void* stream) {
-  const CholRun run = {nullptr, nullptr, 0, max_ctas, 0};
+  const CholRun run = {nullptr, nullptr, 0, max_ctas, 0, 0};
   return gp_lml_grad_run(X, y, n, hyp, Kbuf, Wbuf, Tbuf, vbuf, with_grad, kOne, 1, run, (cudaStream_t)stream);
 }
 
-int ipp_host_chol_plan(int n, int ctas, int* out_host, long long capacity, long long* need) {
-  if (n <= 0 || !need) return IPP_ERR_ARG;
+int ipp_host_chol_plan(int n, int near_slack, int* out_host, long long capacity, long long* need) {
+  if (n <= 0 || !need || near_slack < 0) return IPP_ERR_ARG;
   const GpDims d = gp_dims(n);
   std::vector<int> plan;
-  chol_plan_build(d.np / BLK, use_small_tiles(d.np) ? 1 : 2, ctas > 0 ? ctas : 148, plan);
+  chol_plan_build(d.np / BLK, use_small_tiles(d.np) ? 1 : 2, near_slack, plan);
   *need = (long long)plan.size();
   if (out_host) {
     if (capacity < (long long)plan.size()) return IPP_ERR_ARG;
@@ -1216,7 +1218,7 @@ int ipp_gp_lml_grad_batch(const double* X, const double* y, int n, const double*
   if (R <= 0 || !plan || !sched) return IPP_ERR_ARG;
   const GpDims d = gp_dims(n > 0 ? n : 1);
   const Bat bat = {slots, (long)d.rows * d.ld, (long)d.np * d.ld, (long)d.np * d.ld, v_total(d)};
-  const CholRun run = {plan, sched, (flags & 1) ? 0 : 1, flags >> 8, (flags & 4) ? 2 : ((flags >> 1) & 1)};
+  const CholRun run = {plan, sched, (flags & 1) ? 0 : 1, flags >> 8, (flags & 4) ? 2 : ((flags >> 1) & 1), (flags >> 3) & 1};
   return gp_lml_grad_run(X, y, n, hyp, Kbuf, Wbuf, Tbuf, vbuf, with_grad, bat, R, run, (cudaStream_t)stream);
 }
 
@@ -1237,13 +1239,13 @@ static int gp_fit_final_run(const double* X, const double* y, int n, const doubl
 
 int ipp_gp_fit_final(const double* X, const double* y, int n, const double* hyp, double* Kbuf, double* Wbuf,
                      double* Tbuf, double* vbuf, void* stream) {
-  const CholRun run = {nullptr, nullptr, 0, 0, 0};
+  const CholRun run = {nullptr, nullptr, 0, 0, 0, 0};
   return gp_fit_final_run(X, y, n, hyp, Kbuf, Wbuf, Tbuf, vbuf, run, (cudaStream_t)stream);
 }
 
 int ipp_gp_fit_final_plan(const double* X, const double* y, int n, const double* hyp, double* Kbuf, double* Wbuf,
                           double* Tbuf, double* vbuf, const int* plan, int* sched, int flags, void* stream) {
-  const CholRun run = {plan, plan ? sched : nullptr, (flags & 1) ? 0 : 1, 0, 0};
+  const CholRun run = {plan, plan ? sched : nullptr, (flags & 1) ? 0 : 1, 0, 0, (flags >> 3) & 1};
   return gp_fit_final_run(X, y, n, hyp, Kbuf, Wbuf, Tbuf, vbuf, run, (cudaStream_t)stream);
 }
 
@@ -1261,7 +1263,7 @@ int ipp_mi_logdet(const double* leaf_xy, int L, const double* obs_xy, int na, do
   int rc = use_small_tiles(d.np) ? mi_build<Cfg64>(Gtmp, nap, Lp, nap, trans, beta, Kbuf, d, st)
                                  : mi_build<Cfg128>(Gtmp, nap, Lp, nap, trans, beta, Kbuf, d, st);
   if (rc != IPP_OK) return rc;
-  const CholRun run = {nullptr, nullptr, 0, 0, 0};
+  const CholRun run = {nullptr, nullptr, 0, 0, 0, 0};
   rc = use_small_tiles(d.np) ? chol_inplace<Cfg64>(Kbuf, Wbuf, vbuf, d, kOne, 1, run, st)
                              : chol_inplace<Cfg128>(Kbuf, Wbuf, vbuf, d, kOne, 1, run, st);
   if (rc != IPP_OK) return rc;

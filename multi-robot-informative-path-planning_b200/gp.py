@@ -33,7 +33,8 @@ def _chol_flags():
     """Measurement switches of the dataflow Cholesky: IPP_CHOL_HINTS=0 (no chain hand-over), IPP_CHOL_STATS=1 (per-CTA
     task / cycle counters left in the scheduling scratch)."""
     st = os.environ.get("IPP_CHOL_STATS", "0")
-    return (1 if os.environ.get("IPP_CHOL_HINTS", "1") == "0" else 0) | (2 if st == "1" else 0) | (4 if st == "2" else 0)
+    return ((1 if os.environ.get("IPP_CHOL_HINTS", "1") == "0" else 0) | (2 if st == "1" else 0) | (4 if st == "2" else 0)
+            | (8 if os.environ.get("IPP_CHOL_EAGER_SCAN", "0") == "1" else 0))
 
 
 def chol_trace(ws, R):
@@ -290,6 +291,7 @@ def chol_mode():
 
 _PLANS = {}
 _PLAN_LOCK = threading.Lock()
+NEAR_SLACK = 0
 
 
 def chol_plan(n):
@@ -298,18 +300,17 @@ def chol_plan(n):
     lib = _lib.load()
     dev = torch.cuda.current_device()
     NP = (int(n) + 63) // 64 * 64
+    near = int(os.environ.get("IPP_CHOL_NEAR", str(NEAR_SLACK)))  # tiles within near + 1 super-panels of the front: chain priority
     with _PLAN_LOCK:
-        plan = _PLANS.get((dev, NP))
+        plan = _PLANS.get((dev, NP, near))
         if plan is None:
-            sms = torch.cuda.get_device_properties(dev).multi_processor_count
-            ctas = sms * (2 if NP <= 1536 else 1)  # resident CTAs of the kernel (64x64-tile variant: two per SM)
             need = C.c_longlong(0)
-            _lib.check(lib.ipp_host_chol_plan(int(n), ctas, None, 0, C.byref(need)), "ipp_host_chol_plan")
+            _lib.check(lib.ipp_host_chol_plan(int(n), near, None, 0, C.byref(need)), "ipp_host_chol_plan")
             host = torch.empty(need.value, dtype=torch.int32).pin_memory()
-            _lib.check(lib.ipp_host_chol_plan(int(n), ctas, C.cast(host.data_ptr(), C.POINTER(C.c_int)), need.value,
+            _lib.check(lib.ipp_host_chol_plan(int(n), near, C.cast(host.data_ptr(), C.POINTER(C.c_int)), need.value,
                                               C.byref(need)), "ipp_host_chol_plan")
             plan = host.cuda()
-            _PLANS[(dev, NP)] = plan
+            _PLANS[(dev, NP, near)] = plan
     return plan
 
 

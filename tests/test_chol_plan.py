@@ -23,12 +23,12 @@ TK_TYPE, TK_A, TK_B, TK_C, TK_D, TK_E, TK_F, TK_G, TK_NDEP, TK_DEP0 = range(10)
 TK_OUT, TK_OUTVAL, TK_OUT2 = TK_DEP0 + 2 * MAXDEP, TK_DEP0 + 2 * MAXDEP + 1, TK_DEP0 + 2 * MAXDEP + 2
 
 
-def build_plan(n, ctas):
+def build_plan(n, near):
     lib = _lib.load()
     need = C.c_longlong(0)
-    assert lib.ipp_host_chol_plan(n, ctas, None, 0, C.byref(need)) == 0
+    assert lib.ipp_host_chol_plan(n, near, None, 0, C.byref(need)) == 0
     buf = (C.c_int * need.value)()
-    assert lib.ipp_host_chol_plan(n, ctas, buf, need.value, C.byref(need)) == 0
+    assert lib.ipp_host_chol_plan(n, near, buf, need.value, C.byref(need)) == 0
     return np.frombuffer(buf, dtype=np.int32).copy()
 
 
@@ -231,12 +231,12 @@ class Sim:
                     assert self.applied[r].get((i, j), 0) == j, ("panels applied", i, j, self.applied[r].get((i, j), 0))
 
 
-@pytest.mark.parametrize("n,ctas,R,n_sim", [
-    (64, 148, 1, 1), (100, 148, 2, 3), (300, 148, 1, 7), (500, 8, 3, 5), (700, 148, 1, 1), (1000, 296, 2, 40),
-    (1600, 148, 1, 1), (1700, 148, 1, 16), (2000, 148, 2, 33), (2100, 148, 3, 148),
+@pytest.mark.parametrize("n,near,R,n_sim", [
+    (64, 0, 1, 1), (100, 2, 2, 3), (300, 0, 1, 7), (500, 1, 3, 5), (700, 0, 1, 1), (1000, 2, 2, 40),
+    (1600, 0, 1, 1), (1700, 3, 1, 16), (2000, 0, 2, 33), (2100, 1, 3, 148),
 ])
-def test_plan_is_deadlock_free_and_complete(n, ctas, R, n_sim):
-    plan = build_plan(n, ctas)
+def test_plan_is_deadlock_free_and_complete(n, near, R, n_sim):
+    plan = build_plan(n, near)
     assert plan[PH_MAGIC] == 0x43485132 and plan[PH_TS] == TS and plan[PH_TOTAL] == len(plan)
     for seed in range(2):
         Sim(plan, R, n_sim, seed, hints=bool(seed % 2 == 0)).run()
@@ -245,7 +245,7 @@ def test_plan_is_deadlock_free_and_complete(n, ctas, R, n_sim):
 def test_plan_shape_at_c4():
     """The C4 size (n = 5000): tile mode, queue sizes, scratch size reported by the library."""
     lib = _lib.load()
-    plan = build_plan(5000, 148)
+    plan = build_plan(5000, 0)
     nb = 5056 // 64
     assert plan[PH_NB] == nb and plan[PH_NRB] == nb + 1 and plan[PH_TB] == 2 and plan[PH_NF] == nb
     out = C.c_longlong(0)

@@ -193,9 +193,36 @@ def timing(ns, fits=True):
         os.environ["IPP_CHOL"] = "queue"
 
 
+def chol_only(n):
+    """Batched factorisation alone (no gradient), R = 1, 4, 11: the number the scheduling switches move."""
+    X, y = data(n)
+    NP = (n + 63) // 64 * 64
+    gp = fixed_gp(X, y, "queue")
+    out = []
+    for R in (1, 4, 11):
+        ws = G._Workspace().ensure(n, slots=R)
+        rng = np.random.RandomState(1)
+        thetas = [np.array([rng.uniform(-1, 1), rng.uniform(0, 1.5)]) for _ in range(R)]
+        for _ in range(2):
+            gp._eval_batch(ws, list(range(R)), thetas, False)
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        for _ in range(4):
+            gp._eval_batch(ws, list(range(R)), thetas, False)
+        torch.cuda.synchronize()
+        ms = 1e3 * (time.perf_counter() - t) / 4
+        out.append(f"R={R}: {ms / R:.3f} ms/problem ({R * NP ** 3 / 3 / ms / 1e9:.2f} TF)")
+        del ws
+    print(f"n={n} NEAR={os.environ.get('IPP_CHOL_NEAR', 'default')} EAGER_SCAN={os.environ.get('IPP_CHOL_EAGER_SCAN', '0')} "
+          f"MB={os.environ.get('IPP_GEMM_MB', '1')}: " + "; ".join(out), flush=True)
+
+
 if __name__ == "__main__":
     _lib.require_cuda()
     cmd = sys.argv[1] if len(sys.argv) > 1 else "check"
     if cmd == "check":
         sys.exit(0 if check() else 1)
+    if cmd == "chol":
+        chol_only(int(sys.argv[2]) if len(sys.argv) > 2 else 5000)
+        sys.exit(0)
     timing([int(a) for a in sys.argv[2:]] or [500, 2000, 5000], fits=(cmd != "evals"))
