@@ -79,11 +79,15 @@ int ipp_chol_sched_ints(int n, int R, long long* out_host);
  * flags: bit 0 = do not hand the critical chain over by hints (measurement aid); bit 1 / bit 2 = leave per-CTA task /
  * cycle counters / a per-task trace at the end of sched; bit 3 = advance the ready frontiers after every chain task;
  * bits 8.. = cap on the CTAs of the factorisation kernel (0: whole GPU).  info = -7777 in the result block: the kernel's watchdog fired.
+ * tile_bbox (nullable): {xmin, xmax, ymin, ymax} (unscaled) of every block of T consecutive observations in the order
+ * given (T = 64 for NP <= 1536, else 128; NP / T boxes).  When present the gradient contraction skips tile pairs
+ * whose boxes are farther apart than 13.6 l (every dK entry there is below 2e-38 c): worth giving when the caller has
+ * put the observations in a spatial order (the Python layer: Z-order curve).
  * Replaces the objective evaluations of the n_restarts_optimizer + 1 L-BFGS-B runs of fit (sklearn _gpr.py:302-333),
  * which are independent once their start points are drawn. */
 int ipp_gp_lml_grad_batch(const double* X, const double* y, int n, const double* hyp, double* Kbuf, double* Wbuf,
                           double* Tbuf, double* vbuf, const int* slots, int R, int with_grad, const int* plan, int* sched,
-                          int flags, void* stream);
+                          int flags, const double* tile_bbox, void* stream);
 
 /* ipp_gp_fit_final with the dataflow Cholesky (plan / sched as above; plan == NULL: the cooperative kernel). */
 int ipp_gp_fit_final_plan(const double* X, const double* y, int n, const double* hyp, double* Kbuf, double* Wbuf,

@@ -29,7 +29,7 @@ SIGNATURES = {
     "ipp_gp_fit_final": [_D, _D, _I, _D, _D, _D, _D, _D, _D],
     "ipp_host_chol_plan": [_I, _I, C.POINTER(_I), _LL, C.POINTER(_LL)],
     "ipp_chol_sched_ints": [_I, _I, C.POINTER(_LL)],
-    "ipp_gp_lml_grad_batch": [_D, _D, _I, _D, _D, _D, _D, _D, _D, _I, _I, _D, _D, _I, _D],
+    "ipp_gp_lml_grad_batch": [_D, _D, _I, _D, _D, _D, _D, _D, _D, _I, _I, _D, _D, _I, _D, _D],
     "ipp_gp_fit_final_plan": [_D, _D, _I, _D, _D, _D, _D, _D, _D, _D, _I, _D],
     "ipp_gp_posterior_grid": [_D, _D, _I, _F, _F, _F, _F, _F, _F, _I, _F, _F, _I, _LL, _LL, _D, _D, _D, _D, _D, _D, _F, _I, _D],
     "ipp_gp_posterior_points": [_D, _D, _I, _F, _F, _F, _F, _D, _LL, _D, _D, _D, _D, _I, _D],

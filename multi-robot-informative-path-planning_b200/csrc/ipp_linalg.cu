@@ -713,7 +713,7 @@ template <class C, bool MB>
 __global__ void __launch_bounds__(C::THREADS) lml_grad_kernel(const double* __restrict__ W, long ldw,
                                                               const double* __restrict__ vbuf,
                                                               const double* __restrict__ hyp, double* __restrict__ partials,
-                                                              GpDims d, Bat bat) {
+                                                              GpDims d, Bat bat, const double* __restrict__ tile_bbox) {
   extern __shared__ __align__(16) double smem[];
   __shared__ double red[2][C::THREADS / 32];
   __shared__ __align__(8) uint64_t bars[2 * MB_STAGES];
@@ -730,6 +730,19 @@ __global__ void __launch_bounds__(C::THREADS) lml_grad_kernel(const double* __re
   while ((long)ti * (ti + 1) / 2 > b) --ti;
   const int tj = b - ti * (ti + 1) / 2;
   const int row0 = ti * C::BM, col0 = tj * C::BN;
+  // Block sparsity of the contraction.  Every term carries dK_ij = K_ij (or K_ij d2_ij), and with the observations in
+  // a spatial order a tile pair whose bounding boxes are farther apart than 13.6 l has K_ij d2_ij < 2e-38 c for all
+  // of its 128 x 128 entries: against |alpha_i alpha_j - K^-1_ij| <= ~1e14 that is below 1e-23 of anything the sum
+  // keeps, so the tile contributes exactly nothing representable and its W^T W product is not formed at all.
+  if (tile_bbox != nullptr && ti != tj) {
+    const double4 bi = *reinterpret_cast<const double4*>(tile_bbox + 4 * ti), bj = *reinterpret_cast<const double4*>(tile_bbox + 4 * tj);
+    const double gx = fmax(0.0, fmax(bi.x - bj.y, bj.x - bi.y)), gy = fmax(0.0, fmax(bi.z - bj.w, bj.z - bi.w));
+    const double cut = 13.6 * hyp[1];
+    if (gx * gx + gy * gy > cut * cut) {
+      if (threadIdx.x == 0) partials[2 * b] = partials[2 * b + 1] = 0.0;
+      return;
+    }
+  }
   double acc[C::MI][C::NI][2];
   zero_acc<C>(acc);
   auto fillA = [&](double* sm, int k0) { load_tile_async<C::BM, Lay::MCONT, C::THREADS>(sm, W, ldw, row0, k0, d.np, d.np); };
@@ -1016,19 +1029,20 @@ static int trtri_inplace(const double* Kb, double* Wb, double* Tb, const GpDims&
 
 template <class C, bool MB>
 static int lml_grad_launch_t(const double* Wb, double* vbuf, const double* hyp, const GpDims& d, int* ntiles, const Bat& bat,
-                             int R, cudaStream_t st) {
+                             int R, const double* tile_bbox, cudaStream_t st) {
   constexpr size_t SM = MB ? gemm_mb_smem_bytes<C, Lay::MCONT, Lay::MCONT>() : gemm_smem_bytes<C, Lay::MCONT, Lay::MCONT>();
   if (opt_in_smem(lml_grad_kernel<C, MB>, SM) != cudaSuccess) return IPP_ERR_CUDA;
   const int T = (d.np + C::BM - 1) / C::BM;
   *ntiles = T * (T + 1) / 2;
-  lml_grad_kernel<C, MB><<<dim3(*ntiles, R), C::THREADS, SM, st>>>(Wb, d.ld, vbuf, hyp, vbuf + v_partials_off(d), d, bat);
+  lml_grad_kernel<C, MB><<<dim3(*ntiles, R), C::THREADS, SM, st>>>(Wb, d.ld, vbuf, hyp, vbuf + v_partials_off(d), d, bat,
+                                                                   tile_bbox);
   return IPP_OK;
 }
 template <class C>
 static int lml_grad_launch(const double* Wb, double* vbuf, const double* hyp, const GpDims& d, int* ntiles, const Bat& bat,
-                           int R, cudaStream_t st) {
-  return use_mb_pipeline() ? lml_grad_launch_t<C, true>(Wb, vbuf, hyp, d, ntiles, bat, R, st)
-                           : lml_grad_launch_t<C, false>(Wb, vbuf, hyp, d, ntiles, bat, R, st);
+                           int R, const double* tile_bbox, cudaStream_t st) {
+  return use_mb_pipeline() ? lml_grad_launch_t<C, true>(Wb, vbuf, hyp, d, ntiles, bat, R, tile_bbox, st)
+                           : lml_grad_launch_t<C, false>(Wb, vbuf, hyp, d, ntiles, bat, R, tile_bbox, st);
 }
 
 static int gp_factor(const double* X, const double* y, int n, const double* hyp, double* Kb, double* Wb, double* Tb,
@@ -1051,7 +1065,7 @@ static int gp_factor(const double* X, const double* y, int n, const double* hyp,
 // One LML (+ gradient) evaluation of each of the R problems of a batch.
 static int gp_lml_grad_run(const double* X, const double* y, int n, const double* hyp, double* Kbuf, double* Wbuf,
                            double* Tbuf, double* vbuf, int with_grad, const Bat& bat, int R, const CholRun& run,
-                           cudaStream_t st) {
+                           const double* tile_bbox, cudaStream_t st) {
   int rc = gp_factor(X, y, n, hyp, Kbuf, Wbuf, Tbuf, vbuf, with_grad != 0, bat, R, run, st);
   if (rc != IPP_OK) return rc;
   const GpDims d = gp_dims(n);
@@ -1060,8 +1074,8 @@ static int gp_lml_grad_run(const double* X, const double* y, int n, const double
     // partials go to Tbuf, which the triangular inverse is done with
     gemv_wt_kernel<<<dim3(d.np / BLK, GEMV_SPLIT, R), 256, 0, st>>>(Wbuf, d.ld, Kbuf + (long)d.np * d.ld, Tbuf, d.np, bat);
     gemv_reduce_kernel<<<dim3((d.np + 255) / 256, R), 256, 0, st>>>(Tbuf, vbuf + V_ALPHA * d.npv, d.np, bat);
-    rc = use_small_tiles(d.np) ? lml_grad_launch<Cfg64>(Wbuf, vbuf, hyp, d, &ntiles, bat, R, st)
-                               : lml_grad_launch<Cfg128>(Wbuf, vbuf, hyp, d, &ntiles, bat, R, st);
+    rc = use_small_tiles(d.np) ? lml_grad_launch<Cfg64>(Wbuf, vbuf, hyp, d, &ntiles, bat, R, tile_bbox, st)
+                               : lml_grad_launch<Cfg128>(Wbuf, vbuf, hyp, d, &ntiles, bat, R, tile_bbox, st);
     if (rc != IPP_OK) return rc;
   }
   lml_finalize_kernel<<<R, 256, 0, st>>>(Kbuf, vbuf, ntiles, with_grad, d, bat);
@@ -1190,7 +1204,7 @@ int ipp_gram_rbf(const double* X, int n, const double* Y, int m, double c, doubl
 int ipp_gp_lml_grad(const double* X, const double* y, int n, const double* hyp, double* Kbuf, double* Wbuf,
                     double* Tbuf, double* vbuf, int with_grad, int max_ctas, void* stream) {
   const CholRun run = {nullptr, nullptr, 0, max_ctas, 0, 0};
-  return gp_lml_grad_run(X, y, n, hyp, Kbuf, Wbuf, Tbuf, vbuf, with_grad, kOne, 1, run, (cudaStream_t)stream);
+  return gp_lml_grad_run(X, y, n, hyp, Kbuf, Wbuf, Tbuf, vbuf, with_grad, kOne, 1, run, nullptr, (cudaStream_t)stream);
 }
 
 int ipp_host_chol_plan(int n, int near_slack, int* out_host, long long capacity, long long* need) {
@@ -1214,12 +1228,12 @@ int ipp_chol_sched_ints(int n, int R, long long* out) {
 
 int ipp_gp_lml_grad_batch(const double* X, const double* y, int n, const double* hyp, double* Kbuf, double* Wbuf,
                           double* Tbuf, double* vbuf, const int* slots, int R, int with_grad, const int* plan, int* sched,
-                          int flags, void* stream) {
+                          int flags, const double* tile_bbox, void* stream) {
   if (R <= 0 || !plan || !sched) return IPP_ERR_ARG;
   const GpDims d = gp_dims(n > 0 ? n : 1);
   const Bat bat = {slots, (long)d.rows * d.ld, (long)d.np * d.ld, (long)d.np * d.ld, v_total(d)};
   const CholRun run = {plan, sched, (flags & 1) ? 0 : 1, flags >> 8, (flags & 4) ? 2 : ((flags >> 1) & 1), (flags >> 3) & 1};
-  return gp_lml_grad_run(X, y, n, hyp, Kbuf, Wbuf, Tbuf, vbuf, with_grad, bat, R, run, (cudaStream_t)stream);
+  return gp_lml_grad_run(X, y, n, hyp, Kbuf, Wbuf, Tbuf, vbuf, with_grad, bat, R, run, tile_bbox, (cudaStream_t)stream);
 }
 
 static int gp_fit_final_run(const double* X, const double* y, int n, const double* hyp, double* Kbuf, double* Wbuf,

@@ -404,6 +404,9 @@ class GaussianProcessRegressor:
         self.restart_group = None
         # block sparsity of the lattice posterior: entries of k* below skip_below * c are not computed (0: dense)
         self.skip_below = 1e-30
+        # order in which the optimiser's objective sees the observations: "zcurve" (block-sparse gradient contraction)
+        # or "given"
+        self.objective_order = os.environ.get("IPP_OBJECTIVE_ORDER", "zcurve")
         # ... when the kernel's reach (the skip cutoff) is below this fraction of the data extent: beyond it every
         # tile reaches (nearly) every slab and the clustered order buys nothing
         self.skip_reach_max = 0.8
@@ -436,6 +439,19 @@ class GaussianProcessRegressor:
         self.h2d_bytes_ = 24 * n
         self._perm = np.arange(n)
         self._Xd_fit, self._yd_fit, self._bbox_d = self._Xd, self._yd, None
+        # The OBJECTIVE sees the observations along a Z-order curve (the LML and its gradient do not depend on the order
+        # of the observations; the rounding does, deterministically): 128 consecutive ones are then a compact patch
+        # of the workspace, and the gradient contraction skips the tile pairs whose patches are out of each other's
+        # reach (ipp_gp_lml_grad_batch, tile_bbox).  Small problems keep the given order (one or two tiles anyway).
+        self._Xd_obj, self._yd_obj, self._tile_bbox_d = self._Xd, self._yd, None
+        if self.objective_order == "zcurve" and n >= 1024:
+            order = morton_order(X)
+            od = torch.from_numpy(order).cuda()
+            self._Xd_obj = self._Xd.index_select(0, od).contiguous()
+            self._yd_obj = self._yd.index_select(0, od).contiguous()
+            NP = (n + 63) // 64 * 64
+            tile = 64 if NP <= 1536 else 128
+            self._tile_bbox_d = torch.from_numpy(slab_bounding_boxes(X[order], (NP + tile - 1) // tile * tile, slab=tile)).cuda()
 
     def _eval_device(self, c, l, with_grad, final=False, ws=None, max_ctas=0):
         """Launch one LML (+gradient) evaluation or the final factorisation on the calling thread's
@@ -457,9 +473,10 @@ class GaussianProcessRegressor:
                                            _lib.ptr(ws.sched), flags, st)
             _lib.check(rc, "ipp_gp_fit_final_plan")
         elif ws.plan is not None:
-            rc = lib.ipp_gp_lml_grad_batch(_lib.ptr(self._Xd), _lib.ptr(self._yd), n, _lib.ptr(ws.hyp), _lib.ptr(ws.K),
+            rc = lib.ipp_gp_lml_grad_batch(_lib.ptr(self._Xd_obj), _lib.ptr(self._yd_obj), n, _lib.ptr(ws.hyp), _lib.ptr(ws.K),
                                            _lib.ptr(ws.W), _lib.ptr(ws.T), _lib.ptr(ws.v), None, 1, 1 if with_grad else 0,
-                                           _lib.ptr(ws.plan), _lib.ptr(ws.sched), flags | (int(max_ctas) << 8), st)
+                                           _lib.ptr(ws.plan), _lib.ptr(ws.sched), flags | (int(max_ctas) << 8),
+                                           _lib.ptr(self._tile_bbox_d), st)
             _lib.check(rc, "ipp_gp_lml_grad_batch")
         else:
             rc = lib.ipp_gp_lml_grad(_lib.ptr(self._Xd), _lib.ptr(self._yd), n, _lib.ptr(ws.hyp), _lib.ptr(ws.K),
@@ -485,9 +502,10 @@ class GaussianProcessRegressor:
         ws.hyp.copy_(ws.hyp_host, non_blocking=True)
         ws.slot_ids.copy_(ws.slot_ids_host, non_blocking=True)
         flags = _chol_flags()
-        rc = lib.ipp_gp_lml_grad_batch(_lib.ptr(self._Xd), _lib.ptr(self._yd), n, _lib.ptr(ws.hyp), _lib.ptr(ws.K),
+        rc = lib.ipp_gp_lml_grad_batch(_lib.ptr(self._Xd_obj), _lib.ptr(self._yd_obj), n, _lib.ptr(ws.hyp), _lib.ptr(ws.K),
                                        _lib.ptr(ws.W), _lib.ptr(ws.T), _lib.ptr(ws.v), _lib.ptr(ws.slot_ids), R,
-                                       1 if with_grad else 0, _lib.ptr(ws.plan), _lib.ptr(ws.sched), flags, _lib.stream_ptr())
+                                       1 if with_grad else 0, _lib.ptr(ws.plan), _lib.ptr(ws.sched), flags,
+                                       _lib.ptr(self._tile_bbox_d), _lib.stream_ptr())
         _lib.check(rc, "ipp_gp_lml_grad_batch")
         off, vt, S = ws.layout[8], ws.layout[6], ws.slots
         torch.index_select(ws.v[: S * vt].view(S, vt)[:, off:off + 8], 0, ws.slot_ids[:R].long(), out=ws.res_dev.view(S, 8)[:R])
