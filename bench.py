@@ -676,8 +676,10 @@ def run_b200(args, wl, rank, world, local_rank):
         Xs, meas_s, _ = synth_observations(n, W, 0)
         wps = [Xs[i] for i in range(n)]
 
-        def strong_field(sharded):
+        def strong_field(sharded, fixed=False):
             f = PointSourceField(num_sources=3, workspace_size=(0, W, 0, W), seed=0)
+            if fixed:  # theta fixed: no fit, the call is factorisation (replicated) + lattice slabs + gather
+                f.gp = G.GaussianProcessRegressor(kernel=G.ConstantRBFKernel(*THETA), optimizer=None, normalize_y=True)
             if sharded:
                 f.gp.restart_group = True
                 f.grid_group = True
@@ -702,6 +704,17 @@ def run_b200(args, wl, rank, world, local_rank):
         strong_call(shard, 0)
         t_n, zn, sn = strong_call(shard, 1)
         same = bool(np.array_equal(z1, zn) and np.array_equal(s1, sn))
+        evals_1, evals_n = None, shard.gp.n_lml_evals_ // 2  # objective evaluations THIS rank ran per call (two calls made)
+        fx1, fxn = strong_field(False, fixed=True), strong_field(True, fixed=True)
+        for f_ in (fx1, fxn):
+            strong_call(f_, 0)
+        t_fx1 = min(strong_call(fx1, 0)[0] for _ in range(3))
+        t_fxn = min(strong_call(fxn, 0)[0] for _ in range(3))
+        ev_all = torch.tensor([float(evals_n)], dtype=torch.float64, device="cuda")
+        ev_max = ev_all.clone()
+        dist.all_reduce(ev_all, op=dist.ReduceOp.SUM)
+        dist.all_reduce(ev_max, op=dist.ReduceOp.MAX)
+        del fx1, fxn
         xy0, par0 = synth_tree(B, W, 0)  # the same tree and observations on every rank
         tree0 = TreeArrays(xy0[0], capacity=B + 1)
         for k in range(1, B + 1):
@@ -723,6 +736,13 @@ def run_b200(args, wl, rank, world, local_rank):
                   "n_gpus": world, "seconds": t_n, "seconds_1gpu_same_box": t_one, "speedup": t_one / t_n,
                   "efficiency": t_one / (world * t_n), "value": Gpts / t_n, "unit": UNIT,
                   "identical_to_1gpu": same,
+                  "objective_evaluations": {"all_ranks": float(ev_all.item()), "busiest_rank": float(ev_max.item()),
+                                            "note": "the 11 L-BFGS-B runs are the unit of work of the fit (run i on rank i mod N, "
+                                                    "in lockstep within a rank): its speed-up is bounded by all / busiest"},
+                  "fixed_theta": {"seconds": t_fxn, "seconds_1gpu_same_box": t_fx1, "speedup": t_fx1 / t_fxn,
+                                  "efficiency": t_fx1 / (world * t_fxn),
+                                  "call": "the same call with theta fixed: factorisation on every rank, the lattice by "
+                                          "work-balanced row slabs, one all_gather_into_tensor + pinned read-back"},
                   "branch_batch": {"ms": br_strong_ms, "branches": B, "identical_to_1gpu": bool(np.array_equal(info_s, info, equal_nan=True))}}
         del shard
     if sampler:

@@ -37,23 +37,6 @@ __device__ __forceinline__ unsigned long long global_ns() {
   return t;
 }
 
-__device__ __forceinline__ int ld_relaxed(const int* p) {
-  int v;
-  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ int ld_acquire(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release(int* p, int v) {
-  asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ void red_add_release(int* p, int v) {
-  asm volatile("red.release.gpu.global.add.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
-}
-
 // All dependency flags of a task at or above their thresholds?  The loads are relaxed and independent (in flight
 // together); the caller fences before the CTA touches the data they guard.
 __device__ __forceinline__ bool task_ready(const int* __restrict__ T, const int* flags) {

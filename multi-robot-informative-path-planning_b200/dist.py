@@ -123,13 +123,17 @@ def sharded_grid_posterior(gp, ws, nx: int, ny: int, group=None, compute_slab: O
     g0, g1 = bounds[rank]
     sizes = [b - a for a, b in bounds]
     m, n_loc = max(sizes), g1 - g0
-    if compute_slab is None:
+    if compute_slab is None and hasattr(gp, "_ws"):  # the device estimator: its kernel writes the send buffer itself
         send = torch.empty((2, m), dtype=torch.float64, device="cuda")
         mean = torch.empty(max(n_loc, 1), dtype=torch.float64, device="cuda")
         gp.predict_grid_device(ws[0], ws[1], nx, ws[2], ws[3], ny, g_begin=g0, g_end=g1, want_zpred=True,
                                out=(mean[:n_loc], send[1, :n_loc], send[0, :n_loc]))
-        pinned = (lambda numel: gp._ws.pinned("gather", numel)) if hasattr(gp, "_ws") else None
+        pinned = lambda numel: gp._ws.pinned("gather", numel)
     else:
+        if compute_slab is None:  # an estimator with the slab interface only (the CPU test double)
+            def compute_slab(a, b):
+                _, std_d, z_d = gp.predict_grid_device(ws[0], ws[1], nx, ws[2], ws[3], ny, g_begin=a, g_end=b, want_zpred=True)
+                return z_d, std_d
         z_loc, s_loc = compute_slab(g0, g1)
         send = torch.zeros((2, m), dtype=z_loc.dtype, device=z_loc.device)
         send[0, :n_loc] = z_loc
