@@ -43,6 +43,12 @@ int ipp_gp_layout(int n, long long* out_host);
 int ipp_gram_rbf(const double* X, int n, const double* Y, int m, double c, double l, double jitter, double* K,
                  long long ldk, void* stream);
 
+/* The same builder for the other stationary kernels scikit-learn offers for this slot: kind 0 = RBF, 1 = Matern
+ * nu = 1.5, 2 = Matern nu = 2.5 (sklearn kernels.py:1723-1735), each times the constant c.  The reference only ever
+ * builds C * RBF (point_source.py:86); fit and posterior are RBF-only. */
+int ipp_gram_kernel(int kind, const double* X, int n, const double* Y, int m, double c, double l, double jitter, double* K,
+                    long long ldk, void* stream);
+
 /* One log-marginal-likelihood (+ gradient w.r.t. log c, log l) evaluation.
  * X: n x 2, y: n (already normalised), hyp: DEVICE {c, l, jitter}.  On return the result block
  * in vbuf holds lml / gradient / info; Kbuf holds L (lower, row NP = z = L^-1 y), Wbuf = L^-1.

@@ -25,6 +25,7 @@ SIGNATURES = {
     "ipp_abi_version": [],
     "ipp_gp_layout": [_I, C.POINTER(_LL)],
     "ipp_gram_rbf": [_D, _I, _D, _I, _F, _F, _F, _D, _LL, _D],
+    "ipp_gram_kernel": [_I, _D, _I, _D, _I, _F, _F, _F, _D, _LL, _D],
     "ipp_gp_lml_grad": [_D, _D, _I, _D, _D, _D, _D, _D, _I, _I, _D],
     "ipp_gp_fit_final": [_D, _D, _I, _D, _D, _D, _D, _D, _D],
     "ipp_host_chol_plan": [_I, _I, C.POINTER(_I), _LL, C.POINTER(_LL)],

@@ -118,5 +118,18 @@ __device__ __forceinline__ double sqdist_nofma(double ax, double ay, double bx, 
 __device__ __forceinline__ double rbf_scaled(double ax, double ay, double bx, double by, double c) {
   return __dmul_rn(exp(__dmul_rn(-0.5, sqdist_nofma(ax, ay, bx, by))), c);
 }
+// Stationary kernels of the public Gram builder on pre-scaled coordinates.  kind 0: RBF (above); 1 / 2: Matern with
+// nu = 1.5 / 2.5 as sklearn evaluates them (kernels.py:1723-1735: r = cdist(X / l, Y / l), K = r * sqrt(3),
+// (1 + K) exp(-K);  K = r * sqrt(5), (1 + K + K^2 / 3) exp(-K)), times c.
+__device__ __forceinline__ double stationary_scaled(int kind, double ax, double ay, double bx, double by, double c) {
+  if (kind == 0) return rbf_scaled(ax, ay, bx, by, c);
+  const double r = sqrt(sqdist_nofma(ax, ay, bx, by));
+  if (kind == 1) {
+    const double k = __dmul_rn(r, 1.7320508075688772);
+    return __dmul_rn(__dmul_rn(__dadd_rn(1.0, k), exp(-k)), c);
+  }
+  const double k = __dmul_rn(r, 2.23606797749979);
+  return __dmul_rn(__dmul_rn(__dadd_rn(__dadd_rn(1.0, k), __ddiv_rn(__dmul_rn(k, k), 3.0)), exp(-k)), c);
+}
 
 }  // namespace ipp

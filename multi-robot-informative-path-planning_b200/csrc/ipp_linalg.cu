@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(256) gram_fit_kernel(const double* __restrict_
 // Public dense Gram (gp.kernel(X) / gp.kernel(X, Y): rrt.py:447,452).  out is n x m, ld >= m.
 __global__ void __launch_bounds__(256) gram_rbf_kernel(const double* __restrict__ X, int n, const double* __restrict__ Y,
                                                        int m, double c, double l, double jitter, int symmetric,
-                                                       double* __restrict__ out, long ld) {
+                                                       double* __restrict__ out, long ld, int kind) {
   __shared__ double sx[2][BLK], sy[2][BLK];
   const int i0 = blockIdx.y * BLK, j0 = blockIdx.x * BLK, t = threadIdx.x;
   if (t < 2 * BLK) {
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(256) gram_rbf_kernel(const double* __restrict_
     int r = e / BLK, cc = e % BLK;
     int gi = i0 + r, gj = j0 + cc;
     if (gi < n && gj < m) {
-      double v = (symmetric && gi == gj) ? __dadd_rn(c, jitter) : rbf_scaled(sx[0][r], sy[0][r], sx[1][cc], sy[1][cc], c);
+      double v = (symmetric && gi == gj) ? __dadd_rn(c, jitter) : stationary_scaled(kind, sx[0][r], sy[0][r], sx[1][cc], sy[1][cc], c);
       out[(long)gi * ld + gj] = v;
     }
   }
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(256) gram_rbf_kernel(const double* __restrict_
 // padded shared-memory transpose, its mirror image -- every global store a full 512-byte row segment,
 // streaming (evict-first) because the matrix is written once and is larger than L2 at n = 5000.
 __global__ void __launch_bounds__(256) gram_sym_kernel(const double* __restrict__ X, int n, double c, double l,
-                                                       double jitter, double* __restrict__ out, long ld) {
+                                                       double jitter, double* __restrict__ out, long ld, int kind) {
   __shared__ double sx[2][BLK], sy[2][BLK];
   __shared__ double tile[BLK][BLK + 1];
   const int b = blockIdx.x, t = threadIdx.x;
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(256) gram_sym_kernel(const double* __restrict_
 #pragma unroll 4
   for (int it = 0; it < BLK / 4; ++it) {
     const int r = rq + 4 * it, gi = i0 + r, gj = j0 + cc;
-    const double v = (gi == gj) ? __dadd_rn(c, jitter) : rbf_scaled(sx[0][r], sy[0][r], sx[1][cc], sy[1][cc], c);
+    const double v = (gi == gj) ? __dadd_rn(c, jitter) : stationary_scaled(kind, sx[0][r], sy[0][r], sx[1][cc], sy[1][cc], c);
     tile[r][cc] = v;
     if (gi < n && gj < n) __stcs(out + (long)gi * ld + gj, v);
   }
@@ -1245,7 +1245,12 @@ int ipp_gp_layout(int n, long long* out) {
 
 int ipp_gram_rbf(const double* X, int n, const double* Y, int m, double c, double l, double jitter, double* K,
                  long long ldk, void* stream) {
-  if (!X || n <= 0 || !K || !(l > 0.0)) return IPP_ERR_ARG;
+  return ipp_gram_kernel(0, X, n, Y, m, c, l, jitter, K, ldk, stream);
+}
+
+int ipp_gram_kernel(int kind, const double* X, int n, const double* Y, int m, double c, double l, double jitter, double* K,
+                    long long ldk, void* stream) {
+  if (kind < 0 || kind > 2 || !X || n <= 0 || !K || !(l > 0.0)) return IPP_ERR_ARG;
   const int symmetric = (Y == nullptr);
   if (symmetric) {
     Y = X;
@@ -1254,10 +1259,10 @@ int ipp_gram_rbf(const double* X, int n, const double* Y, int m, double c, doubl
   if (m <= 0 || ldk < m) return IPP_ERR_ARG;
   if (symmetric) {
     const long T = (n + BLK - 1) / BLK;
-    gram_sym_kernel<<<(unsigned)(T * (T + 1) / 2), 256, 0, (cudaStream_t)stream>>>(X, n, c, l, jitter, K, (long)ldk);
+    gram_sym_kernel<<<(unsigned)(T * (T + 1) / 2), 256, 0, (cudaStream_t)stream>>>(X, n, c, l, jitter, K, (long)ldk, kind);
   } else {
     dim3 grid((m + BLK - 1) / BLK, (n + BLK - 1) / BLK);
-    gram_rbf_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, n, Y, m, c, l, jitter, 0, K, (long)ldk);
+    gram_rbf_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, n, Y, m, c, l, jitter, 0, K, (long)ldk, kind);
   }
   IPP_LAUNCH_CHECK();
   return IPP_OK;

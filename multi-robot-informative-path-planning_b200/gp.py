@@ -26,7 +26,7 @@ from scipy.optimize import minimize
 
 from . import _lib
 
-__all__ = ["ConstantRBFKernel", "ConstantKernel", "RBF", "GaussianProcessRegressor"]
+__all__ = ["ConstantRBFKernel", "ConstantKernel", "RBF", "Matern", "GaussianProcessRegressor"]
 
 
 def _chol_flags():
@@ -85,10 +85,10 @@ class _Factor:
 
     def __mul__(self, other):
         if isinstance(self, ConstantKernel) and isinstance(other, RBF):
-            return ConstantRBFKernel(self.value, other.value, self.bounds, other.bounds)
+            return ConstantRBFKernel(self.value, other.value, self.bounds, other.bounds, nu=getattr(other, "nu", np.inf))
         if isinstance(self, RBF) and isinstance(other, ConstantKernel):
-            return ConstantRBFKernel(other.value, self.value, other.bounds, self.bounds)
-        raise TypeError("only ConstantKernel * RBF is on the accelerated path")
+            return ConstantRBFKernel(other.value, self.value, other.bounds, self.bounds, nu=getattr(self, "nu", np.inf))
+        raise TypeError("only ConstantKernel * RBF / Matern is on the accelerated path")
 
 
 class ConstantKernel(_Factor):
@@ -105,6 +105,18 @@ class RBF(_Factor):
         super().__init__(length_scale, length_scale_bounds)
 
 
+class Matern(RBF):
+    """sklearn.gaussian_process.kernels.Matern look-alike for nu in {1.5, 2.5, inf} (factor of the product only).
+    The kernel-matrix builder (`kernel(X[, Y])`, ipp_gram_kernel) covers it; the fit and the posterior are RBF-only,
+    like the reference (point_source.py:86 builds C * RBF and nothing else)."""
+
+    def __init__(self, length_scale=1.0, length_scale_bounds=(1e-5, 1e5), nu=1.5):
+        super().__init__(length_scale, length_scale_bounds)
+        if nu not in (1.5, 2.5, np.inf):
+            raise ValueError("Matern is implemented for nu = 1.5, 2.5 and inf (= RBF)")
+        self.nu = nu
+
+
 class ConstantRBFKernel:
     """``ConstantKernel(c, c_bounds) * RBF(l, l_bounds)`` -- the only kernel the reference builds
     (point_source.py:82-87).  theta = log([c, l]) (sklearn kernels.py:291-312)."""
@@ -113,11 +125,12 @@ class ConstantRBFKernel:
     n_dims = 2
 
     def __init__(self, constant_value=1.0, length_scale=1.0, constant_value_bounds=(1e-3, 50.0),
-                 length_scale_bounds=(1e-2, 50.0)):
+                 length_scale_bounds=(1e-2, 50.0), nu=np.inf):
         self.constant_value = float(constant_value)
         self.length_scale = float(length_scale)
         self.constant_value_bounds = constant_value_bounds
         self.length_scale_bounds = length_scale_bounds
+        self.nu = nu  # inf: RBF; 1.5 / 2.5: Matern (kernel-matrix builder only)
 
     # -- sklearn Kernel protocol -----------------------------------------------------------
     @property
@@ -136,13 +149,13 @@ class ConstantRBFKernel:
 
     def clone_with_theta(self, theta):
         k = ConstantRBFKernel(self.constant_value, self.length_scale, self.constant_value_bounds,
-                              self.length_scale_bounds)
+                              self.length_scale_bounds, nu=self.nu)
         k.theta = theta
         return k
 
     def clone(self):
         return ConstantRBFKernel(self.constant_value, self.length_scale, self.constant_value_bounds,
-                                 self.length_scale_bounds)
+                                 self.length_scale_bounds, nu=self.nu)
 
     def diag(self, X):
         return np.full(len(np.asarray(X)), self.constant_value, dtype=float)
@@ -156,7 +169,7 @@ class ConstantRBFKernel:
         if eval_gradient:
             raise NotImplementedError("the fused LML kernel never materialises dK; use "
                                       "GaussianProcessRegressor.log_marginal_likelihood")
-        return gram_device(X, Y, self.constant_value, self.length_scale).cpu().numpy()
+        return gram_device(X, Y, self.constant_value, self.length_scale, kind={np.inf: 0, 1.5: 1, 2.5: 2}[self.nu]).cpu().numpy()
 
     def __repr__(self):
         # same text sklearn prints for C(c) * RBF(l)
@@ -262,8 +275,8 @@ def as_lattice(Xq):
     return float(xs[0]), float(xs[-1]), nx, float(ys[0]), float(ys[-1]), ny
 
 
-def gram_device(X, Y, c, l, jitter=0.0):
-    """K(X, Y) as a device-resident torch tensor (n x m, fp64)."""
+def gram_device(X, Y, c, l, jitter=0.0, kind=0):
+    """K(X, Y) as a device-resident torch tensor (n x m, fp64).  kind 0: RBF, 1 / 2: Matern nu = 1.5 / 2.5."""
     torch = _lib.require_cuda()
     lib = _lib.load()
     Xd = torch.from_numpy(_as_points(X)).cuda()
@@ -275,8 +288,8 @@ def gram_device(X, Y, c, l, jitter=0.0):
         m = Yd.shape[0]
     out = torch.empty((n, m), dtype=torch.float64, device="cuda")
     if n and m:
-        _lib.check(lib.ipp_gram_rbf(_lib.ptr(Xd), n, _lib.ptr(Yd), m, float(c), float(l), float(jitter),
-                                    _lib.ptr(out), m, _lib.stream_ptr()), "ipp_gram_rbf")
+        _lib.check(lib.ipp_gram_kernel(int(kind), _lib.ptr(Xd), n, _lib.ptr(Yd), m, float(c), float(l), float(jitter),
+                                       _lib.ptr(out), m, _lib.stream_ptr()), "ipp_gram_kernel")
     return out
 
 
@@ -383,6 +396,9 @@ class GaussianProcessRegressor:
             kernel = ConstantRBFKernel(1.0, 1.0, "fixed", "fixed")
         if not isinstance(kernel, ConstantRBFKernel):
             raise TypeError("the B200 path implements ConstantKernel * RBF (point_source.py:86)")
+        if kernel.nu != np.inf:
+            raise NotImplementedError("Matern is available in the kernel-matrix builder (kernel(X[, Y])); the fit and the "
+                                      "posterior implement the reference's C * RBF")
         if np.iterable(alpha):
             raise TypeError("per-sample alpha is not used by the reference and is not implemented")
         self.kernel = kernel

@@ -240,3 +240,26 @@ def test_integration_patch_reference_call_sequence(G, gold):
     # gp.kernel(X[, Y]) as rrt.py:447,452 call it
     L = g["psf_X"][:7]
     assert np.abs(gp.kernel(L) - O.kernel(L, None, 1.0, 1.0)).max() <= 4e-16
+
+
+# ---------------------------------------------------------------------------------------------------
+# Kernel-matrix builder for the Matern family (north_star: "RBF / Matern kernel-matrix builder"): against
+# scikit-learn's own kernels (the reference's dependency; it only ever builds C * RBF itself)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nu", [1.5, 2.5, np.inf])
+def test_matern_gram_matches_sklearn(G, nu):
+    from sklearn.gaussian_process.kernels import ConstantKernel as SC
+    from sklearn.gaussian_process.kernels import Matern as SM
+
+    rng = np.random.RandomState(7)
+    A, B = rng.uniform(0, 30, (333, 2)), rng.uniform(0, 30, (70, 2))
+    A[5] = A[4]  # a duplicate: r = 0 off the diagonal
+    c, l = 2.3, 1.7
+    k = G.ConstantKernel(c, (1e-3, 50)) * G.Matern(l, (1e-2, 50), nu=nu)
+    ref = SC(c) * SM(length_scale=l, nu=nu)
+    Ks, Kc = k(A), k(A, B)
+    # sqrt / exp of CUDA vs glibc: a few ulp of the largest entry
+    assert np.abs(Ks - ref(A)).max() <= 8e-16 * c and np.abs(Kc - ref(A, B)).max() <= 8e-16 * c
+    assert np.array_equal(np.diag(Ks), np.full(len(A), c))
+    with pytest.raises(NotImplementedError):
+        G.GaussianProcessRegressor(kernel=k) if nu != np.inf else (_ for _ in ()).throw(NotImplementedError())
