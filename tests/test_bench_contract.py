@@ -26,10 +26,13 @@ def test_reference_arm_prints_the_contract_line():
 
 
 def test_committed_b200_line_has_the_contract_keys():
-    d = json.loads(open(os.path.join(ROOT, "profiles", "bench_c4_r01.json")).read().strip().splitlines()[-1])
+    d = json.loads(open(os.path.join(ROOT, "profiles", "bench_c4_r02.json")).read().strip().splitlines()[-1])
     assert BASE_KEYS | {"roofline", "clocks"} <= set(d)
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"])
     assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"])
     assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"])
     assert d["gpu_launches"] > 0 and d["n_gpus"] == 1 and d["dtype"] == "f64"
     assert abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-12
+    # the end-to-end number is the STOCK call (11-restart fit included), with the fixed-theta figure as a sub-key
+    assert "STOCK" in d["e2e"]["call"] and d["e2e"]["lml_evals_per_call"] > 100 and d["e2e"]["fixed_theta"]["value"] > d["e2e"]["value"]
+    assert d["value_at_theta_star"] > 0 and d["value_dense"] > 0 and d["fit"]["batch_of_11"]["frac_of_fp64_peak"] > 0.5
