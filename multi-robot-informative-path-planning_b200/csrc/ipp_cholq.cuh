@@ -55,8 +55,9 @@ __device__ __forceinline__ bool task_ready(const int* __restrict__ T, const int*
 }
 
 // F task: D = A(k, k); D -= P P^T with P = A(k, [k - width, k)) (the panels the bulk leaves to this block); factor.
-template <int NT>
-__device__ __forceinline__ void cholq_factor(double* __restrict__ A, long ld, int k, int width, double* psm, double* info) {
+template <int NT, class Sync = CtaSync>
+__device__ __forceinline__ void cholq_factor(double* __restrict__ A, long ld, int k, int width, double* psm, double* info,
+                                             Sync sync = Sync()) {
   double* D = psm;
   double* P = psm + BLK * PSTR;
   const int t = threadIdx.x, j0 = BLK * k, p0 = BLK * (k - width), pw = BLK * width;
@@ -82,7 +83,7 @@ __device__ __forceinline__ void cholq_factor(double* __restrict__ A, long ld, in
     }
   }
   cp_async_wait<0>();
-  __syncthreads();
+  sync();
   if (width > 0) {  // lower part of D -= P P^T on the DMMA pipe: each warp owns 64 / (NT / 32) rows
     constexpr int RPW = BLK / (NT / 32), MT = RPW / 8;
     const int warp = t >> 5, lane = t & 31, g = lane >> 2, tg = lane & 3;
@@ -114,15 +115,15 @@ __device__ __forceinline__ void cholq_factor(double* __restrict__ A, long ld, in
           const int r = warp * RPW + mi * 8 + g, cc = ni * 8 + tg * 2 + e;
           if (cc <= r) D[r * PSTR + cc] -= acc[mi][ni][e];
         }
-    __syncthreads();
+    sync();
   }
-  potf2_block<NT>(D, t, j0, info);
+  potf2_block<NT, Sync>(D, t, j0, info, sync);
   for (int e = t; e < BLK * BLK / 2; e += NT) {
     const int r = e / (BLK / 2), cc = (e % (BLK / 2)) * 2;
     *reinterpret_cast<double2*>(A + (long)(j0 + r) * ld + j0 + cc) =
         make_double2(cc <= r ? D[r * PSTR + cc] : 0.0, cc + 1 <= r ? D[r * PSTR + cc + 1] : 0.0);
   }
-  __syncthreads();
+  sync();
 }
 
 // S task: rows [64 i0, 64 (i0 + nblk)) of block column k:  X <- (X - Pa Pb^T) L_kk^-T, where Pa = A(rows, panel k-1),
@@ -136,8 +137,9 @@ template <int SOLVE_ROWS>
 constexpr size_t solve_smem() {  // X, Pa, Pb, L_kk (+ reciprocal pivots)
   return sizeof(double) * ((SOLVE_ROWS + SOLVE_ROWS + BLK + BLK) * QSTR + BLK);
 }
-template <int NT, int SOLVE_ROWS>
-__device__ __forceinline__ void cholq_solve(double* __restrict__ A, long ld, int k, int i0, int nblk, int width, double* psm) {
+template <int NT, int SOLVE_ROWS, class Sync = CtaSync>
+__device__ __forceinline__ void cholq_solve(double* __restrict__ A, long ld, int k, int i0, int nblk, int width, double* psm,
+                                            Sync sync = Sync()) {
   const int rows = BLK * nblk, t = threadIdx.x, warp = t >> 5, lane = t & 31, g = lane >> 2, tg = lane & 3;
   double* Xs = psm;                          // rows x 64, pitch QSTR
   double* Pa = psm + SOLVE_ROWS * QSTR;      // rows x 64 (own update)
@@ -161,7 +163,7 @@ __device__ __forceinline__ void cholq_solve(double* __restrict__ A, long ld, int
   cp_async_commit();
   if (t < BLK) rinv[t] = 1.0 / __ldcg(A + (long)(j0 + t) * ld + j0 + t);
   cp_async_wait<1>();  // X and the own-update operands have landed; L_kk may still be on its way
-  __syncthreads();
+  sync();
   constexpr int NW = NT / 32;
   if (width > 0) {  // Xs -= Pa Pb^T: warp w owns rows [w * rows / NW, ...) in 8-row groups, all 64 columns
     const int rpw = rows / NW;
@@ -185,7 +187,7 @@ __device__ __forceinline__ void cholq_solve(double* __restrict__ A, long ld, int
     }
   }
   cp_async_wait<0>();
-  __syncthreads();
+  sync();
   for (int c = 0; c < 8; ++c) {
     if (t < rows) {  // one thread per row: the 8 x 8 triangle of group c
       double x[8];
@@ -201,7 +203,7 @@ __device__ __forceinline__ void cholq_solve(double* __restrict__ A, long ld, int
 #pragma unroll
       for (int j = 0; j < 8; ++j) xr[j] = x[j];
     }
-    __syncthreads();
+    sync();
     if (c < 7) {  // columns right of the group: Xs[:, n] -= X[:, group c] L[n, group c]^T
       const int rpw = rows / NW, ntile = 7 - c;
       for (int m0 = 0; m0 < rpw; m0 += 8) {
@@ -229,14 +231,14 @@ __device__ __forceinline__ void cholq_solve(double* __restrict__ A, long ld, int
           if (ni < ntile)
             *reinterpret_cast<double2*>(Xs + rr * QSTR + 8 * (c + 1 + ni) + tg * 2) = make_double2(acc[ni][0], acc[ni][1]);
       }
-      __syncthreads();
+      sync();
     }
   }
   for (int e = t; e < rows * (BLK / 2); e += NT) {
     const int r = e / (BLK / 2), cc = (e % (BLK / 2)) * 2;
     *reinterpret_cast<double2*>(A + (long)(r0 + r) * ld + j0 + cc) = *reinterpret_cast<const double2*>(Xs + r * QSTR + cc);
   }
-  __syncthreads();
+  sync();
 }
 
 // U task: tile (row0, col0) -= A(rows, [kb, ke)) A(cols, [kb, ke))^T over the lower part, columns >= cmin, except the

@@ -201,8 +201,8 @@ constexpr size_t PANEL_SMEM = sizeof(double) * (BLK * PSTR + BLK * QSTR + BLK); 
 // multipliers travel by shuffle, no barrier inside a panel), then the whole CTA applies the rank-8 update.
 // 16 CTA barriers per block instead of 192; every entry sees the same operations in the same order as the
 // textbook right-looking column sweep.
-template <int NT>
-__device__ __forceinline__ void potf2_block(double* D, int t, int first_index, double* info) {
+template <int NT, class Sync = CtaSync>
+__device__ __forceinline__ void potf2_block(double* D, int t, int first_index, double* info, Sync sync = Sync()) {
   const int lane = t & 31, warp = t >> 5;
   for (int jb = 0; jb < BLK; jb += 8) {
     if (warp == 0) {
@@ -238,7 +238,7 @@ __device__ __forceinline__ void potf2_block(double* D, int t, int first_index, d
         if (has1) D[r1 * PSTR + jb + c] = a1[c];
       }
     }
-    __syncthreads();
+    sync();
     // rank-8 update of the trailing lower triangle in 4x4 register tiles (16 independent FMA chains per thread,
     // 5 shared loads per 8 FMAs instead of 17); every entry still sees its 8 subtractions in column order
     for (int blk = t; blk < (BLK / 4) * (BLK / 4); blk += NT) {
@@ -272,7 +272,7 @@ __device__ __forceinline__ void potf2_block(double* D, int t, int first_index, d
           for (int j = 0; j < 4; ++j) D[(r0 + i) * PSTR + c0 + j] = d[i][j];
       }
     }
-    __syncthreads();
+    sync();
   }
 }
 

@@ -263,3 +263,49 @@ def test_matern_gram_matches_sklearn(G, nu):
     assert np.array_equal(np.diag(Ks), np.full(len(A), c))
     with pytest.raises(NotImplementedError):
         G.GaussianProcessRegressor(kernel=k) if nu != np.inf else (_ for _ in ()).throw(NotImplementedError())
+
+
+# ---------------------------------------------------------------------------------------------------
+# (f) row 2: main.py reduces the device-resident posterior with ipp_grid_metrics when nothing is saved or shown
+# ---------------------------------------------------------------------------------------------------
+def test_main_uses_device_metrics(monkeypatch):
+    """The CLI flow (main.py:96-140 of the reference) with save = show = False: the strategies hand back DeviceField
+    handles, the three metrics come from ONE fused device pass, and they equal the reference's numpy expressions on
+    the read-back fields of the same run (1e-12 relative: fixed-order fp64 reductions vs numpy's pairwise sums)."""
+    import copy
+    import json
+    import os
+
+    from mripp_b200 import main as M
+    from mripp_b200.src.point_source.point_source import DeviceField
+    from mripp_b200.src.visualization import plot_helper as PH
+
+    cfg = json.load(open(os.path.join(os.path.dirname(__file__), "..", "config", "small_example_setup.json")))
+    cfg["strategies"] = ["MultiAgentBoustrophedon"]
+    cfg["args"].update(budget=60, rounds=1)
+    calls = []
+    real = PH.field_metrics_device
+
+    def spy(z, s, t):
+        out = real(z, s, t)
+        # the reference's expressions (main.py:113-116, plot_helper.py:383-398) on the same fields, read back
+        zp, sd, zt = (x.detach().cpu().numpy() for x in (z, s, t))
+        err = np.log10(zt + 1) - np.log10(zp + 1)
+        calls.append((out, (np.sqrt(np.mean(err ** 2)), np.sqrt(np.sum(zt * err ** 2) / np.sum(zt)),
+                            PH.calculate_differential_entropy(sd.ravel()))))
+        return out
+
+    monkeypatch.setattr(M, "field_metrics_device", spy)
+    a = types.SimpleNamespace(sweep=False, debug=False, out=None, shard_rounds=False)
+    res = M.run(a, copy.deepcopy(cfg))
+    assert len(res) == 1 and len(calls) == 1, "main did not take the device-metrics path"
+    got, want = calls[0]
+    np.testing.assert_allclose(np.array(got, dtype=float), np.array(want, dtype=float), rtol=1e-10)
+    assert res[0]["rmse"] == pytest.approx(want[0], rel=1e-10)
+    # with save = True the same flow hands numpy arrays to the host metrics
+    sc = M.initialize_scenarios(copy.deepcopy(cfg))[0]
+    assert sc.device_outputs is True
+    cfg2 = copy.deepcopy(cfg)
+    cfg2["args"]["show"] = True
+    assert not getattr(M.initialize_scenarios(cfg2)[0], "device_outputs", False)
+    assert DeviceField is not None
