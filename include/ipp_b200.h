@@ -84,6 +84,8 @@ int ipp_chol_sched_ints(int n, int R, long long* out_host);
  * not depend on R or on the slot.  plan: DEVICE copy of ipp_host_chol_plan; sched: ipp_chol_sched_ints(n, R) ints.
  * flags: bit 0 = do not hand the critical chain over by hints (measurement aid); bit 1 / bit 2 = leave per-CTA task /
  * cycle counters / a per-task trace at the end of sched; bit 3 = advance the ready frontiers after every chain task;
+ * bit 4 = the executor without warp specialisation (every warp claims, copies and multiplies in turn: A/B aid);
+ * bit 5 = tile updates written back by load / subtract / store instead of RED.ADD.F64 (A/B aid; same bits);
  * bits 8.. = cap on the CTAs of the factorisation kernel (0: whole GPU).  info = -7777 in the result block: the kernel's watchdog fired.
  * tile_bbox (nullable): {xmin, xmax, ymin, ymax} (unscaled) of every block of T consecutive observations in the order
  * given (T = 64 for NP <= 1536, else 128; NP / T boxes).  When present the gradient contraction skips tile pairs

@@ -25,6 +25,7 @@ struct CholQ {
   int stats;          // != 0: every CTA leaves {tasks F/S/U, cycles F/S/U, cycles acquiring, cycles total} after the abort word
   int use_mb;         // tile updates on the mbarrier pipeline (gemm_mainloop_mb) instead of a CTA barrier per k-slab
   int eager_scan;     // advance the frontiers after every chain task, even if a chain task is claimable (A/B aid)
+  int red_epilogue;   // tile updates written back as RED.ADD.F64 instead of load / subtract / store
 };
 constexpr int QSTATS = 16;       // ints per CTA
 constexpr int QSTATS_CTAS = 512;
@@ -241,27 +242,11 @@ __device__ __forceinline__ void cholq_solve(double* __restrict__ A, long ld, int
   sync();
 }
 
-// U task: tile (row0, col0) -= A(rows, [kb, ke)) A(cols, [kb, ke))^T over the lower part, columns >= cmin, except the
-// diagonal block `skip` (block index; that one is its F task's own).
+// C(tile) -= acc over the lower part, columns >= cmin, except the diagonal block `skip`: the loads of half the tile are
+// issued before the first dependent store, so the read-modify-write costs two L2 round trips, not one per element.
 template <class C>
-__device__ __forceinline__ void cholq_update_tile(double* __restrict__ A, long ld, int rows_total, int np, int row0, int col0,
-                                                  int kb, int ke, int cmin, int skip, double* smem, uint64_t* bars) {
-  {  // start pulling the C tile into L2 (see chol_syrk_tile)
-    constexpr int LINES_PER_ROW = C::BN * 8 / 128;
-    for (int e = threadIdx.x; e < C::BM * LINES_PER_ROW; e += C::THREADS) {
-      const int gr = row0 + e / LINES_PER_ROW, gc = col0 + (e % LINES_PER_ROW) * 16;
-      if (gr < rows_total && gc < np && gc >= cmin && (gc >> 6) <= (gr >> 6))
-        asm volatile("prefetch.global.L2 [%0];\n" ::"l"(A + (long)gr * ld + gc));
-    }
-  }
-  double acc[C::MI][C::NI][2];
-  zero_acc<C>(acc);
-  auto fillA = [&](double* s, int k0) { load_tile_async<C::BM, Lay::KCONT, C::THREADS>(s, A, ld, row0, k0, rows_total, ke); };
-  auto fillB = [&](double* s, int k0) { load_tile_async<C::BN, Lay::KCONT, C::THREADS>(s, A, ld, col0, k0, np, ke); };
-  if (bars)
-    gemm_mainloop_mb<C, Lay::KCONT, Lay::KCONT>(acc, smem, bars, kb, ke, fillA, fillB);
-  else
-    gemm_mainloop<C, Lay::KCONT, Lay::KCONT>(acc, smem, kb, ke, fillA, fillB);
+__device__ __forceinline__ void cholq_tile_epilogue(double* __restrict__ A, long ld, int rows_total, int np, int row0, int col0,
+                                                    int cmin, int skip, double (&acc)[C::MI][C::NI][2]) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wm = warp / C::WARPS_N, wn = warp % C::WARPS_N, g = lane >> 2, tg = lane & 3;
   constexpr int HALF = C::MI >= 8 ? C::MI / 4 : (C::MI / 2 > 0 ? C::MI / 2 : 1);
@@ -288,6 +273,52 @@ __device__ __forceinline__ void cholq_update_tile(double* __restrict__ A, long l
               make_double2(cv[mi][ni].x - acc[h0 + mi][ni][0], cv[mi][ni].y - acc[h0 + mi][ni][1]);
       }
   }
+}
+
+// The same update as fire-and-forget reductions (RED.ADD.F64 at the L2): C + (-acc) rounds exactly like C - acc, every
+// element is touched by one task at a time (the flags serialise the updates of a tile), so the result is the same bits
+// -- without the load -> subtract -> store round trips of the read-modify-write.
+template <class C>
+__device__ __forceinline__ void cholq_tile_epilogue_red(double* __restrict__ A, long ld, int rows_total, int np, int row0,
+                                                        int col0, int cmin, int skip, double (&acc)[C::MI][C::NI][2]) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wm = warp / C::WARPS_N, wn = warp % C::WARPS_N, g = lane >> 2, tg = lane & 3;
+#pragma unroll
+  for (int mi = 0; mi < C::MI; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < C::NI; ++ni) {
+      const int gr = row0 + wm * C::WTM + mi * 8 + g, gc = col0 + wn * C::WTN + ni * 8 + tg * 2;
+      const int br = gr >> 6, bc = gc >> 6;
+      if (gr < rows_total && gc < np && gc >= cmin && bc <= br && !(br == skip && bc == skip)) {
+        double* p = A + (long)gr * ld + gc;
+        asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;\n" ::"l"(p), "d"(-acc[mi][ni][0]) : "memory");
+        asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;\n" ::"l"(p + 1), "d"(-acc[mi][ni][1]) : "memory");
+      }
+    }
+}
+
+// U task: tile (row0, col0) -= A(rows, [kb, ke)) A(cols, [kb, ke))^T over the lower part, columns >= cmin, except the
+// diagonal block `skip` (block index; that one is its F task's own).
+template <class C>
+__device__ __forceinline__ void cholq_update_tile(double* __restrict__ A, long ld, int rows_total, int np, int row0, int col0,
+                                                  int kb, int ke, int cmin, int skip, double* smem, uint64_t* bars) {
+  {  // start pulling the C tile into L2 (see chol_syrk_tile)
+    constexpr int LINES_PER_ROW = C::BN * 8 / 128;
+    for (int e = threadIdx.x; e < C::BM * LINES_PER_ROW; e += C::THREADS) {
+      const int gr = row0 + e / LINES_PER_ROW, gc = col0 + (e % LINES_PER_ROW) * 16;
+      if (gr < rows_total && gc < np && gc >= cmin && (gc >> 6) <= (gr >> 6))
+        asm volatile("prefetch.global.L2 [%0];\n" ::"l"(A + (long)gr * ld + gc));
+    }
+  }
+  double acc[C::MI][C::NI][2];
+  zero_acc<C>(acc);
+  auto fillA = [&](double* s, int k0) { load_tile_async<C::BM, Lay::KCONT, C::THREADS>(s, A, ld, row0, k0, rows_total, ke); };
+  auto fillB = [&](double* s, int k0) { load_tile_async<C::BN, Lay::KCONT, C::THREADS>(s, A, ld, col0, k0, np, ke); };
+  if (bars)
+    gemm_mainloop_mb<C, Lay::KCONT, Lay::KCONT>(acc, smem, bars, kb, ke, fillA, fillB);
+  else
+    gemm_mainloop<C, Lay::KCONT, Lay::KCONT>(acc, smem, kb, ke, fillA, fillB);
+  cholq_tile_epilogue<C>(A, ld, rows_total, np, row0, col0, cmin, skip, acc);
   __syncthreads();
 }
 
@@ -582,5 +613,428 @@ __global__ void __launch_bounds__(C::THREADS, 1) chol_queue_kernel(CholQ a) {
     for (int i = 0; i < 4; ++i) o[3 + i] = (int)(st_cyc[i] >> 6);  // units of 64 cycles
     o[7] = (int)((clock64() - st_t0) >> 6);
     o[8] = st_polls;
+  }
+}
+
+// =====================================================================================================================
+// Warp-specialised executor of the same plan and the same claiming rules.  In chol_queue_kernel every warp does
+// everything in turn: claim (two round trips to L2), fill the pipeline, multiply, read-modify-write the tile -- a
+// rank-256 tile update takes 45 us of which 33.4 us are DMMA issue.  Here a CTA has twelve warps:
+//   warps 0..7   DMMA warps (224 registers): execute the tasks; for a tile update they only wait on "full" barriers,
+//                multiply out of shared memory and release stages on "empty" barriers;
+//   warps 9..11  copy warps: issue every cp.async of a tile update into a 4-stage ring that is numbered globally
+//                ACROSS tasks, so the first slabs of the next tile land while the DMMA warps are still in the last
+//                slabs and the read-modify-write of the current one;
+//   warp 8       scheduler: claims the next task while the current one runs.  It is released for task n when the copy
+//                warps have issued the last slab of task n - 1 (named barrier A: the DMMA warps are then <= 4 slabs +
+//                epilogue from the end), and hands the task over through a two-slot mailbox (mbarrier for the DMMA
+//                warps, named barrier B for the copy warps).
+// Rules that keep the critical chain as fast as before: a chain-class task (F, S, front tile) is never claimed while
+// the DMMA warps are busy (another CTA may be free for it right now; this CTA takes it, if it is still there, the
+// moment its own tile is done), and after an F or S task -- which use the ring's shared memory as scratch and hand
+// their successor to the same CTA -- the next claim waits for the task to finish, as in chol_queue_kernel.
+// Every wait is bounded (trap) or under the scheduler's watchdog: a protocol bug ends the kernel, it cannot hang it.
+constexpr int WS_STAGES = 4;
+constexpr int WS_LOADERS = 96;
+template <class C>
+__host__ __device__ constexpr size_t cholq_ws_ring_bytes() {
+  return sizeof(double) * WS_STAGES * stage_doubles<C, Lay::KCONT, Lay::KCONT>();
+}
+__device__ __forceinline__ void ws_pair_sync() { asm volatile("bar.sync 2, 128;\n" ::: "memory"); }  // warps 8..11
+__device__ __forceinline__ void ws_wait_done(volatile int* s_done, int need) {
+  for (unsigned spin = 0; *s_done < need; ++spin) {
+    __nanosleep(40);
+    if (spin > (1u << 27)) __trap();
+  }
+}
+
+template <class C>
+__global__ void __launch_bounds__(C::THREADS + 128, 1) chol_queue_ws_kernel(CholQ a) {
+  static_assert(C::THREADS == 256 && C::BM == 128 && C::BN == 128, "eight DMMA warps on 128 x 128 tiles");
+  extern __shared__ __align__(16) double smem[];
+  // mailbox: {queue (0 F, 1 S, 2 C, 3 U; < 0: stop), task index, problem, type, A..F of the task record, slot, OUT, OUTVAL, OUT2}
+  __shared__ int s_task[2][16];
+  __shared__ int s_cnt[2];  // DMMA warps that have finished the tile update in mailbox slot n & 1
+  __shared__ __align__(8) uint64_t bar_full[WS_STAGES], bar_empty[WS_STAGES], bar_task[2];
+  __shared__ volatile int s_done;  // tasks this CTA has finished and published
+  constexpr int SD = stage_doubles<C, Lay::KCONT, Lay::KCONT>();
+  constexpr int AOFF = tile_doubles<C::BM, Lay::KCONT>();
+  const int* __restrict__ plan = a.plan;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int nflags = __ldg(plan + PH_NFLAGS);
+  const int R = a.R, nq = NQ * R;
+  int* qstate = a.sched + (long)R * nflags;
+  int* abortf = qstate + QSTATE * R + 1;
+  if (t == 0) {
+    for (int s = 0; s < WS_STAGES; ++s) {
+      mbar_init(&bar_full[s], WS_LOADERS);        // one cp.async-completion arrival per copy thread
+      mbar_init(&bar_empty[s], C::THREADS / 32);  // one arrival per DMMA warp
+    }
+    mbar_init(&bar_task[0], 1);
+    mbar_init(&bar_task[1], 1);
+    s_done = 0;
+    s_cnt[0] = s_cnt[1] = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp >= C::THREADS / 32) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;\n");
+    if (warp == C::THREADS / 32) {
+      // ------------------------------------------------------------------------------------------ scheduler warp
+      const QueueView qv = {plan, a.sched, qstate, nflags, R};
+      const int rot = blockIdx.x % R;
+      int* n_idle = abortf + 1;  // CTAs polling with nothing to run
+      int hint_q = -1, hint_i = 0, hint_r = 0;
+      int held_q = -1, held_i = 0, held_r = 0;
+      int scan_r = -1, idle_r = rot;
+      int pend_scan = -1, pend_scan2 = -1, pend_hq = -1, pend_hi = 0, pend_hr = 0;  // what the tasks in flight enable once done
+      int scan_r2 = -1;
+      bool pend = false;
+      int n = 0, prev_q = -1;
+      for (;;) {
+        ws_pair_sync();  // (A) the copy warps have issued everything of task n - 1
+        // mailbox slot n & 1 was task n - 2's; after a chain task also wait for the task itself
+        ws_wait_done(&s_done, (prev_q >= 0 && prev_q != 3) ? n : n - 1);
+        int got_q = -1, got_i = 0, got_r = 0;
+        unsigned backoff = 0;
+        long long idle_since = 0;
+        bool idle = false, counted_idle = false;
+        for (;;) {
+          const bool ahead = __shfl_sync(0xffffffffu, (int)s_done, 0) < n;  // the DMMA warps are still in task n - 1
+          if (!ahead && pend) {
+            pend = false;
+            scan_r = pend_scan;
+            scan_r2 = pend_scan2;
+            hint_q = pend_hq;
+            hint_i = pend_hi;
+            hint_r = pend_hr;
+          }
+          int special = 0;
+          if (lane == 6 && hint_q >= 0) {
+            const int* T = plan + __ldg(plan + PH_OFFF + hint_q) + hint_i * PLAN_TS;
+            const int h = ld_relaxed(qstate + QSTATE * hint_r + 2 * hint_q);
+            special = (task_ready(T, a.sched + (long)hint_r * nflags) && h == hint_i) ? 1 : 0;
+          }
+          if (lane == 7 && held_q >= 0)
+            special = task_ready(plan + __ldg(plan + PH_OFFF + held_q) + held_i * PLAN_TS, a.sched + (long)held_r * nflags) ? 1 : 0;
+          int best = 0x7fffffff, best_rdy = 0, best_h = 0;
+          int bulk = 0x7fffffff, bulk_rdy = 0, bulk_h = 0;  // the same among the bulk queues only
+          bool exhausted = held_q < 0;
+          if (lane >= 8)
+            for (int c = lane - 8; c < nq; c += 24) {
+              const int q = c / R, r = (c % R + rot) % R;
+              const int* st = qstate + QSTATE * r + 2 * q;
+              const int h = ld_relaxed(st), f = ld_relaxed(st + 1);
+              if (h < __ldg(plan + PH_NF + q)) exhausted = false;
+              if (h < f && c < best) {
+                best = c;
+                best_rdy = f;
+                best_h = h;
+              }
+              if (h < f && q == NQ - 1 && c < bulk) {
+                bulk = c;
+                bulk_rdy = f;
+                bulk_h = h;
+              }
+            }
+          const int others_idle = ahead ? __shfl_sync(0xffffffffu, lane == 0 ? ld_relaxed(n_idle) : 0, 0) : 0;
+          const int hint_ok = __shfl_sync(0xffffffffu, special, 6), held_ok = __shfl_sync(0xffffffffu, special, 7);
+          int win = best;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) win = min(win, __shfl_xor_sync(0xffffffffu, win, o));
+          // This CTA is still busy: a chain-class task is claimed ahead only if no CTA is idle (an idle one starts it
+          // now, this one in up to 13 us); otherwise look at the bulk queues alone.
+          if (ahead && win != 0x7fffffff && win / R < NQ - 1 && others_idle > 0) {
+            win = bulk;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) win = min(win, __shfl_xor_sync(0xffffffffu, win, o));
+            best_rdy = bulk_rdy;
+            best_h = bulk_h;
+          }
+          const bool all_exhausted = __all_sync(0xffffffffu, exhausted);
+          if (held_q >= 0 && held_ok && (!ahead || held_q == NQ - 1 || others_idle == 0)) {
+            got_q = held_q;
+            got_i = held_i;
+            got_r = held_r;
+            held_q = -1;
+            break;
+          }
+          if (hint_q >= 0) {  // only set once the task it follows is done
+            const int hq = hint_q;
+            hint_q = -1;
+            int ok = 0;
+            if (hint_ok) {
+              if (lane == 0) {
+                int* hp = qstate + QSTATE * hint_r + 2 * hq;
+                ok = (atomicCAS(hp, hint_i, hint_i + 1) == hint_i);
+                if (ok) atomicMax(hp + 1, hint_i + 1);
+              }
+              ok = __shfl_sync(0xffffffffu, ok, 0);
+            }
+            if (ok) {
+              got_q = hq;
+              got_i = hint_i;
+              got_r = hint_r;
+              break;
+            }
+          }
+          if (scan_r >= 0 && (a.eager_scan || !(win != 0x7fffffff && win / R < NQ - 1))) {
+            const int sr = scan_r;
+            scan_r = scan_r2;
+            scan_r2 = -1;
+            if (scan_frontiers(qv, sr, lane)) continue;
+          }
+          if (win != 0x7fffffff) {
+            const int q = win / R, r = (win % R + rot) % R;
+            const int owner = 8 + win % 24;
+            int h = 0, ok = 0;
+            if (lane == owner) {
+              int* hp = qstate + QSTATE * r + 2 * q;
+              if (held_q < 0) {
+                h = atomicAdd(hp, 1);
+                ok = h < __ldg(plan + PH_NF + q) ? (h < best_rdy ? 1 : 2) : 0;
+                if (ok == 2 && task_ready(plan + __ldg(plan + PH_OFFF + q) + h * PLAN_TS, a.sched + (long)r * nflags)) ok = 1;
+              } else {
+                h = best_h;
+                ok = (atomicCAS(hp, best_h, best_h + 1) == best_h) ? 1 : 0;
+              }
+            }
+            ok = __shfl_sync(0xffffffffu, ok, owner);
+            h = __shfl_sync(0xffffffffu, h, owner);
+            if (ok == 1) {
+              got_q = q;
+              got_i = h;
+              got_r = r;
+              break;
+            }
+            if (ok == 2) {
+              held_q = q;
+              held_i = h;
+              held_r = r;
+            }
+            continue;
+          }
+          if (all_exhausted) {
+            got_q = -1;
+            break;
+          }
+          bool moved = false;
+          for (int k = 0; k < R && !moved; ++k) {
+            moved = scan_frontiers(qv, idle_r, lane);
+            idle_r = (idle_r + 1) % R;
+          }
+          if (moved) continue;
+          if (!ahead && !counted_idle) {  // nothing to claim and nothing running here: this CTA is idle
+            counted_idle = true;
+            if (lane == 0) atomicAdd(n_idle, 1);
+          }
+          int stop = 0;
+          if (lane == 0) {
+            const long long now = clock64();
+            if (!idle || ahead) {  // the watchdog counts polling with nothing running on this CTA
+              idle = true;
+              idle_since = now;
+            }
+            if (now - idle_since > a.timeout) atomicExch(abortf, 1);
+            stop = ld_relaxed(abortf);
+          }
+          stop = __shfl_sync(0xffffffffu, stop, 0);
+          if (stop) {
+            got_q = -2;
+            break;
+          }
+          backoff = backoff < 512 ? backoff + 64 : 512;
+          __nanosleep(backoff);
+        }
+        if (counted_idle && lane == 0) atomicSub(n_idle, 1);
+        // what this task enables, applied when it is done: its problem's frontiers (chain task, or a tile close
+        // behind the front) and the successor on the critical chain
+        if (got_q >= 0) {
+          const int* T = plan + __ldg(plan + PH_OFFF + got_q) + got_i * PLAN_TS;
+          const int type = __ldg(T + TK_TYPE), g = __ldg(T + TK_G);
+          pend_scan2 = pend ? pend_scan : -1;  // task n - 1 is still running: its scan waits with this one's
+          pend = true;
+          pend_scan = (got_q != 3 || __ldg(T + TK_B) * (C::BM / BLK) - __ldg(T + TK_D) <= 6) ? got_r : -1;
+          if (pend_scan < 0) {
+            pend_scan = pend_scan2;
+            pend_scan2 = -1;
+          }
+          pend_hq = -1;
+          if (a.use_hints && g >= 0 && (type == PT_F || type == PT_S)) {
+            pend_hq = type == PT_F ? 1 : 0;
+            pend_hi = g;
+            pend_hr = got_r;
+          }
+        }
+        if (lane == 0) {
+          int* m = s_task[n & 1];
+          m[0] = got_q;
+          m[1] = got_i;
+          m[2] = got_r;
+          if (got_q >= 0) {  // the task record, so that nobody else has to go to the plan for it
+            const int* T = plan + __ldg(plan + PH_OFFF + got_q) + got_i * PLAN_TS;
+            int f[10];
+#pragma unroll
+            for (int k = 0; k < 7; ++k) f[k] = __ldg(T + TK_TYPE + k);
+            f[7] = __ldg(T + TK_OUT);
+            f[8] = __ldg(T + TK_OUTVAL);
+            f[9] = __ldg(T + TK_OUT2);
+#pragma unroll
+            for (int k = 0; k < 7; ++k) m[3 + k] = f[k];
+            m[10] = a.slots ? __ldg(a.slots + got_r) : got_r;
+            m[11] = f[7];
+            m[12] = f[8];
+            m[13] = f[9];
+          }
+        }
+        __threadfence();  // acquire side of the relaxed flag loads, before this CTA touches the data they guard
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_task[n & 1]);
+        ws_pair_sync();  // (B) mailbox n & 1 is valid for the copy warps
+        if (got_q < 0) break;
+        prev_q = got_q;
+        ++n;
+      }
+    } else {
+      // ------------------------------------------------------------------------------------------ copy warps
+      const int lt = t - (C::THREADS + 32);  // 0..95
+      unsigned gslab = 0;
+      for (int n = 0;; ++n) {
+        ws_pair_sync();  // (A)
+        ws_pair_sync();  // (B)
+        const int* m = s_task[n & 1];
+        if (m[0] < 0) break;
+        if (m[3] != PT_U) continue;
+        const double* A = a.K + (long)m[10] * a.pstride;
+        const int row0 = m[4] * C::BM, col0 = m[5] * C::BN, kb = m[6] * BLK, ke = m[7] * BLK, cmin = m[8] * BLK;
+        if (!a.red_epilogue) {  // start pulling the C tile into L2 for the read-modify-write at the end
+          constexpr int LINES_PER_ROW = C::BN * 8 / 128;
+          for (int e = lt; e < C::BM * LINES_PER_ROW; e += WS_LOADERS) {
+            const int gr = row0 + e / LINES_PER_ROW, gc = col0 + (e % LINES_PER_ROW) * 16;
+            if (gr < a.rows_total && gc < a.np && gc >= cmin && (gc >> 6) <= (gr >> 6))
+              asm volatile("prefetch.global.L2 [%0];\n" ::"l"(A + (long)gr * a.ld + gc));
+          }
+        }
+        for (int k0 = kb; k0 < ke; k0 += BK) {
+          const unsigned stage = gslab % WS_STAGES, use = gslab / WS_STAGES;
+          if (use > 0) mbar_wait_bounded(&bar_empty[stage], (use - 1) & 1);  // every DMMA warp has read the old contents
+          double* sA = smem + stage * SD;
+          double* sB = sA + AOFF;
+          for (int c = lt; c < C::BM * BK / 2; c += WS_LOADERS) {
+            const int rr = c / (BK / 2), kc = (c % (BK / 2)) * 2;
+            const int gr = row0 + rr, gc = col0 + rr;
+            const bool oka = gr < a.rows_total, okb = gc < a.np;
+            cp_async16(sA + rr * KPAD + kc, oka ? A + (long)gr * a.ld + k0 + kc : A, oka);
+            cp_async16(sB + rr * KPAD + kc, okb ? A + (long)gc * a.ld + k0 + kc : A, okb);
+          }
+          cp_async_mbar_arrive(&bar_full[stage]);
+          ++gslab;
+        }
+      }
+      cp_async_wait<0>();
+    }
+    return;
+  }
+
+  // ---------------------------------------------------------------------------------------------- DMMA warps
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 224;\n");
+  const Group256Sync gsync;
+  const int wm = warp / C::WARPS_N, wn = warp % C::WARPS_N;
+  long long st_cyc[4] = {0, 0, 0, 0}, st_t0 = clock64(), st_mark = st_t0;  // thread 0: F, S, U, waiting for a task
+  int st_n[3] = {0, 0, 0}, tr_n = 0;
+  unsigned long long tr_start = 0, tr_first = 0, tr_loop = 0, tr_epi = 0;
+  int* trace = abortf + 7 + QSTATS * QSTATS_CTAS;
+  unsigned gslab = 0;
+  for (int n = 0;; ++n) {
+    mbar_wait_bounded(&bar_task[n & 1], (n >> 1) & 1);
+    const int* m = s_task[n & 1];
+    const int q = m[0], ti = m[1], r = m[2];
+    if (a.stats && t == 0) {
+      const long long now = clock64();
+      st_cyc[3] += now - st_mark;
+      st_mark = now;
+    }
+    if (q < 0) {
+      if (q == -2 && t == 0)
+        for (int rr = 0; rr < R; ++rr) a.vbuf[(a.slots ? (long)a.slots[rr] : (long)rr) * a.vstride + a.info_off] = -7777.0;
+      break;
+    }
+    if (a.stats == 2 && t == 0) tr_start = global_ns();
+    const int type = m[3], pa = m[4], pb = m[5], pc = m[6], pd = m[7], pe = m[8], pf = m[9], slot = m[10];
+    const int oi = m[11], ov = m[12], o2 = m[13];
+    double* A = a.K + (long)slot * a.pstride;
+    int* flags = a.sched + (long)r * nflags;
+    // F and S use the ring as scratch and are written for the eight warps together; after a tile update the warps
+    // arrive here one by one
+    if (type != PT_U) gsync();
+    if (type == PT_F) {
+      cholq_factor<C::THREADS, Group256Sync>(A, a.ld, pa, pb, smem, a.vbuf + (long)slot * a.vstride + a.info_off, gsync);
+    } else if (type == PT_S) {
+      cholq_solve<C::THREADS, C::BM, Group256Sync>(A, a.ld, pb, pa, pc, pd, smem, gsync);
+    } else {
+      double acc[C::MI][C::NI][2];
+      zero_acc<C>(acc);
+      for (int k0 = pc * BLK; k0 < pd * BLK; k0 += BK) {
+        const unsigned stage = gslab % WS_STAGES, use = gslab / WS_STAGES;
+        mbar_wait_bounded(&bar_full[stage], use & 1);
+        if (a.stats == 2 && t == 0 && k0 == pc * BLK) tr_first = global_ns();
+        const double* cur = smem + stage * SD;
+        mma_slab<C, Lay::KCONT, Lay::KCONT>(acc, cur, cur + AOFF, wm, wn, lane);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_empty[stage]);
+        ++gslab;
+      }
+      if (a.stats == 2 && t == 0) tr_loop = global_ns();
+      if (a.red_epilogue)
+        cholq_tile_epilogue_red<C>(A, a.ld, a.rows_total, a.np, pa * C::BM, pb * C::BN, pe * BLK, pf, acc);
+      else
+        cholq_tile_epilogue<C>(A, a.ld, a.rows_total, a.np, pa * C::BM, pb * C::BN, pe * BLK, pf, acc);
+      if (a.stats == 2 && t == 0) tr_epi = global_ns();
+      // No barrier at the end of a tile update: every warp counts itself out and goes on to the next task (its ring
+      // accesses are ordered by the stage barriers); the last one out publishes the tile.  Its release store is
+      // cumulative over the other warps' updates, which it has observed through the counter (fence - atomic - fence
+      // at CTA scope), exactly as thread 0's was over the barrier.
+      __syncwarp();
+      if (lane == 0) {
+        __threadfence_block();
+        if (atomicAdd(&s_cnt[n & 1], 1) == C::THREADS / 32 - 1) {
+          s_cnt[n & 1] = 0;
+          __threadfence_block();
+          st_release(flags + oi, ov);
+          if (o2 >= 0) st_release(flags + o2, ov);
+          s_done = n + 1;
+        }
+      }
+    }
+    if (a.stats && t == 0) {
+      const long long now = clock64();
+      st_cyc[type] += now - st_mark;
+      st_n[type] += 1;
+      st_mark = now;
+      if (a.stats == 2 && blockIdx.x < QTRACE_CTAS && tr_n < QTRACE_EVENTS) {
+        int* e = trace + 4 * (QTRACE_EVENTS * blockIdx.x + tr_n++);
+        e[0] = q | (r << 8);
+        // tile updates: where the time went inside the task, in units of 64 ns -- first slab landed, main loop done,
+        // stores issued -- in place of the task index (measurement aid)
+        e[1] = type == PT_U ? (int)(((tr_first - tr_start) >> 6 & 0x3ff) | ((tr_loop - tr_start) >> 6 & 0x3ff) << 10 |
+                                    ((tr_epi - tr_start) >> 6 & 0x3ff) << 20)
+                            : ti;
+        e[2] = (int)(tr_start & 0x7fffffffu);
+        e[3] = (int)(global_ns() & 0x7fffffffu);
+      }
+    }
+    if (t == 0 && type != PT_U) {  // F and S end with a barrier of the DMMA warps after their last global store: publish
+      st_release(flags + oi, ov);
+      if (o2 >= 0) st_release(flags + o2, ov);
+      s_done = n + 1;
+    }
+  }
+  if (a.stats && t == 0 && blockIdx.x < QSTATS_CTAS) {
+    int* o = abortf + 7 + QSTATS * blockIdx.x;
+    for (int i = 0; i < 3; ++i) o[i] = st_n[i];
+    for (int i = 0; i < 4; ++i) o[3 + i] = (int)(st_cyc[i] >> 6);
+    o[7] = (int)((clock64() - st_t0) >> 6);
+    o[8] = 0;
   }
 }

@@ -85,6 +85,30 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
       : "memory");
 }
 
+// ---- barrier functors: block routines written for "all threads of the CTA" take one of these, so that the same
+// code runs on the 256 DMMA threads of a warp-specialised kernel (named barrier 1) while its copy / scheduler warps
+// keep going.
+struct CtaSync {
+  __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+struct Group256Sync {  // threads 0..255 of the CTA
+  __device__ __forceinline__ void operator()() const { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
+};
+// A non-blocking test of an mbarrier phase (observer or waiter).
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, unsigned parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(done)
+      : "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+
 // ---- flags in global memory (dataflow Cholesky, backward-substitution chain): relaxed polling, acquire / release
 __device__ __forceinline__ int ld_relaxed(const int* p) {
   int v;

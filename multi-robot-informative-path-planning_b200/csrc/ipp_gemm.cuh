@@ -214,6 +214,75 @@ __device__ __forceinline__ void gemm_mainloop_mb(double (&acc)[C::MI][C::NI][2],
   __syncthreads();  // the caller may reuse the stages
 }
 
+// Warp-specialised form of the same pipeline, for kernels launched with C::THREADS + 128 threads (C::THREADS = 256):
+// warps 0..7 only multiply -- wait on "full", DMMA out of shared memory, release on "empty" -- and a copy warpgroup
+// (warps 8..11, registers handed over with setmaxnreg) issues every cp.async, running up to MB_STAGES slabs ahead.
+// With the copies off their instruction stream the DMMA warps hold the fp64 pipe at its issue rate (measured in the
+// dataflow Cholesky: 2.04 us per 128 x 128 x 16 slab = the 37.2 TFLOP/s peak; 2.5 us with every warp doing both).
+// A kernel uses it as
+//     if (gemm_ws_split<C>(bars)) { body<copy role>(); return; }  body<DMMA role>();
+// with NOTHING but the split before it: ptxas gives the DMMA warps their 224 registers only if every path from the
+// kernel entry runs through the setmaxnreg of its role (an early `return` before the split made it keep 168 and
+// spill half of the accumulators inside the main loop).  The DMMA role's later CTA-wide synchronisation must be
+// Group256Sync (named barrier 1), not __syncthreads().
+template <class C>
+__device__ __forceinline__ bool gemm_ws_split(uint64_t* bars) {
+  static_assert(C::THREADS == 256, "eight DMMA warps + one copy warpgroup");
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < MB_STAGES; ++s) {
+      mbar_init(&bars[s], 128);                              // full: one cp.async-completion arrival per copy thread
+      mbar_init(&bars[MB_STAGES + s], C::THREADS / 32);      // empty: one arrival per DMMA warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x >= C::THREADS) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;\n");
+    return true;
+  }
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 224;\n");
+  return false;
+}
+// Copy role: FillA(sA, k0, tid) / FillB(sB, k0, tid) stage one slab with 128 threads (tid = 0..127).
+template <class C, Lay LA, Lay LB, class FillA, class FillB>
+__device__ __forceinline__ void gemm_ws_produce(double* smem, uint64_t* bars, int kbeg, int kend, FillA fillA, FillB fillB) {
+  constexpr int SD = stage_doubles<C, LA, LB>();
+  constexpr int AOFF = tile_doubles<C::BM, LA>();
+  uint64_t* full = bars;
+  uint64_t* empty = bars + MB_STAGES;
+  const int pt = threadIdx.x - C::THREADS;
+  const int nk = (kend - kbeg + BK - 1) / BK;
+  for (int slab = 0; slab < nk; ++slab) {
+    const int stage = slab % MB_STAGES;
+    if (slab >= MB_STAGES) mbar_wait_bounded(&empty[stage], ((slab / MB_STAGES) - 1) & 1);
+    double* st = smem + stage * SD;
+    fillA(st, kbeg + slab * BK, pt);
+    fillB(st + AOFF, kbeg + slab * BK, pt);
+    cp_async_mbar_arrive(&full[stage]);
+  }
+  cp_async_wait<0>();
+}
+// DMMA role: acc += A(:, [kbeg, kend)) B([kbeg, kend), :)
+template <class C, Lay LA, Lay LB>
+__device__ __forceinline__ void gemm_ws_consume(double (&acc)[C::MI][C::NI][2], const double* smem, uint64_t* bars, int kbeg,
+                                                int kend) {
+  constexpr int SD = stage_doubles<C, LA, LB>();
+  constexpr int AOFF = tile_doubles<C::BM, LA>();
+  uint64_t* full = bars;
+  uint64_t* empty = bars + MB_STAGES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wm = warp / C::WARPS_N, wn = warp % C::WARPS_N;
+  const int nk = (kend - kbeg + BK - 1) / BK;
+  for (int it = 0; it < nk; ++it) {
+    const int stage = it % MB_STAGES;
+    mbar_wait_bounded(&full[stage], (it / MB_STAGES) & 1);
+    const double* cur = smem + stage * SD;
+    mma_slab<C, LA, LB>(acc, cur, cur + AOFF, wm, wn, lane);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[stage]);
+  }
+}
+
 // Visit every accumulator element with its tile-local (row, col).
 template <class C, class F>
 __device__ __forceinline__ void for_each_acc(double (&acc)[C::MI][C::NI][2], F f) {

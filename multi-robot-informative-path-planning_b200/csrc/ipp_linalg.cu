@@ -609,12 +609,13 @@ __global__ void __launch_bounds__(256) diag_inverse_kernel(const double* __restr
 //   STEP 1: T[r1+i][r0+j]  =  sum_{k >= j} L[r1+i][r0+k] * W[r0+k][r0+j]
 //   STEP 2: W[r1+i][r0+j]  = -sum_{k <= i} W[r1+i][r1+k] * T[r1+k][r0+j]
 // ---------------------------------------------------------------------------------------------
-template <class C, int STEP, bool MB>
-__global__ void __launch_bounds__(C::THREADS) trtri_level_kernel(const double* __restrict__ L, long ld,
-                                                                 double* __restrict__ W, long ldw, double* __restrict__ T,
-                                                                 long ldt, int nb, int parts, int s, Bat bat) {
-  extern __shared__ __align__(16) double smem[];
-  __shared__ __align__(8) uint64_t bars[2 * MB_STAGES];
+// MODE: 0 = cp.async ring with a CTA barrier per slab, 1 = mbarrier pipeline (every warp copies and multiplies),
+// 2 = warp-specialised (C::THREADS + 128 threads: eight DMMA warps + a copy warpgroup, gemm_ws_*).
+// ROLE (MODE 2 only): 1 = copy warpgroup, 2 = DMMA warps; 0 = every thread does everything.
+template <class C, int STEP, int MODE, int ROLE>
+__device__ __forceinline__ void trtri_level_body(const double* __restrict__ L, long ld, double* __restrict__ W, long ldw,
+                                                 double* __restrict__ T, long ldt, int nb, int parts, int s, const Bat& bat,
+                                                 double* smem, uint64_t* bars) {
   L += bat.slot(blockIdx.y) * bat.sK;
   W += bat.slot(blockIdx.y) * bat.sW;
   T += bat.slot(blockIdx.y) * bat.sT;
@@ -631,30 +632,58 @@ __global__ void __launch_bounds__(C::THREADS) trtri_level_kernel(const double* _
   if (r1 == r0 || r2 == r1) return;  // an empty half: the other one is already inverted
   const int row0 = r1 + by * C::BM, col0 = r0 + bx * C::BN;
   if (row0 >= r2 || col0 >= r1) return;
-  double acc[C::MI][C::NI][2];
-  zero_acc<C>(acc);
-  if (STEP == 1) {
-    auto fillA = [&](double* sm, int k0) { load_tile_async<C::BM, Lay::KCONT, C::THREADS>(sm, L, ld, row0, k0, r2, r1); };
-    auto fillB = [&](double* sm, int k0) { load_tile_async<C::BN, Lay::MCONT, C::THREADS>(sm, W, ldw, col0, k0, r1, r1); };
-    if (MB)
-      gemm_mainloop_mb<C, Lay::KCONT, Lay::MCONT>(acc, smem, bars, col0, r1, fillA, fillB);
-    else
-      gemm_mainloop<C, Lay::KCONT, Lay::MCONT>(acc, smem, col0, r1, fillA, fillB);
-    for_each_acc<C>(acc, [&](int r, int c, double v) {
-      int gr = row0 + r, gc = col0 + c;
-      if (gr < r2 && gc < r1) T[(long)gr * ldt + gc] = v;
-    });
+  // STEP 1: T = L21 W11 (k in [col0, r1));  STEP 2: W21 = -W22 T (k in [r1, row0 + BM))
+  const double* Am = (STEP == 1) ? L : W;
+  const long lda = (STEP == 1) ? ld : ldw;
+  const double* Bm = (STEP == 1) ? W : T;
+  const long ldb = (STEP == 1) ? ldw : ldt;
+  const int klimA = (STEP == 1) ? r1 : r2, klimB = (STEP == 1) ? r1 : r2;
+  const int kbeg = (STEP == 1) ? col0 : r1, kend = (STEP == 1) ? r1 : min(row0 + C::BM, r2);
+  if constexpr (ROLE == 1) {
+    auto wsA = [&](double* sm, int k0, int tid) { load_tile_async<C::BM, Lay::KCONT, 128>(sm, Am, lda, row0, k0, r2, klimA, tid); };
+    auto wsB = [&](double* sm, int k0, int tid) { load_tile_async<C::BN, Lay::MCONT, 128>(sm, Bm, ldb, col0, k0, r1, klimB, tid); };
+    gemm_ws_produce<C, Lay::KCONT, Lay::MCONT>(smem, bars, kbeg, kend, wsA, wsB);
+    return;
   } else {
-    auto fillA = [&](double* sm, int k0) { load_tile_async<C::BM, Lay::KCONT, C::THREADS>(sm, W, ldw, row0, k0, r2, r2); };
-    auto fillB = [&](double* sm, int k0) { load_tile_async<C::BN, Lay::MCONT, C::THREADS>(sm, T, ldt, col0, k0, r1, r2); };
-    if (MB)
-      gemm_mainloop_mb<C, Lay::KCONT, Lay::MCONT>(acc, smem, bars, r1, min(row0 + C::BM, r2), fillA, fillB);
-    else
-      gemm_mainloop<C, Lay::KCONT, Lay::MCONT>(acc, smem, r1, min(row0 + C::BM, r2), fillA, fillB);
-    for_each_acc<C>(acc, [&](int r, int c, double v) {
-      int gr = row0 + r, gc = col0 + c;
-      if (gr < r2 && gc < r1) W[(long)gr * ldw + gc] = -v;
-    });
+    double acc[C::MI][C::NI][2];
+    zero_acc<C>(acc);
+    if constexpr (ROLE == 2) {
+      gemm_ws_consume<C, Lay::KCONT, Lay::MCONT>(acc, smem, bars, kbeg, kend);
+    } else {
+      auto fillA = [&](double* sm, int k0) { load_tile_async<C::BM, Lay::KCONT, C::THREADS>(sm, Am, lda, row0, k0, r2, klimA); };
+      auto fillB = [&](double* sm, int k0) { load_tile_async<C::BN, Lay::MCONT, C::THREADS>(sm, Bm, ldb, col0, k0, r1, klimB); };
+      if (MODE == 1)
+        gemm_mainloop_mb<C, Lay::KCONT, Lay::MCONT>(acc, smem, bars, kbeg, kend, fillA, fillB);
+      else
+        gemm_mainloop<C, Lay::KCONT, Lay::MCONT>(acc, smem, kbeg, kend, fillA, fillB);
+    }
+    if (STEP == 1) {
+      for_each_acc<C>(acc, [&](int r, int c, double v) {
+        int gr = row0 + r, gc = col0 + c;
+        if (gr < r2 && gc < r1) T[(long)gr * ldt + gc] = v;
+      });
+    } else {
+      for_each_acc<C>(acc, [&](int r, int c, double v) {
+        int gr = row0 + r, gc = col0 + c;
+        if (gr < r2 && gc < r1) W[(long)gr * ldw + gc] = -v;
+      });
+    }
+  }
+}
+template <class C, int STEP, int MODE>
+__global__ void __launch_bounds__(C::THREADS + (MODE == 2 ? 128 : 0), 1) trtri_level_kernel(const double* __restrict__ L, long ld,
+                                                                 double* __restrict__ W, long ldw, double* __restrict__ T,
+                                                                 long ldt, int nb, int parts, int s, Bat bat) {
+  extern __shared__ __align__(16) double smem[];
+  __shared__ __align__(8) uint64_t bars[2 * MB_STAGES];
+  if constexpr (MODE == 2) {
+    if (gemm_ws_split<C>(bars)) {
+      trtri_level_body<C, STEP, MODE, 1>(L, ld, W, ldw, T, ldt, nb, parts, s, bat, smem, bars);
+      return;
+    }
+    trtri_level_body<C, STEP, MODE, 2>(L, ld, W, ldw, T, ldt, nb, parts, s, bat, smem, bars);
+  } else {
+    trtri_level_body<C, STEP, MODE, 0>(L, ld, W, ldw, T, ldt, nb, parts, s, bat, smem, bars);
   }
 }
 
@@ -709,14 +738,11 @@ __global__ void __launch_bounds__(256) gemv_reduce_kernel(const double* __restri
 // dK_1 = K0 o D2 (D2 on l-scaled coordinates, kernels.py:1577).  Lower-triangular tiles only,
 // off-diagonal tiles weighted 2.  Per-tile partials, reduced in fixed order by lml_finalize.
 // ---------------------------------------------------------------------------------------------
-template <class C, bool MB>
-__global__ void __launch_bounds__(C::THREADS) lml_grad_kernel(const double* __restrict__ W, long ldw,
-                                                              const double* __restrict__ vbuf,
-                                                              const double* __restrict__ hyp, double* __restrict__ partials,
-                                                              GpDims d, Bat bat, const double* __restrict__ tile_bbox) {
-  extern __shared__ __align__(16) double smem[];
-  __shared__ double red[2][C::THREADS / 32];
-  __shared__ __align__(8) uint64_t bars[2 * MB_STAGES];
+template <class C, int MODE, int ROLE>
+__device__ __forceinline__ void lml_grad_body(const double* __restrict__ W, long ldw, const double* __restrict__ vbuf,
+                                              const double* __restrict__ hyp, double* __restrict__ partials, const GpDims& d,
+                                              const Bat& bat, const double* __restrict__ tile_bbox, double* smem,
+                                              uint64_t* bars, double (*red)[C::THREADS / 32]) {
   {
     const long slot = bat.slot(blockIdx.y);
     W += slot * bat.sW;
@@ -739,18 +765,28 @@ __global__ void __launch_bounds__(C::THREADS) lml_grad_kernel(const double* __re
     const double gx = fmax(0.0, fmax(bi.x - bj.y, bj.x - bi.y)), gy = fmax(0.0, fmax(bi.z - bj.w, bj.z - bi.w));
     const double cut = 13.6 * hyp[1];
     if (gx * gx + gy * gy > cut * cut) {
-      if (threadIdx.x == 0) partials[2 * b] = partials[2 * b + 1] = 0.0;
+      if (threadIdx.x == 0 && ROLE != 1) partials[2 * b] = partials[2 * b + 1] = 0.0;
       return;
     }
   }
+  if constexpr (ROLE == 1) {
+    auto wsA = [&](double* sm, int k0, int tid) { load_tile_async<C::BM, Lay::MCONT, 128>(sm, W, ldw, row0, k0, d.np, d.np, tid); };
+    auto wsB = [&](double* sm, int k0, int tid) { load_tile_async<C::BN, Lay::MCONT, 128>(sm, W, ldw, col0, k0, d.np, d.np, tid); };
+    gemm_ws_produce<C, Lay::MCONT, Lay::MCONT>(smem, bars, row0, d.np, wsA, wsB);
+    return;
+  }
   double acc[C::MI][C::NI][2];
   zero_acc<C>(acc);
-  auto fillA = [&](double* sm, int k0) { load_tile_async<C::BM, Lay::MCONT, C::THREADS>(sm, W, ldw, row0, k0, d.np, d.np); };
-  auto fillB = [&](double* sm, int k0) { load_tile_async<C::BN, Lay::MCONT, C::THREADS>(sm, W, ldw, col0, k0, d.np, d.np); };
-  if (MB)
-    gemm_mainloop_mb<C, Lay::MCONT, Lay::MCONT>(acc, smem, bars, row0, d.np, fillA, fillB);
-  else
-    gemm_mainloop<C, Lay::MCONT, Lay::MCONT>(acc, smem, row0, d.np, fillA, fillB);
+  if constexpr (ROLE == 2) {
+    gemm_ws_consume<C, Lay::MCONT, Lay::MCONT>(acc, smem, bars, row0, d.np);
+  } else {
+    auto fillA = [&](double* sm, int k0) { load_tile_async<C::BM, Lay::MCONT, C::THREADS>(sm, W, ldw, row0, k0, d.np, d.np); };
+    auto fillB = [&](double* sm, int k0) { load_tile_async<C::BN, Lay::MCONT, C::THREADS>(sm, W, ldw, col0, k0, d.np, d.np); };
+    if (MODE == 1)
+      gemm_mainloop_mb<C, Lay::MCONT, Lay::MCONT>(acc, smem, bars, row0, d.np, fillA, fillB);
+    else
+      gemm_mainloop<C, Lay::MCONT, Lay::MCONT>(acc, smem, row0, d.np, fillA, fillB);
+  }
   const double c = hyp[0];
   const double* xs = vbuf + V_XS * d.npv;
   const double* ys = vbuf + V_YS * d.npv;
@@ -774,7 +810,8 @@ __global__ void __launch_bounds__(C::THREADS) lml_grad_kernel(const double* __re
     red[0][warp] = g0;
     red[1][warp] = g1;
   }
-  __syncthreads();
+  if (ROLE == 2) Group256Sync()();  // the DMMA warps only: the copy warps have returned
+  else __syncthreads();
   if (threadIdx.x == 0) {
     double s0 = 0.0, s1 = 0.0;
     for (int w = 0; w < C::THREADS / 32; ++w) {
@@ -783,6 +820,24 @@ __global__ void __launch_bounds__(C::THREADS) lml_grad_kernel(const double* __re
     }
     partials[2 * b] = wgt * s0;
     partials[2 * b + 1] = wgt * s1;
+  }
+}
+template <class C, int MODE>
+__global__ void __launch_bounds__(C::THREADS + (MODE == 2 ? 128 : 0), 1) lml_grad_kernel(const double* __restrict__ W, long ldw,
+                                                              const double* __restrict__ vbuf,
+                                                              const double* __restrict__ hyp, double* __restrict__ partials,
+                                                              GpDims d, Bat bat, const double* __restrict__ tile_bbox) {
+  extern __shared__ __align__(16) double smem[];
+  __shared__ double red[2][C::THREADS / 32];
+  __shared__ __align__(8) uint64_t bars[2 * MB_STAGES];
+  if constexpr (MODE == 2) {
+    if (gemm_ws_split<C>(bars)) {
+      lml_grad_body<C, MODE, 1>(W, ldw, vbuf, hyp, partials, d, bat, tile_bbox, smem, bars, red);
+      return;
+    }
+    lml_grad_body<C, MODE, 2>(W, ldw, vbuf, hyp, partials, d, bat, tile_bbox, smem, bars, red);
+  } else {
+    lml_grad_body<C, MODE, 0>(W, ldw, vbuf, hyp, partials, d, bat, tile_bbox, smem, bars, red);
   }
 }
 
@@ -936,14 +991,16 @@ static bool use_small_tiles(int np) { return np <= 1536; }
 
 static const Bat kOne = {nullptr, 0, 0, 0, 0};  // a single problem in slot 0
 
-// IPP_GEMM_MB=0 selects the main loop with a CTA barrier per k-slab (A/B measurements); default: the mbarrier pipeline.
-static bool use_mb_pipeline() {
-  static const bool on = [] {
+// Main loop of the GEMM-shaped fit kernels (A/B measurements): IPP_GEMM_MB=0 a CTA barrier per k-slab, =1 the mbarrier
+// pipeline with every warp copying and multiplying, default (=2) warp-specialised where the tile has eight DMMA warps.
+static int gemm_pipeline_mode() {
+  static const int mode = [] {
     const char* e = getenv("IPP_GEMM_MB");
-    return !(e && e[0] == '0');
+    return (e && e[0] == '0') ? 0 : ((e && e[0] == '1') ? 1 : 2);
   }();
-  return on;
+  return mode;
 }
+static bool use_mb_pipeline() { return gemm_pipeline_mode() != 0; }
 
 
 // How the factorisation is run: the cooperative kernel (grid barriers; one problem) or the dataflow kernel driven by
@@ -955,6 +1012,8 @@ struct CholRun {
   int max_ctas;
   int stats;
   int eager_scan;
+  int red;  // tile updates written back as reductions at the L2
+  int ws;  // warp-specialised executor (chol_queue_ws_kernel); 0: every warp claims, copies and multiplies in turn
 };
 
 static int device_sms(int* sms) {
@@ -979,11 +1038,20 @@ static int chol_queue_launch(double* Kb, double* vbuf, const GpDims& d, const Ba
   constexpr size_t SYRK_SM = gemm_smem_bytes<C, Lay::KCONT, Lay::KCONT>();
   constexpr size_t SM1 = SYRK_SM > FACT_SMEM ? SYRK_SM : FACT_SMEM;
   constexpr size_t SM = SM1 > solve_smem<C::BM>() ? SM1 : solve_smem<C::BM>();
-  if (opt_in_smem(chol_queue_kernel<C>, SM) != cudaSuccess) return IPP_ERR_CUDA;
+  constexpr bool CAN_WS = C::THREADS == 256;
+  const bool ws = CAN_WS && run.ws;
+  constexpr size_t SMW = cholq_ws_ring_bytes<Cfg128>() > SM ? cholq_ws_ring_bytes<Cfg128>() : SM;
   int sms = 0, per_sm = 0;
   if (device_sms(&sms) != IPP_OK) return IPP_ERR_CUDA;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chol_queue_kernel<C>, C::THREADS, SM) != cudaSuccess || per_sm < 1)
-    return IPP_ERR_CUDA;
+  if (ws) {
+    if (opt_in_smem(chol_queue_ws_kernel<Cfg128>, SMW) != cudaSuccess) return IPP_ERR_CUDA;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chol_queue_ws_kernel<Cfg128>, 384, SMW) != cudaSuccess || per_sm < 1)
+      return IPP_ERR_CUDA;
+  } else {
+    if (opt_in_smem(chol_queue_kernel<C>, SM) != cudaSuccess) return IPP_ERR_CUDA;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chol_queue_kernel<C>, C::THREADS, SM) != cudaSuccess || per_sm < 1)
+      return IPP_ERR_CUDA;
+  }
   // no more CTAs than the widest front has work for: every extra CTA only polls
   const int T0 = (d.rows + C::BM - 1) / C::BM;
   long useful = (long)R * ((long)T0 * (T0 + 1) / 2 + d.rows / BLK);
@@ -1010,7 +1078,11 @@ static int chol_queue_launch(double* Kb, double* vbuf, const GpDims& d, const Ba
   a.stats = run.stats;
   a.use_mb = use_mb_pipeline() ? 1 : 0;
   a.eager_scan = run.eager_scan;
-  chol_queue_kernel<C><<<(unsigned)ctas, C::THREADS, SM, st>>>(a);
+  a.red_epilogue = run.red;
+  if (ws)
+    chol_queue_ws_kernel<Cfg128><<<(unsigned)ctas, 384, SMW, st>>>(a);
+  else
+    chol_queue_kernel<C><<<(unsigned)ctas, C::THREADS, SM, st>>>(a);
   return IPP_OK;
 }
 
@@ -1053,22 +1125,25 @@ static int chol_inplace(double* Kb, double* Wb, double* vbuf, const GpDims& d, c
   return IPP_OK;
 }
 
-template <class C, bool MB>
+template <class C, int MODE>
 static int trtri_level_t(const double* Kb, double* Wb, double* Tb, const GpDims& d, int parts, int s, const Bat& bat, int R,
                          cudaStream_t st) {
-  constexpr size_t SM = MB ? gemm_mb_smem_bytes<C, Lay::KCONT, Lay::MCONT>() : gemm_smem_bytes<C, Lay::KCONT, Lay::MCONT>();
-  if (opt_in_smem(trtri_level_kernel<C, 1, MB>, SM) != cudaSuccess) return IPP_ERR_CUDA;
-  if (opt_in_smem(trtri_level_kernel<C, 2, MB>, SM) != cudaSuccess) return IPP_ERR_CUDA;
+  constexpr size_t SM = MODE ? gemm_mb_smem_bytes<C, Lay::KCONT, Lay::MCONT>() : gemm_smem_bytes<C, Lay::KCONT, Lay::MCONT>();
+  constexpr int NT = C::THREADS + (MODE == 2 ? 128 : 0);
+  if (opt_in_smem(trtri_level_kernel<C, 1, MODE>, SM) != cudaSuccess) return IPP_ERR_CUDA;
+  if (opt_in_smem(trtri_level_kernel<C, 2, MODE>, SM) != cudaSuccess) return IPP_ERR_CUDA;
   const unsigned grid = (unsigned)(((s + C::BN - 1) / C::BN) * ((s + C::BM - 1) / C::BM) * (parts / 2));
-  trtri_level_kernel<C, 1, MB><<<dim3(grid, R), C::THREADS, SM, st>>>(Kb, d.ld, Wb, d.ld, Tb, d.ld, d.np / BLK, parts, s, bat);
-  trtri_level_kernel<C, 2, MB><<<dim3(grid, R), C::THREADS, SM, st>>>(Kb, d.ld, Wb, d.ld, Tb, d.ld, d.np / BLK, parts, s, bat);
+  trtri_level_kernel<C, 1, MODE><<<dim3(grid, R), NT, SM, st>>>(Kb, d.ld, Wb, d.ld, Tb, d.ld, d.np / BLK, parts, s, bat);
+  trtri_level_kernel<C, 2, MODE><<<dim3(grid, R), NT, SM, st>>>(Kb, d.ld, Wb, d.ld, Tb, d.ld, d.np / BLK, parts, s, bat);
   return IPP_OK;
 }
 template <class C>
 static int trtri_level(const double* Kb, double* Wb, double* Tb, const GpDims& d, int parts, int s, const Bat& bat, int R,
                        cudaStream_t st) {
-  return use_mb_pipeline() ? trtri_level_t<C, true>(Kb, Wb, Tb, d, parts, s, bat, R, st)
-                           : trtri_level_t<C, false>(Kb, Wb, Tb, d, parts, s, bat, R, st);
+  const int mode = gemm_pipeline_mode();
+  if constexpr (C::THREADS == 256)
+    if (mode == 2) return trtri_level_t<C, 2>(Kb, Wb, Tb, d, parts, s, bat, R, st);
+  return mode ? trtri_level_t<C, 1>(Kb, Wb, Tb, d, parts, s, bat, R, st) : trtri_level_t<C, 0>(Kb, Wb, Tb, d, parts, s, bat, R, st);
 }
 
 template <class C>
@@ -1089,22 +1164,25 @@ static int trtri_inplace(const double* Kb, double* Wb, double* Tb, const GpDims&
   return IPP_OK;
 }
 
-template <class C, bool MB>
+template <class C, int MODE>
 static int lml_grad_launch_t(const double* Wb, double* vbuf, const double* hyp, const GpDims& d, int* ntiles, const Bat& bat,
                              int R, const double* tile_bbox, cudaStream_t st) {
-  constexpr size_t SM = MB ? gemm_mb_smem_bytes<C, Lay::MCONT, Lay::MCONT>() : gemm_smem_bytes<C, Lay::MCONT, Lay::MCONT>();
-  if (opt_in_smem(lml_grad_kernel<C, MB>, SM) != cudaSuccess) return IPP_ERR_CUDA;
+  constexpr size_t SM = MODE ? gemm_mb_smem_bytes<C, Lay::MCONT, Lay::MCONT>() : gemm_smem_bytes<C, Lay::MCONT, Lay::MCONT>();
+  if (opt_in_smem(lml_grad_kernel<C, MODE>, SM) != cudaSuccess) return IPP_ERR_CUDA;
   const int T = (d.np + C::BM - 1) / C::BM;
   *ntiles = T * (T + 1) / 2;
-  lml_grad_kernel<C, MB><<<dim3(*ntiles, R), C::THREADS, SM, st>>>(Wb, d.ld, vbuf, hyp, vbuf + v_partials_off(d), d, bat,
-                                                                   tile_bbox);
+  lml_grad_kernel<C, MODE><<<dim3(*ntiles, R), C::THREADS + (MODE == 2 ? 128 : 0), SM, st>>>(
+      Wb, d.ld, vbuf, hyp, vbuf + v_partials_off(d), d, bat, tile_bbox);
   return IPP_OK;
 }
 template <class C>
 static int lml_grad_launch(const double* Wb, double* vbuf, const double* hyp, const GpDims& d, int* ntiles, const Bat& bat,
                            int R, const double* tile_bbox, cudaStream_t st) {
-  return use_mb_pipeline() ? lml_grad_launch_t<C, true>(Wb, vbuf, hyp, d, ntiles, bat, R, tile_bbox, st)
-                           : lml_grad_launch_t<C, false>(Wb, vbuf, hyp, d, ntiles, bat, R, tile_bbox, st);
+  const int mode = gemm_pipeline_mode();
+  if constexpr (C::THREADS == 256)
+    if (mode == 2) return lml_grad_launch_t<C, 2>(Wb, vbuf, hyp, d, ntiles, bat, R, tile_bbox, st);
+  return mode ? lml_grad_launch_t<C, 1>(Wb, vbuf, hyp, d, ntiles, bat, R, tile_bbox, st)
+              : lml_grad_launch_t<C, 0>(Wb, vbuf, hyp, d, ntiles, bat, R, tile_bbox, st);
 }
 
 static int gp_factor(const double* X, const double* y, int n, const double* hyp, double* Kb, double* Wb, double* Tb,
@@ -1270,7 +1348,7 @@ int ipp_gram_kernel(int kind, const double* X, int n, const double* Y, int m, do
 
 int ipp_gp_lml_grad(const double* X, const double* y, int n, const double* hyp, double* Kbuf, double* Wbuf,
                     double* Tbuf, double* vbuf, int with_grad, int max_ctas, void* stream) {
-  const CholRun run = {nullptr, nullptr, 0, max_ctas, 0, 0};
+  const CholRun run = {nullptr, nullptr, 0, max_ctas, 0, 0, 0, 0};
   return gp_lml_grad_run(X, y, n, hyp, Kbuf, Wbuf, Tbuf, vbuf, with_grad, kOne, 1, run, nullptr, (cudaStream_t)stream);
 }
 
@@ -1299,7 +1377,8 @@ int ipp_gp_lml_grad_batch(const double* X, const double* y, int n, const double*
   if (R <= 0 || !plan || !sched) return IPP_ERR_ARG;
   const GpDims d = gp_dims(n > 0 ? n : 1);
   const Bat bat = {slots, (long)d.rows * d.ld, (long)d.np * d.ld, (long)d.np * d.ld, v_total(d)};
-  const CholRun run = {plan, sched, (flags & 1) ? 0 : 1, flags >> 8, (flags & 4) ? 2 : ((flags >> 1) & 1), (flags >> 3) & 1};
+  const CholRun run = {plan, sched, (flags & 1) ? 0 : 1, flags >> 8, (flags & 4) ? 2 : ((flags >> 1) & 1), (flags >> 3) & 1,
+                       (flags & 32) ? 0 : 1, (flags & 16) ? 0 : 1};
   return gp_lml_grad_run(X, y, n, hyp, Kbuf, Wbuf, Tbuf, vbuf, with_grad, bat, R, run, tile_bbox, (cudaStream_t)stream);
 }
 
@@ -1328,13 +1407,13 @@ static int gp_fit_final_run(const double* X, const double* y, int n, const doubl
 
 int ipp_gp_fit_final(const double* X, const double* y, int n, const double* hyp, double* Kbuf, double* Wbuf,
                      double* Tbuf, double* vbuf, void* stream) {
-  const CholRun run = {nullptr, nullptr, 0, 0, 0, 0};
+  const CholRun run = {nullptr, nullptr, 0, 0, 0, 0, 0, 0};
   return gp_fit_final_run(X, y, n, hyp, Kbuf, Wbuf, Tbuf, vbuf, run, (cudaStream_t)stream);
 }
 
 int ipp_gp_fit_final_plan(const double* X, const double* y, int n, const double* hyp, double* Kbuf, double* Wbuf,
                           double* Tbuf, double* vbuf, const int* plan, int* sched, int flags, void* stream) {
-  const CholRun run = {plan, plan ? sched : nullptr, (flags & 1) ? 0 : 1, 0, 0, (flags >> 3) & 1};
+  const CholRun run = {plan, plan ? sched : nullptr, (flags & 1) ? 0 : 1, 0, 0, (flags >> 3) & 1, (flags & 32) ? 0 : 1, (flags & 16) ? 0 : 1};
   return gp_fit_final_run(X, y, n, hyp, Kbuf, Wbuf, Tbuf, vbuf, run, (cudaStream_t)stream);
 }
 
@@ -1352,7 +1431,7 @@ int ipp_mi_logdet(const double* leaf_xy, int L, const double* obs_xy, int na, do
   int rc = use_small_tiles(d.np) ? mi_build<Cfg64>(Gtmp, nap, Lp, nap, trans, beta, Kbuf, d, st)
                                  : mi_build<Cfg128>(Gtmp, nap, Lp, nap, trans, beta, Kbuf, d, st);
   if (rc != IPP_OK) return rc;
-  const CholRun run = {nullptr, nullptr, 0, 0, 0, 0};
+  const CholRun run = {nullptr, nullptr, 0, 0, 0, 0, 0, 0};
   rc = use_small_tiles(d.np) ? chol_inplace<Cfg64>(Kbuf, Wbuf, vbuf, d, kOne, 1, run, st)
                              : chol_inplace<Cfg128>(Kbuf, Wbuf, vbuf, d, kOne, 1, run, st);
   if (rc != IPP_OK) return rc;

@@ -6,6 +6,12 @@
 // 8-agent run once everything dense is on the device).  This is the same loop natively, on the structure-of-arrays
 // tree the device scorer reads (rrt_utils.TreeArrays): ~0.3 us per insertion.
 //
+// The two scans of every insertion (nearest node, nodes within the radius) go through a uniform grid of cells a little
+// wider than the radius: the reference grows every tree with the WHOLE budget (rrt.py:659), so at the size of its own
+// example config a tree has 5 000 - 7 000 nodes in a 40 x 40 workspace and the all-pairs scans were 0.27 s per tree.
+// The grid only selects CANDIDATES; the distances, the comparison and the tie rules (first minimum / ascending ids)
+// are applied to them exactly as the full scans apply them to every node.
+//
 // Decisions and coordinates are the reference's bit for bit.  Every comparison of the reference is on
 // np.linalg.norm of a 2-vector = sqrt(x.dot(x)), whose dot comes from the BLAS numpy links (two roundings, or one
 // fused multiply-add, depending on the ddot kernel); `norm_variant` selects the matching form and the Python side
@@ -13,6 +19,8 @@
 // else is IEEE element-wise arithmetic in the reference's order; the file is compiled with -ffp-contract=off.
 #include <math.h>
 #include <stdint.h>
+#include <algorithm>
+#include <vector>
 #include "../../include/ipp_b200.h"
 
 #define IPP_FMA_FN __attribute__((target("fma")))
@@ -59,6 +67,79 @@ struct Tree {
   }
 };
 
+// Uniform grid over the workspace; nodes outside it (a start position off the map) are kept in the border cells, which
+// keeps every lower bound below valid (such a node is farther away than its cell).
+struct Grid {
+  double x0, y0, cell;
+  int gx, gy;
+  std::vector<int> head, next;
+  Grid(const double* ws4, double cell_want, int capacity) {
+    const double w = ws4[1] - ws4[0], h = ws4[3] - ws4[2];
+    const double span = w > h ? w : h;
+    cell = cell_want > 0.0 ? cell_want * (1.0 + 1e-6) : span / 64.0;  // wider than the radius: see near()
+    if (!(cell >= span / 256.0)) cell = span / 256.0;
+    if (!(cell > 0.0)) cell = 1.0;
+    x0 = ws4[0];
+    y0 = ws4[2];
+    gx = (int)floor(w / cell) + 1;
+    gy = (int)floor(h / cell) + 1;
+    if (gx < 1) gx = 1;
+    if (gy < 1) gy = 1;
+    head.assign((size_t)gx * gy, -1);
+    next.assign((size_t)capacity, -1);
+  }
+  inline int cx(double x) const {
+    const double f = floor((x - x0) / cell);
+    return f < 0.0 ? 0 : (f > gx - 1 ? gx - 1 : (int)f);
+  }
+  inline int cy(double y) const {
+    const double f = floor((y - y0) / cell);
+    return f < 0.0 ? 0 : (f > gy - 1 ? gy - 1 : (int)f);
+  }
+  inline void insert(int i, double x, double y) {
+    const int c = cy(y) * gx + cx(x);
+    next[i] = head[c];
+    head[c] = i;
+  }
+};
+
+// Path costs for the rewire test.  The reference walks leaf-to-root for every near node of every insertion
+// (rrt_utils.py:71-76, 85-88): with ~36 near nodes and paths of a few hundred edges that is the whole cost of a dense
+// tree.  Here every node carries an APPROXIMATE cost (parent's + own edge, kept current through rewires by updating
+// the subtree) with a rigorous bound on its distance from the walked sum -- both are floating-point sums of the same
+// m positive terms, each within (m - 1) eps of the true sum -- and a comparison is decided on the approximations
+// only when the bound cannot change it; otherwise the two walks are done as the reference does them.
+struct Costs {
+  std::vector<double> a;
+  std::vector<int> depth, first, nxt, prv, stack;
+  explicit Costs(int capacity) : a(capacity, 0.0), depth(capacity, 0), first(capacity, -1), nxt(capacity, -1), prv(capacity, -1) {}
+  inline void link(int c, int p) {
+    prv[c] = -1;
+    nxt[c] = first[p];
+    if (first[p] >= 0) prv[first[p]] = c;
+    first[p] = c;
+  }
+  inline void unlink(int c, int p) {
+    if (prv[c] >= 0) nxt[prv[c]] = nxt[c];
+    else first[p] = nxt[c];
+    if (nxt[c] >= 0) prv[nxt[c]] = prv[c];
+  }
+  inline double slack(int i) const { return 4e-16 * (depth[i] + 2) * a[i]; }
+  void refresh_subtree(int c, const double* edge) {  // a[c], depth[c] are current: push them down
+    stack.clear();
+    stack.push_back(c);
+    while (!stack.empty()) {
+      const int u = stack.back();
+      stack.pop_back();
+      for (int v = first[u]; v >= 0; v = nxt[v]) {
+        a[v] = a[u] + edge[v];
+        depth[v] = depth[u] + 1;
+        stack.push_back(v);
+      }
+    }
+  }
+};
+
 template <int V>
 IPP_FMA_FN int grow(int mode, double* xy, long long* parent0, long long* parent, double* edge, long long* nchild, int n,
                     int capacity, const double* uniforms, int K, const double* ws4, double step, double radius,
@@ -68,27 +149,57 @@ IPP_FMA_FN int grow(int mode, double* xy, long long* parent0, long long* parent,
   const double w = ws4[1] - ws4[0], h = ws4[3] - ws4[2];
   // sqrt is monotone: a squared length outside [r2lo, r2hi] decides `norm < radius` without the square root
   const double r2 = radius * radius, r2lo = r2 * (1.0 - 1e-14), r2hi = r2 * (1.0 + 1e-14);
+  Grid grid(ws4, radius > step ? radius : step, capacity);
+  for (int i = 0; i < n; ++i) grid.insert(i, xy[2 * i], xy[2 * i + 1]);
+  Costs cost(mode != 0 ? capacity : 0);
+  if (mode != 0) {  // the nodes the tree already has: children lists, then costs from the roots down
+    for (int i = 0; i < n; ++i)
+      if (parent[i] >= 0) cost.link(i, (int)parent[i]);
+    for (int i = 0; i < n; ++i)
+      if (parent[i] < 0) cost.refresh_subtree(i, edge);
+  }
   double travelled = *travelled_io;
   int nrw = *n_rewires_io, k = 0, done = travelled < budget_portion ? 0 : 1;
   while (!done && k < K && t.n < capacity && nrw + t.n <= rewire_cap) {
     // np.random.rand(2) * (w, h) + (x0, y0)
     const double tx = uniforms[2 * k] * w + ws4[0], ty = uniforms[2 * k + 1] * h + ws4[2];
     ++k;
-    // nearest: min(..., key=norm) keeps the first minimum (rrt_utils.py:100-101).  A node can only beat the
-    // running minimum of sqrt(dot) if its dot is smaller, so the square root is taken for those alone.
-    long long nn = 0;
-    double best_s = dot2<V>(xy[0] - tx, xy[1] - ty), best = sqrt(best_s);
-    for (int i = 1; i < t.n; ++i) {
-      const double s = dot2<V>(xy[2 * i] - tx, xy[2 * i + 1] - ty);
-      if (s < best_s) {
-        const double d = sqrt(s);
-        if (d < best) {
-          best = d;
-          best_s = s;
-          nn = i;
+    // nearest: min(..., key=norm) keeps the first minimum (rrt_utils.py:100-101): the smallest sqrt(dot), and among
+    // equal ones the smallest id.  Rings of cells around the target's cell; once every cell within Chebyshev distance
+    // rho has been seen, an unseen node is at least rho cells away, so the search stops when the best distance is
+    // below that (with a margin far above the rounding of either side).  A node can only match or beat the running
+    // minimum of sqrt(dot) if its dot is not larger (up to rounding), so the square root is taken for those alone.
+    long long nn = -1;
+    double best_s = 0.0, best = 0.0, best_hi = 0.0;
+    {
+      const int tcx = grid.cx(tx), tcy = grid.cy(ty);
+      for (int rho = 0;; ++rho) {
+        bool any = false;
+        for (int iy = tcy - rho; iy <= tcy + rho; ++iy) {
+          if (iy < 0 || iy >= grid.gy) continue;
+          const bool edge_row = (iy == tcy - rho || iy == tcy + rho);
+          for (int ix = tcx - rho; ix <= tcx + rho; ix += (edge_row || rho == 0) ? 1 : 2 * rho) {
+            if (ix < 0 || ix >= grid.gx) continue;
+            any = true;
+            for (int i = grid.head[(size_t)iy * grid.gx + ix]; i >= 0; i = grid.next[i]) {
+              const double s = dot2<V>(xy[2 * i] - tx, xy[2 * i + 1] - ty);
+              if (nn < 0 || s <= best_hi) {
+                const double d = sqrt(s);
+                if (nn < 0 || d < best || (d == best && i < nn)) {
+                  best = d;
+                  best_s = s;
+                  best_hi = s * (1.0 + 1e-14);
+                  nn = i;
+                }
+              }
+            }
+          }
         }
+        if (nn >= 0 && best < rho * grid.cell * (1.0 - 1e-9)) break;
+        if (!any) break;  // the ring lies outside the grid: every cell has been seen
       }
     }
+    (void)best_s;
     // steer (rrt_utils.py:93-98); rrt* uses the literal step 1.0 (rrt.py:285), passed in by the caller
     double dx = tx - xy[2 * nn], dy = ty - xy[2 * nn + 1];
     double distance = norm2<V>(dx, dy);
@@ -99,11 +210,23 @@ IPP_FMA_FN int grow(int mode, double* xy, long long* parent0, long long* parent,
     distance = distance < step ? distance : step;   // Python min(distance, d_max_step): the first of equals
     const double px = xy[2 * nn] + dx * distance, py = xy[2 * nn + 1] + dy * distance;
     int nnb = 0;
-    if (mode != 0)   // near: ascending ids with norm < radius (rrt_utils.py:90-91), before the node is added
-      for (int i = 0; i < t.n; ++i) {
-        const double s = dot2<V>(xy[2 * i] - px, xy[2 * i + 1] - py);
-        if (s < r2lo || (s <= r2hi && sqrt(s) < radius)) scratch[nnb++] = i;
+    if (mode != 0) {   // near: ascending ids with norm < radius (rrt_utils.py:90-91), before the node is added.
+      // The cells are wider than the radius by 1e-6, so a node `reach` + 1 or more cells away is farther than the
+      // radius by a margin no rounding bridges; the candidates are tested as the full scan tests every node.
+      const int pcx = grid.cx(px), pcy = grid.cy(py);
+      const int reach = (int)ceil(radius / grid.cell);
+      for (int iy = pcy - reach; iy <= pcy + reach; ++iy) {
+        if (iy < 0 || iy >= grid.gy) continue;
+        for (int ix = pcx - reach; ix <= pcx + reach; ++ix) {
+          if (ix < 0 || ix >= grid.gx) continue;
+          for (int i = grid.head[(size_t)iy * grid.gx + ix]; i >= 0; i = grid.next[i]) {
+            const double s = dot2<V>(xy[2 * i] - px, xy[2 * i + 1] - py);
+            if (s < r2lo || (s <= r2hi && sqrt(s) < radius)) scratch[nnb++] = i;
+          }
+        }
       }
+      std::sort(scratch, scratch + nnb);
+    }
     long long par = nn;
     if (mode == 1) {   // rrt*: cheapest parent among the near nodes (rrt.py:291-297)
       double c_min = t.path_cost(nn) + t.dist(nn, px, py);
@@ -116,19 +239,35 @@ IPP_FMA_FN int grow(int mode, double* xy, long long* parent0, long long* parent,
       }
     }
     const int nw = t.add(px, py, par);   // rig: add_node overrides choose_parent -- the parent is the nearest node
+    grid.insert(nw, px, py);
     travelled += edge[nw];
-    if (mode != 0)   // rewire (rrt_utils.py:85-88)
+    if (mode != 0) {   // rewire (rrt_utils.py:85-88)
+      cost.link(nw, (int)par);
+      cost.depth[nw] = cost.depth[par] + 1;
+      cost.a[nw] = cost.a[par] + edge[nw];
       for (int q = 0; q < nnb; ++q) {
-        const long long c = scratch[q];
-        if (t.path_cost(nw) + t.dist(c, px, py) < t.path_cost(c)) {
+        const int c = scratch[q];
+        const double d = t.dist(c, px, py);
+        const double lhs = cost.a[nw] + d, tol = cost.slack(nw) + cost.slack(c) + 4e-16 * lhs;
+        bool take;
+        if (lhs + tol < cost.a[c]) take = true;
+        else if (lhs - tol >= cost.a[c]) take = false;
+        else take = t.path_cost(nw) + d < t.path_cost(c);   // too close for the bound: the reference's own walks
+        if (take) {
+          cost.unlink(c, (int)parent[c]);
           parent[c] = nw;
-          edge[c] = t.dist(c, px, py);
+          edge[c] = d;
+          cost.link(c, nw);
+          cost.a[c] = cost.a[nw] + d;
+          cost.depth[c] = cost.depth[nw] + 1;
+          cost.refresh_subtree(c, edge);
           rewires[3 * nrw] = nw;
           rewires[3 * nrw + 1] = c;
           rewires[3 * nrw + 2] = nw;
           ++nrw;
         }
       }
+    }
     if (travelled >= budget_portion) done = 1;
   }
   *travelled_io = travelled;

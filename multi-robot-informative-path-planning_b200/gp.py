@@ -31,10 +31,13 @@ __all__ = ["ConstantRBFKernel", "ConstantKernel", "RBF", "Matern", "GaussianProc
 
 def _chol_flags():
     """Measurement switches of the dataflow Cholesky: IPP_CHOL_HINTS=0 (no chain hand-over), IPP_CHOL_STATS=1 (per-CTA
-    task / cycle counters left in the scheduling scratch)."""
+    task / cycle counters left in the scheduling scratch), IPP_CHOL_WS=0 (the executor without warp specialisation),
+    IPP_CHOL_RED=0 (tile updates written back by load / subtract / store instead of reductions at the L2)."""
     st = os.environ.get("IPP_CHOL_STATS", "0")
     return ((1 if os.environ.get("IPP_CHOL_HINTS", "1") == "0" else 0) | (2 if st == "1" else 0) | (4 if st == "2" else 0)
-            | (8 if os.environ.get("IPP_CHOL_EAGER_SCAN", "0") == "1" else 0))
+            | (8 if os.environ.get("IPP_CHOL_EAGER_SCAN", "0") == "1" else 0)
+            | (16 if os.environ.get("IPP_CHOL_WS", "1") == "0" else 0)
+            | (32 if os.environ.get("IPP_CHOL_RED", "1") == "0" else 0))
 
 
 def chol_trace(ws, R):

@@ -43,18 +43,57 @@ def poisson_log_likelihood(theta: np.ndarray, obs_wp: np.ndarray, obs_vals: np.n
     return float(batched_poisson_log_likelihood(np.asarray(theta, dtype=float)[None, :], obs_wp, obs_vals, lambda_b, M)[0])
 
 
+_LOGPMF_DIRECT = None   # None: untested; True / False after the self-check
+_HOST_BLOCK = 16        # particles per block of the host expression: its temporaries stay in the CPU's caches
+
+
+def _logpmf_direct_ok() -> bool:
+    """scipy.stats.poisson.logpmf(k, mu) validates and masks its arguments (a third of the call at these sizes) and then
+    evaluates xlogy(k, mu) - gammaln(k + 1) - mu on the valid entries (scipy/stats/_discrete_distns.py, poisson_gen).
+    Checked once on this scipy for integer k >= 0 and mu > 0: the bare expression gives the same bits, including k = 0,
+    huge counts and the 1e-10 rate floor."""
+    global _LOGPMF_DIRECT
+    if _LOGPMF_DIRECT is None:
+        try:
+            from scipy.special import gammaln, xlogy
+            rng = np.random.RandomState(5)
+            k = np.concatenate([rng.poisson(10.0 ** rng.uniform(-1, 6, 4000)), [0, 0, 1, 2, 10 ** 7]]).astype(int)
+            mu = np.concatenate([10.0 ** rng.uniform(-3, 6.5, 4000), [1e-10, 3.7, 1e-10, 1e6, 1e7 + 0.5]])
+            a = poisson.logpmf(k[None, :], np.stack([mu, mu[::-1]]))
+            b = xlogy(k[None, :], np.stack([mu, mu[::-1]])) - gammaln(k + 1)[None, :] - np.stack([mu, mu[::-1]])
+            _LOGPMF_DIRECT = bool(np.array_equal(a, b))
+        except Exception:
+            _LOGPMF_DIRECT = False
+    return _LOGPMF_DIRECT
+
+
 def batched_poisson_log_likelihood(thetas: np.ndarray, obs_wp, obs_vals, lambda_b: float, M: int) -> np.ndarray:
-    """Log-likelihood of every row of `thetas` (N x 3M) in ONE array expression instead of the reference's Python
-    loop over particles (estimation.py:97) -- element for element the same numpy / scipy calls, hence the same bits.
+    """Log-likelihood of every row of `thetas` (N x 3M) in array expressions instead of the reference's Python loop over
+    particles (estimation.py:97) -- element for element the same numpy / scipy operations, hence the same bits.
     rate = lambda_b + sum_i A_i / max(d2, 1e-6).  Used for the values that leave this module and to re-decide a stage
-    whose draws fall inside the error band of the device likelihoods."""
+    whose draws fall inside the error band of the device likelihoods.  The particles go through in blocks (every row's
+    reductions are its own, so blocking changes nothing but the size of the temporaries), and where the self-check
+    above holds the Poisson term is evaluated directly, with gammaln(k + 1) once per observation."""
     obs_wp = np.array(obs_wp)
     counts = np.round(obs_vals).astype(int)
-    src = np.asarray(thetas, dtype=float).reshape(thetas.shape[0], M, 3)
-    d2 = (obs_wp[None, :, None, 0] - src[:, None, :, 0]) ** 2 + (obs_wp[None, :, None, 1] - src[:, None, :, 1]) ** 2
-    rate = lambda_b + np.sum(src[:, None, :, 2] / np.maximum(d2, 1e-6), axis=2)
-    rate = np.maximum(rate, 1e-10)
-    return np.sum(poisson.logpmf(counts[None, :], rate), axis=1)
+    thetas = np.asarray(thetas, dtype=float)
+    src = thetas.reshape(thetas.shape[0], M, 3)
+    direct = counts.size > 0 and counts.min() >= 0 and _logpmf_direct_ok()
+    if direct:
+        from scipy.special import gammaln, xlogy
+        lg = gammaln(counts + 1)
+    out = np.empty(src.shape[0])
+    ox, oy = obs_wp[None, :, None, 0], obs_wp[None, :, None, 1]
+    for b0 in range(0, src.shape[0], _HOST_BLOCK):
+        sb = src[b0:b0 + _HOST_BLOCK]
+        d2 = (ox - sb[:, None, :, 0]) ** 2 + (oy - sb[:, None, :, 1]) ** 2
+        rate = lambda_b + np.sum(sb[:, None, :, 2] / np.maximum(d2, 1e-6), axis=2)
+        rate = np.maximum(rate, 1e-10)
+        if direct:
+            out[b0:b0 + _HOST_BLOCK] = np.sum(xlogy(counts[None, :], rate) - lg[None, :] - rate, axis=1)
+        else:
+            out[b0:b0 + _HOST_BLOCK] = np.sum(poisson.logpmf(counts[None, :], rate), axis=1)
+    return out
 
 
 def stage_weights(ll: np.ndarray, gamma: float, n_samples: int) -> np.ndarray:

@@ -44,3 +44,20 @@ for q in range(4):
 f0 = ev[(ev[:, 1] == 0) & (ev[:, 2] == 0)]
 f0 = f0[np.argsort(f0[:, 3])]
 print("F(k) end times of problem 0 (us), every 8th:", [(int(k), round(t / 1e3)) for k, t in zip(f0[::8, 3], f0[::8, 5])])
+if os.environ.get("IPP_CHOL_WS", "1") != "0":  # the warp-specialised executor packs in-task marks into the index field
+    for q in (2, 3):
+        u = ev[ev[:, 1] == q]
+        if len(u):
+            w = u[:, 3]
+            first, loop, epi = (w & 0x3ff) * 0.064, ((w >> 10) & 0x3ff) * 0.064, ((w >> 20) & 0x3ff) * 0.064
+            tot = (u[:, 5] - u[:, 4]) / 1e3
+            print(f"queue {names[q]} inside the task (us, mean): first slab landed {first.mean():.2f}, main loop done {loop.mean():.2f}, "
+                  f"stores issued {epi.mean():.2f}, barrier passed {tot.mean():.2f}")
+    # gap between consecutive tasks of one CTA
+    gaps = []
+    for c in np.unique(ev[:, 0]):
+        e = ev[ev[:, 0] == c]
+        e = e[np.argsort(e[:, 4])]
+        gaps.append((e[1:, 4] - e[:-1, 5]) / 1e3)
+    g = np.concatenate(gaps)
+    print(f"gap between tasks of a CTA (us): median {np.median(g):.2f}, mean of those below 20 us {g[g < 20].mean():.2f}, share below 2 us {(g < 2).mean():.2f}")

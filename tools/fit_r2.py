@@ -66,6 +66,26 @@ def check():
         except Exception:
             ok = False
             traceback.print_exc()
+    section("warp-specialised executor == plain executor, bit for bit")
+    for n in (300, 1000, 2000, 5000):
+        try:
+            X, y = data(n)
+            got = {}
+            for wsf in ("0", "1", "red"):
+                os.environ["IPP_CHOL_WS"] = "0" if wsf == "0" else "1"
+                os.environ["IPP_CHOL_RED"] = "1" if wsf == "red" else "0"  # "1": warp-specialised, read-modify-write
+                gp = fixed_gp(X, y, "queue")
+                lml, gr = gp.log_marginal_likelihood(np.log([1.3, 1.7]), eval_gradient=True)
+                got[wsf] = (lml, gr, gp.L_)
+            os.environ["IPP_CHOL_WS"] = "1"
+            os.environ.pop("IPP_CHOL_RED")
+            same = all(got["0"][0] == got[k][0] and np.array_equal(got["0"][1], got[k][1]) and np.array_equal(got["0"][2], got[k][2])
+                       for k in ("1", "red"))
+            ok &= same
+            print(f"n={n}: identical {same} (lml {got['1'][0]:.12g})", flush=True)
+        except Exception:
+            ok = False
+            traceback.print_exc()
     section("batch == single, bit for bit")
     os.environ["IPP_CHOL"] = "queue"
     for n, R in ((300, 5), (1000, 3), (2000, 4), (5000, 3)):
@@ -213,7 +233,7 @@ def chol_only(n):
         ms = 1e3 * (time.perf_counter() - t) / 4
         out.append(f"R={R}: {ms / R:.3f} ms/problem ({R * NP ** 3 / 3 / ms / 1e9:.2f} TF)")
         del ws
-    print(f"n={n} NEAR={os.environ.get('IPP_CHOL_NEAR', 'default')} EAGER_SCAN={os.environ.get('IPP_CHOL_EAGER_SCAN', '0')} "
+    print(f"n={n} WS={os.environ.get('IPP_CHOL_WS', '1')} RED={os.environ.get('IPP_CHOL_RED', '1')} NEAR={os.environ.get('IPP_CHOL_NEAR', 'default')} EAGER_SCAN={os.environ.get('IPP_CHOL_EAGER_SCAN', '0')} "
           f"MB={os.environ.get('IPP_GEMM_MB', '1')}: " + "; ".join(out), flush=True)
 
 
