@@ -223,12 +223,18 @@ int ipp_host_norm2(int variant, const double* xy, int m, double* out);
  * 2: rig_tree_generation (:307-328); primitives nearest / steer / near / cost / rewire / add_node of
  * src/rrt/rrt_utils.py:59-105 with their first-minimum and strict-inequality semantics.  ws4 = {x0, x1, y0, y1};
  * step = steer's d_max_step, radius = near's distance.  rewires: rows {time = id of the inserted node, node,
- * new parent} appended from *n_rewires_io; scratch: capacity ints.  Outputs: pairs consumed, node count,
+ * new parent} appended from *n_rewires_io; scratch: capacity ints (the library keeps a uniform grid and per-node path
+ * costs of its own for the duration of the call).  Outputs: pairs consumed, node count,
  * finished (1 when the budget portion is spent).  Host pointers. */
 int ipp_host_tree_grow(int mode, int norm_variant, double* xy, long long* parent0, long long* parent, double* edge,
                        long long* nchild, int n, int capacity, const double* uniforms, int K, const double* ws4,
                        double step, double radius, double budget_portion, double* travelled_io, long long* rewires,
                        int rewire_cap, int* n_rewires_io, int* scratch, int* consumed, int* n_out, int* finished);
+
+/* Leaves of a tree in the depth-first order of the reference's traversal (rrt.py:389-395): from the root (node 0)
+ * through the children lists as they were at insertion (parent0; children in insertion order), a node without children
+ * is a leaf.  out: n ints; *n_leaves receives the count.  Host pointers. */
+int ipp_host_leaves_dfs(const long long* parent0, int n, int* out, int* n_leaves);
 
 #ifdef __cplusplus
 }

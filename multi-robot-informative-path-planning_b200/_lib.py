@@ -45,6 +45,7 @@ SIGNATURES = {
     "ipp_grid_metrics": [_D, _D, _D, _LL, _D, _D, _D],
     "ipp_poisson_loglik": [_D, _I, _I, _D, _D, _D, _I, _F, _D, _D],
     "ipp_host_norm2": [_I, _D, _I, _D],
+    "ipp_host_leaves_dfs": [_D, _I, _D, _D],
     "ipp_host_tree_grow": [_I, _I, _D, _D, _D, _D, _D, _I, _I, _D, _I, _D, _F, _F, _F, _D, _D, _I, _D, _D, _D, _D, _D],
 }
 

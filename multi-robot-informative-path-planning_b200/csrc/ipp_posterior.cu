@@ -556,6 +556,6 @@ int ipp_gp_posterior_points(const double* Wbuf, const double* vbuf, int n, doubl
   return launch_posterior(a, false, max_ctas, (cudaStream_t)stream);
 }
 
-int ipp_abi_version(void) { return 10; }
+int ipp_abi_version(void) { return 11; }
 
 }  // extern "C"

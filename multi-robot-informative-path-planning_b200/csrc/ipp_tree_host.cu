@@ -312,4 +312,27 @@ int ipp_host_tree_grow(int mode, int norm_variant, double* xy, long long* parent
 #undef IPP_GROW
 }
 
+int ipp_host_leaves_dfs(const long long* parent0, int n, int* out, int* n_leaves) {
+  if (!parent0 || n <= 0 || !out || !n_leaves) return -1;
+  // children in insertion order: a stable counting sort of the nodes by insertion-time parent
+  std::vector<int> start((size_t)n + 1, 0), kids((size_t)n > 1 ? (size_t)n - 1 : 0), fill, stack;
+  for (int i = 1; i < n; ++i) {
+    if (parent0[i] < 0 || parent0[i] >= n) return -1;
+    ++start[(size_t)parent0[i] + 1];
+  }
+  for (int i = 0; i < n; ++i) start[i + 1] += start[i];
+  fill.assign(start.begin(), start.end() - 1);
+  for (int i = 1; i < n; ++i) kids[fill[parent0[i]]++] = i;
+  int m = 0;
+  stack.push_back(0);
+  while (!stack.empty()) {
+    const int i = stack.back();
+    stack.pop_back();
+    if (start[i] == start[i + 1]) out[m++] = i;
+    for (int k = start[i + 1] - 1; k >= start[i]; --k) stack.push_back(kids[k]);   // first child on top
+  }
+  *n_leaves = m;
+  return 0;
+}
+
 }  // extern "C"

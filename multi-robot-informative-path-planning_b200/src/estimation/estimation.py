@@ -17,6 +17,7 @@ therefore the reference's, bit for bit; STATS counts how often the band was hit.
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Tuple
 
 import numpy as np
@@ -45,6 +46,16 @@ def poisson_log_likelihood(theta: np.ndarray, obs_wp: np.ndarray, obs_vals: np.n
 
 _LOGPMF_DIRECT = None   # None: untested; True / False after the self-check
 _HOST_BLOCK = 16        # particles per block of the host expression: its temporaries stay in the CPU's caches
+_HOST_THREADS = max(1, min(8, (os.cpu_count() or 1) - 1))
+_POOL = None
+
+
+def _host_pool():
+    global _POOL
+    if _POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _POOL = ThreadPoolExecutor(max_workers=_HOST_THREADS, thread_name_prefix="ipp-host-ll")
+    return _POOL
 
 
 def _logpmf_direct_ok() -> bool:
@@ -84,7 +95,8 @@ def batched_poisson_log_likelihood(thetas: np.ndarray, obs_wp, obs_vals, lambda_
         lg = gammaln(counts + 1)
     out = np.empty(src.shape[0])
     ox, oy = obs_wp[None, :, None, 0], obs_wp[None, :, None, 1]
-    for b0 in range(0, src.shape[0], _HOST_BLOCK):
+
+    def block(b0: int) -> None:
         sb = src[b0:b0 + _HOST_BLOCK]
         d2 = (ox - sb[:, None, :, 0]) ** 2 + (oy - sb[:, None, :, 1]) ** 2
         rate = lambda_b + np.sum(sb[:, None, :, 2] / np.maximum(d2, 1e-6), axis=2)
@@ -93,6 +105,14 @@ def batched_poisson_log_likelihood(thetas: np.ndarray, obs_wp, obs_vals, lambda_
             out[b0:b0 + _HOST_BLOCK] = np.sum(xlogy(counts[None, :], rate) - lg[None, :] - rate, axis=1)
         else:
             out[b0:b0 + _HOST_BLOCK] = np.sum(poisson.logpmf(counts[None, :], rate), axis=1)
+
+    starts = range(0, src.shape[0], _HOST_BLOCK)
+    if direct and src.shape[0] * counts.size >= 1 << 18 and _HOST_THREADS > 1:
+        # the blocks are independent rows of the same element-wise expression (numpy releases the GIL inside its loops)
+        list(_host_pool().map(block, starts))
+    else:
+        for b0 in starts:
+            block(b0)
     return out
 
 

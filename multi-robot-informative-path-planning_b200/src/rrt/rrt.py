@@ -267,6 +267,18 @@ def random_path_selection(self, agent_idx: int, current_position: Optional[np.nd
     return tree.path_to_root(int(leaves[k]))
 
 
+def _drop_leaves_at(tree, leaves: List[int], position) -> List[int]:
+    """[i for i in leaves if not np.array_equal(point(i), position)] of rrt.py:398-399 / 420 as one comparison (two
+    coordinates equal; a NaN coordinate is never equal, as in array_equal)."""
+    position = np.asarray(position)
+    if position.shape != (2,) or len(leaves) == 0:
+        return [i for i in leaves if not np.array_equal(tree.point(i), position)]
+    idx = np.asarray(leaves, dtype=np.int64)
+    pts = tree.points()[idx]
+    keep = ~((pts[:, 0] == position[0]) & (pts[:, 1] == position[1]))
+    return idx[keep].tolist()
+
+
 def informative_source_metric_path_selection(self, agent_idx: int, current_position: Optional[np.ndarray] = None,
                                              current_budget: Optional[float] = None) -> List[np.ndarray]:
     """rrt.py:380-436: argmax of node.information over the DFS-ordered leaves (first maximum wins)."""
@@ -277,7 +289,7 @@ def informative_source_metric_path_selection(self, agent_idx: int, current_posit
     if not leaves:
         return []
     if current_position is not None:
-        leaves = [i for i in leaves if not np.array_equal(tree.point(i), current_position)]
+        leaves = _drop_leaves_at(tree, leaves, current_position)
         if not leaves:
             return [current_position]
     if self.best_estimates.size == 0:
@@ -294,7 +306,7 @@ def informative_source_metric_path_selection(self, agent_idx: int, current_posit
             pick = leaves[int(cand[int(np.argmax(exact))])]
     possible_path = tree.path_to_root(pick)
     if len(possible_path) == 1 and np.array_equal(possible_path[0], current_position):
-        leaves = [i for i in leaves if not np.array_equal(tree.point(i), tree.point(pick))]
+        leaves = _drop_leaves_at(tree, leaves, tree.point(pick))
         if leaves:
             pick = leaves[np.random.choice(len(leaves))]
             possible_path = tree.path_to_root(pick)

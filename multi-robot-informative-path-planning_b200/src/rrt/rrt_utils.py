@@ -410,6 +410,18 @@ class TreeArrays:
     def leaves_dfs(self) -> List[int]:
         """Leaves reached from the root through the insertion-time `children` lists, depth first
         (rrt.py:389-395)."""
+        if NATIVE_GROWTH and self.n > 256:   # the same traversal natively: a tree of the reference's example config has
+            try:                              # ~18 000 nodes, 50 ms per call in the loop below
+                from mripp_b200 import _lib
+                import ctypes as C
+                lib = _lib.load()
+                out = np.empty(self.n, dtype=np.int32)
+                m = C.c_int(0)
+                p0 = np.ascontiguousarray(self.parent0[: self.n], dtype=np.int64)
+                if lib.ipp_host_leaves_dfs(p0.ctypes.data, self.n, out.ctypes.data, C.addressof(m)) == 0:
+                    return out[: m.value].tolist()
+            except Exception:
+                pass
         kids: List[List[int]] = [[] for _ in range(self.n)]
         for i in range(1, self.n):
             kids[self.parent0[i]].append(i)

@@ -24,7 +24,7 @@ def test_header_library_and_binding_agree():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in ipp_b200.h but not exported"
     assert sorted(_lib.SIGNATURES) == names
-    assert lib.ipp_abi_version() == 10
+    assert lib.ipp_abi_version() == 11
 
 
 def test_layout_is_host_only_and_consistent():
