@@ -2,7 +2,9 @@
 chol_queue_kernel): a discrete-event simulation of the kernel's own claiming rules -- chain queues with a ready
 frontier, claimed by atomicAdd on a stale view (so that racing claims overshoot the frontier and are HELD), the bulk
 queue claimed in order unconditionally, successor hints -- over random CTA counts, task durations and polling
-orders.  It checks what the device cannot tell us cheaply:
+orders, once with the rules of chol_queue_kernel and once with those of chol_queue_ws_kernel on top (the next task
+claimed while a tile update is still running; chain-class tasks only while no CTA is idle).  It checks what the device
+cannot tell us cheaply:
 
 * no deadlock for any number of resident CTAs (1 included);
 * every block receives every panel to its left exactly once, in ascending order, before it is factored / solved;
@@ -33,8 +35,11 @@ def build_plan(n, near):
 
 
 class Sim:
-    def __init__(self, plan, R, n_ctas, seed, hints=True):
+    def __init__(self, plan, R, n_ctas, seed, hints=True, ws=False):
         self.p, self.R, self.rng, self.hints = plan, R, random.Random(seed), hints
+        # ws: the rules of chol_queue_ws_kernel on top -- a CTA in a tile update claims its NEXT task before the current
+        # one is finished (queue 3 freely; a chain-class task only while no CTA is idle), never after an F / S task
+        self.ws, self.idle_now = ws, 0
         self.nb, self.nrb, self.tb = int(plan[PH_NB]), int(plan[PH_NRB]), int(plan[PH_TB])
         self.cnt = [int(plan[PH_NF + q]) for q in range(4)]
         self.off = [int(plan[PH_OFFF + q]) for q in range(4)]
@@ -47,7 +52,7 @@ class Sim:
         self.final = [set() for _ in range(R)]
         self.parts = [dict() for _ in range(R)]
         self.writing = [dict() for _ in range(R)]
-        self.ctas = [dict(hint=None, busy_until=0, task=None, blocked=None, scan=None, rot=c % R, idle_r=c % R)
+        self.ctas = [dict(hint=None, busy_until=0, task=None, blocked=None, scan=None, rot=c % R, idle_r=c % R, next=None)
                      for c in range(n_ctas)]
         self.executed = 0
 
@@ -135,24 +140,32 @@ class Sim:
                 moved = True
         return moved
 
-    def acquire(self, cta, now, snap):
+    def launch(self, cta, q, i, r, now, ahead):
+        if ahead:
+            assert self.ready(self.task(q, i), r)   # a task handed over early is complete in its dependencies
+            cta["next"] = (q, i, r)
+        else:
+            self.start(cta, q, i, r, now)
+
+    def acquire(self, cta, now, snap, ahead=False):
         """One polling round of one CTA against the queue state `snap` = (heads, frontiers) as it was at the start of
         the tick (every CTA of a tick decides on the same stale view, like concurrent pollers on the device): frontier
         scan if the last task asked for one, held task, hint, then an atomicAdd claim from the first queue (priority
         F, S, C, U; problems rotated by CTA) whose head is behind its frontier -- landing beyond the frontier the
         task is HELD -- else a scan of one problem after the other.  Returns 'exit', 'idle' or 'started'."""
         heads0, front0 = snap
-        if cta["scan"] is not None:
+        chain_ok = (not ahead) or self.idle_now == 0    # busy CTA: chain-class tasks only while nobody is idle
+        if cta["scan"] is not None and not ahead:
             self.scan(cta["scan"])
             cta["scan"] = None
             front0 = self.front.copy()
         if cta["blocked"] is not None:  # a task claimed past the frontier: held, tested first, the CTA keeps serving
             q, h, r = cta["blocked"]
-            if self.ready(self.task(q, h), r):
+            if self.ready(self.task(q, h), r) and (q == 3 or chain_ok):
                 cta["blocked"] = None
-                self.start(cta, q, h, r, now)
+                self.launch(cta, q, h, r, now, ahead)
                 return "started"
-        if cta["hint"] is not None:
+        if cta["hint"] is not None and not ahead:
             q, i, r = cta["hint"]
             cta["hint"] = None
             if self.heads[r, q] == i and self.ready(self.task(q, i), r):
@@ -171,22 +184,26 @@ class Sim:
             q, j = divmod(c, self.R)
             r = (j + rot) % self.R
             if heads0[r, q] < front0[r, q]:
+                if q != 3 and not chain_ok:
+                    continue
                 if cta["blocked"] is None:
                     h = int(self.heads[r, q])  # atomicAdd on the live head
                     self.heads[r, q] += 1
                     if h >= self.cnt[q]:
                         return "idle"
                     if h < front0[r, q] or self.ready(self.task(q, h), r):
-                        self.start(cta, q, h, r, now)
+                        self.launch(cta, q, h, r, now, ahead)
                         return "started"
                     cta["blocked"] = (q, h, r)
                     return "idle"
                 h = int(heads0[r, q])  # holding: compare-and-swap on exactly the head seen
                 if self.heads[r, q] == h:
                     self.heads[r, q] += 1
-                    self.start(cta, q, h, r, now)
+                    self.launch(cta, q, h, r, now, ahead)
                     return "started"
                 return "idle"
+        if ahead:
+            return "idle"
         if exhausted:
             return "exit"
         for _ in range(self.R):
@@ -203,13 +220,23 @@ class Sim:
             progressed = False
             self.rng.shuffle(live)
             snap = (self.heads.copy(), self.front.copy())
+            self.idle_now = sum(1 for c in live if self.ctas[c]["task"] is None)
             for c in list(live):
                 cta = self.ctas[c]
                 if cta["task"] is not None:
                     if cta["busy_until"] <= now:
                         self.finish(cta)
                         progressed = True
+                        if cta["next"] is not None:      # the task claimed ahead starts at once
+                            q, i, r = cta["next"]
+                            cta["next"] = None
+                            self.start(cta, q, i, r, now)
+                            continue
                     else:
+                        if self.ws and cta["next"] is None and int(cta["task"][0][TK_TYPE]) == 2 and self.rng.random() < 0.5:
+                            before = (self.heads.sum(), self.front.sum())
+                            if self.acquire(cta, now, snap, ahead=True) == "started" or before != (self.heads.sum(), self.front.sum()):
+                                progressed = True
                         continue
                 before = (self.heads.sum(), self.front.sum())
                 res = self.acquire(cta, now, snap)
@@ -240,6 +267,7 @@ def test_plan_is_deadlock_free_and_complete(n, near, R, n_sim):
     assert plan[PH_MAGIC] == 0x43485132 and plan[PH_TS] == TS and plan[PH_TOTAL] == len(plan)
     for seed in range(2):
         Sim(plan, R, n_sim, seed, hints=bool(seed % 2 == 0)).run()
+        Sim(plan, R, n_sim, seed + 7, hints=bool(seed % 2 == 0), ws=True).run()
 
 
 def test_plan_shape_at_c4():

@@ -294,3 +294,82 @@ def test_main_configuration_helpers(tmp_path):
                           "specific_params": {"1": [3, 4, 500000]}}], "strategies": [], "args": {"seed": 5, "lazy_gp": True}}
     (sc,) = M.initialize_scenarios(cfg, gp_factory=FastGP)
     assert sc.workspace_size == (0, 12, 0, 8) and list(sc.sources[0]) == [3, 4, 500000]      # 2-tuple widened; source 1 pinned
+
+
+# ---------------------------------------------------------------------------------------------------
+# round 2, late: the host loops that bound the reference's own example config
+# ---------------------------------------------------------------------------------------------------
+def test_native_leaf_order_and_leaf_filter_equal_the_python_forms(monkeypatch):
+    """ipp_host_leaves_dfs against the Python traversal of rrt.py:389-395 on a grown tree with rewires (the DFS runs over
+    the insertion-time children lists), and the vectorised leaf filter against the reference's list comprehension."""
+    np.random.seed(5)
+    t = U.TreeArrays(np.array([20.0, 20.0]))
+    assert t.grow_native(2, (0, 40, 0, 40), 1.0, 1.0, 700.0) is not None
+    assert t.n > 256 and len(t.rewires) > 0
+    fast = t.leaves_dfs()
+    monkeypatch.setattr(U, "NATIVE_GROWTH", False)
+    slow = t.leaves_dfs()
+    assert fast == slow and all(isinstance(i, int) for i in fast)
+    assert sorted(fast) == t.leaves_in_order().tolist()
+    for pos in (t.point(fast[3]).copy(), np.array([1.0, 2.0]), np.array([np.nan, 2.0])):
+        want = [i for i in fast if not np.array_equal(t.point(i), pos)]
+        assert R._drop_leaves_at(t, fast, pos) == want
+    assert len(R._drop_leaves_at(t, fast, t.point(fast[3]))) == len(fast) - 1
+
+
+def test_dense_tree_growth_with_grid_and_cached_costs_equals_python_loops(monkeypatch):
+    """The grid-accelerated nearest / near scans and the bounded path-cost shortcut of ipp_host_tree_grow against the
+    reference's all-pairs loops on a DENSE tree (radius and step 1.0 in a 12 x 12 workspace: ~10 nodes per unit area,
+    tens of near nodes per insertion, hundreds of rewires), continued over several calls."""
+    res = []
+    for native in (False, True):
+        monkeypatch.setattr(U, "NATIVE_GROWTH", native)
+        sc, make = _strategy(R.MR_IPP, 12, 5, budget=120, d_waypoint_distance=1.0, num_agents=1, budget_iter=4)
+        np.random.seed(3)
+        st = make()
+        st.best_estimates = np.array([[3.0, 9.0, 5e5]])
+        start = np.array([6.0, 6.0])
+        st.agents_obs_wp = [[start.copy()]]
+        st.agents_full_path = [[start.copy()]]
+        st.initialize_trees(start, 0)
+        for b in (400.0, 250.0):
+            R.rig_tree_generation(st, b, 0, gain_function=R.point_source_gain_all)
+        t = st.trees_soa[0]
+        res.append((t.points().copy(), t.parent0[: t.n].copy(), t.parent[: t.n].copy(), t.edge[: t.n].copy(),
+                    t.nchild[: t.n].copy(), list(t.rewires), np.random.uniform(size=3)))
+    a, b = res
+    assert len(a[0]) == len(b[0]) > 1200 and len(a[5]) > 300
+    for x, y in zip(a[:5], b[:5]):
+        assert np.array_equal(x, y)
+    assert a[5] == b[5] and np.array_equal(a[6], b[6])
+
+
+def test_host_likelihood_fast_path_keeps_scipy_bits():
+    """batched_poisson_log_likelihood (blocks of particles, threads, the bare xlogy - gammaln - mu expression) against the
+    reference's per-particle scipy call (estimation.py:15-55), bit for bit, including a zero count and the rate floor."""
+    from scipy.stats import poisson
+    from mripp_b200.src.estimation import estimation as E
+
+    rng = np.random.RandomState(2)
+    n, N, M = 700, 420, 2     # 420 x 700 >= 2^18: the threaded path
+    obs = rng.uniform(0, 40, (n, 2))
+    vals = rng.poisson(30.0, n).astype(float)
+    vals[:3] = 0.0
+    th = rng.uniform(0, 40, (N, 3 * M))
+    th[:, 2::3] = rng.uniform(1e3, 1e6, (N, M))
+    th[0, 2::3] = 0.0          # no signal at all: rate = lambda_b
+    assert E._logpmf_direct_ok()
+    got = E.batched_poisson_log_likelihood(th, obs, vals, 1.0, M)
+
+    def reference_one(theta):   # the reference's own function body
+        sources = theta.reshape(M, 3)
+        d2 = (obs[:, None, 0] - sources[:, 0]) ** 2 + (obs[:, None, 1] - sources[:, 1]) ** 2
+        rate = 1.0 + np.sum(sources[:, 2] / np.maximum(d2, 1e-6), axis=1)
+        return np.sum(poisson.logpmf(np.round(vals).astype(int), np.maximum(rate, 1e-10)))
+
+    for i in (0, 1, 17, 255, 256, 419):
+        assert got[i] == reference_one(th[i]), i
+    # a negative count falls back to scipy's own masking (-inf), not to the bare expression
+    vals2 = vals.copy()
+    vals2[5] = -1.0
+    assert np.all(np.isneginf(E.batched_poisson_log_likelihood(th[:4], obs, vals2, 1.0, M)))

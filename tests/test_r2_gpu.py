@@ -309,3 +309,32 @@ def test_main_uses_device_metrics(monkeypatch):
     cfg2["args"]["show"] = True
     assert not getattr(M.initialize_scenarios(cfg2)[0], "device_outputs", False)
     assert DeviceField is not None
+
+
+# ---------------------------------------------------------------------------------------------------
+# G2: the executors of the dataflow Cholesky are interchangeable bit for bit
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [700, 1700, 2600])
+def test_cholesky_executors_agree_bit_for_bit(G, monkeypatch, n):
+    """chol_queue_ws_kernel (scheduler / copy / DMMA warps; tile updates written back as RED.ADD.F64 or by load / subtract /
+    store) against chol_queue_kernel (every warp does everything): the same plan, the same DMMA order inside every task,
+    one writer per tile at a time -- so the factor, alpha, the LML and its gradient must be the same bits, alone and as
+    one of several problems in a batch."""
+    from bench import synth_observations
+
+    X, meas, _ = synth_observations(n, max(10, int(np.sqrt(n) * 1.4)), 0)
+    y = np.log10(meas)
+    th = np.log([1.3, 1.7])
+    got = {}
+    for name, ws, red in (("plain", "0", "1"), ("ws_rmw", "1", "0"), ("ws_red", "1", "1")):
+        monkeypatch.setenv("IPP_CHOL_WS", ws)
+        monkeypatch.setenv("IPP_CHOL_RED", red)
+        gp = _fixed_gp(G, X, y, th)
+        lml, gr = gp.log_marginal_likelihood(th, eval_gradient=True)
+        wsp = G._Workspace().ensure(n, slots=3)
+        batch = gp._eval_batch(wsp, [2, 0, 1], [th, th + 0.3, th - 0.2], True)
+        got[name] = (float(lml), gr.copy(), gp.L_.copy(), gp.alpha_.copy(), np.array(batch, dtype=float))
+    for name in ("ws_rmw", "ws_red"):
+        for a, b in zip(got["plain"], got[name]):
+            assert np.array_equal(a, b), name
+    assert got["plain"][4][0][0] == got["plain"][0]    # batch member == single evaluation
