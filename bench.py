@@ -484,6 +484,10 @@ def run_b200(args, wl, rank, world, local_rank):
     torch.cuda.synchronize()
     full_fit = {"seconds": time.perf_counter() - t0, "lml_evals": gpf.n_lml_evals_ - ev0,
                 "theta_c_l": [gpf.kernel_.constant_value, gpf.kernel_.length_scale], "mode": "lockstep batch (dataflow Cholesky)"}
+    rounds = list(getattr(gpf, "lockstep_rounds_", []))
+    if rounds:  # how many launch sequences, and how many objective evaluations ran in batches of which size
+        full_fit["lockstep_rounds"] = len(rounds)
+        full_fit["evaluations_by_batch_size"] = {str(k): int(k * rounds.count(k)) for k in sorted(set(rounds), reverse=True)}
     # the lattice posterior of THAT fitted state (the block-sparse kernel's cost depends on the length scale)
     for _ in range(2):
         gpf.predict_grid_device(0, W, nx, 0, W, ny, want_zpred=True, out=out)

@@ -692,6 +692,7 @@ class GaussianProcessRegressor:
         stream = torch.cuda.current_stream()
         cond = threading.Condition()
         requests, results, live, outs, errors = {}, {}, set(range(R)), [None] * R, []
+        self.lockstep_rounds_ = []
 
         def run(i):
             def obj_func(theta, eval_gradient=True):
@@ -728,6 +729,7 @@ class GaussianProcessRegressor:
                     break
                 batch = sorted(requests)
                 reqs = [requests.pop(i) for i in batch]
+            self.lockstep_rounds_.append(len(batch))  # batch size of every launch sequence (reported by bench.py)
             try:
                 with torch.cuda.device(device), torch.cuda.stream(stream):
                     res = self._eval_batch(ws, batch, [r[0] for r in reqs], any(r[1] for r in reqs))

@@ -799,7 +799,7 @@ def test_particle_log_likelihood_within_its_bound(n, N, M):
     want = E.batched_poisson_log_likelihood(thetas, list(obs), list(meas), 1, M)
     bound = E.EPS * (E.C_TERM * s1 + E.c_sum(n) * s2)
     assert np.all(np.isfinite(ll)) and np.all(bound > 0)
-    assert np.all(np.abs(ll - want) <= 0.25 * bound), float(np.max(np.abs(ll - want) / bound))
+    assert np.all(np.abs(ll - want) <= 0.6 * bound), float(np.max(np.abs(ll - want) / bound))
     assert np.all(bound <= 1e-12 * s1 + 1e-300)   # the band stays narrow: about 1e4 eps of the pieces' magnitude
     if N > 2:
         assert ll[1] == ll[2]

@@ -373,3 +373,25 @@ def test_host_likelihood_fast_path_keeps_scipy_bits():
     vals2 = vals.copy()
     vals2[5] = -1.0
     assert np.all(np.isneginf(E.batched_poisson_log_likelihood(th[:4], obs, vals2, 1.0, M)))
+
+
+def test_exact_close_counts_many_points_equal_the_scalar_loop():
+    """count_close_exact_many (one array pass per branch, observation lists converted once) against the reference's
+    double loop `np.linalg.norm(point - obs) < d` (rrt.py:246-252), with observations exactly at, one ulp inside and one
+    ulp outside the threshold; the cached conversion follows a growing list."""
+    from mripp_b200 import exact as E
+
+    rng = np.random.RandomState(4)
+    d = 2.5
+    pts = rng.uniform(0, 30, (150, 2))
+    obs_a = [rng.uniform(0, 30, 2) for _ in range(400)]
+    obs_b = []
+    for p in pts[:40]:   # threshold cases: a 3-4-5 triangle scaled to d, and its neighbours in floating point
+        q = p + np.array([1.5, 2.0])
+        obs_b += [q, np.nextafter(q, q + 1), np.nextafter(q, q - 1)]
+    lists = [obs_a, [], obs_b]
+    want = np.array([sum(1 for ob in lists for o in ob if np.linalg.norm(p - o) < d) for p in pts])
+    assert np.array_equal(E.count_close_exact_many(pts, lists, d), want)
+    assert E.count_close_exact(pts[7], lists, d) == want[7]
+    obs_a.append(pts[3] + 0.1)           # the list grows: the cached array must not be reused
+    assert E.count_close_exact(pts[3], lists, d) == want[3] + 1
