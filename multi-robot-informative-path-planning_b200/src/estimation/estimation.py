@@ -38,7 +38,10 @@ STATS = {"stages": 0, "redecided": 0, "device_evaluations": 0, "why_nonfinite": 
 
 
 def c_sum(n: int) -> float:
-    return float(np.ceil(n / 256.0) + 8.0 + 24.0 + max(0.0, np.ceil(np.log2(max(n, 1) / 8192.0))))
+    """Summation part of the bound in units of EPS: (additions in sequence on the device + on the host) * EPS / 2, with
+    1 % for the second-order terms (round 1 charged a whole EPS per addition)."""
+    depth = np.ceil(n / 256.0) + 8.0 + 24.0 + max(0.0, np.ceil(np.log2(max(n, 1) / 8192.0)))
+    return float(0.505 * depth)
 
 
 def poisson_log_likelihood(theta: np.ndarray, obs_wp: np.ndarray, obs_vals: np.ndarray, lambda_b: float, M: int) -> float:

@@ -319,6 +319,9 @@ class TreeArrays:
                 self.rewires.extend(map(tuple, rewires[: n_rw.value].tolist()))
             if finished.value:
                 return samples
+            # the library rebuilds its grid and path costs from the tree on every call: let the blocks grow with the
+            # tree (the reference's example config grows 18 000-node trees: 72 blocks of 256 were 72 rebuilds)
+            block = min(2 * block, 8192)
 
     def points(self) -> np.ndarray:
         return self._xy[: self.n]
