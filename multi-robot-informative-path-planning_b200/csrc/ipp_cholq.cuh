@@ -629,10 +629,11 @@ __global__ void __launch_bounds__(C::THREADS, 1) chol_queue_kernel(CholQ a) {
 //                warps have issued the last slab of task n - 1 (named barrier A: the DMMA warps are then <= 4 slabs +
 //                epilogue from the end), and hands the task over through a two-slot mailbox (mbarrier for the DMMA
 //                warps, named barrier B for the copy warps).
-// Rules that keep the critical chain as fast as before: a chain-class task (F, S, front tile) is never claimed while
-// the DMMA warps are busy (another CTA may be free for it right now; this CTA takes it, if it is still there, the
-// moment its own tile is done), and after an F or S task -- which use the ring's shared memory as scratch and hand
-// their successor to the same CTA -- the next claim waits for the task to finish, as in chol_queue_kernel.
+// Rules that keep the critical chain as fast as before: a chain-class task (F, S, front tile) is claimed ahead only
+// while no CTA is idle (an idle one starts it now, this one in up to 13 us), and after a task that hands its successor
+// to the same CTA (F, the critical S) the next claim waits for the task to finish -- the successor is not ready
+// before.  F and S use the ring's shared memory as scratch: a tile update claimed while one of them runs is loaded
+// when it has finished.
 // Every wait is bounded (trap) or under the scheduler's watchdog: a protocol bug ends the kernel, it cannot hang it.
 constexpr int WS_STAGES = 4;
 constexpr int WS_LOADERS = 96;
@@ -688,27 +689,40 @@ __global__ void __launch_bounds__(C::THREADS + 128, 1) chol_queue_ws_kernel(Chol
       int hint_q = -1, hint_i = 0, hint_r = 0;
       int held_q = -1, held_i = 0, held_r = 0;
       int scan_r = -1, idle_r = rot;
-      int pend_scan = -1, pend_scan2 = -1, pend_hq = -1, pend_hi = 0, pend_hr = 0;  // what the tasks in flight enable once done
+      // What the two tasks in flight enable once they are done (A: task n - 1, B: task n - 2): their problem's frontiers
+      // (a chain task, or a tile close behind the front) and, after F and the critical S, the successor on the chain.
+      int pa_task = -1, pa_scan = -1, pa_hq = -1, pa_hi = 0, pa_hr = 0;
+      int pb_task = -1, pb_scan = -1;
       int scan_r2 = -1;
-      bool pend = false;
-      int n = 0, prev_q = -1;
+      int n = 0;
       for (;;) {
         ws_pair_sync();  // (A) the copy warps have issued everything of task n - 1
-        // mailbox slot n & 1 was task n - 2's; after a chain task also wait for the task itself
-        ws_wait_done(&s_done, (prev_q >= 0 && prev_q != 3) ? n : n - 1);
+        // mailbox slot n & 1 was task n - 2's; a task that hands its successor to this CTA (F, the critical S) is
+        // waited for -- the successor is not ready before.  After any other task the next one is claimed while it runs.
+        ws_wait_done(&s_done, (pa_task >= 0 && pa_hq >= 0) ? n : n - 1);
         int got_q = -1, got_i = 0, got_r = 0;
         unsigned backoff = 0;
         long long idle_since = 0;
         bool idle = false, counted_idle = false;
         for (;;) {
-          const bool ahead = __shfl_sync(0xffffffffu, (int)s_done, 0) < n;  // the DMMA warps are still in task n - 1
-          if (!ahead && pend) {
-            pend = false;
-            scan_r = pend_scan;
-            scan_r2 = pend_scan2;
-            hint_q = pend_hq;
-            hint_i = pend_hi;
-            hint_r = pend_hr;
+          const int dn = __shfl_sync(0xffffffffu, (int)s_done, 0);
+          const bool ahead = dn < n;  // the DMMA warps are still in task n - 1
+          if (pb_task >= 0 && dn > pb_task) {
+            pb_task = -1;
+            if (pb_scan >= 0) {
+              if (scan_r < 0) scan_r = pb_scan;
+              else if (scan_r2 < 0) scan_r2 = pb_scan;
+            }
+          }
+          if (pa_task >= 0 && dn > pa_task) {
+            pa_task = -1;
+            if (pa_scan >= 0) {
+              if (scan_r < 0) scan_r = pa_scan;
+              else if (scan_r2 < 0) scan_r2 = pa_scan;
+            }
+            hint_q = pa_hq;
+            hint_i = pa_hi;
+            hint_r = pa_hr;
           }
           int special = 0;
           if (lane == 6 && hint_q >= 0) {
@@ -853,18 +867,17 @@ __global__ void __launch_bounds__(C::THREADS + 128, 1) chol_queue_ws_kernel(Chol
         if (got_q >= 0) {
           const int* T = plan + __ldg(plan + PH_OFFF + got_q) + got_i * PLAN_TS;
           const int type = __ldg(T + TK_TYPE), g = __ldg(T + TK_G);
-          pend_scan2 = pend ? pend_scan : -1;  // task n - 1 is still running: its scan waits with this one's
-          pend = true;
-          pend_scan = (got_q != 3 || __ldg(T + TK_B) * (C::BM / BLK) - __ldg(T + TK_D) <= 6) ? got_r : -1;
-          if (pend_scan < 0) {
-            pend_scan = pend_scan2;
-            pend_scan2 = -1;
+          if (pa_task >= 0) {  // task n - 1 is still running: keep its scan (task n - 2 is done: applied above)
+            pb_task = pa_task;
+            pb_scan = pa_scan;
           }
-          pend_hq = -1;
+          pa_task = n;
+          pa_scan = (got_q != 3 || __ldg(T + TK_B) * (C::BM / BLK) - __ldg(T + TK_D) <= 6) ? got_r : -1;
+          pa_hq = -1;
           if (a.use_hints && g >= 0 && (type == PT_F || type == PT_S)) {
-            pend_hq = type == PT_F ? 1 : 0;
-            pend_hi = g;
-            pend_hr = got_r;
+            pa_hq = type == PT_F ? 1 : 0;
+            pa_hi = g;
+            pa_hr = got_r;
           }
         }
         if (lane == 0) {
@@ -893,19 +906,24 @@ __global__ void __launch_bounds__(C::THREADS + 128, 1) chol_queue_ws_kernel(Chol
         if (lane == 0) mbar_arrive(&bar_task[n & 1]);
         ws_pair_sync();  // (B) mailbox n & 1 is valid for the copy warps
         if (got_q < 0) break;
-        prev_q = got_q;
         ++n;
       }
     } else {
       // ------------------------------------------------------------------------------------------ copy warps
       const int lt = t - (C::THREADS + 32);  // 0..95
       unsigned gslab = 0;
+      int prev_type = PT_U;
       for (int n = 0;; ++n) {
         ws_pair_sync();  // (A)
         ws_pair_sync();  // (B)
         const int* m = s_task[n & 1];
         if (m[0] < 0) break;
+        const int after = prev_type;
+        prev_type = m[3];
         if (m[3] != PT_U) continue;
+        // an F or S task uses the ring as scratch: a tile update claimed while it was still running is loaded only
+        // when it has finished
+        if (after != PT_U) ws_wait_done(&s_done, n);
         const double* A = a.K + (long)m[10] * a.pstride;
         const int row0 = m[4] * C::BM, col0 = m[5] * C::BN, kb = m[6] * BLK, ke = m[7] * BLK, cmin = m[8] * BLK;
         if (!a.red_epilogue) {  // start pulling the C tile into L2 for the read-modify-write at the end

@@ -38,7 +38,8 @@ class Sim:
     def __init__(self, plan, R, n_ctas, seed, hints=True, ws=False):
         self.p, self.R, self.rng, self.hints = plan, R, random.Random(seed), hints
         # ws: the rules of chol_queue_ws_kernel on top -- a CTA in a tile update claims its NEXT task before the current
-        # one is finished (queue 3 freely; a chain-class task only while no CTA is idle), never after an F / S task
+        # one is finished (queue 3 freely; a chain-class task only while no CTA is idle), except during a task that hands
+        # its successor to the same CTA
         self.ws, self.idle_now = ws, 0
         self.nb, self.nrb, self.tb = int(plan[PH_NB]), int(plan[PH_NRB]), int(plan[PH_TB])
         self.cnt = [int(plan[PH_NF + q]) for q in range(4)]
@@ -233,7 +234,9 @@ class Sim:
                             self.start(cta, q, i, r, now)
                             continue
                     else:
-                        if self.ws and cta["next"] is None and int(cta["task"][0][TK_TYPE]) == 2 and self.rng.random() < 0.5:
+                        T_cur = cta["task"][0]
+                        hands_over = self.hints and int(T_cur[TK_TYPE]) in (0, 1) and int(T_cur[TK_G]) >= 0
+                        if self.ws and cta["next"] is None and not hands_over and self.rng.random() < 0.5:
                             before = (self.heads.sum(), self.front.sum())
                             if self.acquire(cta, now, snap, ahead=True) == "started" or before != (self.heads.sum(), self.front.sum()):
                                 progressed = True
