@@ -414,6 +414,35 @@ def run_b200(args, wl, rank, world, local_rank):
     assert sparse_diff["max_abs_mean"] <= 1e-12 * max(1.0, float(de[0].abs().max())) and sparse_diff["max_abs_std"] <= 1e-12, sparse_diff
     del sp, de
 
+    # ---- (1b) the same posterior at EXPLICIT points (gp.predict on an arbitrary point set; G6) -------------------
+    # two waves of 128-query tiles; generic kernel (exp() per row block of W) against the cross-covariance table +
+    # lattice pipeline, dense and with slab skipping along the Z-order curve of the queries
+    m_pts = 2 * 128 * torch.cuda.get_device_properties(local_rank).multi_processor_count
+    Qd = torch.from_numpy(np.random.RandomState(7).uniform(0, W, (m_pts, 2))).cuda()
+
+    def points_ms(**kw):
+        for _ in range(2):
+            gp.predict_points_device(Qd, **kw)
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for _ in range(3):
+            r_ = gp.predict_points_device(Qd, **kw)
+        p1.record()
+        torch.cuda.synchronize()
+        return p0.elapsed_time(p1) / 3, r_
+
+    pts_generic_ms, r_gen = points_ms(tabled=False)
+    pts_dense_ms, r_den = points_ms(tabled=True, skip_below=0)
+    pts_sparse_ms, r_spa = points_ms(tabled=True)
+    pts_diff = {"tabled_dense_vs_generic_std": float((r_den[1] - r_gen[1]).abs().max()),
+                "tabled_sparse_vs_dense_std": float((r_spa[1] - r_den[1]).abs().max()),
+                "tabled_sparse_vs_dense_mean": float((r_spa[0] - r_den[0]).abs().max())}
+    assert pts_diff["tabled_dense_vs_generic_std"] <= 1e-7 and pts_diff["tabled_sparse_vs_dense_std"] <= 1e-12, pts_diff
+    first_rb = n % 128
+    rlims = ([first_rb] if first_rb else []) + [first_rb + 128 * j for j in range(1, n // 128 + 1)]
+    pts_dense_flops = (m_pts // 128) * sum((r + 15) // 16 for r in rlims) * 2.0 * 128 * 128 * 16
+    del Qd, r_gen, r_den, r_spa
+
     # ---- (2) end to end through the public API with host buffers: the STOCK call ---------------------
     # PointSourceField.predict_spatial_field as the reference's constructor configures it (point_source.py:71:
     # n_restarts_optimizer=10, normalize_y=True): upload, 11 L-BFGS-B runs in lockstep on the batched objective,
@@ -818,6 +847,16 @@ def run_b200(args, wl, rank, world, local_rank):
                                             "sample": f"{E_ref} objective evaluations (the unmodified reference's count, "
                                                       f"profiles/reference_fit_evals.json) x {cpu_post['lml_grad_eval_ms']:.0f} ms "
                                                       f"measured here + the whole lattice at the rate above"}},
+            "explicit_points": {"points": m_pts, "call": "gp.predict_points_device (what gp.predict(X, return_std=True) runs for "
+                                                         "an arbitrary point set), device resident, same fitted state",
+                                "generic_kernel": {"ms": pts_generic_ms, "value": world * m_pts / (pts_generic_ms * 1e-3), "unit": UNIT,
+                                                   "frac_of_fp64_peak": pts_dense_flops / (pts_generic_ms * 1e-3) / 1e12 / peak64},
+                                "tabled_dense": {"ms": pts_dense_ms, "value": world * m_pts / (pts_dense_ms * 1e-3), "unit": UNIT,
+                                                 "frac_of_fp64_peak": pts_dense_flops / (pts_dense_ms * 1e-3) / 1e12 / peak64},
+                                "tabled_block_sparse": {"ms": pts_sparse_ms, "value": world * m_pts / (pts_sparse_ms * 1e-3),
+                                                        "unit": UNIT, "note": "queries along the Z-order curve, slabs of k* below "
+                                                                              "1e-30 c skipped; includes the sort and the un-permute"},
+                                "max_abs_differences": pts_diff},
             "fit": {"lml_grad_eval_ms": lml_ms, "lml_grad_evals_per_s": 1e3 / lml_ms,
                     "tflops": float(NP) ** 3 / (lml_ms * 1e-3) / 1e12,
                     "batch_of_11": {"ms_per_launch": lml_batch_ms, "ms_per_problem": lml_batch_ms / 11,

@@ -130,6 +130,21 @@ int ipp_gp_posterior_points(const double* Wbuf, const double* vbuf, int n, doubl
                             double y_std, const double* Q, long long m, double* mean, double* std, double* zpred,
                             int* neg_count, int max_ctas, void* stream);
 
+/* The same posterior at explicit points through a cross-covariance TABLE: for chunks of `table_rows` queries (a
+ * multiple of 128) the library first writes T[q][k] = exp(-|q - x_k|^2 / 2 l^2) -- one exp() per (query, observation)
+ * where the entry above re-evaluates it once per 128-row block of W -- and then runs the chunk on the lattice kernel's
+ * warp-specialised pipeline as a one-row lattice.  tables: caller-owned scratch of
+ * table_rows * NP + NP + 4 * (table_rows / 128) doubles.  slab_bbox / cutoff as for ipp_gp_posterior_grid; the box of
+ * a 128-query tile is that of its own queries, so skipping needs the caller to pass spatially sorted queries
+ * (the Python layer sorts along the Z-order curve and undoes the permutation).  Results agree with
+ * ipp_gp_posterior_points to rounding (same products; the row blocks of W are aligned from the other end), and do
+ * not depend on the chunking or on the order of the queries when nothing is skipped.
+ * Replaces gp.predict(X, return_std=True) on arbitrary point sets: sklearn _gpr.py:446-500. */
+int ipp_gp_posterior_points_tabled(const double* Wbuf, const double* vbuf, int n, double c, double l, double y_mean,
+                                   double y_std, const double* Q, long long m, double* mean, double* std, double* zpred,
+                                   int* neg_count, double* tables, long long table_rows, const double* slab_bbox,
+                                   double cutoff, int max_ctas, void* stream);
+
 /* ---- information gain / selectors ---------------------------------------------------------
  * 0.5 * log det(I_L + beta * K K^T), K = kernel(leaf_xy (L x 2), obs_xy (na x 2)) with the PRIOR
  * hyper-parameters (c, l).  Factorises the smaller of the L- and na-order forms (Sylvester).

@@ -34,6 +34,7 @@ SIGNATURES = {
     "ipp_gp_fit_final_plan": [_D, _D, _I, _D, _D, _D, _D, _D, _D, _D, _I, _D],
     "ipp_gp_posterior_grid": [_D, _D, _I, _F, _F, _F, _F, _F, _F, _I, _F, _F, _I, _LL, _LL, _D, _D, _D, _D, _D, _D, _F, _I, _D],
     "ipp_gp_posterior_points": [_D, _D, _I, _F, _F, _F, _F, _D, _LL, _D, _D, _D, _D, _I, _D],
+    "ipp_gp_posterior_points_tabled": [_D, _D, _I, _F, _F, _F, _F, _D, _LL, _D, _D, _D, _D, _D, _LL, _D, _F, _I, _D],
     "ipp_mi_logdet": [_D, _I, _D, _I, _F, _F, _F, _D, _D, _D, _D, _D],
     "ipp_count_close": [_D, _I, _D, _I, _F, _D, _D, _D, _D, _D],
     "ipp_node_terms": [_I, _D, _I, _D, _I, _I, _D, _D, _I, _D, _D, _D],

@@ -37,6 +37,7 @@ struct PostArgs {
   int* neg_count;
   const double* slab_bbox;  // [np / 16][4] = {xmin, xmax, ymin, ymax} of each 16-observation slab, or nullptr
   double cutoff2;           // skip a slab when its box is farther than sqrt(cutoff2) from the tile's queries; <= 0: never
+  const double* tile_bbox;  // tabled explicit points: [tile][4] = {xmin, xmax, ymin, ymax} of each 128-query tile, else nullptr
 };
 
 using PC = Cfg128;
@@ -200,7 +201,13 @@ __device__ __forceinline__ void lattice_slab_mask(const PostArgs& a, unsigned* m
   const int ixl = ix0 + nvalid - 1;
   double qx0, qx1, qy0, qy1;
   qy0 = a.y0 + iy0 * a.ystep;
-  if (ixl < a.nx) {  // one lattice row
+  if (a.tile_bbox) {  // explicit points behind a k* table: the box of the tile's own queries
+    const double4 tb = *reinterpret_cast<const double4*>(a.tile_bbox + 4 * ((gq0 - a.g_begin) / QT));
+    qx0 = tb.x;
+    qx1 = tb.y;
+    qy0 = tb.z;
+    qy1 = tb.w;
+  } else if (ixl < a.nx) {  // one lattice row
     qx0 = a.x0 + ix0 * a.xstep;
     qx1 = a.x0 + ixl * a.xstep;
     qy1 = qy0;
@@ -462,6 +469,96 @@ static int launch_lattice(PostArgs& a, double* tables, int max_ctas, cudaStream_
   return IPP_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Explicit points through the table kernel.  A chunk of queries is a one-row "lattice" whose Ex table is the
+// cross-covariance itself, T[q][k] = exp(-|q / l - x_k / l|^2 / 2) -- ONE exp() per (query, observation) instead of one
+// per 128-row block of W that reads it -- and whose single Ey row is the constant c, so the fragment product
+// T * c rounds like the generic kernel's c * exp().  The chunk then runs on the warp-specialised lattice pipeline
+// (cp.async B operand, DMMA warps that only multiply) with the tile boxes of its own queries for the slab test.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) point_table_kernel(const double* __restrict__ xs, const double* __restrict__ ys, int n,
+                                                          int np, double l, const double* __restrict__ Q, long mq,
+                                                          double* __restrict__ T, long ldt) {
+  const long i = blockIdx.x;
+  const int k = blockIdx.y * 256 + threadIdx.x;
+  if (k >= np || i >= mq) return;
+  double v = 0.0;
+  if (k < n) v = rbf_scaled(__ddiv_rn(Q[2 * i], l), __ddiv_rn(Q[2 * i + 1], l), xs[k], ys[k], 1.0);
+  T[i * ldt + k] = v;
+}
+
+// row[k] = c (the Ey row of the one-row lattice) and, one warp per 128-query tile, the tile's bounding box.
+__global__ void __launch_bounds__(256) point_tiles_kernel(const double* __restrict__ Q, long mq, int np, double c,
+                                                          double* __restrict__ row, double* __restrict__ tile_bbox) {
+  const long gt = (long)blockIdx.x * 256 + threadIdx.x;
+  if (gt < np) row[gt] = c;
+  const long tile = gt >> 5;
+  const int lane = threadIdx.x & 31;
+  const long ntiles = (mq + QT - 1) / QT;
+  if (tile >= ntiles) return;
+  double x0 = INFINITY, x1 = -INFINITY, y0 = INFINITY, y1 = -INFINITY;
+  for (long q = tile * QT + lane; q < min(mq, (tile + 1) * QT); q += 32) {
+    const double x = Q[2 * q], y = Q[2 * q + 1];
+    x0 = fmin(x0, x);
+    x1 = fmax(x1, x);
+    y0 = fmin(y0, y);
+    y1 = fmax(y1, y);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    x0 = fmin(x0, __shfl_xor_sync(0xffffffffu, x0, o));
+    x1 = fmax(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+    y0 = fmin(y0, __shfl_xor_sync(0xffffffffu, y0, o));
+    y1 = fmax(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+  }
+  if (lane == 0) {
+    tile_bbox[4 * tile + 0] = x0;
+    tile_bbox[4 * tile + 1] = x1;
+    tile_bbox[4 * tile + 2] = y0;
+    tile_bbox[4 * tile + 3] = y1;
+  }
+}
+
+// scratch per chunk of `rows` queries: rows * NP (table) + NP (the c row) + 4 * ceil(rows / 128) (tile boxes)
+static int launch_points_tabled(PostArgs a, const double* Q, long m, double* tables, long table_rows, int max_ctas,
+                                cudaStream_t st) {
+  const long ldt = a.np;
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) != cudaSuccess) return IPP_ERR_CUDA;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return IPP_ERR_CUDA;
+  if (cudaFuncSetAttribute(posterior_lattice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEP_SMEM) != cudaSuccess)
+    return IPP_ERR_CUDA;
+  double* T = tables;
+  double* crow = tables + table_rows * ldt;
+  double* tbox = crow + ldt;
+  double* mean = a.mean;
+  double* std = a.std;
+  double* zpred = a.zpred;
+  const int kb = (a.np + 255) / 256;
+  for (long q0 = 0; q0 < m; q0 += table_rows) {
+    const long mq = min(table_rows, m - q0);
+    const long ntiles = (mq + QT - 1) / QT;
+    point_table_kernel<<<dim3((unsigned)mq, kb), 256, 0, st>>>(a.xs, a.ys, a.n, a.np, a.l, Q + 2 * q0, mq, T, ldt);
+    const long threads = max((long)a.np, 32 * ntiles);
+    point_tiles_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(Q + 2 * q0, mq, a.np, a.c, crow, tbox);
+    a.Q = nullptr;  // the lattice kernel sees a one-row lattice of mq columns
+    a.nx = (int)mq;
+    a.ny = 1;
+    a.x0 = a.x1 = a.y0 = a.y1 = a.xstep = a.ystep = 0.0;
+    a.g_begin = 0;
+    a.g_end = mq;
+    a.mean = mean + q0;
+    a.std = std + q0;
+    a.zpred = zpred ? zpred + q0 : nullptr;
+    a.tile_bbox = tbox;
+    int ctas = (int)(ntiles < (long)sms ? ntiles : (long)sms);
+    if (max_ctas > 0 && ctas > max_ctas) ctas = max_ctas;
+    posterior_lattice_kernel<<<ctas, LAT_THREADS, SEP_SMEM, st>>>(a, T, crow, ldt);
+    IPP_LAUNCH_CHECK();
+  }
+  return IPP_OK;
+}
+
 static int launch_posterior(PostArgs& a, bool grid, int max_ctas, cudaStream_t st) {
   constexpr size_t SM = gemm_smem_bytes<PC, Lay::KCONT, Lay::MCONT>();
   const long total = a.g_end - a.g_begin;
@@ -556,6 +653,24 @@ int ipp_gp_posterior_points(const double* Wbuf, const double* vbuf, int n, doubl
   return launch_posterior(a, false, max_ctas, (cudaStream_t)stream);
 }
 
-int ipp_abi_version(void) { return 11; }
+int ipp_gp_posterior_points_tabled(const double* Wbuf, const double* vbuf, int n, double c, double l, double y_mean,
+                                   double y_std, const double* Q, long long m, double* mean, double* std, double* zpred,
+                                   int* neg_count, double* tables, long long table_rows, const double* slab_bbox,
+                                   double cutoff, int max_ctas, void* stream) {
+  if (!Wbuf || !vbuf || n <= 0 || !Q || m < 0 || !mean || !std || !(l > 0.0) || !tables) return IPP_ERR_ARG;
+  // a chunk is a whole number of 128-query tiles (the last chunk may be ragged) and fits the one-row lattice's int axis
+  if (table_rows < QT || table_rows % QT != 0 || table_rows > (1LL << 30)) return IPP_ERR_ARG;
+  PostArgs a{};
+  fill_state(a, Wbuf, vbuf, n, c, l, y_mean, y_std);
+  a.neg_count = neg_count;
+  a.mean = mean;
+  a.std = std;
+  a.zpred = zpred;
+  a.slab_bbox = slab_bbox;
+  a.cutoff2 = (slab_bbox && cutoff > 0.0) ? cutoff * cutoff : 0.0;
+  return launch_points_tabled(a, Q, m, tables, table_rows, max_ctas, (cudaStream_t)stream);
+}
+
+int ipp_abi_version(void) { return 12; }
 
 }  // extern "C"

@@ -893,8 +893,56 @@ class GaussianProcessRegressor:
         mean = mean_d.cpu().numpy()
         return (mean, std_d.cpu().numpy()) if return_std else mean
 
-    def predict_points_device(self, Qd, want_zpred=False):
-        """Posterior at explicit device-resident points (m x 2); returns device tensors."""
+    # explicit points: from this many queries on, the cross-covariance goes through a table and the lattice kernel's
+    # pipeline (ipp_gp_posterior_points_tabled); below, the generic kernel (one tile or two: latency either way)
+    TABLED_MIN = 256
+
+    def _table_scratch(self, need):
+        torch = _lib.require_cuda()
+        buf = getattr(self._ws, "tables", None)
+        if buf is None or buf.numel() < need:
+            self._ws.tables = None
+            buf = torch.empty(int(need), dtype=torch.float64, device="cuda")
+            self._ws.tables = buf
+        return buf
+
+    def _point_table_rows(self, m):
+        """Queries per chunk of the tabled explicit-point posterior: everything at once when the table fits a quarter of
+        the free device memory (at most 4 GiB), else whole waves of 128-query tiles (one tile per SM)."""
+        torch = _lib.require_cuda()
+        NP = self._ws.layout[0]
+        rows_all = (int(m) + 127) // 128 * 128
+        have = getattr(self._ws, "tables", None)
+        have_rows = 0 if have is None else (have.numel() - NP) // (NP + 1) // 128 * 128
+        budget = min(4 << 30, torch.cuda.mem_get_info()[0] // 4)
+        fit = max(int(budget // (8 * NP)), have_rows)
+        if rows_all <= fit:
+            return rows_all
+        wave = 128 * torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+        return max(128, fit // wave * wave if fit >= wave else fit // 128 * 128)
+
+    @staticmethod
+    def _morton_order_device(Qd):
+        """morton_order() of device-resident points (same keys: 16 bits per axis over the points' own bounding box)."""
+        import torch
+        lo, hi = Qd.min(dim=0).values, Qd.max(dim=0).values
+        span = torch.where(hi > lo, hi - lo, torch.ones_like(hi))
+        q = ((Qd - lo) / span * 65536.0).to(torch.int64).clamp_(max=65535)
+
+        def spread(v):
+            v = (v | (v << 8)) & 0x00FF00FF
+            v = (v | (v << 4)) & 0x0F0F0F0F
+            v = (v | (v << 2)) & 0x33333333
+            v = (v | (v << 1)) & 0x55555555
+            return v
+
+        return torch.argsort(spread(q[:, 0]) | (spread(q[:, 1]) << 1), stable=True)
+
+    def predict_points_device(self, Qd, want_zpred=False, tabled=None, skip_below=None, table_rows=None):
+        """Posterior at explicit device-resident points (m x 2); returns device tensors.  tabled (default: from
+        TABLED_MIN queries on): the cross-covariance table + lattice pipeline; with a state fitted in clustered order
+        the queries are processed along the Z-order curve so that the 16-observation slabs out of a tile's reach are
+        skipped (skip_below=0: dense), and the results are returned in the caller's order."""
         torch = _lib.require_cuda()
         lib = _lib.load()
         m = int(Qd.shape[0])
@@ -902,10 +950,36 @@ class GaussianProcessRegressor:
         std = torch.empty(m, dtype=torch.float64, device="cuda")
         zp = torch.empty(m, dtype=torch.float64, device="cuda") if want_zpred else None
         neg = torch.zeros(1, dtype=torch.int32, device="cuda")
-        if m:
+        if tabled is None:
+            tabled = m >= self.TABLED_MIN
+        if m and not tabled:
             rc = lib.ipp_gp_posterior_points(*self._posterior_args(), _lib.ptr(Qd), m, _lib.ptr(mean), _lib.ptr(std),
                                              _lib.ptr(zp), _lib.ptr(neg), 0, _lib.stream_ptr())
             _lib.check(rc, "ipp_gp_posterior_points")
+            self._warn_negative(neg)
+        elif m:
+            args = self._posterior_args()
+            Qd = Qd.contiguous()
+            cutoff = self._skip_cutoff(self._fitted_l, skip_below) if self._bbox_d is not None else 0.0
+            order = self._morton_order_device(Qd) if cutoff > 0.0 else None
+            if order is not None:
+                Qd = Qd.index_select(0, order)
+                out = [torch.empty_like(mean), torch.empty_like(std), torch.empty_like(zp) if want_zpred else None]
+            else:
+                out = [mean, std, zp]
+            NP = self._ws.layout[0]
+            rows = int(table_rows) if table_rows else self._point_table_rows(m)
+            tables = self._table_scratch(rows * NP + NP + 4 * (rows // 128))
+            rc = lib.ipp_gp_posterior_points_tabled(*args, _lib.ptr(Qd), m, _lib.ptr(out[0]), _lib.ptr(out[1]),
+                                                    _lib.ptr(out[2]), _lib.ptr(neg), _lib.ptr(tables), rows,
+                                                    _lib.ptr(self._bbox_d) if cutoff > 0.0 else None, float(cutoff), 0,
+                                                    _lib.stream_ptr())
+            _lib.check(rc, "ipp_gp_posterior_points_tabled")
+            if order is not None:
+                mean[order] = out[0]
+                std[order] = out[1]
+                if want_zpred:
+                    zp[order] = out[2]
             self._warn_negative(neg)
         return mean, std, zp
 
@@ -992,13 +1066,7 @@ class GaussianProcessRegressor:
 
     def _lattice_tables(self, nx, ny):
         """Scratch for the lattice fast path of ipp_gp_posterior_grid: (nx + ny) * NP doubles."""
-        torch = _lib.require_cuda()
-        need = (int(nx) + int(ny)) * self._ws.layout[0]
-        buf = getattr(self._ws, "tables", None)
-        if buf is None or buf.numel() < need:
-            buf = torch.empty(need, dtype=torch.float64, device="cuda")
-            self._ws.tables = buf
-        return buf
+        return self._table_scratch((int(nx) + int(ny)) * self._ws.layout[0])
 
     def predict_grid_device(self, x0, x1, nx, y0, y1, ny, g_begin=0, g_end=None, want_zpred=True, out=None,
                             lattice=True, skip_below=None):

@@ -24,7 +24,7 @@ def test_header_library_and_binding_agree():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in ipp_b200.h but not exported"
     assert sorted(_lib.SIGNATURES) == names
-    assert lib.ipp_abi_version() == 11
+    assert lib.ipp_abi_version() == 12
 
 
 def test_layout_is_host_only_and_consistent():
@@ -42,6 +42,8 @@ def test_bad_arguments_are_rejected_without_a_device():
     lib = _lib.load()
     assert lib.ipp_gram_rbf(None, 0, None, 0, 1.0, 1.0, 0.0, None, 0, None) == -1
     assert lib.ipp_gp_posterior_points(None, None, 0, 1.0, 1.0, 0.0, 1.0, None, 0, None, None, None, None, 0, None) == -1
+    assert lib.ipp_gp_posterior_points_tabled(None, None, 0, 1.0, 1.0, 0.0, 1.0, None, 0, None, None, None, None, None, 128,
+                                              None, 0.0, 0, None) == -1
     assert lib.ipp_argmax_first(None, 0, None, None, None) == -1
 
 

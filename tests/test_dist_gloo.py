@@ -77,8 +77,10 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_two_rank_sharding_matches_single_process():
-    world, port = 2, _free_port()
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharding_matches_single_process(world):
+    """world 2, and world 3 for the ragged cases: 5 restarts, 7 scores and 50 lattice rows over 3 ranks."""
+    port = _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
@@ -103,7 +105,7 @@ def test_two_rank_sharding_matches_single_process():
         assert np.array_equal(z, 10 ** m) and np.array_equal(sd, s)  # slabs are row independent: exact
         assert k_nan == 3 and k_tie == 1
         assert np.array_equal(path, [[1.0, 2.0], [3.0, 4.0]])
-        assert rounds == [r_ for r_ in range(7) if r_ % 2 == rank]
+        assert rounds == [r_ for r_ in range(7) if r_ % world == rank]
 
 
 def test_partition_helpers():

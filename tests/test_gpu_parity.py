@@ -231,7 +231,7 @@ def test_grid_paths_agree_and_slabs_bit_exact(G, torch):
     xs, ys = np.linspace(0, W, nx), np.linspace(0.5, 9.25, ny)
     XX, YY = np.meshgrid(xs, ys)
     r = np.column_stack((XX.ravel(), YY.ravel()))
-    mp, sp, zp = gp.predict_points_device(torch.from_numpy(r).cuda(), want_zpred=True)
+    mp, sp, zp = gp.predict_points_device(torch.from_numpy(r).cuda(), want_zpred=True, tabled=False)  # the generic kernel
     mg, sg, zg = gp.predict_grid_device(0, W, nx, 0.5, 9.25, ny, lattice=False)
     assert torch.equal(mg, mp) and torch.equal(sg, sp) and torch.equal(zg, zp)
     m, s, z = gp.predict_grid_device(0, W, nx, 0.5, 9.25, ny)  # lattice fast path (nx >= 128), block-sparse k*

@@ -338,3 +338,59 @@ def test_cholesky_executors_agree_bit_for_bit(G, monkeypatch, n):
         for a, b in zip(got["plain"], got[name]):
             assert np.array_equal(a, b), name
     assert got["plain"][4][0][0] == got["plain"][0]    # batch member == single evaluation
+
+
+# ---------------------------------------------------------------------------------------------------
+# G6 / predict on arbitrary point sets: the tabled explicit-point posterior (ipp_gp_posterior_points_tabled)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,W,l,m", [(700, 40, 1.2, 1000), (1500, 60, 0.6, 20001), (200, 20, 1.0, 257)])
+def test_tabled_points_posterior_vs_generic_kernel_and_oracle(G, n, W, l, m):
+    """Explicit points through the cross-covariance table + the lattice kernel's pipeline: equal to the generic
+    explicit-point kernel to rounding (dense and with slab skipping along the Z-order curve), independent of the
+    chunking and of the order of the queries bit for bit when nothing is skipped, and within the T1 tolerances of the
+    oracle's predict (sklearn _gpr.py:446-500).  Ragged last tiles, a chunk boundary inside the set, queries far from
+    every observation (prior) included; the third case is a state in the given order (n < 256: no slab boxes).
+    (A wide kernel on a small workspace -- n = 300, 20 x 20, l = 3, cond(L) 7e5 -- is outside the T1 model: LAPACK's own
+    variance is 3e-9 from a 50-digit evaluation there and the device's 1.7e-8, both kernels alike.)"""
+    import torch
+    from tests.test_gpu_parity import _make
+
+    X, y = _make(n, W, seed=11)
+    c = 1.3
+    gp = G.GaussianProcessRegressor(kernel=G.ConstantRBFKernel(c, l), optimizer=None, normalize_y=True).fit(X, y)
+    gp._ensure()
+    rng = np.random.RandomState(2)
+    Q = rng.uniform(-0.1 * W, 1.1 * W, (m, 2))
+    Q[:5] = X[:5]                      # interpolation at the data
+    Q[5:9] += 50.0 * W                 # nothing within reach: the prior
+    Qd = torch.from_numpy(Q).cuda()
+    mg, sg, zg = gp.predict_points_device(Qd, want_zpred=True, tabled=False)
+    md, sd, zd = gp.predict_points_device(Qd, want_zpred=True, tabled=True, skip_below=0)
+    st = O.fit(X, y, c, l, optimize=False)
+    sub = np.r_[0:9, rng.choice(m, 150, replace=False)]
+    tol = _mean_tol(st, Q[sub], mg.cpu().numpy()[sub])
+    for mt, s_t, zt in ((md, sd, zd), gp.predict_points_device(Qd, want_zpred=True, tabled=True)):
+        assert (np.abs((mt - mg).cpu().numpy()[sub]) <= tol).all()
+        assert float((s_t - sg).abs().max()) <= 1e-9
+        assert float((s_t * s_t - sg * sg).abs().max()) <= _var_tol(st)
+        fin = torch.isfinite(zg)
+        assert torch.equal(fin, torch.isfinite(zt))
+    sparse_on = gp._bbox_d is not None
+    assert sparse_on == (n >= 256 and l < 2.0)
+    # chunking (a chunk boundary inside the set, ragged last chunk) and query order change nothing when dense
+    mc, sc, zc = gp.predict_points_device(Qd, want_zpred=True, tabled=True, skip_below=0, table_rows=128)
+    assert torch.equal(mc, md) and torch.equal(sc, sd) and torch.equal(zc, zd)
+    perm = torch.from_numpy(rng.permutation(m)).cuda()
+    mp_, sp_, _ = gp.predict_points_device(Qd.index_select(0, perm), tabled=True, skip_below=0, table_rows=256)
+    assert torch.equal(mp_, md.index_select(0, perm)) and torch.equal(sp_, sd.index_select(0, perm))
+    # against the oracle's predict
+    mo, so, _ = O.predict(st, Q[sub])
+    assert (np.abs(md.cpu().numpy()[sub] - mo) <= tol).all()
+    assert np.abs(sd.cpu().numpy()[sub] ** 2 - so ** 2).max() <= _var_tol(st)
+    # the prior far away, exactly (every slab skipped or every product underflowing to zero)
+    far = gp.predict_points_device(Qd[5:9].repeat(100, 1), tabled=True)
+    assert float((far[0] - gp._y_train_mean).abs().max()) == 0.0
+    assert float((far[1] - np.sqrt(c) * gp._y_train_std).abs().max()) <= 1e-15
+    # the public call takes the same route from TABLED_MIN queries on
+    mean_h, std_h = gp.predict(Q, return_std=True)
+    np.testing.assert_array_equal(mean_h, gp.predict_points_device(Qd)[0].cpu().numpy())
