@@ -34,7 +34,8 @@ EPS = float(np.finfo(np.float64).eps)
 # n <= 8192, + 1 per doubling) against the kernel's (ceil(n / 256) sequential + 8 tree levels); each addition
 # contributes EPS / 2 of the running sum, itself <= S2.
 C_TERM = 6.0
-STATS = {"stages": 0, "redecided": 0, "device_evaluations": 0, "why_nonfinite": 0, "why_loose_bound": 0, "why_in_band": 0}
+STATS = {"stages": 0, "redecided": 0, "device_evaluations": 0, "why_nonfinite": 0, "why_loose_bound": 0, "why_in_band": 0,
+         "rows": 0, "distinct_rows": 0}   # rows / distinct_rows: particles of the re-decided stages, and how many were evaluated
 
 
 def c_sum(n: int) -> float:
@@ -193,8 +194,28 @@ def _resample_indices(particles, gamma, n_samples, obs_wp, obs_vals, lambda_b, M
         STATS["why_nonfinite"] += 1
     # inside the band (or a non-finite likelihood): the reference's own expression for the weights, same draws
     STATS["redecided"] += 1
-    w = stage_weights(batched_poisson_log_likelihood(particles, obs_wp, obs_vals, lambda_b, M), gamma, n_samples)
+    w = stage_weights(distinct_rows_log_likelihood(particles, obs_wp, obs_vals, lambda_b, M), gamma, n_samples)
     return choice_from_draws(w, u)[1]
+
+
+def distinct_rows_log_likelihood(particles: np.ndarray, obs_wp, obs_vals, lambda_b: float, M: int) -> np.ndarray:
+    """batched_poisson_log_likelihood evaluated once per DISTINCT particle.  The stages that get re-decided are those
+    of a nearly collapsed cloud -- resampling has left a few distinct rows, each many times over (measured at the
+    reference's example size: 2 to 142 distinct rows among 1000, log-likelihoods within 1e-8 of each other, which is
+    exactly why a draw can land inside the band) -- and the reference's expression is element-wise per row with
+    per-row reductions, so equal rows get equal values: the result is the full evaluation's, bit for bit, at the cost
+    of the distinct rows only."""
+    particles = np.asarray(particles, dtype=float)
+    if particles.ndim == 2 and particles.shape[0] > 1 and np.all(np.isfinite(particles)):
+        uniq, inv = np.unique(particles, axis=0, return_inverse=True)
+        inv = np.asarray(inv).reshape(-1)
+        if uniq.shape[0] < particles.shape[0] and np.array_equal(uniq[inv], particles):
+            STATS["distinct_rows"] = STATS.get("distinct_rows", 0) + int(uniq.shape[0])
+            STATS["rows"] = STATS.get("rows", 0) + int(particles.shape[0])
+            return batched_poisson_log_likelihood(uniq, obs_wp, obs_vals, lambda_b, M)[inv]
+    STATS["distinct_rows"] = STATS.get("distinct_rows", 0) + int(particles.shape[0])
+    STATS["rows"] = STATS.get("rows", 0) + int(particles.shape[0])
+    return batched_poisson_log_likelihood(particles, obs_wp, obs_vals, lambda_b, M)
 
 
 _MVN_DIRECT = None   # None: untested; True / False after the self-check

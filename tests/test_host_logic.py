@@ -375,6 +375,49 @@ def test_host_likelihood_fast_path_keeps_scipy_bits():
     assert np.all(np.isneginf(E.batched_poisson_log_likelihood(th[:4], obs, vals2, 1.0, M)))
 
 
+def test_redecided_stage_evaluates_distinct_rows_only():
+    """A re-decided sampler stage evaluates the reference's expression once per DISTINCT particle (the stages that hit
+    the band are nearly collapsed clouds): same values as the full evaluation bit for bit, same resampled indices as
+    np.random.choice on the reference's weights, and a cloud of all-distinct or non-finite rows takes the full route."""
+    from mripp_b200.src.estimation import estimation as E
+
+    rng = np.random.RandomState(8)
+    n, N, M = 600, 500, 3
+    obs = rng.uniform(0, 40, (n, 2))
+    vals = rng.poisson(50.0, n).astype(float)
+    rows = rng.uniform(0, 40, (7, 3 * M))
+    rows[:, 2::3] = rng.uniform(1e5, 1e6, (7, M))
+    rows[3, 0] = -0.0
+    parts = rows[rng.randint(0, 7, N)]
+    before = dict(E.STATS)
+    got = E.distinct_rows_log_likelihood(parts, obs, vals, 1.0, M)
+    full = E.batched_poisson_log_likelihood(parts, obs, vals, 1.0, M)
+    assert np.array_equal(got, full)
+    assert E.STATS["rows"] - before["rows"] == N and E.STATS["distinct_rows"] - before["distinct_rows"] == 7
+    distinct = rng.uniform(1, 39, (40, 3 * M))
+    assert np.array_equal(E.distinct_rows_log_likelihood(distinct, obs, vals, 1.0, M),
+                          E.batched_poisson_log_likelihood(distinct, obs, vals, 1.0, M))
+    bad = parts.copy()
+    bad[5, 1] = np.nan
+    a, b = E.distinct_rows_log_likelihood(bad, obs, vals, 1.0, M), E.batched_poisson_log_likelihood(bad, obs, vals, 1.0, M)
+    assert np.array_equal(a, b, equal_nan=True) and np.isnan(a[5])
+
+    class LooseBound:   # device values off by 1e-7 relative with a bound the band logic must reject: forces the re-decision
+        def particle_log_likelihood(self, thetas, prepared, lambda_b, M_):
+            ll = E.batched_poisson_log_likelihood(thetas, obs, vals, lambda_b, M_)
+            return ll * (1 + 1e-7), np.full(len(ll), 1e30), np.full(len(ll), 1e30)
+
+    gamma = 0.4
+    np.random.seed(21)
+    before = dict(E.STATS)
+    idx = E.resample_indices(parts, gamma, N, obs, vals, 1.0, M, LooseBound(), None)
+    after_state = np.random.get_state()[2]
+    assert E.STATS["redecided"] - before["redecided"] == 1 and E.STATS["distinct_rows"] - before["distinct_rows"] == 7
+    np.random.seed(21)
+    want = np.random.choice(N, size=N, p=E.stage_weights(full, gamma, N))   # estimation.py:117
+    assert np.array_equal(idx, want) and np.random.get_state()[2] == after_state
+
+
 def test_exact_close_counts_many_points_equal_the_scalar_loop():
     """count_close_exact_many (one array pass per branch, observation lists converted once) against the reference's
     double loop `np.linalg.norm(point - obs) < d` (rrt.py:246-252), with observations exactly at, one ulp inside and one
