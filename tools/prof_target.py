@@ -1,4 +1,5 @@
-"""Small fixed workload for ncu: one fit_final + LML evals + one grid posterior.  Args: n W G n_lml"""
+"""Small fixed workload for ncu: one fit_final + LML evals + one grid posterior.  Args: n W G n_lml [Gy [m_points]]
+(m_points > 0: one dense tabled explicit-point posterior of that many random queries)"""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -18,5 +19,8 @@ if n_lml:
     G.gram_device(X, None, 1.0, 1.0)  # the public symmetric Gram (gp.kernel(X)): HBM-write bound
 if Gx:
     gp.predict_grid_device(0, W, Gx, 0, W * Gy / Gx, Gy)
+if len(sys.argv) > 6 and int(sys.argv[6]) > 0:
+    Qd = torch.from_numpy(rng.uniform(0, W, (int(sys.argv[6]), 2))).cuda()
+    gp.predict_points_device(Qd, tabled=True, skip_below=0)
 torch.cuda.synchronize()
 print("ok")
