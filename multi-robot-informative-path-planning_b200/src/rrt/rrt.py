@@ -144,8 +144,8 @@ def rrt_tree_generation(self, budget_portion: float, agent_idx: int) -> None:
     samples = tree.grow_native(0, self.scenario.workspace_size, self.d_waypoint_distance, 0.0, budget_portion)
     if samples is not None:             # grown natively (csrc/ipp_tree_host.cu): same nodes, same RNG position
         travelled = budget_portion
-        for _ in range(samples - 1):    # the reference's loop registers the root once per non-final iteration
-            self.agents_trees[agent_idx].add(self.agents_roots[agent_idx])
+        # the reference's loop registers the root once per non-final iteration
+        self.agents_trees[agent_idx].add_repeated(self.agents_roots[agent_idx], samples - 1)
     while travelled < budget_portion:
         target = _sample(self)
         nn = tree.nearest(target)
@@ -190,8 +190,7 @@ def rig_tree_generation(self, budget_portion: float, agent_idx: int, gain_functi
                                budget_portion)
     if samples is not None:
         travelled = budget_portion
-        for _ in range(samples - 1):
-            self.agents_trees[agent_idx].add(self.agents_roots[agent_idx])
+        self.agents_trees[agent_idx].add_repeated(self.agents_roots[agent_idx], samples - 1)
     while travelled < budget_portion:
         target = _sample(self)
         nn = tree.nearest(target)

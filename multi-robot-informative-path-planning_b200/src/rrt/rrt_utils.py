@@ -54,6 +54,12 @@ class TreeCollection:
     def add(self, tree: TreeNode) -> None:
         self.trees.append(tree)
 
+    def add_repeated(self, tree: TreeNode, count: int) -> None:
+        """`count` calls of add(tree): the reference's generators register the root once per loop iteration
+        (rrt.py:278,327) -- 18 000 times per tree at the size of its example config."""
+        if count > 0:
+            self.trees.extend([tree] * count)
+
     def __iter__(self):
         return iter(self.trees)
 
@@ -225,6 +231,65 @@ class _RngMark:
 
 
 # ---- structure-of-arrays tree ------------------------------------------------------------------------
+class RewireLog:
+    """The rewire events (time, node, new parent) of a tree in time order: behaves like the list of tuples it used to
+    be (len, iteration, indexing, equality with a list), but the events a native growth call reports stay in the int64
+    array they arrive in -- a tree of the reference's example config logs ~28 000 of them per call, and turning them
+    into tuples and back into an array for the scorer's CSR cost more than a third of the device scoring pass."""
+    __slots__ = ("_parts", "_n", "_cache")
+
+    def __init__(self, events=()):
+        self._parts, self._n, self._cache = [], 0, None
+        for ev in events:
+            self.append(ev)
+
+    def append(self, ev) -> None:
+        ev = (int(ev[0]), int(ev[1]), int(ev[2]))
+        if self._parts and isinstance(self._parts[-1], list):
+            self._parts[-1].append(ev)
+        else:
+            self._parts.append([ev])
+        self._n += 1
+        self._cache = None
+
+    def extend_array(self, events: np.ndarray) -> None:
+        if len(events):
+            self._parts.append(np.array(events, dtype=np.int64).reshape(-1, 3))
+            self._n += len(events)
+            self._cache = None
+
+    def as_array(self) -> np.ndarray:
+        """(E, 3) int64, time order."""
+        if self._cache is None:
+            parts = [np.asarray(q, dtype=np.int64).reshape(-1, 3) for q in self._parts]
+            self._cache = np.concatenate(parts) if parts else np.zeros((0, 3), dtype=np.int64)
+            self._parts = [self._cache] if parts else []
+        return self._cache
+
+    def __len__(self) -> int:
+        return self._n
+
+    def __bool__(self) -> bool:
+        return self._n > 0
+
+    def __iter__(self):
+        return iter([tuple(r) for r in self.as_array().tolist()])
+
+    def __getitem__(self, k):
+        r = self.as_array()[k]
+        return tuple(r.tolist()) if r.ndim == 1 else [tuple(x) for x in r.tolist()]
+
+    def __eq__(self, other):
+        if isinstance(other, RewireLog):
+            return bool(np.array_equal(self.as_array(), other.as_array()))
+        if isinstance(other, (list, tuple)):
+            return list(self) == [tuple(int(v) for v in ev) for ev in other]
+        return NotImplemented
+
+    def __repr__(self) -> str:
+        return f"RewireLog({list(self)!r})"
+
+
 class TreeArrays:
     """One agent's tree as flat arrays; node id = insertion order (index into tree_nodes[agent])."""
 
@@ -235,8 +300,9 @@ class TreeArrays:
         self.edge = np.zeros(capacity, dtype=np.float64)      # |point - current parent|, numpy-exact
         self.nchild = np.zeros(capacity, dtype=np.int64)
         self.info = np.zeros(capacity, dtype=np.float64)
-        self._pt: List[np.ndarray] = []                       # the original point objects, in order
-        self.rewires: List[tuple] = []                        # (time, node, new_parent)
+        self._pt: List[Optional[np.ndarray]] = []             # the original point objects, in order (None: a natively grown
+                                                              # node whose array is made from _xy on first use, see _p)
+        self.rewires = RewireLog()                            # (time, node, new_parent)
         self.n = 0
         self._append(root_point, -1)
 
@@ -264,9 +330,17 @@ class TreeArrays:
         self.info[i] = 0.0
         if parent >= 0:
             self.nchild[parent] += 1
-            self.edge[i] = _norm(point - self._pt[parent])
+            self.edge[i] = _norm(point - self._p(parent))
         self.n += 1
         return i
+
+    def _p(self, i: int) -> np.ndarray:
+        """The point object of node i; nodes inserted by ipp_host_tree_grow get theirs on first use (18 000 small arrays
+        per tree of the reference's example config, of which a selector touches a few dozen)."""
+        q = self._pt[i]
+        if q is None:
+            q = self._pt[i] = self._xy[i].copy()
+        return q
 
     def grow_native(self, mode: int, workspace, step: float, radius: float, budget_portion: float, block: int = 256
                     ) -> Optional[int]:
@@ -311,12 +385,13 @@ class TreeArrays:
                 mark.restore()
                 if consumed.value:
                     np.random.random_sample(2 * consumed.value)
-            for i in range(self.n, n_out.value):
-                self._pt.append(self._xy[i].copy())
+            self._pt.extend([None] * (n_out.value - self.n))
             self.info[self.n: n_out.value] = 0.0
             self.n = n_out.value
             if n_rw.value:
-                self.rewires.extend(map(tuple, rewires[: n_rw.value].tolist()))
+                if not isinstance(self.rewires, RewireLog):
+                    self.rewires = RewireLog(self.rewires)
+                self.rewires.extend_array(rewires[: n_rw.value])
             if finished.value:
                 return samples
             # the library rebuilds its grid and path costs from the tree on every call: let the blocks grow with the
@@ -327,7 +402,7 @@ class TreeArrays:
         return self._xy[: self.n]
 
     def point(self, i) -> np.ndarray:
-        return self._pt[i]
+        return self._p(i)
 
     # -- primitives, decision-exact ---------------------------------------------------------------
     def nearest(self, target: np.ndarray) -> int:
@@ -340,7 +415,7 @@ class TreeArrays:
             return int(cand[0])
         best, best_d = -1, None
         for i in cand:  # ascending index, strict '<' keeps the first minimum
-            di = _norm(self._pt[i] - target)
+            di = _norm(self._p(i) - target)
             if best_d is None or di < best_d:
                 best, best_d = int(i), di
         return best
@@ -351,7 +426,7 @@ class TreeArrays:
         r = np.sqrt(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1])
         out = []
         for i in np.nonzero(r < radius * (1.0 + 1e-12))[0]:
-            if r[i] < radius * (1.0 - 1e-12) or _norm(point - self._pt[i]) < radius:
+            if r[i] < radius * (1.0 - 1e-12) or _norm(point - self._p(i)) < radius:
                 out.append(int(i))
         return out
 
@@ -369,11 +444,11 @@ class TreeArrays:
     def rewire(self, neighbours: List[int], new: int) -> None:
         """rrt_utils.py:85-88; logs (time = id of the inserted node, node, new parent) for the
         versioned branch walk of ipp_branch_gain."""
-        pn = self._pt[new]
+        pn = self._p(new)
         for q in neighbours:
-            if self.path_cost(new) + _norm(pn - self._pt[q]) < self.path_cost(q):
+            if self.path_cost(new) + _norm(pn - self._p(q)) < self.path_cost(q):
                 self.parent[q] = new
-                self.edge[q] = _norm(self._pt[q] - pn)
+                self.edge[q] = _norm(self._p(q) - pn)
                 self.rewires.append((new, q, new))
 
     def history_csr(self):
@@ -382,7 +457,7 @@ class TreeArrays:
         off = np.zeros(self.n + 1, dtype=np.int32)
         if E == 0:
             return off, np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.int32)
-        ev = np.asarray(self.rewires, dtype=np.int64)
+        ev = self.rewires.as_array() if isinstance(self.rewires, RewireLog) else np.asarray(self.rewires, dtype=np.int64)
         order = np.lexsort((ev[:, 0], ev[:, 1]))  # by node, then time (stable)
         ev = ev[order]
         counts = np.bincount(ev[:, 1], minlength=self.n)
@@ -396,12 +471,12 @@ class TreeArrays:
         for t, q, p in self.rewires:
             if t < i:
                 hist[q] = p  # events are appended in time order: the last one before i wins
-        out, q = [self._pt[i]], i
+        out, q = [self._p(i)], i
         while True:
             p = hist.get(q, int(self.parent0[q]))
             if p < 0:
                 break
-            out.append(self._pt[p])
+            out.append(self._p(p))
             q = p
         return out
 
@@ -440,14 +515,14 @@ class TreeArrays:
         """rrt_utils.py:107-114 over the CURRENT parent pointers; returns the original point objects."""
         out = []
         while i >= 0:
-            out.append(self._pt[i])
+            out.append(self._p(i))
             i = self.parent[i]
         out.reverse()
         return out
 
     def materialise(self) -> List[InformativeTreeNode]:
         """Reference-shaped node objects (children from insertion-time parents, parent = current)."""
-        nodes = [InformativeTreeNode(self._pt[i]) for i in range(self.n)]
+        nodes = [InformativeTreeNode(self._p(i)) for i in range(self.n)]
         for i in range(1, self.n):
             nodes[self.parent0[i]].children.append(nodes[i])
         for i in range(self.n):

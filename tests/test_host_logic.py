@@ -264,7 +264,7 @@ def test_native_growth_equals_python_loops(monkeypatch, gen, budgets, d):
         t = st.trees_soa[0]
         res.append((t.points().copy(), t.parent0[: t.n].copy(), t.parent[: t.n].copy(), t.edge[: t.n].copy(),
                     t.nchild[: t.n].copy(), list(t.rewires), t.info[: t.n].copy(), len(st.agents_trees[0].trees),
-                    np.random.uniform(size=3), [p.copy() for p in t._pt]))
+                    np.random.uniform(size=3), [t.point(i).copy() for i in range(t.n)]))
     a, b = res
     assert len(a[0]) == len(b[0]) and len(a[0]) > (1 if budgets != [0, 5] else 0)
     for x, y in zip(a[:5], b[:5]):
@@ -438,3 +438,33 @@ def test_exact_close_counts_many_points_equal_the_scalar_loop():
     assert E.count_close_exact(pts[7], lists, d) == want[7]
     obs_a.append(pts[3] + 0.1)           # the list grows: the cached array must not be reused
     assert E.count_close_exact(pts[3], lists, d) == want[3] + 1
+
+
+def test_rewire_log_behaves_like_the_list_of_tuples():
+    """RewireLog (array-backed rewire events of natively grown trees) against the plain list it replaces: length,
+    iteration, indexing, equality in both directions, mixed Python appends and native blocks in time order, and the
+    scorer's CSR (history_csr) from either form."""
+    from mripp_b200.src.rrt.rrt_utils import RewireLog, TreeArrays
+
+    rng = np.random.RandomState(4)
+    ev = [(int(t), int(rng.randint(1, 40)), int(t)) for t in sorted(rng.randint(2, 60, 50))]
+    log = RewireLog()
+    for e in ev[:7]:
+        log.append(e)
+    log.extend_array(np.array(ev[7:30], dtype=np.int64))
+    log.append(np.array(ev[30]))            # numpy integers are stored as Python ints
+    log.extend_array(np.zeros((0, 3), dtype=np.int64))
+    log.extend_array(np.array(ev[31:], dtype=np.int64))
+    assert len(log) == 50 and bool(log) and not RewireLog()
+    assert list(log) == ev and log == ev and ev == log and log == RewireLog(ev) and log != ev[:-1]
+    assert log[3] == ev[3] and log[-1] == ev[-1] and log[5:9] == ev[5:9]
+    assert all(type(v) is int for e in log for v in e)
+    assert log.as_array().shape == (50, 3) and RewireLog().as_array().shape == (0, 3)
+    a, b = TreeArrays(np.zeros(2)), TreeArrays(np.zeros(2))
+    for k in range(1, 60):
+        for t in (a, b):
+            t.add(np.array([float(k), 0.5 * k]), int(rng.randint(0, k)) if t is a else int(a.parent0[k]))
+    a.rewires, b.rewires = log, list(ev)    # the list form (tests assign one) still works
+    for x, y in zip(a.history_csr(), b.history_csr()):
+        assert x.dtype == y.dtype == np.int32 and np.array_equal(x, y)
+    assert [p.tolist() for p in a.chain_at(41)] == [p.tolist() for p in b.chain_at(41)]
