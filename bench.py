@@ -437,7 +437,8 @@ def run_b200(args, wl, rank, world, local_rank):
     pts_diff = {"tabled_dense_vs_generic_std": float((r_den[1] - r_gen[1]).abs().max()),
                 "tabled_sparse_vs_dense_std": float((r_spa[1] - r_den[1]).abs().max()),
                 "tabled_sparse_vs_dense_mean": float((r_spa[0] - r_den[0]).abs().max())}
-    assert pts_diff["tabled_dense_vs_generic_std"] <= 1e-7 and pts_diff["tabled_sparse_vs_dense_std"] <= 1e-12, pts_diff
+    if rank == 0:  # rank 0's data are those of the 1-GPU run; a failed check elsewhere must not strand the other ranks
+        assert pts_diff["tabled_dense_vs_generic_std"] <= 1e-7 and pts_diff["tabled_sparse_vs_dense_std"] <= 1e-12, pts_diff
     first_rb = n % 128
     rlims = ([first_rb] if first_rb else []) + [first_rb + 128 * j for j in range(1, n // 128 + 1)]
     pts_dense_flops = (m_pts // 128) * sum((r + 15) // 16 for r in rlims) * 2.0 * 128 * 128 * 16

@@ -19,6 +19,21 @@ class FastGP(OracleGP):
     full = False
 
 
+class DrawsOnlyGP(OracleGP):
+    """For decision tests on a 10^6-point lattice: a fit consumes its restart draws (sklearn _gpr.py:329-333) and nothing
+    else, the lattice posterior is not evaluated (the reference's selectors never read the fitted state)."""
+
+    def fit(self, X, y):
+        b = O.log_bounds()
+        for _ in range(self.n_restarts_optimizer):
+            np.random.mtrand._rand.uniform(b[:, 0], b[:, 1])
+        self.X_train_ = np.asarray(X, float).reshape(-1, 2)
+        return self
+
+    def predict_grid_host(self, x0, x1, nx, y0, y1, ny):
+        return np.zeros((ny, nx)), np.zeros(nx * ny)
+
+
 def _nodes_from(pts, parent, nchild):
     """Reference-shaped nodes from a golden snapshot: final parents; `children` only has to be as long as the
     reference's list was (rewire never removes a child from its old parent, so leaves are `nchild == 0`)."""
@@ -126,7 +141,8 @@ def run_multi(g, tag, obstacles, make_scenario, make_strategy):
     """Shared by the CPU (doubles) and the device test: one MR_IPP run at the golden's seed and agent count, compared
     bit for bit with the reference's waypoints, measurements, per-agent paths, source estimates and RNG position."""
     seed, agents, budget = int(g[f"{tag}_seed"]), int(g[f"{tag}_num_agents"]), int(g[f"{tag}_budget"])
-    sc = make_scenario(num_sources=2, workspace_size=(0, 40, 0, 40), obstacles=obstacles, seed=seed)
+    W = int(g[f"{tag}_W"]) if f"{tag}_W" in g else 40
+    sc = make_scenario(num_sources=len(g[f"{tag}_sources"]), workspace_size=(0, W, 0, W), obstacles=obstacles, seed=seed)
     assert np.array_equal(np.array(sc.sources), g[f"{tag}_sources"])
     np.random.seed(2000 + seed)
     st = make_strategy(sc, num_agents=agents, budget=budget, **MULTI_COMMON)
@@ -140,6 +156,16 @@ def run_multi(g, tag, obstacles, make_scenario, make_strategy):
     assert np.array_equal(np.asarray(st.best_estimates, float).reshape(-1, 3), g[f"{tag}_best_estimates"])
     assert np.array_equal(np.random.uniform(size=3), g[f"{tag}_rng_after"])
     return sc, st, Z, std
+
+
+def test_c4_shaped_run_identical_host_logic(gold):
+    """configs[3]'s shape as a whole run -- 8 agents on the 100 x 100 workspace (1000 x 1000 lattice) -- against the
+    unmodified reference (oracle/make_golden_r2.py --only c4run): waypoints, measurements, per-agent paths, estimates
+    and RNG position bit-identical.  Host logic on the CPU doubles here; the device variant of this run
+    (tests/test_r2_gpu.py) is opt-in because it was added after the round's GPU minutes were spent."""
+    g = gold("runs_golden_c4_r2.npz")
+    run_multi(g, "mripp_8a_c4", [], lambda **kw: PointSourceField(gp_factory=DrawsOnlyGP, ground_truth_mode="host", **kw),
+              lambda sc, **kw: R.MR_IPP(sc, scorer=OracleScorer(), **kw))
 
 
 @pytest.mark.parametrize("tag,obstacles", MULTI, ids=[m[0] for m in MULTI])

@@ -159,6 +159,34 @@ def test_multi_agent_runs_identical_on_device(gold, tag, obstacles):
     assert np.abs(std1.reshape(Z1.shape)[::8, ::8] - g[f"{tag}_std"]).max() <= 1e-6
 
 
+@pytest.mark.skipif(__import__("os").environ.get("IPP_RUN_C4_DEVICE_RUN") != "1",
+                    reason="added after the round's GPU minutes were spent: never run on hardware; opt in with "
+                           "IPP_RUN_C4_DEVICE_RUN=1 (the host logic of the same run is checked on CPU in test_r2_cpu.py)")
+def test_c4_shaped_run_identical_on_device(gold):
+    """configs[3]'s shape as a whole run on the device: 8 agents, 100 x 100 workspace, 1000 x 1000 lattice; T3 decisions
+    bit-identical, T1 field at the reference's theta."""
+    from mripp_b200.src.point_source.point_source import PointSourceField
+    from mripp_b200.src.rrt import rrt as R
+
+    g, tag = gold("runs_golden_c4_r2.npz"), "mripp_8a_c4"
+
+    def scenario(**kw):
+        sc = PointSourceField(**kw)
+        sc.gp.lazy = True
+        return sc
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sc, st, Z, std = run_multi(g, tag, [], scenario, lambda s, **kw: R.MR_IPP(s, **kw))
+        assert Z.shape == (1000, 1000) and std.shape == (10 ** 6,)
+        th = g[f"{tag}_theta"]
+        sc.gp.kernel = type(sc.gp.kernel)(float(np.exp(th[0])), float(np.exp(th[1])))
+        sc.gp.optimizer, sc.gp.lazy = None, False
+        Z1, std1 = sc.predict_spatial_field(st.obs_wp, np.asarray(st.measurements, float))
+    assert np.abs(np.log10(Z1[::20, ::20]) - np.log10(g[f"{tag}_Z"])).max() <= 1e-4
+    assert np.abs(std1.reshape(Z1.shape)[::20, ::20] - g[f"{tag}_std"]).max() <= 1e-6
+
+
 # ---------------------------------------------------------------------------------------------------
 # Concurrency contract (include/ipp_b200.h: re-entrant, one stream per calling thread).  The reference calls
 # gp.kernel(...) and the selectors from num_agents threads outside its lock (rrt.py:659-664, 703-711).
