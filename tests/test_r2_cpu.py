@@ -162,10 +162,22 @@ def test_c4_shaped_run_identical_host_logic(gold):
     """configs[3]'s shape as a whole run -- 8 agents on the 100 x 100 workspace (1000 x 1000 lattice) -- against the
     unmodified reference (oracle/make_golden_r2.py --only c4run): waypoints, measurements, per-agent paths, estimates
     and RNG position bit-identical.  Host logic on the CPU doubles here; the device variant of this run
-    (tests/test_r2_gpu.py) is opt-in because it was added after the round's GPU minutes were spent."""
+    (tests/test_r2_gpu.py, IPP_RUN_SHAPED_DEVICE_RUNS=1) is opt-in because it was added after the round's GPU minutes were spent."""
     g = gold("runs_golden_c4_r2.npz")
     run_multi(g, "mripp_8a_c4", [], lambda **kw: PointSourceField(gp_factory=DrawsOnlyGP, ground_truth_mode="host", **kw),
               lambda sc, **kw: R.MR_IPP(sc, scorer=OracleScorer(), **kw))
+
+
+C3_RUNS = [("biasbeta_3a_c3", "RRT_BiasBetaInformative_GP_PathPlanning"), ("mripp_3a_c3", "MR_IPP")]
+
+
+@pytest.mark.parametrize("tag,cls", C3_RUNS, ids=[c[0] for c in C3_RUNS])
+def test_c3_shaped_runs_identical_host_logic(gold, tag, cls):
+    """configs[2]'s shape as whole runs -- 3 agents on the 50 x 50 workspace (500 x 500 lattice), the Bias-Beta class and
+    the adaptive MR_IPP -- against the unmodified reference (oracle/make_golden_r2.py --only c3runs), bit for bit."""
+    g = gold("runs_golden_c3_r2.npz")
+    run_multi(g, tag, [], lambda **kw: PointSourceField(gp_factory=DrawsOnlyGP, ground_truth_mode="host", **kw),
+              lambda sc, **kw: getattr(R, cls)(sc, scorer=OracleScorer(), **kw))
 
 
 @pytest.mark.parametrize("tag,obstacles", MULTI, ids=[m[0] for m in MULTI])

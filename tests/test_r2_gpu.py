@@ -159,16 +159,21 @@ def test_multi_agent_runs_identical_on_device(gold, tag, obstacles):
     assert np.abs(std1.reshape(Z1.shape)[::8, ::8] - g[f"{tag}_std"]).max() <= 1e-6
 
 
-@pytest.mark.skipif(__import__("os").environ.get("IPP_RUN_C4_DEVICE_RUN") != "1",
+SHAPED_RUNS = [("runs_golden_c4_r2.npz", "mripp_8a_c4", "MR_IPP", 20), ("runs_golden_c3_r2.npz", "biasbeta_3a_c3",
+               "RRT_BiasBetaInformative_GP_PathPlanning", 10), ("runs_golden_c3_r2.npz", "mripp_3a_c3", "MR_IPP", 10)]
+
+
+@pytest.mark.skipif(__import__("os").environ.get("IPP_RUN_SHAPED_DEVICE_RUNS") != "1",
                     reason="added after the round's GPU minutes were spent: never run on hardware; opt in with "
-                           "IPP_RUN_C4_DEVICE_RUN=1 (the host logic of the same run is checked on CPU in test_r2_cpu.py)")
-def test_c4_shaped_run_identical_on_device(gold):
-    """configs[3]'s shape as a whole run on the device: 8 agents, 100 x 100 workspace, 1000 x 1000 lattice; T3 decisions
-    bit-identical, T1 field at the reference's theta."""
+                           "IPP_RUN_SHAPED_DEVICE_RUNS=1 (the host logic of the same runs is checked on CPU in test_r2_cpu.py)")
+@pytest.mark.parametrize("fname,tag,cls,stride", SHAPED_RUNS, ids=[r[1] for r in SHAPED_RUNS])
+def test_config_shaped_runs_identical_on_device(gold, fname, tag, cls, stride):
+    """configs[2] / configs[3] shapes as whole runs on the device (3 agents on 50 x 50 with the Bias-Beta class and
+    MR_IPP; 8 agents on 100 x 100): T3 decisions bit-identical, T1 field at the reference's theta."""
     from mripp_b200.src.point_source.point_source import PointSourceField
     from mripp_b200.src.rrt import rrt as R
 
-    g, tag = gold("runs_golden_c4_r2.npz"), "mripp_8a_c4"
+    g = gold(fname)
 
     def scenario(**kw):
         sc = PointSourceField(**kw)
@@ -177,14 +182,15 @@ def test_c4_shaped_run_identical_on_device(gold):
 
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        sc, st, Z, std = run_multi(g, tag, [], scenario, lambda s, **kw: R.MR_IPP(s, **kw))
-        assert Z.shape == (1000, 1000) and std.shape == (10 ** 6,)
+        sc, st, Z, std = run_multi(g, tag, [], scenario, lambda s, **kw: getattr(R, cls)(s, **kw))
+        side = 10 * int(g[f"{tag}_W"])
+        assert Z.shape == (side, side) and std.shape == (side * side,)
         th = g[f"{tag}_theta"]
         sc.gp.kernel = type(sc.gp.kernel)(float(np.exp(th[0])), float(np.exp(th[1])))
         sc.gp.optimizer, sc.gp.lazy = None, False
         Z1, std1 = sc.predict_spatial_field(st.obs_wp, np.asarray(st.measurements, float))
-    assert np.abs(np.log10(Z1[::20, ::20]) - np.log10(g[f"{tag}_Z"])).max() <= 1e-4
-    assert np.abs(std1.reshape(Z1.shape)[::20, ::20] - g[f"{tag}_std"]).max() <= 1e-6
+    assert np.abs(np.log10(Z1[::stride, ::stride]) - np.log10(g[f"{tag}_Z"])).max() <= 1e-4
+    assert np.abs(std1.reshape(Z1.shape)[::stride, ::stride] - g[f"{tag}_std"]).max() <= 1e-6
 
 
 # ---------------------------------------------------------------------------------------------------
