@@ -137,15 +137,16 @@ MULTI_COMMON = dict(d_waypoint_distance=2.5, budget_iter=2, n_samples=60, s_stag
                     stage_lambda=0.5)
 
 
-def run_multi(g, tag, obstacles, make_scenario, make_strategy):
+def run_multi(g, tag, obstacles, make_scenario, make_strategy, common=None):
     """Shared by the CPU (doubles) and the device test: one MR_IPP run at the golden's seed and agent count, compared
     bit for bit with the reference's waypoints, measurements, per-agent paths, source estimates and RNG position."""
+    common = MULTI_COMMON if common is None else common
     seed, agents, budget = int(g[f"{tag}_seed"]), int(g[f"{tag}_num_agents"]), int(g[f"{tag}_budget"])
     W = int(g[f"{tag}_W"]) if f"{tag}_W" in g else 40
     sc = make_scenario(num_sources=len(g[f"{tag}_sources"]), workspace_size=(0, W, 0, W), obstacles=obstacles, seed=seed)
     assert np.array_equal(np.array(sc.sources), g[f"{tag}_sources"])
     np.random.seed(2000 + seed)
-    st = make_strategy(sc, num_agents=agents, budget=budget, **MULTI_COMMON)
+    st = make_strategy(sc, num_agents=agents, budget=budget, **common)
     # agents start spread along the bottom edge (rrt.py:555-558)
     assert len(st.agent_positions) == agents
     Z, std = st.run()
@@ -178,6 +179,24 @@ def test_c3_shaped_runs_identical_host_logic(gold, tag, cls):
     g = gold("runs_golden_c3_r2.npz")
     run_multi(g, tag, [], lambda **kw: PointSourceField(gp_factory=DrawsOnlyGP, ground_truth_mode="host", **kw),
               lambda sc, **kw: getattr(R, cls)(sc, scorer=OracleScorer(), **kw))
+
+
+C2_RUNS = [("naive_c2", "RRT_Random_GP_PathPlanning"), ("bias_c2", "RRTRIG_PointSourceInformative_Distance_SourceMetric_PathPlanning")]
+
+
+def c2_common(g, tag):
+    return dict(d_waypoint_distance=1.0, n_samples=60, s_stages=4, max_sources=2, lambda_b=1, beta_t=5.0,
+                budget_iter=int(g[f"{tag}_budget_iter"]), stage_lambda=float(g[f"{tag}_stage_lambda"]))
+
+
+@pytest.mark.parametrize("tag,cls", C2_RUNS, ids=[c[0] for c in C2_RUNS])
+def test_c2_shaped_runs_identical_host_logic(gold, tag, cls):
+    """configs[1]'s shape as whole runs -- one robot on the 20 x 20 workspace (200 x 200 lattice), a few hundred
+    measurements at d_waypoint_distance 1.0, the naive random-leaf RRT (budget_iter 5) and the distance-biased
+    source-metric strategy (budget_iter 10) -- against the unmodified reference (oracle/make_golden_r2.py --only c2runs)."""
+    g = gold("runs_golden_c2_r2.npz")
+    run_multi(g, tag, [], lambda **kw: PointSourceField(gp_factory=DrawsOnlyGP, ground_truth_mode="host", **kw),
+              lambda sc, **kw: getattr(R, cls)(sc, scorer=OracleScorer(), **kw), common=c2_common(g, tag))
 
 
 @pytest.mark.parametrize("tag,obstacles", MULTI, ids=[m[0] for m in MULTI])

@@ -11,7 +11,7 @@ import pytest
 
 from oracle import gp_oracle as O
 from tests.test_gpu_parity import GRAD_RTOL, _lml_tol, _mean_tol, _var_tol
-from tests.test_r2_cpu import MULTI, _ucb_strategy, run_multi
+from tests.test_r2_cpu import MULTI, _ucb_strategy, c2_common, run_multi
 
 pytestmark = pytest.mark.gpu
 
@@ -160,7 +160,9 @@ def test_multi_agent_runs_identical_on_device(gold, tag, obstacles):
 
 
 SHAPED_RUNS = [("runs_golden_c4_r2.npz", "mripp_8a_c4", "MR_IPP", 20), ("runs_golden_c3_r2.npz", "biasbeta_3a_c3",
-               "RRT_BiasBetaInformative_GP_PathPlanning", 10), ("runs_golden_c3_r2.npz", "mripp_3a_c3", "MR_IPP", 10)]
+               "RRT_BiasBetaInformative_GP_PathPlanning", 10), ("runs_golden_c3_r2.npz", "mripp_3a_c3", "MR_IPP", 10),
+               ("runs_golden_c2_r2.npz", "naive_c2", "RRT_Random_GP_PathPlanning", 4),
+               ("runs_golden_c2_r2.npz", "bias_c2", "RRTRIG_PointSourceInformative_Distance_SourceMetric_PathPlanning", 4)]
 
 
 @pytest.mark.skipif(__import__("os").environ.get("IPP_RUN_SHAPED_DEVICE_RUNS") != "1",
@@ -168,8 +170,9 @@ SHAPED_RUNS = [("runs_golden_c4_r2.npz", "mripp_8a_c4", "MR_IPP", 20), ("runs_go
                            "IPP_RUN_SHAPED_DEVICE_RUNS=1 (the host logic of the same runs is checked on CPU in test_r2_cpu.py)")
 @pytest.mark.parametrize("fname,tag,cls,stride", SHAPED_RUNS, ids=[r[1] for r in SHAPED_RUNS])
 def test_config_shaped_runs_identical_on_device(gold, fname, tag, cls, stride):
-    """configs[2] / configs[3] shapes as whole runs on the device (3 agents on 50 x 50 with the Bias-Beta class and
-    MR_IPP; 8 agents on 100 x 100): T3 decisions bit-identical, T1 field at the reference's theta."""
+    """configs[1] / configs[2] / configs[3] shapes as whole runs on the device (one robot on 20 x 20 with a few hundred
+    measurements; 3 agents on 50 x 50 with the Bias-Beta class and MR_IPP; 8 agents on 100 x 100): T3 decisions
+    bit-identical, T1 field at the reference's theta."""
     from mripp_b200.src.point_source.point_source import PointSourceField
     from mripp_b200.src.rrt import rrt as R
 
@@ -182,7 +185,8 @@ def test_config_shaped_runs_identical_on_device(gold, fname, tag, cls, stride):
 
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        sc, st, Z, std = run_multi(g, tag, [], scenario, lambda s, **kw: getattr(R, cls)(s, **kw))
+        sc, st, Z, std = run_multi(g, tag, [], scenario, lambda s, **kw: getattr(R, cls)(s, **kw),
+                                   common=c2_common(g, tag) if tag.endswith("_c2") else None)
         side = 10 * int(g[f"{tag}_W"])
         assert Z.shape == (side, side) and std.shape == (side * side,)
         th = g[f"{tag}_theta"]
