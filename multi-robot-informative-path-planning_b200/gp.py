@@ -390,6 +390,21 @@ class _Workspace:
         return buf[:numel]
 
 
+def point_table_rows(m, NP, free_bytes, have_numel=0, sms=148):
+    """Queries per chunk of the tabled explicit-point posterior (a multiple of 128): everything at once when the table
+    fits a quarter of the free device memory (at most 4 GiB) or the scratch already held, else whole waves of 128-query
+    tiles (one tile per SM), else whatever fits -- never less than one tile.  The scratch of `rows` queries is
+    rows * NP + NP + 4 * (rows // 128) doubles (include/ipp_b200.h)."""
+    rows_all = (int(m) + 127) // 128 * 128
+    have_rows = max(0, (int(have_numel) - NP) // (NP + 1) // 128 * 128)
+    budget = min(4 << 30, int(free_bytes) // 4)
+    fit = max(int(budget // (8 * NP)), have_rows)
+    if rows_all <= fit:
+        return max(128, rows_all)
+    wave = 128 * int(sms)
+    return max(128, fit // wave * wave if fit >= wave else fit // 128 * 128)
+
+
 class GaussianProcessRegressor:
     """Drop-in for sklearn.gaussian_process.GaussianProcessRegressor on the reference's call sites."""
 
@@ -907,19 +922,11 @@ class GaussianProcessRegressor:
         return buf
 
     def _point_table_rows(self, m):
-        """Queries per chunk of the tabled explicit-point posterior: everything at once when the table fits a quarter of
-        the free device memory (at most 4 GiB), else whole waves of 128-query tiles (one tile per SM)."""
+        """Queries per chunk of the tabled explicit-point posterior (point_table_rows) for this device's free memory."""
         torch = _lib.require_cuda()
-        NP = self._ws.layout[0]
-        rows_all = (int(m) + 127) // 128 * 128
         have = getattr(self._ws, "tables", None)
-        have_rows = 0 if have is None else (have.numel() - NP) // (NP + 1) // 128 * 128
-        budget = min(4 << 30, torch.cuda.mem_get_info()[0] // 4)
-        fit = max(int(budget // (8 * NP)), have_rows)
-        if rows_all <= fit:
-            return rows_all
-        wave = 128 * torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
-        return max(128, fit // wave * wave if fit >= wave else fit // 128 * 128)
+        return point_table_rows(m, self._ws.layout[0], torch.cuda.mem_get_info()[0], 0 if have is None else have.numel(),
+                                torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count)
 
     @staticmethod
     def _morton_order_device(Qd):

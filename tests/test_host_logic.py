@@ -468,3 +468,51 @@ def test_rewire_log_behaves_like_the_list_of_tuples():
     for x, y in zip(a.history_csr(), b.history_csr()):
         assert x.dtype == y.dtype == np.int32 and np.array_equal(x, y)
     assert [p.tolist() for p in a.chain_at(41)] == [p.tolist() for p in b.chain_at(41)]
+
+
+def test_point_table_chunking_policy(monkeypatch):
+    """Chunk size of the tabled explicit-point posterior: a multiple of 128, never below one tile, the whole set when it
+    fits, whole waves of one tile per SM when it does not, and a scratch that is already held is always reused."""
+    import types
+    import torch
+    from mripp_b200 import _lib
+    from mripp_b200 import gp as G
+
+    NP = 5056
+    for m in (1, 127, 128, 129, 256, 37888, 10 ** 6):
+        for free in (0, 1 << 20, 1 << 30, 40 << 30, 170 << 30):
+            for have in (0, 130 * NP, 20000 * NP + NP + 4 * 200):
+                rows = G.point_table_rows(m, NP, free, have)
+                assert rows >= 128 and rows % 128 == 0
+                scratch = rows * NP + NP + 4 * (rows // 128)
+                assert rows <= max(128, (m + 127) // 128 * 128)
+                if rows > 128:   # beyond the one-tile floor the scratch respects the budget or the buffer already held
+                    assert 8 * rows * NP <= max(min(4 << 30, free // 4), 8 * have) and (scratch <= have or 8 * rows * NP <= free // 4)
+                if rows < (m + 127) // 128 * 128 and rows >= 128 * 148:
+                    assert rows % (128 * 148) == 0
+    assert G.point_table_rows(37888, NP, 170 << 30) == 37888
+    assert G.point_table_rows(10 ** 6, NP, 170 << 30) == 5 * 148 * 128
+    assert G.point_table_rows(10 ** 6, NP, 170 << 30, sms=132) == (4 << 30) // (8 * NP) // (132 * 128) * 132 * 128
+    # the method asks the device for the two numbers and nothing else
+    monkeypatch.setattr(_lib, "require_cuda", lambda: torch)
+    monkeypatch.setattr(torch.cuda, "mem_get_info", lambda *a: (8 << 30, 180 << 30))
+    monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
+    monkeypatch.setattr(torch.cuda, "get_device_properties", lambda d: types.SimpleNamespace(multi_processor_count=148))
+    gp = G.GaussianProcessRegressor.__new__(G.GaussianProcessRegressor)
+    gp._ws = types.SimpleNamespace(layout=(NP,), tables=None)
+    assert gp._point_table_rows(10 ** 6) == G.point_table_rows(10 ** 6, NP, 8 << 30, 0, 148) == 2 * 148 * 128
+    gp._ws.tables = torch.empty(300 * NP)
+    assert gp._point_table_rows(200) == 256
+
+
+def test_device_morton_order_equals_the_host_order():
+    """The Z-order permutation of explicit query points computed with tensor ops (predict_points_device) is the host's
+    morton_order -- same 16-bit keys, same stable sort -- including duplicate points and a degenerate axis."""
+    import torch
+    from mripp_b200 import gp as G
+
+    rng = np.random.RandomState(6)
+    for Q in (rng.uniform(-3, 47, (5000, 2)), np.repeat(rng.uniform(0, 10, (40, 2)), 7, axis=0),
+              np.column_stack([rng.uniform(0, 1, 300), np.full(300, 2.5)]), np.zeros((5, 2))):
+        got = G.GaussianProcessRegressor._morton_order_device(torch.from_numpy(Q)).numpy()
+        assert np.array_equal(got, G.morton_order(Q))
