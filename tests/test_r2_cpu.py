@@ -199,6 +199,36 @@ def test_c2_shaped_runs_identical_host_logic(gold, tag, cls):
               lambda sc, **kw: getattr(R, cls)(sc, scorer=OracleScorer(), **kw), common=c2_common(g, tag))
 
 
+ALL_CLASSES_OBSTACLE = [{"type": "rectangle", "x": 20, "y": 18, "width": 8, "height": 6}]
+ALL_CLASSES = [("rig_nopen", "RRTRIG_PointSourceInformative_SourceMetric_PathPlanning"),
+               ("rig_dist", "RRTRIG_PointSourceInformative_Distance_SourceMetric_PathPlanning"),
+               ("rig_rot", "RRTRIG_PointSourceInformative_DistanceRotation_SourceMetric_PathPlanning"),
+               ("rig_all", "RRTRIG_PointSourceInformative_All_SourceMetric_PathPlanning"),
+               ("biasbeta", "RRT_BiasBetaInformative_GP_PathPlanning"), ("rrt_random", "RRT_Random_GP_PathPlanning"),
+               ("rrtstar_random", "RRTStar_Random_GP_PathPlanning")]
+
+
+def classes_common(g, tag):
+    return dict(d_waypoint_distance=2.5, budget_iter=2, n_samples=60, s_stages=4, max_sources=2, lambda_b=1, beta_t=5.0,
+                stage_lambda=float(g[f"{tag}_stage_lambda"]))
+
+
+@pytest.mark.parametrize("name,cls", ALL_CLASSES, ids=[c[0] for c in ALL_CLASSES])
+def test_every_strategy_class_three_agents_with_obstacle_host_logic(gold, name, cls):
+    """Every strategy class with three agents on the 50 x 50 workspace around a rectangle obstacle (round 1 pinned them
+    with one agent, 20 x 20, no obstacle) against the unmodified reference (oracle/make_golden_r2.py --only classes)."""
+    g, tag = gold("runs_golden_classes_r2.npz"), f"{name}_3a_obst"
+    if f"{tag}_reference_error" in g:
+        # rig_nopen with several agents: the reference's gain function reads agents_full_path[i][-1] of an agent that has
+        # not moved yet once another agent's measurements produced estimates (rrt.py:57) and dies with an IndexError
+        pytest.skip(f"the reference itself raises here: {g[f'{tag}_reference_error']}")
+    if f"{tag}_seed" not in g:
+        pytest.skip(f"the reference's rrt module has no class {cls}")
+    run_multi(g, tag, ALL_CLASSES_OBSTACLE,
+              lambda **kw: PointSourceField(gp_factory=DrawsOnlyGP, ground_truth_mode="host", **kw),
+              lambda sc, **kw: getattr(R, cls)(sc, scorer=OracleScorer(), **kw), common=classes_common(g, tag))
+
+
 @pytest.mark.parametrize("tag,obstacles", MULTI, ids=[m[0] for m in MULTI])
 def test_multi_agent_runs_identical_host_logic(gold, tag, obstacles):
     """configs[2] / configs[3] agent counts (3 and 8) and an obstacle run: the N > 1 start rule (rrt.py:555-558), the

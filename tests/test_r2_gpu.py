@@ -11,7 +11,7 @@ import pytest
 
 from oracle import gp_oracle as O
 from tests.test_gpu_parity import GRAD_RTOL, _lml_tol, _mean_tol, _var_tol
-from tests.test_r2_cpu import MULTI, _ucb_strategy, c2_common, run_multi
+from tests.test_r2_cpu import ALL_CLASSES, ALL_CLASSES_OBSTACLE, MULTI, _ucb_strategy, c2_common, classes_common, run_multi
 
 pytestmark = pytest.mark.gpu
 
@@ -163,6 +163,8 @@ SHAPED_RUNS = [("runs_golden_c4_r2.npz", "mripp_8a_c4", "MR_IPP", 20), ("runs_go
                "RRT_BiasBetaInformative_GP_PathPlanning", 10), ("runs_golden_c3_r2.npz", "mripp_3a_c3", "MR_IPP", 10),
                ("runs_golden_c2_r2.npz", "naive_c2", "RRT_Random_GP_PathPlanning", 4),
                ("runs_golden_c2_r2.npz", "bias_c2", "RRTRIG_PointSourceInformative_Distance_SourceMetric_PathPlanning", 4)]
+SHAPED_RUNS += [("runs_golden_classes_r2.npz", f"{name}_3a_obst", cls, 10) for name, cls in ALL_CLASSES
+                if name not in ("rig_nopen", "rig_all")]   # the reference raises / has no such class (test_r2_cpu.py)
 
 
 @pytest.mark.skipif(__import__("os").environ.get("IPP_RUN_SHAPED_DEVICE_RUNS") != "1",
@@ -185,8 +187,9 @@ def test_config_shaped_runs_identical_on_device(gold, fname, tag, cls, stride):
 
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        sc, st, Z, std = run_multi(g, tag, [], scenario, lambda s, **kw: getattr(R, cls)(s, **kw),
-                                   common=c2_common(g, tag) if tag.endswith("_c2") else None)
+        common = c2_common(g, tag) if tag.endswith("_c2") else classes_common(g, tag) if tag.endswith("_obst") else None
+        sc, st, Z, std = run_multi(g, tag, ALL_CLASSES_OBSTACLE if tag.endswith("_obst") else [], scenario,
+                                   lambda s, **kw: getattr(R, cls)(s, **kw), common=common)
         side = 10 * int(g[f"{tag}_W"])
         assert Z.shape == (side, side) and std.shape == (side * side,)
         th = g[f"{tag}_theta"]
