@@ -188,3 +188,42 @@ def test_rounds_sharded_over_two_ranks_equal_one_process(monkeypatch):
         assert p.exitcode == 0
     for rank, res in out:
         assert res == single
+
+
+def _worker8(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        optima = {k: D.sharded_restarts(lambda idx: [(np.array([i, 2.0 * i]), float((i * 7) % 5)) for i in idx], k, 2)
+                  for k in (5, 11, 16)}
+        scores = np.arange(8192, dtype=float) % 97
+        lo, hi = D.slab_bounds(len(scores), world, rank)
+        best = D.sharded_argmax(torch.from_numpy(scores[lo:hi]), lo)
+
+        def slab(a, b):
+            return torch.arange(a, b, dtype=torch.float64), -torch.arange(a, b, dtype=torch.float64)
+
+        z, s = D.sharded_grid_posterior(None, (0, 100, 0, 100), 1000, 1000, compute_slab=slab)
+        q.put((rank, optima, best, float(z.sum()), float(s.sum()), z.shape, bool(np.array_equal(z, np.arange(10 ** 6)))))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_eight_ranks_restarts_argmax_and_lattice_gather():
+    """The rank count of the scaling run: 11 restarts (the stock fit), fewer restarts than ranks (5) and more (16) over
+    8 ranks; the first-maximum argmax of 8192 scores; the gather of a 10^6-point lattice from 8 row slabs."""
+    world, port = 8, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker8, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, optima, best, zs, ss, shape, exact in out:
+        for k, opt in optima.items():
+            assert len(opt) == k
+            assert all(np.array_equal(o[0], [i, 2.0 * i]) and o[1] == float((i * 7) % 5) for i, o in enumerate(opt))
+        assert best == 96 and shape == (10 ** 6,) and exact and ss == -zs
