@@ -123,3 +123,51 @@ def test_native_tree_growth_equals_python_primitives(seed, mode, step, radius, b
                     list(t.rewires), np.random.uniform(size=2)))
     a, b = out
     assert all(np.array_equal(x, y) for x, y in zip(a[:5], b[:5])) and a[5] == b[5] and np.array_equal(a[6], b[6])
+
+
+@SET
+@given(seed=st.integers(0, 2**31 - 1), n_obs=st.integers(1, 80), M=st.integers(1, 3), distinct=st.integers(1, 12),
+       N=st.integers(2, 90))
+def test_distinct_rows_likelihood_is_the_full_evaluation(seed, n_obs, M, distinct, N):
+    """distinct_rows_log_likelihood (what a re-decided sampler stage evaluates) returns the bits of the full
+    batched_poisson_log_likelihood for any cloud of repeated particles."""
+    rng = np.random.RandomState(seed)
+    obs = rng.uniform(0, 40, (n_obs, 2))
+    vals = rng.poisson(10.0 ** rng.uniform(0, 4, n_obs)).astype(float)
+    rows = np.column_stack([rng.uniform(0, 40, (distinct, 2)), rng.uniform(1e5, 1e6, distinct)] * M)
+    parts = rows[rng.randint(0, distinct, N)]
+    assert np.array_equal(E.distinct_rows_log_likelihood(parts, obs, vals, 1.0, M),
+                          E.batched_poisson_log_likelihood(parts, obs, vals, 1.0, M))
+
+
+@SET
+@given(seed=st.integers(0, 2**31 - 1), n=st.integers(0, 60), cuts=st.integers(0, 6))
+def test_rewire_log_is_the_list_it_replaces(seed, n, cuts):
+    """Any interleaving of Python appends and native blocks gives the list of tuples, in order."""
+    from mripp_b200.src.rrt.rrt_utils import RewireLog
+
+    rng = np.random.RandomState(seed)
+    ev = [(int(a), int(b), int(a)) for a, b in zip(np.sort(rng.randint(1, 500, n)), rng.randint(0, 400, n))]
+    edges = sorted(set([0, n] + rng.randint(0, n + 1, cuts).tolist()))
+    log = RewireLog()
+    for k, (a, b) in enumerate(zip(edges[:-1], edges[1:])):
+        if k % 2:
+            log.extend_array(np.array(ev[a:b], dtype=np.int64).reshape(-1, 3))
+        else:
+            for e in ev[a:b]:
+                log.append(e)
+    assert len(log) == n and list(log) == ev and log == ev and bool(log) == (n > 0)
+    assert np.array_equal(log.as_array(), np.array(ev, dtype=np.int64).reshape(-1, 3))
+
+
+@SET
+@given(m=st.integers(1, 3 * 10 ** 6), NP=st.sampled_from([64, 512, 2048, 5056, 16384]), free=st.integers(0, 180 << 30),
+       have=st.integers(0, 1 << 29), sms=st.sampled_from([108, 132, 148]))
+def test_point_table_rows_fit_their_budget(m, NP, free, have, sms):
+    from mripp_b200 import gp as G
+
+    rows = G.point_table_rows(m, NP, free, have, sms)
+    assert rows >= 128 and rows % 128 == 0 and rows <= max(128, (m + 127) // 128 * 128)
+    if rows > 128:
+        scratch = rows * NP + NP + 4 * (rows // 128)
+        assert 8 * rows * NP <= min(4 << 30, free // 4) or scratch <= have
