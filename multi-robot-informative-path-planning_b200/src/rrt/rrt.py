@@ -138,9 +138,22 @@ def _sample(self) -> np.ndarray:
 
 
 # ---- tree generation (rrt.py:263-327) ---------------------------------------------------------------
+def _no_penalties_gain_error(self, agent_idx: int, gain_function: Optional[Callable]) -> None:
+    """The reference's error, kept where it occurs: point_source_gain_no_penalties measures the estimates from
+    agents_full_path[agent_idx][-1] (rrt.py:57); an agent that has not moved yet has no such point once another agent's
+    measurements produced estimates, and the first node its generator inserts -- one sample into the loop
+    (rrt.py:266,274 / :310,321) -- dies with this IndexError."""
+    if (getattr(gain_function, "variant", None) == VARIANT_NO_PENALTIES and not self.agents_full_path[agent_idx]
+            and np.size(getattr(self, "best_estimates", ())) > 0):
+        _sample(self)
+        raise IndexError("list index out of range")
+
+
 def rrt_tree_generation(self, budget_portion: float, agent_idx: int) -> None:
     tree = self.trees_soa[agent_idx]
     travelled = 0
+    if travelled < budget_portion:
+        _no_penalties_gain_error(self, agent_idx, point_source_gain_no_penalties)
     samples = tree.grow_native(0, self.scenario.workspace_size, self.d_waypoint_distance, 0.0, budget_portion)
     if samples is not None:             # grown natively (csrc/ipp_tree_host.cu): same nodes, same RNG position
         travelled = budget_portion
@@ -186,6 +199,8 @@ def rrt_star_tree_generation(self, budget_portion: float, agent_idx: int) -> Non
 def rig_tree_generation(self, budget_portion: float, agent_idx: int, gain_function: Callable) -> None:
     tree = self.trees_soa[agent_idx]
     travelled = 0
+    if travelled < budget_portion:
+        _no_penalties_gain_error(self, agent_idx, gain_function)
     samples = tree.grow_native(2, self.scenario.workspace_size, self.d_waypoint_distance, self.d_waypoint_distance,
                                budget_portion)
     if samples is not None:

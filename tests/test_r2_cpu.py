@@ -220,8 +220,18 @@ def test_every_strategy_class_three_agents_with_obstacle_host_logic(gold, name, 
     g, tag = gold("runs_golden_classes_r2.npz"), f"{name}_3a_obst"
     if f"{tag}_reference_error" in g:
         # rig_nopen with several agents: the reference's gain function reads agents_full_path[i][-1] of an agent that has
-        # not moved yet once another agent's measurements produced estimates (rrt.py:57) and dies with an IndexError
-        pytest.skip(f"the reference itself raises here: {g[f'{tag}_reference_error']}")
+        # not moved yet once another agent's measurements produced estimates (rrt.py:57) and dies with an IndexError --
+        # and so does the mirror, at the same point of the run (same RNG position)
+        assert "IndexError" in str(g[f"{tag}_reference_error"])
+        sc = PointSourceField(num_sources=3, workspace_size=(0, 50, 0, 50), obstacles=ALL_CLASSES_OBSTACLE,
+                              seed=int(g[f"{tag}_error_seed"]), gp_factory=DrawsOnlyGP, ground_truth_mode="host")
+        np.random.seed(2000 + int(g[f"{tag}_error_seed"]))
+        st = getattr(R, cls)(sc, scorer=OracleScorer(), num_agents=3, budget=60,
+                             **dict(classes_common({f"{tag}_stage_lambda": g[f"{tag}_error_stage_lambda"]}, tag)))
+        with pytest.raises(IndexError):
+            st.run()
+        assert np.array_equal(np.random.uniform(size=3), g[f"{tag}_error_rng_after"])
+        return
     if f"{tag}_seed" not in g:
         pytest.skip(f"the reference's rrt module has no class {cls}")
     run_multi(g, tag, ALL_CLASSES_OBSTACLE,
