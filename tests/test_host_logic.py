@@ -140,6 +140,27 @@ def test_boustrophedon_paths(gold, tag, cls, kw):
     assert np.array_equal(np.random.uniform(size=3), g[f"{tag}_rng_after"])
 
 
+@pytest.mark.parametrize("tag,cls,kw", [("boust_c1", Boustrophedon, {}), ("mr_boust_8a_c4", MR_Boustrophedon, dict(num_agents=8))])
+def test_boustrophedon_at_the_config_shapes(gold, tag, cls, kw):
+    """The lawnmower baselines at the shapes of configs[0] (one robot, 40 x 40, the constructor's defaults: 131
+    measurements) and configs[3] (8 robots, 100 x 100) against the unmodified reference (make_golden_r2.py --only boust)."""
+    from tests.test_r2_cpu import DrawsOnlyGP
+
+    g = gold("runs_golden_boust_r2.npz")
+    W = int(g[f"{tag}_W"])
+    sc = PointSourceField(num_sources=len(g[f"{tag}_sources"]), workspace_size=(0, W, 0, W), seed=int(g[f"{tag}_seed"]),
+                          gp_factory=DrawsOnlyGP)
+    assert np.array_equal(np.array(sc.sources), g[f"{tag}_sources"])
+    np.random.seed(2000 + int(g[f"{tag}_seed"]))
+    st = cls(sc, **kw)
+    st.run()
+    assert np.array_equal(np.asarray(st.obs_wp, float), g[f"{tag}_obs_wp"])
+    assert np.array_equal(np.asarray(st.full_path, float), g[f"{tag}_full_path"])
+    if g[f"{tag}_meas"].size:   # (the reference's MR_Boustrophedon keeps no `measurements` attribute)
+        assert np.array_equal(np.asarray(st.measurements, float), g[f"{tag}_meas"])
+    assert np.array_equal(np.random.uniform(size=3), g[f"{tag}_rng_after"])
+
+
 @pytest.mark.parametrize("tag", ["free", "obst"])
 def test_field_physics_bit_exact(gold, tag):
     g = gold("field_golden.npz")

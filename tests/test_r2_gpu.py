@@ -200,6 +200,36 @@ def test_config_shaped_runs_identical_on_device(gold, fname, tag, cls, stride):
     assert np.abs(std1.reshape(Z1.shape)[::stride, ::stride] - g[f"{tag}_std"]).max() <= 1e-6
 
 
+@pytest.mark.skipif(__import__("os").environ.get("IPP_RUN_SHAPED_DEVICE_RUNS") != "1",
+                    reason="added after the round's GPU minutes were spent: never run on hardware; opt in with "
+                           "IPP_RUN_SHAPED_DEVICE_RUNS=1 (the host logic of the same runs is checked on CPU in test_host_logic.py)")
+@pytest.mark.parametrize("tag,cls_name,kw,stride", [("boust_c1", "Boustrophedon", {}, 4),
+                                                    ("mr_boust_8a_c4", "MR_Boustrophedon", dict(num_agents=8), 20)])
+def test_boustrophedon_config_shapes_on_device(gold, tag, cls_name, kw, stride):
+    """The lawnmower baselines at the shapes of configs[0] / configs[3]: waypoints and RNG position identical, field at
+    the reference's theta within T1."""
+    from mripp_b200.src.boustrophedon import boustrophedon as B
+    from mripp_b200.src.point_source.point_source import PointSourceField
+
+    g = gold("runs_golden_boust_r2.npz")
+    W = int(g[f"{tag}_W"])
+    sc = PointSourceField(num_sources=len(g[f"{tag}_sources"]), workspace_size=(0, W, 0, W), seed=int(g[f"{tag}_seed"]))
+    np.random.seed(2000 + int(g[f"{tag}_seed"]))
+    st = getattr(B, cls_name)(sc, **kw)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        st.run()
+        assert np.array_equal(np.asarray(st.obs_wp, float), g[f"{tag}_obs_wp"])
+        assert np.array_equal(np.asarray(st.full_path, float), g[f"{tag}_full_path"])
+        assert np.array_equal(np.random.uniform(size=3), g[f"{tag}_rng_after"])
+        th = g[f"{tag}_theta"]
+        sc.gp.kernel = type(sc.gp.kernel)(float(np.exp(th[0])), float(np.exp(th[1])))
+        sc.gp.optimizer = None
+        Z1, std1 = sc.predict_spatial_field(st.obs_wp, np.asarray(st.measurements, float))
+    assert np.abs(np.log10(Z1[::stride, ::stride]) - np.log10(g[f"{tag}_Z"])).max() <= 1e-4
+    assert np.abs(std1.reshape(Z1.shape)[::stride, ::stride] - g[f"{tag}_std"]).max() <= 1e-6
+
+
 # ---------------------------------------------------------------------------------------------------
 # Concurrency contract (include/ipp_b200.h: re-entrant, one stream per calling thread).  The reference calls
 # gp.kernel(...) and the selectors from num_agents threads outside its lock (rrt.py:659-664, 703-711).
