@@ -226,6 +226,30 @@ def test_source_estimator_exact_under_likelihood_error(gold, scale):
     assert stages == 10 and (redone == 0 if scale == 1.0 else True) and (redone > 0 if scale == 1e7 else True)
 
 
+@pytest.mark.parametrize("backend", ["exact", "device-like", "wide-bands"])
+def test_source_estimator_at_the_stock_config_size(gold, backend):
+    """estimate_sources_bayesian with the particle / stage counts of the reference's shipped example config (1000
+    particles, 25 stages, M = 1..3) on its scenario, against the unmodified reference (make_golden_r2.py --only estimator):
+    estimate, model order, BIC and RNG position bit-identical -- with the reference's own likelihoods, with a backend as
+    wrong as a device is allowed to be, and with bands so wide that stages are re-decided on their distinct particles."""
+    from tests._doubles import NoisyLikelihoodScorer
+    g = gold("estimator_golden_r2.npz")
+    sc = PointSourceField(num_sources=2, workspace_size=(0, 40, 0, 40), seed=95789, gp_factory=FastGP)
+    sc.update_source(0, 5, 35, 1000000)
+    sc.update_source(1, 35, 35, 1000000)
+    assert np.array_equal(np.array(sc.sources), g["sources"])
+    scorer = OracleScorer() if backend == "exact" else NoisyLikelihoodScorer(1.0 if backend == "device-like" else 1e3, seed=5)
+    before = dict(E.STATS)
+    np.random.seed(17)
+    est, M, bic = E.estimate_sources_bayesian(list(g["wp"]), list(g["meas"]), 1, 3, 1000, 25, sc, scorer=scorer)
+    assert M == int(g["M"]) and bic == float(g["bic"]) and np.array_equal(np.asarray(est, float), g["est"])
+    assert np.array_equal(np.random.uniform(size=3), g["rng_after"])
+    redone = E.STATS["redecided"] - before["redecided"]
+    assert E.STATS["stages"] - before["stages"] == 75
+    if backend == "wide-bands":
+        assert redone > 0 and E.STATS["distinct_rows"] - before["distinct_rows"] < E.STATS["rows"] - before["rows"]
+
+
 def test_draws_inside_band():
     cdf = np.array([0.0, 0.25, 0.25, 0.7, 1.0])
     u = np.array([0.1, 0.5, 0.9])
