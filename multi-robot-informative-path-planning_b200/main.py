@@ -128,7 +128,7 @@ def run_simulations(scenarios, makers, args: Dict, debug: bool = False, shard=No
                 src_all[key][name]["n_sources"].append(len(est))
                 results.append({"scenario": s_idx, "round": round_number, "strategy": name, "rmse": float(rmse),
                                 "wrmse": float(wrmse), "entropy": float(entropy), "time": getattr(strategy, "time_taken", None),
-                                "n_obs": int(len(strategy.obs_wp)), "source_errors": calculate_source_errors(scenario.sources, est)})
+                                "n_obs": int(len(strategy.obs_wp)), "source_errors": {k: [float(v) for v in vals] for k, vals in calculate_source_errors(scenario.sources, est).items()}})
                 print(f"Round {round_number}/{args['rounds']} scenario {s_idx} {name}: RMSE {rmse:.4f} WRMSE {wrmse:.4f} "
                       f"time {getattr(strategy, 'time_taken', None)}")
     if args.get("save", False) and (shard is None or shard[1] == 1):  # sharded: the gathered JSON (--out) is the record

@@ -14,22 +14,14 @@ def run_number_from_folder() -> str:
 
 
 def calculate_source_errors(actual_sources, estimated_locs):
-    """Per-coordinate RMSE between true and estimated sources, nearest-first pairing."""
-    actual = np.asarray(actual_sources, dtype=float).reshape(-1, 3)
-    est = np.asarray(estimated_locs, dtype=float).reshape(-1, 3)
-    if est.size == 0 or actual.size == 0:
-        return {"x_error": None, "y_error": None, "intensity_error": None}
-    k = min(len(actual), len(est))
-    d = np.linalg.norm(actual[:, None, :2] - est[None, :, :2], axis=-1)
-    pairs, used = [], set()
-    for i in np.argsort(d.min(axis=1))[:k]:
-        j = next(j for j in np.argsort(d[i]) if j not in used)
-        used.add(j)
-        pairs.append((i, j))
-    a = actual[[p[0] for p in pairs]]
-    e = est[[p[1] for p in pairs]]
-    rm = lambda c: float(np.sqrt(np.mean((a[:, c] - e[:, c]) ** 2)))
-    return {"x_error": rm(0), "y_error": rm(1), "intensity_error": rm(2)}
+    """path_planning_utils.py:125-141: absolute x / y / intensity errors of the estimates paired with the true sources in
+    the order given (zip: the shorter list decides), as three lists."""
+    errors = {"x_error": [], "y_error": [], "intensity_error": []}
+    for actual, estimated in zip(actual_sources, estimated_locs):
+        errors["x_error"].append(abs(actual[0] - estimated[0]))
+        errors["y_error"].append(abs(actual[1] - estimated[1]))
+        errors["intensity_error"].append(abs(actual[2] - estimated[2]))
+    return errors
 
 
 def save_run_info(run_number, rmse, wrmse, entropy, sources, times, args, scenarios, folder="./runs_review"):

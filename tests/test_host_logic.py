@@ -561,3 +561,26 @@ def test_device_morton_order_equals_the_host_order():
               np.column_stack([rng.uniform(0, 1, 300), np.full(300, 2.5)]), np.zeros((5, 2))):
         got = G.GaussianProcessRegressor._morton_order_device(torch.from_numpy(Q)).numpy()
         assert np.array_equal(got, G.morton_order(Q))
+
+
+def test_reported_metrics_are_the_references(gold):
+    """What main.py reports per run -- RMSE and source-weighted RMSE of log10(Z + 1) (main.py:113-114), the differential
+    entropy of std (plot_helper.py:383-398, zeros replaced in place) and calculate_source_errors
+    (path_planning_utils.py:125-141) -- against the reference's own expressions and functions, bit for bit."""
+    from mripp_b200.src.utils.path_planning_utils import calculate_source_errors
+    from mripp_b200.src.visualization.plot_helper import calculate_differential_entropy
+
+    g = gold("metrics_golden_r2.npz")
+    sc = PointSourceField(num_sources=3, workspace_size=(0, 30, 0, 30), seed=int(g["seed"]), gp_factory=FastGP,
+                          ground_truth_mode="host")
+    assert np.array_equal(np.array(sc.sources), g["sources"])
+    Z_true, Z_pred = sc.ground_truth(), g["Z_pred"]
+    err = np.log10(Z_true + 1) - np.log10(Z_pred + 1)          # the host branch of mripp_b200.main
+    assert np.sqrt(np.mean(err ** 2)) == float(g["rmse"])
+    assert np.sqrt(np.sum(Z_true * err ** 2) / np.sum(Z_true)) == float(g["wrmse"])
+    std = g["std"].copy()
+    assert calculate_differential_entropy(std) == float(g["entropy"]) and not np.any(std == 0)
+    errs = calculate_source_errors(sc.sources, g["est"])
+    for k in ("x_error", "y_error", "intensity_error"):
+        assert np.array_equal(np.array(errs[k]), g[k])
+    assert calculate_source_errors(sc.sources, np.zeros((0, 3))) == {"x_error": [], "y_error": [], "intensity_error": []}
