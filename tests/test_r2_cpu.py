@@ -169,6 +169,14 @@ def test_c4_shaped_run_identical_host_logic(gold):
               lambda sc, **kw: R.MR_IPP(sc, scorer=OracleScorer(), **kw))
 
 
+def test_c5_shaped_round_identical_host_logic(gold):
+    """One round at configs[4]'s shape -- 10 sources on the 200 x 200 workspace (2000 x 2000 lattice), MR_IPP with two
+    agents -- against the unmodified reference (oracle/make_golden_r2.py --only c5run), bit for bit."""
+    g = gold("runs_golden_c5_r2.npz")
+    run_multi(g, "mripp_2a_c5", [], lambda **kw: PointSourceField(gp_factory=DrawsOnlyGP, ground_truth_mode="host", **kw),
+              lambda sc, **kw: R.MR_IPP(sc, scorer=OracleScorer(), **kw))
+
+
 C3_RUNS = [("biasbeta_3a_c3", "RRT_BiasBetaInformative_GP_PathPlanning"), ("mripp_3a_c3", "MR_IPP")]
 
 

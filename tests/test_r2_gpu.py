@@ -163,6 +163,7 @@ SHAPED_RUNS = [("runs_golden_c4_r2.npz", "mripp_8a_c4", "MR_IPP", 20), ("runs_go
                "RRT_BiasBetaInformative_GP_PathPlanning", 10), ("runs_golden_c3_r2.npz", "mripp_3a_c3", "MR_IPP", 10),
                ("runs_golden_c2_r2.npz", "naive_c2", "RRT_Random_GP_PathPlanning", 4),
                ("runs_golden_c2_r2.npz", "bias_c2", "RRTRIG_PointSourceInformative_Distance_SourceMetric_PathPlanning", 4)]
+SHAPED_RUNS += [("runs_golden_c5_r2.npz", "mripp_2a_c5", "MR_IPP", 40)]
 SHAPED_RUNS += [("runs_golden_classes_r2.npz", f"{name}_3a_obst", cls, 10) for name, cls in ALL_CLASSES
                 if name not in ("rig_nopen", "rig_all")]   # the reference raises / has no such class (test_r2_cpu.py)
 
