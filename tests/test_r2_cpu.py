@@ -131,6 +131,13 @@ def test_oracle_gp_large_cases_match_reference(gold, tag):
     assert np.abs(gm - g[f"{tag}_gmean"]).max() <= 1e-7 and np.abs(gs - g[f"{tag}_gstd"]).max() <= 1e-7
 
 
+def test_oracle_gp_c4_case_matches_reference(gold):
+    """configs[3]'s own size, n = 5000 on the 1000 x 1000 lattice: the oracle against the reference's sklearn run
+    (make_golden_r2.py --only gpC4; the reference's 11-restart fit alone takes ~25 min on 8 cores).  The device is
+    checked against the ORACLE at this size on hardware (tests/test_gpu_parity.py); this pins the oracle itself."""
+    test_oracle_gp_large_cases_match_reference(lambda _name: gold("gp_golden_c4_r2.npz"), "n5000")
+
+
 MULTI = [("mripp_3a", []), ("mripp_8a", []),
          ("mripp_2a_obst", [{"type": "rectangle", "x": 14, "y": 12, "width": 6, "height": 5}])]
 MULTI_COMMON = dict(d_waypoint_distance=2.5, budget_iter=2, n_samples=60, s_stages=4, max_sources=2, lambda_b=1, beta_t=5.0,

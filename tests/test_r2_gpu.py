@@ -128,6 +128,22 @@ def test_reoptimised_fit_large_vs_reference(G, gold, tag):
     assert np.abs(gp.kernel_.theta - th_ref).max() <= 5e-2  # same basin
 
 
+_OPT_IN_C4 = pytest.mark.skipif(__import__("os").environ.get("IPP_RUN_SHAPED_DEVICE_RUNS") != "1",
+                                reason="the n = 5000 reference golden was generated after the round's GPU minutes were spent: "
+                                       "never run on hardware; opt in with IPP_RUN_SHAPED_DEVICE_RUNS=1")
+
+
+@_OPT_IN_C4
+def test_gp_c4_case_vs_reference(G, gold):
+    """The same checks at configs[3]'s own size (n = 5000, 1000 x 1000 lattice) against the reference's sklearn run."""
+    test_gp_large_cases_vs_reference(G, lambda _name: gold("gp_golden_c4_r2.npz"), "n5000")
+
+
+@_OPT_IN_C4
+def test_reoptimised_fit_c4_vs_reference(G, gold):
+    test_reoptimised_fit_large_vs_reference(G, lambda _name: gold("gp_golden_c4_r2.npz"), "n5000")
+
+
 # ---------------------------------------------------------------------------------------------------
 # T3 at the agent counts of configs[2] / configs[3] and with an obstacle
 # ---------------------------------------------------------------------------------------------------
